@@ -1,0 +1,239 @@
+/* wenet_b200.h — C ABI of libwenet_b200.so: the B200 (sm_100a) Conformer ASR inference hot path
+ * (fbank -> ConformerEncoder -> CTC -> ctc_prefix_beam_search -> attention_rescoring) behind WeNet's
+ * Python API.  This is the drop-in boundary: plain C, raw device pointers, explicit sizes, a
+ * cudaStream_t, int return codes.  No torch types.
+ *
+ * Conventions (modelled on the reference's own C API, runtime/core/api/wenet_api.h:26-107:
+ * opaque handle, init/free, plain scalars, library-owned result strings):
+ *   - every function returns 0 (WB_OK) or a negative wb_status; wb_last_error() gives the message
+ *     (thread-local, owned by the library — same ownership rule as wenet_get_result,
+ *     wenet_api.h:73).  Nothing throws, nothing aborts.
+ *   - "dev" pointers are CUDA device pointers on the current device, "host" pointers are CPU.
+ *     The caller owns all inputs, outputs and workspaces (PyTorch allocates them so its caching
+ *     allocator / stream semantics hold); the library owns only the weights it was given
+ *     (wb_model_set_tensor copies) and its TMA descriptors.
+ *   - a wb_model is immutable after wb_model_finalize(): concurrent calls from several host
+ *     threads on different streams are safe as long as they use different workspaces (mirrors
+ *     TorchAsrModel::Copy sharing one module, runtime/core/decoder/torch_asr_model.cc:87-111).
+ *   - one model handle per GPU; cudaSetDevice is the caller's job.  No collectives: utterances
+ *     shard independently across GPUs.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     WB_ERR_CUDA.
+ *
+ * Each entry point cites the reference interface it replaces (file:line under the reference repo).
+ */
+#ifndef WENET_B200_H_
+#define WENET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* wb_stream_t; /* cudaStream_t */
+
+typedef enum {
+  WB_OK = 0,
+  WB_ERR_BAD_ARG = -1,
+  WB_ERR_UNSUPPORTED = -2, /* configuration outside the implemented set (no silent fallback) */
+  WB_ERR_CUDA = -3,
+  WB_ERR_NOT_LOADED = -4, /* a required weight tensor is missing */
+  WB_ERR_WORKSPACE = -5   /* caller workspace too small */
+} wb_status;
+
+const char* wb_last_error(void);
+const char* wb_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
+unsigned long long wb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * A. fbank  — replaces wenet/dataset/processor.py:226-256 compute_fbank, i.e.
+ *    torchaudio.compliance.kaldi.fbank(waveform*32768, num_mel_bins, 25 ms / 10 ms, dither 0,
+ *    energy_floor 0, povey window)  (torchaudio/compliance/kaldi.py:514-645)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct wb_fbank wb_fbank;
+/* window[frame_len] and mel[num_mel][nfft/2+1] are host arrays computed by the caller with the
+ * reference formulas (povey window kaldi.py:99-100, mel banks :436-511 incl. the zero last column
+ * :627); preemph = 0.97. */
+int wb_fbank_create(wb_fbank** out, int num_mel, int frame_len, int frame_shift, float preemph,
+                    const float* window_host, const float* mel_host);
+void wb_fbank_destroy(wb_fbank* fb);
+/* pcm_dev: [batch][pcm_stride] float32 (pcm_is_int16 = 0) or int16 (= 1); num_samples_dev[batch].
+ * Each sample is multiplied by `scale` (32768 for [-1,1) float input, processor.py:245; 1 for
+ * int16).  feats_dev: [batch][frames_stride][num_mel] float32; frames past an utterance's own count
+ * 1 + (n - frame_len) / frame_shift are written as 0 (zero padding of processor.padding,
+ * processor.py:562-566). */
+int wb_fbank_forward(const wb_fbank* fb, const void* pcm_dev, int pcm_is_int16, int64_t pcm_stride,
+                     const int32_t* num_samples_dev, int batch, float scale, float* feats_dev,
+                     int64_t frames_stride, int max_frames, wb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model handle — the packed weights of one ASRModel (ConformerEncoder + CTC + optional
+ * (Bi)TransformerDecoder); replaces load_state_dict on the reference modules
+ * (wenet/utils/checkpoint.py:26-43).  Tensor names/layouts are produced by the host-side packer
+ * wenet_b200/weights.py from the reference state_dict keys (SURVEY.md section 8a key table).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct wb_model wb_model;
+
+typedef struct {
+  int32_t input_dim;   /* 80 */
+  int32_t d_model;     /* encoder_conf.output_size */
+  int32_t heads;       /* attention_heads (d_model / heads must be 64) */
+  int32_t ffn_dim;     /* linear_units */
+  int32_t enc_layers;  /* num_blocks */
+  int32_t cnn_kernel;  /* cnn_module_kernel */
+  int32_t cnn_causal;  /* causal */
+  int32_t cnn_norm;    /* 0 = layer_norm, 1 = batch_norm (folded, eval) */
+  int32_t vocab;       /* output_dim */
+  int32_t dec_layers;  /* left (l2r) decoder blocks, 0 = no decoder */
+  int32_t rdec_layers; /* right (r2l) decoder blocks, 0 = none */
+  int32_t dec_heads;
+  int32_t dec_ffn_dim;
+  int32_t max_pos;     /* positional-encoding table length (5000) */
+  int32_t has_cmvn;    /* GlobalCMVN present */
+  int32_t precise;     /* 0: bf16 operands; 1: bf16x3 split operands (fp32-grade GEMMs) */
+  float ln_eps;        /* 1e-5 */
+} wb_model_config;
+
+enum { WB_F32 = 0, WB_BF16 = 1, WB_I32 = 2 };
+
+int wb_model_create(wb_model** out, const wb_model_config* cfg);
+void wb_model_destroy(wb_model* m);
+/* copies `host_data` (numel elements of dtype) to the device under `name` */
+int wb_model_set_tensor(wb_model* m, const char* name, const void* host_data, int dtype,
+                        int64_t numel);
+/* checks that every required tensor is present, builds TMA descriptors and the per-layer
+ * relative-position projections P_l = linear_pos(pe) (weight-only, attention.py:395-397) */
+int wb_model_finalize(wb_model* m, wb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * B. encoder — replaces ConformerEncoder.forward (wenet/models/transformer/encoder.py:122-181):
+ *    GlobalCMVN -> Conv2dSubsampling4 -> RelPositionalEncoding -> N x ConformerEncoderLayer ->
+ *    after_norm.  Output is PACKED: rows of all utterances' valid frames back to back
+ *    (utterance b occupies rows [seq_start[b], seq_start[b] + T'_b), T'_b = ((T_b-1)/2-1)/2);
+ *    wb_unpack_rows scatters into the reference's padded (B, T'max, d) layout.
+ *    decoding_chunk_size < 0: full attention; > 0: chunk mask of mask.py:88-123 with
+ *    num_left_chunks (mask.py:164-173); 0 (random training chunk) is rejected.
+ * ------------------------------------------------------------------------------------------ */
+size_t wb_encoder_workspace_bytes(const wb_model* m, int batch, const int32_t* feat_lens_host);
+/* total packed rows M = sum_b T'_b (also returned through *out_rows by wb_encoder_forward) */
+int64_t wb_encoder_out_rows(int batch, const int32_t* feat_lens_host);
+int wb_encoder_forward(const wb_model* m, const float* feats_dev, int64_t feats_stride_b,
+                       const int32_t* feat_lens_host, int batch, int decoding_chunk_size,
+                       int num_decoding_left_chunks, int pad_to_frames /* T'max of the padded batch (symmetric conv quirk) */,
+                       float* enc_out_dev /* [M][d] fp32 */, void* enc_out_bf16_dev /* [M][d] bf16 */,
+                       int32_t* seq_start_dev /* [batch] */, int32_t* seq_len_dev /* [batch] */,
+                       float* layer_dump_dev /* optional [(layers+1)][M][d]: embed out, then each layer */,
+                       void* workspace_dev, size_t workspace_bytes, wb_stream_t stream);
+
+/* streaming step — replaces BaseEncoder.forward_chunk (encoder.py:204-300), batch 1.
+ * xs_dev [T][input_dim]; att_cache_dev [layers][heads][cache_t1][128] (K|V halves) or NULL when
+ * cache_t1 = 0; cnn_cache_dev [layers][d][cnn_kernel-1] or NULL (first chunk);
+ * outputs: y [chunk][d]; r_att_cache [layers][heads][cache_t1+chunk-next_cache_start][128];
+ * r_cnn_cache [layers][d][cnn_kernel-1]. */
+size_t wb_encoder_chunk_workspace_bytes(const wb_model* m, int T, int cache_t1);
+int wb_encoder_forward_chunk(const wb_model* m, const float* xs_dev, int T, int offset,
+                             int required_cache_size, const float* att_cache_dev, int cache_t1,
+                             const float* cnn_cache_dev, float* y_dev, float* r_att_cache_dev,
+                             float* r_cnn_cache_dev, int* out_chunk, int* out_new_cache_t1,
+                             void* workspace_dev, size_t workspace_bytes, wb_stream_t stream);
+
+/* packed [M][d] -> padded [batch][t_stride][d] (rows past seq_len zeroed) and back */
+int wb_unpack_rows(const float* packed_dev, const int32_t* seq_start_dev, const int32_t* seq_len_dev,
+                   int batch, int max_len, int d, float* padded_dev, int64_t t_stride, wb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * C. CTC posteriors — replaces ASRModel.ctc_logprobs / CTC.log_softmax
+ *    (asr_model.py:254-265, ctc.py:73-81) + the per-frame logp.topk(beam) of search.py:158.
+ *    logp_dev [M][ldl] fp32 (ldl >= vocab, multiple of 4) receives the full log-probabilities.
+ * ------------------------------------------------------------------------------------------ */
+int wb_ctc_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t rows, int blank_id,
+                    float blank_penalty, float* logp_dev, int64_t ldl, int topk, float* topk_val_dev,
+                    int32_t* topk_idx_dev, wb_stream_t stream);
+
+/* D1. replaces ctc_greedy_search (search.py:109-124) + remove_duplicates_and_blank
+ *     (wenet/utils/ctc_utils.py:23-33).  tokens_dev [batch][out_stride], lens_dev [batch]. */
+int wb_ctc_greedy_search(const int32_t* topk_idx_dev, int topk, const int32_t* seq_start_dev,
+                         const int32_t* seq_len_dev, int batch, int blank_id, int32_t* tokens_dev,
+                         int out_stride, int32_t* lens_dev, wb_stream_t stream);
+
+/* D2. replaces ctc_prefix_beam_search (search.py:127-249; scores are IEEE doubles, log_add of
+ *     common.py:302-310).  Outputs per utterance up to `beam` hypotheses, best first:
+ *     tokens/times [batch][beam][max_len], lens [batch][beam], scores [batch][beam], nhyp [batch]. */
+size_t wb_prefix_beam_workspace_bytes(int batch, int beam, int max_len);
+int wb_ctc_prefix_beam_search(const float* topk_val_dev, const int32_t* topk_idx_dev, int topk,
+                              const int32_t* seq_start_dev, const int32_t* seq_len_dev, int batch,
+                              int beam, int blank_id, int max_len, int32_t* tokens_dev,
+                              int32_t* times_dev, int32_t* lens_dev, double* scores_dev,
+                              int32_t* nhyp_dev, void* workspace_dev, size_t workspace_bytes,
+                              wb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * E. attention rescoring — replaces attention_rescoring (search.py:374-458) and
+ *    ASRModel.forward_attention_decoder (asr_model.py:453-547): (Bi)TransformerDecoder over all
+ *    hypotheses of all utterances in one batch, cross-attention K/V projected once per utterance.
+ *    Hypotheses are given flattened, utterance-major: hyp h belongs to utterance hyp_utt[h]
+ *    (non-decreasing), has hyp_len[h] tokens at hyp_tokens[hyp_tok0[h] ...].
+ *    Outputs: tok_logp_l2r/r2l [R] with R = sum_h (len_h + 1): log p of token j of hyp h at row
+ *    hyp_row0[h] + j, the <eos> term at + len_h (r2l rows are indexed by decoder position);
+ *    hyp_score[h] = (1-rw)*l2r + rw*r2l + ctc_weight*ctc_score (fp32, reference summation order);
+ *    best[b] = index (within utterance b) of the first maximum.
+ * ------------------------------------------------------------------------------------------ */
+size_t wb_rescoring_workspace_bytes(const wb_model* m, int64_t enc_rows, int64_t total_tokens_plus_hyps);
+int wb_attention_rescoring(const wb_model* m, const void* enc_out_bf16_dev, int64_t enc_rows,
+                           const int32_t* seq_start_host, const int32_t* seq_len_host, int batch,
+                           int n_hyp, const int32_t* hyp_utt_host, const int32_t* hyp_len_host,
+                           const int32_t* hyp_tok0_host, const int32_t* hyp_tokens_host,
+                           const double* ctc_score_host, int sos, int eos, float ctc_weight,
+                           float reverse_weight, float* tok_logp_l2r_dev, float* tok_logp_r2l_dev,
+                           float* hyp_score_dev, int32_t* best_dev, void* workspace_dev,
+                           size_t workspace_bytes, wb_stream_t stream);
+/* full decoder posteriors for API parity with forward_attention_decoder: logp [R][ldl] (l2r) and
+ * r_logp [R][ldl] (r2l, may be NULL) */
+int wb_decoder_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t enc_rows,
+                        const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int n_hyp,
+                        const int32_t* hyp_utt_host, const int32_t* hyp_len_host,
+                        const int32_t* hyp_tok0_host, const int32_t* hyp_tokens_host, int sos, int eos,
+                        int use_r2l, float* logp_dev, float* r_logp_dev, int64_t ldl, void* workspace_dev,
+                        size_t workspace_bytes, wb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator-level entry points (used by the parity tests and micro-benchmarks; same kernels the
+ * stage entry points launch).
+ * ------------------------------------------------------------------------------------------ */
+/* C = epi(A[M,K] * B[N,K]^T + bias); A, B bf16 row-major (lda, K); epi: 0 bf16, 1 bf16+SiLU,
+ * 2 bf16+ReLU, 3 fp32 residual add (C += alpha*(.)), 4 GLU->bf16 (weights packed [16 value|16 gate]
+ * per 32 rows), 5 fp32 */
+int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K,
+               const float* bias_dev, int epi, float alpha, void* c_dev, int64_t ldc, int split3,
+               wb_stream_t stream);
+int wb_op_layernorm(const float* x_dev, int64_t ldx, int M, int d, const float* gamma_dev,
+                    const float* beta_dev, float eps, void* out_bf16_dev, int64_t ld_bf16, int split3,
+                    float* out_f32_dev, int64_t ld_f32, wb_stream_t stream);
+int wb_op_attention(const void* q_dev, int64_t ldq, int64_t q_rows, int q_col0, const void* k_dev,
+                    int64_t ldk, int64_t k_rows, int k_col0, const void* v_dev, int64_t ldv,
+                    int64_t v_rows, int v_col0, const float* kbias_dev, int ld_kbias,
+                    const int32_t* q_start_dev, const int32_t* q_len_dev, const int32_t* k_start_dev,
+                    const int32_t* k_len_dev, int batch, int heads, int max_q_len, int chunk_size,
+                    int num_left_chunks, float scale, void* out_dev, int64_t ldo, int out_col0,
+                    int v_mode, wb_stream_t stream);
+int wb_op_relpos_kprep(const void* k_dev, int64_t ldk, const float* pos_proj_dev,
+                       const int32_t* row_pos_dev, const float* bias_u_dev, const float* bias_v_dev,
+                       int M, int heads, void* kprime_dev, int64_t ldkp, float* kbias_dev,
+                       wb_stream_t stream);
+int wb_op_dwconv(const void* g_dev, int64_t ldg, const int32_t* seq_start_dev,
+                 const int32_t* seq_len_dev, const int32_t* out_start_dev, int batch, int max_len,
+                 int lead, int d, int ksize, int causal, const float* w_dev, const float* bias_dev,
+                 int norm_type, const float* gamma_dev, const float* beta_dev, float eps,
+                 const float* pad_vec_dev, int pad_until, void* out_dev, int64_t ldo,
+                 wb_stream_t stream);
+int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blank_id,
+                          float blank_penalty, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
+                          wb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WENET_B200_H_ */

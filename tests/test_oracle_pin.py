@@ -1,0 +1,123 @@
+"""Pin the CPU oracle (oracle/wenet_oracle.py) against the REAL reference where it is available
+(build container) and against the reference's own known-answer test everywhere."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import shim
+from oracle import wenet_oracle as O
+
+needs_ref = pytest.mark.skipif(not shim.have_reference(), reason="/root/reference not present (GPU box)")
+
+
+def test_prefix_beam_search_kat():
+    """runtime/core/test/ctc_prefix_beam_search_test.cc:29-72 (the reference's only golden vector on this path)."""
+    probs = torch.tensor([[0.25, 0.40, 0.35], [0.40, 0.35, 0.25], [0.10, 0.50, 0.40]]).log().unsqueeze(0)
+    r = O.ctc_prefix_beam_search(probs, torch.tensor([3]), 3)[0]
+    assert r["nbest"] == [[2, 1], [1, 2], [1]]
+    for got, want in zip(r["nbest_scores"], [0.2185, 0.1550, 0.1525]):
+        assert abs(math.exp(got) - want) < 1e-4
+    assert r["nbest_times"] == [[0, 2], [0, 2], [2]]
+    assert O.ctc_greedy_search(probs, torch.tensor([3])) == [[1]] or True  # greedy: argmax path 1,0->blank? see below
+    # frame argmaxes are 1, 0(blank), 1 -> "1 1"
+    assert O.ctc_greedy_search(probs, torch.tensor([3])) == [[1, 1]]
+
+
+def test_fbank_vs_torchaudio():
+    import torchaudio.compliance.kaldi as kaldi
+    g = torch.Generator().manual_seed(3)
+    wav = (torch.randn(1, 16000 * 2 + 123, generator=g) * 3000).clamp(-32767, 32767).round()
+    ref = kaldi.fbank(wav, num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0, energy_floor=0.0,
+                      sample_frequency=16000)
+    got = O.fbank(wav[0])
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 1e-4
+
+
+def _tiny_cfg(bidir=True, causal=True, norm="layer_norm", kernel=8):
+    return {
+        "input_dim": 80, "output_dim": 37, "cmvn": None,
+        "encoder": "conformer",
+        "encoder_conf": dict(output_size=128, attention_heads=2, linear_units=256, num_blocks=2, dropout_rate=0.0,
+                             positional_dropout_rate=0.0, attention_dropout_rate=0.0, input_layer="conv2d",
+                             normalize_before=True, cnn_module_kernel=kernel, use_cnn_module=True,
+                             activation_type="swish", pos_enc_layer_type="rel_pos",
+                             selfattention_layer_type="rel_selfattn", causal=causal, use_dynamic_chunk=causal,
+                             cnn_module_norm=norm, use_dynamic_left_chunk=False),
+        "decoder": "bitransformer" if bidir else "transformer",
+        "decoder_conf": dict(attention_heads=2, linear_units=256, num_blocks=2, dropout_rate=0.0,
+                             positional_dropout_rate=0.0, self_attention_dropout_rate=0.0,
+                             src_attention_dropout_rate=0.0, **({"r_num_blocks": 1} if bidir else {})),
+        "tokenizer": "char", "tokenizer_conf": {},
+        "ctc": "ctc", "ctc_conf": {"ctc_blank_id": 0},
+        "model": "asr_model",
+        "model_conf": dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False,
+                           **({"reverse_weight": 0.3} if bidir else {})),
+    }
+
+
+@needs_ref
+@pytest.mark.parametrize("variant", ["u2pp", "nonstream_bn"])
+def test_oracle_matches_reference(variant):
+    torch.manual_seed(777)
+    cfg = _tiny_cfg(bidir=True) if variant == "u2pp" else _tiny_cfg(bidir=False, causal=False, norm="batch_norm", kernel=15)
+    model = shim.init_reference_model(cfg)
+    # make BatchNorm statistics non-trivial
+    for n, b in model.named_buffers():
+        if n.endswith("running_mean"):
+            b.copy_(torch.randn_like(b) * 0.1)
+        if n.endswith("running_var"):
+            b.copy_(torch.rand_like(b) + 0.5)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ecfg = O.encoder_cfg(p, heads=2, causal=cfg["encoder_conf"]["causal"], cnn_norm=cfg["encoder_conf"]["cnn_module_norm"])
+    xs = torch.randn(2, 131, 80)
+    lens = torch.tensor([131, 90])
+    with torch.no_grad():
+        ref_out, ref_mask = model.encoder(xs, lens, decoding_chunk_size=-1, num_decoding_left_chunks=-1)
+        got_out, got_mask = O.encoder_forward(p, ecfg, xs, lens)
+        assert torch.equal(ref_mask, got_mask)
+        for b in range(2):
+            n = int(ref_mask[b].sum())
+            assert (ref_out[b, :n] - got_out[b, :n]).abs().max().item() < 2e-5
+        if variant == "u2pp":
+            r2, _ = model.encoder(xs, lens, decoding_chunk_size=4, num_decoding_left_chunks=2)
+            g2, _ = O.encoder_forward(p, ecfg, xs, lens, 4, 2)
+            n = int(ref_mask[1].sum())
+            assert (r2[1, :n] - g2[1, :n]).abs().max().item() < 2e-5
+            # streaming chunk step (encoder.py:204-300)
+            att = torch.zeros(0, 0, 0, 0)
+            cnn = torch.zeros(0, 0, 0, 0)
+            att_o, cnn_o = att, cnn
+            off = 0
+            for s in range(0, 131 - 18, 16):
+                chunk_x = xs[0:1, s:s + 19]
+                y, att, cnn = model.encoder.forward_chunk(chunk_x, off, 8, att, cnn)
+                yo, att_o, cnn_o = O.encoder_forward_chunk(p, ecfg, chunk_x, off, 8, att_o, cnn_o)
+                off += y.size(1)
+                assert (y - yo).abs().max().item() < 2e-5
+                assert (att - att_o).abs().max().item() < 2e-5 and (cnn - cnn_o).abs().max().item() < 2e-5
+        # CTC + searches
+        ref_lp = model.ctc_logprobs(ref_out)
+        got_lp = O.ctc_logprobs(p, got_out)
+        assert (ref_lp - got_lp).abs().max().item() < 5e-5
+        enc_lens = ref_mask.squeeze(1).sum(1)
+        from wenet.models.transformer.search import (attention_rescoring, ctc_greedy_search,
+                                                     ctc_prefix_beam_search)
+        rg = ctc_greedy_search(ref_lp, enc_lens)
+        assert [r.tokens for r in rg] == O.ctc_greedy_search(ref_lp, enc_lens)
+        rb = ctc_prefix_beam_search(ref_lp, enc_lens, 4)
+        gb = O.ctc_prefix_beam_search(ref_lp, enc_lens, 4)
+        for r, g in zip(rb, gb):
+            assert [list(x) for x in r.nbest] == g["nbest"]
+            assert r.nbest_scores == g["nbest_scores"]
+            assert [list(x) for x in r.nbest_times] == g["nbest_times"]
+        rw = 0.3 if variant == "u2pp" else 0.0
+        rr = attention_rescoring(model, rb, ref_out, enc_lens, 0.5, rw)
+        dcfg = dict(bidirectional=(variant == "u2pp"), layers=2, r_layers=1, heads=2)
+        gr = O.attention_rescoring(p, dcfg, gb, ref_out, enc_lens, model.sos_symbol(), model.eos_symbol(), 0.5, rw)
+        for r, g in zip(rr, gr):
+            assert list(r.tokens) == g["tokens"]
+            assert abs(r.score - g["best_score"]) < 1e-4

@@ -1,0 +1,346 @@
+// C-ABI of libwenet_b200.so (see include/wenet_b200.h): handle management, weight upload,
+// operator-level entry points.  Stage orchestration lives in encoder.cu / rescoring.cu.
+#include "model.h"
+#include <string.h>
+
+namespace wb {
+
+static size_t dtype_size(int dt) { return dt == WB_BF16 ? 2 : 4; }
+
+int model_get(const Model* m, const std::string& name, int dtype, int64_t numel, const void** out) {
+    auto it = m->tensors.find(name);
+    if (it == m->tensors.end()) {
+        set_last_error("model: required tensor '%s' was not provided", name.c_str());
+        return WB_ERR_NOT_LOADED;
+    }
+    if (it->second.dtype != dtype || (numel >= 0 && it->second.numel != numel)) {
+        set_last_error("model: tensor '%s' has dtype %d numel %lld, expected dtype %d numel %lld", name.c_str(),
+                       it->second.dtype, (long long)it->second.numel, dtype, (long long)numel);
+        return WB_ERR_BAD_ARG;
+    }
+    *out = it->second.ptr;
+    return WB_OK;
+}
+
+static int get_linear(Model* m, const std::string& base, int N, int K, bool bias, Linear* L) {
+    const void* p;
+    int rc = model_get(m, base + ".w", WB_BF16, (int64_t)N * K, &p);
+    if (rc != WB_OK) return rc;
+    L->w = p;
+    L->N = N;
+    L->K = K;
+    L->b = nullptr;
+    if (bias) {
+        rc = model_get(m, base + ".b", WB_F32, N, &p);
+        if (rc != WB_OK) return rc;
+        L->b = (const float*)p;
+    }
+    return make_weight_tmap(&L->tmap, L->w, N, K);
+}
+
+static int get_norm(Model* m, const std::string& base, int d, Norm* n) {
+    const void* p;
+    int rc = model_get(m, base + ".g", WB_F32, d, &p);
+    if (rc != WB_OK) return rc;
+    n->g = (const float*)p;
+    rc = model_get(m, base + ".b", WB_F32, d, &p);
+    if (rc != WB_OK) return rc;
+    n->b = (const float*)p;
+    return WB_OK;
+}
+
+#define RC(x)                  \
+    do {                       \
+        int _rc = (x);         \
+        if (_rc != WB_OK) return _rc; \
+    } while (0)
+
+static int finalize_decoder(Model* m, const std::string& pfx, int nlayers, Decoder* D) {
+    const int d = m->cfg.d_model, V = m->cfg.vocab, ff = m->cfg.dec_ffn_dim;
+    const void* p;
+    RC(model_get(m, pfx + ".emb", WB_F32, (int64_t)V * d, &p));
+    D->emb = (const float*)p;
+    D->layers.resize(nlayers);
+    for (int i = 0; i < nlayers; ++i) {
+        const std::string b = pfx + "." + std::to_string(i);
+        DecLayer& L = D->layers[i];
+        RC(get_norm(m, b + ".norm1", d, &L.n1));
+        RC(get_norm(m, b + ".norm2", d, &L.n2));
+        RC(get_norm(m, b + ".norm3", d, &L.n3));
+        RC(get_linear(m, b + ".sa.qkv", 3 * d, d, true, &L.sa_qkv));
+        RC(get_linear(m, b + ".sa.out", d, d, true, &L.sa_out));
+        RC(get_linear(m, b + ".ca.q", d, d, true, &L.ca_q));
+        RC(get_linear(m, b + ".ca.kv", 2 * d, d, true, &L.ca_kv));
+        RC(get_linear(m, b + ".ca.out", d, d, true, &L.ca_out));
+        RC(get_linear(m, b + ".ff.w1", ff, d, true, &L.ff1));
+        RC(get_linear(m, b + ".ff.w2", d, ff, true, &L.ff2));
+    }
+    RC(get_norm(m, pfx + ".after_norm", d, &D->after));
+    RC(get_linear(m, pfx + ".out", V, d, true, &D->out));
+    return WB_OK;
+}
+
+static int model_finalize(Model* m, cudaStream_t stream) {
+    const wb_model_config& c = m->cfg;
+    WB_REQUIRE(c.precise == 0, WB_ERR_UNSUPPORTED, "precise (bf16x3) mode is not wired into the model path yet");
+    WB_REQUIRE(c.d_model % 128 == 0 && c.d_model == c.heads * 64, WB_ERR_UNSUPPORTED,
+               "unsupported attention geometry: d_model=%d heads=%d (d_k must be 64, d_model %% 128 == 0)", c.d_model,
+               c.heads);
+    WB_REQUIRE(c.input_dim >= 7 && c.ffn_dim % 64 == 0, WB_ERR_UNSUPPORTED, "unsupported input_dim/ffn_dim");
+    WB_REQUIRE(c.cnn_kernel >= 1 && c.cnn_kernel <= 31 && (c.cnn_causal || c.cnn_kernel % 2 == 1), WB_ERR_UNSUPPORTED,
+               "unsupported cnn_module_kernel %d", c.cnn_kernel);
+    if (c.dec_layers > 0)
+        WB_REQUIRE(c.dec_heads * 64 == c.d_model && c.dec_ffn_dim % 64 == 0, WB_ERR_UNSUPPORTED,
+                   "unsupported decoder geometry (heads=%d)", c.dec_heads);
+    const int d = c.d_model, ff = c.ffn_dim;
+    m->F1 = (c.input_dim - 3) / 2 + 1;
+    m->F2 = (m->F1 - 3) / 2 + 1;
+    const void* p;
+    if (c.has_cmvn) {
+        RC(model_get(m, "cmvn.mean", WB_F32, c.input_dim, &p));
+        m->cmvn_mean = (const float*)p;
+        RC(model_get(m, "cmvn.istd", WB_F32, c.input_dim, &p));
+        m->cmvn_istd = (const float*)p;
+    }
+    RC(model_get(m, "embed.conv1.w", WB_F32, 9 * d, &p));
+    m->conv1_w = (const float*)p;
+    RC(model_get(m, "embed.conv1.b", WB_F32, d, &p));
+    m->conv1_b = (const float*)p;
+    RC(get_linear(m, "embed.conv2", d, 9 * d, true, &m->conv2));
+    RC(get_linear(m, "embed.out", d, m->F2 * d, true, &m->embed_out));
+    RC(model_get(m, "embed.pe", WB_F32, (int64_t)c.max_pos * d, &p));
+    m->pe = (const float*)p;
+
+    // bf16x3 copy of the PE table for the (one-off) position projections
+    void* pe3 = nullptr;
+    WB_CHECK_CUDA(cudaMalloc(&pe3, (size_t)c.max_pos * 3 * d * 2));
+    RC(cast_rows_bf16(m->pe, d, c.max_pos, d, pe3, 3 * d, 1, stream));
+
+    m->layers.resize(c.enc_layers);
+    for (int i = 0; i < c.enc_layers; ++i) {
+        const std::string b = "enc." + std::to_string(i);
+        EncLayer& L = m->layers[i];
+        RC(get_norm(m, b + ".norm_ff_macaron", d, &L.n_ffm));
+        RC(get_norm(m, b + ".norm_mha", d, &L.n_mha));
+        RC(get_norm(m, b + ".norm_conv", d, &L.n_conv));
+        RC(get_norm(m, b + ".norm_ff", d, &L.n_ff));
+        RC(get_norm(m, b + ".norm_final", d, &L.n_final));
+        RC(get_linear(m, b + ".ffm.w1", ff, d, true, &L.ffm1));
+        RC(get_linear(m, b + ".ffm.w2", d, ff, true, &L.ffm2));
+        RC(get_linear(m, b + ".ff.w1", ff, d, true, &L.ff1));
+        RC(get_linear(m, b + ".ff.w2", d, ff, true, &L.ff2));
+        RC(get_linear(m, b + ".att.qkv", 3 * d, d, true, &L.qkv));
+        RC(get_linear(m, b + ".att.out", d, d, true, &L.out));
+        RC(get_linear(m, b + ".conv.pw1", 2 * d, d, true, &L.pw1));
+        RC(get_linear(m, b + ".conv.pw2", d, d, true, &L.pw2));
+        RC(model_get(m, b + ".att.pos_u", WB_F32, d, &p));
+        L.pos_u = (const float*)p;
+        RC(model_get(m, b + ".att.pos_v", WB_F32, d, &p));
+        L.pos_v = (const float*)p;
+        RC(model_get(m, b + ".att.pos.w3", WB_BF16, (int64_t)d * 3 * d, &p));
+        L.pos_w3 = p;
+        RC(model_get(m, b + ".conv.dw.w", WB_F32, (int64_t)d * c.cnn_kernel, &p));
+        L.dw_w = (const float*)p;
+        RC(model_get(m, b + ".conv.dw.b", WB_F32, d, &p));
+        L.dw_b = (const float*)p;
+        RC(get_norm(m, b + ".conv.norm", d, &L.n_cnn));
+        RC(model_get(m, b + ".conv.pad_vec", WB_F32, d, &p));
+        L.pad_vec = (const float*)p;
+        // P_l = pe @ W_pos^T in bf16x3 (fp32-grade): A = [hi|lo|hi], B = [hi|hi|lo]
+        WB_CHECK_CUDA(cudaMalloc((void**)&L.pos_proj, (size_t)c.max_pos * d * sizeof(float)));
+        m->owned.push_back(L.pos_proj);
+        RC(gemm_bf16(pe3, 3 * d, nullptr, L.pos_w3, c.max_pos, d, 3 * d, nullptr, EPI_F32, 1.0f, L.pos_proj, d, 0,
+                     stream));
+    }
+    RC(get_norm(m, "after_norm", d, &m->after));
+    RC(get_linear(m, "ctc", c.vocab, d, true, &m->ctc));
+    if (c.dec_layers > 0) RC(finalize_decoder(m, "dec.left", c.dec_layers, &m->left));
+    if (c.rdec_layers > 0) RC(finalize_decoder(m, "dec.right", c.rdec_layers, &m->right));
+    WB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(pe3);
+    m->finalized = true;
+    return WB_OK;
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+extern "C" {
+
+const char* wb_last_error(void) { return get_last_error(); }
+const char* wb_version(void) { return "wenet_b200 0.1 (sm_100a)"; }
+unsigned long long wb_launch_count(void) { return g_launch_count; }
+
+// ---------------------------------------------------------------- fbank
+struct wb_fbank {
+    FbankPlan* plan;
+};
+
+int wb_fbank_create(wb_fbank** out, int num_mel, int frame_len, int frame_shift, float preemph,
+                    const float* window_host, const float* mel_host) {
+    WB_REQUIRE(out && window_host && mel_host, WB_ERR_BAD_ARG, "fbank_create: null argument");
+    FbankPlan* plan = nullptr;
+    int rc = fbank_plan_create(&plan, 16000, num_mel, frame_len, frame_shift, 20.f, preemph, window_host, mel_host);
+    if (rc != WB_OK) return rc;
+    wb_fbank* fb = new wb_fbank();
+    fb->plan = plan;
+    *out = fb;
+    return WB_OK;
+}
+void wb_fbank_destroy(wb_fbank* fb) {
+    if (!fb) return;
+    fbank_plan_destroy(fb->plan);
+    delete fb;
+}
+int wb_fbank_forward(const wb_fbank* fb, const void* pcm_dev, int pcm_is_int16, int64_t pcm_stride,
+                     const int32_t* num_samples_dev, int batch, float scale, float* feats_dev, int64_t frames_stride,
+                     int max_frames, wb_stream_t stream) {
+    WB_REQUIRE(fb && pcm_dev && num_samples_dev && feats_dev, WB_ERR_BAD_ARG, "fbank_forward: null argument");
+    return fbank_forward(fb->plan, pcm_dev, pcm_is_int16, pcm_stride, num_samples_dev, batch, scale, feats_dev,
+                         frames_stride, max_frames, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- model
+int wb_model_create(wb_model** out, const wb_model_config* cfg) {
+    WB_REQUIRE(out && cfg, WB_ERR_BAD_ARG, "model_create: null argument");
+    Model* m = new Model();
+    m->cfg = *cfg;
+    *out = reinterpret_cast<wb_model*>(m);
+    return WB_OK;
+}
+void wb_model_destroy(wb_model* mm) {
+    if (!mm) return;
+    Model* m = reinterpret_cast<Model*>(mm);
+    for (auto& kv : m->tensors) cudaFree(kv.second.ptr);
+    for (void* p : m->owned) cudaFree(p);
+    delete m;
+}
+int wb_model_set_tensor(wb_model* mm, const char* name, const void* host_data, int dtype, int64_t numel) {
+    WB_REQUIRE(mm && name && host_data && numel > 0, WB_ERR_BAD_ARG, "set_tensor: bad argument");
+    Model* m = reinterpret_cast<Model*>(mm);
+    WB_REQUIRE(!m->finalized, WB_ERR_BAD_ARG, "set_tensor: model already finalized");
+    DevTensor t;
+    t.dtype = dtype;
+    t.numel = numel;
+    const size_t bytes = (size_t)numel * dtype_size(dtype);
+    WB_CHECK_CUDA(cudaMalloc(&t.ptr, (bytes + 255) / 256 * 256));
+    WB_CHECK_CUDA(cudaMemcpy(t.ptr, host_data, bytes, cudaMemcpyHostToDevice));
+    auto it = m->tensors.find(name);
+    if (it != m->tensors.end()) {
+        cudaFree(it->second.ptr);
+        it->second = t;
+    } else {
+        m->tensors[name] = t;
+    }
+    return WB_OK;
+}
+int wb_model_finalize(wb_model* mm, wb_stream_t stream) {
+    WB_REQUIRE(mm, WB_ERR_BAD_ARG, "finalize: null model");
+    return model_finalize(reinterpret_cast<Model*>(mm), (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- CTC / searches
+int wb_ctc_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_t rows, int blank_id, float blank_penalty,
+                    float* logp_dev, int64_t ldl, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
+                    wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "ctc_logprobs: model not finalized");
+    WB_REQUIRE(ldl >= m->cfg.vocab, WB_ERR_BAD_ARG, "ctc_logprobs: ldl < vocab");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC(gemm_bf16(enc_out_bf16_dev, m->cfg.d_model, &m->ctc.tmap, m->ctc.w, (int)rows, m->cfg.vocab, m->cfg.d_model,
+                 m->ctc.b, EPI_F32, 1.0f, logp_dev, ldl, 0, st));
+    return ctc_logsoftmax_topk(logp_dev, ldl, (int)rows, m->cfg.vocab, blank_id, blank_penalty, topk, topk_val_dev,
+                               topk_idx_dev, st);
+}
+
+int wb_ctc_greedy_search(const int32_t* topk_idx_dev, int topk, const int32_t* seq_start_dev,
+                         const int32_t* seq_len_dev, int batch, int blank_id, int32_t* tokens_dev, int out_stride,
+                         int32_t* lens_dev, wb_stream_t stream) {
+    return ctc_greedy(topk_idx_dev, topk, seq_start_dev, seq_len_dev, batch, blank_id, tokens_dev, out_stride, lens_dev,
+                      (cudaStream_t)stream);
+}
+
+size_t wb_prefix_beam_workspace_bytes(int batch, int beam, int max_len) {
+    return prefix_beam_workspace_bytes(batch, beam, max_len);
+}
+
+int wb_ctc_prefix_beam_search(const float* topk_val_dev, const int32_t* topk_idx_dev, int topk,
+                              const int32_t* seq_start_dev, const int32_t* seq_len_dev, int batch, int beam,
+                              int blank_id, int max_len, int32_t* tokens_dev, int32_t* times_dev, int32_t* lens_dev,
+                              double* scores_dev, int32_t* nhyp_dev, void* workspace_dev, size_t workspace_bytes,
+                              wb_stream_t stream) {
+    PrefixBeamArgs a;
+    a.topk_val = topk_val_dev;
+    a.topk_idx = topk_idx_dev;
+    a.topk = topk;
+    a.seq_start = seq_start_dev;
+    a.seq_len = seq_len_dev;
+    a.batch = batch;
+    a.beam = beam;
+    a.blank_id = blank_id;
+    a.max_len = max_len;
+    a.out_tokens = tokens_dev;
+    a.out_times = times_dev;
+    a.out_lens = lens_dev;
+    a.out_scores = scores_dev;
+    a.out_nhyp = nhyp_dev;
+    a.workspace = workspace_dev;
+    a.workspace_bytes = workspace_bytes;
+    return ctc_prefix_beam_search(a, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- operator-level entry points
+int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K, const float* bias_dev, int epi,
+               float alpha, void* c_dev, int64_t ldc, int split3, wb_stream_t stream) {
+    return gemm_bf16(a_dev, lda, nullptr, b_dev, M, N, K, bias_dev, epi, alpha, c_dev, ldc, split3,
+                     (cudaStream_t)stream);
+}
+int wb_op_layernorm(const float* x_dev, int64_t ldx, int M, int d, const float* gamma_dev, const float* beta_dev,
+                    float eps, void* out_bf16_dev, int64_t ld_bf16, int split3, float* out_f32_dev, int64_t ld_f32,
+                    wb_stream_t stream) {
+    return layernorm_rows(x_dev, ldx, M, d, gamma_dev, beta_dev, eps, out_bf16_dev, ld_bf16, split3, out_f32_dev,
+                          ld_f32, (cudaStream_t)stream);
+}
+int wb_op_attention(const void* q_dev, int64_t ldq, int64_t q_rows, int q_col0, const void* k_dev, int64_t ldk,
+                    int64_t k_rows, int k_col0, const void* v_dev, int64_t ldv, int64_t v_rows, int v_col0,
+                    const float* kbias_dev, int ld_kbias, const int32_t* q_start_dev, const int32_t* q_len_dev,
+                    const int32_t* k_start_dev, const int32_t* k_len_dev, int batch, int heads, int max_q_len,
+                    int chunk_size, int num_left_chunks, float scale, void* out_dev, int64_t ldo, int out_col0,
+                    int v_mode, wb_stream_t stream) {
+    AttnArgs a;
+    a.q = q_dev; a.ldq = ldq; a.q_rows = q_rows; a.q_col0 = q_col0;
+    a.k = k_dev; a.ldk = ldk; a.k_rows = k_rows; a.k_col0 = k_col0;
+    a.v = v_dev; a.ldv = ldv; a.v_rows = v_rows; a.v_col0 = v_col0;
+    a.kbias = kbias_dev; a.ld_kbias = ld_kbias;
+    a.q_start = q_start_dev; a.q_len = q_len_dev; a.k_start = k_start_dev; a.k_len = k_len_dev;
+    a.batch = batch; a.heads = heads; a.max_q_len = max_q_len;
+    a.chunk_size = chunk_size; a.num_left_chunks = num_left_chunks; a.scale = scale;
+    a.out = out_dev; a.ldo = ldo; a.out_col0 = out_col0; a.split3_out = 0; a.v_mode = v_mode;
+    return attention_forward(a, (cudaStream_t)stream);
+}
+int wb_op_relpos_kprep(const void* k_dev, int64_t ldk, const float* pos_proj_dev, const int32_t* row_pos_dev,
+                       const float* bias_u_dev, const float* bias_v_dev, int M, int heads, void* kprime_dev,
+                       int64_t ldkp, float* kbias_dev, wb_stream_t stream) {
+    return relpos_kprep(k_dev, ldk, pos_proj_dev, row_pos_dev, bias_u_dev, bias_v_dev, M, heads, kprime_dev, ldkp,
+                        kbias_dev, (cudaStream_t)stream);
+}
+int wb_op_dwconv(const void* g_dev, int64_t ldg, const int32_t* seq_start_dev, const int32_t* seq_len_dev,
+                 const int32_t* out_start_dev, int batch, int max_len, int lead, int d, int ksize, int causal,
+                 const float* w_dev, const float* bias_dev, int norm_type, const float* gamma_dev,
+                 const float* beta_dev, float eps, const float* pad_vec_dev, int pad_until, void* out_dev, int64_t ldo,
+                 wb_stream_t stream) {
+    DwConvArgs a;
+    a.g = g_dev; a.ldg = ldg; a.seq_start = seq_start_dev; a.seq_len = seq_len_dev; a.out_start = out_start_dev;
+    a.batch = batch; a.max_len = max_len; a.lead = lead; a.d = d; a.ksize = ksize; a.causal = causal;
+    a.w = w_dev; a.bias = bias_dev; a.norm_type = norm_type; a.gamma = gamma_dev; a.beta = beta_dev; a.eps = eps;
+    a.pad_vec = pad_vec_dev; a.pad_until = pad_until; a.out = out_dev; a.ldo = ldo; a.split3 = 0;
+    return dwconv_norm_silu(a, (cudaStream_t)stream);
+}
+int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blank_id, float blank_penalty, int topk,
+                          float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream) {
+    return ctc_logsoftmax_topk(logits_dev, ldl, M, V, blank_id, blank_penalty, topk, topk_val_dev, topk_idx_dev,
+                               (cudaStream_t)stream);
+}
+
+}  // extern "C"

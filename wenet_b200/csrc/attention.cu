@@ -1,0 +1,421 @@
+// Variable-length multi-head attention on tcgen05 (d_k = 64), used for
+//   * RelPositionMultiHeadedAttention  (wenet/models/transformer/attention.py:364-438, :133-178)
+//       scores[i,j] = ((q_i+u).k_j + (q_i+v).p_j)/sqrt(dk)      (rel_shift is NOT applied, :407-409)
+//                   = (q_i.(k_j+p_j) + (u.k_j + v.p_j))/sqrt(dk) = (q_i.k'_j + c_j)/sqrt(dk)
+//     so ONE score GEMM against K' = K + P plus a per-key bias c_j (both produced by relpos_kprep)
+//     replaces the reference's two (matrix_ac, matrix_bd).
+//   * MultiHeadedAttention self-attn (causal) and MultiHeadedCrossAttention of the rescoring decoder
+//     (attention.py:247-304, :441-520; masks decoder.py:179-185, mask.py:88-123).
+// Masks are generated in-kernel from (k_len, chunk_size, num_left_chunks): key-padding mask, the
+// streaming chunk mask (mask.py:subsequent_chunk_mask) and the causal mask (chunk_size = 1).
+//
+// One CTA = 128 queries of one (sequence, head); 128 threads, thread r owns query row r
+// (TMEM lane r), so softmax needs no cross-thread reduction.
+//   pass 1: S = Q K'^T per 128-key tile (tcgen05.mma 128x128x64 into TMEM), row max only
+//   pass 2: S again, p = exp2(.), P (bf16) -> shared memory in the canonical K-major SWIZZLE_128B
+//           layout, O += P V (tcgen05.mma 128x64x128) — exact max known => no rescaling of O.
+// Q/K'/V tiles arrive by TMA (SWIZZLE_128B); V is consumed directly as an MN-major B operand.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wb {
+
+namespace {
+
+constexpr int AT_M = 128;
+constexpr int AT_N = 128;
+constexpr int DK = 64;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB
+
+struct AttnDev {
+    const float* kbias;
+    int ld_kbias;
+    const int* q_start;
+    const int* q_len;
+    const int* k_start;
+    const int* k_len;
+    int q_col0, k_col0, v_col0;
+    int chunk_size, num_left_chunks;
+    float scale_log2e;
+    __nv_bfloat16* out;
+    long long ldo;
+    int out_col0;
+    int split3_out;
+    int split_width;
+    int v_mode;
+};
+
+constexpr int AT_SMEM = 1024 /*align*/ + 3 * TILE_BYTES /*Q,K,V*/ + 2 * TILE_BYTES /*P*/ + TILE_BYTES /*Vt*/ +
+                        2 * 128 * 4 /*c*/ + 128 /*barriers*/;
+
+__global__ void __launch_bounds__(128, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, AttnDev P) {
+    const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+    const int q_len = P.q_len[b];
+    if (qt * AT_M >= q_len) return;
+    const int q_start = P.q_start[b];
+    const int k_start = P.k_start[b];
+    const int k_len = P.k_len[b];
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + TILE_BYTES;
+    uint8_t* sV = smem + 2 * TILE_BYTES;
+    uint8_t* sP = smem + 3 * TILE_BYTES;
+    uint8_t* sVt = smem + 5 * TILE_BYTES;
+    float* sC = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES + 2 * 128 * 4);
+    uint64_t* bar_q = bars + 0;
+    uint64_t* bar_k = bars + 1;
+    uint64_t* bar_v = bars + 2;
+    uint64_t* bar_s = bars + 3;
+    uint64_t* bar_pv = bars + 4;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int qi = qt * AT_M + tid;  // query index inside the sequence
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        mbar_init(bar_q, 1);
+        mbar_init(bar_k, 1);
+        mbar_init(bar_v, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_pv, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_holder, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_s = tmem_base;         // columns [0,128)
+    const uint32_t tmem_o = tmem_base + 128;   // columns [128,192)
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+
+    // visible key range for this row, and the tile range for the CTA
+    int row_lo = 0, row_hi = k_len;
+    int cta_lo = 0, cta_hi = k_len;
+    if (P.chunk_size > 0) {
+        const int c = P.chunk_size;
+        row_hi = min((qi / c + 1) * c, k_len);
+        row_lo = (P.num_left_chunks < 0) ? 0 : max((qi / c - P.num_left_chunks) * c, 0);
+        const int q_first = qt * AT_M, q_last = min(qt * AT_M + AT_M - 1, q_len - 1);
+        cta_hi = min((q_last / c + 1) * c, k_len);
+        cta_lo = (P.num_left_chunks < 0) ? 0 : max((q_first / c - P.num_left_chunks) * c, 0);
+    }
+    const int kt0 = cta_lo / AT_N;
+    const int kt1 = (cta_hi + AT_N - 1) / AT_N;
+
+    uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_pv = 0;
+    constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, AT_N, 0);
+    const uint32_t idesc_o = make_idesc_bf16(AT_M, DK, P.v_mode == 0 ? 1 : 0);
+
+    if (tid == 0 && kt0 < kt1) {
+        mbar_expect_tx(bar_q, TILE_BYTES);
+        tma_load_2d(sQ, &tmap_q, bar_q, P.q_col0 + h * DK, q_start + qt * AT_M);
+        mbar_expect_tx(bar_k, TILE_BYTES);
+        tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + kt0 * AT_N);
+    }
+
+    float m_run = -INFINITY;
+    // ------------------------------- pass 1: row max -------------------------------
+    for (int kt = kt0; kt < kt1; ++kt) {
+        const int j0 = kt * AT_N;
+        {
+            const int j = j0 + tid;
+            float cv = 0.f;
+            if (P.kbias != nullptr && j < k_len)
+                cv = P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e;
+            sC[(kt & 1) * 128 + tid] = cv;
+        }
+        if (tid == 0) {
+            if (kt == kt0) mbar_wait(bar_q, 0);
+            mbar_wait(bar_k, ph_k);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k)
+                umma_f16(tmem_s, make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                         make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k != 0);
+            umma_commit(bar_s);
+        }
+        ph_k ^= 1;
+        __syncthreads();  // sC visible
+        mbar_wait(bar_s, ph_s);
+        ph_s ^= 1;
+        tc_fence_after();
+        if (tid == 0) {
+            // K smem is free again: prefetch next K tile (or the first tile again for pass 2, plus V)
+            const int nk = (kt + 1 < kt1) ? kt + 1 : kt0;
+            mbar_expect_tx(bar_k, TILE_BYTES);
+            tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + nk * AT_N);
+            if (kt + 1 == kt1) {
+                mbar_expect_tx(bar_v, TILE_BYTES);
+                tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + kt0 * AT_N);
+            }
+        }
+        const float* cc = sC + (kt & 1) * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int j = j0 + c * 32 + i;
+                const float s = fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]);
+                if (j >= row_lo && j < row_hi) m_run = fmaxf(m_run, s);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // everyone done reading S before the next MMA overwrites it
+    }
+    const float m_fin = (m_run == -INFINITY) ? 0.f : m_run;
+
+    // ------------------------------- pass 2: P, O -------------------------------
+    float l_run = 0.f;
+    for (int kt = kt0; kt < kt1; ++kt) {
+        const int j0 = kt * AT_N;
+        {
+            const int j = j0 + tid;
+            float cv = 0.f;
+            if (P.kbias != nullptr && j < k_len)
+                cv = P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e;
+            sC[(kt & 1) * 128 + tid] = cv;
+        }
+        if (tid == 0) {
+            mbar_wait(bar_k, ph_k);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k)
+                umma_f16(tmem_s, make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                         make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k != 0);
+            umma_commit(bar_s);
+        }
+        ph_k ^= 1;
+        __syncthreads();
+        mbar_wait(bar_s, ph_s);
+        ph_s ^= 1;
+        tc_fence_after();
+        if (tid == 0 && kt + 1 < kt1) {
+            mbar_expect_tx(bar_k, TILE_BYTES);
+            tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + (kt + 1) * AT_N);
+        }
+        const float* cc = sC + (kt & 1) * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const int j = j0 + c * 32 + i;
+                float p0 = 0.f, p1 = 0.f;
+                if (j >= row_lo && j < row_hi)
+                    p0 = exp2f(fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]) - m_fin);
+                if (j + 1 >= row_lo && j + 1 < row_hi)
+                    p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[c * 32 + i + 1]) - m_fin);
+                const uint32_t w = pack_bf16x2(p0, p1);
+                // accumulate the normaliser from the *rounded* probabilities actually fed to the MMA
+                l_run += bf16_lo(w) + bf16_hi(w);
+                pk[i >> 1] = w;
+            }
+            // canonical K-major SWIZZLE_128B: row r, 16-byte chunk cidx -> chunk (cidx ^ (r & 7))
+            uint8_t* prow = sP + (c >> 1) * TILE_BYTES + tid * 128;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int cidx = (c & 1) * 4 + u;
+                *reinterpret_cast<uint4*>(prow + ((cidx ^ (tid & 7)) << 4)) =
+                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            }
+        }
+        if (P.v_mode == 1) {
+            // fallback: transpose V tile [key][dk] (TMA swizzled) into K-major [dk][key] panels
+            mbar_wait(bar_v, ph_v);
+            const int key = tid;
+            const uint8_t* vrow = sV + key * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const uint4 v4 = *reinterpret_cast<const uint4*>(vrow + ((ch ^ (key & 7)) << 4));
+                const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int dk = ch * 8 + e;
+                    const uint16_t val = (uint16_t)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffff));
+                    uint8_t* dst = sVt + (key >> 6) * (TILE_BYTES / 2) + dk * 128 +
+                                   ((((key & 63) >> 3) ^ (dk & 7)) << 4) + (key & 7) * 2;
+                    *reinterpret_cast<uint16_t*>(dst) = val;
+                }
+            }
+        }
+        ph_v ^= 1;
+        fence_proxy_async_smem();  // generic-proxy smem writes (P, Vt) -> visible to the tensor core
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            if (P.v_mode == 0) mbar_wait(bar_v, ph_v ^ 1);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sP);
+#pragma unroll
+            for (int ks = 0; ks < AT_N / 16; ++ks) {
+                const uint64_t adesc =
+                    make_smem_desc_sw128(pa + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024);
+                uint64_t bdesc;
+                if (P.v_mode == 0)
+                    bdesc = make_smem_desc_sw128(smem_u32(sV) + ks * 2048, 1024, 1024);
+                else
+                    bdesc = make_smem_desc_sw128(smem_u32(sVt) + (ks >> 2) * (TILE_BYTES / 2) + (ks & 3) * 32,
+                                                 16, 1024);
+                umma_f16(tmem_o, adesc, bdesc, idesc_o, (kt != kt0 || ks != 0) ? 1u : 0u);
+            }
+            umma_commit(bar_pv);
+        }
+        // P / V / Vt buffers and the S accumulator are reused next iteration: wait for the PV MMAs
+        mbar_wait(bar_pv, ph_pv);
+        ph_pv ^= 1;
+        tc_fence_after();
+        if (tid == 0 && kt + 1 < kt1) {
+            mbar_expect_tx(bar_v, TILE_BYTES);
+            tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + (kt + 1) * AT_N);
+        }
+    }
+
+    // ------------------------------- epilogue -------------------------------
+    if (kt0 < kt1) {
+        const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_o + lane_sel + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            if (qi < q_len) {
+                __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK + c * 32;
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    reinterpret_cast<uint4*>(o)[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                if (P.split3_out) {
+                    uint32_t lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        lo[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv - bf16_lo(pk[i]),
+                                            __uint_as_float(r[2 * i + 1]) * inv - bf16_hi(pk[i]));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        reinterpret_cast<uint4*>(o + P.split_width)[u] =
+                            make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+                        reinterpret_cast<uint4*>(o + 2 * P.split_width)[u] =
+                            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    }
+                }
+            }
+        }
+    } else if (qi < q_len) {
+        __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK;
+        for (int i = 0; i < DK; ++i) o[i] = __float2bfloat16_rn(0.f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+__global__ void relpos_kprep_kernel(const __nv_bfloat16* __restrict__ k, long long ldk,
+                                    const float* __restrict__ P, const int* __restrict__ row_pos,
+                                    const float* __restrict__ bias_u, const float* __restrict__ bias_v, int M,
+                                    int heads, __nv_bfloat16* __restrict__ kp, long long ldkp,
+                                    float* __restrict__ kbias) {
+    // one warp per (row, head): 64 channels = 2 per lane
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (long long)M * heads) return;
+    const long long row = gw / heads;
+    const int h = (int)(gw - row * heads);
+    const int d = heads * DK;
+    const int col = h * DK + 2 * lane;
+    const uint32_t kk = *reinterpret_cast<const uint32_t*>(k + row * ldk + col);
+    const float k0 = bf16_lo(kk), k1 = bf16_hi(kk);
+    const float2 p = *reinterpret_cast<const float2*>(P + (long long)row_pos[row] * d + col);
+    const float2 u = *reinterpret_cast<const float2*>(bias_u + col);
+    const float2 v = *reinterpret_cast<const float2*>(bias_v + col);
+    *reinterpret_cast<uint32_t*>(kp + row * ldkp + col) = pack_bf16x2(k0 + p.x, k1 + p.y);
+    float c = u.x * k0 + u.y * k1 + v.x * p.x + v.y * p.y;
+    c = warp_sum(c);
+    if (lane == 0) kbias[row * heads + h] = c;
+}
+
+}  // namespace
+
+int attention_forward(const AttnArgs& a, cudaStream_t stream) {
+    if (a.batch <= 0 || a.max_q_len <= 0) return WB_OK;
+    CUtensorMap tq, tk, tv;
+    int rc;
+    // the maps cover the whole row width so that column offsets select the head
+    if ((rc = make_tmap_2d_bf16(&tq, a.q, (uint64_t)a.q_rows, (uint64_t)a.ldq, (uint64_t)a.ldq, 128, 64)) != WB_OK) return rc;
+    if ((rc = make_tmap_2d_bf16(&tk, a.k, (uint64_t)a.k_rows, (uint64_t)a.ldk, (uint64_t)a.ldk, 128, 64)) != WB_OK) return rc;
+    if ((rc = make_tmap_2d_bf16(&tv, a.v, (uint64_t)a.v_rows, (uint64_t)a.ldv, (uint64_t)a.ldv, 128, 64)) != WB_OK) return rc;
+    AttnDev P;
+    P.kbias = a.kbias;
+    P.ld_kbias = a.ld_kbias;
+    P.q_start = a.q_start;
+    P.q_len = a.q_len;
+    P.k_start = a.k_start;
+    P.k_len = a.k_len;
+    P.q_col0 = a.q_col0;
+    P.k_col0 = a.k_col0;
+    P.v_col0 = a.v_col0;
+    P.chunk_size = a.chunk_size;
+    P.num_left_chunks = a.num_left_chunks;
+    P.scale_log2e = a.scale * 1.4426950408889634f;
+    P.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+    P.ldo = a.ldo;
+    P.out_col0 = a.out_col0;
+    P.split3_out = a.split3_out;
+    P.split_width = a.heads * DK;
+    P.v_mode = a.v_mode;
+    WB_REQUIRE((a.ldo % 8) == 0 && (a.out_col0 % 8) == 0, WB_ERR_BAD_ARG, "attention: output pitch/offset must be %%8");
+    static bool attr_set = false;
+    if (!attr_set) {
+        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(a.max_q_len, AT_M), a.heads, a.batch);
+    attention_kernel<<<grid, 128, AT_SMEM, stream>>>(tq, tk, tv, P);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+int relpos_kprep(const void* k_bf16, long long ldk, const float* P, const int* row_pos, const float* bias_u,
+                 const float* bias_v, int M, int heads, void* kprime_bf16, long long ldkp, float* kbias,
+                 cudaStream_t stream) {
+    if (M <= 0) return WB_OK;
+    const long long warps = (long long)M * heads;
+    const int block = 256;
+    const long long grid = (warps * 32 + block - 1) / block;
+    relpos_kprep_kernel<<<(unsigned)grid, block, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(k_bf16), ldk, P, row_pos, bias_u, bias_v, M, heads,
+        reinterpret_cast<__nv_bfloat16*>(kprime_bf16), ldkp, kbias);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+}  // namespace wb

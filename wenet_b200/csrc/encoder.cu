@@ -1,0 +1,289 @@
+// Host-side orchestration of the ConformerEncoder forward pass (batch, variable length, packed rows).
+// Mirrors wenet/models/transformer/encoder.py:122-188 (BaseEncoder.forward / forward_layers) and
+// encoder_layer.py:188-265 (ConformerEncoderLayer.forward), launching only kernels of this library.
+//
+// Residual stream x: fp32 [M][d].  GEMM operands: bf16.  Per layer (pre-norm macaron block):
+//   x += 1/2 FFN_m(LN(x)); x += MHA_relpos(LN(x)); x += Conv(LN(x)); x += 1/2 FFN(LN(x)); x = LN_final(x)
+#include "model.h"
+#include <math.h>
+#include <vector>
+
+namespace wb {
+
+namespace {
+
+__global__ void unpack_rows_kernel(const float* __restrict__ packed, const int* __restrict__ seq_start,
+                                   const int* __restrict__ seq_len, int max_len, int d, float* __restrict__ padded,
+                                   long long t_stride) {
+    const int b = blockIdx.y;
+    const int n = seq_len[b], s = seq_start[b];
+    const int dv = d / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)max_len * dv;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / dv), c = (int)(i - (long long)t * dv);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < n) v = reinterpret_cast<const float4*>(packed + (long long)(s + t) * d)[c];
+        reinterpret_cast<float4*>(padded + ((long long)b * t_stride + t) * d)[c] = v;
+    }
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+inline int sub4_len(int T) { return T >= 7 ? ((T - 1) / 2 - 1) / 2 : 0; }
+
+struct EncPlan {
+    int batch = 0;
+    long long M = 0;         // packed output rows
+    long long rows1 = 0;     // conv1 output rows (t1, f1)
+    int max_tp = 0, max_t1 = 0;
+    std::vector<int> tp, t1n, seq_start;
+    std::vector<long long> off1, off2;
+    // workspace offsets
+    size_t o_meta = 0, o_out1 = 0, o_a2 = 0, o_out2 = 0, o_x = 0, total = 0;
+    size_t meta_bytes = 0;
+};
+
+void make_plan(const Model* m, int batch, const int32_t* feat_lens, EncPlan* P) {
+    P->batch = batch;
+    P->tp.resize(batch);
+    P->t1n.resize(batch);
+    P->seq_start.resize(batch);
+    P->off1.resize(batch);
+    P->off2.resize(batch);
+    long long M = 0, r1 = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int tp = sub4_len(feat_lens[b]);
+        P->tp[b] = tp;
+        P->t1n[b] = tp > 0 ? 2 * tp + 1 : 0;
+        P->seq_start[b] = (int)M;
+        P->off1[b] = r1;
+        P->off2[b] = M * m->F2;
+        M += tp;
+        r1 += (long long)P->t1n[b] * m->F1;
+        P->max_tp = tp > P->max_tp ? tp : P->max_tp;
+        P->max_t1 = P->t1n[b] > P->max_t1 ? P->t1n[b] : P->max_t1;
+    }
+    P->M = M;
+    P->rows1 = r1;
+    const int d = m->cfg.d_model;
+    // meta: t1n[B] int, tp[B] int, seq_start[B] int, off1[B] ll, off2[B] ll, row_pos[M] int
+    P->meta_bytes = align_up((size_t)batch * (3 * 4 + 2 * 8) + 64) + align_up((size_t)M * 4 + 64);
+    size_t o = 0;
+    P->o_meta = o;
+    o += P->meta_bytes;
+    P->o_out1 = o;
+    o += align_up((size_t)r1 * d * 2);
+    P->o_a2 = o;
+    // the im2col matrix is the largest buffer; all per-layer activations alias it afterwards
+    const size_t a2_bytes = (size_t)M * m->F2 * 9 * d * 2;
+    const size_t layer_bytes = align_up((size_t)M * d * 2) * 4 /*a, ctx, g, g2*/ +
+                               align_up((size_t)M * m->cfg.ffn_dim * 2) + align_up((size_t)M * 3 * d * 2) +
+                               align_up((size_t)M * d * 2) /*kp*/ + align_up((size_t)M * m->cfg.heads * 4);
+    o += align_up(a2_bytes > layer_bytes ? a2_bytes : layer_bytes);
+    P->o_out2 = o;
+    o += align_up((size_t)M * m->F2 * d * 2);
+    P->o_x = o;
+    o += align_up((size_t)M * d * 4);
+    P->total = o + 256;
+}
+
+}  // namespace
+
+}  // namespace wb
+
+using namespace wb;
+
+#define RC(x)                         \
+    do {                              \
+        int _rc = (x);                \
+        if (_rc != WB_OK) return _rc; \
+    } while (0)
+
+extern "C" {
+
+int64_t wb_encoder_out_rows(int batch, const int32_t* feat_lens_host) {
+    long long M = 0;
+    for (int b = 0; b < batch; ++b) M += sub4_len(feat_lens_host[b]);
+    return M;
+}
+
+size_t wb_encoder_workspace_bytes(const wb_model* mm, int batch, const int32_t* feat_lens_host) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    if (!m || !m->finalized || batch <= 0) return 0;
+    EncPlan P;
+    make_plan(m, batch, feat_lens_host, &P);
+    return P.total;
+}
+
+int wb_unpack_rows(const float* packed_dev, const int32_t* seq_start_dev, const int32_t* seq_len_dev, int batch,
+                   int max_len, int d, float* padded_dev, int64_t t_stride, wb_stream_t stream) {
+    if (batch <= 0 || max_len <= 0) return WB_OK;
+    WB_REQUIRE(d % 4 == 0, WB_ERR_BAD_ARG, "unpack_rows: d %% 4");
+    dim3 grid(ceil_div(max_len * (d / 4), 256), batch);
+    if (grid.x > 1024) grid.x = 1024;
+    unpack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(packed_dev, seq_start_dev, seq_len_dev, max_len, d,
+                                                              padded_dev, t_stride);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats_stride_b,
+                       const int32_t* feat_lens_host, int batch, int decoding_chunk_size,
+                       int num_decoding_left_chunks, int pad_to_frames, float* enc_out_dev, void* enc_out_bf16_dev,
+                       int32_t* seq_start_dev, int32_t* seq_len_dev, float* layer_dump_dev, void* workspace_dev,
+                       size_t workspace_bytes, wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "encoder_forward: model not finalized");
+    WB_REQUIRE(feats_dev && feat_lens_host && enc_out_dev && enc_out_bf16_dev && seq_start_dev && seq_len_dev &&
+                   workspace_dev && batch > 0,
+               WB_ERR_BAD_ARG, "encoder_forward: null/empty argument");
+    WB_REQUIRE(decoding_chunk_size != 0, WB_ERR_UNSUPPORTED,
+               "decoding_chunk_size == 0 selects the random training chunk (mask.py:167-180); not an inference mode");
+    cudaStream_t st = (cudaStream_t)stream;
+    const wb_model_config& c = m->cfg;
+    const int d = c.d_model, ff = c.ffn_dim, H = c.heads;
+    EncPlan P;
+    make_plan(m, batch, feat_lens_host, &P);
+    WB_REQUIRE(workspace_bytes >= P.total, WB_ERR_WORKSPACE, "encoder_forward: workspace %zu < required %zu",
+               workspace_bytes, P.total);
+    WB_REQUIRE(P.max_tp <= c.max_pos, WB_ERR_UNSUPPORTED, "utterance longer than the positional table (%d > %d)",
+               P.max_tp, c.max_pos);
+    const long long M = P.M;
+    if (M == 0) return WB_OK;
+    WB_REQUIRE(M * (long long)m->F2 < 2147483647LL, WB_ERR_UNSUPPORTED, "batch too large for 32-bit row indices");
+
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
+    // ---- meta upload (one copy) ----
+    size_t ll_off = ((size_t)batch * 12 + 7) / 8 * 8;  // 3 int arrays, then 8-byte aligned long long arrays
+    std::vector<uint8_t> meta(ll_off + (size_t)batch * 16);
+    int* h_t1n = reinterpret_cast<int*>(meta.data());
+    int* h_tp = h_t1n + batch;
+    int* h_ss = h_tp + batch;
+    long long* h_off1 = reinterpret_cast<long long*>(meta.data() + ll_off);
+    long long* h_off2 = h_off1 + batch;
+    for (int b = 0; b < batch; ++b) {
+        h_t1n[b] = P.t1n[b];
+        h_tp[b] = P.tp[b];
+        h_ss[b] = P.seq_start[b];
+        h_off1[b] = P.off1[b];
+        h_off2[b] = P.off2[b];
+    }
+    WB_CHECK_CUDA(cudaMemcpyAsync(ws + P.o_meta, meta.data(), meta.size(), cudaMemcpyHostToDevice, st));
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));  // `meta` is pageable host memory about to go out of scope
+    const int* d_t1n = reinterpret_cast<const int*>(ws + P.o_meta);
+    const int* d_tp = d_t1n + batch;
+    const int* d_ss = d_tp + batch;
+    const long long* d_off1 = reinterpret_cast<const long long*>(ws + P.o_meta + ll_off);
+    const long long* d_off2 = d_off1 + batch;
+    int* d_row_pos = reinterpret_cast<int*>(ws + P.o_meta + align_up((size_t)batch * 28 + 64));
+    WB_CHECK_CUDA(cudaMemcpyAsync(seq_start_dev, d_ss, (size_t)batch * 4, cudaMemcpyDeviceToDevice, st));
+    WB_CHECK_CUDA(cudaMemcpyAsync(seq_len_dev, d_tp, (size_t)batch * 4, cudaMemcpyDeviceToDevice, st));
+
+    void* out1 = ws + P.o_out1;
+    void* a2 = ws + P.o_a2;
+    void* out2 = ws + P.o_out2;
+    float* x = reinterpret_cast<float*>(ws + P.o_x);
+
+    // ---- Conv2dSubsampling4 (subsampling.py:203-228) ----
+    RC(subsample_conv1(feats_dev, feats_stride_b, c.input_dim, d_t1n, d_off1, batch, P.max_t1, m->cmvn_mean,
+                       m->cmvn_istd, m->conv1_w, m->conv1_b, d, out1, 0, st));
+    RC(subsample_im2col(out1, d_off1, d_tp, d_off2, batch, P.max_tp, m->F1, m->F2, d, a2, 0, st));
+    RC(gemm_bf16(a2, 9 * d, &m->conv2.tmap, m->conv2.w, (int)(M * m->F2), d, 9 * d, m->conv2.b, EPI_BF16_RELU, 1.0f,
+                 out2, d, 0, st));
+    // Linear(F2*d -> d), x * sqrt(d)  (embedding.py:141-147: RelPositionalEncoding scales, no add)
+    RC(gemm_bf16(out2, (long long)m->F2 * d, &m->embed_out.tmap, m->embed_out.w, (int)M, d, m->F2 * d, m->embed_out.b,
+                 EPI_F32, sqrtf((float)d), x, d, 0, st));
+    if (layer_dump_dev)
+        WB_CHECK_CUDA(cudaMemcpyAsync(layer_dump_dev, x, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, st));
+    RC(fill_row_pos(d_ss, d_tp, batch, 0, d_row_pos, P.max_tp, st));
+
+    // ---- per-layer buffers alias the (now dead) im2col region ----
+    uint8_t* lb = reinterpret_cast<uint8_t*>(a2);
+    size_t lo = 0;
+    auto carve = [&](size_t bytes) {
+        void* p = lb + lo;
+        lo += align_up(bytes);
+        return p;
+    };
+    void* a = carve((size_t)M * d * 2);
+    void* ctx = carve((size_t)M * d * 2);
+    void* g = carve((size_t)M * d * 2);
+    void* g2 = carve((size_t)M * d * 2);
+    void* h = carve((size_t)M * ff * 2);
+    void* qkv = carve((size_t)M * 3 * d * 2);
+    void* kp = carve((size_t)M * d * 2);
+    float* kbias = reinterpret_cast<float*>(carve((size_t)M * H * 4));
+
+    const int chunk = decoding_chunk_size > 0 ? decoding_chunk_size : 0;
+    const float att_scale = 1.0f / sqrtf(64.0f);
+    const int Mi = (int)M;
+    for (int li = 0; li < c.enc_layers; ++li) {
+        const EncLayer& L = m->layers[li];
+        // macaron feed-forward (encoder_layer.py:221-228)
+        RC(layernorm_rows(x, d, Mi, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.ffm1.tmap, L.ffm1.w, Mi, ff, d, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
+        RC(gemm_bf16(h, ff, &L.ffm2.tmap, L.ffm2.w, Mi, d, ff, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        // rel-pos multi-headed self-attention (:231-238)
+        RC(layernorm_rows(x, d, Mi, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, Mi, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
+        RC(relpos_kprep(reinterpret_cast<const uint8_t*>(qkv) + (size_t)d * 2, 3 * d, L.pos_proj, d_row_pos, L.pos_u,
+                        L.pos_v, Mi, H, kp, d, kbias, st));
+        {
+            AttnArgs A;
+            A.q = qkv; A.ldq = 3 * d; A.q_rows = M; A.q_col0 = 0;
+            A.k = kp; A.ldk = d; A.k_rows = M; A.k_col0 = 0;
+            A.v = qkv; A.ldv = 3 * d; A.v_rows = M; A.v_col0 = 2 * d;
+            A.kbias = kbias; A.ld_kbias = H;
+            A.q_start = d_ss; A.q_len = d_tp; A.k_start = d_ss; A.k_len = d_tp;
+            A.batch = batch; A.heads = H; A.max_q_len = P.max_tp;
+            A.chunk_size = chunk; A.num_left_chunks = num_decoding_left_chunks; A.scale = att_scale;
+            A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
+            RC(attention_forward(A, st));
+        }
+        RC(gemm_bf16(ctx, d, &L.out.tmap, L.out.w, Mi, d, d, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        // convolution module (:243-251)
+        RC(layernorm_rows(x, d, Mi, d, L.n_conv.g, L.n_conv.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.pw1.tmap, L.pw1.w, Mi, 2 * d, d, L.pw1.b, EPI_GLU_BF16, 1.0f, g, d, 0, st));
+        {
+            DwConvArgs D;
+            D.g = g; D.ldg = d; D.seq_start = d_ss; D.seq_len = d_tp; D.out_start = d_ss;
+            D.batch = batch; D.max_len = P.max_tp; D.lead = 0; D.d = d; D.ksize = c.cnn_kernel;
+            D.causal = c.cnn_causal; D.w = L.dw_w; D.bias = L.dw_b; D.norm_type = c.cnn_norm;
+            D.gamma = L.n_cnn.g; D.beta = L.n_cnn.b; D.eps = c.ln_eps; D.pad_vec = L.pad_vec;
+            D.pad_until = pad_to_frames > 0 ? pad_to_frames : P.max_tp;
+            D.out = g2; D.ldo = d; D.split3 = 0;
+            RC(dwconv_norm_silu(D, st));
+        }
+        RC(gemm_bf16(g2, d, &L.pw2.tmap, L.pw2.w, Mi, d, d, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        // feed-forward (:254-259) and norm_final (:262-263)
+        RC(layernorm_rows(x, d, Mi, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, Mi, ff, d, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
+        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, Mi, d, ff, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        RC(layernorm_rows(x, d, Mi, d, L.n_final.g, L.n_final.b, c.ln_eps, nullptr, 0, 0, x, d, st));
+        if (layer_dump_dev)
+            WB_CHECK_CUDA(cudaMemcpyAsync(layer_dump_dev + (size_t)(li + 1) * M * d, x, (size_t)M * d * 4,
+                                          cudaMemcpyDeviceToDevice, st));
+    }
+    // after_norm (encoder.py:176-177): fp32 result + bf16 copy for the CTC / decoder GEMMs
+    RC(layernorm_rows(x, d, Mi, d, m->after.g, m->after.b, c.ln_eps, enc_out_bf16_dev, d, 0, enc_out_dev, d, st));
+    return WB_OK;
+}
+
+size_t wb_encoder_chunk_workspace_bytes(const wb_model* mm, int T, int cache_t1) {
+    (void)mm; (void)T; (void)cache_t1;
+    return 0;
+}
+
+int wb_encoder_forward_chunk(const wb_model* mm, const float* xs_dev, int T, int offset, int required_cache_size,
+                             const float* att_cache_dev, int cache_t1, const float* cnn_cache_dev, float* y_dev,
+                             float* r_att_cache_dev, float* r_cnn_cache_dev, int* out_chunk, int* out_new_cache_t1,
+                             void* workspace_dev, size_t workspace_bytes, wb_stream_t stream) {
+    (void)mm; (void)xs_dev; (void)T; (void)offset; (void)required_cache_size; (void)att_cache_dev; (void)cache_t1;
+    (void)cnn_cache_dev; (void)y_dev; (void)r_att_cache_dev; (void)r_cnn_cache_dev; (void)out_chunk;
+    (void)out_new_cache_t1; (void)workspace_dev; (void)workspace_bytes; (void)stream;
+    set_last_error("encoder_forward_chunk: not implemented yet");
+    return WB_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

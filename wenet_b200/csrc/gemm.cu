@@ -1,0 +1,395 @@
+// tcgen05 GEMM for every Linear / pointwise-conv / im2col-conv on the path.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T + bias[N] )        A, B bf16 (K-major), fp32 accumulate
+//
+// Replaces: nn.Linear / Conv1d(k=1) / Conv2d-as-im2col in the reference
+//   (wenet/models/transformer/positionwise_feed_forward.py:50-58, attention.py:74-77,109-131,
+//    convolution.py:46-53,88-95, subsampling.py:194-195,203-228, ctc.py:44, decoder.py:96-103).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      : TMA producer   — cp.async.bulk.tensor 2-D loads of A (128x64) and B (BNx64)
+//                                  tiles, SWIZZLE_128B, ring of kStages smem slots (mbarrier
+//                                  full/empty)
+//   warp 1      : MMA issuer     — one lane issues tcgen05.mma.cta_group::1.kind::f16
+//                                  (M=128, N=BN, K=16) x4 per k-block into a TMEM accumulator;
+//                                  tcgen05.commit frees smem slots / publishes the accumulator
+//   warps 2..5  : epilogue       — tcgen05.ld 32x32b.x32 (thread == accumulator row), bias +
+//                                  activation / residual / GLU, vectorised global stores.
+//                                  TMEM holds two accumulator stages so the epilogue of tile i
+//                                  overlaps the main loop of tile i+1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator (power of two)
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+    int M, N, K;
+    int epi;
+    float alpha;
+    const float* bias;
+    void* out;
+    long long ldc;
+    int split3;
+    int num_m_tiles, num_n_tiles;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                       // [kStages]
+    uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+    uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m_tile = t % p.num_m_tiles;
+                const int n_tile = t / p.num_m_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK,
+                                m_tile * BM);
+                    tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK,
+                                n_tile * BN);
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator complete
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m_tile = t % p.num_m_tiles;
+            const int n_tile = t / p.num_m_tiles;
+            const long long row = (long long)m_tile * BM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int n0 = n_tile * BN + c * 32;
+                if (n0 >= p.N) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
+                float v[32];
+                const bool full = (n0 + 32 <= p.N);
+                if (p.bias != nullptr) {
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                            v[i] = __uint_as_float(r[i]) + b4.x;
+                            v[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
+                            v[i + 2] = __uint_as_float(r[i + 2]) + b4.z;
+                            v[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            v[i] = __uint_as_float(r[i]) + ((n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                }
+                if (!row_ok) continue;
+
+                switch (p.epi) {
+                    case EPI_BF16:
+                    case EPI_BF16_SILU:
+                    case EPI_BF16_RELU: {
+                        if (p.epi == EPI_BF16_SILU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                        } else if (p.epi == EPI_BF16_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (p.alpha != 1.0f) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                        }
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + n0;
+                        const bool vec = full && ((p.ldc & 7) == 0) && ((p.N & 7) == 0);
+                        if (vec) {
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                reinterpret_cast<uint4*>(o)[i] =
+                                    make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                            if (p.split3) {
+                                uint32_t lo[16];
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    lo[i] = pack_bf16x2(v[2 * i] - bf16_lo(pk[i]),
+                                                        v[2 * i + 1] - bf16_hi(pk[i]));
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    reinterpret_cast<uint4*>(o + p.N)[i] =
+                                        make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                                    reinterpret_cast<uint4*>(o + 2 * (long long)p.N)[i] =
+                                        make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                                }
+                            }
+                        } else {
+                            for (int i = 0; i < 32; ++i) {
+                                if (n0 + i < p.N) {
+                                    const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+                                    o[i] = h;
+                                    if (p.split3) {
+                                        o[p.N + i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+                                        o[2 * (long long)p.N + i] = h;
+                                    }
+                                }
+                            }
+                        }
+                    } break;
+                    case EPI_GLU_BF16: {
+                        // weight rows are packed in groups of 32: [16 value rows | 16 gate rows]
+                        const int on = p.N >> 1;
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + (n0 >> 1);
+                        float g[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_f(v[16 + i]);
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
+                        reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        if (p.split3) {
+                            uint32_t lo[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                lo[i] = pack_bf16x2(g[2 * i] - bf16_lo(pk[i]), g[2 * i + 1] - bf16_hi(pk[i]));
+                            reinterpret_cast<uint4*>(o + on)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            reinterpret_cast<uint4*>(o + on)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                            reinterpret_cast<uint4*>(o + 2 * on)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            reinterpret_cast<uint4*>(o + 2 * on)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
+                    } break;
+                    case EPI_RESID_F32: {
+                        float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + n0;
+                        if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float4 x = reinterpret_cast<float4*>(o)[i];
+                                x.x += p.alpha * v[4 * i];
+                                x.y += p.alpha * v[4 * i + 1];
+                                x.z += p.alpha * v[4 * i + 2];
+                                x.w += p.alpha * v[4 * i + 3];
+                                reinterpret_cast<float4*>(o)[i] = x;
+                            }
+                        } else {
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + i < p.N) o[i] += p.alpha * v[i];
+                        }
+                    } break;
+                    case EPI_F32:
+                    default: {
+                        float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + n0;
+                        if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                reinterpret_cast<float4*>(o)[i] =
+                                    make_float4(p.alpha * v[4 * i], p.alpha * v[4 * i + 1],
+                                                p.alpha * v[4 * i + 2], p.alpha * v[4 * i + 3]);
+                        } else {
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + i < p.N) o[i] = p.alpha * v[i];
+                        }
+                    } break;
+                }
+            }
+            // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+int g_num_sms = 0;
+
+template <int BN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        WB_CHECK_CUDA(cudaGetDevice(&dev));
+        WB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    gemm_tcgen05_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+}  // namespace
+
+int gemm_bn_for(int N) { return (N % 256 == 0 || N >= 1024) ? 256 : 128; }
+
+int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K) {
+    return make_tmap_2d_bf16(out, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)gemm_bn_for(N), BK);
+}
+
+int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
+              int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
+              cudaStream_t stream) {
+    if (M <= 0) return WB_OK;
+    WB_REQUIRE(N > 0 && K > 0, WB_ERR_BAD_ARG, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    WB_REQUIRE((K % 8) == 0 && (lda % 8) == 0, WB_ERR_BAD_ARG,
+               "gemm: K (%d) and lda (%lld) must be multiples of 8 (TMA 16-byte row pitch)", K, lda);
+    WB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0, WB_ERR_BAD_ARG, "gemm: A not 16B aligned");
+    if (epi == EPI_GLU_BF16) {
+        WB_REQUIRE((N % 32) == 0 && (ldc % 8) == 0, WB_ERR_BAD_ARG, "gemm GLU: N %% 32 and ldc %% 8 required");
+    }
+    if (epi == EPI_RESID_F32 || epi == EPI_F32) {
+        WB_REQUIRE(!split3, WB_ERR_BAD_ARG, "gemm: split3 only for bf16 outputs");
+    }
+    const int bn = gemm_bn_for(N);
+    CUtensorMap ta, tb_local;
+    int rc = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+    if (rc != WB_OK) return rc;
+    const CUtensorMap* tb = tmap_b_opt;
+    if (tb == nullptr) {
+        rc = make_tmap_2d_bf16(&tb_local, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, BK);
+        if (rc != WB_OK) return rc;
+        tb = &tb_local;
+    }
+    GemmParams p;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.epi = epi;
+    p.alpha = alpha;
+    p.bias = bias;
+    p.out = out;
+    p.ldc = ldc;
+    p.split3 = split3;
+    p.num_m_tiles = ceil_div(M, BM);
+    p.num_n_tiles = ceil_div(N, bn);
+    if (bn == 256) return launch_gemm<256>(ta, *tb, p, stream);
+    return launch_gemm<128>(ta, *tb, p, stream);
+}
+
+}  // namespace wb

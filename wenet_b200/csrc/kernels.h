@@ -1,0 +1,162 @@
+// Internal (C++) interface between the kernel translation units and api.cu.
+// Everything here is implementation detail; the public surface is include/wenet_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+
+namespace wb {
+
+// ---- GEMM epilogues (gemm.cu) ----------------------------------------------------------------
+enum GemmEpi : int {
+    EPI_BF16 = 0,       // out_bf16 = alpha * (acc + bias)
+    EPI_BF16_SILU = 1,  // out_bf16 = alpha * silu(acc + bias)
+    EPI_BF16_RELU = 2,  // out_bf16 = alpha * relu(acc + bias)
+    EPI_RESID_F32 = 3,  // out_f32 += alpha * (acc + bias)      (in-place residual stream update)
+    EPI_GLU_BF16 = 4,   // out_bf16[:, N/2] = a * sigmoid(g), weight rows packed [16 a | 16 g] x N/32
+    EPI_F32 = 5,        // out_f32  = alpha * (acc + bias)
+};
+
+int gemm_bn_for(int N);
+// tensor map for a [N, K] bf16 weight (B operand), box rows = gemm_bn_for(N)
+int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K);
+// C = epi(A[M,K](lda) * B[N,K]^T + bias). tmap_b_opt may be null (then built from B).
+// split3: bf16 outputs are written as [hi | lo | hi] column blocks of width N (N/2 for GLU) so the
+// next GEMM can run in "bf16x3" mode against weights packed as [hi | hi | lo].
+int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
+              int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
+              cudaStream_t stream);
+
+// ---- fbank (fbank.cu) ------------------------------------------------------------------------
+struct FbankPlan {  // device-resident constants, built once by fbank_plan_create
+    float* window;      // [frame_len]
+    float* twiddle;     // [nfft/2] complex (cos, -sin) pairs for the nfft/2-point complex FFT
+    float* twiddle_r;   // [nfft/2 + 1] complex for the real-FFT split step
+    int* mel_start;     // [num_mel]
+    int* mel_len;       // [num_mel]
+    int* mel_off;       // [num_mel] offset into mel_w
+    float* mel_w;       // flat non-zero weights
+    int num_mel, frame_len, frame_shift, nfft, mel_nnz;
+    float preemph;
+};
+int fbank_plan_create(FbankPlan** out, int sample_rate, int num_mel, int frame_len, int frame_shift,
+                      float low_freq, float preemph, const float* window_host,
+                      const float* mel_dense_host /*[num_mel, nfft/2+1]*/);
+void fbank_plan_destroy(FbankPlan* p);
+// pcm: [B, pcm_stride] (float if !is_int16 else int16), num_samples[B] (device int32)
+// out: [B, out_frames_stride, num_mel] fp32; frames beyond the utterance's own count are zeroed.
+int fbank_forward(const FbankPlan* plan, const void* pcm, int is_int16, long long pcm_stride,
+                  const int* num_samples_dev, int batch, float scale, float* out,
+                  long long out_frames_stride, int max_frames, cudaStream_t stream);
+
+// ---- row-wise ops (norm.cu) --------------------------------------------------------------------
+// y = (x - mean) / sqrt(var + eps) * gamma + beta over the last dim (d).  out_bf16 / out_f32 are
+// optional; out_f32 may alias x.  split3: bf16 output as [hi|lo|hi] blocks (row pitch ld_bf16).
+int layernorm_rows(const float* x, long long ldx, int M, int d, const float* gamma, const float* beta,
+                   float eps, void* out_bf16, long long ld_bf16, int split3, float* out_f32,
+                   long long ld_f32, cudaStream_t stream);
+// f32 -> bf16 row copy with optional split3
+int cast_rows_bf16(const float* x, long long ldx, int M, int d, void* out_bf16, long long ld_bf16,
+                   int split3, cudaStream_t stream);
+
+// ---- conv2d subsampling front (subsample.cu) ---------------------------------------------------
+// feats: [B, feat_stride_t, idim] fp32 padded; writes conv1 output (ReLU) channels-last bf16:
+// row (off1[b] + t1 * F1 + f1), d channels.  Only t1 < T1[b] rows are produced.
+int subsample_conv1(const float* feats, long long feat_stride_b, int idim, const int* t1_len,
+                    const long long* off1, int batch, int max_t1, const float* cmvn_mean,
+                    const float* cmvn_istd, const float* w /*[9][d] fp32*/, const float* bias, int d,
+                    void* out1_bf16, int split_unused, cudaStream_t stream);
+// im2col for conv2 (3x3 stride 2) from channels-last conv1 output.
+// out row (off2[b] + t2 * F2 + f2) has K = 9*d entries ordered (kh, kw, c).
+int subsample_im2col(const void* out1_bf16, const long long* off1, const int* t2_len,
+                     const long long* off2, int batch, int max_t2, int F1, int F2, int d,
+                     void* a2_bf16, int split3, cudaStream_t stream);
+
+// ---- attention (attention.cu) ------------------------------------------------------------------
+struct AttnArgs {
+    const void* q;  long long ldq;  long long q_rows;   // bf16 [q_rows, ldq]; head h at col q_col0 + 64h
+    int q_col0;
+    const void* k;  long long ldk;  long long k_rows;   int k_col0;
+    const void* v;  long long ldv;  long long v_rows;   int v_col0;
+    const float* kbias;  int ld_kbias;                  // [k_rows, heads] fp32 or null
+    const int* q_start; const int* q_len;               // [batch] device
+    const int* k_start; const int* k_len;               // [batch] device
+    int batch, heads, max_q_len;
+    int chunk_size;        // 0: no chunk mask.  >0: key j visible to query i iff
+    int num_left_chunks;   //   max((i/c - left)*c, 0) <= j < (i/c + 1)*c   (left < 0: from 0)
+    float scale;
+    void* out; long long ldo;  int out_col0;            // bf16 [q_rows, ldo]
+    int split3_out;                                     // write [hi|lo|hi] with block width heads*64
+    int v_mode;                                         // 0: MN-major UMMA descriptor, 1: smem transpose
+};
+int attention_forward(const AttnArgs& a, cudaStream_t stream);
+// K' = bf16(k + P[pos]) and c[m,h] = sum_i u[h,i]*k[m,h,i] + v[h,i]*P[pos,h,i]
+// (rel-pos attention with rel_shift removed, wenet attention.py:395-417, folded into one score GEMM)
+int relpos_kprep(const void* k_bf16, long long ldk, const float* P /*[maxlen, d]*/, const int* row_pos,
+                 const float* bias_u, const float* bias_v, int M, int heads, void* kprime_bf16,
+                 long long ldkp, float* kbias /*[M, heads]*/, cudaStream_t stream);
+
+// ---- convolution module tail (convmod.cu) ------------------------------------------------------
+struct DwConvArgs {
+    const void* g; long long ldg;          // bf16 [rows, ldg] post-GLU activations
+    const int* seq_start; const int* seq_len;  // per sequence rows in g (including `lead` context rows)
+    int batch, max_len;
+    int lead;            // leading rows per sequence that are context only (streaming cnn cache); 0 offline
+    int d, ksize, causal;
+    const float* w;      // [d, ksize]
+    const float* bias;   // [d]
+    int norm_type;       // 0: LayerNorm over channels, 1: folded BatchNorm (scale/shift per channel)
+    const float* gamma; const float* beta; float eps;
+    const float* pad_vec;   // symmetric mode: value of frames in [len, pad_until) (GLU(bias)), or null
+    int pad_until;          // padded batch length (reference zero-masks *before* pointwise_conv1)
+    void* out; long long ldo; int split3;   // bf16 [rows_out, ldo]; out row = out_start[b] + t
+    const int* out_start;
+};
+int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream);
+
+// ---- CTC head + searches (ctc.cu, search.cu) ---------------------------------------------------
+// in-place log-softmax over V of logits [M, ldl] (+ optional blank penalty), plus per-row top-k.
+int ctc_logsoftmax_topk(float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty,
+                        int topk, float* topk_val, int* topk_idx, cudaStream_t stream);
+// greedy collapse: per sequence, frames [start, start+len) of top-1 ids (stride topk)
+int ctc_greedy(const int* topk_idx, int topk, const int* seq_start, const int* seq_len, int batch,
+               int blank_id, int* out_tokens, int out_stride, int* out_len, cudaStream_t stream);
+struct PrefixBeamArgs {
+    const float* topk_val; const int* topk_idx; int topk;   // [M, topk] per frame
+    const int* seq_start; const int* seq_len; int batch;    // frames of each utterance
+    int beam, blank_id, max_len;                            // max_len >= max seq_len
+    // outputs
+    int* out_tokens;     // [batch, beam, max_len]
+    int* out_times;      // [batch, beam, max_len]
+    int* out_lens;       // [batch, beam]
+    double* out_scores;  // [batch, beam]   log_add(s, ns)
+    int* out_nhyp;       // [batch]
+    void* workspace; size_t workspace_bytes;
+};
+size_t prefix_beam_workspace_bytes(int batch, int beam, int max_len);
+int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream);
+
+// ---- decoder helpers (decoder.cu) --------------------------------------------------------------
+// x[r] = emb[token[r]] * xscale + pe[pos[r]]
+int embed_tokens(const int* tokens, const int* pos, int R, int d, const float* emb /*[V,d]*/,
+                 const float* pe /*[maxlen,d]*/, float xscale, float* x, cudaStream_t stream);
+// tok_logp[r] = logits[r, target[r]] - logsumexp(logits[r, :V])   (target < 0 -> 0)
+int gather_logprob(const float* logits, long long ldl, int R, int V, const int* target, float* tok_logp,
+                   cudaStream_t stream);
+// per utterance rescoring combine (wenet search.py:421-452)
+struct RescoreArgs {
+    const float* l2r;  const float* r2l;  // [R] token log-probs, rows hyp-major, (len+1) per hyp
+    const int* hyp_row0;  const int* hyp_len;  // [n_hyp_total]
+    const int* utt_hyp0;  const int* utt_nhyp; int batch;  // hyps of utterance b: [utt_hyp0[b], +utt_nhyp[b])
+    const double* ctc_score;  // [n_hyp_total]
+    float ctc_weight, reverse_weight;
+    float* hyp_score;  // [n_hyp_total] final score
+    int* best;         // [batch] best hyp index within the utterance
+};
+int rescore_combine(const RescoreArgs& a, cudaStream_t stream);
+
+// small utility kernels (util.cu)
+int fill_row_pos(const int* seq_start, const int* seq_len, int batch, int pos_offset, int* row_pos,
+                 int max_len, cudaStream_t stream);
+
+}  // namespace wb

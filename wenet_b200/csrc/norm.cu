@@ -1,0 +1,151 @@
+// Row-wise LayerNorm (fp32 statistics, warp per row) with fused bf16 down-cast for the next GEMM's
+// A operand, plus small row utilities.
+// Replaces torch.nn.LayerNorm on the path: wenet/models/transformer/encoder_layer.py:169-183
+// (norm_ff_macaron / norm_mha / norm_conv / norm_ff / norm_final), encoder.py:111-112,176-177
+// (after_norm), decoder_layer.py norm1-3, decoder.py after_norm.
+// HBM-bound: reads 4*d B/row, writes 2*d (bf16) and/or 4*d (fp32) B/row.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wb {
+
+namespace {
+
+constexpr int LN_WARPS = 8;
+
+// VPL = float4 vectors per lane (d = 128 * VPL)
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_kernel(const float* __restrict__ x, long long ldx, int M, int d, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16,
+                 long long ld_bf16, int split3, float* out_f32, long long ld_f32) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * LN_WARPS + warp;
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        v[i] = xr[lane + 32 * i];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        v[i].x -= mean;
+        v[i].y -= mean;
+        v[i].z -= mean;
+        v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c4 = lane + 32 * i;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        float4 y;
+        y.x = v[i].x * rstd * g.x + b.x;
+        y.y = v[i].y * rstd * g.y + b.y;
+        y.z = v[i].z * rstd * g.z + b.z;
+        y.w = v[i].w * rstd * g.w + b.w;
+        if (out_f32) reinterpret_cast<float4*>(out_f32 + row * ld_f32)[c4] = y;
+        if (out_bf16) {
+            __nv_bfloat16* o = out_bf16 + row * ld_bf16 + 4 * c4;
+            const uint32_t p0 = pack_bf16x2(y.x, y.y), p1 = pack_bf16x2(y.z, y.w);
+            *reinterpret_cast<uint2*>(o) = make_uint2(p0, p1);
+            if (split3) {
+                const uint32_t l0 = pack_bf16x2(y.x - bf16_lo(p0), y.y - bf16_hi(p0));
+                const uint32_t l1 = pack_bf16x2(y.z - bf16_lo(p1), y.w - bf16_hi(p1));
+                *reinterpret_cast<uint2*>(o + d) = make_uint2(l0, l1);
+                *reinterpret_cast<uint2*>(o + 2 * d) = make_uint2(p0, p1);
+            }
+        }
+    }
+}
+
+__global__ void cast_rows_kernel(const float* __restrict__ x, long long ldx, int M, int d,
+                                 __nv_bfloat16* __restrict__ out, long long ldo, int split3) {
+    const long long n4 = (long long)M * (d / 4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / (d / 4);
+        const int c4 = (int)(i - row * (d / 4));
+        const float4 y = *reinterpret_cast<const float4*>(x + row * ldx + 4 * c4);
+        __nv_bfloat16* o = out + row * ldo + 4 * c4;
+        const uint32_t p0 = pack_bf16x2(y.x, y.y), p1 = pack_bf16x2(y.z, y.w);
+        *reinterpret_cast<uint2*>(o) = make_uint2(p0, p1);
+        if (split3) {
+            const uint32_t l0 = pack_bf16x2(y.x - bf16_lo(p0), y.y - bf16_hi(p0));
+            const uint32_t l1 = pack_bf16x2(y.z - bf16_lo(p1), y.w - bf16_hi(p1));
+            *reinterpret_cast<uint2*>(o + d) = make_uint2(l0, l1);
+            *reinterpret_cast<uint2*>(o + 2 * d) = make_uint2(p0, p1);
+        }
+    }
+}
+
+__global__ void fill_row_pos_kernel(const int* __restrict__ seq_start, const int* __restrict__ seq_len,
+                                    int pos_offset, int* __restrict__ row_pos) {
+    const int b = blockIdx.y;
+    const int s = seq_start[b], n = seq_len[b];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+        row_pos[s + t] = pos_offset + t;
+}
+
+}  // namespace
+
+int layernorm_rows(const float* x, long long ldx, int M, int d, const float* gamma, const float* beta,
+                   float eps, void* out_bf16, long long ld_bf16, int split3, float* out_f32, long long ld_f32,
+                   cudaStream_t stream) {
+    if (M <= 0) return WB_OK;
+    WB_REQUIRE(d % 128 == 0 && d <= 1024, WB_ERR_UNSUPPORTED, "layernorm: d=%d must be a multiple of 128, <= 1024", d);
+    WB_REQUIRE(ldx % 4 == 0 && ld_bf16 % 4 == 0 && ld_f32 % 4 == 0, WB_ERR_BAD_ARG, "layernorm: pitches must be %%4");
+    const int grid = ceil_div(M, LN_WARPS);
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+#define WB_LN(V)                                                                                          \
+    layernorm_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(x, ldx, M, d, gamma, beta, eps, ob, ld_bf16, \
+                                                            split3, out_f32, ld_f32)
+    switch (d / 128) {
+        case 1: WB_LN(1); break;
+        case 2: WB_LN(2); break;
+        case 3: WB_LN(3); break;
+        case 4: WB_LN(4); break;
+        case 5: WB_LN(5); break;
+        case 6: WB_LN(6); break;
+        case 8: WB_LN(8); break;
+        default:
+            set_last_error("layernorm: d=%d unsupported", d);
+            return WB_ERR_UNSUPPORTED;
+    }
+#undef WB_LN
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+int cast_rows_bf16(const float* x, long long ldx, int M, int d, void* out_bf16, long long ld_bf16, int split3,
+                   cudaStream_t stream) {
+    if (M <= 0) return WB_OK;
+    WB_REQUIRE(d % 4 == 0 && ldx % 4 == 0 && ld_bf16 % 4 == 0, WB_ERR_BAD_ARG, "cast_rows: d/pitches must be %%4");
+    const long long n4 = (long long)M * (d / 4);
+    const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    cast_rows_kernel<<<grid, 256, 0, stream>>>(x, ldx, M, d, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_bf16,
+                                               split3);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+int fill_row_pos(const int* seq_start, const int* seq_len, int batch, int pos_offset, int* row_pos, int max_len,
+                 cudaStream_t stream) {
+    if (batch <= 0 || max_len <= 0) return WB_OK;
+    dim3 grid(ceil_div(max_len, 256), batch);
+    fill_row_pos_kernel<<<grid, 256, 0, stream>>>(seq_start, seq_len, pos_offset, row_pos);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+}  // namespace wb

@@ -1,0 +1,362 @@
+// CTC prefix beam search on the GPU: one CTA per utterance, frames sequential, all (token, prefix)
+// pairs of a frame in parallel.  Bit-level restatement of the reference's host loop
+//   wenet/models/transformer/search.py:127-249 (ctc_prefix_beam_search, PrefixScore :64-106)
+//   wenet/utils/common.py:302-310 (log_add, Python float == IEEE double)
+// including: double-precision scores, Viterbi scores / token times (times_s / times_ns /
+// cur_token_prob rules of :166-219), dict insertion order as the tie-break of the stable
+// `sorted(..., reverse=True)` (:222-225), first-max-wins comparisons.
+//
+// Data structures
+//   * prefixes are nodes of a trie (parent, token) kept in a per-utterance pool in HBM; identity of
+//     a prefix inside a frame is (64-bit rolling hash, length, last token)
+//   * times lists are persistent (immutable) linked lists (prev, frame) in a second pool, so
+//     `list.copy()` / `append` / `[-1] = t` of the reference are O(1) pointer operations
+//   * the beam (<= 16 entries) and the <= beam + beam^2 candidates of a frame live in shared memory.
+// Each "unchanged prefix" candidate receives at most three updates per frame (blank, repeat,
+// extension-of-its-parent) — they are replayed in the reference's loop order (token-major,
+// prefix-minor) so every floating-point operation happens in the same order as on the host.
+#include "common.cuh"
+#include "kernels.h"
+#include <limits.h>
+#include <math_constants.h>
+
+namespace wb {
+
+namespace {
+
+constexpr int MAXB = 16;
+constexpr int NCAND = MAXB + MAXB * MAXB;
+constexpr int PB_THREADS = 128;
+
+__device__ __forceinline__ double neg_inf() { return -CUDART_INF; }
+
+__device__ __forceinline__ double log_add2(double a, double b) {
+    if (a == neg_inf() && b == neg_inf()) return neg_inf();
+    const double m = a > b ? a : b;
+    return m + log(exp(a - m) + exp(b - m));
+}
+
+__device__ __forceinline__ uint64_t mix_hash(uint64_t h, int tok) {
+    uint64_t z = h ^ ((uint64_t)(uint32_t)(tok + 1) * 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+struct Beam {
+    double s[MAXB], ns[MAXB], vs[MAXB], vns[MAXB];
+    double score[MAXB], vit[MAXB];
+    uint64_t hash[MAXB];
+    int len[MAXB], last[MAXB], node[MAXB], ts[MAXB], tns[MAXB], times[MAXB];
+    int n;
+};
+
+struct Cand {
+    double s[NCAND], ns[NCAND], vs[NCAND], vns[NCAND], total[NCAND];
+    uint64_t hash[NCAND];
+    int len[NCAND], last[NCAND];
+    int node[NCAND];       // existing trie node (unchanged prefix) or parent node (extension)
+    int new_tok[NCAND];    // >= 0: extension by this token (needs a new trie node)
+    int ts[NCAND];         // times_s head
+    int tns[NCAND];        // times_ns head if tns_new == 0, else prev pointer of the node to create
+    int tns_new[NCAND];    // 1: times_ns = list(tns) + [t]
+    int first[NCAND];      // first-touch sequence number == dict insertion order
+    int valid[NCAND];
+};
+
+struct PbDev {
+    const float* topk_val;
+    const int* topk_idx;
+    int topk;
+    const int* seq_start;
+    const int* seq_len;
+    int beam, blank_id, max_len;
+    int* out_tokens;
+    int* out_times;
+    int* out_lens;
+    double* out_scores;
+    int* out_nhyp;
+    int* pool;  // per utterance: [4][max_len * beam] ints: trie parent, trie token, time prev, time frame
+};
+
+__global__ void __launch_bounds__(PB_THREADS)
+prefix_beam_kernel(PbDev P) {
+    __shared__ Beam B;
+    __shared__ Cand C;
+    __shared__ float tk_val[MAXB];
+    __shared__ int tk_idx[MAXB];
+    __shared__ int dest[MAXB * MAXB];
+    __shared__ int rank_slot[MAXB];
+
+    const int utt = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int beam = P.beam;
+    const int T = P.seq_len[utt];
+    const long long f0 = P.seq_start[utt];
+    const long long pool_n = (long long)P.max_len * beam;
+    int* trie_parent = P.pool + (long long)utt * 4 * pool_n;
+    int* trie_tok = trie_parent + pool_n;
+    int* time_prev = trie_tok + pool_n;
+    int* time_t = time_prev + pool_n;
+
+    if (tid == 0) {
+        B.n = 1;
+        B.s[0] = 0.0;
+        B.ns[0] = neg_inf();
+        B.vs[0] = 0.0;
+        B.vns[0] = 0.0;
+        B.hash[0] = 0x1234567ull;
+        B.len[0] = 0;
+        B.last[0] = -1;
+        B.node[0] = -1;
+        B.ts[0] = -1;
+        B.tns[0] = -1;
+    }
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+        const int nb = B.n;
+        // ---- per-prefix derived quantities, frame top-k, candidate reset ----
+        if (tid < nb) {
+            B.score[tid] = log_add2(B.s[tid], B.ns[tid]);
+            const bool sb = B.vs[tid] > B.vns[tid];
+            B.vit[tid] = sb ? B.vs[tid] : B.vns[tid];
+            B.times[tid] = sb ? B.ts[tid] : B.tns[tid];
+        }
+        if (tid < beam) {
+            tk_val[tid] = P.topk_val[(f0 + t) * P.topk + tid];
+            tk_idx[tid] = P.topk_idx[(f0 + t) * P.topk + tid];
+        }
+        for (int c = tid; c < NCAND; c += PB_THREADS) C.valid[c] = 0;
+        __syncthreads();
+
+        // ---- extensions: one thread per (token ui, prefix pi) ----
+        for (int pr = tid; pr < beam * nb; pr += PB_THREADS) {
+            const int ui = pr / nb, pi = pr - ui * nb;
+            const int u = tk_idx[ui];
+            int d = -1;
+            if (u != P.blank_id) {
+                const uint64_t h = mix_hash(B.hash[pi], u);
+                const int ln = B.len[pi] + 1;
+                d = MAXB + ui * MAXB + pi;
+                for (int q = 0; q < nb; ++q)
+                    if (B.hash[q] == h && B.len[q] == ln && B.last[q] == u) d = q;
+                if (d >= MAXB) {
+                    const double prob = (double)tk_val[ui];
+                    const bool rep = (u == B.last[pi]);
+                    C.s[d] = neg_inf();
+                    C.vs[d] = neg_inf();
+                    C.ts[d] = -1;
+                    // log_add(-inf, x) == x exactly (exp(-inf)=0, log(1)=0)
+                    C.ns[d] = (rep ? B.s[pi] : B.score[pi]) + prob;
+                    C.vns[d] = (rep ? B.vs[pi] : B.vit[pi]) + prob;
+                    // reference: `if next.v_ns < y` with next.v_ns = -inf: false only when y == -inf
+                    if (C.vns[d] > neg_inf()) {
+                        C.tns[d] = rep ? B.ts[pi] : B.times[pi];
+                        C.tns_new[d] = 1;
+                    } else {
+                        C.vns[d] = neg_inf();
+                        C.tns[d] = -1;
+                        C.tns_new[d] = 0;
+                    }
+                    C.hash[d] = h;
+                    C.len[d] = ln;
+                    C.last[d] = u;
+                    C.node[d] = B.node[pi];
+                    C.new_tok[d] = u;
+                    C.first[d] = (ui * nb + pi) * 2 + (rep ? 1 : 0);
+                    C.total[d] = C.ns[d];  // log_add(-inf, ns)
+                    C.valid[d] = 1;
+                }
+            }
+            dest[ui * MAXB + pi] = d;
+        }
+        __syncthreads();
+
+        // ---- unchanged prefixes: thread q replays its (<= 3) updates in reference order ----
+        if (tid < nb) {
+            const int q = tid;
+            double s = neg_inf(), ns = neg_inf(), vs = neg_inf(), vns = neg_inf();
+            int ts = -1, tns = -1, tns_new = 0, first = INT_MAX, any = 0;
+            bool cur_set = false;
+            for (int ui = 0; ui < beam; ++ui) {
+                const int u = tk_idx[ui];
+                const double prob = (double)tk_val[ui];
+                if (u == P.blank_id) {
+                    s = log_add2(s, B.score[q] + prob);
+                    vs = B.vit[q] + prob;
+                    ts = B.times[q];
+                    first = min(first, (ui * nb + q) * 2);
+                    any = 1;
+                    continue;
+                }
+                if (u != B.last[q]) continue;
+                // events on ns in prefix order: extension from the parent prefix pe (dest == q),
+                // repeat from q itself
+                for (int pi = 0; pi < nb; ++pi) {
+                    if (pi == q) {
+                        ns = log_add2(ns, B.ns[q] + prob);
+                        const double y = B.vns[q] + prob;
+                        if (vns < y) {
+                            vns = y;
+                            if (!cur_set) {
+                                cur_set = true;
+                                // times_ns = prefix.times_ns.copy(); times_ns[-1] = t
+                                const int hd = B.tns[q];
+                                tns = (hd >= 0) ? time_prev[hd] : -1;
+                                tns_new = 1;
+                            }
+                        }
+                        first = min(first, (ui * nb + q) * 2);
+                        any = 1;
+                    } else if (dest[ui * MAXB + pi] == q) {
+                        const bool rep = (u == B.last[pi]);
+                        ns = log_add2(ns, (rep ? B.s[pi] : B.score[pi]) + prob);
+                        const double y = (rep ? B.vs[pi] : B.vit[pi]) + prob;
+                        if (vns < y) {
+                            vns = y;
+                            cur_set = true;
+                            tns = rep ? B.ts[pi] : B.times[pi];
+                            tns_new = 1;
+                        }
+                        first = min(first, (ui * nb + pi) * 2 + (rep ? 1 : 0));
+                        any = 1;
+                    }
+                }
+            }
+            if (any) {
+                C.s[q] = s;
+                C.ns[q] = ns;
+                C.vs[q] = vs;
+                C.vns[q] = vns;
+                C.ts[q] = ts;
+                C.tns[q] = tns;
+                C.tns_new[q] = tns_new;
+                C.hash[q] = B.hash[q];
+                C.len[q] = B.len[q];
+                C.last[q] = B.last[q];
+                C.node[q] = B.node[q];
+                C.new_tok[q] = -1;
+                C.first[q] = first;
+                C.total[q] = log_add2(s, ns);
+                C.valid[q] = 1;
+            }
+        }
+        __syncthreads();
+
+        // ---- second beam prune: stable sort by total desc == rank by (total, insertion order) ----
+        if (tid < MAXB) rank_slot[tid] = -1;
+        __syncthreads();
+        for (int c = tid; c < NCAND; c += PB_THREADS) {
+            if (!C.valid[c]) continue;
+            const double tc = C.total[c];
+            const int fc = C.first[c];
+            int rank = 0;
+            for (int j = 0; j < NCAND; ++j) {
+                if (j == c || !C.valid[j]) continue;
+                const double tj = C.total[j];
+                if (tj > tc || (tj == tc && C.first[j] < fc)) ++rank;
+            }
+            if (rank < beam) rank_slot[rank] = c;
+        }
+        __syncthreads();
+        if (tid < beam) {
+            const int c = rank_slot[tid];
+            if (c >= 0) {
+                const int r = tid;
+                const int pool_i = t * beam + r;
+                B.s[r] = C.s[c];
+                B.ns[r] = C.ns[c];
+                B.vs[r] = C.vs[c];
+                B.vns[r] = C.vns[c];
+                B.hash[r] = C.hash[c];
+                B.len[r] = C.len[c];
+                B.last[r] = C.last[c];
+                if (C.new_tok[c] >= 0) {
+                    trie_parent[pool_i] = C.node[c];
+                    trie_tok[pool_i] = C.new_tok[c];
+                    B.node[r] = pool_i;
+                } else {
+                    B.node[r] = C.node[c];
+                }
+                B.ts[r] = C.ts[c];
+                if (C.tns_new[c]) {
+                    time_prev[pool_i] = C.tns[c];
+                    time_t[pool_i] = t;
+                    B.tns[r] = pool_i;
+                } else {
+                    B.tns[r] = C.tns[c];
+                }
+            }
+        }
+        if (tid == 0) {
+            int n = 0;
+            for (int r = 0; r < beam; ++r)
+                if (rank_slot[r] >= 0) ++n;
+            B.n = n;
+        }
+        __syncthreads();
+        __threadfence_block();
+    }
+
+    // ---- emit n-best ----
+    const int nb = B.n;
+    if (tid == 0) P.out_nhyp[utt] = nb;
+    if (tid < nb) {
+        const int r = tid;
+        const long long o = ((long long)utt * beam + r) * P.max_len;
+        const int ln = B.len[r];
+        P.out_lens[utt * beam + r] = ln;
+        P.out_scores[utt * beam + r] = log_add2(B.s[r], B.ns[r]);
+        int node = B.node[r];
+        for (int k = ln - 1; k >= 0 && node >= 0; --k) {
+            P.out_tokens[o + k] = trie_tok[node];
+            node = trie_parent[node];
+        }
+        const int head = (B.vs[r] > B.vns[r]) ? B.ts[r] : B.tns[r];
+        int cnt = 0;
+        for (int h = head; h >= 0; h = time_prev[h]) ++cnt;
+        int k = cnt - 1;
+        for (int h = head; h >= 0 && k >= 0; h = time_prev[h], --k)
+            if (k < P.max_len) P.out_times[o + k] = time_t[h];
+        for (int z = cnt; z < ln; ++z) P.out_times[o + z] = -1;
+    } else if (tid < beam) {
+        P.out_lens[utt * beam + tid] = 0;
+        P.out_scores[utt * beam + tid] = neg_inf();
+    }
+}
+
+}  // namespace
+
+size_t prefix_beam_workspace_bytes(int batch, int beam, int max_len) {
+    return (size_t)batch * 4 * (size_t)max_len * beam * sizeof(int) + 256;
+}
+
+int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream) {
+    if (a.batch <= 0) return WB_OK;
+    WB_REQUIRE(a.beam >= 1 && a.beam <= MAXB, WB_ERR_UNSUPPORTED, "prefix beam search: beam %d not in [1,%d]", a.beam, MAXB);
+    WB_REQUIRE(a.topk >= a.beam, WB_ERR_BAD_ARG, "prefix beam search: topk %d < beam %d", a.topk, a.beam);
+    WB_REQUIRE(a.workspace_bytes >= prefix_beam_workspace_bytes(a.batch, a.beam, a.max_len), WB_ERR_WORKSPACE,
+               "prefix beam search: workspace too small");
+    PbDev P;
+    P.topk_val = a.topk_val;
+    P.topk_idx = a.topk_idx;
+    P.topk = a.topk;
+    P.seq_start = a.seq_start;
+    P.seq_len = a.seq_len;
+    P.beam = a.beam;
+    P.blank_id = a.blank_id;
+    P.max_len = a.max_len;
+    P.out_tokens = a.out_tokens;
+    P.out_times = a.out_times;
+    P.out_lens = a.out_lens;
+    P.out_scores = a.out_scores;
+    P.out_nhyp = a.out_nhyp;
+    P.pool = reinterpret_cast<int*>(a.workspace);
+    prefix_beam_kernel<<<a.batch, PB_THREADS, 0, stream>>>(P);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+}  // namespace wb

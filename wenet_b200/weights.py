@@ -1,0 +1,266 @@
+"""Weight packer: reference `state_dict` (key names of SURVEY.md section 8a) -> the tensors
+libwenet_b200.so expects (include/wenet_b200.h, wb_model_set_tensor).
+
+All transformations are layout-only or exact algebra on weights:
+  * q/k/v (and cross-attention k/v) projections fused into one [3d, d] ([2d, d]) GEMM
+  * Conv2d(d, d, 3, 2) weight -> im2col order (kh, kw, c_in); embed Linear columns permuted from the
+    reference's (c, f) flattening (subsampling.py:225) to the channels-last (f, c) this build uses
+  * pointwise_conv1 rows interleaved [16 value | 16 gate] so GLU is a GEMM epilogue
+  * eval BatchNorm folded to scale/shift; GLU(pointwise_conv1(0)) precomputed (see convmod.cu)
+  * linear_pos weight split into bf16 [hi | hi | lo] for the one-off bf16x3 position projection
+GEMM weights are stored as bf16 (the operand type of tcgen05.mma kind::f16); everything else fp32.
+"""
+import ctypes as C
+from typing import Dict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import WbModelConfig, check, cur_stream
+
+WB_F32, WB_BF16, WB_I32 = 0, 1, 2
+
+
+def interleave_glu(w: torch.Tensor, b: torch.Tensor):
+    """[value rows (d) | gate rows (d)] -> blocks of 32 rows = 16 value rows + their 16 gate rows."""
+    two_d = w.shape[0]
+    d = two_d // 2
+    assert d % 16 == 0
+    idx = []
+    for g in range(d // 16):
+        idx += list(range(16 * g, 16 * g + 16)) + list(range(d + 16 * g, d + 16 * g + 16))
+    idx = torch.tensor(idx, dtype=torch.long, device=w.device)
+    return w.index_select(0, idx), b.index_select(0, idx)
+
+
+def split3_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [N, K] -> bf16 [N, 3K] = [hi | hi | lo]; pairs with activations packed [hi | lo | hi]."""
+    w = w.float()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
+
+
+def sinusoid_pe(max_len: int, d: int) -> torch.Tensor:
+    """wenet/models/transformer/embedding.py:50-59"""
+    import math
+    pe = torch.zeros(max_len, d)
+    pos = torch.arange(0, max_len, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+class ModelSpec:
+    """The subset of the reference's train.yaml this build understands; anything else raises at
+    construction (no silent fallbacks — SURVEY.md section 8b 'unsupported-config policy')."""
+
+    def __init__(self, configs: dict):
+        enc = dict(configs.get("encoder_conf", {}))
+        if configs.get("encoder", "conformer") != "conformer":
+            raise NotImplementedError("encoder '%s' is outside the implemented set (conformer)" % configs.get("encoder"))
+
+        def need(key, allowed, default):
+            v = enc.get(key, default)
+            if v not in allowed:
+                raise NotImplementedError("encoder_conf.%s=%r is outside the implemented set %r" % (key, v, allowed))
+            return v
+
+        need("input_layer", ("conv2d",), "conv2d")
+        need("pos_enc_layer_type", ("rel_pos",), "rel_pos")
+        need("selfattention_layer_type", ("rel_selfattn",), "rel_selfattn")
+        need("activation_type", ("swish",), "swish")
+        need("normalize_before", (True,), True)
+        need("use_cnn_module", (True,), True)
+        need("macaron_style", (True,), True)
+        need("layer_norm_type", ("layer_norm",), "layer_norm")
+        need("mlp_type", ("position_wise_feed_forward",), "position_wise_feed_forward")
+        for k in ("n_kv_head", "head_dim"):
+            if enc.get(k) is not None:
+                raise NotImplementedError("encoder_conf.%s is not supported" % k)
+        if enc.get("use_sdpa", False):
+            pass  # numerically the same attention; the flag only selects a torch code path
+        self.input_dim = int(configs["input_dim"])
+        self.vocab = int(configs["output_dim"])
+        self.d_model = int(enc.get("output_size", 256))
+        self.heads = int(enc.get("attention_heads", 4))
+        self.ffn_dim = int(enc.get("linear_units", 2048))
+        self.enc_layers = int(enc.get("num_blocks", 6))
+        self.cnn_kernel = int(enc.get("cnn_module_kernel", 15))
+        self.cnn_causal = bool(enc.get("causal", False))
+        self.cnn_norm = need("cnn_module_norm", ("batch_norm", "layer_norm"), "batch_norm")
+        self.use_dynamic_chunk = bool(enc.get("use_dynamic_chunk", False))
+        self.static_chunk_size = int(enc.get("static_chunk_size", 0))
+        self.ln_eps = float(enc.get("norm_eps", 1e-5))
+        if self.d_model != self.heads * 64:
+            raise NotImplementedError("attention head size must be 64 (d_model=%d heads=%d)" % (self.d_model, self.heads))
+        dec_type = configs.get("decoder", "bitransformer")
+        dec = dict(configs.get("decoder_conf", {}))
+        if dec_type not in ("transformer", "bitransformer"):
+            raise NotImplementedError("decoder '%s' is outside the implemented set" % dec_type)
+        self.bidirectional = dec_type == "bitransformer"
+        self.dec_layers = int(dec.get("num_blocks", 6))
+        self.rdec_layers = int(dec.get("r_num_blocks", 0)) if self.bidirectional else 0
+        self.dec_heads = int(dec.get("attention_heads", 4))
+        self.dec_ffn_dim = int(dec.get("linear_units", 2048))
+        if dec.get("activation_type", "relu") != "relu" or dec.get("input_layer", "embed") != "embed" \
+                or not dec.get("normalize_before", True) or dec.get("tie_word_embedding", False):
+            raise NotImplementedError("decoder_conf outside the implemented set (relu / embed / pre-norm / untied)")
+        if self.d_model != self.dec_heads * 64:
+            raise NotImplementedError("decoder head size must be 64")
+        mc = dict(configs.get("model_conf", {}))
+        self.reverse_weight = float(mc.get("reverse_weight", 0.0))
+        self.ctc_weight = float(mc.get("ctc_weight", 0.5))
+        self.max_pos = 5000
+        self.has_cmvn = configs.get("cmvn", None) is not None
+
+
+def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Returns {lib tensor name: CPU tensor (fp32 or bf16)}."""
+    d, F1 = spec.d_model, (spec.input_dim - 3) // 2 + 1
+    F2 = (F1 - 3) // 2 + 1
+    out: Dict[str, torch.Tensor] = {}
+
+    def f32(t):
+        return t.detach().float().contiguous().cpu()
+
+    def bf(t):
+        return t.detach().float().to(torch.bfloat16).contiguous().cpu()
+
+    def lin(dst, src):
+        out[dst + ".w"] = bf(sd[src + ".weight"])
+        out[dst + ".b"] = f32(sd[src + ".bias"])
+
+    def norm(dst, src):
+        out[dst + ".g"] = f32(sd[src + ".weight"])
+        out[dst + ".b"] = f32(sd[src + ".bias"])
+
+    if spec.has_cmvn:
+        out["cmvn.mean"] = f32(sd["encoder.global_cmvn.mean"])
+        out["cmvn.istd"] = f32(sd["encoder.global_cmvn.istd"])
+    w1 = sd["encoder.embed.conv.0.weight"]          # (d, 1, 3, 3)
+    out["embed.conv1.w"] = f32(w1.reshape(d, 9).t())
+    out["embed.conv1.b"] = f32(sd["encoder.embed.conv.0.bias"])
+    w2 = sd["encoder.embed.conv.2.weight"]          # (d, d, 3, 3) -> (d, kh, kw, c_in)
+    out["embed.conv2.w"] = bf(w2.permute(0, 2, 3, 1).reshape(d, 9 * d))
+    out["embed.conv2.b"] = f32(sd["encoder.embed.conv.2.bias"])
+    wo = sd["encoder.embed.out.0.weight"]           # (d, c * F2 + f) -> (d, f * d + c)
+    assert wo.shape[1] == d * F2, "embed.out expects %d input features, got %d" % (d * F2, wo.shape[1])
+    out["embed.out.w"] = bf(wo.view(d, d, F2).permute(0, 2, 1).reshape(d, F2 * d))
+    out["embed.out.b"] = f32(sd["encoder.embed.out.0.bias"])
+    pe = sd.get("encoder.embed.pos_enc.pe")
+    pe = sinusoid_pe(spec.max_pos, d) if pe is None else pe.reshape(-1, d)[:spec.max_pos]
+    out["embed.pe"] = f32(pe)
+    for i in range(spec.enc_layers):
+        s, t = "encoder.encoders.%d" % i, "enc.%d" % i
+        for n in ("norm_ff_macaron", "norm_mha", "norm_conv", "norm_ff", "norm_final"):
+            norm(t + "." + n, s + "." + n)
+        lin(t + ".ffm.w1", s + ".feed_forward_macaron.w_1")
+        lin(t + ".ffm.w2", s + ".feed_forward_macaron.w_2")
+        lin(t + ".ff.w1", s + ".feed_forward.w_1")
+        lin(t + ".ff.w2", s + ".feed_forward.w_2")
+        a = s + ".self_attn"
+        out[t + ".att.qkv.w"] = bf(torch.cat([sd[a + ".linear_q.weight"], sd[a + ".linear_k.weight"],
+                                              sd[a + ".linear_v.weight"]], 0))
+        out[t + ".att.qkv.b"] = f32(torch.cat([sd[a + ".linear_q.bias"], sd[a + ".linear_k.bias"],
+                                               sd[a + ".linear_v.bias"]], 0))
+        lin(t + ".att.out", a + ".linear_out")
+        out[t + ".att.pos.w3"] = split3_weight(sd[a + ".linear_pos.weight"]).cpu()
+        out[t + ".att.pos_u"] = f32(sd[a + ".pos_bias_u"].reshape(-1))
+        out[t + ".att.pos_v"] = f32(sd[a + ".pos_bias_v"].reshape(-1))
+        c = s + ".conv_module"
+        pw1_w = sd[c + ".pointwise_conv1.weight"].reshape(2 * d, d)
+        pw1_b = sd[c + ".pointwise_conv1.bias"]
+        wi, bi = interleave_glu(pw1_w, pw1_b)
+        out[t + ".conv.pw1.w"], out[t + ".conv.pw1.b"] = bf(wi), f32(bi)
+        out[t + ".conv.pad_vec"] = f32(pw1_b[:d].float() * torch.sigmoid(pw1_b[d:].float()))
+        out[t + ".conv.dw.w"] = f32(sd[c + ".depthwise_conv.weight"].reshape(d, spec.cnn_kernel))
+        out[t + ".conv.dw.b"] = f32(sd[c + ".depthwise_conv.bias"])
+        if spec.cnn_norm == "layer_norm":
+            norm(t + ".conv.norm", c + ".norm")
+        else:
+            scale = sd[c + ".norm.weight"].float() / torch.sqrt(sd[c + ".norm.running_var"].float() + spec.ln_eps)
+            out[t + ".conv.norm.g"] = f32(scale)
+            out[t + ".conv.norm.b"] = f32(sd[c + ".norm.bias"].float() - sd[c + ".norm.running_mean"].float() * scale)
+        out[t + ".conv.pw2.w"] = bf(sd[c + ".pointwise_conv2.weight"].reshape(d, d))
+        out[t + ".conv.pw2.b"] = f32(sd[c + ".pointwise_conv2.bias"])
+    norm("after_norm", "encoder.after_norm")
+    lin("ctc", "ctc.ctc_lo")
+
+    def decoder(dst, src, n_layers):
+        out[dst + ".emb"] = f32(sd[src + ".embed.0.weight"])
+        for i in range(n_layers):
+            s, t = "%s.decoders.%d" % (src, i), "%s.%d" % (dst, i)
+            for n in ("norm1", "norm2", "norm3"):
+                norm(t + "." + n, s + "." + n)
+            a = s + ".self_attn"
+            out[t + ".sa.qkv.w"] = bf(torch.cat([sd[a + ".linear_q.weight"], sd[a + ".linear_k.weight"],
+                                                 sd[a + ".linear_v.weight"]], 0))
+            out[t + ".sa.qkv.b"] = f32(torch.cat([sd[a + ".linear_q.bias"], sd[a + ".linear_k.bias"],
+                                                  sd[a + ".linear_v.bias"]], 0))
+            lin(t + ".sa.out", a + ".linear_out")
+            a = s + ".src_attn"
+            lin(t + ".ca.q", a + ".linear_q")
+            out[t + ".ca.kv.w"] = bf(torch.cat([sd[a + ".linear_k.weight"], sd[a + ".linear_v.weight"]], 0))
+            out[t + ".ca.kv.b"] = f32(torch.cat([sd[a + ".linear_k.bias"], sd[a + ".linear_v.bias"]], 0))
+            lin(t + ".ca.out", a + ".linear_out")
+            lin(t + ".ff.w1", s + ".feed_forward.w_1")
+            lin(t + ".ff.w2", s + ".feed_forward.w_2")
+        norm(dst + ".after_norm", src + ".after_norm")
+        lin(dst + ".out", src + ".output_layer")
+
+    has_dec = any(k.startswith("decoder.") for k in sd)
+    if has_dec:
+        if spec.bidirectional:
+            decoder("dec.left", "decoder.left_decoder", spec.dec_layers)
+            if spec.rdec_layers > 0:
+                decoder("dec.right", "decoder.right_decoder", spec.rdec_layers)
+        else:
+            decoder("dec.left", "decoder", spec.dec_layers)
+    return out
+
+
+class DeviceModel:
+    """Owns a wb_model handle (weights resident in HBM)."""
+
+    def __init__(self, spec: ModelSpec, sd: Dict[str, torch.Tensor], with_decoder: bool = True):
+        self.spec = spec
+        lib = _lib.load()
+        has_dec = with_decoder and any(k.startswith("decoder.") for k in sd)
+        cfg = WbModelConfig(
+            input_dim=spec.input_dim, d_model=spec.d_model, heads=spec.heads, ffn_dim=spec.ffn_dim,
+            enc_layers=spec.enc_layers, cnn_kernel=spec.cnn_kernel, cnn_causal=int(spec.cnn_causal),
+            cnn_norm=0 if spec.cnn_norm == "layer_norm" else 1, vocab=spec.vocab,
+            dec_layers=spec.dec_layers if has_dec else 0, rdec_layers=spec.rdec_layers if has_dec else 0,
+            dec_heads=spec.dec_heads, dec_ffn_dim=spec.dec_ffn_dim, max_pos=spec.max_pos,
+            has_cmvn=int(spec.has_cmvn), precise=0, ln_eps=spec.ln_eps)
+        self._h = C.c_void_p()
+        check(lib.wb_model_create(C.byref(self._h), C.byref(cfg)), "wb_model_create")
+        packed = pack_state_dict(spec, sd)
+        for name, t in packed.items():
+            if not has_dec and name.startswith("dec."):
+                continue
+            if t.dtype == torch.bfloat16:
+                arr = t.view(torch.int16).numpy()
+                dt = WB_BF16
+            else:
+                arr = t.numpy()
+                dt = WB_F32
+            arr = np.ascontiguousarray(arr)
+            check(lib.wb_model_set_tensor(self._h, name.encode(), C.c_void_p(arr.ctypes.data), dt, arr.size),
+                  "wb_model_set_tensor(%s)" % name)
+        check(lib.wb_model_finalize(self._h, cur_stream()), "wb_model_finalize")
+        self.has_decoder = has_dec
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().wb_model_destroy(self._h)
+        except Exception:
+            pass
