@@ -1,0 +1,475 @@
+"""Host-side mirror of the reference's model API for the hot path:
+
+    B200ASRModel.decode(methods, speech, speech_lengths, beam_size, ...) -> Dict[str, List[DecodeResult]]
+        == wenet/models/transformer/asr_model.py:267-343 (ASRModel.decode)
+    B200ASRModel.encoder(xs, xs_lens, decoding_chunk_size, num_decoding_left_chunks) -> (xs, masks)
+        == wenet/models/transformer/encoder.py:122-181
+    B200ASRModel.encoder.forward_chunk(...) / forward_chunk_by_chunk(...)   == encoder.py:204-362
+    B200ASRModel.ctc_logprobs / ctc.log_softmax                             == asr_model.py:254-265
+    B200ASRModel.forward_attention_decoder(hyps, hyps_lens, encoder_out, reverse_weight)
+        == asr_model.py:453-547
+
+Same argument names, defaults and return types; every stage is a call into libwenet_b200.so with raw
+device pointers (torch only allocates the buffers and supplies the stream).  No CPU fallback: all
+tensors must live on a CUDA device.
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+from .search import DecodeResult
+from .weights import DeviceModel, ModelSpec
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+class _EncOut:
+    """Packed encoder output of one batch (rows of valid frames back to back)."""
+    __slots__ = ("f32", "bf16", "seq_start", "seq_len", "lens_host", "starts_host", "rows", "max_len", "dump")
+
+
+class _Subsampling:
+    subsampling_rate = 4   # wenet/models/transformer/subsampling.py:196
+    right_context = 6      # :197
+
+
+class B200CTC:
+    """model.ctc with the one method the decode path uses (ctc.py:73-81)."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def log_softmax(self, hs_pad: torch.Tensor) -> torch.Tensor:
+        return self._o.ctc_logprobs(hs_pad)
+
+
+class B200ConformerEncoder:
+    """Drop-in for ConformerEncoder's inference methods."""
+
+    def __init__(self, owner):
+        self._o = owner
+        self.embed = _Subsampling()
+        spec = owner.spec
+        self.use_dynamic_chunk = spec.use_dynamic_chunk
+        self.static_chunk_size = spec.static_chunk_size
+
+    def output_size(self) -> int:
+        return self._o.spec.d_model
+
+    # encoder.py:122-181
+    def forward(self, xs: torch.Tensor, xs_lens: torch.Tensor, decoding_chunk_size: int = 0,
+                num_decoding_left_chunks: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
+        eo = self._o._encode(xs, xs_lens, decoding_chunk_size, num_decoding_left_chunks)
+        return self._o._unpack(eo, xs.size(1))
+
+    __call__ = forward
+
+    def forward_chunk(self, xs, offset, required_cache_size, att_cache=None, cnn_cache=None, att_mask=None):
+        return self._o._forward_chunk(xs, offset, required_cache_size, att_cache, cnn_cache)
+
+    # encoder.py:302-362
+    def forward_chunk_by_chunk(self, xs: torch.Tensor, decoding_chunk_size: int,
+                               num_decoding_left_chunks: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
+        assert decoding_chunk_size > 0
+        assert self.static_chunk_size > 0 or self.use_dynamic_chunk
+        subsampling = self.embed.subsampling_rate
+        context = self.embed.right_context + 1
+        stride = subsampling * decoding_chunk_size
+        decoding_window = (decoding_chunk_size - 1) * subsampling + context
+        num_frames = xs.size(1)
+        att_cache = torch.zeros((0, 0, 0, 0), device=xs.device)
+        cnn_cache = torch.zeros((0, 0, 0, 0), device=xs.device)
+        outputs = []
+        offset = 0
+        required_cache_size = decoding_chunk_size * num_decoding_left_chunks
+        for cur in range(0, num_frames - context + 1, stride):
+            end = min(cur + decoding_window, num_frames)
+            chunk_xs = xs[:, cur:end, :]
+            (y, att_cache, cnn_cache) = self.forward_chunk(chunk_xs, offset, required_cache_size, att_cache, cnn_cache)
+            outputs.append(y)
+            offset += y.size(1)
+        ys = torch.cat(outputs, 1)
+        masks = torch.ones((1, 1, ys.size(1)), device=ys.device, dtype=torch.bool)
+        return ys, masks
+
+
+class B200ASRModel:
+    """U2 / U2++ model (ConformerEncoder + CTC + (Bi)TransformerDecoder) on libwenet_b200.so."""
+
+    def __init__(self, configs: dict, state_dict: Dict[str, torch.Tensor], device=None, with_decoder: bool = True):
+        if not torch.cuda.is_available():
+            raise _lib.WbError("B200ASRModel needs a CUDA device (there is no CPU fallback)")
+        self.spec = ModelSpec(configs)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(self.device):
+            self.dm = DeviceModel(self.spec, state_dict, with_decoder=with_decoder)
+        self.vocab_size = self.spec.vocab
+        self.sos = self.vocab_size - 1      # asr_model.py:62-64
+        self.eos = self.vocab_size - 1
+        self.ignore_id = -1
+        self.reverse_weight = self.spec.reverse_weight
+        self.ctc_weight = self.spec.ctc_weight
+        self.default_decode_method = "attention_rescoring"
+        self.encoder = B200ConformerEncoder(self)
+        self.ctc = B200CTC(self)
+        self._lib = _lib.load()
+        self._ws = None
+        self._ws2 = None
+        self.keep_layer_dump = False
+
+    # ----- reference jit-export style accessors (asr_model.py:360-450) -----
+    def subsampling_rate(self) -> int:
+        return 4
+
+    def right_context(self) -> int:
+        return 6
+
+    def sos_symbol(self) -> int:
+        return self.sos
+
+    def eos_symbol(self) -> int:
+        return self.eos
+
+    def is_bidirectional_decoder(self) -> bool:
+        return self.spec.bidirectional and self.dm.has_decoder
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @classmethod
+    def from_reference(cls, model, configs: dict, device=None):
+        """Wrap a loaded reference ASRModel (same weights, same results, B200 kernels)."""
+        return cls(configs, {k: v.detach().cpu() for k, v in model.state_dict().items()}, device=device)
+
+    # ----- buffers -----
+    def _workspace(self, nbytes: int, which: int = 0) -> torch.Tensor:
+        cur = self._ws if which == 0 else self._ws2
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=self.device)
+            if which == 0:
+                self._ws = cur
+            else:
+                self._ws2 = cur
+        return cur
+
+    # ----- encoder -----
+    def _encode(self, speech: torch.Tensor, speech_lengths: torch.Tensor, decoding_chunk_size: int,
+                num_decoding_left_chunks: int) -> _EncOut:
+        if not speech.is_cuda:
+            raise _lib.WbError("speech must be a CUDA tensor (no CPU fallback)")
+        if decoding_chunk_size == 0:
+            raise NotImplementedError("decoding_chunk_size=0 selects the random *training* chunk "
+                                      "(wenet/utils/mask.py:167-180); pass <0 (full) or >0")
+        if not (self.spec.use_dynamic_chunk or self.spec.static_chunk_size > 0):
+            decoding_chunk_size = -1  # add_optional_chunk_mask ignores the argument (mask.py:193-195)
+        elif not self.spec.use_dynamic_chunk and self.spec.static_chunk_size > 0:
+            decoding_chunk_size = self.spec.static_chunk_size
+        x = speech.to(torch.float32).contiguous()
+        B, T, D = x.shape
+        assert D == self.spec.input_dim
+        lens_host = _i32(speech_lengths.detach().cpu().numpy())
+        assert int(lens_host.max()) <= T
+        lib = self._lib
+        rows = int(lib.wb_encoder_out_rows(B, ptr(lens_host)))
+        d = self.spec.d_model
+        eo = _EncOut()
+        eo.rows = rows
+        eo.f32 = torch.empty(max(rows, 1), d, device=self.device, dtype=torch.float32)
+        eo.bf16 = torch.empty(max(rows, 1), d, device=self.device, dtype=torch.bfloat16)
+        eo.seq_start = torch.zeros(B, device=self.device, dtype=torch.int32)
+        eo.seq_len = torch.zeros(B, device=self.device, dtype=torch.int32)
+        tp = np.where(lens_host >= 7, ((lens_host - 1) // 2 - 1) // 2, 0).astype(np.int32)
+        eo.lens_host = tp
+        eo.starts_host = np.concatenate([[0], np.cumsum(tp)[:-1]]).astype(np.int32)
+        eo.max_len = int(tp.max()) if B else 0
+        eo.dump = None
+        if rows == 0:
+            return eo
+        wsb = lib.wb_encoder_workspace_bytes(self.dm.handle, B, ptr(lens_host))
+        ws = self._workspace(wsb)
+        dump = None
+        if self.keep_layer_dump:
+            dump = torch.empty(self.spec.enc_layers + 1, rows, d, device=self.device, dtype=torch.float32)
+            eo.dump = dump
+        pad_to = ((T - 1) // 2 - 1) // 2
+        with torch.cuda.device(self.device):
+            check(lib.wb_encoder_forward(self.dm.handle, ptr(x), x.stride(0), ptr(lens_host), B,
+                                         int(decoding_chunk_size), int(num_decoding_left_chunks), int(pad_to),
+                                         ptr(eo.f32), ptr(eo.bf16), ptr(eo.seq_start), ptr(eo.seq_len), ptr(dump),
+                                         ptr(ws), ws.numel(), cur_stream()), "wb_encoder_forward")
+        return eo
+
+    def _unpack(self, eo: _EncOut, T_in: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        B = eo.seq_start.numel()
+        Tp = ((T_in - 1) // 2 - 1) // 2 if T_in >= 7 else 0
+        d = self.spec.d_model
+        out = torch.empty(B, Tp, d, device=self.device, dtype=torch.float32)
+        if Tp > 0:
+            check(self._lib.wb_unpack_rows(ptr(eo.f32), ptr(eo.seq_start), ptr(eo.seq_len), B, Tp, d, ptr(out), Tp,
+                                           cur_stream()), "wb_unpack_rows")
+        masks = (torch.arange(Tp, device=self.device).unsqueeze(0) < eo.seq_len.unsqueeze(1)).unsqueeze(1)
+        return out, masks
+
+    def _forward_encoder(self, speech, speech_lengths, decoding_chunk_size=-1, num_decoding_left_chunks=-1,
+                         simulate_streaming=False):
+        # asr_model.py:216-239
+        if simulate_streaming and decoding_chunk_size > 0:
+            return self.encoder.forward_chunk_by_chunk(speech, decoding_chunk_size, num_decoding_left_chunks)
+        return self.encoder.forward(speech, speech_lengths, decoding_chunk_size, num_decoding_left_chunks)
+
+    def _forward_chunk(self, xs, offset, required_cache_size, att_cache, cnn_cache):
+        if not xs.is_cuda:
+            raise _lib.WbError("xs must be a CUDA tensor (no CPU fallback)")
+        assert xs.size(0) == 1
+        spec = self.spec
+        lib = self._lib
+        x = xs[0].to(torch.float32).contiguous()
+        T = x.size(0)
+        L, H, d, K = spec.enc_layers, spec.heads, spec.d_model, spec.cnn_kernel
+        cache_t1 = att_cache.size(2) if (att_cache is not None and att_cache.numel() > 0) else 0
+        chunk = ((T - 1) // 2 - 1) // 2
+        key_size = cache_t1 + chunk
+        if required_cache_size < 0:
+            nxt = 0
+        elif required_cache_size == 0:
+            nxt = key_size
+        else:
+            nxt = max(key_size - required_cache_size, 0)
+        y = torch.empty(1, chunk, d, device=self.device, dtype=torch.float32)
+        r_att = torch.empty(L, H, key_size - nxt, 128, device=self.device, dtype=torch.float32)
+        r_cnn = torch.empty(L, 1, d, max(K - 1, 0), device=self.device, dtype=torch.float32) if spec.cnn_causal \
+            else torch.zeros(0, 0, 0, 0, device=self.device)
+        ac = att_cache.to(torch.float32).contiguous() if cache_t1 > 0 else None
+        cc = cnn_cache.to(torch.float32).contiguous() if (cnn_cache is not None and cnn_cache.numel() > 0) else None
+        wsb = lib.wb_encoder_chunk_workspace_bytes(self.dm.handle, T, cache_t1)
+        ws = self._workspace(wsb)
+        oc, on = C.c_int(0), C.c_int(0)
+        check(lib.wb_encoder_forward_chunk(self.dm.handle, ptr(x), T, int(offset), int(required_cache_size), ptr(ac),
+                                           cache_t1, ptr(cc), ptr(y), ptr(r_att), ptr(r_cnn) if spec.cnn_causal else None,
+                                           C.byref(oc), C.byref(on), ptr(ws), ws.numel(), cur_stream()),
+              "wb_encoder_forward_chunk")
+        return y, r_att, r_cnn
+
+    # ----- CTC -----
+    def _ctc(self, eo: _EncOut, topk: int, blank_id: int, blank_penalty: float):
+        V = self.spec.vocab
+        ldl = (V + 7) // 8 * 8
+        rows = max(eo.rows, 1)
+        logp = torch.empty(rows, ldl, device=self.device, dtype=torch.float32)
+        k = max(int(topk), 1)
+        tv = torch.empty(rows, k, device=self.device, dtype=torch.float32)
+        ti = torch.empty(rows, k, device=self.device, dtype=torch.int32)
+        if eo.rows > 0:
+            check(self._lib.wb_ctc_logprobs(self.dm.handle, ptr(eo.bf16), eo.rows, int(blank_id), float(blank_penalty),
+                                            ptr(logp), ldl, k, ptr(tv), ptr(ti), cur_stream()), "wb_ctc_logprobs")
+        return logp, tv, ti
+
+    def ctc_logprobs(self, encoder_out: torch.Tensor, blank_penalty: float = 0.0, blank_id: int = 0) -> torch.Tensor:
+        """asr_model.py:254-265 on a padded (B, T', d) tensor (API parity; decode() uses the packed path)."""
+        if not encoder_out.is_cuda:
+            raise _lib.WbError("encoder_out must be a CUDA tensor (no CPU fallback)")
+        B, Tp, d = encoder_out.shape
+        eo = _EncOut()
+        eo.rows = B * Tp
+        eo.bf16 = encoder_out.reshape(B * Tp, d).to(torch.bfloat16).contiguous()
+        logp, _, _ = self._ctc(eo, 1, blank_id, blank_penalty)
+        return logp[:, :self.spec.vocab].reshape(B, Tp, self.spec.vocab)
+
+    # ----- decode (asr_model.py:267-343) -----
+    def decode(self, methods: List[str], speech: torch.Tensor, speech_lengths: torch.Tensor, beam_size: int = 1,
+               decoding_chunk_size: int = -1, num_decoding_left_chunks: int = -1, ctc_weight: float = 0.0,
+               simulate_streaming: bool = False, reverse_weight: float = 0.0, context_graph=None,
+               blank_id: int = 0, blank_penalty: float = 0.0, length_penalty: float = 0.0,
+               infos: Dict[str, List[str]] = None) -> Dict[str, List[DecodeResult]]:
+        assert speech.shape[0] == speech_lengths.shape[0]
+        assert decoding_chunk_size != 0
+        if context_graph is not None:
+            raise NotImplementedError("context_graph biasing is not implemented (SURVEY.md section 8f #3)")
+        if "attention" in methods:
+            raise NotImplementedError("autoregressive 'attention' decoding is not implemented (section 8f #1)")
+        with torch.cuda.device(self.device):
+            if simulate_streaming and decoding_chunk_size > 0:
+                ys, _ = self.encoder.forward_chunk_by_chunk(speech, decoding_chunk_size, num_decoding_left_chunks)
+                eo = self._pack_padded(ys)
+            else:
+                eo = self._encode(speech, speech_lengths, decoding_chunk_size, num_decoding_left_chunks)
+            need_beam = ("ctc_prefix_beam_search" in methods) or ("attention_rescoring" in methods)
+            topk = beam_size if need_beam else 1
+            logp, tv, ti = self._ctc(eo, topk, blank_id, blank_penalty)
+            results = {}
+            if "ctc_greedy_search" in methods:
+                results["ctc_greedy_search"] = self._greedy(eo, ti, blank_id)
+            beam_out = None
+            if need_beam:
+                beam_out = self._prefix_beam(eo, tv, ti, beam_size, blank_id)
+                if "ctc_prefix_beam_search" in methods:
+                    results["ctc_prefix_beam_search"] = beam_out
+            if "attention_rescoring" in methods:
+                results["attention_rescoring"] = self._rescore(eo, beam_out, ctc_weight, reverse_weight)
+        return results
+
+    def _pack_padded(self, ys: torch.Tensor) -> _EncOut:
+        B, Tp, d = ys.shape
+        eo = _EncOut()
+        eo.rows = B * Tp
+        eo.f32 = ys.reshape(B * Tp, d).contiguous()
+        eo.bf16 = eo.f32.to(torch.bfloat16)
+        eo.lens_host = np.full(B, Tp, dtype=np.int32)
+        eo.starts_host = (np.arange(B) * Tp).astype(np.int32)
+        eo.seq_start = torch.from_numpy(eo.starts_host).to(self.device)
+        eo.seq_len = torch.from_numpy(eo.lens_host).to(self.device)
+        eo.max_len = Tp
+        eo.dump = None
+        return eo
+
+    def _greedy(self, eo: _EncOut, ti: torch.Tensor, blank_id: int) -> List[DecodeResult]:
+        B = eo.seq_start.numel()
+        stride = max(eo.max_len, 1)
+        toks = torch.zeros(B, stride, device=self.device, dtype=torch.int32)
+        lens = torch.zeros(B, device=self.device, dtype=torch.int32)
+        check(self._lib.wb_ctc_greedy_search(ptr(ti), ti.stride(0), ptr(eo.seq_start), ptr(eo.seq_len), B, int(blank_id),
+                                             ptr(toks), stride, ptr(lens), cur_stream()), "wb_ctc_greedy_search")
+        th, lh = toks.cpu().numpy(), lens.cpu().numpy()
+        return [DecodeResult(th[b, :lh[b]].tolist()) for b in range(B)]
+
+    def _prefix_beam(self, eo: _EncOut, tv, ti, beam_size: int, blank_id: int) -> List[DecodeResult]:
+        B = eo.seq_start.numel()
+        max_len = max(eo.max_len, 1)
+        lib = self._lib
+        toks = torch.zeros(B, beam_size, max_len, device=self.device, dtype=torch.int32)
+        times = torch.zeros(B, beam_size, max_len, device=self.device, dtype=torch.int32)
+        lens = torch.zeros(B, beam_size, device=self.device, dtype=torch.int32)
+        scores = torch.zeros(B, beam_size, device=self.device, dtype=torch.float64)
+        nhyp = torch.zeros(B, device=self.device, dtype=torch.int32)
+        wsb = lib.wb_prefix_beam_workspace_bytes(B, beam_size, max_len)
+        ws = self._workspace(wsb, 1)
+        check(lib.wb_ctc_prefix_beam_search(ptr(tv), ptr(ti), tv.stride(0), ptr(eo.seq_start), ptr(eo.seq_len), B,
+                                            int(beam_size), int(blank_id), max_len, ptr(toks), ptr(times), ptr(lens),
+                                            ptr(scores), ptr(nhyp), ptr(ws), wsb, cur_stream()),
+              "wb_ctc_prefix_beam_search")
+        th, mh, lh = toks.cpu().numpy(), times.cpu().numpy(), lens.cpu().numpy()
+        sh, nh = scores.cpu().numpy(), nhyp.cpu().numpy()
+        out = []
+        for b in range(B):
+            n = int(nh[b])
+            nbest = [tuple(th[b, r, :lh[b, r]].tolist()) for r in range(n)]
+            nscores = [float(sh[b, r]) for r in range(n)]
+            ntimes = [mh[b, r, :lh[b, r]].tolist() for r in range(n)]
+            out.append(DecodeResult(tokens=nbest[0], score=nscores[0], times=ntimes[0], nbest=nbest,
+                                    nbest_scores=nscores, nbest_times=ntimes))
+        return out
+
+    def _flatten_hyps(self, hyps_per_utt):
+        hyp_utt, hyp_len, hyp_tok0, toks = [], [], [], []
+        for b, hyps in enumerate(hyps_per_utt):
+            for h in hyps:
+                hyp_utt.append(b)
+                hyp_len.append(len(h))
+                hyp_tok0.append(len(toks))
+                toks.extend(int(t) for t in h)
+        if not toks:
+            toks = [0]
+        return _i32(hyp_utt), _i32(hyp_len), _i32(hyp_tok0), _i32(toks)
+
+    def _rescore(self, eo: _EncOut, beam_out: List[DecodeResult], ctc_weight: float, reverse_weight: float):
+        """search.py:374-458"""
+        if not self.dm.has_decoder:
+            raise _lib.WbError("attention_rescoring needs decoder weights")
+        lib = self._lib
+        B = len(beam_out)
+        hyp_utt, hyp_len, hyp_tok0, toks = self._flatten_hyps([r.nbest for r in beam_out])
+        ctc_scores = np.ascontiguousarray(np.array([s for r in beam_out for s in r.nbest_scores], dtype=np.float64))
+        n_hyp = int(hyp_utt.size)
+        R = int(hyp_len.sum()) + n_hyp
+        l2r = torch.zeros(R, device=self.device, dtype=torch.float32)
+        use_r2l = reverse_weight > 0 and self.spec.bidirectional and self.spec.rdec_layers > 0
+        r2l = torch.zeros(R, device=self.device, dtype=torch.float32)
+        hyp_score = torch.zeros(n_hyp, device=self.device, dtype=torch.float32)
+        best = torch.zeros(B, device=self.device, dtype=torch.int32)
+        wsb = lib.wb_rescoring_workspace_bytes(self.dm.handle, eo.rows, R)
+        ws = self._workspace(wsb)
+        check(lib.wb_attention_rescoring(self.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host), ptr(eo.lens_host),
+                                         B, n_hyp, ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks),
+                                         ptr(ctc_scores), self.sos, self.eos, float(ctc_weight),
+                                         float(reverse_weight if use_r2l else 0.0), ptr(l2r), ptr(r2l), ptr(hyp_score),
+                                         ptr(best), ptr(ws), ws.numel(), cur_stream()), "wb_attention_rescoring")
+        l2r_h, r2l_h = l2r.cpu().numpy(), r2l.cpu().numpy()
+        hs, bh = hyp_score.cpu().numpy(), best.cpu().numpy()
+        out = []
+        h0 = 0
+        row0 = np.concatenate([[0], np.cumsum(hyp_len + 1)]).astype(np.int64)
+        for b in range(B):
+            nb = len(beam_out[b].nbest)
+            bi = int(bh[b])
+            h = h0 + bi
+            n = int(hyp_len[h])
+            r0 = int(row0[h])
+            tc = [math.exp(float(l2r_h[r0 + j])) for j in range(n)]
+            score = np.float32(0.0)
+            for j in range(n + 1):
+                score = np.float32(score + l2r_h[r0 + j])
+            if use_r2l:
+                r_score = np.float32(0.0)
+                for j in range(n):
+                    s = r2l_h[r0 + (n - j - 1)]
+                    r_score = np.float32(r_score + s)
+                    tc[j] = (tc[j] + math.exp(float(s))) / 2
+                r_score = np.float32(r_score + r2l_h[r0 + n])
+                score = np.float32(score * np.float32(1 - reverse_weight) + r_score * np.float32(reverse_weight))
+            conf = math.exp(float(score) / (n + 1))
+            res = DecodeResult(beam_out[b].nbest[bi], float(hs[h]), confidence=conf,
+                               times=beam_out[b].nbest_times[bi], tokens_confidence=tc)
+            res.nbest_scores = [float(x) for x in hs[h0:h0 + nb]]   # extra: all rescored hypotheses
+            out.append(res)
+            h0 += nb
+        return out
+
+    # ----- asr_model.py:453-547 -----
+    def forward_attention_decoder(self, hyps: torch.Tensor, hyps_lens: torch.Tensor, encoder_out: torch.Tensor,
+                                  reverse_weight: float = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """hyps (N, L) with <sos> first, hyps_lens (N,) counting <sos>; encoder_out (1, T', d).
+        Returns (log-probs (N, L, V), r_log-probs (N, L, V) or tensor(0.)).  Positions past a
+        hypothesis' own length are zero-filled (the reference computes don't-care values there)."""
+        if not encoder_out.is_cuda:
+            raise _lib.WbError("encoder_out must be a CUDA tensor (no CPU fallback)")
+        assert encoder_out.size(0) == 1
+        lib = self._lib
+        N, L = hyps.shape
+        V = self.spec.vocab
+        lens = (hyps_lens.detach().cpu().numpy().astype(np.int64) - 1)
+        hy = hyps.detach().cpu().numpy()
+        hyp_list = [hy[i, 1:1 + lens[i]].tolist() for i in range(N)]
+        hyp_utt, hyp_len, hyp_tok0, toks = self._flatten_hyps([hyp_list])
+        Tp = encoder_out.size(1)
+        enc_bf16 = encoder_out[0].to(torch.bfloat16).contiguous()
+        R = int(hyp_len.sum()) + N
+        ldl = (V + 7) // 8 * 8
+        use_r2l = reverse_weight > 0 and self.is_bidirectional_decoder()
+        lp = torch.empty(R, ldl, device=self.device, dtype=torch.float32)
+        rlp = torch.empty(R, ldl, device=self.device, dtype=torch.float32) if use_r2l else None
+        wsb = lib.wb_rescoring_workspace_bytes(self.dm.handle, Tp, R)
+        ws = self._workspace(wsb)
+        check(lib.wb_decoder_logprobs(self.dm.handle, ptr(enc_bf16), Tp, ptr(_i32([0])), ptr(_i32([Tp])), 1, N,
+                                      ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks), int(hy[0, 0]), self.eos,
+                                      int(use_r2l), ptr(lp), ptr(rlp), ldl, ptr(ws), ws.numel(), cur_stream()),
+              "wb_decoder_logprobs")
+        out = torch.zeros(N, L, V, device=self.device, dtype=torch.float32)
+        r_out = torch.zeros(N, L, V, device=self.device, dtype=torch.float32) if use_r2l else torch.tensor(0.0)
+        r0 = 0
+        for i in range(N):
+            n = int(hyp_len[i]) + 1
+            out[i, :n] = lp[r0:r0 + n, :V]
+            if use_r2l:
+                r_out[i, :n] = rlp[r0:r0 + n, :V]
+            r0 += n
+        return out, r_out

@@ -1,0 +1,296 @@
+// Host-side orchestration of attention rescoring: (Bi)TransformerDecoder over ALL hypotheses of ALL
+// utterances in one varlen batch.  Mirrors wenet/models/transformer/search.py:374-458
+// (attention_rescoring), asr_model.py:453-547 (forward_attention_decoder), decoder.py:146-201,430-463
+// and decoder_layer.py:68-153 — with the cross-attention K/V of the encoder memory projected once per
+// utterance instead of once per hypothesis (the reference repeats encoder_out N times, asr_model.py:478)
+// and the output layer fused with log-softmax + target gather (no (N, L, V) tensor).
+#include "model.h"
+#include <math.h>
+#include <vector>
+
+namespace wb {
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct RsPlan {
+    int batch = 0, n_hyp = 0;
+    long long R = 0;  // decoder rows
+    int max_hyp_rows = 0, max_utt_rows = 0, max_enc_len = 0;
+    size_t o_int = 0, o_dbl = 0, o_x = 0, o_a = 0, o_qkv = 0, o_ctx = 0, o_q = 0, o_h = 0, o_memkv = 0, o_logits = 0,
+           total = 0;
+    long long ldl = 0;
+    size_t n_int = 0;
+};
+
+void rs_layout(const Model* m, long long enc_rows, long long R, int batch, int n_hyp, RsPlan* P) {
+    const int d = m->cfg.d_model, ff = m->cfg.dec_ffn_dim;
+    P->ldl = (m->cfg.vocab + 7) / 8 * 8;
+    P->n_int = (size_t)5 * R + (size_t)3 * n_hyp + (size_t)6 * batch + 64;
+    size_t o = 0;
+    P->o_int = o; o += align_up(P->n_int * 4);
+    P->o_dbl = o; o += align_up((size_t)n_hyp * 8 + 64);
+    P->o_x = o; o += align_up((size_t)R * d * 4);
+    P->o_a = o; o += align_up((size_t)R * d * 2);
+    P->o_qkv = o; o += align_up((size_t)R * 3 * d * 2);
+    P->o_ctx = o; o += align_up((size_t)R * d * 2);
+    P->o_q = o; o += align_up((size_t)R * d * 2);
+    P->o_h = o; o += align_up((size_t)R * ff * 2);
+    P->o_memkv = o; o += align_up((size_t)enc_rows * 2 * d * 2);
+    P->o_logits = o; o += align_up((size_t)R * P->ldl * 4);
+    P->total = o + 256;
+}
+
+#define RC(x)                         \
+    do {                              \
+        int _rc = (x);                \
+        if (_rc != WB_OK) return _rc; \
+    } while (0)
+
+struct RsDevPtrs {
+    int *tok_l2r, *tok_r2l, *pos, *tgt_l2r, *tgt_r2l, *hyp_row0, *hyp_rows, *hyp_len, *utt_q0, *utt_qn, *utt_hyp0,
+        *utt_nhyp, *enc_start, *enc_len;
+    double* ctc;
+};
+
+// one direction of the decoder: x = embed(tokens); layers; after_norm; logits = out(x)
+int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPtrs& dp, const int* tokens,
+                const void* enc_bf16, long long enc_rows, uint8_t* ws, float* logits, long long ldl,
+                cudaStream_t st) {
+    const wb_model_config& c = m->cfg;
+    const int d = c.d_model, ff = c.dec_ffn_dim, H = c.dec_heads;
+    const int R = (int)P.R;
+    float* x = reinterpret_cast<float*>(ws + P.o_x);
+    void* a = ws + P.o_a;
+    void* qkv = ws + P.o_qkv;
+    void* ctx = ws + P.o_ctx;
+    void* q = ws + P.o_q;
+    void* h = ws + P.o_h;
+    void* memkv = ws + P.o_memkv;
+    const float scale = 1.0f / sqrtf(64.0f);
+    RC(embed_tokens(tokens, dp.pos, R, d, D.emb, m->pe, sqrtf((float)d), x, st));
+    for (size_t li = 0; li < D.layers.size(); ++li) {
+        const DecLayer& L = D.layers[li];
+        // masked (causal) self-attention, decoder_layer.py:101-118
+        RC(layernorm_rows(x, d, R, d, L.n1.g, L.n1.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.sa_qkv.tmap, L.sa_qkv.w, R, 3 * d, d, L.sa_qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
+        {
+            AttnArgs A;
+            A.q = qkv; A.ldq = 3 * d; A.q_rows = R; A.q_col0 = 0;
+            A.k = qkv; A.ldk = 3 * d; A.k_rows = R; A.k_col0 = d;
+            A.v = qkv; A.ldv = 3 * d; A.v_rows = R; A.v_col0 = 2 * d;
+            A.kbias = nullptr; A.ld_kbias = 0;
+            A.q_start = dp.hyp_row0; A.q_len = dp.hyp_rows; A.k_start = dp.hyp_row0; A.k_len = dp.hyp_rows;
+            A.batch = P.n_hyp; A.heads = H; A.max_q_len = P.max_hyp_rows;
+            A.chunk_size = 1; A.num_left_chunks = -1; A.scale = scale;   // causal == chunk size 1
+            A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
+            RC(attention_forward(A, st));
+        }
+        RC(gemm_bf16(ctx, d, &L.sa_out.tmap, L.sa_out.w, R, d, d, L.sa_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        // cross-attention over the utterance's encoder frames, decoder_layer.py:120-139
+        RC(layernorm_rows(x, d, R, d, L.n2.g, L.n2.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.ca_q.tmap, L.ca_q.w, R, d, d, L.ca_q.b, EPI_BF16, 1.0f, q, d, 0, st));
+        RC(gemm_bf16(enc_bf16, d, &L.ca_kv.tmap, L.ca_kv.w, (int)enc_rows, 2 * d, d, L.ca_kv.b, EPI_BF16, 1.0f, memkv,
+                     2 * d, 0, st));
+        {
+            AttnArgs A;
+            A.q = q; A.ldq = d; A.q_rows = R; A.q_col0 = 0;
+            A.k = memkv; A.ldk = 2 * d; A.k_rows = enc_rows; A.k_col0 = 0;
+            A.v = memkv; A.ldv = 2 * d; A.v_rows = enc_rows; A.v_col0 = d;
+            A.kbias = nullptr; A.ld_kbias = 0;
+            A.q_start = dp.utt_q0; A.q_len = dp.utt_qn; A.k_start = dp.enc_start; A.k_len = dp.enc_len;
+            A.batch = P.batch; A.heads = H; A.max_q_len = P.max_utt_rows;
+            A.chunk_size = 0; A.num_left_chunks = -1; A.scale = scale;
+            A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
+            RC(attention_forward(A, st));
+        }
+        RC(gemm_bf16(ctx, d, &L.ca_out.tmap, L.ca_out.w, R, d, d, L.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        // feed-forward (ReLU), decoder_layer.py:141-147
+        RC(layernorm_rows(x, d, R, d, L.n3.g, L.n3.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, R, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
+        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, R, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+    }
+    RC(layernorm_rows(x, d, R, d, D.after.g, D.after.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+    RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, ldl, 0, st));
+    return WB_OK;
+}
+
+// builds the flattened decoder inputs on the host and uploads them (one copy)
+int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, const int32_t* seq_len_host, int batch,
+            int n_hyp, const int32_t* hyp_utt, const int32_t* hyp_len, const int32_t* hyp_tok0,
+            const int32_t* hyp_tokens, const double* ctc_score, int sos, int eos, uint8_t* ws, size_t ws_bytes,
+            RsPlan* P, RsDevPtrs* dp, cudaStream_t st) {
+    long long R = 0;
+    for (int h = 0; h < n_hyp; ++h) R += hyp_len[h] + 1;
+    rs_layout(m, enc_rows, R, batch, n_hyp, P);
+    P->batch = batch;
+    P->n_hyp = n_hyp;
+    P->R = R;
+    WB_REQUIRE(ws_bytes >= P->total, WB_ERR_WORKSPACE, "rescoring: workspace %zu < required %zu", ws_bytes, P->total);
+    WB_REQUIRE(R < 2147483647LL, WB_ERR_UNSUPPORTED, "rescoring: too many decoder rows");
+    std::vector<int> buf(P->n_int, 0);
+    int* tok_l2r = buf.data();
+    int* tok_r2l = tok_l2r + R;
+    int* pos = tok_r2l + R;
+    int* tgt_l2r = pos + R;
+    int* tgt_r2l = tgt_l2r + R;
+    int* hyp_row0 = tgt_r2l + R;
+    int* hyp_rows = hyp_row0 + n_hyp;
+    int* hyp_ln = hyp_rows + n_hyp;
+    int* utt_q0 = hyp_ln + n_hyp;
+    int* utt_qn = utt_q0 + batch;
+    int* utt_hyp0 = utt_qn + batch;
+    int* utt_nhyp = utt_hyp0 + batch;
+    int* enc_start = utt_nhyp + batch;
+    int* enc_len = enc_start + batch;
+    for (int b = 0; b < batch; ++b) {
+        utt_q0[b] = 0;
+        utt_qn[b] = 0;
+        utt_hyp0[b] = 0;
+        utt_nhyp[b] = 0;
+        enc_start[b] = seq_start_host[b];
+        enc_len[b] = seq_len_host[b];
+        if (seq_len_host[b] > P->max_enc_len) P->max_enc_len = seq_len_host[b];
+    }
+    long long r = 0;
+    int prev_utt = -1;
+    for (int h = 0; h < n_hyp; ++h) {
+        const int b = hyp_utt[h], n = hyp_len[h];
+        WB_REQUIRE(b >= 0 && b < batch && b >= prev_utt, WB_ERR_BAD_ARG, "rescoring: hyp_utt must be non-decreasing in [0,batch)");
+        if (b != prev_utt) {
+            utt_q0[b] = (int)r;
+            utt_hyp0[b] = h;
+            prev_utt = b;
+        }
+        utt_nhyp[b] += 1;
+        utt_qn[b] += n + 1;
+        hyp_row0[h] = (int)r;
+        hyp_rows[h] = n + 1;
+        hyp_ln[h] = n;
+        if (n + 1 > P->max_hyp_rows) P->max_hyp_rows = n + 1;
+        const int32_t* y = hyp_tokens + hyp_tok0[h];
+        // l2r: in = [sos, y0..y_{n-1}], target = [y0..y_{n-1}, eos]      (common.py:113-156 add_sos_eos)
+        // r2l: in = [sos, y_{n-1}..y0], target = [y_{n-1}..y0, eos]      (asr_model.py:487-536)
+        for (int j = 0; j <= n; ++j) {
+            tok_l2r[r + j] = (j == 0) ? sos : y[j - 1];
+            tok_r2l[r + j] = (j == 0) ? sos : y[n - j];
+            tgt_l2r[r + j] = (j < n) ? y[j] : eos;
+            tgt_r2l[r + j] = (j < n) ? y[n - 1 - j] : eos;
+            pos[r + j] = j;
+        }
+        r += n + 1;
+    }
+    for (int b = 0; b < batch; ++b)
+        if (utt_qn[b] > P->max_utt_rows) P->max_utt_rows = utt_qn[b];
+    WB_REQUIRE(P->max_hyp_rows <= m->cfg.max_pos, WB_ERR_UNSUPPORTED, "hypothesis longer than the positional table");
+    WB_CHECK_CUDA(cudaMemcpyAsync(ws + P->o_int, buf.data(), P->n_int * 4, cudaMemcpyHostToDevice, st));
+    if (ctc_score)
+        WB_CHECK_CUDA(cudaMemcpyAsync(ws + P->o_dbl, ctc_score, (size_t)n_hyp * 8, cudaMemcpyHostToDevice, st));
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));  // host staging buffers go out of scope
+    int* base = reinterpret_cast<int*>(ws + P->o_int);
+    dp->tok_l2r = base;
+    dp->tok_r2l = base + R;
+    dp->pos = base + 2 * R;
+    dp->tgt_l2r = base + 3 * R;
+    dp->tgt_r2l = base + 4 * R;
+    dp->hyp_row0 = base + 5 * R;
+    dp->hyp_rows = dp->hyp_row0 + n_hyp;
+    dp->hyp_len = dp->hyp_rows + n_hyp;
+    dp->utt_q0 = dp->hyp_len + n_hyp;
+    dp->utt_qn = dp->utt_q0 + batch;
+    dp->utt_hyp0 = dp->utt_qn + batch;
+    dp->utt_nhyp = dp->utt_hyp0 + batch;
+    dp->enc_start = dp->utt_nhyp + batch;
+    dp->enc_len = dp->enc_start + batch;
+    dp->ctc = reinterpret_cast<double*>(ws + P->o_dbl);
+    return WB_OK;
+}
+
+}  // namespace
+}  // namespace wb
+
+using namespace wb;
+
+extern "C" {
+
+size_t wb_rescoring_workspace_bytes(const wb_model* mm, int64_t enc_rows, int64_t total_tokens_plus_hyps) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    if (!m || !m->finalized) return 0;
+    RsPlan P;
+    // n_hyp and batch only size small integer tables: bound both by the row count
+    rs_layout(m, enc_rows, total_tokens_plus_hyps, (int)(total_tokens_plus_hyps < 1 ? 1 : total_tokens_plus_hyps),
+              (int)(total_tokens_plus_hyps < 1 ? 1 : total_tokens_plus_hyps), &P);
+    return P.total;
+}
+
+int wb_attention_rescoring(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows,
+                           const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int n_hyp,
+                           const int32_t* hyp_utt_host, const int32_t* hyp_len_host, const int32_t* hyp_tok0_host,
+                           const int32_t* hyp_tokens_host, const double* ctc_score_host, int sos, int eos,
+                           float ctc_weight, float reverse_weight, float* tok_logp_l2r_dev, float* tok_logp_r2l_dev,
+                           float* hyp_score_dev, int32_t* best_dev, void* workspace_dev, size_t workspace_bytes,
+                           wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "attention_rescoring: model not finalized");
+    WB_REQUIRE(m->cfg.dec_layers > 0, WB_ERR_UNSUPPORTED, "attention_rescoring: model has no decoder");
+    WB_REQUIRE(batch > 0 && n_hyp > 0 && enc_out_bf16_dev && tok_logp_l2r_dev && hyp_score_dev && best_dev &&
+                   workspace_dev && ctc_score_host,
+               WB_ERR_BAD_ARG, "attention_rescoring: null/empty argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
+    RsPlan P;
+    RsDevPtrs dp;
+    RC(prepare(m, enc_rows, seq_start_host, seq_len_host, batch, n_hyp, hyp_utt_host, hyp_len_host, hyp_tok0_host,
+               hyp_tokens_host, ctc_score_host, sos, eos, ws, workspace_bytes, &P, &dp, st));
+    float* logits = reinterpret_cast<float*>(ws + P.o_logits);
+    RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, logits, P.ldl, st));
+    RC(gather_logprob(logits, P.ldl, (int)P.R, m->cfg.vocab, dp.tgt_l2r, tok_logp_l2r_dev, st));
+    const bool use_r2l = reverse_weight > 0.f && m->cfg.rdec_layers > 0;
+    if (use_r2l) {
+        WB_REQUIRE(tok_logp_r2l_dev, WB_ERR_BAD_ARG, "attention_rescoring: r2l output buffer missing");
+        RC(run_decoder(m, m->right, P, dp, dp.tok_r2l, enc_out_bf16_dev, enc_rows, ws, logits, P.ldl, st));
+        RC(gather_logprob(logits, P.ldl, (int)P.R, m->cfg.vocab, dp.tgt_r2l, tok_logp_r2l_dev, st));
+    }
+    RescoreArgs a;
+    a.l2r = tok_logp_l2r_dev;
+    a.r2l = use_r2l ? tok_logp_r2l_dev : nullptr;
+    a.hyp_row0 = dp.hyp_row0;
+    a.hyp_len = dp.hyp_len;
+    a.utt_hyp0 = dp.utt_hyp0;
+    a.utt_nhyp = dp.utt_nhyp;
+    a.batch = batch;
+    a.ctc_score = dp.ctc;
+    a.ctc_weight = ctc_weight;
+    a.reverse_weight = use_r2l ? reverse_weight : 0.f;
+    a.hyp_score = hyp_score_dev;
+    a.best = best_dev;
+    return rescore_combine(a, st);
+}
+
+int wb_decoder_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows,
+                        const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int n_hyp,
+                        const int32_t* hyp_utt_host, const int32_t* hyp_len_host, const int32_t* hyp_tok0_host,
+                        const int32_t* hyp_tokens_host, int sos, int eos, int use_r2l, float* logp_dev,
+                        float* r_logp_dev, int64_t ldl, void* workspace_dev, size_t workspace_bytes,
+                        wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "decoder_logprobs: model not finalized");
+    WB_REQUIRE(m->cfg.dec_layers > 0, WB_ERR_UNSUPPORTED, "decoder_logprobs: model has no decoder");
+    WB_REQUIRE(ldl >= m->cfg.vocab && logp_dev, WB_ERR_BAD_ARG, "decoder_logprobs: bad output");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
+    RsPlan P;
+    RsDevPtrs dp;
+    RC(prepare(m, enc_rows, seq_start_host, seq_len_host, batch, n_hyp, hyp_utt_host, hyp_len_host, hyp_tok0_host,
+               hyp_tokens_host, nullptr, sos, eos, ws, workspace_bytes, &P, &dp, st));
+    RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, logp_dev, ldl, st));
+    RC(ctc_logsoftmax_topk(logp_dev, ldl, (int)P.R, m->cfg.vocab, -1, 0.f, 0, nullptr, nullptr, st));
+    if (use_r2l && m->cfg.rdec_layers > 0 && r_logp_dev) {
+        RC(run_decoder(m, m->right, P, dp, dp.tok_r2l, enc_out_bf16_dev, enc_rows, ws, r_logp_dev, ldl, st));
+        RC(ctc_logsoftmax_topk(r_logp_dev, ldl, (int)P.R, m->cfg.vocab, -1, 0.f, 0, nullptr, nullptr, st));
+    }
+    return WB_OK;
+}
+
+}  // extern "C"

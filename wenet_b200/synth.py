@@ -1,0 +1,192 @@
+"""Deterministic synthetic weights and audio (no network, no checkpoints, no torch RNG):
+the same `state_dict` can be regenerated bit-for-bit on any box from (configs, seed), so parity tests
+on the GPU box load exactly the weights the golden fixtures were produced with in the build
+container (oracle/make_goldens.py feeds them to the UNMODIFIED reference).
+
+Key names and shapes are the reference's own; distributions follow torch's
+default initialisers closely enough to give well-conditioned activations:
+  Linear / Conv weights and biases  ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+  LayerNorm / BatchNorm             weight 1 + 0.1 U(-1,1), bias 0.1 U(-1,1), var in [0.5, 1.5]
+  pos_bias_u / pos_bias_v           xavier uniform
+  Embedding                         U(-sqrt(3), sqrt(3))   (unit variance)
+The CTC head is sharpened (weight * alpha, blank bias + beta) so that posteriors are peaky like a
+trained model's (flat random posteriors make beam search pathological).
+"""
+import hashlib
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+
+
+def _rng(seed: int, name: str) -> np.random.Generator:
+    h = hashlib.sha256(("%d:%s" % (seed, name)).encode()).digest()
+    return np.random.Generator(np.random.PCG64(int.from_bytes(h[:8], "little")))
+
+
+def _uniform(seed, name, shape, bound) -> torch.Tensor:
+    u = _rng(seed, name).random(size=shape)  # float64 in [0, 1)
+    return torch.from_numpy(((u * 2.0 - 1.0) * bound).astype(np.float32))
+
+
+def sinusoid_pe(max_len: int, d: int) -> torch.Tensor:
+    pe = torch.zeros(max_len, d)
+    pos = torch.arange(0, max_len, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def synth_state_dict(configs: dict, seed: int = 777, ctc_alpha: float = 6.0, ctc_blank_beta: float = 4.0,
+                     with_pe: bool = True) -> Dict[str, torch.Tensor]:
+    enc = configs["encoder_conf"]
+    dec = configs.get("decoder_conf", {})
+    d = int(enc.get("output_size", 256))
+    h = int(enc.get("attention_heads", 4))
+    ff = int(enc.get("linear_units", 2048))
+    L = int(enc.get("num_blocks", 6))
+    K = int(enc.get("cnn_module_kernel", 15))
+    bn = enc.get("cnn_module_norm", "batch_norm") == "batch_norm"
+    idim = int(configs["input_dim"])
+    V = int(configs["output_dim"])
+    F2 = ((idim - 1) // 2 - 1) // 2
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out_f, in_f, extra_shape=()):
+        b = 1.0 / math.sqrt(in_f * int(np.prod(extra_shape)) if extra_shape else in_f)
+        sd[name + ".weight"] = _uniform(seed, name + ".weight", (out_f, in_f) + tuple(extra_shape), b)
+        sd[name + ".bias"] = _uniform(seed, name + ".bias", (out_f,), b)
+
+    def norm(name, n=d):
+        sd[name + ".weight"] = 1.0 + _uniform(seed, name + ".weight", (n,), 0.1)
+        sd[name + ".bias"] = _uniform(seed, name + ".bias", (n,), 0.1)
+
+    if configs.get("cmvn", None) is not None:
+        sd["encoder.global_cmvn.mean"] = 8.0 + _uniform(seed, "cmvn.mean", (idim,), 4.0)
+        sd["encoder.global_cmvn.istd"] = 0.25 + _uniform(seed, "cmvn.istd", (idim,), 0.1)
+    lin("encoder.embed.conv.0", d, 1, (3, 3))
+    lin("encoder.embed.conv.2", d, d, (3, 3))
+    lin("encoder.embed.out.0", d, d * F2)
+    if with_pe:
+        sd["encoder.embed.pos_enc.pe"] = sinusoid_pe(5000, d).unsqueeze(0)
+    norm("encoder.after_norm")
+    for i in range(L):
+        p = "encoder.encoders.%d" % i
+        xb = math.sqrt(6.0 / (h + d // h))
+        sd[p + ".self_attn.pos_bias_u"] = _uniform(seed, p + ".pos_bias_u", (h, d // h), xb)
+        sd[p + ".self_attn.pos_bias_v"] = _uniform(seed, p + ".pos_bias_v", (h, d // h), xb)
+        for n in ("linear_q", "linear_k", "linear_v", "linear_out"):
+            lin(p + ".self_attn." + n, d, d)
+        sd[p + ".self_attn.linear_pos.weight"] = _uniform(seed, p + ".linear_pos", (d, d), 1.0 / math.sqrt(d))
+        for f in ("feed_forward", "feed_forward_macaron"):
+            lin(p + "." + f + ".w_1", ff, d)
+            lin(p + "." + f + ".w_2", d, ff)
+        lin(p + ".conv_module.pointwise_conv1", 2 * d, d, (1,))
+        lin(p + ".conv_module.depthwise_conv", d, 1, (K,))
+        norm(p + ".conv_module.norm")
+        if bn:
+            sd[p + ".conv_module.norm.running_mean"] = _uniform(seed, p + ".bn.mean", (d,), 0.1)
+            sd[p + ".conv_module.norm.running_var"] = 1.0 + _uniform(seed, p + ".bn.var", (d,), 0.5)
+            sd[p + ".conv_module.norm.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+        lin(p + ".conv_module.pointwise_conv2", d, d, (1,))
+        for n in ("norm_ff", "norm_mha", "norm_ff_macaron", "norm_conv", "norm_final"):
+            norm(p + "." + n)
+    lin("ctc.ctc_lo", V, d)
+    sd["ctc.ctc_lo.weight"] = sd["ctc.ctc_lo.weight"] * ctc_alpha
+    sd["ctc.ctc_lo.bias"] = sd["ctc.ctc_lo.bias"].clone()
+    sd["ctc.ctc_lo.bias"][0] += ctc_blank_beta
+
+    dec_type = configs.get("decoder", "bitransformer")
+    dff = int(dec.get("linear_units", 2048))
+
+    def decoder(prefix, n_layers):
+        sd[prefix + ".embed.0.weight"] = _uniform(seed, prefix + ".emb", (V, d), math.sqrt(3.0))
+        if with_pe:
+            sd[prefix + ".embed.1.pe"] = sinusoid_pe(5000, d).unsqueeze(0)
+        norm(prefix + ".after_norm")
+        lin(prefix + ".output_layer", V, d)
+        for i in range(n_layers):
+            p = "%s.decoders.%d" % (prefix, i)
+            for a in ("self_attn", "src_attn"):
+                for n in ("linear_q", "linear_k", "linear_v", "linear_out"):
+                    lin(p + "." + a + "." + n, d, d)
+            lin(p + ".feed_forward.w_1", dff, d)
+            lin(p + ".feed_forward.w_2", d, dff)
+            for n in ("norm1", "norm2", "norm3"):
+                norm(p + "." + n)
+
+    if dec_type == "bitransformer":
+        decoder("decoder.left_decoder", int(dec.get("num_blocks", 6)))
+        decoder("decoder.right_decoder", int(dec.get("r_num_blocks", 0)))
+    else:
+        decoder("decoder", int(dec.get("num_blocks", 6)))
+    return sd
+
+
+def synth_pcm(batch: int, num_samples, seed: int = 777, sigma: float = 3000.0) -> torch.Tensor:
+    """int16 PCM (batch, max_n): Gaussian noise + a few slowly chirping tones per utterance, clipped to
+    int16.  num_samples: int or list of ints; shorter rows are zero padded."""
+    ns = [int(num_samples)] * batch if np.isscalar(num_samples) else [int(n) for n in num_samples]
+    n_max = (max(ns) + 7) // 8 * 8
+    out = np.zeros((batch, n_max), dtype=np.int16)
+    for b, n in enumerate(ns):
+        r = _rng(seed, "pcm%d" % b)
+        u1 = np.maximum(r.random(size=n), 1e-12)
+        u2 = r.random(size=n)
+        x = np.sqrt(-2.0 * np.log(u1)) * np.cos(2 * np.pi * u2) * sigma   # Box-Muller: raw-uniform only
+        t = np.arange(n) / 16000.0
+        for k in range(3):
+            f0 = 150.0 + 900.0 * r.random()
+            x += 1500.0 * np.sin(2 * np.pi * (f0 * t + 40.0 * (k + 1) * t * t))
+        out[b, :n] = np.clip(np.round(x), -32767, 32767).astype(np.int16)
+    return torch.from_numpy(out)
+
+
+# the recipe configurations of SURVEY.md section 8 (values from the reference's yaml files:
+# examples/aishell/s0/conf/train_u2++_conformer.yaml, train_unified_conformer.yaml, train_conformer.yaml,
+# examples/wenetspeech/s0/conf/train_u2++_conformer.yaml)
+def recipe(name: str) -> dict:
+    def enc(d, h, ff, L, K, causal, norm, dyn):
+        return dict(output_size=d, attention_heads=h, linear_units=ff, num_blocks=L, dropout_rate=0.1,
+                    positional_dropout_rate=0.1, attention_dropout_rate=0.1, input_layer="conv2d",
+                    normalize_before=True, cnn_module_kernel=K, use_cnn_module=True, activation_type="swish",
+                    pos_enc_layer_type="rel_pos", selfattention_layer_type="rel_selfattn", causal=causal,
+                    use_dynamic_chunk=dyn, cnn_module_norm=norm, use_dynamic_left_chunk=False)
+
+    def dec(h, ff, n, r=None):
+        c = dict(attention_heads=h, linear_units=ff, num_blocks=n, dropout_rate=0.1, positional_dropout_rate=0.1,
+                 self_attention_dropout_rate=0.1, src_attention_dropout_rate=0.1)
+        if r is not None:
+            c["r_num_blocks"] = r
+        return c
+
+    base = dict(input_dim=80, cmvn=None, encoder="conformer", tokenizer="char", tokenizer_conf={}, ctc="ctc",
+                ctc_conf={"ctc_blank_id": 0}, model="asr_model")
+    if name == "u2pp_small":        # AISHELL-1 U2++ 12L/256d/4h, K=8 causal LN, bitransformer 3+3
+        return dict(base, output_dim=4233, encoder_conf=enc(256, 4, 2048, 12, 8, True, "layer_norm", True),
+                    decoder="bitransformer", decoder_conf=dec(4, 2048, 3, 3),
+                    model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False, reverse_weight=0.3))
+    if name == "u2_small":          # train_unified_conformer.yaml: K=15 causal LN, transformer x6
+        return dict(base, output_dim=4233, encoder_conf=enc(256, 4, 2048, 12, 15, True, "layer_norm", True),
+                    decoder="transformer", decoder_conf=dec(4, 2048, 6),
+                    model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False))
+    if name == "conformer_small":   # train_conformer.yaml: K=15 symmetric BatchNorm, transformer x6
+        return dict(base, output_dim=4233, encoder_conf=enc(256, 4, 2048, 12, 15, False, "batch_norm", False),
+                    decoder="transformer", decoder_conf=dec(4, 2048, 6),
+                    model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False))
+    if name in ("u2pp_large", "u2pp_large12"):   # WenetSpeech U2++ 512d/8h K=15 causal LN, 3+3
+        L = 24 if name == "u2pp_large" else 12
+        return dict(base, output_dim=5538, encoder_conf=enc(512, 8, 2048, L, 15, True, "layer_norm", True),
+                    decoder="bitransformer", decoder_conf=dec(8, 2048, 3, 3),
+                    model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False, reverse_weight=0.3))
+    if name == "tiny":              # test-sized U2++ (2L/128d/2h, V=37)
+        return dict(base, output_dim=37, encoder_conf=enc(128, 2, 256, 2, 8, True, "layer_norm", True),
+                    decoder="bitransformer", decoder_conf=dec(2, 256, 2, 1),
+                    model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False, reverse_weight=0.3))
+    if name == "tiny_bn":           # test-sized non-streaming variant (symmetric K=15, BatchNorm)
+        return dict(base, output_dim=37, encoder_conf=enc(128, 2, 256, 2, 15, False, "batch_norm", False),
+                    decoder="transformer", decoder_conf=dec(2, 256, 2),
+                    model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False))
+    raise KeyError(name)
