@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — RTFx (audio-seconds decoded per wall-second) of the B200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" = one pass of the whole hot path over one batch of synthetic 16 kHz utterances:
+fbank -> ConformerEncoder -> CTC log-softmax/top-k -> ctc_prefix_beam_search -> attention_rescoring,
+ending with the token ids on the host.  Workload at N=1 (BASELINE.json configs[1] model, decoded in the
+mode BASELINE.json's `metric` names): U2++ Conformer 12L/256d/4h (AISHELL-1 recipe), batch 64 x 30 s per
+GPU, beam 10, attention_rescoring (which contains ctc_prefix_beam_search).  Weak scaling: every rank
+decodes its own 64 x 30 s (utterances shard independently; no data-path collective).
+
+`value`   : inputs (int16 PCM) already resident in HBM when the timed region starts.
+`e2e`     : same metric through the public API with HOST (pinned) PCM: H2D copy of the batch and D2H
+            of the results inside the timed region.
+`roofline`: the dominant kernel family (tcgen05 GEMM) — algorithmic FLOPs / CUDA-event time measured
+            live around every launch in the timed steps (wb_prof_*), against MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle port of the reference path (oracle/wenet_oracle.py, torch-CPU ops with
+            all host threads + the reference's Python search loops) on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RTFx (audio-s/s) U2++ Conformer attention_rescoring at 1/2/4/8 B200"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons every 200 ms during the timed region (pynvml, else nvidia-smi)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake_slowdown"}
+            while not self.stop_flag:
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.2)
+        except Exception:
+            import subprocess
+            while not self.stop_flag:
+                try:
+                    o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = [float(x) for x in o.strip().split(",")]
+                    self.sm.append(a)
+                    self.sm_max = b
+                except Exception:
+                    pass
+                time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def workload(name):
+    from wenet_b200 import synth
+    if name == "small":
+        return dict(recipe="u2pp_small", batch=64, seconds=30.0, beam=10, ctc_weight=0.5, reverse_weight=0.3,
+                    label="U2++ Conformer (AISHELL-1 12L/256d/4h), batch 64x30s per GPU, attention_rescoring "
+                          "(incl. ctc_prefix_beam_search), beam 10")
+    if name == "large":
+        return dict(recipe="u2pp_large", batch=32, seconds=30.0, beam=10, ctc_weight=0.5, reverse_weight=0.3,
+                    label="U2++ Conformer-large (WenetSpeech 24L/512d/8h), batch 32x30s per GPU, attention_rescoring")
+    raise KeyError(name)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ----------------------------------------------------------------------------------------------
+def cpu_oracle_step(sd, cfg, pcm_rows, wl):
+    """One pass of the reference path on the CPU (oracle port): fbank -> encoder -> ctc -> prefix beam
+    search -> attention rescoring, as wenet/bin/recognize.py:282-303 does per batch."""
+    import torch
+    from oracle import wenet_oracle as O
+    e = cfg["encoder_conf"]
+    ecfg = O.encoder_cfg(sd, e["attention_heads"], e["causal"], e["cnn_module_norm"])
+    d = cfg["decoder_conf"]
+    dcfg = dict(bidirectional=cfg["decoder"] == "bitransformer", layers=d["num_blocks"],
+                r_layers=d.get("r_num_blocks", 0), heads=d["attention_heads"])
+    with torch.no_grad():
+        feats = [O.fbank(r.float()) for r in pcm_rows]
+        lens = torch.tensor([f.shape[0] for f in feats])
+        xs = torch.zeros(len(feats), int(lens.max()), 80)
+        for b, f in enumerate(feats):
+            xs[b, :f.shape[0]] = f
+        enc, mask = O.encoder_forward(sd, ecfg, xs, lens)
+        el = mask.squeeze(1).sum(1)
+        lp = O.ctc_logprobs(sd, enc)
+        pb = O.ctc_prefix_beam_search(lp, el, wl["beam"])
+        V = cfg["output_dim"]
+        rs = O.attention_rescoring(sd, dcfg, pb, enc, el, V - 1, V - 1, wl["ctc_weight"], wl["reverse_weight"])
+    return [r["tokens"] for r in rs]
+
+
+def cpu_sample(wl, n_utts, seed=777):
+    import torch
+    from wenet_b200 import synth
+    cfg = synth.recipe(wl["recipe"])
+    sd = synth.synth_state_dict(cfg, seed=seed)
+    n = int(wl["seconds"] * 16000)
+    pcm = synth.synth_pcm(n_utts, n, seed=seed)
+    torch.set_num_threads(os.cpu_count() or 1)
+    return cfg, sd, [pcm[b, :n] for b in range(n_utts)]
+
+
+def run_reference_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = workload(args.workload)
+    total = args.steps + args.warmup
+    n_utts = max(1, min(4, 24 // max(total, 1)))
+    cfg, sd, rows = cpu_sample(wl, n_utts)
+    for _ in range(args.warmup):
+        cpu_oracle_step(sd, cfg, rows, wl)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_step(sd, cfg, rows, wl)
+    dt = time.perf_counter() - t0
+    audio = n_utts * wl["seconds"] * args.steps
+    val = audio / dt
+    sample = "%d x %.0f s utterance(s) per step, same model/mode/beam" % (n_utts, wl["seconds"])
+    line = {"metric": METRIC, "value": val, "unit": "audio-s/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "recipe": wl["recipe"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="small", choices=["small", "large"])
+    ap.add_argument("--batch", type=int, default=0, help="override utterances per GPU")
+    ap.add_argument("--seconds", type=float, default=0.0, help="override utterance length")
+    ap.add_argument("--mode", default="attention_rescoring",
+                    choices=["attention_rescoring", "ctc_prefix_beam_search", "ctc_greedy_search"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-utts", type=int, default=2)
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event profiler")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from wenet_b200 import _lib, synth
+    from wenet_b200.asr_model import B200ASRModel
+    from wenet_b200.fbank import FbankExtractor
+    from wenet_b200.shard import shard_utterances
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = workload(args.workload)
+    if args.batch:
+        wl["batch"] = args.batch
+    if args.seconds:
+        wl["seconds"] = args.seconds
+    B, n = wl["batch"], int(wl["seconds"] * 16000)
+    cfg = synth.recipe(wl["recipe"])
+    sd = synth.synth_state_dict(cfg, seed=777)
+    model = B200ASRModel(cfg, sd, device=dev)
+    fb = FbankExtractor(80)
+    lib = _lib.load()
+
+    # global utterance list (world * B utterances of equal length) sharded without any collective
+    mine = shard_utterances([int(wl["seconds"] * 100)] * (world * B), world, rank)
+    assert len(mine) == B
+    NROT = 3  # rotate over 3 distinct PCM batches: 3 x B x n x 2 B (184 MB at 64 x 30 s) > the 126 MB L2
+    host_pcm = [synth.synth_pcm(4, n, seed=1000 * rank + r).repeat((B + 3) // 4, 1)[:B].contiguous().pin_memory()
+                for r in range(NROT)]
+    for r in range(NROT):   # make the rows of a batch distinct without generating 64 x 30 s three times
+        host_pcm[r] += (torch.arange(B, dtype=torch.int16).unsqueeze(1) % 7)
+    dev_pcm = [h.to(dev) for h in host_pcm]
+    ns = torch.full((B,), n, dtype=torch.int32, device=dev)
+    nframes = fb.num_frames(n)
+    flens = torch.full((B,), nframes, dtype=torch.int64, device=dev)
+    methods = [args.mode]
+
+    def step(pcm_dev):
+        feats = fb(pcm_dev, ns)
+        return model.decode(methods, feats, flens, beam_size=wl["beam"], ctc_weight=wl["ctc_weight"],
+                            reverse_weight=wl["reverse_weight"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- warm-up ----
+    for i in range(args.warmup):
+        res = step(dev_pcm[i % NROT])
+    torch.cuda.synchronize()
+    n_tok = sum(len(r.tokens) for r in res[args.mode])
+
+    # ---- device-resident timing (headline `value`) with the per-kernel profiler on ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.wb_launch_count()
+    if not args.no_profile:
+        lib.wb_prof_reset()
+        lib.wb_prof_enable(1)
+    ms = timed(lambda i: step(dev_pcm[i % NROT]), args.steps)
+    launches = lib.wb_launch_count() - launches0
+    prof = None
+    if not args.no_profile:
+        lib.wb_prof_enable(0)
+        nt = lib.wb_prof_num_tags()
+        pms, pwork, pl = (C.c_double * nt)(), (C.c_double * nt)(), (C.c_longlong * nt)()
+        lib.wb_prof_collect(pms, pwork, pl)
+        prof = {lib.wb_prof_tag_name(t).decode(): {"ms": pms[t], "work": pwork[t], "launches": int(pl[t])}
+                for t in range(nt) if pl[t] > 0}
+        lib.wb_prof_reset()
+
+    # ---- end to end: pinned host PCM -> H2D -> decode -> results on host ----
+    model.d2h_bytes = 0
+
+    def e2e_step(i):
+        pcm = host_pcm[i % NROT].to(dev, non_blocking=True)
+        return step(pcm)
+
+    for i in range(2):
+        e2e_step(i)
+    model.d2h_bytes = 0
+    ms_e2e = timed(e2e_step, args.steps)
+    d2h = int(getattr(model, "d2h_bytes", 0) / max(args.steps, 1))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    audio_per_step = world * B * wl["seconds"]
+    value = audio_per_step * args.steps / (ms / 1e3)
+    e2e_val = audio_per_step * args.steps / (ms_e2e / 1e3)
+    peaks = load_peaks()
+    line = {
+        "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["label"], "recipe": wl["recipe"], "batch_per_gpu": B, "seconds": wl["seconds"],
+                   "mode": args.mode, "beam": wl["beam"], "ctc_weight": wl["ctc_weight"],
+                   "reverse_weight": wl["reverse_weight"], "parallelism": "dp%d (utterance shards, no collective)" % world,
+                   "l2": "inputs rotate over %d distinct PCM batches (%.0f MB > L2) and every step streams GBs of "
+                         "activations" % (NROT, NROT * B * n * 2 / 1e6),
+                   "weights": "random init, seed 777, CTC head sharpened (synth.py)",
+                   "tokens_per_batch": n_tok},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": B * n * 2, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+    }
+    if prof is not None and "gemm_tcgen05" in prof:
+        g = prof["gemm_tcgen05"]
+        ach = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        line["roofline"] = {"kernel": "gemm_tcgen05_kernel (all Linear / pointwise-conv / im2col-conv GEMMs)",
+                            "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                            "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + " (sustained bf16)",
+                            "launches": g["launches"], "avg_launch_us": 1e3 * g["ms"] / max(g["launches"], 1),
+                            "share_of_step": g["ms"] / ms}
+        tot = sum(v["ms"] for v in prof.values())
+        line["kernels"] = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                               "share": v["ms"] / tot,
+                               **({"GBps": v["work"] / (v["ms"] * 1e-3) / 1e9} if (v["work"] > 0 and k != "gemm_tcgen05") else {})}
+                           for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    if rank == 0 and not args.no_cpu_baseline:
+        cfgc, sdc, rows = cpu_sample(wl, args.cpu_utts)
+        t0 = time.perf_counter()
+        cpu_oracle_step(sdc, cfgc, rows, wl)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": args.cpu_utts * wl["seconds"] / dt, "unit": "audio-s/s",
+                                "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "%d x %.0f s utterances, one pass, same model/mode/beam (oracle port of the "
+                                          "reference path, torch-CPU ops + the reference's Python search loops)"
+                                          % (args.cpu_utts, wl["seconds"])}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,6 +48,16 @@ const char* wb_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
 unsigned long long wb_launch_count(void);
 
+/* Per-kernel-family profiler: when enabled, every launch is bracketed by CUDA events on the
+ * launching stream.  wb_prof_collect synchronises the device and returns, per tag, the summed
+ * elapsed ms, the summed algorithmic work (FLOPs for gemm_tcgen05, bytes for the memory-bound
+ * kernels, 0 where not tracked) and the number of launches since wb_prof_reset. */
+void wb_prof_enable(int on);
+void wb_prof_reset(void);
+int wb_prof_num_tags(void);
+const char* wb_prof_tag_name(int tag);
+int wb_prof_collect(double* ms, double* work, long long* launches);
+
 /* ------------------------------------------------------------------------------------------
  * A. fbank  — replaces wenet/dataset/processor.py:226-256 compute_fbank, i.e.
  *    torchaudio.compliance.kaldi.fbank(waveform*32768, num_mel_bins, 25 ms / 10 ms, dither 0,

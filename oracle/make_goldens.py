@@ -1,0 +1,125 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference, through
+oracle/shim.py) on deterministic synthetic weights (wenet_b200/synth.py) and inputs.
+
+Run in the build container only:   python oracle/make_goldens.py
+The fixtures hold OUTPUTS only (inputs and weights are regenerated from seeds at test time), so they
+stay small.  TEST INFRASTRUCTURE — nothing in wenet_b200/ imports this.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import shim  # noqa: E402
+from wenet_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SEED = 777
+
+
+def ref_fbank(pcm_i16: torch.Tensor, n: int) -> torch.Tensor:
+    shim.install()
+    from wenet.dataset import processor
+    wav = (pcm_i16[:n].float() / 32768.0).unsqueeze(0)
+    s = processor.compute_fbank(dict(key="k", wav=wav, sample_rate=16000), num_mel_bins=80, frame_length=25,
+                                frame_shift=10, dither=0.0)
+    return s["feat"]
+
+
+def fbank_goldens():
+    ns = [32000 + 123, 20800, 400, 16000 * 5]
+    pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
+    out = {"num_samples": np.array(ns)}
+    for b, n in enumerate(ns):
+        out["feat%d" % b] = ref_fbank(pcm[b], n).numpy()
+    np.savez_compressed(os.path.join(GOLD, "fbank.npz"), **out)
+    print("fbank:", {k: v.shape for k, v in out.items()})
+
+
+def model_goldens(name, recipe, ns, beam=4, ctc_weight=0.5, store_logp=True, chunk=(4, 2), stream=True):
+    torch.manual_seed(0)
+    cfg = synth.recipe(recipe)
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    ref_cfg = dict(cfg, cmvn=None)      # the CMVN statistics come with the state_dict (buffers), not a file
+    ref_cfg.pop("cmvn_conf", None)
+    model = shim.init_reference_model(ref_cfg)
+    if cfg.get("cmvn") is not None:
+        from wenet.models.transformer.cmvn import GlobalCMVN
+        model.encoder.global_cmvn = GlobalCMVN(torch.zeros(80), torch.ones(80))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith("num_batches_tracked") for k in missing), missing
+    model.eval()
+    pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
+    feats = [ref_fbank(pcm[b], n) for b, n in enumerate(ns)]
+    lens = torch.tensor([f.shape[0] for f in feats])
+    T = int(lens.max())
+    xs = torch.zeros(len(ns), T, 80)
+    for b, f in enumerate(feats):
+        xs[b, :f.shape[0]] = f
+    out = {"num_samples": np.array(ns), "beam": np.array(beam), "ctc_weight": np.array(ctc_weight)}
+    from wenet.models.transformer.search import (attention_rescoring, ctc_greedy_search, ctc_prefix_beam_search)
+    with torch.no_grad():
+        enc, mask = model.encoder(xs, lens, decoding_chunk_size=-1, num_decoding_left_chunks=-1)
+        enc_lens = mask.squeeze(1).sum(1)
+        out["enc_lens"] = enc_lens.numpy()
+        out["enc_out"] = enc.numpy()
+        logp = model.ctc_logprobs(enc)
+        if store_logp:
+            out["ctc_logp"] = logp.numpy()
+        tv, ti = logp.topk(max(beam, 10), dim=-1)
+        out["ctc_topk_val"], out["ctc_topk_idx"] = tv.numpy(), ti.numpy().astype(np.int32)
+        g = ctc_greedy_search(logp, enc_lens)
+        for b, r in enumerate(g):
+            out["greedy%d" % b] = np.array(r.tokens, dtype=np.int32)
+        pb = ctc_prefix_beam_search(logp, enc_lens, beam)
+        for b, r in enumerate(pb):
+            out["nbest_n%d" % b] = np.array(len(r.nbest))
+            for i, (h, s, t) in enumerate(zip(r.nbest, r.nbest_scores, r.nbest_times)):
+                out["nbest%d_%d" % (b, i)] = np.array(h, dtype=np.int32)
+                out["nbest_time%d_%d" % (b, i)] = np.array(t, dtype=np.int32)
+            out["nbest_scores%d" % b] = np.array(r.nbest_scores, dtype=np.float64)
+        rw = cfg["model_conf"].get("reverse_weight", 0.0)
+        rs = attention_rescoring(model, pb, enc, enc_lens, ctc_weight, rw)
+        for b, r in enumerate(rs):
+            out["resc_tokens%d" % b] = np.array(r.tokens, dtype=np.int32)
+            out["resc_score%d" % b] = np.array(r.score, dtype=np.float64)
+            out["resc_conf%d" % b] = np.array(r.confidence, dtype=np.float64)
+        if cfg["encoder_conf"]["use_dynamic_chunk"]:
+            enc_c, _ = model.encoder(xs, lens, decoding_chunk_size=chunk[0], num_decoding_left_chunks=chunk[1])
+            out["enc_out_chunk"] = enc_c.numpy()
+            out["chunk"] = np.array(chunk)
+            if stream:
+                # streaming: forward_chunk over utterance 0 (encoder.py:302-362), chunk 4 / 2 left chunks
+                ys, _ = model.encoder.forward_chunk_by_chunk(xs[0:1, :lens[0]], chunk[0], chunk[1])
+                out["stream_out"] = ys.numpy()
+                att = torch.zeros(0, 0, 0, 0)
+                cnn = torch.zeros(0, 0, 0, 0)
+                win = (chunk[0] - 1) * 4 + 7
+                y, att, cnn = model.encoder.forward_chunk(xs[0:1, :win], 0, chunk[0] * chunk[1], att, cnn)
+                y2, att2, cnn2 = model.encoder.forward_chunk(xs[0:1, 4 * chunk[0]:4 * chunk[0] + win], y.size(1),
+                                                             chunk[0] * chunk[1], att, cnn)
+                out["stream_y1"], out["stream_att1"], out["stream_cnn1"] = y.numpy(), att.numpy(), cnn.numpy()
+                out["stream_y2"], out["stream_att2"], out["stream_cnn2"] = y2.numpy(), att2.numpy(), cnn2.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    toks = [len(out["greedy%d" % b]) for b in range(len(ns))]
+    blank = float((logp.argmax(-1) == 0).float().mean())
+    print(name, "enc", tuple(enc.shape), "greedy tokens", toks, "blank frac %.2f" % blank,
+          "nbest0", out["nbest0_0"].tolist()[:12], "size %.0f KB" % (os.path.getsize(os.path.join(GOLD, name + ".npz")) / 1024))
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["fbank", "tiny", "tiny_bn", "u2pp_small"]
+    if "fbank" in which:
+        fbank_goldens()
+    if "tiny" in which:
+        model_goldens("tiny", "tiny", [32000 + 123, 20800, 48000])
+    if "tiny_bn" in which:
+        model_goldens("tiny_bn", "tiny_bn", [32000 + 123, 20800, 48000], stream=False)
+    if "u2pp_small" in which:
+        model_goldens("u2pp_small", "u2pp_small", [48000, 30000], beam=10, store_logp=False, chunk=(16, 4), stream=False)

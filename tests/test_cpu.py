@@ -1,0 +1,200 @@
+"""CPU-only suite (no GPU, no reference tree needed): oracle vs committed golden vectors, host logic,
+C-ABI surface, multi-process sharding over gloo.  Runs in a few minutes."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import SEED, batch_inputs, decoder_cfg, err, load_golden, oracle_cfg
+from oracle import wenet_oracle as O
+from wenet_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI surface
+def test_library_exports_every_declared_symbol():
+    from wenet_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "wenet_b200.h")).read()
+    declared = set(re.findall(r"\b(wb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"wb_stream_t"}
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load()  # raises if the .so is missing or lacks a symbol (getattr on each prototype)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.wb_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never route to the oracle."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from wenet_b200 import _lib
+    from wenet_b200.asr_model import B200ASRModel
+    cfg = synth.recipe("tiny")
+    with pytest.raises(_lib.WbError):
+        B200ASRModel(cfg, synth.synth_state_dict(cfg))
+    import wenet_b200
+    src = ""
+    for f in os.listdir(os.path.dirname(wenet_b200.__file__)):
+        if f.endswith(".py"):
+            src += open(os.path.join(os.path.dirname(wenet_b200.__file__), f)).read()
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+# ------------------------------------------------------------------ oracle vs golden fixtures
+def test_oracle_fbank_vs_golden():
+    g = load_golden("fbank")
+    ns = g["num_samples"].tolist()
+    pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
+    for b, n in enumerate(ns):
+        got = O.fbank(pcm[b, :n].float())
+        ref = torch.from_numpy(g["feat%d" % b])
+        assert got.shape == ref.shape
+        assert err(got, ref)[0] < 1e-4
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_bn"])
+def test_oracle_model_vs_golden(name):
+    """The oracle restatement on regenerated synthetic weights reproduces what the unmodified reference
+    produced in the build container (also proves synth.py is deterministic across boxes)."""
+    g = load_golden(name)
+    cfg = synth.recipe(name)
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    ns = g["num_samples"].tolist()
+    _, xs, lens = batch_inputs(ns, lambda p: O.fbank(p.float()))
+    el = g["enc_lens"].tolist()
+    with torch.no_grad():
+        enc, mask = O.encoder_forward(sd, oracle_cfg(cfg, sd), xs, lens)
+        assert mask.squeeze(1).sum(1).tolist() == el
+        for b, n in enumerate(el):
+            assert err(enc[b, :n], torch.from_numpy(g["enc_out"][b, :n]))[0] < 5e-4
+        lp = O.ctc_logprobs(sd, enc)
+        for b, n in enumerate(el):
+            assert err(lp[b, :n], torch.from_numpy(g["ctc_logp"][b, :n]))[0] < 2e-3
+        ref_lp = torch.from_numpy(g["ctc_logp"])
+        assert [list(x) for x in O.ctc_greedy_search(ref_lp, torch.tensor(el))] == \
+            [g["greedy%d" % b].tolist() for b in range(len(el))]
+        beam = int(g["beam"])
+        pb = O.ctc_prefix_beam_search(ref_lp, torch.tensor(el), beam)
+        for b, r in enumerate(pb):
+            n = int(g["nbest_n%d" % b])
+            assert r["nbest"] == [g["nbest%d_%d" % (b, i)].tolist() for i in range(n)]
+            assert r["nbest_times"] == [g["nbest_time%d_%d" % (b, i)].tolist() for i in range(n)]
+            assert np.allclose(r["nbest_scores"], g["nbest_scores%d" % b], rtol=0, atol=1e-12)
+        rw = cfg["model_conf"].get("reverse_weight", 0.0)
+        rs = O.attention_rescoring(sd, decoder_cfg(cfg), pb, torch.from_numpy(g["enc_out"]), torch.tensor(el),
+                                   cfg["output_dim"] - 1, cfg["output_dim"] - 1, float(g["ctc_weight"]), rw)
+        for b, r in enumerate(rs):
+            assert r["tokens"] == g["resc_tokens%d" % b].tolist()
+            assert abs(r["best_score"] - float(g["resc_score%d" % b])) < 1e-3
+        if "stream_y1" in g:
+            c, l = [int(v) for v in g["chunk"]]
+            win = (c - 1) * 4 + 7
+            e = oracle_cfg(cfg, sd)
+            y, att, cnn = O.encoder_forward_chunk(sd, e, xs[0:1, :win], 0, c * l, torch.zeros(0, 0, 0, 0),
+                                                  torch.zeros(0, 0, 0, 0))
+            assert err(y, torch.from_numpy(g["stream_y1"]))[0] < 5e-4
+            y2, att2, cnn2 = O.encoder_forward_chunk(sd, e, xs[0:1, 4 * c:4 * c + win], y.size(1), c * l, att, cnn)
+            assert err(y2, torch.from_numpy(g["stream_y2"]))[0] < 5e-4
+            assert err(att2, torch.from_numpy(g["stream_att2"]))[0] < 5e-4
+            assert err(cnn2, torch.from_numpy(g["stream_cnn2"]))[0] < 5e-4
+
+
+def test_oracle_bf16_emulation_is_within_reference_bf16_yardstick():
+    """The operand-rounding model of the GPU path stays inside the reference's own bf16 error budget."""
+    cfg = synth.recipe("tiny")
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    _, xs, lens = batch_inputs([32000, 20000], lambda p: O.fbank(p.float()))
+    with torch.no_grad():
+        a, m = O.encoder_forward(sd, oracle_cfg(cfg, sd), xs, lens)
+        b, _ = O.encoder_forward(sd, oracle_cfg(cfg, sd), xs, lens, quant=O.bf16_round)
+    n = int(m[1].sum())
+    mx, mn = err(a[1, :n], b[1, :n])
+    assert mx < 5.9e-2 and mn < 8.2e-3
+
+
+# ------------------------------------------------------------------ host logic
+def test_packer_layouts():
+    from wenet_b200.weights import ModelSpec, interleave_glu, pack_state_dict, split3_weight
+    cfg = synth.recipe("tiny")
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    spec = ModelSpec(cfg)
+    p = pack_state_dict(spec, sd)
+    d, F2 = 128, 19
+    # embed.out column permutation: reference flattens (c, f), this build (f, c)
+    x = torch.randn(3, d, F2)                       # (row, c, f)
+    ref = torch.nn.functional.linear(x.reshape(3, d * F2), sd["encoder.embed.out.0.weight"].to(torch.bfloat16).float())
+    got = torch.nn.functional.linear(x.permute(0, 2, 1).reshape(3, F2 * d), p["embed.out.w"].float())
+    assert torch.allclose(ref, got, atol=1e-5)
+    # conv2 im2col order (kh, kw, c_in)
+    w = sd["encoder.embed.conv.2.weight"]
+    assert torch.equal(p["embed.conv2.w"].float().view(d, 3, 3, d)[5, 1, 2, 7], w[5, 7, 1, 2].to(torch.bfloat16).float())
+    # GLU interleave: value/gate pairs stay aligned
+    wi, bi = interleave_glu(torch.arange(2 * d).float().unsqueeze(1), torch.arange(2 * d).float())
+    assert bi[:16].tolist() == list(range(16)) and bi[16:32].tolist() == list(range(d, d + 16))
+    # bf16x3 split reconstructs fp32 weights to ~2^-17
+    w32 = torch.randn(8, 16)
+    s3 = split3_weight(w32).float()
+    assert (s3[:, :16] + s3[:, 32:] - w32).abs().max() < 2e-5 * w32.abs().max() + 1e-6
+    assert torch.equal(s3[:, :16], s3[:, 16:32])
+    # pad_vec = GLU(pointwise_conv1(0))
+    b1 = sd["encoder.encoders.0.conv_module.pointwise_conv1.bias"]
+    assert torch.allclose(p["enc.0.conv.pad_vec"], b1[:d] * torch.sigmoid(b1[d:]))
+
+
+@pytest.mark.parametrize("key,val", [("input_layer", "conv2d6"), ("pos_enc_layer_type", "abs_pos"),
+                                     ("selfattention_layer_type", "selfattn"), ("activation_type", "relu")])
+def test_unsupported_configs_raise(key, val):
+    from wenet_b200.weights import ModelSpec
+    cfg = synth.recipe("tiny")
+    cfg["encoder_conf"][key] = val
+    with pytest.raises(NotImplementedError):
+        ModelSpec(cfg)
+
+
+def test_shard_partition_properties():
+    from wenet_b200.shard import shard_utterances
+    lens = [2998, 500, 1200, 2998, 800, 1999, 300, 2500, 999, 1500, 2998]
+    for ws in (1, 2, 4, 8):
+        parts = [shard_utterances(lens, ws, r) for r in range(ws)]
+        assert sorted(i for p in parts for i in p) == list(range(len(lens)))
+    two = [shard_utterances(lens, 2, r) for r in range(2)]
+    load = [sum(lens[i] for i in p) for p in two]
+    assert abs(load[0] - load[1]) < 0.2 * sum(lens)
+
+
+def test_shard_over_gloo_world_size_2(tmp_path):
+    """N>1 host path: two processes (gloo), each owns its shard, host-side gather of results only."""
+    script = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from wenet_b200.shard import shard_utterances
+dist.init_process_group("gloo")
+rank, ws = dist.get_rank(), dist.get_world_size()
+lens = [2998, 500, 1200, 2998, 800, 1999, 300, 2500]
+mine = shard_utterances(lens, ws, rank)
+res = [None] * ws
+dist.all_gather_object(res, {i: [i, lens[i] %% 7] for i in mine})      # token lists stand-in
+merged = {}
+for r in res: merged.update(r)
+assert sorted(merged) == list(range(len(lens))), merged
+secs = torch.tensor([sum(lens[i] for i in mine)], dtype=torch.float64)
+dist.all_reduce(secs)
+assert int(secs.item()) == sum(lens)
+dist.barrier()
+print("rank", rank, "ok", mine)
+''' % ROOT
+    f = tmp_path / "shard_gloo.py"
+    f.write_text(script)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(f)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

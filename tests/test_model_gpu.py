@@ -1,0 +1,214 @@
+"""End-to-end parity on the GPU: the CUDA path (through the C ABI) against
+  (1) the committed golden fixtures produced by the UNMODIFIED reference in fp32
+      (oracle/make_goldens.py), and
+  (2) the CPU oracle evaluated at the GPU path's operand precision (bf16 GEMM operands, fp32
+      accumulation / residual stream) on the same seeded weights and inputs.
+
+Tolerances (stated once, used below):
+  * fbank: |log-mel error| <= 1e-3 (fp32 arithmetic, different FFT factorisation).
+  * encoder_out / CTC log-probs vs the bf16-emulating oracle: after the embedding (no rounding
+    flips yet) max <= 3e-3 / mean <= 1e-4; after L layers the tensor core's non-IEEE fp32
+    accumulation flips bf16 operand roundings (each flip = 2^-8 relative on one operand), so the
+    end-to-end bound is the same as against fp32: it must stay below the reference-bf16 yard-stick
+    and below 1.5x the oracle's own fp32-vs-bf16-emulation distance (DESIGN.md "parity budget").
+  * encoder_out / CTC log-probs vs the fp32 reference goldens: must be no worse than the reference's
+    OWN bf16 autocast path (max 5.9e-2 / mean 8.2e-3 on encoder_out,
+    max 6.5e-2 / mean 1.6e-2 on log-probs).
+  * search kernels on identical posteriors: token ids and times bit-exact, scores 1e-9 relative
+    (tests/test_ops_gpu.py).  End to end (posteriors differ by the above): best hypothesis ids equal
+    the reference's on these peaky synthetic posteriors.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import SEED, batch_inputs, decoder_cfg, err, load_golden, oracle_cfg
+from oracle import wenet_oracle as O
+from wenet_b200 import synth
+
+NS = {"tiny": [32000 + 123, 20800, 48000], "tiny_bn": [32000 + 123, 20800, 48000], "u2pp_small": [48000, 30000]}
+
+
+def _gpu_fbank(ns):
+    from wenet_b200.fbank import FbankExtractor
+    pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
+    ex = FbankExtractor(80)
+    nsd = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    feats = ex(pcm.cuda(), nsd)
+    lens = torch.tensor([ex.num_frames(n) for n in ns], dtype=torch.int64)
+    return feats[:, :int(lens.max())].contiguous(), lens
+
+
+def test_fbank_golden():
+    g = load_golden("fbank")
+    ns = g["num_samples"].tolist()
+    feats, lens = _gpu_fbank(ns)
+    for b in range(len(ns)):
+        ref = torch.from_numpy(g["feat%d" % b])
+        assert ref.shape[0] == int(lens[b])
+        mx, mean = err(feats[b, :ref.shape[0]].cpu(), ref)
+        assert mx < 1e-3, (b, mx, mean)
+
+
+@pytest.fixture(scope="module", params=["tiny", "tiny_bn", "u2pp_small"])
+def setup(request):
+    from wenet_b200.asr_model import B200ASRModel
+    name = request.param
+    cfg = synth.recipe(name)
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    model = B200ASRModel(cfg, sd)
+    feats, lens = _gpu_fbank(NS[name])
+    return name, cfg, sd, model, feats, lens, load_golden(name)
+
+
+def _packed(t, el):
+    return torch.cat([t[b, :el[b]] for b in range(len(el))], 0)
+
+
+def test_encoder_and_ctc(setup):
+    name, cfg, sd, model, feats, lens, g = setup
+    el = g["enc_lens"].tolist()
+    out, masks = model.encoder(feats, lens.cuda(), decoding_chunk_size=-1, num_decoding_left_chunks=-1)
+    assert out.shape == tuple(g["enc_out"].shape)
+    assert masks.squeeze(1).sum(1).cpu().tolist() == el
+    got = _packed(out.cpu(), el)
+    ref32 = _packed(torch.from_numpy(g["enc_out"]), el)
+    with torch.no_grad():
+        oq, _ = O.encoder_forward(sd, oracle_cfg(cfg, sd), feats.cpu(), lens, -1, -1, O.bf16_round)
+        lq = O.ctc_logprobs(sd, oq, quant=O.bf16_round)
+    refq = _packed(oq, el)
+    mx32, mn32 = err(got, ref32)
+    mxq, mnq = err(got, refq)
+    print("%s encoder_out: vs fp32 reference max %.3e mean %.3e; vs bf16-emulating oracle max %.3e mean %.3e"
+          % (name, mx32, mn32, mxq, mnq))
+    with torch.no_grad():
+        o32, _ = O.encoder_forward(sd, oracle_cfg(cfg, sd), feats.cpu(), lens, -1, -1, None)
+    mxo, mno = err(_packed(o32, el), refq)
+    print("%s oracle fp32 vs oracle bf16-emulation: max %.3e mean %.3e" % (name, mxo, mno))
+    assert mx32 < 5.9e-2 and mn32 < 8.2e-3
+    assert mxq < 5.9e-2 and mnq < 1.5 * mno + 1e-4
+    assert mn32 < 1.5 * mno + 1e-4      # no worse than pure operand rounding explains
+    # padded rows are zero
+    for b, n in enumerate(el):
+        assert (out[b, n:] == 0).all()
+    # CTC posteriors through the public API (padded) == packed path
+    lp = model.ctc_logprobs(out).cpu()
+    lpq = _packed(lq, el)
+    mxl, mnl = err(_packed(lp, el), lpq)
+    print("%s ctc log-probs vs bf16-emulating oracle max %.3e mean %.3e" % (name, mxl, mnl))
+    # the synthetic CTC head is sharpened x8 (synth.py), which scales posterior errors by the same
+    # factor: bound the log-prob error by the oracle's own fp32-vs-bf16-emulation distance
+    with torch.no_grad():
+        l32 = O.ctc_logprobs(sd, o32)
+    mxlo, mnlo = err(_packed(l32, el), lpq)
+    mxl32, mnl32 = err(_packed(lp, el), _packed(l32, el))
+    print("%s ctc log-probs vs fp32 oracle max %.3e mean %.3e; oracle fp32-vs-emulation max %.3e mean %.3e"
+          % (name, mxl32, mnl32, mxlo, mnlo))
+    assert mnl32 < 1.5 * mnlo + 1e-3 and mxl32 < 3 * mxlo + 1e-2
+    if "ctc_logp" in g:
+        mx, mn = err(_packed(lp, el), _packed(torch.from_numpy(g["ctc_logp"]), el))
+        print("%s ctc log-probs vs fp32 reference max %.3e mean %.3e" % (name, mx, mn))
+        assert mn < 1.5 * mnlo + 1e-3 and mx < 3 * mxlo + 1e-2
+    # top-1 agreement with the reference on (almost) every frame
+    ref_top = _packed(torch.from_numpy(g["ctc_topk_idx"][:, :, 0].astype(np.int64)), el)
+    agree = float((_packed(lp, el).argmax(-1) == ref_top).float().mean())
+    assert agree > 0.98, agree
+
+
+def test_chunk_mask(setup):
+    name, cfg, sd, model, feats, lens, g = setup
+    if "enc_out_chunk" not in g:
+        pytest.skip("non-streaming recipe")
+    c, l = [int(v) for v in g["chunk"]]
+    el = g["enc_lens"].tolist()
+    out, _ = model.encoder(feats, lens.cuda(), decoding_chunk_size=c, num_decoding_left_chunks=l)
+    mx, mn = err(_packed(out.cpu(), el), _packed(torch.from_numpy(g["enc_out_chunk"]), el))
+    print("%s chunk(%d,%d) encoder_out vs fp32 reference max %.3e mean %.3e" % (name, c, l, mx, mn))
+    assert mx < 5.9e-2 and mn < 8.2e-3
+
+
+def test_decode(setup):
+    """decode() end to end.  Searches are checked EXACTLY against the CPU oracle run on the GPU path's own
+    log-probabilities (identical input => identical ids / times, scores to 1e-9); against the reference
+    goldens (whose posteriors differ by the bf16 budget) the frame-level and best-path agreement is
+    checked, exactly for the tiny recipes whose posteriors have clear margins."""
+    name, cfg, sd, model, feats, lens, g = setup
+    beam = int(g["beam"])
+    cw = float(g["ctc_weight"])
+    rw = cfg["model_conf"].get("reverse_weight", 0.0)
+    res = model.decode(["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"], feats, lens.cuda(),
+                       beam_size=beam, ctc_weight=cw, reverse_weight=rw)
+    el = g["enc_lens"].tolist()
+    out, _ = model.encoder(feats, lens.cuda(), -1, -1)
+    lp = model.ctc_logprobs(out).cpu()
+    og = O.ctc_greedy_search(lp, torch.tensor(el))
+    ob = O.ctc_prefix_beam_search(lp, torch.tensor(el), beam)
+    B = len(NS[name])
+    for b in range(B):
+        assert res["ctc_greedy_search"][b].tokens == og[b], ("greedy", b)
+        r = res["ctc_prefix_beam_search"][b]
+        assert [list(h) for h in r.nbest] == ob[b]["nbest"], ("nbest", b)
+        assert r.nbest_times == ob[b]["nbest_times"], ("times", b)
+        assert np.allclose(r.nbest_scores, ob[b]["nbest_scores"], rtol=1e-9, atol=1e-9)
+        assert list(r.tokens) == ob[b]["nbest"][0] and r.score == r.nbest_scores[0]
+        if name.startswith("tiny"):
+            assert res["ctc_greedy_search"][b].tokens == g["greedy%d" % b].tolist(), ("greedy vs reference", b)
+            assert list(r.tokens) == g["nbest%d_0" % b].tolist(), ("beam best vs reference", b)
+            a = res["attention_rescoring"][b]
+            assert list(a.tokens) == g["resc_tokens%d" % b].tolist(), ("rescoring best vs reference", b)
+            assert abs(a.score - float(g["resc_score%d" % b])) < 0.02 * max(1.0, abs(a.score)) + 0.05
+            assert abs(a.confidence - float(g["resc_conf%d" % b])) < 0.05
+
+
+def test_rescoring_on_identical_inputs(setup):
+    """Decoder + rescoring against the bf16-emulating oracle on IDENTICAL encoder output and n-best."""
+    name, cfg, sd, model, feats, lens, g = setup
+    beam = int(g["beam"])
+    rw = cfg["model_conf"].get("reverse_weight", 0.0)
+    el = g["enc_lens"].tolist()
+    res = model.decode(["ctc_prefix_beam_search", "attention_rescoring"], feats, lens.cuda(), beam_size=beam,
+                       ctc_weight=0.5, reverse_weight=rw)
+    out, _ = model.encoder(feats, lens.cuda(), -1, -1)
+    enc = out.cpu().to(torch.bfloat16).float()   # the decoder consumes the bf16 copy of encoder_out
+    beams = [dict(nbest=[list(h) for h in r.nbest], nbest_scores=r.nbest_scores) for r in res["ctc_prefix_beam_search"]]
+    with torch.no_grad():
+        ref = O.attention_rescoring(sd, decoder_cfg(cfg), beams, enc, torch.tensor(el), model.sos, model.eos, 0.5, rw,
+                                    quant=O.bf16_round)
+    for b, (r, a) in enumerate(zip(ref, res["attention_rescoring"])):
+        sc = np.array(a.nbest_scores)
+        rs = np.array(r["scores"])
+        print("%s utt %d rescoring scores: max |diff| %.3e (|score| up to %.1f)" % (name, b, np.abs(sc - rs).max(), np.abs(rs).max()))
+        assert np.abs(sc - rs).max() < 0.02 * max(1.0, np.abs(rs).max()), (b, sc, rs)
+        if np.sort(rs)[-1] - np.sort(rs)[-2] > 0.05 if len(rs) > 1 else True:
+            assert list(a.tokens) == r["tokens"]
+
+
+def test_forward_attention_decoder_api(setup):
+    name, cfg, sd, model, feats, lens, g = setup
+    el = g["enc_lens"].tolist()
+    out, _ = model.encoder(feats, lens.cuda(), -1, -1)
+    enc = out[0:1, :el[0]]
+    V = cfg["output_dim"]
+    hyps = torch.tensor([[model.sos, 3, 5, 7, 9], [model.sos, 4, 6, model.eos, model.eos]], dtype=torch.long)
+    hl = torch.tensor([5, 3])
+    rw = cfg["model_conf"].get("reverse_weight", 0.0)
+    lp, rlp = model.forward_attention_decoder(hyps.cuda(), hl.cuda(), enc, rw)
+    with torch.no_grad():
+        ref, rref = O.forward_attention_decoder(sd, decoder_cfg(cfg), hyps, hl, enc.cpu().to(torch.bfloat16).float(),
+                                                rw, model.eos, quant=O.bf16_round)
+    with torch.no_grad():
+        ref32, rref32 = O.forward_attention_decoder(sd, decoder_cfg(cfg), hyps, hl, enc.cpu(), rw, model.eos, quant=None)
+    assert lp.shape == (2, 5, V)
+    for i, n in enumerate(hl.tolist()):
+        mx, mn = err(lp[i, :n].cpu(), ref[i, :n])
+        mx32, mn32 = err(lp[i, :n].cpu(), ref32[i, :n])
+        mxo, mno = err(ref[i, :n], ref32[i, :n])
+        print("%s decoder log-probs hyp %d: vs emulation max %.3e mean %.3e | vs fp32 max %.3e mean %.3e | "
+              "oracle fp32-vs-emulation max %.3e mean %.3e" % (name, i, mx, mn, mx32, mn32, mxo, mno))
+        assert mn32 < 1.5 * mno + 2e-3 and mx32 < 3 * mxo + 2e-2, (i, mx32, mn32, mxo, mno)
+        if rw > 0:
+            mx32, mn32 = err(rlp[i, :n].cpu(), rref32[i, :n])
+            mxo, mno = err(rref[i, :n], rref32[i, :n])
+            assert mn32 < 1.5 * mno + 2e-3 and mx32 < 3 * mxo + 2e-2, ("r2l", i, mx32, mn32, mxo, mno)

@@ -1,0 +1,51 @@
+"""Streaming encoder (forward_chunk / forward_chunk_by_chunk) on the GPU against the reference goldens
+and the oracle (encoder.py:204-362)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import SEED, batch_inputs, err, load_golden, oracle_cfg
+from oracle import wenet_oracle as O
+from wenet_b200 import synth
+
+
+def test_forward_chunk_vs_reference_golden():
+    from wenet_b200.asr_model import B200ASRModel
+    g = load_golden("tiny")
+    cfg = synth.recipe("tiny")
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    model = B200ASRModel(cfg, sd)
+    ns = g["num_samples"].tolist()
+    _, xs, lens = batch_inputs(ns, lambda p: O.fbank(p.float()))
+    xs = xs.cuda()
+    c, l = [int(v) for v in g["chunk"]]
+    win = (c - 1) * 4 + 7
+    att = torch.zeros(0, 0, 0, 0, device="cuda")
+    cnn = torch.zeros(0, 0, 0, 0, device="cuda")
+    y, att, cnn = model.encoder.forward_chunk(xs[0:1, :win], 0, c * l, att, cnn)
+    assert tuple(y.shape) == tuple(g["stream_y1"].shape)
+    assert tuple(att.shape) == tuple(g["stream_att1"].shape) and tuple(cnn.shape) == tuple(g["stream_cnn1"].shape)
+    print("chunk1 y", err(y.cpu(), torch.from_numpy(g["stream_y1"])), "att", err(att.cpu(), torch.from_numpy(g["stream_att1"])),
+          "cnn", err(cnn.cpu(), torch.from_numpy(g["stream_cnn1"])))
+    assert err(y.cpu(), torch.from_numpy(g["stream_y1"]))[0] < 5.9e-2
+    y2, att2, cnn2 = model.encoder.forward_chunk(xs[0:1, 4 * c:4 * c + win], y.size(1), c * l, att, cnn)
+    assert tuple(att2.shape) == tuple(g["stream_att2"].shape)
+    for got, key in ((y2, "stream_y2"), (att2, "stream_att2"), (cnn2, "stream_cnn2")):
+        mx, mn = err(got.cpu(), torch.from_numpy(g[key]))
+        print(key, mx, mn)
+        assert mx < 5.9e-2 and mn < 8.2e-3
+    # whole utterance chunk by chunk == reference forward_chunk_by_chunk; and == chunk-masked full forward
+    n0 = int(lens[0])
+    ys, masks = model.encoder.forward_chunk_by_chunk(xs[0:1, :n0], c, l)
+    mx, mn = err(ys.cpu(), torch.from_numpy(g["stream_out"]))
+    print("chunk-by-chunk vs reference", mx, mn)
+    assert ys.shape == g["stream_out"].shape and mx < 5.9e-2 and mn < 8.2e-3
+    full, _ = model.encoder(xs[0:1, :n0], lens[0:1].cuda(), c, l)
+    mx, mn = err(ys.cpu(), full[:, :ys.size(1)].cpu())
+    print("chunk-by-chunk vs chunk-masked forward (both CUDA)", mx, mn)
+    assert mx < 5.9e-2 and mn < 8.2e-3
+    # simulate_streaming decode path runs
+    res = model.decode(["ctc_greedy_search"], xs[0:1, :n0], lens[0:1].cuda(), decoding_chunk_size=c,
+                       num_decoding_left_chunks=l, simulate_streaming=True)
+    assert len(res["ctc_greedy_search"]) == 1

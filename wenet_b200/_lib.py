@@ -32,6 +32,11 @@ _PROTOS = {
     "wb_last_error": (C.c_char_p, []),
     "wb_version": (C.c_char_p, []),
     "wb_launch_count": (C.c_ulonglong, []),
+    "wb_prof_enable": (None, [i32]),
+    "wb_prof_reset": (None, []),
+    "wb_prof_num_tags": (i32, []),
+    "wb_prof_tag_name": (C.c_char_p, [i32]),
+    "wb_prof_collect": (i32, [vp, vp, vp]),
     "wb_fbank_create": (i32, [C.POINTER(vp), i32, i32, i32, f32, vp, vp]),
     "wb_fbank_destroy": (None, [vp]),
     "wb_fbank_forward": (i32, [vp, vp, i32, i64, vp, i32, f32, vp, i64, i32, vp]),

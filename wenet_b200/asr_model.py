@@ -123,6 +123,7 @@ class B200ASRModel:
         self._ws = None
         self._ws2 = None
         self.keep_layer_dump = False
+        self.d2h_bytes = 0      # bytes copied device -> host by decode() (bench.py: e2e.d2h_bytes_per_step)
 
     # ----- reference jit-export style accessors (asr_model.py:360-450) -----
     def subsampling_rate(self) -> int:
@@ -150,6 +151,11 @@ class B200ASRModel:
     def from_reference(cls, model, configs: dict, device=None):
         """Wrap a loaded reference ASRModel (same weights, same results, B200 kernels)."""
         return cls(configs, {k: v.detach().cpu() for k, v in model.state_dict().items()}, device=device)
+
+    def _host(self, t: torch.Tensor) -> np.ndarray:
+        """device -> host copy of a result tensor (counted)."""
+        self.d2h_bytes += t.numel() * t.element_size()
+        return t.cpu().numpy()
 
     # ----- buffers -----
     def _workspace(self, nbytes: int, which: int = 0) -> torch.Tensor:
@@ -339,7 +345,7 @@ class B200ASRModel:
         lens = torch.zeros(B, device=self.device, dtype=torch.int32)
         check(self._lib.wb_ctc_greedy_search(ptr(ti), ti.stride(0), ptr(eo.seq_start), ptr(eo.seq_len), B, int(blank_id),
                                              ptr(toks), stride, ptr(lens), cur_stream()), "wb_ctc_greedy_search")
-        th, lh = toks.cpu().numpy(), lens.cpu().numpy()
+        th, lh = self._host(toks), self._host(lens)
         return [DecodeResult(th[b, :lh[b]].tolist()) for b in range(B)]
 
     def _prefix_beam(self, eo: _EncOut, tv, ti, beam_size: int, blank_id: int) -> List[DecodeResult]:
@@ -357,8 +363,8 @@ class B200ASRModel:
                                             int(beam_size), int(blank_id), max_len, ptr(toks), ptr(times), ptr(lens),
                                             ptr(scores), ptr(nhyp), ptr(ws), wsb, cur_stream()),
               "wb_ctc_prefix_beam_search")
-        th, mh, lh = toks.cpu().numpy(), times.cpu().numpy(), lens.cpu().numpy()
-        sh, nh = scores.cpu().numpy(), nhyp.cpu().numpy()
+        th, mh, lh = self._host(toks), self._host(times), self._host(lens)
+        sh, nh = self._host(scores), self._host(nhyp)
         out = []
         for b in range(B):
             n = int(nh[b])
@@ -403,8 +409,8 @@ class B200ASRModel:
                                          ptr(ctc_scores), self.sos, self.eos, float(ctc_weight),
                                          float(reverse_weight if use_r2l else 0.0), ptr(l2r), ptr(r2l), ptr(hyp_score),
                                          ptr(best), ptr(ws), ws.numel(), cur_stream()), "wb_attention_rescoring")
-        l2r_h, r2l_h = l2r.cpu().numpy(), r2l.cpu().numpy()
-        hs, bh = hyp_score.cpu().numpy(), best.cpu().numpy()
+        l2r_h, r2l_h = self._host(l2r), self._host(r2l)
+        hs, bh = self._host(hyp_score), self._host(best)
         out = []
         h0 = 0
         row0 = np.concatenate([[0], np.cumsum(hyp_len + 1)]).astype(np.int64)
@@ -459,7 +465,8 @@ class B200ASRModel:
         rlp = torch.empty(R, ldl, device=self.device, dtype=torch.float32) if use_r2l else None
         wsb = lib.wb_rescoring_workspace_bytes(self.dm.handle, Tp, R)
         ws = self._workspace(wsb)
-        check(lib.wb_decoder_logprobs(self.dm.handle, ptr(enc_bf16), Tp, ptr(_i32([0])), ptr(_i32([Tp])), 1, N,
+        starts, slens = _i32([0]), _i32([Tp])   # keep the host arrays alive across the call
+        check(lib.wb_decoder_logprobs(self.dm.handle, ptr(enc_bf16), Tp, ptr(starts), ptr(slens), 1, N,
                                       ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks), int(hy[0, 0]), self.eos,
                                       int(use_r2l), ptr(lp), ptr(rlp), ldl, ptr(ws), ws.numel(), cur_stream()),
               "wb_decoder_logprobs")

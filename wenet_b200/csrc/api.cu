@@ -172,6 +172,18 @@ const char* wb_last_error(void) { return get_last_error(); }
 const char* wb_version(void) { return "wenet_b200 0.1 (sm_100a)"; }
 unsigned long long wb_launch_count(void) { return g_launch_count; }
 
+void wb_prof_enable(int on) { g_prof_on = on; }
+void wb_prof_reset(void) { wb::prof_reset(); }
+int wb_prof_num_tags(void) { return PT_COUNT; }
+const char* wb_prof_tag_name(int tag) {
+    static const char* names[PT_COUNT] = {"gemm_tcgen05", "attention", "layernorm", "dwconv_norm_silu", "conv1",
+                                          "im2col", "relpos_kprep", "fbank", "logsoftmax_topk", "ctc_greedy",
+                                          "ctc_prefix_beam", "embed_tokens", "gather_logprob", "rescore_combine",
+                                          "misc"};
+    return (tag >= 0 && tag < PT_COUNT) ? names[tag] : "?";
+}
+int wb_prof_collect(double* ms, double* work, long long* launches) { return wb::prof_collect(ms, work, launches); }
+
 // ---------------------------------------------------------------- fbank
 struct wb_fbank {
     FbankPlan* plan;

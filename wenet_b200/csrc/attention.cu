@@ -397,6 +397,7 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid(ceil_div(a.max_q_len, AT_M), a.heads, a.batch);
+    ProfScope _ps(PT_ATTENTION, stream, 0.0);
     attention_kernel<<<grid, 128, AT_SMEM, stream>>>(tq, tk, tv, P);
     count_launch();
     WB_CHECK_LAUNCH();
@@ -410,6 +411,7 @@ int relpos_kprep(const void* k_bf16, long long ldk, const float* P, const int* r
     const long long warps = (long long)M * heads;
     const int block = 256;
     const long long grid = (warps * 32 + block - 1) / block;
+    ProfScope _ps(PT_KPREP, stream, (double)M * heads * 64 * 8.0);
     relpos_kprep_kernel<<<(unsigned)grid, block, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(k_bf16), ldk, P, row_pos, bias_u, bias_v, M, heads,
         reinterpret_cast<__nv_bfloat16*>(kprime_bf16), ldkp, kbias);

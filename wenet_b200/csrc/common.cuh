@@ -43,6 +43,28 @@ const char* get_last_error();
 extern unsigned long long g_launch_count;
 static inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
+// Optional per-kernel-family profiler (CUDA events on the launching stream around every launch).
+// Off by default; bench.py switches it on to obtain live per-kernel durations and roofline numbers.
+enum ProfTag : int {
+    PT_GEMM = 0, PT_ATTENTION, PT_LAYERNORM, PT_DWCONV, PT_CONV1, PT_IM2COL, PT_KPREP, PT_FBANK, PT_LOGSOFTMAX_TOPK,
+    PT_GREEDY, PT_PREFIX_BEAM, PT_EMBED, PT_GATHER_LOGPROB, PT_RESCORE, PT_MISC, PT_COUNT
+};
+extern int g_prof_on;
+void prof_begin(int tag, cudaStream_t st, double work);
+void prof_end(cudaStream_t st);
+void prof_reset();
+int prof_collect(double* ms, double* work, long long* launches);
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(int tag, cudaStream_t s, double work) : st(s), on(g_prof_on != 0) {
+        if (on) prof_begin(tag, st, work);
+    }
+    ~ProfScope() {
+        if (on) prof_end(st);
+    }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -172,6 +172,7 @@ int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream) {
         smem_set = smem;
     }
     dim3 grid(ceil_div(a.max_len, TT), a.batch);
+    ProfScope _ps(PT_DWCONV, stream, (double)a.batch * a.max_len * a.d * 4.0);
     dwconv_kernel<<<grid, DW_THREADS, smem, stream>>>(P);
     count_launch();
     WB_CHECK_LAUNCH();

@@ -135,6 +135,7 @@ int ctc_logsoftmax_topk(float* logits, long long ldl, int M, int V, int blank_id
         WB_CHECK_CUDA(cudaFuncSetAttribute(logsoftmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
+    ProfScope _ps(PT_LOGSOFTMAX_TOPK, stream, (double)M * V * 8.0);
     logsoftmax_topk_kernel<<<M, LS_THREADS, smem, stream>>>(logits, ldl, V, blank_id, blank_penalty, topk, topk_val,
                                                             topk_idx);
     count_launch();
@@ -145,6 +146,7 @@ int ctc_logsoftmax_topk(float* logits, long long ldl, int M, int V, int blank_id
 int ctc_greedy(const int* topk_idx, int topk, const int* seq_start, const int* seq_len, int batch, int blank_id,
                int* out_tokens, int out_stride, int* out_len, cudaStream_t stream) {
     if (batch <= 0) return WB_OK;
+    ProfScope _ps(PT_GREEDY, stream, 0.0);
     greedy_kernel<<<batch, 32, 0, stream>>>(topk_idx, topk, seq_start, seq_len, blank_id, out_tokens, out_stride,
                                             out_len);
     count_launch();

@@ -109,6 +109,7 @@ int embed_tokens(const int* tokens, const int* pos, int R, int d, const float* e
     WB_REQUIRE(d % 4 == 0, WB_ERR_BAD_ARG, "embed: d %% 4");
     const long long n = (long long)R * (d / 4);
     const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    ProfScope _ps(PT_EMBED, stream, (double)R * d * 12.0);
     embed_kernel<<<grid, 256, 0, stream>>>(tokens, pos, R, d, emb, pe, xscale, x);
     count_launch();
     WB_CHECK_LAUNCH();
@@ -118,6 +119,7 @@ int embed_tokens(const int* tokens, const int* pos, int R, int d, const float* e
 int gather_logprob(const float* logits, long long ldl, int R, int V, const int* target, float* tok_logp,
                    cudaStream_t stream) {
     if (R <= 0) return WB_OK;
+    ProfScope _ps(PT_GATHER_LOGPROB, stream, (double)R * V * 4.0);
     gather_logprob_kernel<<<R, GL_THREADS, 0, stream>>>(logits, ldl, V, target, tok_logp);
     count_launch();
     WB_CHECK_LAUNCH();
@@ -138,6 +140,7 @@ int rescore_combine(const RescoreArgs& a, cudaStream_t stream) {
     P.reverse_weight = a.reverse_weight;
     P.hyp_score = a.hyp_score;
     P.best = a.best;
+    ProfScope _ps(PT_RESCORE, stream, 0.0);
     rescore_kernel<<<ceil_div(a.batch, 64), 64, 0, stream>>>(P, a.batch);
     count_launch();
     WB_CHECK_LAUNCH();

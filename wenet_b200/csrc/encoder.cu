@@ -27,6 +27,60 @@ __global__ void unpack_rows_kernel(const float* __restrict__ packed, const int* 
     }
 }
 
+
+// ---- streaming helpers (encoder.py:204-300) ----------------------------------------------------
+// K/V history: att_cache fp32 [H][cache_t1][128] (K | V halves) + this chunk's k, v (bf16 columns of
+// the fused qkv GEMM output) -> kcat / vcat bf16 [key_size][d] for the attention kernel, and the
+// trimmed fp32 cache [H][key_size - nxt][128] handed back to the caller (r_att_cache).
+__global__ void att_cache_concat_kernel(const float* __restrict__ att_cache, int cache_t1,
+                                        const __nv_bfloat16* __restrict__ qkv, int chunk, int d, int H,
+                                        __nv_bfloat16* __restrict__ kcat, __nv_bfloat16* __restrict__ vcat,
+                                        float* __restrict__ r_att, int nxt) {
+    const int key_size = cache_t1 + chunk;
+    const int total = key_size * d;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int j = i / d, c = i - j * d;
+        const int h = c >> 6, e = c & 63;
+        float kv, vv;
+        if (j < cache_t1) {
+            const float* src = att_cache + ((size_t)h * cache_t1 + j) * 128;
+            kv = src[e];
+            vv = src[64 + e];
+        } else {
+            const __nv_bfloat16* row = qkv + (size_t)(j - cache_t1) * 3 * d;
+            kv = __bfloat162float(row[d + c]);
+            vv = __bfloat162float(row[2 * d + c]);
+        }
+        kcat[i] = __float2bfloat16_rn(kv);
+        vcat[i] = __float2bfloat16_rn(vv);
+        if (j >= nxt) {
+            float* dst = r_att + ((size_t)h * (key_size - nxt) + (j - nxt)) * 128;
+            dst[e] = kv;
+            dst[64 + e] = vv;
+        }
+    }
+}
+
+// conv-module input history: rows [0, lead) of `acat` (bf16 [lead + chunk][d]) from cnn_cache fp32
+// [d][lead] (zeros on the first chunk), and the new cache = last `lead` rows of [cache ; LN_conv(x)].
+__global__ void cnn_cache_kernel(const float* __restrict__ cnn_cache, const float* __restrict__ a_f32, int chunk,
+                                 int d, int lead, __nv_bfloat16* __restrict__ acat, float* __restrict__ r_cnn) {
+    const int total = lead * d;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / d, c = i - r * d;  // history row r, channel c
+        const float old = cnn_cache ? cnn_cache[(size_t)c * lead + r] : 0.f;
+        acat[(size_t)r * d + c] = __float2bfloat16_rn(old);
+        // new cache column r  <-  row (chunk + r) of [cache rows (lead) ; new rows (chunk)]
+        const int src = chunk + r;
+        float v;
+        if (src < lead)
+            v = cnn_cache ? cnn_cache[(size_t)c * lead + src] : 0.f;
+        else
+            v = a_f32[(size_t)(src - lead) * d + c];
+        r_cnn[(size_t)c * lead + r] = v;
+    }
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 inline int sub4_len(int T) { return T >= 7 ? ((T - 1) / 2 - 1) / 2 : 0; }
@@ -270,20 +324,177 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
     return WB_OK;
 }
 
+namespace {
+struct ChunkPlan {
+    int chunk, key_size, t1n, lead;
+    size_t o_meta, o_out1, o_a2, o_out2, o_x, o_acat, o_af32, o_h, o_qkv, o_kcat, o_vcat, o_kp, o_kbias, o_ctx, o_g,
+        o_g2, o_rowpos, total;
+};
+void chunk_plan(const Model* m, int T, int cache_t1, ChunkPlan* P) {
+    const wb_model_config& c = m->cfg;
+    const int d = c.d_model;
+    P->chunk = sub4_len(T);
+    P->key_size = cache_t1 + P->chunk;
+    P->t1n = P->chunk > 0 ? 2 * P->chunk + 1 : 0;
+    P->lead = c.cnn_causal ? c.cnn_kernel - 1 : 0;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o += align_up(bytes + 16);
+        return at;
+    };
+    P->o_meta = take(256);
+    P->o_out1 = take((size_t)P->t1n * m->F1 * d * 2);
+    P->o_a2 = take((size_t)P->chunk * m->F2 * 9 * d * 2);
+    P->o_out2 = take((size_t)P->chunk * m->F2 * d * 2);
+    P->o_x = take((size_t)P->chunk * d * 4);
+    P->o_acat = take((size_t)(P->lead + P->chunk) * d * 2);
+    P->o_af32 = take((size_t)P->chunk * d * 4);
+    P->o_h = take((size_t)P->chunk * c.ffn_dim * 2);
+    P->o_qkv = take((size_t)P->chunk * 3 * d * 2);
+    P->o_kcat = take((size_t)P->key_size * d * 2);
+    P->o_vcat = take((size_t)P->key_size * d * 2);
+    P->o_kp = take((size_t)P->key_size * d * 2);
+    P->o_kbias = take((size_t)P->key_size * c.heads * 4);
+    P->o_ctx = take((size_t)P->chunk * d * 2);
+    P->o_g = take((size_t)(P->lead + P->chunk) * d * 2);
+    P->o_g2 = take((size_t)P->chunk * d * 2);
+    P->o_rowpos = take((size_t)P->key_size * 4);
+    P->total = o + 256;
+}
+}  // namespace
+
 size_t wb_encoder_chunk_workspace_bytes(const wb_model* mm, int T, int cache_t1) {
-    (void)mm; (void)T; (void)cache_t1;
-    return 0;
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    if (!m || !m->finalized) return 0;
+    ChunkPlan P;
+    chunk_plan(m, T, cache_t1, &P);
+    return P.total;
 }
 
 int wb_encoder_forward_chunk(const wb_model* mm, const float* xs_dev, int T, int offset, int required_cache_size,
                              const float* att_cache_dev, int cache_t1, const float* cnn_cache_dev, float* y_dev,
                              float* r_att_cache_dev, float* r_cnn_cache_dev, int* out_chunk, int* out_new_cache_t1,
                              void* workspace_dev, size_t workspace_bytes, wb_stream_t stream) {
-    (void)mm; (void)xs_dev; (void)T; (void)offset; (void)required_cache_size; (void)att_cache_dev; (void)cache_t1;
-    (void)cnn_cache_dev; (void)y_dev; (void)r_att_cache_dev; (void)r_cnn_cache_dev; (void)out_chunk;
-    (void)out_new_cache_t1; (void)workspace_dev; (void)workspace_bytes; (void)stream;
-    set_last_error("encoder_forward_chunk: not implemented yet");
-    return WB_ERR_UNSUPPORTED;
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "forward_chunk: model not finalized");
+    WB_REQUIRE(xs_dev && y_dev && r_att_cache_dev && workspace_dev, WB_ERR_BAD_ARG, "forward_chunk: null argument");
+    WB_REQUIRE(cache_t1 == 0 || att_cache_dev, WB_ERR_BAD_ARG, "forward_chunk: att_cache missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const wb_model_config& c = m->cfg;
+    const int d = c.d_model, ff = c.ffn_dim, H = c.heads;
+    ChunkPlan P;
+    chunk_plan(m, T, cache_t1, &P);
+    WB_REQUIRE(P.chunk > 0, WB_ERR_BAD_ARG, "forward_chunk: %d input frames give no output frame", T);
+    WB_REQUIRE(workspace_bytes >= P.total, WB_ERR_WORKSPACE, "forward_chunk: workspace %zu < required %zu",
+               workspace_bytes, P.total);
+    WB_REQUIRE(offset - cache_t1 >= 0 && offset + P.chunk <= c.max_pos, WB_ERR_BAD_ARG,
+               "forward_chunk: positions [%d, %d) outside the positional table", offset - cache_t1, offset + P.chunk);
+    const int chunk = P.chunk, key_size = P.key_size, lead = P.lead;
+    int nxt;
+    if (required_cache_size < 0) nxt = 0;
+    else if (required_cache_size == 0) nxt = key_size;
+    else nxt = key_size - required_cache_size > 0 ? key_size - required_cache_size : 0;
+    if (out_chunk) *out_chunk = chunk;
+    if (out_new_cache_t1) *out_new_cache_t1 = key_size - nxt;
+    WB_REQUIRE(lead == 0 || r_cnn_cache_dev, WB_ERR_BAD_ARG, "forward_chunk: r_cnn_cache missing");
+
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
+    // meta: ints {t1n, chunk, zero, key_size, lead+chunk} then long long {0}
+    struct { int v[6]; long long z[2]; } meta;
+    meta.v[0] = P.t1n; meta.v[1] = chunk; meta.v[2] = 0; meta.v[3] = key_size; meta.v[4] = lead + chunk; meta.v[5] = 0;
+    meta.z[0] = 0; meta.z[1] = 0;
+    WB_CHECK_CUDA(cudaMemcpyAsync(ws + P.o_meta, &meta, sizeof(meta), cudaMemcpyHostToDevice, st));
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));
+    const int* d_t1n = reinterpret_cast<const int*>(ws + P.o_meta);
+    const int* d_chunk = d_t1n + 1;
+    const int* d_zero = d_t1n + 2;
+    const int* d_key = d_t1n + 3;
+    const int* d_cin = d_t1n + 4;
+    const long long* d_zero64 = reinterpret_cast<const long long*>(ws + P.o_meta + 24);
+
+    void* out1 = ws + P.o_out1;
+    void* a2 = ws + P.o_a2;
+    void* out2 = ws + P.o_out2;
+    float* x = reinterpret_cast<float*>(ws + P.o_x);
+    __nv_bfloat16* acat = reinterpret_cast<__nv_bfloat16*>(ws + P.o_acat);
+    __nv_bfloat16* a = acat + (size_t)lead * d;   // LayerNorm output rows of this chunk
+    float* af32 = reinterpret_cast<float*>(ws + P.o_af32);
+    void* h = ws + P.o_h;
+    void* qkv = ws + P.o_qkv;
+    __nv_bfloat16* kcat = reinterpret_cast<__nv_bfloat16*>(ws + P.o_kcat);
+    __nv_bfloat16* vcat = reinterpret_cast<__nv_bfloat16*>(ws + P.o_vcat);
+    void* kp = ws + P.o_kp;
+    float* kbias = reinterpret_cast<float*>(ws + P.o_kbias);
+    void* ctx = ws + P.o_ctx;
+    void* g = ws + P.o_g;
+    void* g2 = ws + P.o_g2;
+    int* d_row_pos = reinterpret_cast<int*>(ws + P.o_rowpos);
+
+    RC(subsample_conv1(xs_dev, 0, c.input_dim, d_t1n, d_zero64, 1, P.t1n, m->cmvn_mean, m->cmvn_istd, m->conv1_w,
+                       m->conv1_b, d, out1, 0, st));
+    RC(subsample_im2col(out1, d_zero64, d_chunk, d_zero64, 1, chunk, m->F1, m->F2, d, a2, 0, st));
+    RC(gemm_bf16(a2, 9 * d, &m->conv2.tmap, m->conv2.w, chunk * m->F2, d, 9 * d, m->conv2.b, EPI_BF16_RELU, 1.0f, out2,
+                 d, 0, st));
+    RC(gemm_bf16(out2, (long long)m->F2 * d, &m->embed_out.tmap, m->embed_out.w, chunk, d, m->F2 * d, m->embed_out.b,
+                 EPI_F32, sqrtf((float)d), x, d, 0, st));
+    RC(fill_row_pos(d_zero, d_key, 1, offset - cache_t1, d_row_pos, key_size, st));
+    const float att_scale = 1.0f / sqrtf(64.0f);
+    const size_t att_l = (size_t)H * cache_t1 * 128, ratt_l = (size_t)H * (key_size - nxt) * 128;
+    const size_t cnn_l = (size_t)d * lead;
+    for (int li = 0; li < c.enc_layers; ++li) {
+        const EncLayer& L = m->layers[li];
+        RC(layernorm_rows(x, d, chunk, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.ffm1.tmap, L.ffm1.w, chunk, ff, d, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
+        RC(gemm_bf16(h, ff, &L.ffm2.tmap, L.ffm2.w, chunk, d, ff, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        RC(layernorm_rows(x, d, chunk, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, chunk, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
+        att_cache_concat_kernel<<<ceil_div(key_size * d, 256), 256, 0, st>>>(
+            cache_t1 > 0 ? att_cache_dev + li * att_l : nullptr, cache_t1, reinterpret_cast<const __nv_bfloat16*>(qkv),
+            chunk, d, H, kcat, vcat, r_att_cache_dev + li * ratt_l, nxt);
+        count_launch();
+        WB_CHECK_LAUNCH();
+        RC(relpos_kprep(kcat, d, L.pos_proj, d_row_pos, L.pos_u, L.pos_v, key_size, H, kp, d, kbias, st));
+        {
+            AttnArgs A;
+            A.q = qkv; A.ldq = 3 * d; A.q_rows = chunk; A.q_col0 = 0;
+            A.k = kp; A.ldk = d; A.k_rows = key_size; A.k_col0 = 0;
+            A.v = vcat; A.ldv = d; A.v_rows = key_size; A.v_col0 = 0;
+            A.kbias = kbias; A.ld_kbias = H;
+            A.q_start = d_zero; A.q_len = d_chunk; A.k_start = d_zero; A.k_len = d_key;
+            A.batch = 1; A.heads = H; A.max_q_len = chunk;
+            A.chunk_size = 0; A.num_left_chunks = -1; A.scale = att_scale;   // att_mask is all-ones (encoder.py:243-247)
+            A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
+            RC(attention_forward(A, st));
+        }
+        RC(gemm_bf16(ctx, d, &L.out.tmap, L.out.w, chunk, d, d, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        // conv module with left-context cache (convolution.py:122-130)
+        RC(layernorm_rows(x, d, chunk, d, L.n_conv.g, L.n_conv.b, c.ln_eps, a, d, 0, af32, d, st));
+        if (lead > 0) {
+            cnn_cache_kernel<<<ceil_div(lead * d, 256), 256, 0, st>>>(cnn_cache_dev ? cnn_cache_dev + li * cnn_l : nullptr,
+                                                                      af32, chunk, d, lead, acat,
+                                                                      r_cnn_cache_dev + li * cnn_l);
+            count_launch();
+            WB_CHECK_LAUNCH();
+        }
+        RC(gemm_bf16(acat, d, &L.pw1.tmap, L.pw1.w, lead + chunk, 2 * d, d, L.pw1.b, EPI_GLU_BF16, 1.0f, g, d, 0, st));
+        {
+            DwConvArgs D;
+            D.g = g; D.ldg = d; D.seq_start = d_zero; D.seq_len = d_cin; D.out_start = d_zero;
+            D.batch = 1; D.max_len = chunk; D.lead = lead; D.d = d; D.ksize = c.cnn_kernel;
+            D.causal = c.cnn_causal; D.w = L.dw_w; D.bias = L.dw_b; D.norm_type = c.cnn_norm;
+            D.gamma = L.n_cnn.g; D.beta = L.n_cnn.b; D.eps = c.ln_eps; D.pad_vec = L.pad_vec; D.pad_until = chunk;
+            D.out = g2; D.ldo = d; D.split3 = 0;
+            RC(dwconv_norm_silu(D, st));
+        }
+        RC(gemm_bf16(g2, d, &L.pw2.tmap, L.pw2.w, chunk, d, d, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(layernorm_rows(x, d, chunk, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, chunk, ff, d, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
+        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, chunk, d, ff, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        RC(layernorm_rows(x, d, chunk, d, L.n_final.g, L.n_final.b, c.ln_eps, nullptr, 0, 0, x, d, st));
+    }
+    RC(layernorm_rows(x, d, chunk, d, m->after.g, m->after.b, c.ln_eps, nullptr, 0, 0, y_dev, d, st));
+    return WB_OK;
 }
 
 }  // extern "C"

@@ -271,6 +271,8 @@ int fbank_forward(const FbankPlan* plan, const void* pcm, int is_int16, long lon
     const int pcm_bytes = (span * esz + 15) & ~15;
     const size_t smem = 16 + pcm_bytes + (size_t)(FB_THREADS / 32) * (2 * half + half + 8) * sizeof(float);
     dim3 grid(ceil_div(max_frames, FR), batch);
+    ProfScope _ps(PT_FBANK, stream,
+                  (double)batch * ((double)max_frames * plan->frame_shift * esz + (double)max_frames * plan->num_mel * 4.0));
     if (is_int16) {
         if (smem > 48 * 1024)
             WB_CHECK_CUDA(cudaFuncSetAttribute(fbank_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -338,6 +338,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
     gemm_tcgen05_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, p);
     count_launch();
     WB_CHECK_LAUNCH();

@@ -103,6 +103,7 @@ int layernorm_rows(const float* x, long long ldx, int M, int d, const float* gam
     WB_REQUIRE(d % 128 == 0 && d <= 1024, WB_ERR_UNSUPPORTED, "layernorm: d=%d must be a multiple of 128, <= 1024", d);
     WB_REQUIRE(ldx % 4 == 0 && ld_bf16 % 4 == 0 && ld_f32 % 4 == 0, WB_ERR_BAD_ARG, "layernorm: pitches must be %%4");
     const int grid = ceil_div(M, LN_WARPS);
+    ProfScope _ps(PT_LAYERNORM, stream, (double)M * d * (4.0 + (out_bf16 ? 2.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
 #define WB_LN(V)                                                                                          \
     layernorm_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(x, ldx, M, d, gamma, beta, eps, ob, ld_bf16, \
@@ -131,6 +132,7 @@ int cast_rows_bf16(const float* x, long long ldx, int M, int d, void* out_bf16, 
     WB_REQUIRE(d % 4 == 0 && ldx % 4 == 0 && ld_bf16 % 4 == 0, WB_ERR_BAD_ARG, "cast_rows: d/pitches must be %%4");
     const long long n4 = (long long)M * (d / 4);
     const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    ProfScope _ps(PT_MISC, stream, (double)M * d * 6.0);
     cast_rows_kernel<<<grid, 256, 0, stream>>>(x, ldx, M, d, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_bf16,
                                                split3);
     count_launch();
@@ -142,6 +144,7 @@ int fill_row_pos(const int* seq_start, const int* seq_len, int batch, int pos_of
                  cudaStream_t stream) {
     if (batch <= 0 || max_len <= 0) return WB_OK;
     dim3 grid(ceil_div(max_len, 256), batch);
+    ProfScope _ps(PT_MISC, stream, 0.0);
     fill_row_pos_kernel<<<grid, 256, 0, stream>>>(seq_start, seq_len, pos_offset, row_pos);
     count_launch();
     WB_CHECK_LAUNCH();

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 #include <mutex>
+#include <vector>
+#include <utility>
 
 namespace wb {
 
@@ -17,6 +19,58 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_last_error() { return g_err; }
+
+// ---------------------------------------------------------------- profiler
+int g_prof_on = 0;
+namespace {
+struct ProfRec {
+    int tag;
+    double work;
+    cudaEvent_t e0, e1;
+};
+std::vector<ProfRec> g_recs;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_free_events;
+}  // namespace
+
+void prof_begin(int tag, cudaStream_t st, double work) {
+    ProfRec r;
+    r.tag = tag;
+    r.work = work;
+    if (!g_free_events.empty()) {
+        r.e0 = g_free_events.back().first;
+        r.e1 = g_free_events.back().second;
+        g_free_events.pop_back();
+    } else {
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+    }
+    cudaEventRecord(r.e0, st);
+    g_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+    if (!g_recs.empty()) cudaEventRecord(g_recs.back().e1, st);
+}
+void prof_reset() {
+    for (auto& r : g_recs) g_free_events.push_back({r.e0, r.e1});
+    g_recs.clear();
+}
+int prof_collect(double* ms, double* work, long long* launches) {
+    cudaDeviceSynchronize();
+    for (int t = 0; t < PT_COUNT; ++t) {
+        ms[t] = 0;
+        work[t] = 0;
+        launches[t] = 0;
+    }
+    for (auto& r : g_recs) {
+        float e = 0.f;
+        if (cudaEventElapsedTime(&e, r.e0, r.e1) == cudaSuccess) {
+            ms[r.tag] += e;
+            work[r.tag] += r.work;
+            launches[r.tag] += 1;
+        }
+    }
+    return 0;
+}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,

@@ -353,6 +353,7 @@ int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream) {
     P.out_scores = a.out_scores;
     P.out_nhyp = a.out_nhyp;
     P.pool = reinterpret_cast<int*>(a.workspace);
+    ProfScope _ps(PT_PREFIX_BEAM, stream, 0.0);
     prefix_beam_kernel<<<a.batch, PB_THREADS, 0, stream>>>(P);
     count_launch();
     WB_CHECK_LAUNCH();

@@ -87,6 +87,7 @@ int subsample_conv1(const float* feats, long long feat_stride_b, int idim, const
     if (batch <= 0 || max_t1 <= 0) return WB_OK;
     WB_REQUIRE(d % 64 == 0 && d <= 2048, WB_ERR_UNSUPPORTED, "conv1: d=%d unsupported", d);
     dim3 grid(max_t1, batch);
+    ProfScope _ps(PT_CONV1, stream, (double)batch * max_t1 * (((idim - 3) / 2 + 1) * (double)d * 2.0 + 2.0 * idim * 4.0));
     conv1_kernel<<<grid, d / 2, 3 * idim * sizeof(float), stream>>>(
         feats, feat_stride_b, idim, t1_len, off1, cmvn_mean, cmvn_istd, w, bias, d,
         reinterpret_cast<__nv_bfloat16*>(out1_bf16));
@@ -102,6 +103,7 @@ int subsample_im2col(const void* out1_bf16, const long long* off1, const int* t2
     WB_REQUIRE(split3 == 0, WB_ERR_UNSUPPORTED, "im2col: split3 not supported");
     WB_REQUIRE(d % 8 == 0, WB_ERR_BAD_ARG, "im2col: d %% 8");
     dim3 grid(max_t2, batch);
+    ProfScope _ps(PT_IM2COL, stream, (double)batch * max_t2 * F2 * 9.0 * d * 4.0);
     im2col_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(out1_bf16), off1, t2_len, off2, F1,
                                             F2, d, reinterpret_cast<uint4*>(a2_bf16));
     count_launch();

@@ -39,7 +39,7 @@ def sinusoid_pe(max_len: int, d: int) -> torch.Tensor:
     return pe
 
 
-def synth_state_dict(configs: dict, seed: int = 777, ctc_alpha: float = 6.0, ctc_blank_beta: float = 4.0,
+def synth_state_dict(configs: dict, seed: int = 777, ctc_alpha: float = 8.0, ctc_blank_beta: float = None,
                      with_pe: bool = True) -> Dict[str, torch.Tensor]:
     enc = configs["encoder_conf"]
     dec = configs.get("decoder_conf", {})
@@ -64,8 +64,10 @@ def synth_state_dict(configs: dict, seed: int = 777, ctc_alpha: float = 6.0, ctc
         sd[name + ".bias"] = _uniform(seed, name + ".bias", (n,), 0.1)
 
     if configs.get("cmvn", None) is not None:
-        sd["encoder.global_cmvn.mean"] = 8.0 + _uniform(seed, "cmvn.mean", (idim,), 4.0)
-        sd["encoder.global_cmvn.istd"] = 0.25 + _uniform(seed, "cmvn.istd", (idim,), 0.1)
+        # closed-form fit of the per-bin mean / std of synth_pcm()'s log-mel features
+        f = torch.arange(idim, dtype=torch.float32)
+        sd["encoder.global_cmvn.mean"] = 9.8 + 11.5 * (1.0 - torch.exp(-f / 30.0))
+        sd["encoder.global_cmvn.istd"] = torch.full((idim,), 1.0 / 3.0)
     lin("encoder.embed.conv.0", d, 1, (3, 3))
     lin("encoder.embed.conv.2", d, d, (3, 3))
     lin("encoder.embed.out.0", d, d * F2)
@@ -94,6 +96,10 @@ def synth_state_dict(configs: dict, seed: int = 777, ctc_alpha: float = 6.0, ctc
         for n in ("norm_ff", "norm_mha", "norm_ff_macaron", "norm_conv", "norm_final"):
             norm(p + "." + n)
     lin("ctc.ctc_lo", V, d)
+    if ctc_blank_beta is None:
+        # blank logit offset ~ expected maximum of the V-1 non-blank logits (std alpha * 0.58) + 1 sigma:
+        # gives a blank fraction of 0.7-0.9 like a trained CTC model
+        ctc_blank_beta = ctc_alpha * 0.58 * (math.sqrt(2.0 * math.log(V)) + (1.0 if V > 100 else -0.1))
     sd["ctc.ctc_lo.weight"] = sd["ctc.ctc_lo.weight"] * ctc_alpha
     sd["ctc.ctc_lo.bias"] = sd["ctc.ctc_lo.bias"].clone()
     sd["ctc.ctc_lo.bias"][0] += ctc_blank_beta
@@ -125,9 +131,12 @@ def synth_state_dict(configs: dict, seed: int = 777, ctc_alpha: float = 6.0, ctc
     return sd
 
 
-def synth_pcm(batch: int, num_samples, seed: int = 777, sigma: float = 3000.0) -> torch.Tensor:
-    """int16 PCM (batch, max_n): Gaussian noise + a few slowly chirping tones per utterance, clipped to
-    int16.  num_samples: int or list of ints; shorter rows are zero padded."""
+def synth_pcm(batch: int, num_samples, seed: int = 777, sigma: float = 1200.0) -> torch.Tensor:
+    """int16 PCM (batch, max_n): speech-like NON-stationary synthetic audio — a sequence of 60-320 ms
+    segments, each with its own tone pair, amplitude and noise level (silence with probability 0.25) —
+    so that encoder outputs and CTC posteriors vary over time like real speech does (stationary noise
+    gives time-invariant posteriors, which makes every search degenerate).  Clipped to int16.
+    num_samples: int or list of ints; shorter rows are zero padded."""
     ns = [int(num_samples)] * batch if np.isscalar(num_samples) else [int(n) for n in num_samples]
     n_max = (max(ns) + 7) // 8 * 8
     out = np.zeros((batch, n_max), dtype=np.int16)
@@ -135,11 +144,23 @@ def synth_pcm(batch: int, num_samples, seed: int = 777, sigma: float = 3000.0) -
         r = _rng(seed, "pcm%d" % b)
         u1 = np.maximum(r.random(size=n), 1e-12)
         u2 = r.random(size=n)
-        x = np.sqrt(-2.0 * np.log(u1)) * np.cos(2 * np.pi * u2) * sigma   # Box-Muller: raw-uniform only
+        noise = np.sqrt(-2.0 * np.log(u1)) * np.cos(2 * np.pi * u2)      # Box-Muller: raw uniforms only
+        x = np.zeros(n)
         t = np.arange(n) / 16000.0
-        for k in range(3):
-            f0 = 150.0 + 900.0 * r.random()
-            x += 1500.0 * np.sin(2 * np.pi * (f0 * t + 40.0 * (k + 1) * t * t))
+        pos = 0
+        while pos < n:
+            seg = int(16000 * (0.06 + 0.26 * r.random()))
+            e = min(n, pos + seg)
+            kind = r.random()
+            f1 = 120.0 + 3000.0 * r.random()
+            f2 = 300.0 + 5000.0 * r.random()
+            amp = 600.0 + 6000.0 * r.random()
+            ns_amp = sigma * (0.2 + 1.5 * r.random())
+            if kind < 0.25:
+                amp, ns_amp = 0.0, 0.05 * sigma
+            tt = t[pos:e]
+            x[pos:e] = amp * (np.sin(2 * np.pi * f1 * tt) + 0.6 * np.sin(2 * np.pi * f2 * tt)) + ns_amp * noise[pos:e]
+            pos = e
         out[b, :n] = np.clip(np.round(x), -32767, 32767).astype(np.int16)
     return torch.from_numpy(out)
 
@@ -162,7 +183,10 @@ def recipe(name: str) -> dict:
             c["r_num_blocks"] = r
         return c
 
-    base = dict(input_dim=80, cmvn=None, encoder="conformer", tokenizer="char", tokenizer_conf={}, ctc="ctc",
+    # cmvn: the recipes use global CMVN (examples/aishell/s0/conf/*.yaml `cmvn: global_cmvn`); the
+    # statistics are part of the state_dict (encoder.global_cmvn.mean / istd)
+    base = dict(input_dim=80, cmvn="global_cmvn", cmvn_conf={"cmvn_file": None, "is_json_cmvn": True},
+                encoder="conformer", tokenizer="char", tokenizer_conf={}, ctc="ctc",
                 ctc_conf={"ctc_blank_id": 0}, model="asr_model")
     if name == "u2pp_small":        # AISHELL-1 U2++ 12L/256d/4h, K=8 causal LN, bitransformer 3+3
         return dict(base, output_dim=4233, encoder_conf=enc(256, 4, 2048, 12, 8, True, "layer_norm", True),
