@@ -120,3 +120,34 @@ def test_oracle_matches_reference(variant):
         for r, g in zip(rr, gr):
             assert list(r.tokens) == g["tokens"]
             assert abs(r.score - g["best_score"]) < 1e-4
+
+
+@needs_ref
+def test_plugin_config_reconstruction_and_registry():
+    """wenet_b200.plugin: the train.yaml subset is recovered from a constructed reference model, and
+    install() rebinds the reference's registries."""
+    from wenet_b200 import plugin, synth
+    from wenet_b200.weights import ModelSpec
+    cfg = synth.recipe("tiny")
+    ref_cfg = dict(cfg, cmvn=None)
+    ref_cfg.pop("cmvn_conf", None)
+    model = shim.init_reference_model(ref_cfg)
+    got = plugin.configs_from_reference_model(model)
+    a, b = ModelSpec(got), ModelSpec(dict(cfg, cmvn=None))
+    for k in ("input_dim", "vocab", "d_model", "heads", "ffn_dim", "enc_layers", "cnn_kernel", "cnn_causal", "cnn_norm",
+              "use_dynamic_chunk", "bidirectional", "dec_layers", "rdec_layers", "dec_heads", "dec_ffn_dim", "has_cmvn"):
+        assert getattr(a, k) == getattr(b, k), k
+    cls = plugin.install()
+    from wenet.utils import init_model as im
+    import wenet.dataset.processor as processor
+    from wenet_b200.fbank import compute_fbank
+    assert im.WENET_MODEL_CLASSES["asr_model"] is cls and processor.compute_fbank is compute_fbank
+    m2 = shim.init_reference_model(dict(ref_cfg))
+    assert type(m2).__name__ == "B200ASRModelPlugin"
+    assert set(m2.state_dict().keys()) == set(model.state_dict().keys())
+    import wenet_b200._lib as L
+    with pytest.raises(L.WbError):          # CPU model -> loud failure, never a fallback
+        m2.decode(["ctc_greedy_search"], torch.zeros(1, 50, 80), torch.tensor([50]))
+    # restore the registry for other tests in this process
+    from wenet.models.transformer.asr_model import ASRModel
+    im.WENET_MODEL_CLASSES["asr_model"] = ASRModel

@@ -35,6 +35,8 @@ struct DwDev {
     int split3;
 };
 
+// KT: compile-time kernel size (8 / 15 are the recipe values), 0 = run-time loop
+template <int KT>
 __global__ void __launch_bounds__(DW_THREADS)
 dwconv_kernel(DwDev P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -43,7 +45,7 @@ dwconv_kernel(DwDev P) {
     const int n_out = n_in - P.lead;
     const int t0 = blockIdx.x * TT;
     if (t0 >= n_out) return;
-    const int d = P.d, K = P.ksize;
+    const int d = P.d, K = (KT > 0) ? KT : P.ksize;
     const int left = P.causal ? (K - 1) : (K - 1) / 2;
     const int rows_in = TT + K - 1;
     __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(smem_raw);           // [rows_in][d]
@@ -72,33 +74,41 @@ dwconv_kernel(DwDev P) {
     __syncthreads();
 
     const int nt = min(TT, n_out - t0);
-    // depthwise conv: thread handles channel pairs
-    for (int c = 2 * threadIdx.x; c < d; c += 2 * DW_THREADS) {
-        float w0[MAX_K], w1[MAX_K];
+    // depthwise conv: thread = (channel pair, frame group); weights live in registers
+    {
+        const int pairs = d >> 1;
+        const int ngroups = (DW_THREADS / pairs) > 0 ? (DW_THREADS / pairs) : 1;
+        for (int idx = threadIdx.x; idx < pairs * ngroups; idx += DW_THREADS) {
+            const int c = 2 * (idx % pairs);
+            const int grp = idx / pairs;
+            constexpr int KR = (KT > 0) ? KT : MAX_K;
+            float w0[KR], w1[KR];
 #pragma unroll
-        for (int k = 0; k < MAX_K; ++k) {
-            if (k < K) {
-                w0[k] = P.w[(size_t)c * K + k];
-                w1[k] = P.w[(size_t)(c + 1) * K + k];
+            for (int k = 0; k < KR; ++k) {
+                w0[k] = (k < K) ? P.w[(size_t)c * K + k] : 0.f;
+                w1[k] = (k < K) ? P.w[(size_t)(c + 1) * K + k] : 0.f;
             }
-        }
-        const float b0 = P.bias[c], b1 = P.bias[c + 1];
-        for (int t = 0; t < nt; ++t) {
-            float a0 = b0, a1 = b1;
+            const float b0 = P.bias[c], b1 = P.bias[c + 1];
+            float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
+            if (P.norm_type == 1) {
+                sc0 = P.gamma[c]; sc1 = P.gamma[c + 1]; sh0 = P.beta[c]; sh1 = P.beta[c + 1];
+            }
+            for (int t = grp; t < nt; t += ngroups) {
+                float a0 = b0, a1 = b1;
 #pragma unroll
-            for (int k = 0; k < MAX_K; ++k) {
-                if (k < K) {
-                    const uint32_t xx = *reinterpret_cast<const uint32_t*>(s_in + (size_t)(t + k) * d + c);
-                    a0 = fmaf(w0[k], bf16_lo(xx), a0);
-                    a1 = fmaf(w1[k], bf16_hi(xx), a1);
+                for (int k = 0; k < KR; ++k) {
+                    if (KT > 0 || k < K) {
+                        const uint32_t xx = *reinterpret_cast<const uint32_t*>(s_in + (size_t)(t + k) * d + c);
+                        a0 = fmaf(w0[k], bf16_lo(xx), a0);
+                        a1 = fmaf(w1[k], bf16_hi(xx), a1);
+                    }
                 }
+                if (P.norm_type == 1) {  // folded BatchNorm (eval): y = x*scale + shift, then SiLU
+                    a0 = silu_f(fmaf(a0, sc0, sh0));
+                    a1 = silu_f(fmaf(a1, sc1, sh1));
+                }
+                *reinterpret_cast<float2*>(s_out + (size_t)t * d + c) = make_float2(a0, a1);
             }
-            if (P.norm_type == 1) {  // folded BatchNorm (eval): y = x*scale + shift, then SiLU
-                a0 = silu_f(fmaf(a0, P.gamma[c], P.beta[c]));
-                a1 = silu_f(fmaf(a1, P.gamma[c + 1], P.beta[c + 1]));
-            }
-            s_out[(size_t)t * d + c] = a0;
-            s_out[(size_t)t * d + c + 1] = a1;
         }
     }
     __syncthreads();
@@ -166,14 +176,22 @@ int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream) {
     P.split3 = a.split3;
     const int rows_in = TT + a.ksize - 1;
     const size_t smem = ((size_t)rows_in * a.d * 2 + 15) / 16 * 16 + (size_t)TT * a.d * sizeof(float);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(dwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
     dim3 grid(ceil_div(a.max_len, TT), a.batch);
     ProfScope _ps(PT_DWCONV, stream, (double)a.batch * a.max_len * a.d * 4.0);
-    dwconv_kernel<<<grid, DW_THREADS, smem, stream>>>(P);
+#define WB_DW(KT)                                                                                              \
+    do {                                                                                                       \
+        static size_t smem_set = 0;                                                                            \
+        if (smem > 48 * 1024 && smem > smem_set) {                                                             \
+            WB_CHECK_CUDA(cudaFuncSetAttribute(dwconv_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)smem));                                                    \
+            smem_set = smem;                                                                                   \
+        }                                                                                                      \
+        dwconv_kernel<KT><<<grid, DW_THREADS, smem, stream>>>(P);                                              \
+    } while (0)
+    if (a.ksize == 8) WB_DW(8);
+    else if (a.ksize == 15) WB_DW(15);
+    else WB_DW(0);
+#undef WB_DW
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

@@ -6,19 +6,22 @@
 //   (wenet/models/transformer/positionwise_feed_forward.py:50-58, attention.py:74-77,109-131,
 //    convolution.py:46-53,88-95, subsampling.py:194-195,203-228, ctc.py:44, decoder.py:96-103).
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      : TMA producer   — cp.async.bulk.tensor 2-D loads of A (128x64) and B (BNx64)
 //                                  tiles, SWIZZLE_128B, ring of kStages smem slots (mbarrier
 //                                  full/empty)
 //   warp 1      : MMA issuer     — one lane issues tcgen05.mma.cta_group::1.kind::f16
 //                                  (M=128, N=BN, K=16) x4 per k-block into a TMEM accumulator;
 //                                  tcgen05.commit frees smem slots / publishes the accumulator
-//   warps 2..5  : epilogue       — tcgen05.ld 32x32b.x32 (thread == accumulator row), bias +
-//                                  activation / residual / GLU, vectorised global stores.
+//   warps 2..9  : epilogue       — two warps per TMEM lane quarter, tcgen05.ld 32x32b.x32 (thread ==
+//                                  accumulator row), bias + activation / GLU / alpha, staged through
+//                                  SWIZZLE_128B shared memory and written by TMA store (bf16, fp32) or
+//                                  TMA reduce-add (fp32 residual stream: no read-modify-write in the SM).
 //                                  TMEM holds two accumulator stages so the epilogue of tile i
 //                                  overlaps the main loop of tile i+1.
 #include "common.cuh"
 #include "kernels.h"
+#include <string.h>
 
 namespace wb {
 
@@ -34,7 +37,9 @@ struct GemmCfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator (power of two)
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    // epilogue staging: 8 warps x (32 rows x 128 B), SWIZZLE_128B, read back by TMA stores
+    static constexpr int kOutBytes = 8 * 4096;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -45,20 +50,23 @@ struct GemmParams {
     void* out;
     long long ldc;
     int split3;
+    int use_tma_out;  // epilogue through shared memory + TMA store / reduce-add (all non-split3 cases)
     int num_m_tiles, num_n_tiles;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, GemmParams p) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint8_t* smem_out = smem + Cfg::kStages * Cfg::kStageBytes;   // 1024-aligned (stage sizes are multiples of 1024)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes);
     uint64_t* full_bar = bars;                       // [kStages]
     uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
     uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]
@@ -73,13 +81,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (p.use_tma_out) tma_prefetch_desc(&tmap_c);
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[s], 8);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -151,10 +160,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
+        // two warps per TMEM lane quarter; each takes half of the tile's 32-column chunks
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;
+        constexpr int kChunksPerWarp = BN / 64;
         int acc = 0;
         uint32_t acc_phase = 0;
+        bool need_wait = false;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m_tile = t % p.num_m_tiles;
             const int n_tile = t / p.num_m_tiles;
@@ -164,7 +177,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half * kChunksPerWarp; c < (half + 1) * kChunksPerWarp; ++c) {
                 const int n0 = n_tile * BN + c * 32;
                 if (n0 >= p.N) break;  // warp-uniform
                 uint32_t r[32];
@@ -190,6 +203,71 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                }
+                if (p.use_tma_out) {
+                    // ---- staged epilogue: registers -> swizzled smem (row = lane, 128 B) -> TMA ----
+                    // rows >= M and columns >= N are clipped by the tensor map, so no guards are needed.
+                    uint8_t* sbuf = smem_out + (warp - 2) * 4096 + lane * 128;
+                    if (need_wait) {  // the previous TMA store of this warp must have finished reading the buffer
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+                        need_wait = false;
+                    }
+                    const int sw = lane & 7;
+                    bool flush = false;
+                    int out_col = 0;
+                    if (p.epi == EPI_F32 || p.epi == EPI_RESID_F32) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            *reinterpret_cast<float4*>(sbuf + ((u ^ sw) << 4)) =
+                                make_float4(p.alpha * v[4 * u], p.alpha * v[4 * u + 1], p.alpha * v[4 * u + 2],
+                                            p.alpha * v[4 * u + 3]);
+                        flush = true;
+                        out_col = n0;
+                    } else if (p.epi == EPI_GLU_BF16) {
+                        float g[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_f(v[16 + i]);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+                            *reinterpret_cast<uint4*>(sbuf + ((((c & 3) * 2 + u) ^ sw) << 4)) =
+                                make_uint4(pack_bf16x2(g[8 * u], g[8 * u + 1]), pack_bf16x2(g[8 * u + 2], g[8 * u + 3]),
+                                           pack_bf16x2(g[8 * u + 4], g[8 * u + 5]), pack_bf16x2(g[8 * u + 6], g[8 * u + 7]));
+                        flush = ((c & 3) == 3) || (n0 + 32 >= p.N);
+                        out_col = (n_tile * BN + (c & ~3) * 32) >> 1;
+                    } else {
+                        if (p.epi == EPI_BF16_SILU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                        } else if (p.epi == EPI_BF16_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            *reinterpret_cast<uint4*>(sbuf + ((((c & 1) * 4 + u) ^ sw) << 4)) = make_uint4(
+                                pack_bf16x2(p.alpha * v[8 * u], p.alpha * v[8 * u + 1]),
+                                pack_bf16x2(p.alpha * v[8 * u + 2], p.alpha * v[8 * u + 3]),
+                                pack_bf16x2(p.alpha * v[8 * u + 4], p.alpha * v[8 * u + 5]),
+                                pack_bf16x2(p.alpha * v[8 * u + 6], p.alpha * v[8 * u + 7]));
+                        flush = ((c & 1) == 1) || (n0 + 32 >= p.N);
+                        out_col = n_tile * BN + (c & ~1) * 32;
+                    }
+                    if (flush) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const void* src = smem_out + (warp - 2) * 4096;
+                            const int row0 = m_tile * BM + q * 32;
+                            if (p.epi == EPI_RESID_F32)
+                                tma_reduce_add_2d(&tmap_c, src, out_col, row0);
+                            else
+                                tma_store_2d(&tmap_c, src, out_col, row0);
+                            tma_store_commit();
+                        }
+                        need_wait = true;
+                    }
+                    continue;
                 }
                 if (!row_ok) continue;
 
@@ -310,6 +388,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 acc_phase ^= 1;
             }
         }
+        if (p.use_tma_out && lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores
     }
 
     tc_fence_before();
@@ -323,7 +402,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 int g_num_sms = 0;
 
 template <int BN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -339,7 +419,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
-    gemm_tcgen05_kernel<BN><<<grid, 192, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    gemm_tcgen05_kernel<BN><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
@@ -362,7 +442,7 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
                "gemm: K (%d) and lda (%lld) must be multiples of 8 (TMA 16-byte row pitch)", K, lda);
     WB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0, WB_ERR_BAD_ARG, "gemm: A not 16B aligned");
     if (epi == EPI_GLU_BF16) {
-        WB_REQUIRE((N % 32) == 0 && (ldc % 8) == 0, WB_ERR_BAD_ARG, "gemm GLU: N %% 32 and ldc %% 8 required");
+        WB_REQUIRE((N % 256) == 0 && (ldc % 8) == 0, WB_ERR_BAD_ARG, "gemm GLU: N %% 256 and ldc %% 8 required");
     }
     if (epi == EPI_RESID_F32 || epi == EPI_F32) {
         WB_REQUIRE(!split3, WB_ERR_BAD_ARG, "gemm: split3 only for bf16 outputs");
@@ -389,8 +469,19 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
     p.split3 = split3;
     p.num_m_tiles = ceil_div(M, BM);
     p.num_n_tiles = ceil_div(N, bn);
-    if (bn == 256) return launch_gemm<256>(ta, *tb, p, stream);
-    return launch_gemm<128>(ta, *tb, p, stream);
+    // output tensor map: 32-row x 128-byte boxes (one per epilogue warp and column group)
+    CUtensorMap tc;
+    memset(&tc, 0, sizeof(tc));
+    const bool f32_out = (epi == EPI_RESID_F32 || epi == EPI_F32);
+    const int out_cols = (epi == EPI_GLU_BF16) ? N / 2 : N;
+    const int eb = f32_out ? 4 : 2;
+    p.use_tma_out = (!split3 && (ldc * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    if (p.use_tma_out) {
+        rc = make_tmap_2d(&tc, out, eb, (uint64_t)M, (uint64_t)out_cols, (uint64_t)ldc, 32, f32_out ? 32 : 64);
+        if (rc != WB_OK) return rc;
+    }
+    if (bn == 256) return launch_gemm<256>(ta, *tb, tc, p, stream);
+    return launch_gemm<128>(ta, *tb, tc, p, stream);
 }
 
 }  // namespace wb

@@ -89,26 +89,32 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                      uint32_t box_rows, uint32_t box_cols) {
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols) {
     PFN_encodeTiled fn = get_encode_fn();
     WB_REQUIRE(fn != nullptr, WB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+    WB_REQUIRE(elem_bytes == 2 || elem_bytes == 4, WB_ERR_BAD_ARG, "tmap: element size %d", elem_bytes);
     WB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, WB_ERR_BAD_ARG, "tmap: base not 16B aligned");
-    WB_REQUIRE((ld_elems * 2) % 16 == 0, WB_ERR_BAD_ARG, "tmap: row pitch %llu B not a multiple of 16",
-               (unsigned long long)(ld_elems * 2));
-    WB_REQUIRE(box_cols * 2 == 128 && box_rows <= 256, WB_ERR_BAD_ARG, "tmap: bad box %u x %u", box_rows,
+    WB_REQUIRE((ld_elems * elem_bytes) % 16 == 0, WB_ERR_BAD_ARG, "tmap: row pitch %llu B not a multiple of 16",
+               (unsigned long long)(ld_elems * elem_bytes));
+    WB_REQUIRE(box_cols * elem_bytes == 128 && box_rows <= 256, WB_ERR_BAD_ARG, "tmap: bad box %u x %u", box_rows,
                box_cols);
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {ld_elems * 2};
+    cuuint64_t gstride[1] = {ld_elems * (uint64_t)elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WB_REQUIRE(r == CUDA_SUCCESS, WB_ERR_CUDA,
                "cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r, base,
                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, box_cols);
     return WB_OK;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+    return make_tmap_2d(out, base, 2, rows, cols, ld_elems, box_rows, box_cols);
 }
 
 }  // namespace wb

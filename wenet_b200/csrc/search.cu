@@ -26,14 +26,21 @@ namespace {
 
 constexpr int MAXB = 16;
 constexpr int NCAND = MAXB + MAXB * MAXB;
-constexpr int PB_THREADS = 128;
+constexpr int PB_THREADS = 32;          // one warp per utterance: every barrier is a __syncwarp
+constexpr int MAXPL = (NCAND + 31) / 32;  // candidates per lane in the selection step
 
 __device__ __forceinline__ double neg_inf() { return -CUDART_INF; }
 
+// log_add of wenet/utils/common.py:302-310 for two arguments, bit-for-bit:
+//   m + log(exp(a - m) + exp(b - m)); the larger argument contributes exp(0) == 1.0 exactly, and
+//   log_add(-inf, x) == x exactly (0.0 + 1.0 -> log 1.0 == 0.0), so those cases skip the libm calls.
 __device__ __forceinline__ double log_add2(double a, double b) {
-    if (a == neg_inf() && b == neg_inf()) return neg_inf();
+    if (a == neg_inf()) return b;
+    if (b == neg_inf()) return a;
     const double m = a > b ? a : b;
-    return m + log(exp(a - m) + exp(b - m));
+    const double lo = a > b ? b : a;
+    // Python: sum(...) adds exp(a-m) then exp(b-m); IEEE addition is commutative so the order is immaterial
+    return m + log(1.0 + exp(lo - m));
 }
 
 __device__ __forceinline__ uint64_t mix_hash(uint64_t h, int tok) {
@@ -79,17 +86,23 @@ struct PbDev {
     int* pool;  // per utterance: [4][max_len * beam] ints: trie parent, trie token, time prev, time frame
 };
 
+__device__ __forceinline__ bool cand_better(double ta, int fa, double tb, int fb) {
+    return ta > tb || (ta == tb && fa < fb);
+}
+
 __global__ void __launch_bounds__(PB_THREADS)
 prefix_beam_kernel(PbDev P) {
-    __shared__ Beam B;
+    __shared__ Beam Bs[2];
     __shared__ Cand C;
     __shared__ float tk_val[MAXB];
     __shared__ int tk_idx[MAXB];
     __shared__ int dest[MAXB * MAXB];
     __shared__ int rank_slot[MAXB];
+    __shared__ int vlist[NCAND];
 
     const int utt = blockIdx.x;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int beam = P.beam;
     const int T = P.seq_len[utt];
     const long long f0 = P.seq_start[utt];
@@ -98,13 +111,18 @@ prefix_beam_kernel(PbDev P) {
     int* trie_tok = trie_parent + pool_n;
     int* time_prev = trie_tok + pool_n;
     int* time_t = time_prev + pool_n;
+    const int ncs = MAXB + beam * MAXB;  // candidate slots in use
 
-    if (tid == 0) {
+    if (lane == 0) {
+        Beam& B = Bs[0];
         B.n = 1;
         B.s[0] = 0.0;
         B.ns[0] = neg_inf();
         B.vs[0] = 0.0;
         B.vns[0] = 0.0;
+        B.score[0] = 0.0;   // log_add(0, -inf)
+        B.vit[0] = 0.0;     // v_s > v_ns is false -> v_ns
+        B.times[0] = -1;
         B.hash[0] = 0x1234567ull;
         B.len[0] = 0;
         B.last[0] = -1;
@@ -112,26 +130,31 @@ prefix_beam_kernel(PbDev P) {
         B.ts[0] = -1;
         B.tns[0] = -1;
     }
-    __syncthreads();
+    int cur = 0;
+    float pf_val = 0.f;
+    int pf_idx = 0;
+    if (lane < beam && T > 0) {
+        pf_val = P.topk_val[f0 * P.topk + lane];
+        pf_idx = P.topk_idx[f0 * P.topk + lane];
+    }
+    __syncwarp();
 
     for (int t = 0; t < T; ++t) {
+        if (lane < beam) {
+            tk_val[lane] = pf_val;
+            tk_idx[lane] = pf_idx;
+        }
+        for (int c = lane; c < ncs; c += 32) C.valid[c] = 0;
+        __syncwarp();
+        if (lane < beam && t + 1 < T) {  // prefetch the next frame's top-k behind this frame's work
+            pf_val = P.topk_val[(f0 + t + 1) * P.topk + lane];
+            pf_idx = P.topk_idx[(f0 + t + 1) * P.topk + lane];
+        }
+        Beam& B = Bs[cur];
         const int nb = B.n;
-        // ---- per-prefix derived quantities, frame top-k, candidate reset ----
-        if (tid < nb) {
-            B.score[tid] = log_add2(B.s[tid], B.ns[tid]);
-            const bool sb = B.vs[tid] > B.vns[tid];
-            B.vit[tid] = sb ? B.vs[tid] : B.vns[tid];
-            B.times[tid] = sb ? B.ts[tid] : B.tns[tid];
-        }
-        if (tid < beam) {
-            tk_val[tid] = P.topk_val[(f0 + t) * P.topk + tid];
-            tk_idx[tid] = P.topk_idx[(f0 + t) * P.topk + tid];
-        }
-        for (int c = tid; c < NCAND; c += PB_THREADS) C.valid[c] = 0;
-        __syncthreads();
 
-        // ---- extensions: one thread per (token ui, prefix pi) ----
-        for (int pr = tid; pr < beam * nb; pr += PB_THREADS) {
+        // ---- extensions: (token ui, prefix pi) pairs strided over the lanes ----
+        for (int pr = lane; pr < beam * nb; pr += 32) {
             const int ui = pr / nb, pi = pr - ui * nb;
             const int u = tk_idx[ui];
             int d = -1;
@@ -147,54 +170,76 @@ prefix_beam_kernel(PbDev P) {
                     C.s[d] = neg_inf();
                     C.vs[d] = neg_inf();
                     C.ts[d] = -1;
-                    // log_add(-inf, x) == x exactly (exp(-inf)=0, log(1)=0)
-                    C.ns[d] = (rep ? B.s[pi] : B.score[pi]) + prob;
-                    C.vns[d] = (rep ? B.vs[pi] : B.vit[pi]) + prob;
+                    // log_add(-inf, x) == x exactly
+                    const double nsv = (rep ? B.s[pi] : B.score[pi]) + prob;
+                    double vn = (rep ? B.vs[pi] : B.vit[pi]) + prob;
                     // reference: `if next.v_ns < y` with next.v_ns = -inf: false only when y == -inf
-                    if (C.vns[d] > neg_inf()) {
+                    if (vn > neg_inf()) {
                         C.tns[d] = rep ? B.ts[pi] : B.times[pi];
                         C.tns_new[d] = 1;
                     } else {
-                        C.vns[d] = neg_inf();
+                        vn = neg_inf();
                         C.tns[d] = -1;
                         C.tns_new[d] = 0;
                     }
+                    C.ns[d] = nsv;
+                    C.vns[d] = vn;
                     C.hash[d] = h;
                     C.len[d] = ln;
                     C.last[d] = u;
                     C.node[d] = B.node[pi];
                     C.new_tok[d] = u;
                     C.first[d] = (ui * nb + pi) * 2 + (rep ? 1 : 0);
-                    C.total[d] = C.ns[d];  // log_add(-inf, ns)
+                    C.total[d] = nsv;  // log_add(-inf, ns)
                     C.valid[d] = 1;
                 }
             }
             dest[ui * MAXB + pi] = d;
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- unchanged prefixes: thread q replays its (<= 3) updates in reference order ----
-        if (tid < nb) {
-            const int q = tid;
-            double s = neg_inf(), ns = neg_inf(), vs = neg_inf(), vns = neg_inf();
-            int ts = -1, tns = -1, tns_new = 0, first = INT_MAX, any = 0;
-            bool cur_set = false;
+        // ---- unchanged prefixes: lane q replays its (<= 3) updates in the reference's loop order ----
+        if (lane < nb) {
+            const int q = lane;
+            const int lastq = B.last[q];
+            int ui_blank = -1, ui_last = -1;
             for (int ui = 0; ui < beam; ++ui) {
                 const int u = tk_idx[ui];
-                const double prob = (double)tk_val[ui];
-                if (u == P.blank_id) {
-                    s = log_add2(s, B.score[q] + prob);
-                    vs = B.vit[q] + prob;
-                    ts = B.times[q];
-                    first = min(first, (ui * nb + q) * 2);
-                    any = 1;
-                    continue;
-                }
-                if (u != B.last[q]) continue;
-                // events on ns in prefix order: extension from the parent prefix pe (dest == q),
-                // repeat from q itself
-                for (int pi = 0; pi < nb; ++pi) {
-                    if (pi == q) {
+                if (u == P.blank_id) ui_blank = ui;
+                else if (u == lastq) ui_last = ui;
+            }
+            double s = neg_inf(), ns = neg_inf(), vs = neg_inf(), vns = neg_inf();
+            int ts = -1, tns = -1, tns_new = 0, first = INT_MAX, any = 0;
+            if (ui_blank >= 0) {
+                const double prob = (double)tk_val[ui_blank];
+                s = B.score[q] + prob;          // log_add(-inf, x)
+                vs = B.vit[q] + prob;
+                ts = B.times[q];
+                first = (ui_blank * nb + q) * 2;
+                any = 1;
+            }
+            if (ui_last >= 0) {
+                const double prob = (double)tk_val[ui_last];
+                int pe = -1;  // parent prefix whose extension by last(q) lands on q
+                for (int pi = 0; pi < nb; ++pi)
+                    if (pi != q && dest[ui_last * MAXB + pi] == q) pe = pi;
+                bool cur_set = false;
+                // two possible events on ns, in prefix order: extension from pe, repeat from q itself
+                for (int ev = 0; ev < 2; ++ev) {
+                    const bool do_ext = (pe >= 0) && ((ev == 0) == (pe < q));
+                    const bool do_rep = (ev == 0) == !(pe >= 0 && pe < q);
+                    if (do_ext) {
+                        const bool rep = (lastq == B.last[pe]);
+                        ns = log_add2(ns, (rep ? B.s[pe] : B.score[pe]) + prob);
+                        const double y = (rep ? B.vs[pe] : B.vit[pe]) + prob;
+                        if (vns < y) {
+                            vns = y;
+                            cur_set = true;
+                            tns = rep ? B.ts[pe] : B.times[pe];
+                            tns_new = 1;
+                        }
+                        first = min(first, (ui_last * nb + pe) * 2 + (rep ? 1 : 0));
+                    } else if (do_rep) {
                         ns = log_add2(ns, B.ns[q] + prob);
                         const double y = B.vns[q] + prob;
                         if (vns < y) {
@@ -207,22 +252,10 @@ prefix_beam_kernel(PbDev P) {
                                 tns_new = 1;
                             }
                         }
-                        first = min(first, (ui * nb + q) * 2);
-                        any = 1;
-                    } else if (dest[ui * MAXB + pi] == q) {
-                        const bool rep = (u == B.last[pi]);
-                        ns = log_add2(ns, (rep ? B.s[pi] : B.score[pi]) + prob);
-                        const double y = (rep ? B.vs[pi] : B.vit[pi]) + prob;
-                        if (vns < y) {
-                            vns = y;
-                            cur_set = true;
-                            tns = rep ? B.ts[pi] : B.times[pi];
-                            tns_new = 1;
-                        }
-                        first = min(first, (ui * nb + pi) * 2 + (rep ? 1 : 0));
-                        any = 1;
+                        first = min(first, (ui_last * nb + q) * 2);
                     }
                 }
+                any = 1;
             }
             if (any) {
                 C.s[q] = s;
@@ -234,7 +267,7 @@ prefix_beam_kernel(PbDev P) {
                 C.tns_new[q] = tns_new;
                 C.hash[q] = B.hash[q];
                 C.len[q] = B.len[q];
-                C.last[q] = B.last[q];
+                C.last[q] = lastq;
                 C.node[q] = B.node[q];
                 C.new_tok[q] = -1;
                 C.first[q] = first;
@@ -242,87 +275,132 @@ prefix_beam_kernel(PbDev P) {
                 C.valid[q] = 1;
             }
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- second beam prune: stable sort by total desc == rank by (total, insertion order) ----
-        if (tid < MAXB) rank_slot[tid] = -1;
-        __syncthreads();
-        for (int c = tid; c < NCAND; c += PB_THREADS) {
-            if (!C.valid[c]) continue;
-            const double tc = C.total[c];
-            const int fc = C.first[c];
-            int rank = 0;
-            for (int j = 0; j < NCAND; ++j) {
-                if (j == c || !C.valid[j]) continue;
-                const double tj = C.total[j];
-                if (tj > tc || (tj == tc && C.first[j] < fc)) ++rank;
-            }
-            if (rank < beam) rank_slot[rank] = c;
+        // ---- second beam prune: stable sort by total desc == top-beam by (total, insertion order) ----
+        int nvalid = 0;
+        for (int base = 0; base < ncs; base += 32) {
+            const int c = base + lane;
+            const bool v = (c < ncs) && C.valid[c];
+            const unsigned m = __ballot_sync(0xffffffffu, v);
+            if (v) vlist[nvalid + __popc(m & lt_mask)] = c;
+            nvalid += __popc(m);
         }
-        __syncthreads();
-        if (tid < beam) {
-            const int c = rank_slot[tid];
-            if (c >= 0) {
-                const int r = tid;
-                const int pool_i = t * beam + r;
-                B.s[r] = C.s[c];
-                B.ns[r] = C.ns[c];
-                B.vs[r] = C.vs[c];
-                B.vns[r] = C.vns[c];
-                B.hash[r] = C.hash[c];
-                B.len[r] = C.len[c];
-                B.last[r] = C.last[c];
-                if (C.new_tok[c] >= 0) {
-                    trie_parent[pool_i] = C.node[c];
-                    trie_tok[pool_i] = C.new_tok[c];
-                    B.node[r] = pool_i;
-                } else {
-                    B.node[r] = C.node[c];
-                }
-                B.ts[r] = C.ts[c];
-                if (C.tns_new[c]) {
-                    time_prev[pool_i] = C.tns[c];
-                    time_t[pool_i] = t;
-                    B.tns[r] = pool_i;
-                } else {
-                    B.tns[r] = C.tns[c];
-                }
+        __syncwarp();
+        double my_tot[MAXPL];
+        int my_first[MAXPL], my_slot[MAXPL];
+#pragma unroll
+        for (int k = 0; k < MAXPL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nvalid) {
+                const int c = vlist[i];
+                my_slot[k] = c;
+                my_tot[k] = C.total[c];
+                my_first[k] = C.first[c];
+            } else {
+                my_slot[k] = -1;
+                my_tot[k] = neg_inf();
+                my_first[k] = INT_MAX;
             }
         }
-        if (tid == 0) {
-            int n = 0;
-            for (int r = 0; r < beam; ++r)
-                if (rank_slot[r] >= 0) ++n;
-            B.n = n;
+        const int nnew = nvalid < beam ? nvalid : beam;
+        for (int r = 0; r < nnew; ++r) {
+            double bt = neg_inf();
+            int bf = INT_MAX, bs = -1;
+#pragma unroll
+            for (int k = 0; k < MAXPL; ++k)
+                if (my_slot[k] >= 0 && cand_better(my_tot[k], my_first[k], bt, bf)) {
+                    bt = my_tot[k];
+                    bf = my_first[k];
+                    bs = my_slot[k];
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                const int of = __shfl_xor_sync(0xffffffffu, bf, o);
+                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (cand_better(ot, of, bt, bf)) {
+                    bt = ot;
+                    bf = of;
+                    bs = os;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < MAXPL; ++k)
+                if (my_slot[k] == bs) my_slot[k] = -1;  // taken
+            if (lane == 0) rank_slot[r] = bs;
         }
-        __syncthreads();
-        __threadfence_block();
+        __syncwarp();
+
+        // ---- materialise the new beam ----
+        Beam& NB = Bs[cur ^ 1];
+        if (lane < nnew) {
+            const int r = lane;
+            const int c = rank_slot[r];
+            const int pool_i = t * beam + r;
+            const double vs = C.vs[c], vns = C.vns[c];
+            NB.s[r] = C.s[c];
+            NB.ns[r] = C.ns[c];
+            NB.vs[r] = vs;
+            NB.vns[r] = vns;
+            NB.score[r] = C.total[c];
+            NB.hash[r] = C.hash[c];
+            NB.len[r] = C.len[c];
+            NB.last[r] = C.last[c];
+            if (C.new_tok[c] >= 0) {
+                trie_parent[pool_i] = C.node[c];
+                trie_tok[pool_i] = C.new_tok[c];
+                NB.node[r] = pool_i;
+            } else {
+                NB.node[r] = C.node[c];
+            }
+            const int tsv = C.ts[c];
+            int tnsv;
+            if (C.tns_new[c]) {
+                time_prev[pool_i] = C.tns[c];
+                time_t[pool_i] = t;
+                tnsv = pool_i;
+            } else {
+                tnsv = C.tns[c];
+            }
+            NB.ts[r] = tsv;
+            NB.tns[r] = tnsv;
+            const bool sb = vs > vns;
+            NB.vit[r] = sb ? vs : vns;
+            NB.times[r] = sb ? tsv : tnsv;
+        }
+        if (lane == 0) NB.n = nnew;
+        __syncwarp();
+        cur ^= 1;
     }
 
     // ---- emit n-best ----
+    __threadfence_block();
+    __syncwarp();
+    const Beam& B = Bs[cur];
     const int nb = B.n;
-    if (tid == 0) P.out_nhyp[utt] = nb;
-    if (tid < nb) {
-        const int r = tid;
+    if (lane == 0) P.out_nhyp[utt] = nb;
+    if (lane < nb) {
+        const int r = lane;
         const long long o = ((long long)utt * beam + r) * P.max_len;
         const int ln = B.len[r];
         P.out_lens[utt * beam + r] = ln;
-        P.out_scores[utt * beam + r] = log_add2(B.s[r], B.ns[r]);
+        P.out_scores[utt * beam + r] = B.score[r];
         int node = B.node[r];
         for (int k = ln - 1; k >= 0 && node >= 0; --k) {
             P.out_tokens[o + k] = trie_tok[node];
             node = trie_parent[node];
         }
-        const int head = (B.vs[r] > B.vns[r]) ? B.ts[r] : B.tns[r];
+        const int head = B.times[r];
         int cnt = 0;
         for (int h = head; h >= 0; h = time_prev[h]) ++cnt;
         int k = cnt - 1;
         for (int h = head; h >= 0 && k >= 0; h = time_prev[h], --k)
             if (k < P.max_len) P.out_times[o + k] = time_t[h];
         for (int z = cnt; z < ln; ++z) P.out_times[o + z] = -1;
-    } else if (tid < beam) {
-        P.out_lens[utt * beam + tid] = 0;
-        P.out_scores[utt * beam + tid] = neg_inf();
+    } else if (lane < beam) {
+        P.out_lens[utt * beam + lane] = 0;
+        P.out_scores[utt * beam + lane] = neg_inf();
     }
 }
 
