@@ -365,14 +365,32 @@ class B200ASRModel:
               "wb_ctc_prefix_beam_search")
         th, mh, lh = self._host(toks), self._host(times), self._host(lens)
         sh, nh = self._host(scores), self._host(nhyp)
+        # flat, utterance-major view of all hypotheses (vectorised; reused by _rescore)
+        valid = np.arange(beam_size)[None, :] < nh[:, None]                       # (B, beam)
+        hyp_utt = np.nonzero(valid)[0].astype(np.int32)
+        hyp_len = lh[valid].astype(np.int32)
+        tok_mask = np.arange(max_len)[None, :] < hyp_len[:, None]                 # (n_hyp, max_len)
+        flat_toks = np.ascontiguousarray(th[valid][tok_mask].astype(np.int32))
+        flat_times = mh[valid][tok_mask]
+        hyp_tok0 = np.concatenate([[0], np.cumsum(hyp_len)[:-1]]).astype(np.int32) if hyp_len.size else \
+            np.zeros(0, np.int32)
+        flat_scores = np.ascontiguousarray(sh[valid].astype(np.float64))
+        tok_list, time_list = flat_toks.tolist(), flat_times.tolist()
         out = []
+        h = 0
         for b in range(B):
             n = int(nh[b])
-            nbest = [tuple(th[b, r, :lh[b, r]].tolist()) for r in range(n)]
-            nscores = [float(sh[b, r]) for r in range(n)]
-            ntimes = [mh[b, r, :lh[b, r]].tolist() for r in range(n)]
+            nbest, ntimes = [], []
+            for r in range(n):
+                a, e = int(hyp_tok0[h + r]), int(hyp_tok0[h + r]) + int(hyp_len[h + r])
+                nbest.append(tuple(tok_list[a:e]))
+                ntimes.append(time_list[a:e])
+            nscores = flat_scores[h:h + n].tolist()
             out.append(DecodeResult(tokens=nbest[0], score=nscores[0], times=ntimes[0], nbest=nbest,
                                     nbest_scores=nscores, nbest_times=ntimes))
+            h += n
+        self._last_flat = (hyp_utt, hyp_len, hyp_tok0, flat_toks if flat_toks.size else np.zeros(1, np.int32),
+                           flat_scores, out)
         return out
 
     def _flatten_hyps(self, hyps_per_utt):
@@ -393,8 +411,12 @@ class B200ASRModel:
             raise _lib.WbError("attention_rescoring needs decoder weights")
         lib = self._lib
         B = len(beam_out)
-        hyp_utt, hyp_len, hyp_tok0, toks = self._flatten_hyps([r.nbest for r in beam_out])
-        ctc_scores = np.ascontiguousarray(np.array([s for r in beam_out for s in r.nbest_scores], dtype=np.float64))
+        flat = getattr(self, "_last_flat", None)
+        if flat is not None and flat[5] is beam_out:
+            hyp_utt, hyp_len, hyp_tok0, toks, ctc_scores = flat[:5]
+        else:
+            hyp_utt, hyp_len, hyp_tok0, toks = self._flatten_hyps([r.nbest for r in beam_out])
+            ctc_scores = np.ascontiguousarray(np.array([s for r in beam_out for s in r.nbest_scores], dtype=np.float64))
         n_hyp = int(hyp_utt.size)
         R = int(hyp_len.sum()) + n_hyp
         l2r = torch.zeros(R, device=self.device, dtype=torch.float32)
@@ -409,35 +431,33 @@ class B200ASRModel:
                                          ptr(ctc_scores), self.sos, self.eos, float(ctc_weight),
                                          float(reverse_weight if use_r2l else 0.0), ptr(l2r), ptr(r2l), ptr(hyp_score),
                                          ptr(best), ptr(ws), ws.numel(), cur_stream()), "wb_attention_rescoring")
-        l2r_h, r2l_h = self._host(l2r), self._host(r2l)
+        l2r_h = self._host(l2r)
+        r2l_h = self._host(r2l) if use_r2l else None
         hs, bh = self._host(hyp_score), self._host(best)
+        row0 = np.concatenate([[0], np.cumsum(hyp_len.astype(np.int64) + 1)])
+        nb_per_utt = np.bincount(hyp_utt, minlength=B)
+        h0s = np.concatenate([[0], np.cumsum(nb_per_utt)[:-1]])
         out = []
-        h0 = 0
-        row0 = np.concatenate([[0], np.cumsum(hyp_len + 1)]).astype(np.int64)
         for b in range(B):
-            nb = len(beam_out[b].nbest)
+            nb = int(nb_per_utt[b])
             bi = int(bh[b])
-            h = h0 + bi
+            h = int(h0s[b]) + bi
             n = int(hyp_len[h])
             r0 = int(row0[h])
-            tc = [math.exp(float(l2r_h[r0 + j])) for j in range(n)]
-            score = np.float32(0.0)
-            for j in range(n + 1):
-                score = np.float32(score + l2r_h[r0 + j])
+            seg = l2r_h[r0:r0 + n + 1]
+            tc = np.exp(seg[:n].astype(np.float64))
+            score = np.cumsum(seg, dtype=np.float32)[-1]          # sequential fp32 sum, as the reference
             if use_r2l:
-                r_score = np.float32(0.0)
-                for j in range(n):
-                    s = r2l_h[r0 + (n - j - 1)]
-                    r_score = np.float32(r_score + s)
-                    tc[j] = (tc[j] + math.exp(float(s))) / 2
-                r_score = np.float32(r_score + r2l_h[r0 + n])
+                rseg = r2l_h[r0:r0 + n + 1]
+                # r_decoder_out[i][len-j-1][hyp[j]] (search.py:438-441): position n-1-j scores token j
+                tc = (tc + np.exp(rseg[:n][::-1].astype(np.float64))) / 2
+                r_score = np.cumsum(np.concatenate([rseg[:n][::-1], rseg[n:n + 1]]), dtype=np.float32)[-1]
                 score = np.float32(score * np.float32(1 - reverse_weight) + r_score * np.float32(reverse_weight))
             conf = math.exp(float(score) / (n + 1))
             res = DecodeResult(beam_out[b].nbest[bi], float(hs[h]), confidence=conf,
-                               times=beam_out[b].nbest_times[bi], tokens_confidence=tc)
-            res.nbest_scores = [float(x) for x in hs[h0:h0 + nb]]   # extra: all rescored hypotheses
+                               times=beam_out[b].nbest_times[bi], tokens_confidence=tc.tolist())
+            res.nbest_scores = hs[int(h0s[b]):int(h0s[b]) + nb].tolist()   # extra: all rescored hypotheses
             out.append(res)
-            h0 += nb
         return out
 
     # ----- asr_model.py:453-547 -----

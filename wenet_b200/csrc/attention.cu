@@ -15,6 +15,9 @@
 //   pass 2: S again, p = exp2(.), P (bf16) -> shared memory in the canonical K-major SWIZZLE_128B
 //           layout, O += P V (tcgen05.mma 128x64x128) — exact max known => no rescaling of O.
 // Q/K'/V tiles arrive by TMA (SWIZZLE_128B); V is consumed directly as an MN-major B operand.
+// The softmax normaliser is produced by the tensor core too (P times an all-ones operand -> TMEM),
+// and mask comparisons are only executed on tiles that cross a mask boundary: the kernel is bound by
+// instruction issue in the softmax loops, so every per-element instruction counts (ncu: profiles/).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -45,7 +48,7 @@ struct AttnDev {
     int v_mode;
 };
 
-constexpr int AT_SMEM = 1024 /*align*/ + 3 * TILE_BYTES /*Q,K,V*/ + 2 * TILE_BYTES /*P*/ + TILE_BYTES /*Vt*/ +
+constexpr int AT_SMEM = 1024 /*align*/ + 3 * TILE_BYTES /*Q,K,V*/ + 2 * TILE_BYTES /*P*/ + TILE_BYTES /*ones (2 KB used)*/ +
                         2 * 128 * 4 /*c*/ + 128 /*barriers*/;
 
 __global__ void __launch_bounds__(128, 2)
@@ -93,12 +96,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tmem_alloc(tmem_holder, 256);
         tmem_relinquish();
     }
+    // all-ones bf16 operand (layout-agnostic): P x ones accumulates the softmax normaliser in TMEM
+    for (int i = tid; i < 2048 / 16; i += 128)
+        reinterpret_cast<uint4*>(sVt)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t tmem_s = tmem_base;         // columns [0,128)
     const uint32_t tmem_o = tmem_base + 128;   // columns [128,192)
+    const uint32_t tmem_l = tmem_base + 192;   // columns [192,208): row sums of P
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
 
     // visible key range for this row, and the tile range for the CTA
@@ -114,10 +122,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     const int kt0 = cta_lo / AT_N;
     const int kt1 = (cta_hi + AT_N - 1) / AT_N;
+    // keys in [full_lo, full_hi) are visible to EVERY row of this CTA -> no per-element mask tests there
+    int full_lo = 0, full_hi = k_len;
+    if (P.chunk_size > 0) {
+        const int c = P.chunk_size;
+        const int q_first = qt * AT_M, q_last = qt * AT_M + AT_M - 1;
+        full_hi = min((q_first / c + 1) * c, k_len);
+        full_lo = (P.num_left_chunks < 0) ? 0 : max((q_last / c - P.num_left_chunks) * c, 0);
+    }
 
     uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_pv = 0;
     constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, AT_N, 0);
-    const uint32_t idesc_o = make_idesc_bf16(AT_M, DK, P.v_mode == 0 ? 1 : 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, DK, 1);   // V: MN-major B operand
+    constexpr uint32_t idesc_l = make_idesc_bf16(AT_M, 16, 1);
 
     if (tid == 0 && kt0 < kt1) {
         mbar_expect_tx(bar_q, TILE_BYTES);
@@ -164,16 +181,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
         }
         const float* cc = sC + (kt & 1) * 128;
+        const bool tile_full = (j0 >= full_lo) && (j0 + AT_N <= full_hi);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
             tmem_ld_wait();
+            if (tile_full) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int j = j0 + c * 32 + i;
-                const float s = fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]);
-                if (j >= row_lo && j < row_hi) m_run = fmaxf(m_run, s);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(cc + c * 32 + i);
+                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x));
+                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y));
+                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z));
+                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int j = j0 + c * 32 + i;
+                    const float s = fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]);
+                    if (j >= row_lo && j < row_hi) m_run = fmaxf(m_run, s);
+                }
             }
         }
         tc_fence_before();
@@ -182,7 +211,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const float m_fin = (m_run == -INFINITY) ? 0.f : m_run;
 
     // ------------------------------- pass 2: P, O -------------------------------
-    float l_run = 0.f;
     for (int kt = kt0; kt < kt1; ++kt) {
         const int j0 = kt * AT_N;
         {
@@ -212,24 +240,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + (kt + 1) * AT_N);
         }
         const float* cc = sC + (kt & 1) * 128;
+        const bool tile_full = (j0 >= full_lo) && (j0 + AT_N <= full_hi);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
             tmem_ld_wait();
             uint32_t pk[16];
+            if (tile_full) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                const int j = j0 + c * 32 + i;
-                float p0 = 0.f, p1 = 0.f;
-                if (j >= row_lo && j < row_hi)
-                    p0 = exp2f(fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]) - m_fin);
-                if (j + 1 >= row_lo && j + 1 < row_hi)
-                    p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[c * 32 + i + 1]) - m_fin);
-                const uint32_t w = pack_bf16x2(p0, p1);
-                // accumulate the normaliser from the *rounded* probabilities actually fed to the MMA
-                l_run += bf16_lo(w) + bf16_hi(w);
-                pk[i >> 1] = w;
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(cc + c * 32 + i);
+                    const float p0 = exp2f(fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x) - m_fin);
+                    const float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y) - m_fin);
+                    const float p2 = exp2f(fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z) - m_fin);
+                    const float p3 = exp2f(fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w) - m_fin);
+                    pk[i >> 1] = pack_bf16x2(p0, p1);
+                    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const int j = j0 + c * 32 + i;
+                    float p0 = 0.f, p1 = 0.f;
+                    if (j >= row_lo && j < row_hi)
+                        p0 = exp2f(fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]) - m_fin);
+                    if (j + 1 >= row_lo && j + 1 < row_hi)
+                        p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[c * 32 + i + 1]) - m_fin);
+                    pk[i >> 1] = pack_bf16x2(p0, p1);
+                }
             }
             // canonical K-major SWIZZLE_128B: row r, 16-byte chunk cidx -> chunk (cidx ^ (r & 7))
             uint8_t* prow = sP + (c >> 1) * TILE_BYTES + tid * 128;
@@ -240,44 +279,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
             }
         }
-        if (P.v_mode == 1) {
-            // fallback: transpose V tile [key][dk] (TMA swizzled) into K-major [dk][key] panels
-            mbar_wait(bar_v, ph_v);
-            const int key = tid;
-            const uint8_t* vrow = sV + key * 128;
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                const uint4 v4 = *reinterpret_cast<const uint4*>(vrow + ((ch ^ (key & 7)) << 4));
-                const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int dk = ch * 8 + e;
-                    const uint16_t val = (uint16_t)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffff));
-                    uint8_t* dst = sVt + (key >> 6) * (TILE_BYTES / 2) + dk * 128 +
-                                   ((((key & 63) >> 3) ^ (dk & 7)) << 4) + (key & 7) * 2;
-                    *reinterpret_cast<uint16_t*>(dst) = val;
-                }
-            }
-        }
         ph_v ^= 1;
-        fence_proxy_async_smem();  // generic-proxy smem writes (P, Vt) -> visible to the tensor core
+        fence_proxy_async_smem();  // generic-proxy smem writes (P) -> visible to the tensor core
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
-            if (P.v_mode == 0) mbar_wait(bar_v, ph_v ^ 1);
+            mbar_wait(bar_v, ph_v ^ 1);
             tc_fence_after();
-            const uint32_t pa = smem_u32(sP);
+            const uint32_t pa = smem_u32(sP), va = smem_u32(sV), oa = smem_u32(sVt);
 #pragma unroll
             for (int ks = 0; ks < AT_N / 16; ++ks) {
                 const uint64_t adesc =
                     make_smem_desc_sw128(pa + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024);
-                uint64_t bdesc;
-                if (P.v_mode == 0)
-                    bdesc = make_smem_desc_sw128(smem_u32(sV) + ks * 2048, 1024, 1024);
-                else
-                    bdesc = make_smem_desc_sw128(smem_u32(sVt) + (ks >> 2) * (TILE_BYTES / 2) + (ks & 3) * 32,
-                                                 16, 1024);
-                umma_f16(tmem_o, adesc, bdesc, idesc_o, (kt != kt0 || ks != 0) ? 1u : 0u);
+                const uint32_t acc = (kt != kt0 || ks != 0) ? 1u : 0u;
+                umma_f16(tmem_o, adesc, make_smem_desc_sw128(va + ks * 2048, 1024, 1024), idesc_o, acc);
+                // row sums of the (bf16-rounded) probabilities: P x ones, 16 columns wide
+                umma_f16(tmem_l, adesc, make_smem_desc_sw128(oa, 1024, 1024), idesc_l, acc);  // same 2 KB of ones for every k-step
             }
             umma_commit(bar_pv);
         }
@@ -293,6 +310,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     // ------------------------------- epilogue -------------------------------
     if (kt0 < kt1) {
+        float l_run;
+        {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_l + lane_sel, r);
+            tmem_ld_wait();
+            l_run = __uint_as_float(r[0]);
+        }
         const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
