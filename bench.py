@@ -186,6 +186,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=2)
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event profiler")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="batches in flight per GPU (host threads x CUDA streams sharing one weight replica); "
+                         "1 = strictly sequential steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -233,10 +236,52 @@ def main():
     flens = torch.full((B,), nframes, dtype=torch.int64, device=dev)
     methods = [args.mode]
 
-    def step(pcm_dev):
+    def step(pcm_dev, mdl=None):
         feats = fb(pcm_dev, ns)
-        return model.decode(methods, feats, flens, beam_size=wl["beam"], ctc_weight=wl["ctc_weight"],
-                            reverse_weight=wl["reverse_weight"])
+        return (mdl or model).decode(methods, feats, flens, beam_size=wl["beam"], ctc_weight=wl["ctc_weight"],
+                                     reverse_weight=wl["reverse_weight"])
+
+    # several batches in flight: one host thread + one CUDA stream + one workspace set per slot, all on the
+    # same (immutable) device weights.  Hides the host-side result handling and the latency-bound search
+    # kernel of one batch behind the GEMMs of the next.  A step is still one full pass over one batch.
+    import threading
+    n_slots = max(1, args.inflight)
+    lib.wb_set_sm_reserve(8 if n_slots > 1 else 0)   # room for the other batch's search kernel (batch/8 CTAs)
+    slot_models = [model] + [model.clone_shared() for _ in range(n_slots - 1)]
+    slot_streams = [torch.cuda.Stream(device=dev) for _ in range(n_slots)]
+
+    def run_steps(fn, steps):
+        """fn(i, mdl) for i in range(steps), distributed over the slots."""
+        if n_slots == 1:
+            for i in range(steps):
+                fn(i, model)
+            return
+        nxt = [0]
+        lock = threading.Lock()
+        errs = []
+
+        def worker(w):
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(slot_streams[w]):
+                    while True:
+                        with lock:
+                            i = nxt[0]
+                            nxt[0] += 1
+                        if i >= steps:
+                            break
+                        fn(i, slot_models[w])
+                    slot_streams[w].synchronize()
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        ths = [threading.Thread(target=worker, args=(w,)) for w in range(n_slots)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,8 +293,7 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
-            fn(i)
+        run_steps(fn, steps)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -263,6 +307,7 @@ def main():
     # ---- warm-up ----
     for i in range(args.warmup):
         res = step(dev_pcm[i % NROT])
+    run_steps(lambda i, mdl: step(dev_pcm[i % NROT], mdl), 2 * n_slots if n_slots > 1 else 0)   # warm every slot
     torch.cuda.synchronize()
     n_tok = sum(len(r.tokens) for r in res[args.mode])
 
@@ -273,7 +318,7 @@ def main():
     if not args.no_profile:
         lib.wb_prof_reset()
         lib.wb_prof_enable(1)
-    ms = timed(lambda i: step(dev_pcm[i % NROT]), args.steps)
+    ms = timed(lambda i, mdl: step(dev_pcm[i % NROT], mdl), args.steps)
     launches = lib.wb_launch_count() - launches0
     prof = None
     if not args.no_profile:
@@ -286,17 +331,16 @@ def main():
         lib.wb_prof_reset()
 
     # ---- end to end: pinned host PCM -> H2D -> decode -> results on host ----
-    model.d2h_bytes = 0
-
-    def e2e_step(i):
+    def e2e_step(i, mdl):
         pcm = host_pcm[i % NROT].to(dev, non_blocking=True)
-        return step(pcm)
+        return step(pcm, mdl)
 
     for i in range(2):
-        e2e_step(i)
-    model.d2h_bytes = 0
+        e2e_step(i, model)
+    for m_ in slot_models:
+        m_.d2h_bytes = 0
     ms_e2e = timed(e2e_step, args.steps)
-    d2h = int(getattr(model, "d2h_bytes", 0) / max(args.steps, 1))
+    d2h = int(sum(m_.d2h_bytes for m_ in slot_models) / max(args.steps, 1))
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -314,7 +358,7 @@ def main():
                    "l2": "inputs rotate over %d distinct PCM batches (%.0f MB > L2) and every step streams GBs of "
                          "activations" % (NROT, NROT * B * n * 2 / 1e6),
                    "weights": "random init, seed 777, CTC head sharpened (synth.py)",
-                   "tokens_per_batch": n_tok},
+                   "tokens_per_batch": n_tok, "inflight_batches": n_slots},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": B * n * 2, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},

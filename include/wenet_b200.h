@@ -52,6 +52,9 @@ unsigned long long wb_launch_count(void);
  * launching stream.  wb_prof_collect synchronises the device and returns, per tag, the summed
  * elapsed ms, the summed algorithmic work (FLOPs for gemm_tcgen05, bytes for the memory-bound
  * kernels, 0 where not tracked) and the number of launches since wb_prof_reset. */
+/* the persistent GEMM kernels use (num_SMs - n) CTAs, leaving n SMs for latency-bound kernels (prefix beam
+ * search) of other in-flight batches running on other streams; default 0 */
+void wb_set_sm_reserve(int n);
 void wb_prof_enable(int on);
 void wb_prof_reset(void);
 int wb_prof_num_tags(void);

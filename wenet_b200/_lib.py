@@ -32,6 +32,7 @@ _PROTOS = {
     "wb_last_error": (C.c_char_p, []),
     "wb_version": (C.c_char_p, []),
     "wb_launch_count": (C.c_ulonglong, []),
+    "wb_set_sm_reserve": (None, [i32]),
     "wb_prof_enable": (None, [i32]),
     "wb_prof_reset": (None, []),
     "wb_prof_num_tags": (i32, []),

@@ -147,6 +147,20 @@ class B200ASRModel:
     def to(self, *a, **k):
         return self
 
+    def clone_shared(self) -> "B200ASRModel":
+        """A second front-end on the SAME device weights with its own workspaces — a finalized wb_model is
+        immutable, so several host threads may decode concurrently on different streams (header comment
+        of include/wenet_b200.h; mirrors TorchAsrModel::Copy, runtime/core/decoder/torch_asr_model.cc:87-111)."""
+        import copy
+        other = copy.copy(self)
+        other.encoder = B200ConformerEncoder(other)
+        other.ctc = B200CTC(other)
+        other._ws = None
+        other._ws2 = None
+        other.d2h_bytes = 0
+        other._last_flat = None
+        return other
+
     @classmethod
     def from_reference(cls, model, configs: dict, device=None):
         """Wrap a loaded reference ASRModel (same weights, same results, B200 kernels)."""

@@ -170,8 +170,9 @@ extern "C" {
 
 const char* wb_last_error(void) { return get_last_error(); }
 const char* wb_version(void) { return "wenet_b200 0.1 (sm_100a)"; }
-unsigned long long wb_launch_count(void) { return g_launch_count; }
+unsigned long long wb_launch_count(void) { return g_launch_count.load(); }
 
+void wb_set_sm_reserve(int n) { gemm_set_sm_reserve(n); }
 void wb_prof_enable(int on) { g_prof_on = on; }
 void wb_prof_reset(void) { wb::prof_reset(); }
 int wb_prof_num_tags(void) { return PT_COUNT; }

@@ -251,10 +251,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 c4 = *reinterpret_cast<const float4*>(cc + c * 32 + i);
-                    const float p0 = exp2f(fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x) - m_fin);
-                    const float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y) - m_fin);
-                    const float p2 = exp2f(fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z) - m_fin);
-                    const float p3 = exp2f(fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w) - m_fin);
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x) - m_fin);
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y) - m_fin);
+                    const float p2 = fast_exp2(fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z) - m_fin);
+                    const float p3 = fast_exp2(fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w) - m_fin);
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                     pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
                 }
@@ -264,9 +264,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const int j = j0 + c * 32 + i;
                     float p0 = 0.f, p1 = 0.f;
                     if (j >= row_lo && j < row_hi)
-                        p0 = exp2f(fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]) - m_fin);
+                        p0 = fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]) - m_fin);
                     if (j + 1 >= row_lo && j + 1 < row_hi)
-                        p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[c * 32 + i + 1]) - m_fin);
+                        p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[c * 32 + i + 1]) - m_fin);
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                 }
             }

@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/wenet_b200.h"  // wb_status codes
 
 namespace wb {
@@ -40,8 +41,8 @@ const char* get_last_error();
     } while (0)
 
 // launch counter: every kernel launch made by this library bumps it (bench.py reports it)
-extern unsigned long long g_launch_count;
-static inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+extern std::atomic<unsigned long long> g_launch_count;
+static inline void count_launch(int n = 1) { g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 // Optional per-kernel-family profiler (CUDA events on the launching stream around every launch).
 // Off by default; bench.py switches it on to obtain live per-kernel durations and roofline numbers.
@@ -88,8 +89,20 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// fast-math activations for the GEMM epilogues (ex2.approx + rcp.approx: ~2 ulp, far below bf16 output rounding)
-__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+// single-instruction MUFU approximations (ex2.approx.ftz / rcp.approx.ftz, ~2 ulp — far below the bf16 rounding
+// of everything they feed).  NB: __expf / exp2f / __frcp_rn expand to 5-70 SASS instructions each (denormal
+// range fix-ups, IEEE-rounded reciprocal), which made the SiLU / GLU GEMM epilogues ALU-bound.
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fast_rcp(1.0f + fast_exp2(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -107,8 +107,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m_tile = t % p.num_m_tiles;
-                const int n_tile = t / p.num_m_tiles;
+                const int n_tile = t % p.num_n_tiles;  // n fastest: concurrently running CTAs cover whole output rows
+                const int m_tile = t / p.num_n_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -169,8 +169,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t acc_phase = 0;
         bool need_wait = false;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int m_tile = t % p.num_m_tiles;
-            const int n_tile = t / p.num_m_tiles;
+            const int n_tile = t % p.num_n_tiles;
+            const int m_tile = t / p.num_n_tiles;
             const long long row = (long long)m_tile * BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -400,6 +400,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 int g_num_sms = 0;
+int g_sm_reserve = 0;  // SMs left free for concurrently running latency-bound kernels on other streams
 
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
@@ -417,7 +418,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         WB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    const int usable = (g_num_sms - g_sm_reserve) > 1 ? (g_num_sms - g_sm_reserve) : 1;
+    const int grid = tiles < usable ? tiles : usable;
     ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
     gemm_tcgen05_kernel<BN><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
     count_launch();
@@ -426,6 +428,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 }
 
 }  // namespace
+
+void gemm_set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 
 int gemm_bn_for(int N) { return (N % 256 == 0 || N >= 1024) ? 256 : 128; }
 

@@ -18,6 +18,7 @@ enum GemmEpi : int {
 };
 
 int gemm_bn_for(int N);
+void gemm_set_sm_reserve(int n);
 // tensor map for a [N, K] bf16 weight (B operand), box rows = gemm_bn_for(N)
 int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K);
 // C = epi(A[M,K](lda) * B[N,K]^T + bias). tmap_b_opt may be null (then built from B).

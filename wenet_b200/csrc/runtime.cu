@@ -2,13 +2,14 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
 #include <vector>
 #include <utility>
 
 namespace wb {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 static thread_local char g_err[1024] = {0};
 
@@ -30,9 +31,13 @@ struct ProfRec {
 };
 std::vector<ProfRec> g_recs;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_free_events;
+std::mutex g_prof_mu;
+// prof_begin/prof_end pairs are issued by one host thread per stream; the record index travels in TLS
+thread_local long g_cur_rec = -1;
 }  // namespace
 
 void prof_begin(int tag, cudaStream_t st, double work) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfRec r;
     r.tag = tag;
     r.work = work;
@@ -46,16 +51,21 @@ void prof_begin(int tag, cudaStream_t st, double work) {
     }
     cudaEventRecord(r.e0, st);
     g_recs.push_back(r);
+    g_cur_rec = (long)g_recs.size() - 1;
 }
 void prof_end(cudaStream_t st) {
-    if (!g_recs.empty()) cudaEventRecord(g_recs.back().e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_cur_rec >= 0 && g_cur_rec < (long)g_recs.size()) cudaEventRecord(g_recs[g_cur_rec].e1, st);
+    g_cur_rec = -1;
 }
 void prof_reset() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& r : g_recs) g_free_events.push_back({r.e0, r.e1});
     g_recs.clear();
 }
 int prof_collect(double* ms, double* work, long long* launches) {
     cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (int t = 0; t < PT_COUNT; ++t) {
         ms[t] = 0;
         work[t] = 0;

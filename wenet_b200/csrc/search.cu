@@ -26,7 +26,9 @@ namespace {
 
 constexpr int MAXB = 16;
 constexpr int NCAND = MAXB + MAXB * MAXB;
-constexpr int PB_THREADS = 32;          // one warp per utterance: every barrier is a __syncwarp
+constexpr int PB_WARPS = 8;             // utterances per CTA: one warp each, every barrier is a __syncwarp, so the
+                                        // whole batch occupies only batch/8 SMs and other streams keep the rest
+constexpr int PB_THREADS = 32 * PB_WARPS;
 constexpr int MAXPL = (NCAND + 31) / 32;  // candidates per lane in the selection step
 
 __device__ __forceinline__ double neg_inf() { return -CUDART_INF; }
@@ -90,18 +92,30 @@ __device__ __forceinline__ bool cand_better(double ta, int fa, double tb, int fb
     return ta > tb || (ta == tb && fa < fb);
 }
 
-__global__ void __launch_bounds__(PB_THREADS)
-prefix_beam_kernel(PbDev P) {
-    __shared__ Beam Bs[2];
-    __shared__ Cand C;
-    __shared__ float tk_val[MAXB];
-    __shared__ int tk_idx[MAXB];
-    __shared__ int dest[MAXB * MAXB];
-    __shared__ int rank_slot[MAXB];
-    __shared__ int vlist[NCAND];
+struct WarpState {
+    Beam Bs[2];
+    Cand C;
+    float tk_val[MAXB];
+    int tk_idx[MAXB];
+    int dest[MAXB * MAXB];
+    int rank_slot[MAXB];
+    int vlist[NCAND];
+};
 
-    const int utt = blockIdx.x;
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(PB_THREADS)
+prefix_beam_kernel(PbDev P, int batch) {
+    extern __shared__ __align__(16) uint8_t pb_smem[];
+    const int utt = blockIdx.x * PB_WARPS + (threadIdx.x >> 5);
+    if (utt >= batch) return;  // whole warp; no block-level barriers are used anywhere below
+    WarpState& W = reinterpret_cast<WarpState*>(pb_smem)[threadIdx.x >> 5];
+    Beam* Bs = W.Bs;
+    Cand& C = W.C;
+    float* tk_val = W.tk_val;
+    int* tk_idx = W.tk_idx;
+    int* dest = W.dest;
+    int* rank_slot = W.rank_slot;
+    int* vlist = W.vlist;
+    const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int beam = P.beam;
     const int T = P.seq_len[utt];
@@ -113,6 +127,7 @@ prefix_beam_kernel(PbDev P) {
     int* time_t = time_prev + pool_n;
     const int ncs = MAXB + beam * MAXB;  // candidate slots in use
 
+    for (int c = lane; c < NCAND; c += 32) C.valid[c] = 0;
     if (lane == 0) {
         Beam& B = Bs[0];
         B.n = 1;
@@ -144,7 +159,6 @@ prefix_beam_kernel(PbDev P) {
             tk_val[lane] = pf_val;
             tk_idx[lane] = pf_idx;
         }
-        for (int c = lane; c < ncs; c += 32) C.valid[c] = 0;
         __syncwarp();
         if (lane < beam && t + 1 < T) {  // prefetch the next frame's top-k behind this frame's work
             pf_val = P.topk_val[(f0 + t + 1) * P.topk + lane];
@@ -163,7 +177,7 @@ prefix_beam_kernel(PbDev P) {
                 const int ln = B.len[pi] + 1;
                 d = MAXB + ui * MAXB + pi;
                 for (int q = 0; q < nb; ++q)
-                    if (B.hash[q] == h && B.len[q] == ln && B.last[q] == u) d = q;
+                    if (B.last[q] == u && B.len[q] == ln && B.hash[q] == h) d = q;
                 if (d >= MAXB) {
                     const double prob = (double)tk_val[ui];
                     const bool rep = (u == B.last[pi]);
@@ -191,7 +205,7 @@ prefix_beam_kernel(PbDev P) {
                     C.new_tok[d] = u;
                     C.first[d] = (ui * nb + pi) * 2 + (rep ? 1 : 0);
                     C.total[d] = nsv;  // log_add(-inf, ns)
-                    C.valid[d] = 1;
+                    C.valid[d] = t + 1;   // frame stamp: no per-frame reset of the flags
                 }
             }
             dest[ui * MAXB + pi] = d;
@@ -272,7 +286,7 @@ prefix_beam_kernel(PbDev P) {
                 C.new_tok[q] = -1;
                 C.first[q] = first;
                 C.total[q] = log_add2(s, ns);
-                C.valid[q] = 1;
+                C.valid[q] = t + 1;
             }
         }
         __syncwarp();
@@ -281,7 +295,7 @@ prefix_beam_kernel(PbDev P) {
         int nvalid = 0;
         for (int base = 0; base < ncs; base += 32) {
             const int c = base + lane;
-            const bool v = (c < ncs) && C.valid[c];
+            const bool v = (c < ncs) && (C.valid[c] == t + 1);
             const unsigned m = __ballot_sync(0xffffffffu, v);
             if (v) vlist[nvalid + __popc(m & lt_mask)] = c;
             nvalid += __popc(m);
@@ -289,6 +303,7 @@ prefix_beam_kernel(PbDev P) {
         __syncwarp();
         double my_tot[MAXPL];
         int my_first[MAXPL], my_slot[MAXPL];
+        const int kmax = (nvalid + 31) >> 5;  // warp-uniform: candidates per lane actually in use
 #pragma unroll
         for (int k = 0; k < MAXPL; ++k) {
             const int i = lane + 32 * k;
@@ -309,7 +324,7 @@ prefix_beam_kernel(PbDev P) {
             int bf = INT_MAX, bs = -1;
 #pragma unroll
             for (int k = 0; k < MAXPL; ++k)
-                if (my_slot[k] >= 0 && cand_better(my_tot[k], my_first[k], bt, bf)) {
+                if (k < kmax && my_slot[k] >= 0 && cand_better(my_tot[k], my_first[k], bt, bf)) {
                     bt = my_tot[k];
                     bf = my_first[k];
                     bs = my_slot[k];
@@ -327,7 +342,7 @@ prefix_beam_kernel(PbDev P) {
             }
 #pragma unroll
             for (int k = 0; k < MAXPL; ++k)
-                if (my_slot[k] == bs) my_slot[k] = -1;  // taken
+                if (k < kmax && my_slot[k] == bs) my_slot[k] = -1;  // taken
             if (lane == 0) rank_slot[r] = bs;
         }
         __syncwarp();
@@ -431,8 +446,14 @@ int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream) {
     P.out_scores = a.out_scores;
     P.out_nhyp = a.out_nhyp;
     P.pool = reinterpret_cast<int*>(a.workspace);
+    const size_t smem = sizeof(WarpState) * PB_WARPS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        WB_CHECK_CUDA(cudaFuncSetAttribute(prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
     ProfScope _ps(PT_PREFIX_BEAM, stream, 0.0);
-    prefix_beam_kernel<<<a.batch, PB_THREADS, 0, stream>>>(P);
+    prefix_beam_kernel<<<ceil_div(a.batch, PB_WARPS), PB_THREADS, smem, stream>>>(P, a.batch);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
