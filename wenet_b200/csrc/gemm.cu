@@ -40,6 +40,12 @@ struct GemmCfg {
     // epilogue staging: 8 warps x (32 rows x 128 B), SWIZZLE_128B, read back by TMA stores
     static constexpr int kOutBytes = 8 * 4096;
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    // weight-stationary mode (K <= kResMaxKB * 64): the whole [BN x K] weight panel of the current n-tile
+    // stays in shared memory while the CTA streams A tiles past it -> per tile only the 128 x K A tile is
+    // fetched from L2 (the per-SM L2 path, ~80 GB/s, is what bounds the K = 256 GEMMs otherwise)
+    static constexpr int kResMaxKB = (BN == 256) ? 4 : 8;
+    static constexpr int kResBBytes = kResMaxKB * kBBytes;
+    static constexpr int kResAStages = (kStages * kStageBytes - kResBBytes) / kABytes;
 };
 
 struct GemmParams {
@@ -54,7 +60,7 @@ struct GemmParams {
     int num_m_tiles, num_n_tiles;
 };
 
-template <int BN>
+template <int BN, bool BRES>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
@@ -63,15 +69,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~uintptr_t(1023));
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+    constexpr int kRing = BRES ? Cfg::kResAStages : Cfg::kStages;   // A (or A+B) ring depth
+    uint8_t* smem_a = BRES ? smem + Cfg::kResBBytes : smem;
+    uint8_t* smem_b = BRES ? smem : smem + Cfg::kStages * Cfg::kABytes;
     uint8_t* smem_out = smem + Cfg::kStages * Cfg::kStageBytes;   // 1024-aligned (stage sizes are multiples of 1024)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes);
-    uint64_t* full_bar = bars;                       // [kStages]
-    uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
-    uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]
-    uint64_t* tmem_empty = tmem_full + 2;            // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* full_bar = bars;                // [kRing]
+    uint64_t* empty_bar = bars + 8;           // [kRing]
+    uint64_t* tmem_full = bars + 16;          // [2]
+    uint64_t* tmem_empty = bars + 18;         // [2]
+    uint64_t* b_full = bars + 20;             // resident weight panel landed
+    uint64_t* b_empty = bars + 21;            // all MMAs reading the resident panel retired
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 22);
+    static_assert(kRing <= 8, "barrier layout");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -82,10 +92,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if (p.use_tma_out) tma_prefetch_desc(&tmap_c);
-        for (int s = 0; s < Cfg::kStages; ++s) {
+        for (int s = 0; s < kRing; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
+        mbar_init(b_full, 1);
+        mbar_init(b_empty, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 8);  // one arrive per epilogue warp
@@ -100,23 +112,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    // tile schedule.  streaming mode: t = blockIdx.x + i * gridDim.x, n fastest.  weight-stationary mode: each
+    // CTA owns a contiguous range of the n-major tile list, so its weight panel changes at most a few times.
+    const int per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = BRES ? blockIdx.x * per_cta : blockIdx.x;
+    const int t_end = BRES ? min(num_tiles, t_begin + per_cta) : num_tiles;
+    const int t_step = BRES ? 1 : gridDim.x;
+#define WB_TILE_COORDS(t)                                                      \
+    const int n_tile = BRES ? (t) / p.num_m_tiles : (t) % p.num_n_tiles;      \
+    const int m_tile = BRES ? (t) % p.num_m_tiles : (t) / p.num_n_tiles;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int n_tile = t % p.num_n_tiles;  // n fastest: concurrently running CTAs cover whole output rows
-                const int m_tile = t / p.num_n_tiles;
+            int cur_n = -1;
+            uint32_t bemp_phase = 0;
+            for (int t = t_begin; t < t_end; t += t_step) {
+                WB_TILE_COORDS(t)
+                if (BRES && n_tile != cur_n) {
+                    if (cur_n >= 0) {  // the previous panel must not be overwritten while MMAs still read it
+                        mbar_wait(b_empty, bemp_phase);
+                        bemp_phase ^= 1;
+                    }
+                    mbar_expect_tx(b_full, (uint32_t)num_kb * Cfg::kBBytes);
+                    for (int kb = 0; kb < num_kb; ++kb)
+                        tma_load_2d(smem_b + kb * Cfg::kBBytes, &tmap_b, b_full, kb * BK, n_tile * BN);
+                    cur_n = n_tile;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    mbar_expect_tx(&full_bar[stage], BRES ? Cfg::kABytes : Cfg::kStageBytes);
                     tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK,
                                 m_tile * BM);
-                    tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK,
-                                n_tile * BN);
-                    if (++stage == Cfg::kStages) {
+                    if (!BRES)
+                        tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK,
+                                    n_tile * BN);
+                    if (++stage == kRing) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -131,7 +164,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int cur_n = -1;
+            uint32_t bfull_phase = 0;
+            for (int t = t_begin; t < t_end; t += t_step) {
+                WB_TILE_COORDS(t)
+                (void)m_tile;
+                if (BRES && n_tile != cur_n) {
+                    mbar_wait(b_full, bfull_phase);
+                    bfull_phase ^= 1;
+                    cur_n = n_tile;
+                }
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -139,7 +181,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+                    const uint32_t b_addr = smem_u32(smem_b + (BRES ? kb : stage) * Cfg::kBBytes);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
@@ -147,12 +189,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
-                    if (++stage == Cfg::kStages) {
+                    if (++stage == kRing) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
                 umma_commit(&tmem_full[acc]);  // accumulator complete
+                if (BRES && t + t_step < t_end) {
+                    const int next_n = (t + t_step) / p.num_m_tiles;
+                    if (next_n != n_tile) umma_commit(b_empty);  // panel may be replaced once these MMAs retire
+                }
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -168,9 +214,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         int acc = 0;
         uint32_t acc_phase = 0;
         bool need_wait = false;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int n_tile = t % p.num_n_tiles;
-            const int m_tile = t / p.num_n_tiles;
+        for (int t = t_begin; t < t_end; t += t_step) {
+            WB_TILE_COORDS(t)
             const long long row = (long long)m_tile * BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -227,7 +272,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     } else if (p.epi == EPI_GLU_BF16) {
                         float g[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_f(v[16 + i]);
+                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_t(v[16 + i]);
 #pragma unroll
                         for (int u = 0; u < 2; ++u)
                             *reinterpret_cast<uint4*>(sbuf + ((((c & 3) * 2 + u) ^ sw) << 4)) =
@@ -238,7 +283,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     } else {
                         if (p.epi == EPI_BF16_SILU) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                            for (int i = 0; i < 32; ++i) v[i] = silu_t(v[i]);
                         } else if (p.epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -277,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     case EPI_BF16_RELU: {
                         if (p.epi == EPI_BF16_SILU) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                            for (int i = 0; i < 32; ++i) v[i] = silu_t(v[i]);
                         } else if (p.epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -329,7 +374,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + (n0 >> 1);
                         float g[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_f(v[16 + i]);
+                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_t(v[16 + i]);
                         uint32_t pk[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
@@ -391,6 +436,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (p.use_tma_out && lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores
     }
 
+#undef WB_TILE_COORDS
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -402,13 +448,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 int g_num_sms = 0;
 int g_sm_reserve = 0;  // SMs left free for concurrently running latency-bound kernels on other streams
 
-template <int BN>
+template <int BN, bool BRES>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                 cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
+        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, BRES>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
@@ -421,7 +467,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     const int usable = (g_num_sms - g_sm_reserve) > 1 ? (g_num_sms - g_sm_reserve) : 1;
     const int grid = tiles < usable ? tiles : usable;
     ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
-    gemm_tcgen05_kernel<BN><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
+    gemm_tcgen05_kernel<BN, BRES><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
@@ -484,8 +530,13 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
         rc = make_tmap_2d(&tc, out, eb, (uint64_t)M, (uint64_t)out_cols, (uint64_t)ldc, 32, f32_out ? 32 : 64);
         if (rc != WB_OK) return rc;
     }
-    if (bn == 256) return launch_gemm<256>(ta, *tb, tc, p, stream);
-    return launch_gemm<128>(ta, *tb, tc, p, stream);
+    const int num_kb = ceil_div(K, BK);
+    if (bn == 256) {
+        if (num_kb <= GemmCfg<256>::kResMaxKB) return launch_gemm<256, true>(ta, *tb, tc, p, stream);
+        return launch_gemm<256, false>(ta, *tb, tc, p, stream);
+    }
+    if (num_kb <= GemmCfg<128>::kResMaxKB) return launch_gemm<128, true>(ta, *tb, tc, p, stream);
+    return launch_gemm<128, false>(ta, *tb, tc, p, stream);
 }
 
 }  // namespace wb

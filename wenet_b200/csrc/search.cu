@@ -19,6 +19,7 @@
 #include "kernels.h"
 #include <limits.h>
 #include <math_constants.h>
+#include "softplus_table.h"
 
 namespace wb {
 
@@ -33,16 +34,34 @@ constexpr int MAXPL = (NCAND + 31) / 32;  // candidates per lane in the selectio
 
 __device__ __forceinline__ double neg_inf() { return -CUDART_INF; }
 
-// log_add of wenet/utils/common.py:302-310 for two arguments, bit-for-bit:
-//   m + log(exp(a - m) + exp(b - m)); the larger argument contributes exp(0) == 1.0 exactly, and
-//   log_add(-inf, x) == x exactly (0.0 + 1.0 -> log 1.0 == 0.0), so those cases skip the libm calls.
+// f(d) = log(1 + exp(d)) for d <= 0: piecewise degree-12 polynomials (softplus_table.h, max abs error 1.1e-16
+// against the exact value — the same as libm's log1p(exp(d))).  libdevice's fp64 exp + log are ~250 dependent
+// instructions; in this single-warp, latency-bound kernel they were 2/3 of the run time (ncu, profiles/).
+__device__ __forceinline__ double softplus_neg(double d) {
+    // reference arithmetic: 1.0 + exp(d) rounds to 1.0 once exp(d) <= 2^-53, and log(1.0) == 0 exactly
+    if (d < -36.7368005696771) return 0.0;
+    int idx = (int)(-2.0 * d);
+    idx = idx > WB_SOFTPLUS_NINT - 1 ? WB_SOFTPLUS_NINT - 1 : idx;
+    const double t = fma(4.0, d, 2.0 * (double)idx + 1.0);   // (d - mid) / 0.25, mid = -(idx + 0.5) / 2
+    const double* c = g_softplus_tab[idx];
+    double coef[WB_SOFTPLUS_DEG + 1];
+#pragma unroll
+    for (int j = 0; j <= WB_SOFTPLUS_DEG; ++j) coef[j] = __ldg(c + j);
+    double v = coef[WB_SOFTPLUS_DEG];
+#pragma unroll
+    for (int j = WB_SOFTPLUS_DEG - 1; j >= 0; --j) v = fma(v, t, coef[j]);
+    return v;
+}
+
+// log_add of wenet/utils/common.py:302-310 for two arguments:
+//   m + log(exp(a - m) + exp(b - m)) = m + log(1 + exp(lo - m))   (the larger argument contributes exp(0) == 1.0
+//   exactly); log_add(-inf, x) == x exactly, so those cases return early as the reference's arithmetic does.
 __device__ __forceinline__ double log_add2(double a, double b) {
     if (a == neg_inf()) return b;
     if (b == neg_inf()) return a;
     const double m = a > b ? a : b;
     const double lo = a > b ? b : a;
-    // Python: sum(...) adds exp(a-m) then exp(b-m); IEEE addition is commutative so the order is immaterial
-    return m + log(1.0 + exp(lo - m));
+    return m + softplus_neg(lo - m);
 }
 
 __device__ __forceinline__ uint64_t mix_hash(uint64_t h, int tok) {
@@ -301,49 +320,117 @@ prefix_beam_kernel(PbDev P, int batch) {
             nvalid += __popc(m);
         }
         __syncwarp();
+        // Exact top-`beam` of <= beam + beam^2 candidates without serial arg-max rounds:
+        //  (1) every lane reduces its own <= MAXPL candidates to a local best; the `beam`-th best of the 32 local
+        //      bests is a lower bound of the true `beam`-th best total, so everything strictly below it is pruned
+        //      (ranks among lanes by 31 independent shuffle rotations);
+        //  (2) the survivors (>= beam, typically 10-15) are compacted one per lane and ranked the same way.
+        //  Order = the reference's stable descending sort: (total desc, dict insertion order asc).
+        const int kmax = (nvalid + 31) >> 5;  // warp-uniform
         double my_tot[MAXPL];
         int my_first[MAXPL], my_slot[MAXPL];
-        const int kmax = (nvalid + 31) >> 5;  // warp-uniform: candidates per lane actually in use
+        double lt = neg_inf();
+        int lf = INT_MAX;
 #pragma unroll
         for (int k = 0; k < MAXPL; ++k) {
-            const int i = lane + 32 * k;
-            if (i < nvalid) {
-                const int c = vlist[i];
-                my_slot[k] = c;
-                my_tot[k] = C.total[c];
-                my_first[k] = C.first[c];
-            } else {
-                my_slot[k] = -1;
-                my_tot[k] = neg_inf();
-                my_first[k] = INT_MAX;
+            my_slot[k] = -1;
+            my_tot[k] = neg_inf();
+            my_first[k] = INT_MAX;
+            if (k < kmax) {
+                const int i = lane + 32 * k;
+                if (i < nvalid) {
+                    const int c = vlist[i];
+                    my_slot[k] = c;
+                    my_tot[k] = C.total[c];
+                    my_first[k] = C.first[c];
+                    if (cand_better(my_tot[k], my_first[k], lt, lf)) {
+                        lt = my_tot[k];
+                        lf = my_first[k];
+                    }
+                }
             }
         }
+        double thr_t = neg_inf();
+        int thr_f = INT_MAX;  // default: nothing is pruned
+        if (nvalid > 32) {
+            int rk = 0;
+#pragma unroll
+            for (int r = 1; r < 32; ++r) {
+                const double ot = __shfl_sync(0xffffffffu, lt, (lane + r) & 31);
+                const int of = __shfl_sync(0xffffffffu, lf, (lane + r) & 31);
+                rk += cand_better(ot, of, lt, lf) ? 1 : 0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, rk == beam - 1);  // all 32 lanes hold a candidate here
+            if (m) {
+                const int src = __ffs(m) - 1;
+                thr_t = __shfl_sync(0xffffffffu, lt, src);
+                thr_f = __shfl_sync(0xffffffffu, lf, src);
+            }
+        }
+        __syncwarp();  // vlist fully consumed -> reuse it for the survivor list
+        int ns = 0;
+#pragma unroll
+        for (int k = 0; k < MAXPL; ++k) {
+            if (k < kmax) {
+                const bool sv = my_slot[k] >= 0 && !cand_better(thr_t, thr_f, my_tot[k], my_first[k]);
+                const unsigned m = __ballot_sync(0xffffffffu, sv);
+                if (sv) vlist[ns + __popc(m & lt_mask)] = my_slot[k];
+                ns += __popc(m);
+            }
+        }
+        __syncwarp();
         const int nnew = nvalid < beam ? nvalid : beam;
-        for (int r = 0; r < nnew; ++r) {
-            double bt = neg_inf();
-            int bf = INT_MAX, bs = -1;
+        if (ns <= 32) {
+            const int c = lane < ns ? vlist[lane] : -1;
+            const double t_ = c >= 0 ? C.total[c] : neg_inf();
+            const int f_ = c >= 0 ? C.first[c] : INT_MAX;
+            int rk = 0;
 #pragma unroll
-            for (int k = 0; k < MAXPL; ++k)
-                if (k < kmax && my_slot[k] >= 0 && cand_better(my_tot[k], my_first[k], bt, bf)) {
-                    bt = my_tot[k];
-                    bf = my_first[k];
-                    bs = my_slot[k];
-                }
+            for (int r = 1; r < 32; ++r) {
+                const double ot = __shfl_sync(0xffffffffu, t_, (lane + r) & 31);
+                const int of = __shfl_sync(0xffffffffu, f_, (lane + r) & 31);
+                rk += cand_better(ot, of, t_, f_) ? 1 : 0;   // empty lanes carry (-inf, INT_MAX): never better
+            }
+            if (c >= 0 && rk < beam) rank_slot[rk] = c;
+        } else {
+            // rare fallback (many candidates tie with / exceed the bound): serial arg-max rounds over the survivors
+            const int kmax2 = (ns + 31) >> 5;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ot = __shfl_xor_sync(0xffffffffu, bt, o);
-                const int of = __shfl_xor_sync(0xffffffffu, bf, o);
-                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-                if (cand_better(ot, of, bt, bf)) {
-                    bt = ot;
-                    bf = of;
-                    bs = os;
+            for (int k = 0; k < MAXPL; ++k) {
+                my_slot[k] = -1;
+                if (k < kmax2 && lane + 32 * k < ns) {
+                    const int c = vlist[lane + 32 * k];
+                    my_slot[k] = c;
+                    my_tot[k] = C.total[c];
+                    my_first[k] = C.first[c];
                 }
             }
+            for (int r = 0; r < nnew; ++r) {
+                double bt = neg_inf();
+                int bf = INT_MAX, bs = -1;
 #pragma unroll
-            for (int k = 0; k < MAXPL; ++k)
-                if (k < kmax && my_slot[k] == bs) my_slot[k] = -1;  // taken
-            if (lane == 0) rank_slot[r] = bs;
+                for (int k = 0; k < MAXPL; ++k)
+                    if (k < kmax2 && my_slot[k] >= 0 && cand_better(my_tot[k], my_first[k], bt, bf)) {
+                        bt = my_tot[k];
+                        bf = my_first[k];
+                        bs = my_slot[k];
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                    const int of = __shfl_xor_sync(0xffffffffu, bf, o);
+                    const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                    if (cand_better(ot, of, bt, bf)) {
+                        bt = ot;
+                        bf = of;
+                        bs = os;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < MAXPL; ++k)
+                    if (k < kmax2 && my_slot[k] == bs) my_slot[k] = -1;
+                if (lane == 0) rank_slot[r] = bs;
+            }
         }
         __syncwarp();
 
