@@ -222,6 +222,11 @@ int wb_decoder_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t
 int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K,
                const float* bias_dev, int epi, float alpha, void* c_dev, int64_t ldc, int split3,
                wb_stream_t stream);
+/* fused feed-forward (d_model == 256): x += alpha * (act(a W1^T + b1) W2^T + b2); W1 [ff][d], W2 [d][ff] bf16;
+ * act 0 = SiLU (encoder), 1 = ReLU (decoder) */
+int wb_op_ffn(const void* a_dev, int64_t lda, const void* w1_dev, const float* b1_dev, const void* w2_dev,
+              const float* b2_dev, int M, int d, int ff, float alpha, int act, float* x_dev, int64_t ldx,
+              wb_stream_t stream);
 int wb_op_layernorm(const float* x_dev, int64_t ldx, int M, int d, const float* gamma_dev,
                     const float* beta_dev, float eps, void* out_bf16_dev, int64_t ld_bf16, int split3,
                     float* out_f32_dev, int64_t ld_f32, wb_stream_t stream);
@@ -245,6 +250,11 @@ int wb_op_dwconv(const void* g_dev, int64_t ldg, const int32_t* seq_start_dev,
 int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blank_id,
                           float blank_penalty, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
                           wb_stream_t stream);
+
+/* hardware probe (tools/tests only): one 3-D TMA tiled load with element strides; see csrc/probe.cu */
+int wb_probe_tma3d(const void* base_dev, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                   const uint32_t* estr, int c0, int c1, int c2, uint32_t expect_bytes, uint32_t copy_bytes,
+                   uint8_t* out_dev, int* status_dev, wb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -319,3 +319,26 @@ def test_fbank():
             assert (out_i[b, :m].cpu() - ref).abs().max().item() < 1e-3
             assert (out_f[b, :m].cpu() - ref).abs().max().item() < 1e-3
         assert (out_i[b, m:] == 0).all()
+
+
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("M,ff", [(300, 256), (1000, 2048), (128 * 150 + 77, 2048)])
+def test_ffn_fused(M, ff, act):
+    """Fused FFN (hidden activation stays on chip) == the two-GEMM formulation on identical bf16 operands."""
+    from wenet_b200 import ops
+    g = torch.Generator().manual_seed(M + ff)
+    d = 256
+    a = _rb(torch.randn(M, d, generator=g)).to(_dev())
+    w1 = _rb(torch.randn(ff, d, generator=g) / 16).to(_dev())
+    b1 = torch.randn(ff, generator=g).to(_dev())
+    w2 = _rb(torch.randn(d, ff, generator=g) / math.sqrt(ff)).to(_dev())
+    b2 = torch.randn(d, generator=g).to(_dev())
+    x0 = torch.randn(M, d, generator=g).to(_dev())
+    x = ops.ffn_fused(a, w1, b1, w2, b2, x0.clone(), alpha=0.5, act=act)
+    pre = a.float() @ w1.float().T + b1
+    h = (torch.nn.functional.silu(pre) if act == 0 else torch.relu(pre)).to(torch.bfloat16).float()
+    ref = x0 + 0.5 * (h @ w2.float().T + b2)
+    _close(x, ref, 1e-5, 3e-3)   # hidden rounding flips (2^-8 rel on one of ff terms) are the only difference
+    two = ops.gemm(ops.gemm(a, w1, b1, ops.EPI_BF16_SILU if act == 0 else ops.EPI_BF16_RELU), w2, b2, ops.EPI_RESID_F32, 0.5,
+                   out=x0.clone())
+    assert (x - two).abs().max().item() < 3e-3

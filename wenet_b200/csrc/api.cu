@@ -172,7 +172,10 @@ const char* wb_last_error(void) { return get_last_error(); }
 const char* wb_version(void) { return "wenet_b200 0.1 (sm_100a)"; }
 unsigned long long wb_launch_count(void) { return g_launch_count.load(); }
 
-void wb_set_sm_reserve(int n) { gemm_set_sm_reserve(n); }
+void wb_set_sm_reserve(int n) {
+    gemm_set_sm_reserve(n);
+    ffn_set_sm_reserve(n);
+}
 void wb_prof_enable(int on) { g_prof_on = on; }
 void wb_prof_reset(void) { wb::prof_reset(); }
 int wb_prof_num_tags(void) { return PT_COUNT; }
@@ -180,7 +183,7 @@ const char* wb_prof_tag_name(int tag) {
     static const char* names[PT_COUNT] = {"gemm_tcgen05", "attention", "layernorm", "dwconv_norm_silu", "conv1",
                                           "im2col", "relpos_kprep", "fbank", "logsoftmax_topk", "ctc_greedy",
                                           "ctc_prefix_beam", "embed_tokens", "gather_logprob", "rescore_combine",
-                                          "misc"};
+                                          "misc", "ffn_fused_tcgen05"};
     return (tag >= 0 && tag < PT_COUNT) ? names[tag] : "?";
 }
 int wb_prof_collect(double* ms, double* work, long long* launches) { return wb::prof_collect(ms, work, launches); }
@@ -308,6 +311,10 @@ int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, 
                float alpha, void* c_dev, int64_t ldc, int split3, wb_stream_t stream) {
     return gemm_bf16(a_dev, lda, nullptr, b_dev, M, N, K, bias_dev, epi, alpha, c_dev, ldc, split3,
                      (cudaStream_t)stream);
+}
+int wb_op_ffn(const void* a_dev, int64_t lda, const void* w1_dev, const float* b1_dev, const void* w2_dev,
+              const float* b2_dev, int M, int d, int ff, float alpha, int act, float* x_dev, int64_t ldx, wb_stream_t stream) {
+    return ffn_fused(a_dev, lda, w1_dev, b1_dev, w2_dev, b2_dev, M, d, ff, alpha, act, x_dev, ldx, (cudaStream_t)stream);
 }
 int wb_op_layernorm(const float* x_dev, int64_t ldx, int M, int d, const float* gamma_dev, const float* beta_dev,
                     float eps, void* out_bf16_dev, int64_t ld_bf16, int split3, float* out_f32_dev, int64_t ld_f32,

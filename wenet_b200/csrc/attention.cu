@@ -20,13 +20,13 @@
 // instruction issue in the softmax loops, so every per-element instruction counts (ncu: profiles/).
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace wb {
 
 namespace {
 
 constexpr int AT_M = 128;
-constexpr int AT_N = 128;
 constexpr int DK = 64;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB
 
@@ -48,10 +48,19 @@ struct AttnDev {
     int v_mode;
 };
 
-constexpr int AT_SMEM = 1024 /*align*/ + 3 * TILE_BYTES /*Q,K,V*/ + 2 * TILE_BYTES /*P*/ + TILE_BYTES /*ones (2 KB used)*/ +
-                        2 * 128 * 4 /*c*/ + 128 /*barriers*/;
+// KN = keys per tile.  128: 100 KB smem, 256 TMEM columns (S 128 | O 64 | L 16) -> 2 CTAs/SM.
+//                      64:  51 KB smem, 128 TMEM columns (S 64 | O 64)         -> 4 CTAs/SM (row sums by FADD).
+template <int KN>
+struct AttnCfg {
+    static constexpr int kKVBytes = KN * 128;
+    static constexpr int kPBytes = KN * 256;
+    static constexpr int kTmemCols = (KN == 128) ? 256 : 128;
+    static constexpr int kSmem = 1024 /*align*/ + TILE_BYTES /*Q*/ + 2 * kKVBytes /*K,V*/ + kPBytes + 2048 /*ones*/ +
+                                 2 * KN * 4 /*c*/ + 128 /*barriers*/;
+};
 
-__global__ void __launch_bounds__(128, 2)
+template <int KN>
+__global__ void __launch_bounds__(128, (KN == 128) ? 2 : 4)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, AttnDev P) {
     const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
@@ -64,12 +73,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
+    using Cfg = AttnCfg<KN>;
+    constexpr int AT_N = KN;
     uint8_t* sK = smem + TILE_BYTES;
-    uint8_t* sV = smem + 2 * TILE_BYTES;
-    uint8_t* sP = smem + 3 * TILE_BYTES;
-    uint8_t* sVt = smem + 5 * TILE_BYTES;
-    float* sC = reinterpret_cast<float*>(smem + 6 * TILE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES + 2 * 128 * 4);
+    uint8_t* sV = sK + Cfg::kKVBytes;
+    uint8_t* sP = sV + Cfg::kKVBytes;
+    uint8_t* sVt = sP + Cfg::kPBytes;   // 2 KB of bf16 ones
+    float* sC = reinterpret_cast<float*>(sVt + 2048);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sVt + 2048 + 2 * KN * 4);
     uint64_t* bar_q = bars + 0;
     uint64_t* bar_k = bars + 1;
     uint64_t* bar_v = bars + 2;
@@ -93,7 +104,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         fence_mbar_init();
     }
     if (warp == 0) {
-        tmem_alloc(tmem_holder, 256);
+        tmem_alloc(tmem_holder, Cfg::kTmemCols);
         tmem_relinquish();
     }
     // all-ones bf16 operand (layout-agnostic): P x ones accumulates the softmax normaliser in TMEM
@@ -104,9 +115,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_s = tmem_base;         // columns [0,128)
-    const uint32_t tmem_o = tmem_base + 128;   // columns [128,192)
-    const uint32_t tmem_l = tmem_base + 192;   // columns [192,208): row sums of P
+    const uint32_t tmem_s = tmem_base;             // columns [0,KN)
+    const uint32_t tmem_o = tmem_base + KN;        // columns [KN,KN+64)
+    const uint32_t tmem_l = tmem_base + KN + 64;   // KN == 128 only: columns [192,208), row sums of P
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
 
     // visible key range for this row, and the tile range for the CTA
@@ -139,7 +150,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (tid == 0 && kt0 < kt1) {
         mbar_expect_tx(bar_q, TILE_BYTES);
         tma_load_2d(sQ, &tmap_q, bar_q, P.q_col0 + h * DK, q_start + qt * AT_M);
-        mbar_expect_tx(bar_k, TILE_BYTES);
+        mbar_expect_tx(bar_k, Cfg::kKVBytes);
         tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + kt0 * AT_N);
     }
 
@@ -152,7 +163,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             float cv = 0.f;
             if (P.kbias != nullptr && j < k_len)
                 cv = P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e;
-            sC[(kt & 1) * 128 + tid] = cv;
+            if (tid < KN) sC[(kt & 1) * KN + tid] = cv;
         }
         if (tid == 0) {
             if (kt == kt0) mbar_wait(bar_q, 0);
@@ -173,17 +184,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (tid == 0) {
             // K smem is free again: prefetch next K tile (or the first tile again for pass 2, plus V)
             const int nk = (kt + 1 < kt1) ? kt + 1 : kt0;
-            mbar_expect_tx(bar_k, TILE_BYTES);
+            mbar_expect_tx(bar_k, Cfg::kKVBytes);
             tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + nk * AT_N);
             if (kt + 1 == kt1) {
-                mbar_expect_tx(bar_v, TILE_BYTES);
+                mbar_expect_tx(bar_v, Cfg::kKVBytes);
                 tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + kt0 * AT_N);
             }
         }
-        const float* cc = sC + (kt & 1) * 128;
+        const float* cc = sC + (kt & 1) * KN;
         const bool tile_full = (j0 >= full_lo) && (j0 + AT_N <= full_hi);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < KN / 32; ++c) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
             tmem_ld_wait();
@@ -211,6 +222,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const float m_fin = (m_run == -INFINITY) ? 0.f : m_run;
 
     // ------------------------------- pass 2: P, O -------------------------------
+    float l_acc = 0.f;
     for (int kt = kt0; kt < kt1; ++kt) {
         const int j0 = kt * AT_N;
         {
@@ -218,7 +230,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             float cv = 0.f;
             if (P.kbias != nullptr && j < k_len)
                 cv = P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e;
-            sC[(kt & 1) * 128 + tid] = cv;
+            if (tid < KN) sC[(kt & 1) * KN + tid] = cv;
         }
         if (tid == 0) {
             mbar_wait(bar_k, ph_k);
@@ -236,13 +248,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ph_s ^= 1;
         tc_fence_after();
         if (tid == 0 && kt + 1 < kt1) {
-            mbar_expect_tx(bar_k, TILE_BYTES);
+            mbar_expect_tx(bar_k, Cfg::kKVBytes);
             tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + (kt + 1) * AT_N);
         }
-        const float* cc = sC + (kt & 1) * 128;
+        const float* cc = sC + (kt & 1) * KN;
         const bool tile_full = (j0 >= full_lo) && (j0 + AT_N <= full_hi);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < KN / 32; ++c) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
             tmem_ld_wait();
@@ -257,6 +269,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const float p3 = fast_exp2(fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w) - m_fin);
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                     pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+                    if (KN != 128) l_acc += (p0 + p1) + (p2 + p3);
                 }
             } else {
 #pragma unroll
@@ -268,6 +281,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     if (j + 1 >= row_lo && j + 1 < row_hi)
                         p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[c * 32 + i + 1]) - m_fin);
                     pk[i >> 1] = pack_bf16x2(p0, p1);
+                    if (KN != 128) l_acc += p0 + p1;
                 }
             }
             // canonical K-major SWIZZLE_128B: row r, 16-byte chunk cidx -> chunk (cidx ^ (r & 7))
@@ -294,7 +308,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const uint32_t acc = (kt != kt0 || ks != 0) ? 1u : 0u;
                 umma_f16(tmem_o, adesc, make_smem_desc_sw128(va + ks * 2048, 1024, 1024), idesc_o, acc);
                 // row sums of the (bf16-rounded) probabilities: P x ones, 16 columns wide
-                umma_f16(tmem_l, adesc, make_smem_desc_sw128(oa, 1024, 1024), idesc_l, acc);  // same 2 KB of ones for every k-step
+                if (KN == 128)
+                    umma_f16(tmem_l, adesc, make_smem_desc_sw128(oa, 1024, 1024), idesc_l, acc);  // same 2 KB of ones
             }
             umma_commit(bar_pv);
         }
@@ -303,15 +318,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ph_pv ^= 1;
         tc_fence_after();
         if (tid == 0 && kt + 1 < kt1) {
-            mbar_expect_tx(bar_v, TILE_BYTES);
+            mbar_expect_tx(bar_v, Cfg::kKVBytes);
             tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + (kt + 1) * AT_N);
         }
     }
 
     // ------------------------------- epilogue -------------------------------
     if (kt0 < kt1) {
-        float l_run;
-        {
+        float l_run = l_acc;
+        if (KN == 128) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem_l + lane_sel, r);
             tmem_ld_wait();
@@ -356,7 +371,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -389,12 +404,18 @@ __global__ void relpos_kprep_kernel(const __nv_bfloat16* __restrict__ k, long lo
 
 int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     if (a.batch <= 0 || a.max_q_len <= 0) return WB_OK;
+    static int kn_cfg = 0;
+    if (kn_cfg == 0) {
+        const char* e = getenv("WB_ATTN_KN");
+        kn_cfg = (e && atoi(e) == 128) ? 128 : 64;
+    }
+    const int KN = kn_cfg;
     CUtensorMap tq, tk, tv;
     int rc;
     // the maps cover the whole row width so that column offsets select the head
     if ((rc = make_tmap_2d_bf16(&tq, a.q, (uint64_t)a.q_rows, (uint64_t)a.ldq, (uint64_t)a.ldq, 128, 64)) != WB_OK) return rc;
-    if ((rc = make_tmap_2d_bf16(&tk, a.k, (uint64_t)a.k_rows, (uint64_t)a.ldk, (uint64_t)a.ldk, 128, 64)) != WB_OK) return rc;
-    if ((rc = make_tmap_2d_bf16(&tv, a.v, (uint64_t)a.v_rows, (uint64_t)a.ldv, (uint64_t)a.ldv, 128, 64)) != WB_OK) return rc;
+    if ((rc = make_tmap_2d_bf16(&tk, a.k, (uint64_t)a.k_rows, (uint64_t)a.ldk, (uint64_t)a.ldk, KN, 64)) != WB_OK) return rc;
+    if ((rc = make_tmap_2d_bf16(&tv, a.v, (uint64_t)a.v_rows, (uint64_t)a.ldv, (uint64_t)a.ldv, KN, 64)) != WB_OK) return rc;
     AttnDev P;
     P.kbias = a.kbias;
     P.ld_kbias = a.ld_kbias;
@@ -417,12 +438,18 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     WB_REQUIRE((a.ldo % 8) == 0 && (a.out_col0 % 8) == 0, WB_ERR_BAD_ARG, "attention: output pitch/offset must be %%8");
     static bool attr_set = false;
     if (!attr_set) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           AttnCfg<128>::kSmem));
+        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           AttnCfg<64>::kSmem));
         attr_set = true;
     }
     dim3 grid(ceil_div(a.max_q_len, AT_M), a.heads, a.batch);
     ProfScope _ps(PT_ATTENTION, stream, 0.0);
-    attention_kernel<<<grid, 128, AT_SMEM, stream>>>(tq, tk, tv, P);
+    if (KN == 128)
+        attention_kernel<128><<<grid, 128, AttnCfg<128>::kSmem, stream>>>(tq, tk, tv, P);
+    else
+        attention_kernel<64><<<grid, 128, AttnCfg<64>::kSmem, stream>>>(tq, tk, tv, P);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

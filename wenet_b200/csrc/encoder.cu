@@ -6,6 +6,7 @@
 //   x += 1/2 FFN_m(LN(x)); x += MHA_relpos(LN(x)); x += Conv(LN(x)); x += 1/2 FFN(LN(x)); x = LN_final(x)
 #include "model.h"
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace wb {
@@ -95,7 +96,18 @@ struct EncPlan {
     // workspace offsets
     size_t o_meta = 0, o_out1 = 0, o_a2 = 0, o_out2 = 0, o_x = 0, total = 0;
     size_t meta_bytes = 0;
+    // conv2 as an implicit GEMM (gemm.cu conv mode): one int4 per 6-frame x 19-bin output tile
+    bool implicit_conv = false;
+    int conv_tiles = 0;
+    size_t o_tiles = 0;
 };
+
+constexpr int kConvTileT = 6;   // output frames per conv2 tile (6 x F2 = 114 rows of the 128-row MMA tile)
+
+bool implicit_conv_enabled(const Model* m) {
+    static const bool off = getenv("WB_NO_IMPLICIT_CONV") != nullptr;
+    return !off && m->F1 == 39 && m->F2 == 19 && m->cfg.d_model % 256 == 0;
+}
 
 void make_plan(const Model* m, int batch, const int32_t* feat_lens, EncPlan* P) {
     P->batch = batch;
@@ -119,17 +131,23 @@ void make_plan(const Model* m, int batch, const int32_t* feat_lens, EncPlan* P) 
     }
     P->M = M;
     P->rows1 = r1;
+    P->implicit_conv = implicit_conv_enabled(m);
+    P->conv_tiles = 0;
+    if (P->implicit_conv)
+        for (int b = 0; b < batch; ++b) P->conv_tiles += (P->tp[b] + kConvTileT - 1) / kConvTileT;
     const int d = m->cfg.d_model;
     // meta: t1n[B] int, tp[B] int, seq_start[B] int, off1[B] ll, off2[B] ll, row_pos[M] int
     P->meta_bytes = align_up((size_t)batch * (3 * 4 + 2 * 8) + 64) + align_up((size_t)M * 4 + 64);
     size_t o = 0;
     P->o_meta = o;
     o += P->meta_bytes;
+    P->o_tiles = o;
+    o += align_up((size_t)P->conv_tiles * 16 + 16);
     P->o_out1 = o;
     o += align_up((size_t)r1 * d * 2);
     P->o_a2 = o;
     // the im2col matrix is the largest buffer; all per-layer activations alias it afterwards
-    const size_t a2_bytes = (size_t)M * m->F2 * 9 * d * 2;
+    const size_t a2_bytes = P->implicit_conv ? 0 : (size_t)M * m->F2 * 9 * d * 2;
     const size_t layer_bytes = align_up((size_t)M * d * 2) * 4 /*a, ctx, g, g2*/ +
                                align_up((size_t)M * m->cfg.ffn_dim * 2) + align_up((size_t)M * 3 * d * 2) +
                                align_up((size_t)M * d * 2) /*kp*/ + align_up((size_t)M * m->cfg.heads * 4);
@@ -242,9 +260,29 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
     // ---- Conv2dSubsampling4 (subsampling.py:203-228) ----
     RC(subsample_conv1(feats_dev, feats_stride_b, c.input_dim, d_t1n, d_off1, batch, P.max_t1, m->cmvn_mean,
                        m->cmvn_istd, m->conv1_w, m->conv1_b, d, out1, 0, st));
-    RC(subsample_im2col(out1, d_off1, d_tp, d_off2, batch, P.max_tp, m->F1, m->F2, d, a2, 0, st));
-    RC(gemm_bf16(a2, 9 * d, &m->conv2.tmap, m->conv2.w, (int)(M * m->F2), d, 9 * d, m->conv2.b, EPI_BF16_RELU, 1.0f,
-                 out2, d, 0, st));
+    if (P.implicit_conv) {
+        // tile table: (t1 row of tap kh = 0, first output row, valid rows) per 6-frame tile, never crossing utterances
+        std::vector<int> tiles((size_t)P.conv_tiles * 4);
+        size_t ti = 0;
+        for (int b = 0; b < batch; ++b) {
+            const int t1_base = (int)(P.off1[b] / m->F1);
+            for (int t0 = 0; t0 < P.tp[b]; t0 += kConvTileT, ++ti) {
+                const int nt = P.tp[b] - t0 < kConvTileT ? P.tp[b] - t0 : kConvTileT;
+                tiles[4 * ti + 0] = t1_base + 2 * t0;
+                tiles[4 * ti + 1] = (int)(P.off2[b] + (long long)t0 * m->F2);
+                tiles[4 * ti + 2] = nt * m->F2;
+                tiles[4 * ti + 3] = 0;
+            }
+        }
+        WB_CHECK_CUDA(cudaMemcpyAsync(ws + P.o_tiles, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, st));
+        WB_CHECK_CUDA(cudaStreamSynchronize(st));
+        RC(gemm_conv2_implicit(out1, P.rows1 / m->F1, m->F1, d, &m->conv2.tmap, m->conv2.b, ws + P.o_tiles, P.conv_tiles,
+                               M * m->F2, out2, st));
+    } else {
+        RC(subsample_im2col(out1, d_off1, d_tp, d_off2, batch, P.max_tp, m->F1, m->F2, d, a2, 0, st));
+        RC(gemm_bf16(a2, 9 * d, &m->conv2.tmap, m->conv2.w, (int)(M * m->F2), d, 9 * d, m->conv2.b, EPI_BF16_RELU, 1.0f,
+                     out2, d, 0, st));
+    }
     // Linear(F2*d -> d), x * sqrt(d)  (embedding.py:141-147: RelPositionalEncoding scales, no add)
     RC(gemm_bf16(out2, (long long)m->F2 * d, &m->embed_out.tmap, m->embed_out.w, (int)M, d, m->F2 * d, m->embed_out.b,
                  EPI_F32, sqrtf((float)d), x, d, 0, st));
@@ -272,12 +310,20 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
     const int chunk = decoding_chunk_size > 0 ? decoding_chunk_size : 0;
     const float att_scale = 1.0f / sqrtf(64.0f);
     const int Mi = (int)M;
+    // fused FFN (h stays on chip, ffn.cu) is opt-in (WB_FFN_FUSION=1): it is bound by shared-memory bandwidth (every
+    // 128-row tile streams the full 2 MB of W1/W2 through smem) and measures slower than the two pipelined GEMMs
+    static const bool ffn_fusion_on = (getenv("WB_FFN_FUSION") != nullptr);
+    const bool fuse_ffn = ffn_fusion_on && ffn_fused_supported(d, ff) && Mi >= 1024;
     for (int li = 0; li < c.enc_layers; ++li) {
         const EncLayer& L = m->layers[li];
         // macaron feed-forward (encoder_layer.py:221-228)
         RC(layernorm_rows(x, d, Mi, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.ffm1.tmap, L.ffm1.w, Mi, ff, d, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
-        RC(gemm_bf16(h, ff, &L.ffm2.tmap, L.ffm2.w, Mi, d, ff, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        if (fuse_ffn) {
+            RC(ffn_fused(a, d, L.ffm1.w, L.ffm1.b, L.ffm2.w, L.ffm2.b, Mi, d, ff, 0.5f, 0, x, d, st));
+        } else {
+            RC(gemm_bf16(a, d, &L.ffm1.tmap, L.ffm1.w, Mi, ff, d, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
+            RC(gemm_bf16(h, ff, &L.ffm2.tmap, L.ffm2.w, Mi, d, ff, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        }
         // rel-pos multi-headed self-attention (:231-238)
         RC(layernorm_rows(x, d, Mi, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, Mi, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
@@ -312,8 +358,12 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
         RC(gemm_bf16(g2, d, &L.pw2.tmap, L.pw2.w, Mi, d, d, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // feed-forward (:254-259) and norm_final (:262-263)
         RC(layernorm_rows(x, d, Mi, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, Mi, ff, d, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
-        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, Mi, d, ff, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        if (fuse_ffn) {
+            RC(ffn_fused(a, d, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, Mi, d, ff, 0.5f, 0, x, d, st));
+        } else {
+            RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, Mi, ff, d, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
+            RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, Mi, d, ff, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        }
         RC(layernorm_rows(x, d, Mi, d, L.n_final.g, L.n_final.b, c.ln_eps, nullptr, 0, 0, x, d, st));
         if (layer_dump_dev)
             WB_CHECK_CUDA(cudaMemcpyAsync(layer_dump_dev + (size_t)(li + 1) * M * d, x, (size_t)M * d * 4,

@@ -58,13 +58,21 @@ struct GemmParams {
     int split3;
     int use_tma_out;  // epilogue through shared memory + TMA store / reduce-add (all non-split3 cases)
     int num_m_tiles, num_n_tiles;
+    // conv mode (Conv2d 3x3 stride 2 as an implicit GEMM): the A tile of k-block (kh, kw, c-block) is one 3-D TMA box
+    // {64 channels, 19 frequency taps (element stride 2), 6 time taps (element stride 2)} of the channels-last conv1
+    // output = 114 rows (t2, f2) of the im2col matrix, which is never materialised.
+    int conv;
+    int cblocks;            // d / 64
+    const int4* tile_tab;   // per m-tile: .x t coordinate of tap kh = 0, .y first output row, .z valid rows (<= 114)
 };
+constexpr int kConvRows = 114;   // 6 x 19
 
 template <int BN, bool BRES>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_c, GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
+                    GemmParams p) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -92,6 +100,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if (p.use_tma_out) tma_prefetch_desc(&tmap_c);
+        if (p.conv) tma_prefetch_desc(&tmap_c2);
         for (int s = 0; s < kRing; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -141,11 +150,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         tma_load_2d(smem_b + kb * Cfg::kBBytes, &tmap_b, b_full, kb * BK, n_tile * BN);
                     cur_n = n_tile;
                 }
+                int conv_t = 0;
+                if (!BRES && p.conv) conv_t = __ldg(&p.tile_tab[m_tile]).x;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], BRES ? Cfg::kABytes : Cfg::kStageBytes);
-                    tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK,
-                                m_tile * BM);
+                    if (!BRES && p.conv) {
+                        const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                        const int kh = tap / 3, kw = tap - 3 * kh;
+                        mbar_expect_tx(&full_bar[stage], kConvRows * 128 + Cfg::kBBytes);
+                        tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], cb * BK, kw, conv_t + kh);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], BRES ? Cfg::kABytes : Cfg::kStageBytes);
+                        tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK,
+                                    m_tile * BM);
+                    }
                     if (!BRES)
                         tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK,
                                     n_tile * BN);
@@ -216,8 +234,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         bool need_wait = false;
         for (int t = t_begin; t < t_end; t += t_step) {
             WB_TILE_COORDS(t)
-            const long long row = (long long)m_tile * BM + q * 32 + lane;
-            const bool row_ok = row < p.M;
+            long long row_base = (long long)m_tile * BM;
+            int n_in = 32;   // valid rows in this warp's 32-row slice
+            if (!BRES && p.conv) {
+                const int4 tt = __ldg(&p.tile_tab[m_tile]);
+                row_base = tt.y;
+                n_in = min(32, max(0, tt.z - q * 32));
+            }
+            const long long row = row_base + q * 32 + lane;
+            const bool row_ok = (!BRES && p.conv) ? (lane < n_in) : (row < p.M);
+            // conv tiles hold 114 rows: slices of 32 and 18 rows leave through TMA boxes of that height, the ragged
+            // last tile of an utterance falls back to guarded register stores
+            const bool warp_tma = p.use_tma_out && (n_in == 32 || n_in == 18);
+            const CUtensorMap* cmap = (n_in == 18) ? &tmap_c2 : &tmap_c;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -249,7 +278,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                 }
-                if (p.use_tma_out) {
+                if (warp_tma) {
                     // ---- staged epilogue: registers -> swizzled smem (row = lane, 128 B) -> TMA ----
                     // rows >= M and columns >= N are clipped by the tensor map, so no guards are needed.
                     uint8_t* sbuf = smem_out + (warp - 2) * 4096 + lane * 128;
@@ -272,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     } else if (p.epi == EPI_GLU_BF16) {
                         float g[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_t(v[16 + i]);
+                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_f(v[16 + i]);
 #pragma unroll
                         for (int u = 0; u < 2; ++u)
                             *reinterpret_cast<uint4*>(sbuf + ((((c & 3) * 2 + u) ^ sw) << 4)) =
@@ -283,7 +312,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     } else {
                         if (p.epi == EPI_BF16_SILU) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = silu_t(v[i]);
+                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
                         } else if (p.epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -303,11 +332,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         __syncwarp();
                         if (lane == 0) {
                             const void* src = smem_out + (warp - 2) * 4096;
-                            const int row0 = m_tile * BM + q * 32;
+                            const int row0 = (int)row_base + q * 32;
                             if (p.epi == EPI_RESID_F32)
-                                tma_reduce_add_2d(&tmap_c, src, out_col, row0);
+                                tma_reduce_add_2d(cmap, src, out_col, row0);
                             else
-                                tma_store_2d(&tmap_c, src, out_col, row0);
+                                tma_store_2d(cmap, src, out_col, row0);
                             tma_store_commit();
                         }
                         need_wait = true;
@@ -322,7 +351,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     case EPI_BF16_RELU: {
                         if (p.epi == EPI_BF16_SILU) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = silu_t(v[i]);
+                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
                         } else if (p.epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -374,7 +403,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + (n0 >> 1);
                         float g[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_t(v[16 + i]);
+                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_f(v[16 + i]);
                         uint32_t pk[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
@@ -449,8 +478,8 @@ int g_num_sms = 0;
 int g_sm_reserve = 0;  // SMs left free for concurrently running latency-bound kernels on other streams
 
 template <int BN, bool BRES>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
-                cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
+                const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -467,7 +496,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     const int usable = (g_num_sms - g_sm_reserve) > 1 ? (g_num_sms - g_sm_reserve) : 1;
     const int grid = tiles < usable ? tiles : usable;
     ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
-    gemm_tcgen05_kernel<BN, BRES><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
+    gemm_tcgen05_kernel<BN, BRES><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
@@ -530,13 +559,52 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
         rc = make_tmap_2d(&tc, out, eb, (uint64_t)M, (uint64_t)out_cols, (uint64_t)ldc, 32, f32_out ? 32 : 64);
         if (rc != WB_OK) return rc;
     }
+    p.conv = 0;
+    p.cblocks = 0;
+    p.tile_tab = nullptr;
     const int num_kb = ceil_div(K, BK);
     if (bn == 256) {
-        if (num_kb <= GemmCfg<256>::kResMaxKB) return launch_gemm<256, true>(ta, *tb, tc, p, stream);
-        return launch_gemm<256, false>(ta, *tb, tc, p, stream);
+        if (num_kb <= GemmCfg<256>::kResMaxKB) return launch_gemm<256, true>(ta, *tb, tc, tc, p, stream);
+        return launch_gemm<256, false>(ta, *tb, tc, tc, p, stream);
     }
-    if (num_kb <= GemmCfg<128>::kResMaxKB) return launch_gemm<128, true>(ta, *tb, tc, p, stream);
-    return launch_gemm<128, false>(ta, *tb, tc, p, stream);
+    if (num_kb <= GemmCfg<128>::kResMaxKB) return launch_gemm<128, true>(ta, *tb, tc, tc, p, stream);
+    return launch_gemm<128, false>(ta, *tb, tc, tc, p, stream);
+}
+
+// Conv2d(d -> d, 3x3, stride 2) + bias + ReLU over the channels-last conv1 output, as an implicit GEMM:
+//   out2[(tile row), n] = relu(bias[n] + sum_{kh,kw,c} out1[t1 = 2 t2 + kh][f1 = 2 f2 + kw][c] * W[n][(kh,kw,c)])
+// out1: [T1_total][F1][d] bf16 (utterances stacked along t), out2: [rows_out][d] bf16, tile_tab_dev: one int4 per
+// 114-row tile (see GemmParams).
+int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, const CUtensorMap* tmap_w, const float* bias,
+                        const void* tile_tab_dev, int num_tiles, long long rows_out, void* out2, cudaStream_t stream) {
+    if (num_tiles <= 0) return WB_OK;
+    WB_REQUIRE(d % 256 == 0 && F1 == 39, WB_ERR_UNSUPPORTED, "conv2 implicit GEMM: d=%d F1=%d unsupported", d, F1);
+    CUtensorMap ta, tc, tc18;
+    const uint64_t dims[3] = {(uint64_t)d, (uint64_t)F1, (uint64_t)t1_total};
+    const uint64_t strides[2] = {(uint64_t)d * 2, (uint64_t)F1 * d * 2};
+    const uint32_t box[3] = {64, 37, 11};     // traversal extents: ceil(37/2) = 19 taps in f, ceil(11/2) = 6 in t
+    const uint32_t estr[3] = {1, 2, 2};
+    int rc;
+    if ((rc = make_tmap_3d_bf16(&ta, out1, dims, strides, box, estr)) != WB_OK) return rc;
+    if ((rc = make_tmap_2d(&tc, out2, 2, (uint64_t)rows_out, (uint64_t)d, (uint64_t)d, 32, 64)) != WB_OK) return rc;
+    if ((rc = make_tmap_2d(&tc18, out2, 2, (uint64_t)rows_out, (uint64_t)d, (uint64_t)d, 18, 64)) != WB_OK) return rc;
+    GemmParams p;
+    p.M = (int)rows_out;
+    p.N = d;
+    p.K = 9 * d;
+    p.epi = EPI_BF16_RELU;
+    p.alpha = 1.0f;
+    p.bias = bias;
+    p.out = out2;
+    p.ldc = d;
+    p.split3 = 0;
+    p.use_tma_out = 1;
+    p.num_m_tiles = num_tiles;
+    p.num_n_tiles = d / 256;
+    p.conv = 1;
+    p.cblocks = d / 64;
+    p.tile_tab = reinterpret_cast<const int4*>(tile_tab_dev);
+    return launch_gemm<256, false>(ta, *tmap_w, tc, tc18, p, stream);
 }
 
 }  // namespace wb

@@ -28,6 +28,17 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
               int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
               cudaStream_t stream);
 
+// Conv2d(d->d, 3x3, s2) + ReLU as an implicit GEMM whose A tiles are fetched by 3-D strided TMA boxes (no im2col buffer)
+int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, const CUtensorMap* tmap_w, const float* bias,
+                        const void* tile_tab_dev /*int4 per tile*/, int num_tiles, long long rows_out, void* out2,
+                        cudaStream_t stream);
+
+// ---- fused feed-forward (ffn.cu): x += alpha * (SiLU(a W1^T + b1) W2^T + b2), d_model == 256 only ------------
+bool ffn_fused_supported(int d, int ff);
+void ffn_set_sm_reserve(int n);
+int ffn_fused(const void* a_bf16, long long lda, const void* w1, const float* b1, const void* w2, const float* b2, int M,
+              int d, int ff, float alpha, int act /*0 SiLU, 1 ReLU*/, float* x, long long ldx, cudaStream_t stream);
+
 // ---- fbank (fbank.cu) ------------------------------------------------------------------------
 struct FbankPlan {  // device-resident constants, built once by fbank_plan_create
     float* window;      // [frame_len]

@@ -108,8 +108,13 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
         RC(gemm_bf16(ctx, d, &L.ca_out.tmap, L.ca_out.w, R, d, d, L.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // feed-forward (ReLU), decoder_layer.py:141-147
         RC(layernorm_rows(x, d, R, d, L.n3.g, L.n3.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, R, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
-        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, R, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        static const bool ffn_fusion_on = (getenv("WB_FFN_FUSION") != nullptr);   // see encoder.cu
+        if (ffn_fusion_on && ffn_fused_supported(d, ff) && R >= 1024) {
+            RC(ffn_fused(a, d, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, R, d, ff, 1.0f, 1, x, d, st));
+        } else {
+            RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, R, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
+            RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, R, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        }
     }
     RC(layernorm_rows(x, d, R, d, D.after.g, D.after.b, c.ln_eps, a, d, 0, nullptr, 0, st));
     RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, ldl, 0, st));

@@ -122,6 +122,27 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
     return WB_OK;
 }
 
+// 3-D bf16 tensor [d2][d1][d0] (d0 innermost, contiguous) with element (traversal) strides: used for the
+// TMA-side im2col of Conv2d(3x3, stride 2): box {64 channels, 19 frequency taps (stride 2), 6 time taps (stride 2)}
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
+                      const uint32_t box[3], const uint32_t estr[3]) {
+    PFN_encodeTiled fn = get_encode_fn();
+    WB_REQUIRE(fn != nullptr, WB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+    WB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && strides_bytes[0] % 16 == 0 && strides_bytes[1] % 16 == 0,
+               WB_ERR_BAD_ARG, "tmap3d: alignment");
+    cuuint64_t gdim[3] = {dims[0], dims[1], dims[2]};
+    cuuint64_t gstride[2] = {strides_bytes[0], strides_bytes[1]};
+    cuuint32_t b[3] = {box[0], box[1], box[2]};
+    cuuint32_t e[3] = {estr[0], estr[1], estr[2]};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, b, e,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WB_REQUIRE(r == CUDA_SUCCESS, WB_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d): dims %llu %llu %llu box %u %u %u",
+               (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1],
+               box[2]);
+    return WB_OK;
+}
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols) {
     return make_tmap_2d(out, base, 2, rows, cols, ld_elems, box_rows, box_cols);

@@ -37,6 +37,16 @@ def gemm(a, b, bias=None, epi=EPI_BF16, alpha=1.0, out=None, split3=False):
     return out
 
 
+def ffn_fused(a, w1, b1, w2, b2, x, alpha=0.5, act=0):
+    """x += alpha * (silu(a @ w1.T + b1) @ w2.T + b2) in one kernel (d_model == 256)."""
+    _need_cuda(a, w1, w2, x)
+    M, d = a.shape
+    ff = w1.shape[0]
+    check(_lib.load().wb_op_ffn(ptr(a), a.stride(0), ptr(w1), ptr(b1), ptr(w2), ptr(b2), M, d, ff, float(alpha), int(act),
+                                ptr(x), x.stride(0), cur_stream()), "wb_op_ffn")
+    return x
+
+
 def layernorm(x, gamma, beta, eps=1e-5, want_bf16=True, want_f32=False, split3=False):
     _need_cuda(x, gamma, beta)
     M, d = x.shape

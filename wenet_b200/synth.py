@@ -213,4 +213,8 @@ def recipe(name: str) -> dict:
         return dict(base, output_dim=37, encoder_conf=enc(128, 2, 256, 2, 15, False, "batch_norm", False),
                     decoder="transformer", decoder_conf=dec(2, 256, 2),
                     model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False))
+    if name == "tiny512":           # test-sized wide variant (2L/512d/8h, K=15 causal) — the WenetSpeech geometry
+        return dict(base, output_dim=61, encoder_conf=enc(512, 8, 1024, 2, 15, True, "layer_norm", True),
+                    decoder="bitransformer", decoder_conf=dec(8, 1024, 1, 1),
+                    model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False, reverse_weight=0.3))
     raise KeyError(name)
