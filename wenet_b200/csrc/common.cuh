@@ -104,6 +104,41 @@ __device__ __forceinline__ float fast_rcp(float x) {
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return fast_rcp(1.0f + fast_exp2(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+// Four sigmoids for five MUFU ops instead of eight: with y_i = 1 + 2^(-x_i log2 e), one reciprocal of the product
+// y0 y1 y2 y3 gives every 1/y_i by multiplications (1/y0 = r y2 y3 y1 ...).  y_i is clamped to 2^30 + 1 so the
+// product stays below 2^127; the clamp changes sigmoid(x) only for x < -20.8, by less than 1e-9 absolute.  The
+// SiLU / GLU GEMM epilogues are bound by the 16-lane MUFU pipe (ncu stall_mio), not by the FMA pipe that takes
+// the extra multiplications.  Relative error ~3 ulp (one rcp.approx + three roundings).
+__device__ __forceinline__ void sigmoid4(const float x0, const float x1, const float x2, const float x3, float& s0,
+                                         float& s1, float& s2, float& s3) {
+    constexpr float kNegLog2e = -1.4426950408889634f;
+    constexpr float kCap = 1073741824.0f;   // 2^30
+    const float y0 = 1.0f + fminf(fast_exp2(kNegLog2e * x0), kCap);
+    const float y1 = 1.0f + fminf(fast_exp2(kNegLog2e * x1), kCap);
+    const float y2 = 1.0f + fminf(fast_exp2(kNegLog2e * x2), kCap);
+    const float y3 = 1.0f + fminf(fast_exp2(kNegLog2e * x3), kCap);
+    const float p01 = y0 * y1, p23 = y2 * y3;
+    const float r = fast_rcp(p01 * p23);
+    const float r01 = r * p23, r23 = r * p01;   // 1 / (y0 y1), 1 / (y2 y3)
+    s0 = r01 * y1;
+    s1 = r01 * y0;
+    s2 = r23 * y3;
+    s3 = r23 * y2;
+}
+// in-place SiLU over a register array whose length is a multiple of 4
+template <int N>
+__device__ __forceinline__ void silu_inplace(float (&v)[N]) {
+    static_assert(N % 4 == 0, "silu_inplace: N % 4");
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+        float s0, s1, s2, s3;
+        sigmoid4(v[i], v[i + 1], v[i + 2], v[i + 3], s0, s1, s2, s3);
+        v[i] *= s0;
+        v[i + 1] *= s1;
+        v[i + 2] *= s2;
+        v[i + 3] *= s3;
+    }
+}
 // One-MUFU variants: sigmoid(x) = 0.5 + 0.5 tanh(x/2) with tanh.approx.f32 (max rel. error 2^-11, i.e. <= 2.5e-4
 // absolute on the sigmoid).  The SiLU / GLU GEMM epilogues are MUFU-throughput bound (16 ops/clk/SM, ncu
 // stall_mio) and this form makes FFN1 21 % faster (110 -> 87 us), but the systematic 2.5e-4 error flipped a

@@ -48,8 +48,6 @@ struct FfnParams {
     int num_tiles;
 };
 
-__device__ __forceinline__ float ffn_act(float v, int act) { return act == 0 ? silu_f(v) : fmaxf(v, 0.f); }
-
 __global__ void __launch_bounds__(352, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x, FfnParams p) {
@@ -222,16 +220,23 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const float* bp = p.b1 + c * FF_C;
                 uint32_t pk[32];
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
-                    pk[i >> 1] = pack_bf16x2(ffn_act(__uint_as_float(r0[i]) + b4.x, act), ffn_act(__uint_as_float(r0[i + 1]) + b4.y, act));
-                    pk[(i >> 1) + 1] = pack_bf16x2(ffn_act(__uint_as_float(r0[i + 2]) + b4.z, act), ffn_act(__uint_as_float(r0[i + 3]) + b4.w, act));
-                }
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t* rr = hh == 0 ? r0 : r1;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + 32 + i));
-                    pk[16 + (i >> 1)] = pack_bf16x2(ffn_act(__uint_as_float(r1[i]) + b4.x, act), ffn_act(__uint_as_float(r1[i + 1]) + b4.y, act));
-                    pk[16 + (i >> 1) + 1] = pack_bf16x2(ffn_act(__uint_as_float(r1[i + 2]) + b4.z, act), ffn_act(__uint_as_float(r1[i + 3]) + b4.w, act));
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + hh * 32 + i));
+                        float t0 = __uint_as_float(rr[i]) + b4.x, t1 = __uint_as_float(rr[i + 1]) + b4.y;
+                        float t2 = __uint_as_float(rr[i + 2]) + b4.z, t3 = __uint_as_float(rr[i + 3]) + b4.w;
+                        if (act == 0) {
+                            float s0, s1, s2, s3;
+                            sigmoid4(t0, t1, t2, t3, s0, s1, s2, s3);
+                            t0 *= s0; t1 *= s1; t2 *= s2; t3 *= s3;
+                        } else {
+                            t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f);
+                        }
+                        pk[hh * 16 + (i >> 1)] = pack_bf16x2(t0, t1);
+                        pk[hh * 16 + (i >> 1) + 1] = pack_bf16x2(t2, t3);
+                    }
                 }
                 mbar_wait(&ha_empty[s], ph ^ 1);   // MMA2 of chunk g-2 has finished reading this buffer
                 uint8_t* hrow = smem + SM_H + s * 16384 + row_in_tile * 128;

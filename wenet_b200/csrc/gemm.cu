@@ -301,7 +301,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     } else if (p.epi == EPI_GLU_BF16) {
                         float g[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_f(v[16 + i]);
+                        for (int i = 0; i < 16; i += 4) {
+                            sigmoid4(v[16 + i], v[17 + i], v[18 + i], v[19 + i], g[i], g[i + 1], g[i + 2], g[i + 3]);
+                            g[i] *= v[i];
+                            g[i + 1] *= v[i + 1];
+                            g[i + 2] *= v[i + 2];
+                            g[i + 3] *= v[i + 3];
+                        }
 #pragma unroll
                         for (int u = 0; u < 2; ++u)
                             *reinterpret_cast<uint4*>(sbuf + ((((c & 3) * 2 + u) ^ sw) << 4)) =
@@ -311,8 +317,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         out_col = (n_tile * BN + (c & ~3) * 32) >> 1;
                     } else {
                         if (p.epi == EPI_BF16_SILU) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                            silu_inplace(v);
                         } else if (p.epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -350,8 +355,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     case EPI_BF16_SILU:
                     case EPI_BF16_RELU: {
                         if (p.epi == EPI_BF16_SILU) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                            silu_inplace(v);
                         } else if (p.epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -403,7 +407,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + (n0 >> 1);
                         float g[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) g[i] = v[i] * sigmoid_f(v[16 + i]);
+                        for (int i = 0; i < 16; i += 4) {
+                            sigmoid4(v[16 + i], v[17 + i], v[18 + i], v[19 + i], g[i], g[i + 1], g[i + 2], g[i + 3]);
+                            g[i] *= v[i];
+                            g[i + 1] *= v[i + 1];
+                            g[i + 2] *= v[i + 2];
+                            g[i + 3] *= v[i + 3];
+                        }
                         uint32_t pk[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
