@@ -290,6 +290,8 @@ def main():
     # kernel of one batch behind the GEMMs of the next.  A step is still one full pass over one batch.
     import threading
     n_slots = max(1, args.inflight)
+    if n_slots > 1:
+        sys.setswitchinterval(5e-4)   # the slot threads hand the GIL over between (GIL-releasing) C-ABI calls
     lib.wb_set_sm_reserve(8 if n_slots > 1 else 0)   # room for the other batch's search kernel (batch/8 CTAs)
     slot_models = [model] + [model.clone_shared() for _ in range(n_slots - 1)]
     slot_streams = [torch.cuda.Stream(device=dev) for _ in range(n_slots)]

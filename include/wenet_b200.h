@@ -203,6 +203,19 @@ int wb_attention_rescoring(const wb_model* m, const void* enc_out_bf16_dev, int6
                            float reverse_weight, float* tok_logp_l2r_dev, float* tok_logp_r2l_dev,
                            float* hyp_score_dev, int32_t* best_dev, void* workspace_dev,
                            size_t workspace_bytes, wb_stream_t stream);
+/* Same, with the hypothesis tokens still ON THE DEVICE: hyp h reads hyp_len[h] tokens at
+ * hyp_tokens_dev[hyp_tok0[h] ...] (e.g. the [batch][beam][max_len] token buffer written by
+ * wb_ctc_prefix_beam_search with hyp_tok0 = (b*beam + rank)*max_len).  Only the per-hypothesis lengths and
+ * CTC scores cross to the host between the two stages; the reference moves every n-best list to Python
+ * and back (search.py:236-248 -> :395-412). */
+int wb_attention_rescoring_dev(const wb_model* m, const void* enc_out_bf16_dev, int64_t enc_rows,
+                               const int32_t* seq_start_host, const int32_t* seq_len_host, int batch,
+                               int n_hyp, const int32_t* hyp_utt_host, const int32_t* hyp_len_host,
+                               const int32_t* hyp_tok0_host, const int32_t* hyp_tokens_dev,
+                               const double* ctc_score_host, int sos, int eos, float ctc_weight,
+                               float reverse_weight, float* tok_logp_l2r_dev, float* tok_logp_r2l_dev,
+                               float* hyp_score_dev, int32_t* best_dev, void* workspace_dev,
+                               size_t workspace_bytes, wb_stream_t stream);
 /* full decoder posteriors for API parity with forward_attention_decoder: logp [R][ldl] (l2r) and
  * r_logp [R][ldl] (r2l, may be NULL) */
 int wb_decoder_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t enc_rows,

@@ -276,3 +276,41 @@ def test_conv2_implicit_gemm_ragged_tiles():
         mx, mn = err(out[b, :n].cpu(), o32[b, :n])
         mxo, mno = err(oq[b, :n], o32[b, :n])
         assert mx < 5.9e-2 and mn < 2.0 * mno + 1e-3, (b, n, mx, mn, mxo, mno)
+
+
+def test_rescoring_host_and_device_token_entry_points_agree(setup):
+    """wb_attention_rescoring (hypothesis tokens in host memory, the reference's data flow) and
+    wb_attention_rescoring_dev (tokens read from the beam search's device buffer, what decode() uses) run the same
+    decoder on the same rows -> identical scores and choices."""
+    from wenet_b200._lib import check, cur_stream, load, ptr
+    name, cfg, sd, model, feats, lens, g = setup
+    beam = int(g["beam"])
+    rw = cfg["model_conf"].get("reverse_weight", 0.0)
+    res = model.decode(["ctc_prefix_beam_search", "attention_rescoring"], feats, lens.cuda(), beam_size=beam,
+                       ctc_weight=0.5, reverse_weight=rw)
+    eo = model._encode(feats, lens.cuda(), -1, -1)
+    nbest = [r.nbest for r in res["ctc_prefix_beam_search"]]
+    hyp_utt, hyp_len, hyp_tok0, toks = model._flatten_hyps(nbest)
+    ctc = np.ascontiguousarray(np.array([s for r in res["ctc_prefix_beam_search"] for s in r.nbest_scores], np.float64))
+    n_hyp, B = int(hyp_utt.size), len(nbest)
+    R = int(hyp_len.sum()) + n_hyp
+    dev = feats.device
+    l2r = torch.zeros(R, device=dev)
+    r2l = torch.zeros(R, device=dev)
+    hs = torch.zeros(n_hyp, device=dev)
+    best = torch.zeros(B, device=dev, dtype=torch.int32)
+    lib = load()
+    wsb = lib.wb_rescoring_workspace_bytes(model.dm.handle, eo.rows, R)
+    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+    use_r2l = rw > 0 and model.spec.bidirectional
+    check(lib.wb_attention_rescoring(model.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host), ptr(eo.lens_host), B,
+                                     n_hyp, ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks), ptr(ctc), model.sos,
+                                     model.eos, 0.5, float(rw if use_r2l else 0.0), ptr(l2r), ptr(r2l), ptr(hs), ptr(best),
+                                     ptr(ws), wsb, cur_stream()), "wb_attention_rescoring")
+    hs, best = hs.cpu().numpy(), best.cpu().numpy()
+    h = 0
+    for b, r in enumerate(res["attention_rescoring"]):
+        n = len(nbest[b])
+        assert np.array_equal(np.array(r.nbest_scores, np.float32), hs[h:h + n]), (b, r.nbest_scores, hs[h:h + n])
+        assert tuple(r.tokens) == tuple(nbest[b][int(best[b])])
+        h += n

@@ -15,6 +15,7 @@ tensors must live on a CUDA device.
 """
 import ctypes as C
 import math
+from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -158,7 +159,7 @@ class B200ASRModel:
         other._ws = None
         other._ws2 = None
         other.d2h_bytes = 0
-        other._last_flat = None
+        other._pin = {}
         return other
 
     @classmethod
@@ -329,13 +330,20 @@ class B200ASRModel:
             results = {}
             if "ctc_greedy_search" in methods:
                 results["ctc_greedy_search"] = self._greedy(eo, ti, blank_id)
-            beam_out = None
             if need_beam:
-                beam_out = self._prefix_beam(eo, tv, ti, beam_size, blank_id)
+                # device-resident pipeline: only the per-hypothesis lengths / scores cross to the host before the
+                # rescoring pass is enqueued; the Python result objects are built while the decoder runs
+                bd = self._prefix_beam_launch(eo, tv, ti, beam_size, blank_id)
+                meta = self._beam_meta(bd)
+                fetch = self._beam_fetch_async(bd, meta)
+                rs = None
+                if "attention_rescoring" in methods:
+                    rs = self._rescore_launch(eo, bd, meta, ctc_weight, reverse_weight)
+                beam_out = self._beam_results(bd, meta, fetch)
                 if "ctc_prefix_beam_search" in methods:
                     results["ctc_prefix_beam_search"] = beam_out
-            if "attention_rescoring" in methods:
-                results["attention_rescoring"] = self._rescore(eo, beam_out, ctc_weight, reverse_weight)
+                if rs is not None:
+                    results["attention_rescoring"] = self._rescore_results(rs, meta, beam_out, reverse_weight)
         return results
 
     def _pack_padded(self, ys: torch.Tensor) -> _EncOut:
@@ -362,49 +370,93 @@ class B200ASRModel:
         th, lh = self._host(toks), self._host(lens)
         return [DecodeResult(th[b, :lh[b]].tolist()) for b in range(B)]
 
-    def _prefix_beam(self, eo: _EncOut, tv, ti, beam_size: int, blank_id: int) -> List[DecodeResult]:
+    # pinned staging buffers for asynchronous device -> host copies (allocated once, grown on demand)
+    def _pinned(self, name: str, numel: int, dtype) -> torch.Tensor:
+        bufs = self.__dict__.setdefault("_pin", {})
+        cur = bufs.get(name)
+        if cur is None or cur.numel() < numel or cur.dtype != dtype:
+            cur = torch.empty(max(int(numel * 1.25), 1024), dtype=dtype, pin_memory=True)
+            bufs[name] = cur
+        return cur[:numel]
+
+    def _d2h_async(self, name: str, t: torch.Tensor) -> np.ndarray:
+        """enqueue a device -> pinned-host copy on the current stream; valid after the next event/stream sync"""
+        t = t.contiguous()
+        dst = self._pinned(name, t.numel(), t.dtype)
+        dst.copy_(t.view(-1), non_blocking=True)
+        self.d2h_bytes += t.numel() * t.element_size()
+        return dst.numpy().reshape(tuple(t.shape))
+
+    def _prefix_beam_launch(self, eo: _EncOut, tv, ti, beam_size: int, blank_id: int):
         B = eo.seq_start.numel()
         max_len = max(eo.max_len, 1)
         lib = self._lib
-        toks = torch.zeros(B, beam_size, max_len, device=self.device, dtype=torch.int32)
-        times = torch.zeros(B, beam_size, max_len, device=self.device, dtype=torch.int32)
-        lens = torch.zeros(B, beam_size, device=self.device, dtype=torch.int32)
-        scores = torch.zeros(B, beam_size, device=self.device, dtype=torch.float64)
-        nhyp = torch.zeros(B, device=self.device, dtype=torch.int32)
+        bd = SimpleNamespace()
+        bd.B, bd.beam, bd.max_len = B, beam_size, max_len
+        bd.toks = torch.zeros(B, beam_size, max_len, device=self.device, dtype=torch.int32)
+        bd.times = torch.zeros(B, beam_size, max_len, device=self.device, dtype=torch.int32)
+        bd.lens = torch.zeros(B, beam_size, device=self.device, dtype=torch.int32)
+        bd.scores = torch.zeros(B, beam_size, device=self.device, dtype=torch.float64)
+        bd.nhyp = torch.zeros(B, device=self.device, dtype=torch.int32)
         wsb = lib.wb_prefix_beam_workspace_bytes(B, beam_size, max_len)
         ws = self._workspace(wsb, 1)
         check(lib.wb_ctc_prefix_beam_search(ptr(tv), ptr(ti), tv.stride(0), ptr(eo.seq_start), ptr(eo.seq_len), B,
-                                            int(beam_size), int(blank_id), max_len, ptr(toks), ptr(times), ptr(lens),
-                                            ptr(scores), ptr(nhyp), ptr(ws), wsb, cur_stream()),
+                                            int(beam_size), int(blank_id), max_len, ptr(bd.toks), ptr(bd.times),
+                                            ptr(bd.lens), ptr(bd.scores), ptr(bd.nhyp), ptr(ws), wsb, cur_stream()),
               "wb_ctc_prefix_beam_search")
-        th, mh, lh = self._host(toks), self._host(times), self._host(lens)
-        sh, nh = self._host(scores), self._host(nhyp)
-        # flat, utterance-major view of all hypotheses (vectorised; reused by _rescore)
-        valid = np.arange(beam_size)[None, :] < nh[:, None]                       # (B, beam)
-        hyp_utt = np.nonzero(valid)[0].astype(np.int32)
-        hyp_len = lh[valid].astype(np.int32)
-        tok_mask = np.arange(max_len)[None, :] < hyp_len[:, None]                 # (n_hyp, max_len)
-        flat_toks = np.ascontiguousarray(th[valid][tok_mask].astype(np.int32))
-        flat_times = mh[valid][tok_mask]
-        hyp_tok0 = np.concatenate([[0], np.cumsum(hyp_len)[:-1]]).astype(np.int32) if hyp_len.size else \
-            np.zeros(0, np.int32)
-        flat_scores = np.ascontiguousarray(sh[valid].astype(np.float64))
-        tok_list, time_list = flat_toks.tolist(), flat_times.tolist()
+        return bd
+
+    def _beam_meta(self, bd):
+        """lengths / scores / counts of the n-best lists -> flat utterance-major hypothesis tables (host, small)"""
+        lh = self._d2h_async("beam_lens", bd.lens)
+        sh = self._d2h_async("beam_scores", bd.scores)
+        nh = self._d2h_async("beam_nhyp", bd.nhyp)
+        torch.cuda.current_stream().synchronize()
+        m = SimpleNamespace()
+        valid = np.arange(bd.beam)[None, :] < nh[:, None]                          # (B, beam)
+        bi, ri = np.nonzero(valid)
+        m.nh = nh.copy()
+        m.hyp_utt = bi.astype(np.int32)
+        m.hyp_len = np.ascontiguousarray(lh[valid].astype(np.int32))
+        m.hyp_src = ((bi * bd.beam + ri) * bd.max_len).astype(np.int32)             # offsets into bd.toks (device)
+        m.scores = np.ascontiguousarray(sh[valid].astype(np.float64))
+        m.slot = (bi * bd.beam + ri).astype(np.int64)
+        m.lmax = int(m.hyp_len.max()) if m.hyp_len.size else 0
+        return m
+
+    def _beam_fetch_async(self, bd, meta):
+        L = max(meta.lmax, 1)
+        th = self._d2h_async("beam_toks", bd.toks[:, :, :L])
+        mh = self._d2h_async("beam_times", bd.times[:, :, :L])
+        ev = torch.cuda.Event()
+        ev.record()
+        return th, mh, ev
+
+    def _beam_results(self, bd, meta, fetch) -> List[DecodeResult]:
+        th, mh, ev = fetch
+        ev.synchronize()
+        L = th.shape[2]
+        th = th.reshape(-1, L)[meta.slot]                                           # (n_hyp, L)
+        mh = mh.reshape(-1, L)[meta.slot]
+        tok_mask = np.arange(L)[None, :] < meta.hyp_len[:, None]
+        tok_list, time_list = th[tok_mask].tolist(), mh[tok_mask].tolist()
+        ends = np.cumsum(meta.hyp_len).tolist()
+        score_list = meta.scores.tolist()
         out = []
         h = 0
-        for b in range(B):
-            n = int(nh[b])
+        a = 0
+        for b in range(bd.B):
+            n = int(meta.nh[b])
             nbest, ntimes = [], []
             for r in range(n):
-                a, e = int(hyp_tok0[h + r]), int(hyp_tok0[h + r]) + int(hyp_len[h + r])
+                e = ends[h + r]
                 nbest.append(tuple(tok_list[a:e]))
                 ntimes.append(time_list[a:e])
-            nscores = flat_scores[h:h + n].tolist()
+                a = e
+            nscores = score_list[h:h + n]
             out.append(DecodeResult(tokens=nbest[0], score=nscores[0], times=ntimes[0], nbest=nbest,
                                     nbest_scores=nscores, nbest_times=ntimes))
             h += n
-        self._last_flat = (hyp_utt, hyp_len, hyp_tok0, flat_toks if flat_toks.size else np.zeros(1, np.int32),
-                           flat_scores, out)
         return out
 
     def _flatten_hyps(self, hyps_per_utt):
@@ -419,37 +471,44 @@ class B200ASRModel:
             toks = [0]
         return _i32(hyp_utt), _i32(hyp_len), _i32(hyp_tok0), _i32(toks)
 
-    def _rescore(self, eo: _EncOut, beam_out: List[DecodeResult], ctc_weight: float, reverse_weight: float):
-        """search.py:374-458"""
+    def _rescore_launch(self, eo: _EncOut, bd, meta, ctc_weight: float, reverse_weight: float):
+        """search.py:374-458; hypotheses are read from the beam search's device buffer"""
         if not self.dm.has_decoder:
             raise _lib.WbError("attention_rescoring needs decoder weights")
         lib = self._lib
-        B = len(beam_out)
-        flat = getattr(self, "_last_flat", None)
-        if flat is not None and flat[5] is beam_out:
-            hyp_utt, hyp_len, hyp_tok0, toks, ctc_scores = flat[:5]
-        else:
-            hyp_utt, hyp_len, hyp_tok0, toks = self._flatten_hyps([r.nbest for r in beam_out])
-            ctc_scores = np.ascontiguousarray(np.array([s for r in beam_out for s in r.nbest_scores], dtype=np.float64))
-        n_hyp = int(hyp_utt.size)
-        R = int(hyp_len.sum()) + n_hyp
+        B = bd.B
+        n_hyp = int(meta.hyp_utt.size)
+        R = int(meta.hyp_len.sum()) + n_hyp
+        rs = SimpleNamespace()
+        rs.use_r2l = reverse_weight > 0 and self.spec.bidirectional and self.spec.rdec_layers > 0
         l2r = torch.zeros(R, device=self.device, dtype=torch.float32)
-        use_r2l = reverse_weight > 0 and self.spec.bidirectional and self.spec.rdec_layers > 0
         r2l = torch.zeros(R, device=self.device, dtype=torch.float32)
         hyp_score = torch.zeros(n_hyp, device=self.device, dtype=torch.float32)
         best = torch.zeros(B, device=self.device, dtype=torch.int32)
         wsb = lib.wb_rescoring_workspace_bytes(self.dm.handle, eo.rows, R)
         ws = self._workspace(wsb)
-        check(lib.wb_attention_rescoring(self.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host), ptr(eo.lens_host),
-                                         B, n_hyp, ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks),
-                                         ptr(ctc_scores), self.sos, self.eos, float(ctc_weight),
-                                         float(reverse_weight if use_r2l else 0.0), ptr(l2r), ptr(r2l), ptr(hyp_score),
-                                         ptr(best), ptr(ws), ws.numel(), cur_stream()), "wb_attention_rescoring")
-        l2r_h = self._host(l2r)
-        r2l_h = self._host(r2l) if use_r2l else None
-        hs, bh = self._host(hyp_score), self._host(best)
+        check(lib.wb_attention_rescoring_dev(self.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host),
+                                             ptr(eo.lens_host), B, n_hyp, ptr(meta.hyp_utt), ptr(meta.hyp_len),
+                                             ptr(meta.hyp_src), ptr(bd.toks), ptr(meta.scores), self.sos, self.eos,
+                                             float(ctc_weight), float(reverse_weight if rs.use_r2l else 0.0), ptr(l2r),
+                                             ptr(r2l), ptr(hyp_score), ptr(best), ptr(ws), ws.numel(), cur_stream()),
+              "wb_attention_rescoring_dev")
+        rs.l2r = self._d2h_async("rs_l2r", l2r)
+        rs.r2l = self._d2h_async("rs_r2l", r2l) if rs.use_r2l else None
+        rs.hs = self._d2h_async("rs_score", hyp_score)
+        rs.best = self._d2h_async("rs_best", best)
+        rs.ev = torch.cuda.Event()
+        rs.ev.record()
+        return rs
+
+    def _rescore_results(self, rs, meta, beam_out: List[DecodeResult], reverse_weight: float):
+        rs.ev.synchronize()
+        B = len(beam_out)
+        l2r_h, r2l_h, hs, bh = rs.l2r, rs.r2l, rs.hs, rs.best
+        use_r2l = rs.use_r2l
+        hyp_len = meta.hyp_len
         row0 = np.concatenate([[0], np.cumsum(hyp_len.astype(np.int64) + 1)])
-        nb_per_utt = np.bincount(hyp_utt, minlength=B)
+        nb_per_utt = np.bincount(meta.hyp_utt, minlength=B)
         h0s = np.concatenate([[0], np.cumsum(nb_per_utt)[:-1]])
         out = []
         for b in range(B):

@@ -27,7 +27,7 @@ struct RsPlan {
 void rs_layout(const Model* m, long long enc_rows, long long R, int batch, int n_hyp, RsPlan* P) {
     const int d = m->cfg.d_model, ff = m->cfg.dec_ffn_dim;
     P->ldl = (m->cfg.vocab + 7) / 8 * 8;
-    P->n_int = (size_t)5 * R + (size_t)3 * n_hyp + (size_t)6 * batch + 64;
+    P->n_int = (size_t)5 * R + (size_t)4 * n_hyp + (size_t)6 * batch + 64;
     size_t o = 0;
     P->o_int = o; o += align_up(P->n_int * 4);
     P->o_dbl = o; o += align_up((size_t)n_hyp * 8 + 64);
@@ -49,8 +49,8 @@ void rs_layout(const Model* m, long long enc_rows, long long R, int batch, int n
     } while (0)
 
 struct RsDevPtrs {
-    int *tok_l2r, *tok_r2l, *pos, *tgt_l2r, *tgt_r2l, *hyp_row0, *hyp_rows, *hyp_len, *utt_q0, *utt_qn, *utt_hyp0,
-        *utt_nhyp, *enc_start, *enc_len;
+    int *tok_l2r, *tok_r2l, *pos, *tgt_l2r, *tgt_r2l, *hyp_row0, *hyp_rows, *hyp_len, *hyp_src, *utt_q0, *utt_qn,
+        *utt_hyp0, *utt_nhyp, *enc_start, *enc_len;
     double* ctc;
 };
 
@@ -121,11 +121,31 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
     return WB_OK;
 }
 
+// decoder inputs from hypotheses that are still on the device (the prefix beam search output): one warp per hypothesis
+//   l2r: in = [sos, y0..y_{n-1}], target = [y0..y_{n-1}, eos];  r2l: the same on the reversed hypothesis
+__global__ void build_decoder_inputs_kernel(int n_hyp, const int* __restrict__ hyp_row0, const int* __restrict__ hyp_len,
+                                            const int* __restrict__ hyp_src, const int* __restrict__ tokens, int sos,
+                                            int eos, int* __restrict__ tok_l2r, int* __restrict__ tok_r2l,
+                                            int* __restrict__ tgt_l2r, int* __restrict__ tgt_r2l, int* __restrict__ pos) {
+    const int h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (h >= n_hyp) return;
+    const int lane = threadIdx.x & 31;
+    const int n = hyp_len[h], r = hyp_row0[h];
+    const int* y = tokens + hyp_src[h];
+    for (int j = lane; j <= n; j += 32) {
+        tok_l2r[r + j] = (j == 0) ? sos : y[j - 1];
+        tok_r2l[r + j] = (j == 0) ? sos : y[n - j];
+        tgt_l2r[r + j] = (j < n) ? y[j] : eos;
+        tgt_r2l[r + j] = (j < n) ? y[n - 1 - j] : eos;
+        pos[r + j] = j;
+    }
+}
+
 // builds the flattened decoder inputs on the host and uploads them (one copy)
 int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, const int32_t* seq_len_host, int batch,
             int n_hyp, const int32_t* hyp_utt, const int32_t* hyp_len, const int32_t* hyp_tok0,
-            const int32_t* hyp_tokens, const double* ctc_score, int sos, int eos, uint8_t* ws, size_t ws_bytes,
-            RsPlan* P, RsDevPtrs* dp, cudaStream_t st) {
+            const int32_t* hyp_tokens, bool tokens_on_device, const double* ctc_score, int sos, int eos, uint8_t* ws,
+            size_t ws_bytes, RsPlan* P, RsDevPtrs* dp, cudaStream_t st) {
     long long R = 0;
     for (int h = 0; h < n_hyp; ++h) R += hyp_len[h] + 1;
     rs_layout(m, enc_rows, R, batch, n_hyp, P);
@@ -143,7 +163,8 @@ int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, c
     int* hyp_row0 = tgt_r2l + R;
     int* hyp_rows = hyp_row0 + n_hyp;
     int* hyp_ln = hyp_rows + n_hyp;
-    int* utt_q0 = hyp_ln + n_hyp;
+    int* hyp_src = hyp_ln + n_hyp;
+    int* utt_q0 = hyp_src + n_hyp;
     int* utt_qn = utt_q0 + batch;
     int* utt_hyp0 = utt_qn + batch;
     int* utt_nhyp = utt_hyp0 + batch;
@@ -173,11 +194,12 @@ int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, c
         hyp_row0[h] = (int)r;
         hyp_rows[h] = n + 1;
         hyp_ln[h] = n;
+        hyp_src[h] = hyp_tok0[h];
         if (n + 1 > P->max_hyp_rows) P->max_hyp_rows = n + 1;
         const int32_t* y = hyp_tokens + hyp_tok0[h];
         // l2r: in = [sos, y0..y_{n-1}], target = [y0..y_{n-1}, eos]      (common.py:113-156 add_sos_eos)
         // r2l: in = [sos, y_{n-1}..y0], target = [y_{n-1}..y0, eos]      (asr_model.py:487-536)
-        for (int j = 0; j <= n; ++j) {
+        for (int j = 0; j <= n && !tokens_on_device; ++j) {
             tok_l2r[r + j] = (j == 0) ? sos : y[j - 1];
             tok_r2l[r + j] = (j == 0) ? sos : y[n - j];
             tgt_l2r[r + j] = (j < n) ? y[j] : eos;
@@ -202,13 +224,21 @@ int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, c
     dp->hyp_row0 = base + 5 * R;
     dp->hyp_rows = dp->hyp_row0 + n_hyp;
     dp->hyp_len = dp->hyp_rows + n_hyp;
-    dp->utt_q0 = dp->hyp_len + n_hyp;
+    dp->hyp_src = dp->hyp_len + n_hyp;
+    dp->utt_q0 = dp->hyp_src + n_hyp;
     dp->utt_qn = dp->utt_q0 + batch;
     dp->utt_hyp0 = dp->utt_qn + batch;
     dp->utt_nhyp = dp->utt_hyp0 + batch;
     dp->enc_start = dp->utt_nhyp + batch;
     dp->enc_len = dp->enc_start + batch;
     dp->ctc = reinterpret_cast<double*>(ws + P->o_dbl);
+    if (tokens_on_device) {
+        build_decoder_inputs_kernel<<<ceil_div(n_hyp, 8), 256, 0, st>>>(n_hyp, dp->hyp_row0, dp->hyp_len, dp->hyp_src,
+                                                                       hyp_tokens, sos, eos, dp->tok_l2r, dp->tok_r2l,
+                                                                       dp->tgt_l2r, dp->tgt_r2l, dp->pos);
+        count_launch();
+        WB_CHECK_LAUNCH();
+    }
     return WB_OK;
 }
 
@@ -229,13 +259,14 @@ size_t wb_rescoring_workspace_bytes(const wb_model* mm, int64_t enc_rows, int64_
     return P.total;
 }
 
-int wb_attention_rescoring(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows,
-                           const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int n_hyp,
-                           const int32_t* hyp_utt_host, const int32_t* hyp_len_host, const int32_t* hyp_tok0_host,
-                           const int32_t* hyp_tokens_host, const double* ctc_score_host, int sos, int eos,
-                           float ctc_weight, float reverse_weight, float* tok_logp_l2r_dev, float* tok_logp_r2l_dev,
-                           float* hyp_score_dev, int32_t* best_dev, void* workspace_dev, size_t workspace_bytes,
-                           wb_stream_t stream) {
+static int attention_rescoring_impl(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows,
+                                    const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int n_hyp,
+                                    const int32_t* hyp_utt_host, const int32_t* hyp_len_host,
+                                    const int32_t* hyp_tok0_host, const int32_t* hyp_tokens, bool tokens_on_device,
+                                    const double* ctc_score_host, int sos, int eos, float ctc_weight,
+                                    float reverse_weight, float* tok_logp_l2r_dev, float* tok_logp_r2l_dev,
+                                    float* hyp_score_dev, int32_t* best_dev, void* workspace_dev,
+                                    size_t workspace_bytes, wb_stream_t stream) {
     const Model* m = reinterpret_cast<const Model*>(mm);
     WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "attention_rescoring: model not finalized");
     WB_REQUIRE(m->cfg.dec_layers > 0, WB_ERR_UNSUPPORTED, "attention_rescoring: model has no decoder");
@@ -247,7 +278,7 @@ int wb_attention_rescoring(const wb_model* mm, const void* enc_out_bf16_dev, int
     RsPlan P;
     RsDevPtrs dp;
     RC(prepare(m, enc_rows, seq_start_host, seq_len_host, batch, n_hyp, hyp_utt_host, hyp_len_host, hyp_tok0_host,
-               hyp_tokens_host, ctc_score_host, sos, eos, ws, workspace_bytes, &P, &dp, st));
+               hyp_tokens, tokens_on_device, ctc_score_host, sos, eos, ws, workspace_bytes, &P, &dp, st));
     float* logits = reinterpret_cast<float*>(ws + P.o_logits);
     RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, logits, P.ldl, st));
     RC(gather_logprob(logits, P.ldl, (int)P.R, m->cfg.vocab, dp.tgt_l2r, tok_logp_l2r_dev, st));
@@ -273,6 +304,33 @@ int wb_attention_rescoring(const wb_model* mm, const void* enc_out_bf16_dev, int
     return rescore_combine(a, st);
 }
 
+int wb_attention_rescoring(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows,
+                           const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int n_hyp,
+                           const int32_t* hyp_utt_host, const int32_t* hyp_len_host, const int32_t* hyp_tok0_host,
+                           const int32_t* hyp_tokens_host, const double* ctc_score_host, int sos, int eos,
+                           float ctc_weight, float reverse_weight, float* tok_logp_l2r_dev, float* tok_logp_r2l_dev,
+                           float* hyp_score_dev, int32_t* best_dev, void* workspace_dev, size_t workspace_bytes,
+                           wb_stream_t stream) {
+    return attention_rescoring_impl(mm, enc_out_bf16_dev, enc_rows, seq_start_host, seq_len_host, batch, n_hyp,
+                                    hyp_utt_host, hyp_len_host, hyp_tok0_host, hyp_tokens_host, false, ctc_score_host,
+                                    sos, eos, ctc_weight, reverse_weight, tok_logp_l2r_dev, tok_logp_r2l_dev,
+                                    hyp_score_dev, best_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int wb_attention_rescoring_dev(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows,
+                               const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int n_hyp,
+                               const int32_t* hyp_utt_host, const int32_t* hyp_len_host, const int32_t* hyp_tok0_host,
+                               const int32_t* hyp_tokens_dev, const double* ctc_score_host, int sos, int eos,
+                               float ctc_weight, float reverse_weight, float* tok_logp_l2r_dev,
+                               float* tok_logp_r2l_dev, float* hyp_score_dev, int32_t* best_dev, void* workspace_dev,
+                               size_t workspace_bytes, wb_stream_t stream) {
+    WB_REQUIRE(hyp_tokens_dev, WB_ERR_BAD_ARG, "attention_rescoring_dev: null token buffer");
+    return attention_rescoring_impl(mm, enc_out_bf16_dev, enc_rows, seq_start_host, seq_len_host, batch, n_hyp,
+                                    hyp_utt_host, hyp_len_host, hyp_tok0_host, hyp_tokens_dev, true, ctc_score_host, sos,
+                                    eos, ctc_weight, reverse_weight, tok_logp_l2r_dev, tok_logp_r2l_dev, hyp_score_dev,
+                                    best_dev, workspace_dev, workspace_bytes, stream);
+}
+
 int wb_decoder_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows,
                         const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int n_hyp,
                         const int32_t* hyp_utt_host, const int32_t* hyp_len_host, const int32_t* hyp_tok0_host,
@@ -288,7 +346,7 @@ int wb_decoder_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_
     RsPlan P;
     RsDevPtrs dp;
     RC(prepare(m, enc_rows, seq_start_host, seq_len_host, batch, n_hyp, hyp_utt_host, hyp_len_host, hyp_tok0_host,
-               hyp_tokens_host, nullptr, sos, eos, ws, workspace_bytes, &P, &dp, st));
+               hyp_tokens_host, false, nullptr, sos, eos, ws, workspace_bytes, &P, &dp, st));
     RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, logp_dev, ldl, st));
     RC(ctc_logsoftmax_topk(logp_dev, ldl, (int)P.R, m->cfg.vocab, -1, 0.f, 0, nullptr, nullptr, st));
     if (use_r2l && m->cfg.rdec_layers > 0 && r_logp_dev) {
