@@ -60,6 +60,12 @@ void wb_prof_reset(void);
 int wb_prof_num_tags(void);
 const char* wb_prof_tag_name(int tag);
 int wb_prof_collect(double* ms, double* work, long long* launches);
+/* Stall accounting of the tcgen05 GEMM kernel (cycles, summed over CTAs and launches since the last reset):
+ * out8 = {producer waits for a ring slot, MMA waits for operands, MMA waits for a drained accumulator stage,
+ * epilogue waits for an accumulator, epilogue waits for its staging buffer, epilogue loop time (one warp),
+ * CTA lifetime, tiles, epilogue tcgen05.ld wait, epilogue bias + activation, epilogue staging stores + TMA issue, 0}
+ * (12 values).  Tuning aid used by tools/bench_ops.py; out12 may be NULL (reset only). */
+int wb_gemm_diag(uint64_t* out12, int reset);
 
 /* ------------------------------------------------------------------------------------------
  * A. fbank  — replaces wenet/dataset/processor.py:226-256 compute_fbank, i.e.
@@ -166,6 +172,14 @@ int wb_ctc_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t row
                     float blank_penalty, float* logp_dev, int64_t ldl, int topk, float* topk_val_dev,
                     int32_t* topk_idx_dev, wb_stream_t stream);
 
+/* Same posteriors, but only the per-frame top-k leaves the kernel: topk_val_dev [M][topk] holds the log-probabilities
+ * (log-softmax normalised, blank penalty applied) of the topk best tokens in (value desc, index asc) order and
+ * topk_idx_dev their ids.  logits_scratch_dev [M][ldl] receives the RAW CTC logits (not normalised); it is scratch
+ * for the caller.  This is what decode() uses: the [frames, V] matrix is read twice and never rewritten. */
+int wb_ctc_topk(const wb_model* m, const void* enc_out_bf16_dev, int64_t rows, int blank_id, float blank_penalty,
+                float* logits_scratch_dev, int64_t ldl, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
+                wb_stream_t stream);
+
 /* D1. replaces ctc_greedy_search (search.py:109-124) + remove_duplicates_and_blank
  *     (wenet/utils/ctc_utils.py:23-33).  tokens_dev [batch][out_stride], lens_dev [batch]. */
 int wb_ctc_greedy_search(const int32_t* topk_idx_dev, int topk, const int32_t* seq_start_dev,
@@ -263,6 +277,8 @@ int wb_op_dwconv(const void* g_dev, int64_t ldg, const int32_t* seq_start_dev,
 int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blank_id,
                           float blank_penalty, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
                           wb_stream_t stream);
+int wb_op_lse_topk(const float* logits_dev, int64_t ldl, int M, int V, int blank_id, float blank_penalty,
+                   int topk, float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream);
 
 /* hardware probe (tools/tests only): one 3-D TMA tiled load with element strides; see csrc/probe.cu */
 int wb_probe_tma3d(const void* base_dev, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,

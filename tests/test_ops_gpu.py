@@ -342,3 +342,39 @@ def test_ffn_fused(M, ff, act):
     two = ops.gemm(ops.gemm(a, w1, b1, ops.EPI_BF16_SILU if act == 0 else ops.EPI_BF16_RELU), w2, b2, ops.EPI_RESID_F32, 0.5,
                    out=x0.clone())
     assert (x - two).abs().max().item() < 3e-3
+
+
+@pytest.mark.parametrize("V,k", [(4233, 10), (37, 5), (5538, 1), (300, 64)])
+def test_lse_topk_without_writeback(V, k):
+    """wb_ctc_topk's kernel mode (no normalised matrix written): same top-k as the write-back mode and as torch,
+    logits untouched; flat / tied rows (more candidates than the per-warp list holds) take the ordered re-scan path."""
+    from wenet_b200 import ops
+    g = torch.Generator().manual_seed(V + k)
+    M = 257
+    ld = (V + 7) // 8 * 8
+    logits = _peaky_logits(M, V, g)
+    logits[3] = 0.25                                  # completely flat row: every element ties
+    logits[4, : V // 2] = 1.5                         # half the row tied at the maximum
+    logits[5] = torch.arange(V, dtype=torch.float32) * 1e-3   # slowly increasing: many near-candidates
+    buf = torch.zeros(M, ld)
+    buf[:, :V] = logits
+    dbuf = buf.to(_dev())
+    tv, ti = ops.lse_topk(dbuf, V, k, blank_id=0, blank_penalty=0.5)
+    assert torch.equal(dbuf.cpu(), buf)               # input left as it was
+    pen = logits.clone()
+    pen[:, 0] -= 0.5
+    ref = pen.log_softmax(-1)
+    # reference order: value descending, index ascending (ties are common in rows 3 and 4)
+    order = torch.argsort(-ref.double() + torch.arange(V, dtype=torch.float64) * 0, dim=-1, stable=True)[:, :k]
+    got_i = ti.cpu().long()
+    got_v = tv.cpu()
+    assert (got_v - torch.gather(ref, 1, got_i)).abs().max().item() < 2e-5
+    for r in range(M):
+        rv = ref[r, order[r]]
+        assert (got_v[r] - rv).abs().max().item() < 2e-5, r
+        if r in (3, 4, 5) or torch.unique(pen[r]).numel() == V:
+            assert torch.equal(got_i[r], order[r]), (r, got_i[r], order[r])
+    # the write-back mode agrees bit for bit on the top-k and produces the full normalised matrix
+    tv2, ti2 = ops.logsoftmax_topk(dbuf, V, k, blank_id=0, blank_penalty=0.5)
+    assert torch.equal(ti2, ti) and torch.equal(tv2, tv)
+    assert (dbuf[:, :V].cpu() - ref).abs().max().item() < 2e-5

@@ -53,6 +53,7 @@ _PROTOS = {
                                         C.POINTER(C.c_int), C.POINTER(C.c_int), vp, sz, vp]),
     "wb_unpack_rows": (i32, [vp, vp, vp, i32, i32, i32, vp, i64, vp]),
     "wb_ctc_logprobs": (i32, [vp, vp, i64, i32, f32, vp, i64, i32, vp, vp, vp]),
+    "wb_ctc_topk": (i32, [vp, vp, i64, i32, f32, vp, i64, i32, vp, vp, vp]),
     "wb_ctc_greedy_search": (i32, [vp, i32, vp, vp, i32, i32, vp, i32, vp, vp]),
     "wb_prefix_beam_workspace_bytes": (sz, [i32, i32, i32]),
     "wb_ctc_prefix_beam_search": (i32, [vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
@@ -60,6 +61,7 @@ _PROTOS = {
     "wb_rescoring_workspace_bytes": (sz, [vp, i64, i64]),
     "wb_attention_rescoring": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, f32,
                                       f32, vp, vp, vp, vp, vp, sz, vp]),
+    "wb_gemm_diag": (i32, [vp, i32]),
     "wb_attention_rescoring_dev": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, f32,
                                           f32, vp, vp, vp, vp, vp, sz, vp]),
     "wb_decoder_logprobs": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp,
@@ -74,6 +76,7 @@ _PROTOS = {
     "wb_op_dwconv": (i32, [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, f32,
                             vp, i32, vp, i64, vp]),
     "wb_op_logsoftmax_topk": (i32, [vp, i64, i32, i32, i32, f32, i32, vp, vp, vp]),
+    "wb_op_lse_topk": (i32, [vp, i64, i32, i32, i32, f32, i32, vp, vp, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_PROTOS))

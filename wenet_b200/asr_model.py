@@ -282,7 +282,8 @@ class B200ASRModel:
         return y, r_att, r_cnn
 
     # ----- CTC -----
-    def _ctc(self, eo: _EncOut, topk: int, blank_id: int, blank_penalty: float):
+    def _ctc(self, eo: _EncOut, topk: int, blank_id: int, blank_penalty: float, full: bool = True):
+        """full=True: normalised log-probs for every token (API parity); False: only the per-frame top-k (decode())."""
         V = self.spec.vocab
         ldl = (V + 7) // 8 * 8
         rows = max(eo.rows, 1)
@@ -291,8 +292,9 @@ class B200ASRModel:
         tv = torch.empty(rows, k, device=self.device, dtype=torch.float32)
         ti = torch.empty(rows, k, device=self.device, dtype=torch.int32)
         if eo.rows > 0:
-            check(self._lib.wb_ctc_logprobs(self.dm.handle, ptr(eo.bf16), eo.rows, int(blank_id), float(blank_penalty),
-                                            ptr(logp), ldl, k, ptr(tv), ptr(ti), cur_stream()), "wb_ctc_logprobs")
+            fn = self._lib.wb_ctc_logprobs if (full or k > 64) else self._lib.wb_ctc_topk
+            check(fn(self.dm.handle, ptr(eo.bf16), eo.rows, int(blank_id), float(blank_penalty), ptr(logp), ldl, k, ptr(tv),
+                     ptr(ti), cur_stream()), "wb_ctc_logprobs")
         return logp, tv, ti
 
     def ctc_logprobs(self, encoder_out: torch.Tensor, blank_penalty: float = 0.0, blank_id: int = 0) -> torch.Tensor:
@@ -326,7 +328,7 @@ class B200ASRModel:
                 eo = self._encode(speech, speech_lengths, decoding_chunk_size, num_decoding_left_chunks)
             need_beam = ("ctc_prefix_beam_search" in methods) or ("attention_rescoring" in methods)
             topk = beam_size if need_beam else 1
-            logp, tv, ti = self._ctc(eo, topk, blank_id, blank_penalty)
+            logp, tv, ti = self._ctc(eo, topk, blank_id, blank_penalty, full=False)
             results = {}
             if "ctc_greedy_search" in methods:
                 results["ctc_greedy_search"] = self._greedy(eo, ti, blank_id)

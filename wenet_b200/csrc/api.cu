@@ -187,6 +187,7 @@ const char* wb_prof_tag_name(int tag) {
     return (tag >= 0 && tag < PT_COUNT) ? names[tag] : "?";
 }
 int wb_prof_collect(double* ms, double* work, long long* launches) { return wb::prof_collect(ms, work, launches); }
+int wb_gemm_diag(uint64_t* out8, int reset) { return wb::gemm_diag(reinterpret_cast<unsigned long long*>(out8), reset); }
 
 // ---------------------------------------------------------------- fbank
 struct wb_fbank {
@@ -268,6 +269,20 @@ int wb_ctc_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_t ro
                  m->ctc.b, EPI_F32, 1.0f, logp_dev, ldl, 0, st));
     return ctc_logsoftmax_topk(logp_dev, ldl, (int)rows, m->cfg.vocab, blank_id, blank_penalty, topk, topk_val_dev,
                                topk_idx_dev, st);
+}
+
+int wb_ctc_topk(const wb_model* mm, const void* enc_out_bf16_dev, int64_t rows, int blank_id, float blank_penalty,
+                float* logits_scratch_dev, int64_t ldl, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
+                wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "ctc_topk: model not finalized");
+    WB_REQUIRE(ldl >= m->cfg.vocab && topk_val_dev && topk_idx_dev && logits_scratch_dev, WB_ERR_BAD_ARG,
+               "ctc_topk: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    RC(gemm_bf16(enc_out_bf16_dev, m->cfg.d_model, &m->ctc.tmap, m->ctc.w, (int)rows, m->cfg.vocab, m->cfg.d_model,
+                 m->ctc.b, EPI_F32, 1.0f, logits_scratch_dev, ldl, 0, st));
+    return ctc_lse_topk(logits_scratch_dev, ldl, (int)rows, m->cfg.vocab, blank_id, blank_penalty, topk, topk_val_dev,
+                        topk_idx_dev, st);
 }
 
 int wb_ctc_greedy_search(const int32_t* topk_idx_dev, int topk, const int32_t* seq_start_dev,
@@ -361,6 +376,11 @@ int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blan
                           float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream) {
     return ctc_logsoftmax_topk(logits_dev, ldl, M, V, blank_id, blank_penalty, topk, topk_val_dev, topk_idx_dev,
                                (cudaStream_t)stream);
+}
+int wb_op_lse_topk(const float* logits_dev, int64_t ldl, int M, int V, int blank_id, float blank_penalty, int topk,
+                   float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream) {
+    return ctc_lse_topk(logits_dev, ldl, M, V, blank_id, blank_penalty, topk, topk_val_dev, topk_idx_dev,
+                        (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -312,6 +312,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// wait for outstanding tcgen05.ld and tie the destination registers to the wait, so uses of `r` cannot be scheduled
+// above it when the load was issued earlier (software-pipelined epilogues)
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 
 // Shared-memory matrix descriptor, SWIZZLE_128B canonical layouts (PTX ISA "matrix descriptor"):
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4

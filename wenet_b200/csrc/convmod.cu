@@ -35,8 +35,17 @@ struct DwDev {
     int split3;
 };
 
-// KT: compile-time kernel size (8 / 15 are the recipe values), 0 = run-time loop
-template <int KT>
+// KT: compile-time kernel size (8 / 15 are the recipe values), 0 = run-time loop.
+//
+// One warp owns FPW consecutive output frames for ALL channels, in passes of 128 channels (4 per lane): the
+// (FPW + K - 1) input rows of a pass are read once from the staged tile and each value feeds up to FPW accumulators
+// (sliding window in registers), the conv outputs stay in registers, LayerNorm statistics are two warp reductions per
+// frame, and the 4-channel groups go through the quad sigmoid.  No intermediate fp32 tile, one __syncthreads.
+constexpr int FPW = TT / (DW_THREADS / 32);   // 4 frames per warp
+constexpr int MAX_PASSES = 4;                 // d <= 512
+
+// NP: passes of 128 channels (d <= 128 * NP)
+template <int KT, int NP>
 __global__ void __launch_bounds__(DW_THREADS)
 dwconv_kernel(DwDev P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -49,8 +58,14 @@ dwconv_kernel(DwDev P) {
     const int left = P.causal ? (K - 1) : (K - 1) / 2;
     const int rows_in = TT + K - 1;
     __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(smem_raw);           // [rows_in][d]
-    float* s_out = reinterpret_cast<float*>(smem_raw + ((size_t)rows_in * d * 2 + 15) / 16 * 16);  // [TT][d]
+    float* s_w = reinterpret_cast<float*>(smem_raw + ((size_t)rows_in * d * 2 + 15) / 16 * 16);   // [K][d] (tap-major)
     const long long base = P.seq_start[b];
+
+    // depthwise weights [d][K] -> shared memory, tap-major, so a lane fetches its 4 channels of tap k as one float4
+    for (int i = threadIdx.x; i < d * K; i += DW_THREADS) {
+        const int c = i / K, k = i - c * K;
+        s_w[k * d + c] = P.w[i];
+    }
 
     // stage input rows: input position p = lead + t0 - left + r
     const int dv = d / 8;
@@ -74,73 +89,111 @@ dwconv_kernel(DwDev P) {
     __syncthreads();
 
     const int nt = min(TT, n_out - t0);
-    // depthwise conv: thread = (channel pair, frame group); weights live in registers
-    {
-        const int pairs = d >> 1;
-        const int ngroups = (DW_THREADS / pairs) > 0 ? (DW_THREADS / pairs) : 1;
-        for (int idx = threadIdx.x; idx < pairs * ngroups; idx += DW_THREADS) {
-            const int c = 2 * (idx % pairs);
-            const int grp = idx / pairs;
-            constexpr int KR = (KT > 0) ? KT : MAX_K;
-            float w0[KR], w1[KR];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tw0 = warp * FPW;            // first frame (within the tile) of this warp
+    if (tw0 >= nt) return;
+    constexpr int KR = (KT > 0) ? KT : MAX_K;
+    float acc[NP][FPW][4];
+#pragma unroll
+    for (int ps = 0; ps < NP; ++ps) {
+        const int c0 = ps * 128 + 4 * lane;
+        const bool act = c0 < d;   // d % 4 == 0: a lane's four channels are all inside or all outside
+        {
+            float w[4][KR];
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
-                w0[k] = (k < K) ? P.w[(size_t)c * K + k] : 0.f;
-                w1[k] = (k < K) ? P.w[(size_t)(c + 1) * K + k] : 0.f;
+                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act && (KT > 0 || k < K)) w4 = *reinterpret_cast<const float4*>(s_w + k * d + c0);
+                w[0][k] = w4.x;
+                w[1][k] = w4.y;
+                w[2][k] = w4.z;
+                w[3][k] = w4.w;
             }
-            const float b0 = P.bias[c], b1 = P.bias[c + 1];
-            float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
-            if (P.norm_type == 1) {
-                sc0 = P.gamma[c]; sc1 = P.gamma[c + 1]; sh0 = P.beta[c]; sh1 = P.beta[c + 1];
-            }
-            for (int t = grp; t < nt; t += ngroups) {
-                float a0 = b0, a1 = b1;
+            const float4 bb = act ? *reinterpret_cast<const float4*>(P.bias + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < KR; ++k) {
-                    if (KT > 0 || k < K) {
-                        const uint32_t xx = *reinterpret_cast<const uint32_t*>(s_in + (size_t)(t + k) * d + c);
-                        a0 = fmaf(w0[k], bf16_lo(xx), a0);
-                        a1 = fmaf(w1[k], bf16_hi(xx), a1);
+            for (int f = 0; f < FPW; ++f) {
+                acc[ps][f][0] = bb.x;
+                acc[ps][f][1] = bb.y;
+                acc[ps][f][2] = bb.z;
+                acc[ps][f][3] = bb.w;
+            }
+#pragma unroll
+            for (int r = 0; r < FPW + KR - 1; ++r) {
+                if (KT > 0 || r < FPW + K - 1) {
+                    const uint2 xx = act ? *reinterpret_cast<const uint2*>(s_in + (size_t)(tw0 + r) * d + c0) : make_uint2(0u, 0u);
+                    const float x0 = bf16_lo(xx.x), x1 = bf16_hi(xx.x), x2 = bf16_lo(xx.y), x3 = bf16_hi(xx.y);
+#pragma unroll
+                    for (int f = 0; f < FPW; ++f) {
+                        const int k = r - f;   // tap index of input row r for output frame tw0 + f
+                        if (k >= 0 && k < KR && (KT > 0 || k < K)) {
+                            acc[ps][f][0] = fmaf(w[0][k], x0, acc[ps][f][0]);
+                            acc[ps][f][1] = fmaf(w[1][k], x1, acc[ps][f][1]);
+                            acc[ps][f][2] = fmaf(w[2][k], x2, acc[ps][f][2]);
+                            acc[ps][f][3] = fmaf(w[3][k], x3, acc[ps][f][3]);
+                        }
                     }
                 }
-                if (P.norm_type == 1) {  // folded BatchNorm (eval): y = x*scale + shift, then SiLU
-                    a0 = silu_f(fmaf(a0, sc0, sh0));
-                    a1 = silu_f(fmaf(a1, sc1, sh1));
-                }
-                *reinterpret_cast<float2*>(s_out + (size_t)t * d + c) = make_float2(a0, a1);
             }
         }
     }
-    __syncthreads();
 
-    // norm (LayerNorm over channels) + SiLU + store: warp per frame
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int t = warp; t < nt; t += DW_THREADS / 32) {
-        const float* row = s_out + (size_t)t * d;
+    const float inv_d = 1.0f / (float)d;
+#pragma unroll
+    for (int f = 0; f < FPW; ++f) {
+        const int t = tw0 + f;
+        if (t >= nt) break;   // warp-uniform
         float mean = 0.f, rstd = 1.f;
         if (P.norm_type == 0) {
-            float s = 0.f;
-            for (int c = lane; c < d; c += 32) s += row[c];
-            mean = warp_sum(s) / (float)d;
+            float sm = 0.f;
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) sm += (acc[ps][f][0] + acc[ps][f][1]) + (acc[ps][f][2] + acc[ps][f][3]);
+            mean = warp_sum(sm) * inv_d;
             float q = 0.f;
-            for (int c = lane; c < d; c += 32) {
-                const float z = row[c] - mean;
-                q += z * z;
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) {
+                if (ps * 128 + 4 * lane < d) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float z = acc[ps][f][j] - mean;
+                        q = fmaf(z, z, q);
+                    }
+                }
             }
-            rstd = rsqrtf(warp_sum(q) / (float)d + P.eps);
+            rstd = rsqrtf(warp_sum(q) * inv_d + P.eps);
         }
         __nv_bfloat16* o = P.out + ((long long)P.out_start[b] + t0 + t) * P.ldo;
-        for (int c = 2 * lane; c < d; c += 64) {
-            float y0 = row[c], y1 = row[c + 1];
-            if (P.norm_type == 0) {
-                y0 = silu_f((y0 - mean) * rstd * P.gamma[c] + P.beta[c]);
-                y1 = silu_f((y1 - mean) * rstd * P.gamma[c + 1] + P.beta[c + 1]);
-            }
-            const uint32_t pk = pack_bf16x2(y0, y1);
-            *reinterpret_cast<uint32_t*>(o + c) = pk;
-            if (P.split3) {
-                *reinterpret_cast<uint32_t*>(o + d + c) = pack_bf16x2(y0 - bf16_lo(pk), y1 - bf16_hi(pk));
-                *reinterpret_cast<uint32_t*>(o + 2 * d + c) = pk;
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) {
+            const int c0 = ps * 128 + 4 * lane;
+            if (c0 < d) {
+                const float4 g4 = *reinterpret_cast<const float4*>(P.gamma + c0);
+                const float4 b4 = *reinterpret_cast<const float4*>(P.beta + c0);
+                float y0, y1, y2, y3;
+                if (P.norm_type == 0) {
+                    y0 = (acc[ps][f][0] - mean) * rstd * g4.x + b4.x;
+                    y1 = (acc[ps][f][1] - mean) * rstd * g4.y + b4.y;
+                    y2 = (acc[ps][f][2] - mean) * rstd * g4.z + b4.z;
+                    y3 = (acc[ps][f][3] - mean) * rstd * g4.w + b4.w;
+                } else {  // folded BatchNorm (eval): y = x * scale + shift
+                    y0 = fmaf(acc[ps][f][0], g4.x, b4.x);
+                    y1 = fmaf(acc[ps][f][1], g4.y, b4.y);
+                    y2 = fmaf(acc[ps][f][2], g4.z, b4.z);
+                    y3 = fmaf(acc[ps][f][3], g4.w, b4.w);
+                }
+                float s0, s1, s2, s3;
+                sigmoid4(y0, y1, y2, y3, s0, s1, s2, s3);
+                y0 *= s0;
+                y1 *= s1;
+                y2 *= s2;
+                y3 *= s3;
+                const uint32_t p01 = pack_bf16x2(y0, y1), p23 = pack_bf16x2(y2, y3);
+                *reinterpret_cast<uint2*>(o + c0) = make_uint2(p01, p23);
+                if (P.split3) {
+                    *reinterpret_cast<uint2*>(o + d + c0) =
+                        make_uint2(pack_bf16x2(y0 - bf16_lo(p01), y1 - bf16_hi(p01)),
+                                   pack_bf16x2(y2 - bf16_lo(p23), y3 - bf16_hi(p23)));
+                    *reinterpret_cast<uint2*>(o + 2 * d + c0) = make_uint2(p01, p23);
+                }
             }
         }
     }
@@ -151,7 +204,8 @@ dwconv_kernel(DwDev P) {
 int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream) {
     if (a.batch <= 0 || a.max_len <= 0) return WB_OK;
     WB_REQUIRE(a.ksize >= 1 && a.ksize <= MAX_K, WB_ERR_UNSUPPORTED, "dwconv: kernel size %d unsupported", a.ksize);
-    WB_REQUIRE(a.d % 8 == 0 && a.ldg % 8 == 0 && a.ldo % 2 == 0, WB_ERR_BAD_ARG, "dwconv: alignment");
+    WB_REQUIRE(a.d % 8 == 0 && a.d <= 128 * MAX_PASSES && a.ldg % 8 == 0 && a.ldo % 4 == 0, WB_ERR_UNSUPPORTED,
+               "dwconv: d=%d must be a multiple of 8 (<= %d) with 8-byte aligned rows", a.d, 128 * MAX_PASSES);
     WB_REQUIRE(a.causal || (a.ksize % 2 == 1), WB_ERR_BAD_ARG, "dwconv: symmetric kernel must be odd");
     DwDev P;
     P.g = reinterpret_cast<const __nv_bfloat16*>(a.g);
@@ -175,22 +229,29 @@ int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream) {
     P.ldo = a.ldo;
     P.split3 = a.split3;
     const int rows_in = TT + a.ksize - 1;
-    const size_t smem = ((size_t)rows_in * a.d * 2 + 15) / 16 * 16 + (size_t)TT * a.d * sizeof(float);
+    const size_t smem = ((size_t)rows_in * a.d * 2 + 15) / 16 * 16 + (size_t)a.ksize * a.d * sizeof(float);
     dim3 grid(ceil_div(a.max_len, TT), a.batch);
     ProfScope _ps(PT_DWCONV, stream, (double)a.batch * a.max_len * a.d * 4.0);
-#define WB_DW(KT)                                                                                              \
-    do {                                                                                                       \
-        static size_t smem_set = 0;                                                                            \
-        if (smem > 48 * 1024 && smem > smem_set) {                                                             \
-            WB_CHECK_CUDA(cudaFuncSetAttribute(dwconv_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                               (int)smem));                                                    \
-            smem_set = smem;                                                                                   \
-        }                                                                                                      \
-        dwconv_kernel<KT><<<grid, DW_THREADS, smem, stream>>>(P);                                              \
+#define WB_DW(KT, NP)                                                                                              \
+    do {                                                                                                           \
+        static size_t smem_set = 0;                                                                                \
+        if (smem > 48 * 1024 && smem > smem_set) {                                                                 \
+            WB_CHECK_CUDA(cudaFuncSetAttribute(dwconv_kernel<KT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)smem));                                                        \
+            smem_set = smem;                                                                                       \
+        }                                                                                                          \
+        dwconv_kernel<KT, NP><<<grid, DW_THREADS, smem, stream>>>(P);                                              \
     } while (0)
-    if (a.ksize == 8) WB_DW(8);
-    else if (a.ksize == 15) WB_DW(15);
-    else WB_DW(0);
+#define WB_DW_NP(KT)                  \
+    do {                              \
+        if (a.d <= 128) WB_DW(KT, 1); \
+        else if (a.d <= 256) WB_DW(KT, 2); \
+        else WB_DW(KT, 4);            \
+    } while (0)
+    if (a.ksize == 8) WB_DW_NP(8);
+    else if (a.ksize == 15) WB_DW_NP(15);
+    else WB_DW(0, 4);
+#undef WB_DW_NP
 #undef WB_DW
     count_launch();
     WB_CHECK_LAUNCH();

@@ -3,8 +3,8 @@
 // Replaces wenet/models/transformer/ctc.py:73-81 (log_softmax), asr_model.py:254-265 (blank penalty),
 // search.py:158 (logp.topk(beam_size) per frame) and search.py:109-124 + ctc_utils.py:23-33 (greedy).
 //
-// HBM-bound: one read + one write of the [frames, V] fp32 matrix (12.7 MB per 30 s utterance at
-// V = 4233); the row lives in shared memory for max / sum-exp / k rounds of block arg-max.
+// HBM-bound: one read (+ one write when the normalised matrix is requested) of the [frames, V] fp32 matrix
+// (12.7 MB per 30 s utterance at V = 4233).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -12,90 +12,181 @@ namespace wb {
 
 namespace {
 
-constexpr int LS_THREADS = 256;
+// ---------------------------------------------------------------------------------------------------------------
+// Log-softmax + per-frame top-k, one warp per row, the row is read twice (HBM, then L2).  The normalised matrix is
+// written back only when out_logp != nullptr (ctc_logprobs API parity); decode() passes nullptr because the searches
+// consume nothing but the per-frame top-k (search.py:158).
+//   pass 1: online log-sum-exp (5 MUFU per 4 elements) + the two largest elements of every lane;
+//           tau = k-th largest of those 64 values  =>  every true top-k element is >= tau;
+//   pass 2: elements >= tau are compacted into a per-warp candidate list (ballot / popc), from which k rounds of warp
+//           arg-max pick the winners in (value desc, index asc) order - torch.topk's order on distinct values.
+// Rows with more than LT_CAP candidates (flat posteriors) take k ordered re-scans of the row instead.
+constexpr int LT_WARPS = 4;
+constexpr int LT_CAP = 192;
 
-__device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int oi) {
-    if (ov > v || (ov == v && oi < i)) {
-        v = ov;
-        i = oi;
+// (v, i) precedes (pv, pi) in the output order
+__device__ __forceinline__ bool lt_before(float v, int i, float pv, int pi) { return v > pv || (v == pv && i < pi); }
+
+__device__ __forceinline__ void lt_warp_best(float& v, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (lt_before(ov, oi, v, i)) {
+            v = ov;
+            i = oi;
+        }
     }
 }
 
-__global__ void __launch_bounds__(LS_THREADS)
-logsoftmax_topk_kernel(float* __restrict__ logits, long long ldl, int V, int blank_id, float blank_penalty,
-                       int topk, float* __restrict__ topk_val, int* __restrict__ topk_idx) {
-    extern __shared__ float s_row[];  // [V]
-    __shared__ float s_redv[LS_THREADS / 32];
-    __shared__ int s_redi[LS_THREADS / 32];
-    __shared__ float s_bcast;
-    __shared__ int s_bcasti;
-    const long long row = blockIdx.x;
-    float* g = logits + row * ldl;
+__global__ void __launch_bounds__(LT_WARPS * 32)
+lse_topk_kernel(const float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
+                float* __restrict__ topk_val, int* __restrict__ topk_idx, float* out_logp /* may alias logits */) {
+    __shared__ float s_cv[LT_WARPS][LT_CAP];
+    __shared__ int s_ci[LT_WARPS][LT_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * LT_WARPS + warp;
+    if (row >= M) return;
+    const float* g = logits + row * ldl;
+    const int n4 = (V + 3) >> 2;
+    constexpr float kLog2e = 1.4426950408889634f;
+    auto load4_from = [&](const float* src, float pen, int i4, float (&v)[4]) {
+        const float4 x = *reinterpret_cast<const float4*>(src + 4 * i4);   // ldl >= round_up(V, 4): in bounds
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = 4 * i4 + e;
+            if (idx == blank_id) v[e] -= pen;
+            if (idx >= V) v[e] = -INFINITY;
+        }
+    };
+    auto load4 = [&](int i4, float (&v)[4]) { load4_from(g, blank_penalty, i4, v); };
 
-    float mx = -INFINITY;
-    for (int i = threadIdx.x; i < V; i += LS_THREADS) {
-        float v = g[i];
-        if (i == blank_id) v -= blank_penalty;
-        s_row[i] = v;
-        mx = fmaxf(mx, v);
+    // ---- pass 1 ----
+    float m = -INFINITY, ssum = 0.f;
+    float v1 = -INFINITY, v2 = -INFINITY;
+    for (int i4 = lane; i4 < n4; i4 += 32) {
+        float v[4];
+        load4(i4, v);
+        const float gm = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+        const float mn = fmaxf(m, gm);
+        if (mn > -INFINITY) {
+            float acc = ssum * fast_exp2((m - mn) * kLog2e);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc += fast_exp2((v[e] - mn) * kLog2e);
+            ssum = acc;
+            m = mn;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (v[e] > v2) {          // only the VALUES of the two largest elements are needed for tau
+                if (v[e] > v1) {
+                    v2 = v1;
+                    v1 = v[e];
+                } else {
+                    v2 = v[e];
+                }
+            }
+        }
     }
-    mx = warp_max(mx);
-    if (lane == 0) s_redv[warp] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float m = s_redv[0];
-        for (int w = 1; w < LS_THREADS / 32; ++w) m = fmaxf(m, s_redv[w]);
-        s_bcast = m;
+    float mx = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float part = (m > -INFINITY) ? ssum * fast_exp2((m - mx) * kLog2e) : 0.f;
+    part = warp_sum(part);
+    const float lse = mx + logf(part);
+
+    // tau: k-th largest of the 64 lane maxima
+    float tau = -INFINITY;
+    {
+        float h1 = v1, h2 = v2;
+        for (int r = 0; r < topk; ++r) {
+            float bv = h1;
+            int bl = lane;
+            lt_warp_best(bv, bl);
+            tau = bv;
+            if (bl == lane) {
+                h1 = h2;
+                h2 = -INFINITY;
+            }
+        }
     }
-    __syncthreads();
-    mx = s_bcast;
-    float sum = 0.f;
-    for (int i = threadIdx.x; i < V; i += LS_THREADS) sum += expf(s_row[i] - mx);
-    sum = warp_sum(sum);
-    __syncthreads();
-    if (lane == 0) s_redv[warp] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < LS_THREADS / 32; ++w) s += s_redv[w];
-        s_bcast = mx + logf(s);
+
+    // ---- pass 2: candidates >= tau ----
+    int count = 0;
+    for (int i0 = 0; i0 < n4; i0 += 32) {
+        const int i4 = i0 + lane;
+        float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (i4 < n4) {
+            load4(i4, v);
+            if (out_logp != nullptr) {
+                float* o = out_logp + row * ldl + 4 * i4;
+                if (4 * i4 + 3 < V) {
+                    *reinterpret_cast<float4*>(o) = make_float4(v[0] - lse, v[1] - lse, v[2] - lse, v[3] - lse);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * i4 + e < V) o[e] = v[e] - lse;
+                }
+            }
+        }
+        if (topk == 0) continue;   // warp-uniform
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool hit = (i4 < n4) && (4 * i4 + e < V) && (v[e] >= tau);
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int pos = count + __popc(bal & ((1u << lane) - 1));
+                if (pos < LT_CAP) {
+                    s_cv[warp][pos] = v[e];
+                    s_ci[warp][pos] = 4 * i4 + e;
+                }
+            }
+            count += __popc(bal);
+        }
     }
-    __syncthreads();
-    const float lse = s_bcast;
-    for (int i = threadIdx.x; i < V; i += LS_THREADS) {
-        const float lp = s_row[i] - lse;
-        s_row[i] = lp;
-        g[i] = lp;
-    }
-    __syncthreads();
-    // k rounds of block arg-max (ties -> lowest index), winner removed each round
-    for (int k = 0; k < topk; ++k) {
+    __syncwarp();
+
+    // ordered re-scans read the row again: after an in-place write-back it already holds normalised values
+    const bool inplace = (out_logp != nullptr);
+    const float* g2 = inplace ? out_logp + row * ldl : g;
+    const float pen2 = inplace ? 0.f : blank_penalty;
+    const float sub2 = inplace ? 0.f : lse;
+    float pv = INFINITY;
+    int pi = -1;
+    for (int r = 0; r < topk; ++r) {
         float bv = -INFINITY;
         int bi = 0x7fffffff;
-        for (int i = threadIdx.x; i < V; i += LS_THREADS) argmax_combine(bv, bi, s_row[i], i);
+        if (count <= LT_CAP) {
+            for (int c = lane; c < count; c += 32) {
+                const float v = s_cv[warp][c];
+                const int i = s_ci[warp][c];
+                if (lt_before(pv, pi, v, i) && lt_before(v, i, bv, bi)) {   // after the previous winner, best so far
+                    bv = v;
+                    bi = i;
+                }
+            }
+        } else {
+            for (int i4 = lane; i4 < n4; i4 += 32) {
+                float v[4];
+                load4_from(g2, pen2, i4, v);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            argmax_combine(bv, bi, ov, oi);
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 4 * i4 + e;
+                    if (i < V && lt_before(pv, pi, v[e], i) && lt_before(v[e], i, bv, bi)) {
+                        bv = v[e];
+                        bi = i;
+                    }
+                }
+            }
         }
+        lt_warp_best(bv, bi);
         if (lane == 0) {
-            s_redv[warp] = bv;
-            s_redi[warp] = bi;
+            topk_val[row * topk + r] = (count <= LT_CAP) ? bv - lse : bv - sub2;
+            topk_idx[row * topk + r] = (bi == 0x7fffffff) ? 0 : bi;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float v = s_redv[0];
-            int ix = s_redi[0];
-            for (int w = 1; w < LS_THREADS / 32; ++w) argmax_combine(v, ix, s_redv[w], s_redi[w]);
-            s_bcast = v;
-            s_bcasti = ix;
-            topk_val[row * topk + k] = v;
-            topk_idx[row * topk + k] = ix;
-            if (ix >= 0 && ix < V) s_row[ix] = -INFINITY;
-        }
-        __syncthreads();
+        pv = bv;
+        pi = bi;
     }
 }
 
@@ -124,23 +215,29 @@ __global__ void greedy_kernel(const int* __restrict__ topk_idx, int topk, const 
 
 }  // namespace
 
-int ctc_logsoftmax_topk(float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
-                        float* topk_val, int* topk_idx, cudaStream_t stream) {
+static int launch_lse_topk(const float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
+                           float* topk_val, int* topk_idx, float* out_logp, cudaStream_t stream) {
     if (M <= 0) return WB_OK;
     WB_REQUIRE(topk >= 0 && topk <= V, WB_ERR_BAD_ARG, "logsoftmax_topk: bad k=%d (V=%d)", topk, V);
-    const size_t smem = (size_t)V * sizeof(float);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        WB_REQUIRE(smem <= 200 * 1024, WB_ERR_UNSUPPORTED, "logsoftmax_topk: V=%d too large", V);
-        WB_CHECK_CUDA(cudaFuncSetAttribute(logsoftmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
-    ProfScope _ps(PT_LOGSOFTMAX_TOPK, stream, (double)M * V * 8.0);
-    logsoftmax_topk_kernel<<<M, LS_THREADS, smem, stream>>>(logits, ldl, V, blank_id, blank_penalty, topk, topk_val,
-                                                            topk_idx);
+    WB_REQUIRE(ldl % 4 == 0 && ldl >= (V + 3) / 4 * 4 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, WB_ERR_BAD_ARG,
+               "logsoftmax_topk: rows must be 16-byte aligned with pitch >= round_up(V, 4) (pitch %lld, V %d)", ldl, V);
+    WB_REQUIRE(topk == 0 || (topk_val && topk_idx), WB_ERR_BAD_ARG, "logsoftmax_topk: null top-k output");
+    ProfScope _ps(PT_LOGSOFTMAX_TOPK, stream, (double)M * V * (out_logp ? 8.0 : 4.0));
+    lse_topk_kernel<<<ceil_div(M, LT_WARPS), LT_WARPS * 32, 0, stream>>>(logits, ldl, M, V, blank_id, blank_penalty, topk,
+                                                                         topk_val, topk_idx, out_logp);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
+}
+
+int ctc_logsoftmax_topk(float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
+                        float* topk_val, int* topk_idx, cudaStream_t stream) {
+    return launch_lse_topk(logits, ldl, M, V, blank_id, blank_penalty, topk, topk_val, topk_idx, logits, stream);
+}
+
+int ctc_lse_topk(const float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
+                 float* topk_val, int* topk_idx, cudaStream_t stream) {
+    return launch_lse_topk(logits, ldl, M, V, blank_id, blank_penalty, topk, topk_val, topk_idx, nullptr, stream);
 }
 
 int ctc_greedy(const int* topk_idx, int topk, const int* seq_start, const int* seq_len, int batch, int blank_id,

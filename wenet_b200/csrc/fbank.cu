@@ -27,7 +27,7 @@ constexpr int MAX_NFFT = 512;
 
 struct FbankDev {
     const float* window;
-    const float* twiddle;    // nfft/4 complex: exp(-2*pi*i*k/(nfft/2)), k < nfft/4
+    const float* twiddle;    // nfft/2 complex: exp(-2*pi*i*k/(nfft/2)), k < nfft/2
     const float* twiddle_r;  // nfft/2+1 complex: exp(-2*pi*i*k/nfft)
     const int* mel_start;
     const int* mel_len;
@@ -38,6 +38,11 @@ struct FbankDev {
 };
 
 __device__ __forceinline__ int bitrev(int x, int bits) { return (int)(__brev((unsigned)x) >> (32 - bits)); }
+// base-4 digit reversal of a `bits`-bit index (bits even): bit reversal with the two bits of every digit swapped back
+__device__ __forceinline__ int digitrev4(int x, int bits) {
+    const unsigned r = __brev((unsigned)x) >> (32 - bits);
+    return (int)(((r & 0xAAAAAAAAu) >> 1) | ((r & 0x55555555u) << 1));
+}
 
 template <typename T>
 __device__ __forceinline__ float load_sample(const T* p, int i);
@@ -100,6 +105,7 @@ fbank_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, const 
     }
 
     const int log2half = 31 - __clz(half);
+    const bool radix4 = (log2half & 1) == 0;   // half is a power of 4
     for (int fi = warp; fi < FR; fi += nwarps) {
         const int f = f0 + fi;
         if (f >= max_frames) break;
@@ -124,28 +130,59 @@ fbank_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, const 
             w_fft[j] = y;  // natural order: (re, im) of z[j/2] interleaved == y itself
         }
         __syncwarp();
-        // 3. half-point complex FFT, radix-2 decimation-in-frequency (natural in, bit-reversed out)
-        for (int s = 0; s < log2half; ++s) {
-            const int hs = half >> (s + 1);  // butterfly half-span
-            for (int t = lane; t < half / 2; t += 32) {
-                const int grp = t / hs, pos = t - grp * hs;
-                const int i0 = grp * 2 * hs + pos, i1 = i0 + hs;
-                const int tw = pos << s;  // twiddle index in units of 2*pi/half
-                const float wr = P.twiddle[2 * tw], wi = P.twiddle[2 * tw + 1];
-                const float ar = w_fft[2 * i0], ai = w_fft[2 * i0 + 1];
-                const float br = w_fft[2 * i1], bi = w_fft[2 * i1 + 1];
-                w_fft[2 * i0] = ar + br;
-                w_fft[2 * i0 + 1] = ai + bi;
-                const float dr = ar - br, di = ai - bi;
-                w_fft[2 * i1] = dr * wr - di * wi;
-                w_fft[2 * i1 + 1] = dr * wi + di * wr;
+        // 3. half-point complex FFT, decimation in frequency (natural in, digit-reversed out).  half = 4^n (the 25 ms /
+        //    16 kHz front-end: 512-point real FFT -> 256 complex points) runs radix-4 on float2 elements: a quarter of
+        //    the shared-memory instructions of the radix-2 loop, which was bound by exactly those.
+        if (radix4) {
+            float2* z = reinterpret_cast<float2*>(w_fft);
+            const float2* twd = reinterpret_cast<const float2*>(P.twiddle);
+            for (int ns = half; ns >= 4; ns >>= 2) {
+                const int q = ns >> 2;             // quarter of the current sub-transform
+                const int tws = half / ns;         // twiddle stride: W_ns^j = W_half^(j * tws)
+                for (int t = lane; t < half / 4; t += 32) {
+                    const int grp = t / q, pos = t - grp * q;
+                    const int i0 = grp * ns + pos;
+                    const float2 x0 = z[i0], x1 = z[i0 + q], x2 = z[i0 + 2 * q], x3 = z[i0 + 3 * q];
+                    const float2 a0 = make_float2(x0.x + x2.x, x0.y + x2.y);
+                    const float2 a1 = make_float2(x0.x - x2.x, x0.y - x2.y);
+                    const float2 a2 = make_float2(x1.x + x3.x, x1.y + x3.y);
+                    const float2 a3 = make_float2(x1.y - x3.y, -(x1.x - x3.x));   // -i (x1 - x3)
+                    const float2 y0 = make_float2(a0.x + a2.x, a0.y + a2.y);
+                    const float2 y1 = make_float2(a1.x + a3.x, a1.y + a3.y);
+                    const float2 y2 = make_float2(a0.x - a2.x, a0.y - a2.y);
+                    const float2 y3 = make_float2(a1.x - a3.x, a1.y - a3.y);
+                    const float2 w1 = twd[pos * tws], w2 = twd[2 * pos * tws], w3 = twd[3 * pos * tws];
+                    z[i0] = y0;
+                    z[i0 + q] = make_float2(y1.x * w1.x - y1.y * w1.y, y1.x * w1.y + y1.y * w1.x);
+                    z[i0 + 2 * q] = make_float2(y2.x * w2.x - y2.y * w2.y, y2.x * w2.y + y2.y * w2.x);
+                    z[i0 + 3 * q] = make_float2(y3.x * w3.x - y3.y * w3.y, y3.x * w3.y + y3.y * w3.x);
+                }
+                __syncwarp();
             }
-            __syncwarp();
+        } else {
+            for (int s = 0; s < log2half; ++s) {
+                const int hs = half >> (s + 1);  // butterfly half-span
+                for (int t = lane; t < half / 2; t += 32) {
+                    const int grp = t / hs, pos = t - grp * hs;
+                    const int i0 = grp * 2 * hs + pos, i1 = i0 + hs;
+                    const int tw = pos << s;  // twiddle index in units of 2*pi/half
+                    const float wr = P.twiddle[2 * tw], wi = P.twiddle[2 * tw + 1];
+                    const float ar = w_fft[2 * i0], ai = w_fft[2 * i0 + 1];
+                    const float br = w_fft[2 * i1], bi = w_fft[2 * i1 + 1];
+                    w_fft[2 * i0] = ar + br;
+                    w_fft[2 * i0 + 1] = ai + bi;
+                    const float dr = ar - br, di = ai - bi;
+                    w_fft[2 * i1] = dr * wr - di * wi;
+                    w_fft[2 * i1 + 1] = dr * wi + di * wr;
+                }
+                __syncwarp();
+            }
         }
         // 4. real-FFT split + power:  X[k] = (Z[k] + conj(Z[h-k]))/2 - i*W^k*(Z[k] - conj(Z[h-k]))/2
         for (int k = lane; k <= half; k += 32) {
-            const int ka = bitrev(k & (half - 1), log2half);
-            const int kb = bitrev((half - k) & (half - 1), log2half);
+            const int ka = radix4 ? digitrev4(k & (half - 1), log2half) : bitrev(k & (half - 1), log2half);
+            const int kb = radix4 ? digitrev4((half - k) & (half - 1), log2half)
+                                  : bitrev((half - k) & (half - 1), log2half);
             const float zr = w_fft[2 * ka], zi = w_fft[2 * ka + 1];
             const float yr = w_fft[2 * kb], yi = -w_fft[2 * kb + 1];  // conj(Z[h-k])
             const float er = 0.5f * (zr + yr), ei = 0.5f * (zi + yi);
@@ -187,8 +224,8 @@ int fbank_plan_create(FbankPlan** out, int sample_rate, int num_mel, int frame_l
     p->nfft = nfft;
     p->preemph = preemph;
     const int half = nfft / 2;
-    std::vector<float> tw(2 * (half / 2)), twr(2 * (half + 1));
-    for (int k = 0; k < half / 2; ++k) {
+    std::vector<float> tw(2 * half), twr(2 * (half + 1));   // radix-4 needs W^k up to k < 3 half / 4
+    for (int k = 0; k < half; ++k) {
         const double a = -2.0 * M_PI * k / half;
         tw[2 * k] = (float)cos(a);
         tw[2 * k + 1] = (float)sin(a);

@@ -39,7 +39,10 @@ struct GemmCfg {
     static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator (power of two)
     // epilogue staging: 8 warps x (32 rows x 128 B), SWIZZLE_128B, read back by TMA stores
     static constexpr int kOutBytes = 8 * 4096;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    // bias staging: 2 tile parities x BN floats (<= 2 KB), then 256 B of barriers; the dynamic smem window is declared
+    // 1024-aligned, so no alignment slack is needed
+    static constexpr int kBiasBytes = 2 * 256 * 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kBiasBytes + 256 /*barriers*/;
     // weight-stationary mode (K <= kResMaxKB * 64): the whole [BN x K] weight panel of the current n-tile
     // stays in shared memory while the CTA streams A tiles past it -> per tile only the 128 x K A tile is
     // fetched from L2 (the per-SM L2 path, ~80 GB/s, is what bounds the K = 256 GEMMs otherwise)
@@ -67,21 +70,36 @@ struct GemmParams {
 };
 constexpr int kConvRows = 114;   // 6 x 19
 
-template <int BN, bool BRES>
+// Stall accounting (wb_gemm_diag): cycles one lane of each role spent waiting, summed over CTAs and launches.
+//   0 producer: ring slot not free      1 MMA: operands not landed     2 MMA: accumulator stage not drained
+//   3 epilogue: accumulator not ready   4 epilogue: staging buffer still being read by a TMA store
+//   5 epilogue: total time in the tile loop (warp 2)   6 CTA lifetime   7 tiles
+__device__ unsigned long long g_gemm_diag[12];   // 8: epilogue tcgen05.ld wait, 9: bias + activation, 10: staging stores + TMA issue
+#define WB_TIMED_WAIT(slot, call)            \
+    do {                                     \
+        const long long _t0 = clock64();     \
+        call;                                \
+        diag[slot] += clock64() - _t0;       \
+    } while (0)
+
+// EPI >= 0 fixes the epilogue at compile time (the kernel is ~150 KB of SASS with all six variants behind a runtime
+// switch and then stalls on instruction fetch); EPI = -1 keeps the runtime switch (BN = 128: small / test models only).
+template <int BN, bool BRES, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                     GemmParams p) {
     using Cfg = GemmCfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-B alignment
     constexpr int kRing = BRES ? Cfg::kResAStages : Cfg::kStages;   // A (or A+B) ring depth
     uint8_t* smem_a = BRES ? smem + Cfg::kResBBytes : smem;
     uint8_t* smem_b = BRES ? smem : smem + Cfg::kStages * Cfg::kABytes;
     uint8_t* smem_out = smem + Cfg::kStages * Cfg::kStageBytes;   // 1024-aligned (stage sizes are multiples of 1024)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes);
+    float* smem_bias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes + Cfg::kBiasBytes);
     uint64_t* full_bar = bars;                // [kRing]
     uint64_t* empty_bar = bars + 8;           // [kRing]
     uint64_t* tmem_full = bars + 16;          // [2]
@@ -95,6 +113,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int num_kb = (p.K + BK - 1) / BK;
+    const int epi = (EPI >= 0) ? EPI : p.epi;
+    long long diag[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long cta_t0 = clock64();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -153,7 +174,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 int conv_t = 0;
                 if (!BRES && p.conv) conv_t = __ldg(&p.tile_tab[m_tile]).x;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    WB_TIMED_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
                     if (!BRES && p.conv) {
                         const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                         const int kh = tap / 3, kw = tap - 3 * kh;
@@ -192,11 +213,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     bfull_phase ^= 1;
                     cur_n = n_tile;
                 }
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                WB_TIMED_WAIT(2, mbar_wait(&tmem_empty[acc], acc_phase ^ 1));
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    WB_TIMED_WAIT(1, mbar_wait(&full_bar[stage], phase));
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
                     const uint32_t b_addr = smem_u32(smem_b + (BRES ? kb : stage) * Cfg::kBBytes);
@@ -232,6 +253,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         int acc = 0;
         uint32_t acc_phase = 0;
         bool need_wait = false;
+        int tile_par = 0;
+        const long long epi_t0 = clock64();
         for (int t = t_begin; t < t_end; t += t_step) {
             WB_TILE_COORDS(t)
             long long row_base = (long long)m_tile * BM;
@@ -247,32 +270,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // last tile of an utterance falls back to guarded register stores
             const bool warp_tma = p.use_tma_out && (n_in == 32 || n_in == 18);
             const CUtensorMap* cmap = (n_in == 18) ? &tmap_c2 : &tmap_c;
-            mbar_wait(&tmem_full[acc], acc_phase);
+            // this warp's slice of the bias (kChunksPerWarp x 32 columns) is fetched before the accumulator wait and
+            // parked in shared memory (one copy per tile parity; the four warps of a column half write identical
+            // values), so the chunk loop reads it with broadcast LDS instead of an L2 round trip per chunk
+            float4 bpre = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int bcol = n_tile * BN + half * (kChunksPerWarp * 32) + 4 * lane;
+            if (p.bias != nullptr && 4 * lane < kChunksPerWarp * 32) {
+                if (bcol + 0 < p.N) bpre.x = __ldg(p.bias + bcol + 0);
+                if (bcol + 1 < p.N) bpre.y = __ldg(p.bias + bcol + 1);
+                if (bcol + 2 < p.N) bpre.z = __ldg(p.bias + bcol + 2);
+                if (bcol + 3 < p.N) bpre.w = __ldg(p.bias + bcol + 3);
+            }
+            float* sbias = smem_bias + (tile_par * 256 + half * (kChunksPerWarp * 32));
+            WB_TIMED_WAIT(3, mbar_wait(&tmem_full[acc], acc_phase));
             tc_fence_after();
+            if (4 * lane < kChunksPerWarp * 32) *reinterpret_cast<float4*>(sbias + 4 * lane) = bpre;
+            __syncwarp();
+            tile_par ^= 1;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-            for (int c = half * kChunksPerWarp; c < (half + 1) * kChunksPerWarp; ++c) {
+            // software pipeline over the warp's 32-column chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c
+            // goes through bias / activation / staging (two register sets, loop fully unrolled)
+            uint32_t rbuf[2][32];
+            constexpr int c_begin_rel = 0;
+            const int c0 = half * kChunksPerWarp;
+            if (n_tile * BN + c0 * 32 < p.N) tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c0 * 32), rbuf[0]);
+#pragma unroll
+            for (int ci = c_begin_rel; ci < kChunksPerWarp; ++ci) {
+                const int c = c0 + ci;
                 const int n0 = n_tile * BN + c * 32;
                 if (n0 >= p.N) break;  // warp-uniform
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
-                tmem_ld_wait();
+                uint32_t (&r)[32] = rbuf[ci & 1];
+                WB_TIMED_WAIT(8, tmem_ld_wait_regs(r));
+                const long long t_math0 = clock64();
+                if (ci + 1 < kChunksPerWarp && n0 + 32 < p.N)
+                    tmem_ld_32x32b_x32(taddr0 + (uint32_t)((c + 1) * 32), rbuf[(ci + 1) & 1]);
                 float v[32];
                 const bool full = (n0 + 32 <= p.N);
                 if (p.bias != nullptr) {
-                    if (full) {
+                    const float* sb = sbias + ci * 32;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-                            v[i] = __uint_as_float(r[i]) + b4.x;
-                            v[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
-                            v[i + 2] = __uint_as_float(r[i + 2]) + b4.z;
-                            v[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            v[i] = __uint_as_float(r[i]) + ((n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f);
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(sb + i);
+                        v[i] = __uint_as_float(r[i]) + b4.x;
+                        v[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
+                        v[i + 2] = __uint_as_float(r[i + 2]) + b4.z;
+                        v[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
                     }
                 } else {
 #pragma unroll
@@ -282,15 +324,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     // ---- staged epilogue: registers -> swizzled smem (row = lane, 128 B) -> TMA ----
                     // rows >= M and columns >= N are clipped by the tensor map, so no guards are needed.
                     uint8_t* sbuf = smem_out + (warp - 2) * 4096 + lane * 128;
-                    if (need_wait) {  // the previous TMA store of this warp must have finished reading the buffer
-                        if (lane == 0) tma_store_wait_read<0>();
-                        __syncwarp();
-                        need_wait = false;
-                    }
+                    // the previous TMA store of this warp must have finished reading the staging buffer before it is
+                    // overwritten; the check sits after the activation math so that latency is hidden behind it
+                    auto staging_ready = [&]() {
+                        if (need_wait) {
+                            WB_TIMED_WAIT(4, if (lane == 0) tma_store_wait_read<0>(); __syncwarp());
+                            need_wait = false;
+                        }
+                    };
                     const int sw = lane & 7;
+                    long long t_st0 = 0;
                     bool flush = false;
                     int out_col = 0;
-                    if (p.epi == EPI_F32 || p.epi == EPI_RESID_F32) {
+                    if (epi == EPI_F32 || epi == EPI_RESID_F32) {
+                        diag[9] += clock64() - t_math0;
+                        staging_ready();
+                        t_st0 = clock64();
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
                             *reinterpret_cast<float4*>(sbuf + ((u ^ sw) << 4)) =
@@ -298,7 +347,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                             p.alpha * v[4 * u + 3]);
                         flush = true;
                         out_col = n0;
-                    } else if (p.epi == EPI_GLU_BF16) {
+                    } else if (epi == EPI_GLU_BF16) {
                         float g[16];
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
@@ -308,6 +357,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             g[i + 2] *= v[i + 2];
                             g[i + 3] *= v[i + 3];
                         }
+                        diag[9] += clock64() - t_math0;
+                        staging_ready();
+                        t_st0 = clock64();
 #pragma unroll
                         for (int u = 0; u < 2; ++u)
                             *reinterpret_cast<uint4*>(sbuf + ((((c & 3) * 2 + u) ^ sw) << 4)) =
@@ -316,19 +368,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         flush = ((c & 3) == 3) || (n0 + 32 >= p.N);
                         out_col = (n_tile * BN + (c & ~3) * 32) >> 1;
                     } else {
-                        if (p.epi == EPI_BF16_SILU) {
+                        if (epi == EPI_BF16_SILU) {
                             silu_inplace(v);
-                        } else if (p.epi == EPI_BF16_RELU) {
+                        } else if (epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
+                        if (p.alpha != 1.0f) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                        }
+                        diag[9] += clock64() - t_math0;
+                        staging_ready();
+                        t_st0 = clock64();
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             *reinterpret_cast<uint4*>(sbuf + ((((c & 1) * 4 + u) ^ sw) << 4)) = make_uint4(
-                                pack_bf16x2(p.alpha * v[8 * u], p.alpha * v[8 * u + 1]),
-                                pack_bf16x2(p.alpha * v[8 * u + 2], p.alpha * v[8 * u + 3]),
-                                pack_bf16x2(p.alpha * v[8 * u + 4], p.alpha * v[8 * u + 5]),
-                                pack_bf16x2(p.alpha * v[8 * u + 6], p.alpha * v[8 * u + 7]));
+                                pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
                         flush = ((c & 1) == 1) || (n0 + 32 >= p.N);
                         out_col = n_tile * BN + (c & ~1) * 32;
                     }
@@ -338,7 +395,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         if (lane == 0) {
                             const void* src = smem_out + (warp - 2) * 4096;
                             const int row0 = (int)row_base + q * 32;
-                            if (p.epi == EPI_RESID_F32)
+                            if (epi == EPI_RESID_F32)
                                 tma_reduce_add_2d(cmap, src, out_col, row0);
                             else
                                 tma_store_2d(cmap, src, out_col, row0);
@@ -346,17 +403,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         }
                         need_wait = true;
                     }
+                    diag[10] += clock64() - t_st0;
                     continue;
                 }
                 if (!row_ok) continue;
 
-                switch (p.epi) {
+                switch (epi) {
                     case EPI_BF16:
                     case EPI_BF16_SILU:
                     case EPI_BF16_RELU: {
-                        if (p.epi == EPI_BF16_SILU) {
+                        if (epi == EPI_BF16_SILU) {
                             silu_inplace(v);
-                        } else if (p.epi == EPI_BF16_RELU) {
+                        } else if (epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
@@ -473,9 +531,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
         }
         if (p.use_tma_out && lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores
+        diag[5] = clock64() - epi_t0;
     }
 
 #undef WB_TILE_COORDS
+    if (lane == 0 && warp <= 2) {   // one lane per role: producer (0), MMA issuer (1), first epilogue warp (2)
+        for (int i = 0; i < 12; ++i)
+            if (i != 6 && i != 7 && diag[i] != 0) atomicAdd(&g_gemm_diag[i], (unsigned long long)diag[i]);
+        if (warp == 0) {
+            atomicAdd(&g_gemm_diag[6], (unsigned long long)(clock64() - cta_t0));
+            int nt = 0;
+            for (int t = t_begin; t < t_end; t += t_step) ++nt;
+            atomicAdd(&g_gemm_diag[7], (unsigned long long)nt);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -487,13 +556,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 int g_num_sms = 0;
 int g_sm_reserve = 0;  // SMs left free for concurrently running latency-bound kernels on other streams
 
-template <int BN, bool BRES>
+template <int BN, bool BRES, int EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
                 const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, BRES>,
+        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, BRES, EPI>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
@@ -506,7 +575,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     const int usable = (g_num_sms - g_sm_reserve) > 1 ? (g_num_sms - g_sm_reserve) : 1;
     const int grid = tiles < usable ? tiles : usable;
     ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
-    gemm_tcgen05_kernel<BN, BRES><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
+    gemm_tcgen05_kernel<BN, BRES, EPI><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
@@ -574,11 +643,25 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
     p.tile_tab = nullptr;
     const int num_kb = ceil_div(K, BK);
     if (bn == 256) {
-        if (num_kb <= GemmCfg<256>::kResMaxKB) return launch_gemm<256, true>(ta, *tb, tc, tc, p, stream);
-        return launch_gemm<256, false>(ta, *tb, tc, tc, p, stream);
+        const bool res = num_kb <= GemmCfg<256>::kResMaxKB;
+        switch (epi) {
+#define WB_GEMM_CASE(E)                                                                  \
+    case E:                                                                              \
+        return res ? launch_gemm<256, true, E>(ta, *tb, tc, tc, p, stream)               \
+                   : launch_gemm<256, false, E>(ta, *tb, tc, tc, p, stream);
+            WB_GEMM_CASE(EPI_BF16)
+            WB_GEMM_CASE(EPI_BF16_SILU)
+            WB_GEMM_CASE(EPI_BF16_RELU)
+            WB_GEMM_CASE(EPI_RESID_F32)
+            WB_GEMM_CASE(EPI_GLU_BF16)
+            WB_GEMM_CASE(EPI_F32)
+#undef WB_GEMM_CASE
+            default:
+                WB_REQUIRE(false, WB_ERR_BAD_ARG, "gemm: unknown epilogue %d", epi);
+        }
     }
-    if (num_kb <= GemmCfg<128>::kResMaxKB) return launch_gemm<128, true>(ta, *tb, tc, tc, p, stream);
-    return launch_gemm<128, false>(ta, *tb, tc, tc, p, stream);
+    if (num_kb <= GemmCfg<128>::kResMaxKB) return launch_gemm<128, true, -1>(ta, *tb, tc, tc, p, stream);
+    return launch_gemm<128, false, -1>(ta, *tb, tc, tc, p, stream);
 }
 
 // Conv2d(d -> d, 3x3, stride 2) + bias + ReLU over the channels-last conv1 output, as an implicit GEMM:
@@ -614,7 +697,16 @@ int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, con
     p.conv = 1;
     p.cblocks = d / 64;
     p.tile_tab = reinterpret_cast<const int4*>(tile_tab_dev);
-    return launch_gemm<256, false>(ta, *tmap_w, tc, tc18, p, stream);
+    return launch_gemm<256, false, EPI_BF16_RELU>(ta, *tmap_w, tc, tc18, p, stream);
+}
+
+int gemm_diag(unsigned long long* out8, int reset) {
+    if (out8) WB_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_gemm_diag, sizeof(unsigned long long) * 12));
+    if (reset) {
+        unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        WB_CHECK_CUDA(cudaMemcpyToSymbol(g_gemm_diag, z, sizeof(z)));
+    }
+    return WB_OK;
 }
 
 }  // namespace wb

@@ -28,6 +28,9 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
               int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
               cudaStream_t stream);
 
+// stall accounting of gemm_tcgen05_kernel (see gemm.cu); out8 may be null
+int gemm_diag(unsigned long long* out8, int reset);
+
 // Conv2d(d->d, 3x3, s2) + ReLU as an implicit GEMM whose A tiles are fetched by 3-D strided TMA boxes (no im2col buffer)
 int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, const CUtensorMap* tmap_w, const float* bias,
                         const void* tile_tab_dev /*int4 per tile*/, int num_tiles, long long rows_out, void* out2,
@@ -130,6 +133,9 @@ int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream);
 // in-place log-softmax over V of logits [M, ldl] (+ optional blank penalty), plus per-row top-k.
 int ctc_logsoftmax_topk(float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty,
                         int topk, float* topk_val, int* topk_idx, cudaStream_t stream);
+// top-k of the log-softmax (values normalised) without writing the matrix back; logits are left untouched
+int ctc_lse_topk(const float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
+                 float* topk_val, int* topk_idx, cudaStream_t stream);
 // greedy collapse: per sequence, frames [start, start+len) of top-1 ids (stride topk)
 int ctc_greedy(const int* topk_idx, int topk, const int* seq_start, const int* seq_len, int batch,
                int blank_id, int* out_tokens, int out_stride, int* out_len, cudaStream_t stream);

@@ -115,6 +115,17 @@ def logsoftmax_topk(logits, V, topk, blank_id=0, blank_penalty=0.0):
     return tv, ti
 
 
+def lse_topk(logits, V, topk, blank_id=0, blank_penalty=0.0):
+    """(topk_val, topk_idx) of log_softmax(logits[:, :V]) without touching `logits`."""
+    _need_cuda(logits)
+    M = logits.shape[0]
+    tv = torch.empty(M, topk, device=logits.device, dtype=torch.float32)
+    ti = torch.empty(M, topk, device=logits.device, dtype=torch.int32)
+    check(_lib.load().wb_op_lse_topk(ptr(logits), logits.stride(0), M, V, blank_id, float(blank_penalty), topk, ptr(tv),
+                                     ptr(ti), cur_stream()), "wb_op_lse_topk")
+    return tv, ti
+
+
 def ctc_greedy_search(topk_idx, seq_start, seq_len, blank_id=0):
     _need_cuda(topk_idx)
     batch = seq_start.numel()
