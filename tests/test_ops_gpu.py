@@ -112,7 +112,7 @@ def test_layernorm(d):
     _close(ob, ref, 2 ** -8, 1e-5)
 
 
-def _attn_ref(q, k, v, kbias, q_start, q_len, k_start, k_len, heads, chunk, left, scale):
+def _attn_ref(q, k, v, kbias, q_start, q_len, k_start, k_len, heads, chunk, left, scale, round_p=False):
     out = torch.zeros(q.shape[0], heads * 64)
     for b in range(len(q_start)):
         qs, ql, ks, kl = q_start[b], q_len[b], k_start[b], k_len[b]
@@ -131,7 +131,9 @@ def _attn_ref(q, k, v, kbias, q_start, q_len, k_start, k_len, heads, chunk, left
                 end = (i // chunk + 1) * chunk
                 S = S.masked_fill(~((j >= start) & (j < end)), -float("inf"))
             mx = S.max(dim=-1, keepdim=True).values
-            P = torch.exp(S - mx).to(torch.bfloat16).float()
+            P = torch.exp(S - mx)
+            if round_p:
+                P = P.to(torch.bfloat16).float()
             out[qs:qs + ql, h * 64:(h + 1) * 64] = (P @ V) / P.sum(-1, keepdim=True)
     return out
 
@@ -140,7 +142,7 @@ def _attn_ref(q, k, v, kbias, q_start, q_len, k_start, k_len, heads, chunk, left
 @pytest.mark.parametrize("case", ["self_full", "self_chunk", "causal", "cross"])
 def test_attention(case, v_mode):
     from wenet_b200 import ops
-    g = torch.Generator().manual_seed(hash(case) % 1000)
+    g = torch.Generator().manual_seed({"self_full": 11, "self_chunk": 12, "causal": 13, "cross": 14}[case])
     heads = 2
     if case == "cross":
         q_len, k_len = [37, 260, 5], [200, 333, 129]
@@ -165,7 +167,13 @@ def test_attention(case, v_mode):
                         heads, kbias.to(_dev()) if kbias is not None else None, chunk, left, scale,
                         v_mode=v_mode, max_q_len=max(q_len))
     torch.cuda.synchronize()
-    _close(out.cpu(), ref, 2 ** -7, 2e-3)
+    # exact fp32 softmax reference.  The kernel rounds the probabilities to bf16 (2^-9 relative each, relative to a
+    # lazily updated running maximum, so the rounding pattern cannot be replayed on the host): the worst case is
+    # 2^-8 max|v| per output, the typical error is an order of magnitude below that.
+    diff = (out.cpu().float() - ref).abs()
+    bound = 2 ** -7 * ref.abs() + 2 ** -8 * float(v.float().abs().max())
+    assert not (diff > bound).any(), "max diff %g" % diff.max().item()
+    assert diff.mean().item() < 1e-3, diff.mean().item()
 
 
 def test_relpos_kprep():

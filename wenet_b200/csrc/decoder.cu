@@ -72,33 +72,62 @@ struct RsDev {
     int* best;
 };
 
-// one thread per utterance (<= 16 hyps x ~100 tokens of sequential fp32 adds, as the reference does)
-__global__ void rescore_kernel(RsDev P, int batch) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
-    const int h0 = P.utt_hyp0[b], nh = P.utt_nhyp[b];
-    float best_score = -INFINITY;
-    int best_i = 0;
-    for (int i = 0; i < nh; ++i) {
-        const int hy = h0 + i;
-        const int r0 = P.hyp_row0[hy], ln = P.hyp_len[hy];
-        float score = 0.f;
-        for (int j = 0; j <= ln; ++j) score += P.l2r[r0 + j];  // tokens then <eos>
-        if (P.reverse_weight > 0.f && P.r2l != nullptr) {
-            float r_score = 0.f;
-            // r_decoder_out[i][len-j-1][hyp[j]] for j = 0..len-1 (search.py:438-441), then eos
-            for (int j = 0; j < ln; ++j) r_score += P.r2l[r0 + (ln - j - 1)];
-            r_score += P.r2l[r0 + ln];
-            score = score * (1.f - P.reverse_weight) + r_score * P.reverse_weight;
-        }
-        score += (float)(P.ctc_score[hy] * (double)P.ctc_weight);
-        P.hyp_score[hy] = score;
-        if (score > best_score) {
-            best_score = score;
-            best_i = i;
-        }
+// Score combine of search.py:421-452.  The reference adds the token log-probs of a hypothesis one by one in fp32
+// (score += ...), so the ORDER is kept: a warp per hypothesis loads 32 values at a time in parallel and then every
+// lane replays the same sequential chain of additions through shuffles (a serial thread per utterance spent 340 us
+// in dependent global loads).  One CTA per utterance; the first maximum wins (strict >, search.py:448).
+constexpr int RS_WARPS = 8;
+
+__device__ __forceinline__ float seq_sum(const float* __restrict__ src, int n, bool reversed_head, int ln, int lane) {
+    // sum_{j < n} src[idx(j)], idx(j) = j, or for the r2l branch (ln - 1 - j) for j < ln and ln for j == ln
+    float acc = 0.f;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        float v = 0.f;
+        if (j < n) v = src[reversed_head ? ((j < ln) ? (ln - 1 - j) : ln) : j];
+        const int m = min(32, n - j0);
+        for (int i = 0; i < m; ++i) acc += __shfl_sync(0xffffffffu, v, i);
     }
-    P.best[b] = best_i;
+    return acc;
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32) rescore_kernel(RsDev P, int batch) {
+    __shared__ float s_score[64];
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h0 = P.utt_hyp0[b], nh = P.utt_nhyp[b];
+    for (int base = 0; base < nh; base += 64) {       // 64 hypotheses per round (beam sizes beyond that loop)
+        const int cnt = min(64, nh - base);
+        for (int i = warp; i < cnt; i += RS_WARPS) {
+            const int hy = h0 + base + i;
+            const int r0 = P.hyp_row0[hy], ln = P.hyp_len[hy];
+            float score = seq_sum(P.l2r + r0, ln + 1, false, ln, lane);   // tokens then <eos>
+            if (P.reverse_weight > 0.f && P.r2l != nullptr) {
+                // r_decoder_out[i][len-j-1][hyp[j]] for j = 0..len-1 (search.py:438-441), then eos
+                const float r_score = seq_sum(P.r2l + r0, ln + 1, true, ln, lane);
+                score = score * (1.f - P.reverse_weight) + r_score * P.reverse_weight;
+            }
+            score += (float)(P.ctc_score[hy] * (double)P.ctc_weight);
+            if (lane == 0) {
+                P.hyp_score[hy] = score;
+                s_score[i] = score;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float best_score = (base == 0) ? -INFINITY : P.hyp_score[h0 + P.best[b]];
+            int best_i = (base == 0) ? 0 : P.best[b];
+            for (int i = 0; i < cnt; ++i)
+                if (s_score[i] > best_score) {
+                    best_score = s_score[i];
+                    best_i = base + i;
+                }
+            P.best[b] = best_i;
+        }
+        __syncthreads();
+    }
+    if (nh == 0 && threadIdx.x == 0) P.best[b] = 0;
 }
 
 }  // namespace
@@ -141,7 +170,7 @@ int rescore_combine(const RescoreArgs& a, cudaStream_t stream) {
     P.hyp_score = a.hyp_score;
     P.best = a.best;
     ProfScope _ps(PT_RESCORE, stream, 0.0);
-    rescore_kernel<<<ceil_div(a.batch, 64), 64, 0, stream>>>(P, a.batch);
+    rescore_kernel<<<a.batch, RS_WARPS * 32, 0, stream>>>(P, a.batch);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
