@@ -67,6 +67,7 @@ struct GemmParams {
     int conv;
     int cblocks;            // d / 64
     const int4* tile_tab;   // per m-tile: .x t coordinate of tap kh = 0, .y first output row, .z valid rows (<= 114)
+    float2* lse_part;       // EPI_LSE: [M][2 * num_n_tiles]
 };
 constexpr int kConvRows = 114;   // 6 x 19
 
@@ -291,6 +292,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // software pipeline over the warp's 32-column chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c
             // goes through bias / activation / staging (two register sets, loop fully unrolled)
             uint32_t rbuf[2][32];
+            float lse_m = -INFINITY, lse_s = 0.f;   // EPI_LSE: running (max, sum) over this warp's columns, log2 domain
             constexpr int c_begin_rel = 0;
             const int c0 = half * kChunksPerWarp;
             if (n_tile * BN + c0 * 32 < p.N) tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c0 * 32), rbuf[0]);
@@ -319,6 +321,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                }
+                if (epi == EPI_LSE) {
+                    constexpr float kLog2e = 1.4426950408889634f;
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = (full || n0 + i < p.N) ? v[i] * kLog2e : -INFINITY;
+                        cm = fmaxf(cm, v[i]);
+                    }
+                    const float mn = fmaxf(lse_m, cm);
+                    float acc_s = (lse_m == -INFINITY) ? 0.f : lse_s * fast_exp2(lse_m - mn);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc_s += fast_exp2(v[i] - mn);
+                    lse_s = acc_s;
+                    lse_m = mn;
+                    continue;
                 }
                 if (warp_tma) {
                     // ---- staged epilogue: registers -> swizzled smem (row = lane, 128 B) -> TMA ----
@@ -521,6 +539,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     } break;
                 }
             }
+            if (epi == EPI_LSE && row_ok)
+                p.lse_part[row * (2 * p.num_n_tiles) + n_tile * 2 + half] = make_float2(lse_m, lse_s);
             // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -591,9 +611,9 @@ int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K) {
     return make_tmap_2d_bf16(out, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)gemm_bn_for(N), BK);
 }
 
-int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
-              int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
-              cudaStream_t stream) {
+static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
+                     int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
+                     float2* lse_part, cudaStream_t stream) {
     if (M <= 0) return WB_OK;
     WB_REQUIRE(N > 0 && K > 0, WB_ERR_BAD_ARG, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     WB_REQUIRE((K % 8) == 0 && (lda % 8) == 0, WB_ERR_BAD_ARG,
@@ -633,7 +653,7 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
     const bool f32_out = (epi == EPI_RESID_F32 || epi == EPI_F32);
     const int out_cols = (epi == EPI_GLU_BF16) ? N / 2 : N;
     const int eb = f32_out ? 4 : 2;
-    p.use_tma_out = (!split3 && (ldc * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    p.use_tma_out = (epi != EPI_LSE && !split3 && (ldc * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
     if (p.use_tma_out) {
         rc = make_tmap_2d(&tc, out, eb, (uint64_t)M, (uint64_t)out_cols, (uint64_t)ldc, 32, f32_out ? 32 : 64);
         if (rc != WB_OK) return rc;
@@ -641,6 +661,7 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
     p.conv = 0;
     p.cblocks = 0;
     p.tile_tab = nullptr;
+    p.lse_part = lse_part;
     const int num_kb = ceil_div(K, BK);
     if (bn == 256) {
         const bool res = num_kb <= GemmCfg<256>::kResMaxKB;
@@ -655,6 +676,7 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
             WB_GEMM_CASE(EPI_RESID_F32)
             WB_GEMM_CASE(EPI_GLU_BF16)
             WB_GEMM_CASE(EPI_F32)
+            WB_GEMM_CASE(EPI_LSE)
 #undef WB_GEMM_CASE
             default:
                 WB_REQUIRE(false, WB_ERR_BAD_ARG, "gemm: unknown epilogue %d", epi);
@@ -662,6 +684,21 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
     }
     if (num_kb <= GemmCfg<128>::kResMaxKB) return launch_gemm<128, true, -1>(ta, *tb, tc, tc, p, stream);
     return launch_gemm<128, false, -1>(ta, *tb, tc, tc, p, stream);
+}
+
+int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
+              int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
+              cudaStream_t stream) {
+    WB_REQUIRE(epi != EPI_LSE, WB_ERR_BAD_ARG, "gemm: EPI_LSE goes through gemm_lse_partials");
+    return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, epi, alpha, out, ldc, split3, nullptr, stream);
+}
+
+int lse_parts(int N) { return 2 * ceil_div(N, gemm_bn_for(N)); }
+
+int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N, int K,
+                      const float* bias, float2* part, cudaStream_t stream) {
+    WB_REQUIRE(part != nullptr, WB_ERR_BAD_ARG, "gemm_lse_partials: null output");
+    return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, EPI_LSE, 1.0f, part /*unused as matrix*/, 0, 0, part, stream);
 }
 
 // Conv2d(d -> d, 3x3, stride 2) + bias + ReLU over the channels-last conv1 output, as an implicit GEMM:
@@ -694,6 +731,7 @@ int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, con
     p.use_tma_out = 1;
     p.num_m_tiles = num_tiles;
     p.num_n_tiles = d / 256;
+    p.lse_part = nullptr;
     p.conv = 1;
     p.cblocks = d / 64;
     p.tile_tab = reinterpret_cast<const int4*>(tile_tab_dev);

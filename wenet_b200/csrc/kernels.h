@@ -15,6 +15,7 @@ enum GemmEpi : int {
     EPI_RESID_F32 = 3,  // out_f32 += alpha * (acc + bias)      (in-place residual stream update)
     EPI_GLU_BF16 = 4,   // out_bf16[:, N/2] = a * sigmoid(g), weight rows packed [16 a | 16 g] x N/32
     EPI_F32 = 5,        // out_f32  = alpha * (acc + bias)
+    EPI_LSE = 6,        // no matrix output: per (row, 128-column half tile) partial log-sum-exp (max2, sum) of acc + bias
 };
 
 int gemm_bn_for(int N);
@@ -27,6 +28,12 @@ int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K);
 int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
               int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
               cudaStream_t stream);
+
+// log-softmax denominators without the logits: part[row][2 * n_tiles] = (max of v log2 e, sum 2^(v log2 e - max)) over each
+// 128-column half of each n-tile of v = A B^T + bias.  lse_parts() = entries per row for a given N.
+int lse_parts(int N);
+int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N, int K,
+                      const float* bias, float2* part, cudaStream_t stream);
 
 // stall accounting of gemm_tcgen05_kernel (see gemm.cu); out8 may be null
 int gemm_diag(unsigned long long* out8, int reset);
@@ -161,6 +168,9 @@ int embed_tokens(const int* tokens, const int* pos, int R, int d, const float* e
 // tok_logp[r] = logits[r, target[r]] - logsumexp(logits[r, :V])   (target < 0 -> 0)
 int gather_logprob(const float* logits, long long ldl, int R, int V, const int* target, float* tok_logp,
                    cudaStream_t stream);
+// tok_logp[r] = (a[r] . W[target[r]] + bias[target[r]]) - logsumexp_r, the latter from gemm_lse_partials (target < 0 -> 0)
+int lse_target_logprob(const float2* part, int n_parts, const void* a_bf16, long long lda, const void* w_bf16, int d,
+                       const float* bias, const int* target, int R, int V, float* tok_logp, cudaStream_t stream);
 // per utterance rescoring combine (wenet search.py:421-452)
 struct RescoreArgs {
     const float* l2r;  const float* r2l;  // [R] token log-probs, rows hyp-major, (len+1) per hyp

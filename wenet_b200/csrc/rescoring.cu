@@ -38,7 +38,8 @@ void rs_layout(const Model* m, long long enc_rows, long long R, int batch, int n
     P->o_q = o; o += align_up((size_t)R * d * 2);
     P->o_h = o; o += align_up((size_t)R * ff * 2);
     P->o_memkv = o; o += align_up((size_t)enc_rows * 2 * d * 2);
-    P->o_logits = o; o += align_up((size_t)R * P->ldl * 4);
+    // rescoring never materialises the [R, V] logits: the output GEMM leaves per-tile log-sum-exp partials only
+    P->o_logits = o; o += align_up((size_t)R * lse_parts(m->cfg.vocab) * sizeof(float2));
     P->total = o + 256;
 }
 
@@ -55,9 +56,11 @@ struct RsDevPtrs {
 };
 
 // one direction of the decoder: x = embed(tokens); layers; after_norm; logits = out(x)
+// Output: either the raw logits [R][ldl] (logits != null; decoder_logprobs API) or, for rescoring, only
+// tok_logp[r] = log_softmax(logits[r])[target[r]] via LSE partials (logits == null).
 int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPtrs& dp, const int* tokens,
-                const void* enc_bf16, long long enc_rows, uint8_t* ws, float* logits, long long ldl,
-                cudaStream_t st) {
+                const void* enc_bf16, long long enc_rows, uint8_t* ws, float* logits, long long ldl, const int* target,
+                float* tok_logp, cudaStream_t st) {
     const wb_model_config& c = m->cfg;
     const int d = c.d_model, ff = c.dec_ffn_dim, H = c.dec_heads;
     const int R = (int)P.R;
@@ -117,7 +120,13 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
         }
     }
     RC(layernorm_rows(x, d, R, d, D.after.g, D.after.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-    RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, ldl, 0, st));
+    if (logits != nullptr) {
+        RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, ldl, 0, st));
+    } else {
+        float2* part = reinterpret_cast<float2*>(ws + P.o_logits);
+        RC(gemm_lse_partials(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, part, st));
+        RC(lse_target_logprob(part, lse_parts(c.vocab), a, d, D.out.w, d, D.out.b, target, R, c.vocab, tok_logp, st));
+    }
     return WB_OK;
 }
 
@@ -279,14 +288,12 @@ static int attention_rescoring_impl(const wb_model* mm, const void* enc_out_bf16
     RsDevPtrs dp;
     RC(prepare(m, enc_rows, seq_start_host, seq_len_host, batch, n_hyp, hyp_utt_host, hyp_len_host, hyp_tok0_host,
                hyp_tokens, tokens_on_device, ctc_score_host, sos, eos, ws, workspace_bytes, &P, &dp, st));
-    float* logits = reinterpret_cast<float*>(ws + P.o_logits);
-    RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, logits, P.ldl, st));
-    RC(gather_logprob(logits, P.ldl, (int)P.R, m->cfg.vocab, dp.tgt_l2r, tok_logp_l2r_dev, st));
+    RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, nullptr, 0, dp.tgt_l2r, tok_logp_l2r_dev, st));
     const bool use_r2l = reverse_weight > 0.f && m->cfg.rdec_layers > 0;
     if (use_r2l) {
         WB_REQUIRE(tok_logp_r2l_dev, WB_ERR_BAD_ARG, "attention_rescoring: r2l output buffer missing");
-        RC(run_decoder(m, m->right, P, dp, dp.tok_r2l, enc_out_bf16_dev, enc_rows, ws, logits, P.ldl, st));
-        RC(gather_logprob(logits, P.ldl, (int)P.R, m->cfg.vocab, dp.tgt_r2l, tok_logp_r2l_dev, st));
+        RC(run_decoder(m, m->right, P, dp, dp.tok_r2l, enc_out_bf16_dev, enc_rows, ws, nullptr, 0, dp.tgt_r2l, tok_logp_r2l_dev,
+                       st));
     }
     RescoreArgs a;
     a.l2r = tok_logp_l2r_dev;
@@ -347,10 +354,10 @@ int wb_decoder_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_
     RsDevPtrs dp;
     RC(prepare(m, enc_rows, seq_start_host, seq_len_host, batch, n_hyp, hyp_utt_host, hyp_len_host, hyp_tok0_host,
                hyp_tokens_host, false, nullptr, sos, eos, ws, workspace_bytes, &P, &dp, st));
-    RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, logp_dev, ldl, st));
+    RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, logp_dev, ldl, nullptr, nullptr, st));
     RC(ctc_logsoftmax_topk(logp_dev, ldl, (int)P.R, m->cfg.vocab, -1, 0.f, 0, nullptr, nullptr, st));
     if (use_r2l && m->cfg.rdec_layers > 0 && r_logp_dev) {
-        RC(run_decoder(m, m->right, P, dp, dp.tok_r2l, enc_out_bf16_dev, enc_rows, ws, r_logp_dev, ldl, st));
+        RC(run_decoder(m, m->right, P, dp, dp.tok_r2l, enc_out_bf16_dev, enc_rows, ws, r_logp_dev, ldl, nullptr, nullptr, st));
         RC(ctc_logsoftmax_topk(r_logp_dev, ldl, (int)P.R, m->cfg.vocab, -1, 0.f, 0, nullptr, nullptr, st));
     }
     return WB_OK;
