@@ -158,6 +158,16 @@ int wb_encoder_forward_chunk(const wb_model* m, const float* xs_dev, int T, int 
                              const float* cnn_cache_dev, float* y_dev, float* r_att_cache_dev,
                              float* r_cnn_cache_dev, int* out_chunk, int* out_new_cache_t1,
                              void* workspace_dev, size_t workspace_bytes, wb_stream_t stream);
+/* Capture-safe form of the same step for CUDA graphs (steady-state streaming: T, cache_t1 and the buffers are
+ * fixed, only the position changes): issues no host -> device copy and no synchronisation, reads the position
+ * offset from offset_dev (device int32; positions are clamped to the table), and expects the workspace to have been
+ * used by a regular wb_encoder_forward_chunk call with the same T / cache_t1 before (that call leaves the small
+ * shape block in it).  Capture it once (e.g. torch.cuda.CUDAGraph), then per chunk: write xs / offset, replay. */
+int wb_encoder_forward_chunk_static(const wb_model* m, const float* xs_dev, int T, const int32_t* offset_dev,
+                                    int required_cache_size, const float* att_cache_dev, int cache_t1,
+                                    const float* cnn_cache_dev, float* y_dev, float* r_att_cache_dev,
+                                    float* r_cnn_cache_dev, void* workspace_dev, size_t workspace_bytes,
+                                    wb_stream_t stream);
 
 /* packed [M][d] -> padded [batch][t_stride][d] (rows past seq_len zeroed) and back */
 int wb_unpack_rows(const float* packed_dev, const int32_t* seq_start_dev, const int32_t* seq_len_dev,

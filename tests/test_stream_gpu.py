@@ -49,3 +49,31 @@ def test_forward_chunk_vs_reference_golden():
     res = model.decode(["ctc_greedy_search"], xs[0:1, :n0], lens[0:1].cuda(), decoding_chunk_size=c,
                        num_decoding_left_chunks=l, simulate_streaming=True)
     assert len(res["ctc_greedy_search"]) == 1
+
+
+def test_streaming_session_graph_replay_is_bit_identical():
+    """StreamingSession replays the steady-state chunk step as a CUDA graph (wb_encoder_forward_chunk_static: position
+    offset read on the device, caches rotated by captured copies); outputs must equal forward_chunk() bit for bit."""
+    from wenet_b200.asr_model import B200ASRModel, StreamingSession
+    cfg = synth.recipe("tiny")
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    model = B200ASRModel(cfg, sd, with_decoder=False)
+    chunk, left = 4, 2
+    window, stride = (chunk - 1) * 4 + 7, 4 * chunk
+    n_chunks = 12
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(1, stride * n_chunks + window, 80, generator=g).cuda()
+    att = torch.zeros(0, 0, 0, 0, device="cuda")
+    cnn = torch.zeros(0, 0, 0, 0, device="cuda")
+    sess = StreamingSession(model, chunk, left)
+    offset = 0
+    replayed = 0
+    for i in range(n_chunks):
+        xs = feats[:, i * stride:i * stride + window]
+        y_ref, att, cnn = model.encoder.forward_chunk(xs, offset, chunk * left, att, cnn)
+        offset += y_ref.size(1)
+        y = sess.step(xs).clone()
+        replayed += int(sess.graph is not None)
+        assert torch.equal(y, y_ref), (i, (y - y_ref).abs().max().item())
+    assert replayed >= n_chunks - left - 1      # everything after the cache filled up went through the graph
+    assert torch.equal(sess.s_att, att) and torch.equal(sess.s_cnn, cnn)

@@ -15,7 +15,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from wenet_b200 import _lib, synth  # noqa: E402
-from wenet_b200.asr_model import B200ASRModel  # noqa: E402
+from wenet_b200.asr_model import B200ASRModel, StreamingSession  # noqa: E402
 
 
 def main():
@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=16)
     ap.add_argument("--left", type=int, default=4, help="left chunks kept in the attention cache")
     ap.add_argument("--ctc", action="store_true", help="include the CTC head + per-chunk top-k in the timed region")
+    ap.add_argument("--graph", action="store_true", help="steady-state chunk step replayed as a CUDA graph (StreamingSession)")
     a = ap.parse_args()
     cfg = synth.recipe("u2pp_small")
     model = B200ASRModel(cfg, synth.synth_state_dict(cfg, seed=777), with_decoder=False)
@@ -41,10 +42,14 @@ def main():
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(total)]
     offset = 0
     n0 = lib.wb_launch_count()
+    sess = StreamingSession(model, chunk, a.left) if a.graph else None
     for i in range(total):
         xs = feats[:, i * stride:i * stride + window]
         evs[i][0].record()
-        y, att, cnn = enc.forward_chunk(xs, offset, chunk * a.left, att, cnn)
+        if sess is not None:
+            y = sess.step(xs)
+        else:
+            y, att, cnn = enc.forward_chunk(xs, offset, chunk * a.left, att, cnn)
         if a.ctc:
             model.ctc.log_softmax(y)
         evs[i][1].record()
@@ -56,7 +61,7 @@ def main():
            "p50_ms": float(np.percentile(ms, 50)), "p99_ms": float(np.percentile(ms, 99)), "mean_ms": float(ms.mean()),
            "chunks": a.chunks, "warmup": a.warmup, "audio_s_per_chunk": chunk * 0.04,
            "chunk_rtf": float(np.percentile(ms, 50)) / 1e3 / (chunk * 0.04), "launches_per_chunk": launches,
-           "with_ctc": bool(a.ctc)}
+           "with_ctc": bool(a.ctc), "cuda_graph": bool(a.graph)}
     print(json.dumps(out))
 
 

@@ -101,6 +101,83 @@ class B200ConformerEncoder:
         return ys, masks
 
 
+class StreamingSession:
+    """Chunk-by-chunk streaming of ONE utterance through encoder.forward_chunk with the steady-state step replayed
+    as a CUDA graph (the step is ~220 small launches: launch-bound on the host otherwise).
+
+    Mirrors the loop of BaseEncoder.forward_chunk_by_chunk (encoder.py:302-362): call step(xs_chunk) with the
+    (1, (chunk-1)*4+7, 80) feature window of each chunk; it returns y (1, chunk, d).  The first chunks (attention
+    cache still growing) go through the regular call; once the cache has its final size the step is captured with
+    static buffers and replayed - outputs are bit-identical to forward_chunk().
+    """
+
+    def __init__(self, model: "B200ASRModel", decoding_chunk_size: int, num_decoding_left_chunks: int,
+                 use_graph: bool = True):
+        assert decoding_chunk_size > 0
+        self.m = model
+        self.chunk = decoding_chunk_size
+        self.required = decoding_chunk_size * num_decoding_left_chunks   # < 0: unbounded history (never steady)
+        self.window = (decoding_chunk_size - 1) * 4 + 7
+        self.use_graph = use_graph and self.required > 0 and model.spec.cnn_causal
+        self.offset = 0
+        dev = model.device
+        self.att = torch.zeros(0, 0, 0, 0, device=dev)
+        self.cnn = torch.zeros(0, 0, 0, 0, device=dev)
+        self.graph = None
+        self._warm = 0
+
+    def _capture(self):
+        m, spec, lib = self.m, self.m.spec, self.m._lib
+        dev = m.device
+        L, H, d, K = spec.enc_layers, spec.heads, spec.d_model, spec.cnn_kernel
+        T, c1 = self.window, self.required
+        self.s_xs = torch.zeros(T, 80, device=dev, dtype=torch.float32)
+        self.s_att = self.att.to(torch.float32).contiguous().clone()          # (L, H, c1, 128)
+        self.s_cnn = self.cnn.to(torch.float32).contiguous().clone()          # (L, 1, d, K-1)
+        self.s_ratt = torch.empty_like(self.s_att)
+        self.s_rcnn = torch.empty_like(self.s_cnn)
+        self.s_y = torch.empty(1, self.chunk, d, device=dev, dtype=torch.float32)
+        self.s_off = torch.zeros(1, device=dev, dtype=torch.int32)   # position offset, advanced by the graph itself
+        wsb = lib.wb_encoder_chunk_workspace_bytes(m.dm.handle, T, c1)
+        self.s_ws = torch.empty(int(wsb) + 1024, device=dev, dtype=torch.uint8)
+        oc, on = C.c_int(0), C.c_int(0)
+        # a regular call leaves the shape block in the workspace (and warms every kernel's one-time attribute set-up)
+        check(lib.wb_encoder_forward_chunk(m.dm.handle, ptr(self.s_xs), T, int(self.offset), int(self.required),
+                                           ptr(self.s_att), c1, ptr(self.s_cnn), ptr(self.s_y), ptr(self.s_ratt),
+                                           ptr(self.s_rcnn), C.byref(oc), C.byref(on), ptr(self.s_ws), self.s_ws.numel(),
+                                           cur_stream()), "wb_encoder_forward_chunk")
+        assert oc.value == self.chunk and on.value == c1
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            check(lib.wb_encoder_forward_chunk_static(m.dm.handle, ptr(self.s_xs), T, ptr(self.s_off), int(self.required),
+                                                      ptr(self.s_att), c1, ptr(self.s_cnn), ptr(self.s_y),
+                                                      ptr(self.s_ratt), ptr(self.s_rcnn), ptr(self.s_ws),
+                                                      self.s_ws.numel(), cur_stream()), "wb_encoder_forward_chunk_static")
+            self.s_att.copy_(self.s_ratt)     # the new caches are the next step's inputs
+            self.s_cnn.copy_(self.s_rcnn)
+            self.s_off.add_(self.chunk)
+        self.s_off.fill_(self.offset)
+        self.graph = g
+
+    def step(self, xs: torch.Tensor) -> torch.Tensor:
+        m = self.m
+        assert xs.size(0) == 1 and xs.size(1) == self.window, "steady streaming expects full windows"
+        steady = self.use_graph and self.att.numel() > 0 and self.att.size(2) == self.required
+        if steady and self.offset + self.chunk > m.spec.max_pos:
+            raise _lib.WbError("utterance longer than the positional table")
+        if not steady:
+            y, self.att, self.cnn = m._forward_chunk(xs, self.offset, self.required, self.att, self.cnn)
+            self.offset += y.size(1)
+            return y
+        if self.graph is None:
+            self._capture()
+        self.s_xs.copy_(xs[0], non_blocking=True)
+        self.graph.replay()
+        self.offset += self.chunk
+        return self.s_y            # static buffer: consume (or clone) before the next step
+
+
 class B200ASRModel:
     """U2 / U2++ model (ConformerEncoder + CTC + (Bi)TransformerDecoder) on libwenet_b200.so."""
 

@@ -422,10 +422,14 @@ size_t wb_encoder_chunk_workspace_bytes(const wb_model* mm, int T, int cache_t1)
     return P.total;
 }
 
-int wb_encoder_forward_chunk(const wb_model* mm, const float* xs_dev, int T, int offset, int required_cache_size,
-                             const float* att_cache_dev, int cache_t1, const float* cnn_cache_dev, float* y_dev,
-                             float* r_att_cache_dev, float* r_cnn_cache_dev, int* out_chunk, int* out_new_cache_t1,
-                             void* workspace_dev, size_t workspace_bytes, wb_stream_t stream) {
+// offset_dev != nullptr selects the capture-safe form (wb_encoder_forward_chunk_static): no host -> device copy, no
+// stream synchronisation; the position offset is read on the device and the small meta block must already be in the
+// workspace (written by an earlier regular call with the same T / cache_t1 / workspace).
+static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, int T, int offset, const int* offset_dev,
+                                      int required_cache_size, const float* att_cache_dev, int cache_t1,
+                                      const float* cnn_cache_dev, float* y_dev, float* r_att_cache_dev,
+                                      float* r_cnn_cache_dev, int* out_chunk, int* out_new_cache_t1, void* workspace_dev,
+                                      size_t workspace_bytes, wb_stream_t stream) {
     const Model* m = reinterpret_cast<const Model*>(mm);
     WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "forward_chunk: model not finalized");
     WB_REQUIRE(xs_dev && y_dev && r_att_cache_dev && workspace_dev, WB_ERR_BAD_ARG, "forward_chunk: null argument");
@@ -438,7 +442,7 @@ int wb_encoder_forward_chunk(const wb_model* mm, const float* xs_dev, int T, int
     WB_REQUIRE(P.chunk > 0, WB_ERR_BAD_ARG, "forward_chunk: %d input frames give no output frame", T);
     WB_REQUIRE(workspace_bytes >= P.total, WB_ERR_WORKSPACE, "forward_chunk: workspace %zu < required %zu",
                workspace_bytes, P.total);
-    WB_REQUIRE(offset - cache_t1 >= 0 && offset + P.chunk <= c.max_pos, WB_ERR_BAD_ARG,
+    WB_REQUIRE(offset_dev != nullptr || (offset - cache_t1 >= 0 && offset + P.chunk <= c.max_pos), WB_ERR_BAD_ARG,
                "forward_chunk: positions [%d, %d) outside the positional table", offset - cache_t1, offset + P.chunk);
     const int chunk = P.chunk, key_size = P.key_size, lead = P.lead;
     int nxt;
@@ -454,8 +458,10 @@ int wb_encoder_forward_chunk(const wb_model* mm, const float* xs_dev, int T, int
     struct { int v[6]; long long z[2]; } meta;
     meta.v[0] = P.t1n; meta.v[1] = chunk; meta.v[2] = 0; meta.v[3] = key_size; meta.v[4] = lead + chunk; meta.v[5] = 0;
     meta.z[0] = 0; meta.z[1] = 0;
-    WB_CHECK_CUDA(cudaMemcpyAsync(ws + P.o_meta, &meta, sizeof(meta), cudaMemcpyHostToDevice, st));
-    WB_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (offset_dev == nullptr) {
+        WB_CHECK_CUDA(cudaMemcpyAsync(ws + P.o_meta, &meta, sizeof(meta), cudaMemcpyHostToDevice, st));
+        WB_CHECK_CUDA(cudaStreamSynchronize(st));
+    }
     const int* d_t1n = reinterpret_cast<const int*>(ws + P.o_meta);
     const int* d_chunk = d_t1n + 1;
     const int* d_zero = d_t1n + 2;
@@ -488,7 +494,7 @@ int wb_encoder_forward_chunk(const wb_model* mm, const float* xs_dev, int T, int
                  d, 0, st));
     RC(gemm_bf16(out2, (long long)m->F2 * d, &m->embed_out.tmap, m->embed_out.w, chunk, d, m->F2 * d, m->embed_out.b,
                  EPI_F32, sqrtf((float)d), x, d, 0, st));
-    RC(fill_row_pos(d_zero, d_key, 1, offset - cache_t1, d_row_pos, key_size, st));
+    RC(fill_row_pos(d_zero, d_key, 1, (offset_dev ? 0 : offset) - cache_t1, d_row_pos, key_size, st, offset_dev, c.max_pos));
     const float att_scale = 1.0f / sqrtf(64.0f);
     const size_t att_l = (size_t)H * cache_t1 * 128, ratt_l = (size_t)H * (key_size - nxt) * 128;
     const size_t cnn_l = (size_t)d * lead;
@@ -545,6 +551,26 @@ int wb_encoder_forward_chunk(const wb_model* mm, const float* xs_dev, int T, int
     }
     RC(layernorm_rows(x, d, chunk, d, m->after.g, m->after.b, c.ln_eps, nullptr, 0, 0, y_dev, d, st));
     return WB_OK;
+}
+
+int wb_encoder_forward_chunk(const wb_model* mm, const float* xs_dev, int T, int offset, int required_cache_size,
+                             const float* att_cache_dev, int cache_t1, const float* cnn_cache_dev, float* y_dev,
+                             float* r_att_cache_dev, float* r_cnn_cache_dev, int* out_chunk, int* out_new_cache_t1,
+                             void* workspace_dev, size_t workspace_bytes, wb_stream_t stream) {
+    return encoder_forward_chunk_impl(mm, xs_dev, T, offset, nullptr, required_cache_size, att_cache_dev, cache_t1,
+                                      cnn_cache_dev, y_dev, r_att_cache_dev, r_cnn_cache_dev, out_chunk, out_new_cache_t1,
+                                      workspace_dev, workspace_bytes, stream);
+}
+
+int wb_encoder_forward_chunk_static(const wb_model* mm, const float* xs_dev, int T, const int32_t* offset_dev,
+                                    int required_cache_size, const float* att_cache_dev, int cache_t1,
+                                    const float* cnn_cache_dev, float* y_dev, float* r_att_cache_dev,
+                                    float* r_cnn_cache_dev, void* workspace_dev, size_t workspace_bytes,
+                                    wb_stream_t stream) {
+    WB_REQUIRE(offset_dev != nullptr, WB_ERR_BAD_ARG, "forward_chunk_static: null offset pointer");
+    return encoder_forward_chunk_impl(mm, xs_dev, T, 0, offset_dev, required_cache_size, att_cache_dev, cache_t1,
+                                      cnn_cache_dev, y_dev, r_att_cache_dev, r_cnn_cache_dev, nullptr, nullptr,
+                                      workspace_dev, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -185,6 +185,6 @@ int rescore_combine(const RescoreArgs& a, cudaStream_t stream);
 
 // small utility kernels (util.cu)
 int fill_row_pos(const int* seq_start, const int* seq_len, int batch, int pos_offset, int* row_pos,
-                 int max_len, cudaStream_t stream);
+                 int max_len, cudaStream_t stream, const int* pos_offset_dev = nullptr, int max_pos = 0x7fffffff);
 
 }  // namespace wb
