@@ -230,7 +230,8 @@ def main():
                     choices=["attention_rescoring", "ctc_prefix_beam_search", "ctc_greedy_search"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event profiler")
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the GEMM / FFN kernels leave free (-1: 8 when in flight > 1)")
+    ap.add_argument("--inflight", type=int, default=3,
                     help="batches in flight per GPU (host threads x CUDA streams sharing one weight replica); "
                          "1 = strictly sequential steps")
     args = ap.parse_args()
@@ -292,7 +293,7 @@ def main():
     n_slots = max(1, args.inflight)
     if n_slots > 1:
         sys.setswitchinterval(5e-4)   # the slot threads hand the GIL over between (GIL-releasing) C-ABI calls
-    lib.wb_set_sm_reserve(8 if n_slots > 1 else 0)   # room for the other batch's search kernel (batch/8 CTAs)
+    lib.wb_set_sm_reserve(args.sm_reserve if args.sm_reserve >= 0 else (8 if n_slots > 1 else 0))   # room for the other batch's search kernel (batch/8 CTAs)
     slot_models = [model] + [model.clone_shared() for _ in range(n_slots - 1)]
     slot_streams = [torch.cuda.Stream(device=dev) for _ in range(n_slots)]
 
@@ -357,17 +358,28 @@ def main():
     torch.cuda.synchronize()
     n_tok = sum(len(r.tokens) for r in res[args.mode])
 
-    # ---- device-resident timing (headline `value`) with the per-kernel profiler on ----
+    # ---- device-resident timing (headline `value`): profiler off, all slots in flight ----
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.wb_launch_count()
-    if not args.no_profile:
-        lib.wb_prof_reset()
-        lib.wb_prof_enable(1)
     ms = timed(lambda i, mdl: step(dev_pcm[i % NROT], mdl), args.steps)
     launches = lib.wb_launch_count() - launches0
+
+    # ---- per-kernel pass (roofline / kernel table): CUDA events around every launch, ONE batch in flight so that the
+    #      durations are not stretched by kernels of other batches sharing the SMs ----
     prof = None
+    prof_steps = 0
     if not args.no_profile:
+        prof_steps = max(2, min(args.steps, 4))
+        lib.wb_set_sm_reserve(0)
+        lib.wb_prof_reset()
+        lib.wb_prof_enable(1)
+        torch.cuda.synchronize()
+        t_p0 = time.perf_counter()
+        for i in range(prof_steps):
+            step(dev_pcm[i % NROT], model)
+        torch.cuda.synchronize()
+        prof_ms = 1e3 * (time.perf_counter() - t_p0)
         lib.wb_prof_enable(0)
         nt = lib.wb_prof_num_tags()
         pms, pwork, pl = (C.c_double * nt)(), (C.c_double * nt)(), (C.c_longlong * nt)()
@@ -375,6 +387,7 @@ def main():
         prof = {lib.wb_prof_tag_name(t).decode(): {"ms": pms[t], "work": pwork[t], "launches": int(pl[t])}
                 for t in range(nt) if pl[t] > 0}
         lib.wb_prof_reset()
+        lib.wb_set_sm_reserve(args.sm_reserve if args.sm_reserve >= 0 else (8 if n_slots > 1 else 0))
 
     # ---- end to end: pinned host PCM -> H2D -> decode -> results on host ----
     def e2e_step(i, mdl):
@@ -420,14 +433,25 @@ def main():
         g = {"ms": sum(v["ms"] for v in fam), "work": sum(v["work"] for v in fam),
              "launches": sum(v["launches"] for v in fam)}
         ach = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        traffic, traffic_of = None, None
+        try:   # DRAM bytes per launch of the family's largest member, from the committed `ncu --set full` capture
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_traffic.json")) as f:
+                tj = json.load(f)
+            traffic, traffic_of = tj["traffic_bytes_per_launch"], tj["kernel"]
+        except (OSError, KeyError, ValueError):
+            pass
         line["roofline"] = {"kernel": "tcgen05 GEMM family: gemm_tcgen05_kernel (Linear / pointwise-conv / im2col-conv) + "
                                       "ffn_fused_kernel (W1+SiLU+W2)",
                             "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                            "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + " (sustained bf16)",
+                            "frac": ach / peaks["tf_sust"], "traffic": traffic, "traffic_of": traffic_of,
+                            "peak_source": peaks["src"] + " (sustained bf16)",
                             "launches": g["launches"], "avg_launch_us": 1e3 * g["ms"] / max(g["launches"], 1),
-                            "share_of_step": g["ms"] / ms}
+                            "share_of_step": g["ms"] / prof_ms,
+                            "measured": "CUDA events around every launch of the family, %d extra steps with one batch in "
+                                        "flight right after the timed region (%.2f ms/step in that pass)"
+                                        % (prof_steps, prof_ms / prof_steps)}
         tot = sum(v["ms"] for v in prof.values())
-        line["kernels"] = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+        line["kernels"] = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
                                "share": v["ms"] / tot,
                                **({"GBps": v["work"] / (v["ms"] * 1e-3) / 1e9} if (v["work"] > 0 and "tcgen05" not in k) else {}),
                                **({"TFLOPs": v["work"] / (v["ms"] * 1e-3) / 1e12} if (v["work"] > 0 and "tcgen05" in k) else {})}
