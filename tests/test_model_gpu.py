@@ -279,9 +279,10 @@ def test_conv2_implicit_gemm_ragged_tiles():
 
 
 def test_rescoring_host_and_device_token_entry_points_agree(setup):
-    """wb_attention_rescoring (hypothesis tokens in host memory, the reference's data flow) and
-    wb_attention_rescoring_dev (tokens read from the beam search's device buffer, what decode() uses) run the same
-    decoder on the same rows -> identical scores and choices."""
+    """wb_attention_rescoring (hypothesis tokens in host memory: what decode() uses; the library then computes decoder
+    rows with a common input prefix ONCE per utterance) and wb_attention_rescoring_dev (tokens read from the beam
+    search's device buffer, every row of every hypothesis computed) are the same function of the same inputs ->
+    bit-identical scores and choices.  This is the exactness check of the prefix sharing."""
     from wenet_b200._lib import check, cur_stream, load, ptr
     name, cfg, sd, model, feats, lens, g = setup
     beam = int(g["beam"])
@@ -303,10 +304,11 @@ def test_rescoring_host_and_device_token_entry_points_agree(setup):
     wsb = lib.wb_rescoring_workspace_bytes(model.dm.handle, eo.rows, R)
     ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
     use_r2l = rw > 0 and model.spec.bidirectional
-    check(lib.wb_attention_rescoring(model.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host), ptr(eo.lens_host), B,
-                                     n_hyp, ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks), ptr(ctc), model.sos,
-                                     model.eos, 0.5, float(rw if use_r2l else 0.0), ptr(l2r), ptr(r2l), ptr(hs), ptr(best),
-                                     ptr(ws), wsb, cur_stream()), "wb_attention_rescoring")
+    toks_dev = torch.from_numpy(toks).to(dev)
+    check(lib.wb_attention_rescoring_dev(model.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host), ptr(eo.lens_host), B,
+                                         n_hyp, ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks_dev), ptr(ctc),
+                                         model.sos, model.eos, 0.5, float(rw if use_r2l else 0.0), ptr(l2r), ptr(r2l),
+                                         ptr(hs), ptr(best), ptr(ws), wsb, cur_stream()), "wb_attention_rescoring_dev")
     hs, best = hs.cpu().numpy(), best.cpu().numpy()
     h = 0
     for b, r in enumerate(res["attention_rescoring"]):

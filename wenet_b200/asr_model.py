@@ -15,6 +15,7 @@ tensors must live on a CUDA device.
 """
 import ctypes as C
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
 
@@ -417,7 +418,7 @@ class B200ASRModel:
                 fetch = self._beam_fetch_async(bd, meta)
                 rs = None
                 if "attention_rescoring" in methods:
-                    rs = self._rescore_launch(eo, bd, meta, ctc_weight, reverse_weight)
+                    rs = self._rescore_launch(eo, bd, meta, fetch, ctc_weight, reverse_weight)
                 beam_out = self._beam_results(bd, meta, fetch)
                 if "ctc_prefix_beam_search" in methods:
                     results["ctc_prefix_beam_search"] = beam_out
@@ -550,8 +551,10 @@ class B200ASRModel:
             toks = [0]
         return _i32(hyp_utt), _i32(hyp_len), _i32(hyp_tok0), _i32(toks)
 
-    def _rescore_launch(self, eo: _EncOut, bd, meta, ctc_weight: float, reverse_weight: float):
-        """search.py:374-458; hypotheses are read from the beam search's device buffer"""
+    def _rescore_launch(self, eo: _EncOut, bd, meta, fetch, ctc_weight: float, reverse_weight: float):
+        """search.py:374-458.  The n-best token ids (a few hundred KB, already on their way to pinned host memory for the
+        result objects) are handed to the library on the host side, which lets it share decoder rows between
+        hypotheses with a common prefix; WB_RESCORE_DEVICE_TOKENS=1 keeps them on the device (no sharing)."""
         if not self.dm.has_decoder:
             raise _lib.WbError("attention_rescoring needs decoder weights")
         lib = self._lib
@@ -566,12 +569,23 @@ class B200ASRModel:
         best = torch.zeros(B, device=self.device, dtype=torch.int32)
         wsb = lib.wb_rescoring_workspace_bytes(self.dm.handle, eo.rows, R)
         ws = self._workspace(wsb)
-        check(lib.wb_attention_rescoring_dev(self.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host),
+        if os.environ.get("WB_RESCORE_DEVICE_TOKENS"):
+            check(lib.wb_attention_rescoring_dev(self.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host),
+                                                 ptr(eo.lens_host), B, n_hyp, ptr(meta.hyp_utt), ptr(meta.hyp_len),
+                                                 ptr(meta.hyp_src), ptr(bd.toks), ptr(meta.scores), self.sos, self.eos,
+                                                 float(ctc_weight), float(reverse_weight if rs.use_r2l else 0.0), ptr(l2r),
+                                                 ptr(r2l), ptr(hyp_score), ptr(best), ptr(ws), ws.numel(), cur_stream()),
+                  "wb_attention_rescoring_dev")
+        else:
+            th, _, ev = fetch
+            ev.synchronize()                                   # token ids have landed in pinned host memory
+            tok0 = np.ascontiguousarray((meta.slot * th.shape[2]).astype(np.int32))   # hyp h starts at th[b, rank, 0]
+            check(lib.wb_attention_rescoring(self.dm.handle, ptr(eo.bf16), eo.rows, ptr(eo.starts_host),
                                              ptr(eo.lens_host), B, n_hyp, ptr(meta.hyp_utt), ptr(meta.hyp_len),
-                                             ptr(meta.hyp_src), ptr(bd.toks), ptr(meta.scores), self.sos, self.eos,
+                                             ptr(tok0), ptr(th), ptr(meta.scores), self.sos, self.eos,
                                              float(ctc_weight), float(reverse_weight if rs.use_r2l else 0.0), ptr(l2r),
                                              ptr(r2l), ptr(hyp_score), ptr(best), ptr(ws), ws.numel(), cur_stream()),
-              "wb_attention_rescoring_dev")
+                  "wb_attention_rescoring")
         rs.l2r = self._d2h_async("rs_l2r", l2r)
         rs.r2l = self._d2h_async("rs_r2l", r2l) if rs.use_r2l else None
         rs.hs = self._d2h_async("rs_score", hyp_score)

@@ -65,16 +65,18 @@ gather_logprob_kernel(const float* __restrict__ logits, long long ldl, int V, co
 __global__ void __launch_bounds__(256)
 lse_target_kernel(const float2* __restrict__ part, int n_parts, const __nv_bfloat16* __restrict__ a, long long lda,
                   const __nv_bfloat16* __restrict__ w, int d, const float* __restrict__ bias,
-                  const int* __restrict__ target, int R, int V, float* __restrict__ tok_logp) {
+                  const int* __restrict__ target, const int* __restrict__ row_map, int R, int V,
+                  float* __restrict__ tok_logp) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= R) return;
+    const int src = row_map ? row_map[row] : row;   // decoder state row that produced this position (prefix sharing)
     const int tg = target[row];
     if (tg < 0 || tg >= V) {
         if (lane == 0) tok_logp[row] = 0.f;
         return;
     }
-    const float2* pr = part + (long long)row * n_parts;
+    const float2* pr = part + (long long)src * n_parts;
     float m = -INFINITY;
     for (int i = lane; i < n_parts; i += 32) m = fmaxf(m, pr[i].x);
     m = warp_max(m);
@@ -86,7 +88,7 @@ lse_target_kernel(const float2* __restrict__ part, int n_parts, const __nv_bfloa
     ssum = warp_sum(ssum);
     const float lse = (m + log2f(ssum)) * 0.6931471805599453f;   // back from the log2 domain
     // target logit: bf16 x bf16 products, fp32 accumulation (the tensor core's contract)
-    const __nv_bfloat16* ar = a + (long long)row * lda;
+    const __nv_bfloat16* ar = a + (long long)src * lda;
     const __nv_bfloat16* wr = w + (long long)tg * d;
     float dot = 0.f;
     for (int c = lane * 8; c < d; c += 256) {
@@ -202,13 +204,14 @@ int gather_logprob(const float* logits, long long ldl, int R, int V, const int* 
 }
 
 int lse_target_logprob(const float2* part, int n_parts, const void* a_bf16, long long lda, const void* w_bf16, int d,
-                       const float* bias, const int* target, int R, int V, float* tok_logp, cudaStream_t stream) {
+                       const float* bias, const int* target, const int* row_map, int R, int V, float* tok_logp,
+                       cudaStream_t stream) {
     if (R <= 0) return WB_OK;
     WB_REQUIRE(d % 8 == 0 && lda % 8 == 0, WB_ERR_BAD_ARG, "lse_target_logprob: d / lda must be multiples of 8");
     ProfScope _ps(PT_GATHER_LOGPROB, stream, (double)R * (n_parts * 8.0 + d * 4.0));
     lse_target_kernel<<<ceil_div(R, 8), 256, 0, stream>>>(part, n_parts, reinterpret_cast<const __nv_bfloat16*>(a_bf16), lda,
                                                           reinterpret_cast<const __nv_bfloat16*>(w_bf16), d, bias, target,
-                                                          R, V, tok_logp);
+                                                          row_map, R, V, tok_logp);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

@@ -170,7 +170,8 @@ int gather_logprob(const float* logits, long long ldl, int R, int V, const int* 
                    cudaStream_t stream);
 // tok_logp[r] = (a[r] . W[target[r]] + bias[target[r]]) - logsumexp_r, the latter from gemm_lse_partials (target < 0 -> 0)
 int lse_target_logprob(const float2* part, int n_parts, const void* a_bf16, long long lda, const void* w_bf16, int d,
-                       const float* bias, const int* target, int R, int V, float* tok_logp, cudaStream_t stream);
+                       const float* bias, const int* target, const int* row_map /*null: identity*/, int R, int V,
+                       float* tok_logp, cudaStream_t stream);
 // per utterance rescoring combine (wenet search.py:421-452)
 struct RescoreArgs {
     const float* l2r;  const float* r2l;  // [R] token log-probs, rows hyp-major, (len+1) per hyp

@@ -19,15 +19,19 @@ struct RsPlan {
     long long R = 0;  // decoder rows
     int max_hyp_rows = 0, max_utt_rows = 0, max_enc_len = 0;
     size_t o_int = 0, o_dbl = 0, o_x = 0, o_a = 0, o_qkv = 0, o_ctx = 0, o_q = 0, o_h = 0, o_memkv = 0, o_logits = 0,
-           total = 0;
+           o_qkv_full = 0, o_ctx_full = 0, total = 0;
     long long ldl = 0;
     size_t n_int = 0;
+    // prefix sharing (dedup): decoder rows that see the same input prefix (same utterance) are computed once
+    bool dedup = false;
+    int U[2] = {0, 0};           // unique rows, l2r / r2l
+    int max_utt_u[2] = {0, 0};   // largest per-utterance unique-row count
 };
 
 void rs_layout(const Model* m, long long enc_rows, long long R, int batch, int n_hyp, RsPlan* P) {
     const int d = m->cfg.d_model, ff = m->cfg.dec_ffn_dim;
     P->ldl = (m->cfg.vocab + 7) / 8 * 8;
-    P->n_int = (size_t)5 * R + (size_t)4 * n_hyp + (size_t)6 * batch + 64;
+    P->n_int = (size_t)13 * R + (size_t)4 * n_hyp + (size_t)10 * batch + 64;
     size_t o = 0;
     P->o_int = o; o += align_up(P->n_int * 4);
     P->o_dbl = o; o += align_up((size_t)n_hyp * 8 + 64);
@@ -38,6 +42,8 @@ void rs_layout(const Model* m, long long enc_rows, long long R, int batch, int n
     P->o_q = o; o += align_up((size_t)R * d * 2);
     P->o_h = o; o += align_up((size_t)R * ff * 2);
     P->o_memkv = o; o += align_up((size_t)enc_rows * 2 * d * 2);
+    P->o_qkv_full = o; o += align_up((size_t)R * 3 * d * 2);   // self-attention runs on every row of every hypothesis
+    P->o_ctx_full = o; o += align_up((size_t)R * d * 2);
     // rescoring never materialises the [R, V] logits: the output GEMM leaves per-tile log-sum-exp partials only
     P->o_logits = o; o += align_up((size_t)R * lse_parts(m->cfg.vocab) * sizeof(float2));
     P->total = o + 256;
@@ -52,18 +58,57 @@ void rs_layout(const Model* m, long long enc_rows, long long R, int batch, int n
 struct RsDevPtrs {
     int *tok_l2r, *tok_r2l, *pos, *tgt_l2r, *tgt_r2l, *hyp_row0, *hyp_rows, *hyp_len, *hyp_src, *utt_q0, *utt_qn,
         *utt_hyp0, *utt_nhyp, *enc_start, *enc_len;
+    // dedup maps per direction (0 = l2r, 1 = r2l): unique row of every row, a representative row of every unique row,
+    // decoder inputs of the unique rows, and the unique-row range of every utterance
+    int *uniq[2], *rep[2], *tok_u[2], *pos_u[2], *utt_q0_u[2], *utt_qn_u[2];
     double* ctc;
 };
+
+// rows of one decoder direction as the layers see them
+struct DirRows {
+    int n;                      // rows the row-wise layers run on (unique rows, or all rows without dedup)
+    const int* tok;             // [n] input tokens
+    const int* pos;             // [n] positions
+    const int* utt_q0;          // [batch] row range of every utterance (cross-attention queries)
+    const int* utt_qn;
+    int max_utt_rows;
+    const int* uniq_of_row;     // [R] or null (identity)
+    const int* rep_row;         // [n] or null
+};
+
+// dst[i] = src[idx[i]] for rows of `vecs` 16-byte vectors; one warp per row
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, int n, int vecs,
+                                   uint4* __restrict__ dst) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const uint4* s = src + (long long)idx[i] * vecs;
+    uint4* d = dst + (long long)i * vecs;
+    for (int v = threadIdx.x & 31; v < vecs; v += 32) d[v] = s[v];
+}
+int gather_rows(const void* src, const int* idx, int n, int row_bytes, void* dst, cudaStream_t st) {
+    if (n <= 0) return WB_OK;
+    ProfScope _ps(PT_MISC, st, (double)n * row_bytes * 2.0);
+    gather_rows_kernel<<<ceil_div(n, 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), idx, n, row_bytes / 16,
+                                                       reinterpret_cast<uint4*>(dst));
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
 
 // one direction of the decoder: x = embed(tokens); layers; after_norm; logits = out(x)
 // Output: either the raw logits [R][ldl] (logits != null; decoder_logprobs API) or, for rescoring, only
 // tok_logp[r] = log_softmax(logits[r])[target[r]] via LSE partials (logits == null).
-int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPtrs& dp, const int* tokens,
+// With prefix sharing (Q.uniq_of_row != null) every row-wise layer runs on the unique rows only; the causal
+// self-attention still sees every row of every hypothesis: Q/K/V are expanded unique -> all rows before it and its
+// output is compacted back (two row gathers per layer instead of 2 x the FLOPs of the whole decoder).
+int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPtrs& dp, const DirRows& Q,
                 const void* enc_bf16, long long enc_rows, uint8_t* ws, float* logits, long long ldl, const int* target,
                 float* tok_logp, cudaStream_t st) {
     const wb_model_config& c = m->cfg;
     const int d = c.d_model, ff = c.dec_ffn_dim, H = c.dec_heads;
-    const int R = (int)P.R;
+    const int R = (int)P.R;      // all rows (hypothesis-major)
+    const int N = Q.n;           // rows of the row-wise layers
+    const bool shared = Q.uniq_of_row != nullptr;
     float* x = reinterpret_cast<float*>(ws + P.o_x);
     void* a = ws + P.o_a;
     void* qkv = ws + P.o_qkv;
@@ -71,61 +116,67 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
     void* q = ws + P.o_q;
     void* h = ws + P.o_h;
     void* memkv = ws + P.o_memkv;
+    void* qkv_full = shared ? ws + P.o_qkv_full : qkv;
+    void* ctx_full = shared ? ws + P.o_ctx_full : ctx;
     const float scale = 1.0f / sqrtf(64.0f);
-    RC(embed_tokens(tokens, dp.pos, R, d, D.emb, m->pe, sqrtf((float)d), x, st));
+    RC(embed_tokens(Q.tok, Q.pos, N, d, D.emb, m->pe, sqrtf((float)d), x, st));
     for (size_t li = 0; li < D.layers.size(); ++li) {
         const DecLayer& L = D.layers[li];
         // masked (causal) self-attention, decoder_layer.py:101-118
-        RC(layernorm_rows(x, d, R, d, L.n1.g, L.n1.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.sa_qkv.tmap, L.sa_qkv.w, R, 3 * d, d, L.sa_qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
+        RC(layernorm_rows(x, d, N, d, L.n1.g, L.n1.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.sa_qkv.tmap, L.sa_qkv.w, N, 3 * d, d, L.sa_qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
+        if (shared) RC(gather_rows(qkv, Q.uniq_of_row, R, 3 * d * 2, qkv_full, st));
         {
             AttnArgs A;
-            A.q = qkv; A.ldq = 3 * d; A.q_rows = R; A.q_col0 = 0;
-            A.k = qkv; A.ldk = 3 * d; A.k_rows = R; A.k_col0 = d;
-            A.v = qkv; A.ldv = 3 * d; A.v_rows = R; A.v_col0 = 2 * d;
+            A.q = qkv_full; A.ldq = 3 * d; A.q_rows = R; A.q_col0 = 0;
+            A.k = qkv_full; A.ldk = 3 * d; A.k_rows = R; A.k_col0 = d;
+            A.v = qkv_full; A.ldv = 3 * d; A.v_rows = R; A.v_col0 = 2 * d;
             A.kbias = nullptr; A.ld_kbias = 0;
             A.q_start = dp.hyp_row0; A.q_len = dp.hyp_rows; A.k_start = dp.hyp_row0; A.k_len = dp.hyp_rows;
             A.batch = P.n_hyp; A.heads = H; A.max_q_len = P.max_hyp_rows;
             A.chunk_size = 1; A.num_left_chunks = -1; A.scale = scale;   // causal == chunk size 1
-            A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
+            A.out = ctx_full; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
             RC(attention_forward(A, st));
         }
-        RC(gemm_bf16(ctx, d, &L.sa_out.tmap, L.sa_out.w, R, d, d, L.sa_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        if (shared) RC(gather_rows(ctx_full, Q.rep_row, N, d * 2, ctx, st));
+        RC(gemm_bf16(ctx, d, &L.sa_out.tmap, L.sa_out.w, N, d, d, L.sa_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // cross-attention over the utterance's encoder frames, decoder_layer.py:120-139
-        RC(layernorm_rows(x, d, R, d, L.n2.g, L.n2.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.ca_q.tmap, L.ca_q.w, R, d, d, L.ca_q.b, EPI_BF16, 1.0f, q, d, 0, st));
+        RC(layernorm_rows(x, d, N, d, L.n2.g, L.n2.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(gemm_bf16(a, d, &L.ca_q.tmap, L.ca_q.w, N, d, d, L.ca_q.b, EPI_BF16, 1.0f, q, d, 0, st));
         RC(gemm_bf16(enc_bf16, d, &L.ca_kv.tmap, L.ca_kv.w, (int)enc_rows, 2 * d, d, L.ca_kv.b, EPI_BF16, 1.0f, memkv,
                      2 * d, 0, st));
         {
             AttnArgs A;
-            A.q = q; A.ldq = d; A.q_rows = R; A.q_col0 = 0;
+            A.q = q; A.ldq = d; A.q_rows = N; A.q_col0 = 0;
             A.k = memkv; A.ldk = 2 * d; A.k_rows = enc_rows; A.k_col0 = 0;
             A.v = memkv; A.ldv = 2 * d; A.v_rows = enc_rows; A.v_col0 = d;
             A.kbias = nullptr; A.ld_kbias = 0;
-            A.q_start = dp.utt_q0; A.q_len = dp.utt_qn; A.k_start = dp.enc_start; A.k_len = dp.enc_len;
-            A.batch = P.batch; A.heads = H; A.max_q_len = P.max_utt_rows;
+            A.q_start = Q.utt_q0; A.q_len = Q.utt_qn; A.k_start = dp.enc_start; A.k_len = dp.enc_len;
+            A.batch = P.batch; A.heads = H; A.max_q_len = Q.max_utt_rows;
             A.chunk_size = 0; A.num_left_chunks = -1; A.scale = scale;
             A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
             RC(attention_forward(A, st));
         }
-        RC(gemm_bf16(ctx, d, &L.ca_out.tmap, L.ca_out.w, R, d, d, L.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(gemm_bf16(ctx, d, &L.ca_out.tmap, L.ca_out.w, N, d, d, L.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // feed-forward (ReLU), decoder_layer.py:141-147
-        RC(layernorm_rows(x, d, R, d, L.n3.g, L.n3.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(layernorm_rows(x, d, N, d, L.n3.g, L.n3.b, c.ln_eps, a, d, 0, nullptr, 0, st));
         static const bool ffn_fusion_on = (getenv("WB_FFN_FUSION") != nullptr);   // see encoder.cu
-        if (ffn_fusion_on && ffn_fused_supported(d, ff) && R >= 1024) {
-            RC(ffn_fused(a, d, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, R, d, ff, 1.0f, 1, x, d, st));
+        if (ffn_fusion_on && ffn_fused_supported(d, ff) && N >= 1024) {
+            RC(ffn_fused(a, d, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, N, d, ff, 1.0f, 1, x, d, st));
         } else {
-            RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, R, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
-            RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, R, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+            RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, N, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
+            RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, N, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         }
     }
-    RC(layernorm_rows(x, d, R, d, D.after.g, D.after.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+    RC(layernorm_rows(x, d, N, d, D.after.g, D.after.b, c.ln_eps, a, d, 0, nullptr, 0, st));
     if (logits != nullptr) {
-        RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, ldl, 0, st));
+        WB_REQUIRE(!shared, WB_ERR_BAD_ARG, "decoder logits are only produced without prefix sharing");
+        RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, N, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, ldl, 0, st));
     } else {
         float2* part = reinterpret_cast<float2*>(ws + P.o_logits);
-        RC(gemm_lse_partials(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, part, st));
-        RC(lse_target_logprob(part, lse_parts(c.vocab), a, d, D.out.w, d, D.out.b, target, R, c.vocab, tok_logp, st));
+        RC(gemm_lse_partials(a, d, &D.out.tmap, D.out.w, N, c.vocab, d, D.out.b, part, st));
+        RC(lse_target_logprob(part, lse_parts(c.vocab), a, d, D.out.w, d, D.out.b, target, Q.uniq_of_row, R, c.vocab,
+                              tok_logp, st));
     }
     return WB_OK;
 }
@@ -153,8 +204,8 @@ __global__ void build_decoder_inputs_kernel(int n_hyp, const int* __restrict__ h
 // builds the flattened decoder inputs on the host and uploads them (one copy)
 int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, const int32_t* seq_len_host, int batch,
             int n_hyp, const int32_t* hyp_utt, const int32_t* hyp_len, const int32_t* hyp_tok0,
-            const int32_t* hyp_tokens, bool tokens_on_device, const double* ctc_score, int sos, int eos, uint8_t* ws,
-            size_t ws_bytes, RsPlan* P, RsDevPtrs* dp, cudaStream_t st) {
+            const int32_t* hyp_tokens, bool tokens_on_device, bool dedup, const double* ctc_score, int sos, int eos,
+            uint8_t* ws, size_t ws_bytes, RsPlan* P, RsDevPtrs* dp, cudaStream_t st) {
     long long R = 0;
     for (int h = 0; h < n_hyp; ++h) R += hyp_len[h] + 1;
     rs_layout(m, enc_rows, R, batch, n_hyp, P);
@@ -179,6 +230,15 @@ int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, c
     int* utt_nhyp = utt_hyp0 + batch;
     int* enc_start = utt_nhyp + batch;
     int* enc_len = enc_start + batch;
+    // dedup tables (l2r then r2l): uniq[R], rep[R], tok_u[R], pos_u[R] each, then utt_q0_u[batch], utt_qn_u[batch] each
+    int* dd = enc_len + batch;
+    int* h_uniq[2] = {dd, dd + 4 * R};
+    int* h_rep[2] = {dd + R, dd + 5 * R};
+    int* h_tok_u[2] = {dd + 2 * R, dd + 6 * R};
+    int* h_pos_u[2] = {dd + 3 * R, dd + 7 * R};
+    int* h_q0_u[2] = {dd + 8 * R, dd + 8 * R + 2 * batch};
+    int* h_qn_u[2] = {dd + 8 * R + batch, dd + 8 * R + 3 * batch};
+    P->dedup = dedup && !tokens_on_device && hyp_tokens != nullptr;
     for (int b = 0; b < batch; ++b) {
         utt_q0[b] = 0;
         utt_qn[b] = 0;
@@ -219,6 +279,50 @@ int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, c
     }
     for (int b = 0; b < batch; ++b)
         if (utt_qn[b] > P->max_utt_rows) P->max_utt_rows = utt_qn[b];
+    if (P->dedup) {
+        // Row (h, j) of a direction sees the input prefix [sos, s_0 .. s_{j-1}] (s = the hypothesis, reversed for
+        // r2l) and the utterance's encoder memory, nothing else: rows of the SAME utterance with equal prefixes are
+        // the same computation.  Hypothesis h shares rows 0 .. lcp with the earlier hypothesis g* of its utterance
+        // that has the longest common prefix; those rows point at g*'s unique rows, the rest get new unique rows.
+        for (int dir = 0; dir < 2; ++dir) {
+            int U = 0;
+            auto tokat = [&](int h, int i) {   // i-th token of the sequence hypothesis h presents in this direction
+                const int32_t* y = hyp_tokens + hyp_tok0[h];
+                return dir == 0 ? y[i] : y[hyp_len[h] - 1 - i];
+            };
+            for (int b = 0; b < batch; ++b) {
+                const int hb = utt_hyp0[b], he = hb + utt_nhyp[b];
+                h_q0_u[dir][b] = U;
+                for (int h = hb; h < he; ++h) {
+                    const int n = hyp_len[h], r0 = hyp_row0[h];
+                    int best = -1, best_g = -1;   // rows 0 .. best are shared with hypothesis best_g
+                    for (int g = hb; g < h; ++g) {
+                        const int lim = n < hyp_len[g] ? n : hyp_len[g];
+                        int l = 0;
+                        while (l < lim && tokat(h, l) == tokat(g, l)) ++l;
+                        if (l > best) {
+                            best = l;
+                            best_g = g;
+                        }
+                    }
+                    for (int j = 0; j <= n; ++j) {
+                        if (best_g >= 0 && j <= best) {
+                            h_uniq[dir][r0 + j] = h_uniq[dir][hyp_row0[best_g] + j];
+                        } else {
+                            h_uniq[dir][r0 + j] = U;
+                            h_rep[dir][U] = r0 + j;
+                            h_tok_u[dir][U] = (j == 0) ? sos : tokat(h, j - 1);
+                            h_pos_u[dir][U] = j;
+                            ++U;
+                        }
+                    }
+                }
+                h_qn_u[dir][b] = U - h_q0_u[dir][b];
+                if (h_qn_u[dir][b] > P->max_utt_u[dir]) P->max_utt_u[dir] = h_qn_u[dir][b];
+            }
+            P->U[dir] = U;
+        }
+    }
     WB_REQUIRE(P->max_hyp_rows <= m->cfg.max_pos, WB_ERR_UNSUPPORTED, "hypothesis longer than the positional table");
     WB_CHECK_CUDA(cudaMemcpyAsync(ws + P->o_int, buf.data(), P->n_int * 4, cudaMemcpyHostToDevice, st));
     if (ctc_score)
@@ -240,6 +344,17 @@ int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, c
     dp->utt_nhyp = dp->utt_hyp0 + batch;
     dp->enc_start = dp->utt_nhyp + batch;
     dp->enc_len = dp->enc_start + batch;
+    {
+        int* ddv = dp->enc_len + batch;
+        for (int dir = 0; dir < 2; ++dir) {
+            dp->uniq[dir] = ddv + (dir ? 4 * R : 0);
+            dp->rep[dir] = ddv + (dir ? 5 * R : R);
+            dp->tok_u[dir] = ddv + (dir ? 6 * R : 2 * R);
+            dp->pos_u[dir] = ddv + (dir ? 7 * R : 3 * R);
+            dp->utt_q0_u[dir] = ddv + 8 * R + (dir ? 2 * batch : 0);
+            dp->utt_qn_u[dir] = ddv + 8 * R + (dir ? 3 * batch : batch);
+        }
+    }
     dp->ctc = reinterpret_cast<double*>(ws + P->o_dbl);
     if (tokens_on_device) {
         build_decoder_inputs_kernel<<<ceil_div(n_hyp, 8), 256, 0, st>>>(n_hyp, dp->hyp_row0, dp->hyp_len, dp->hyp_src,
@@ -286,14 +401,39 @@ static int attention_rescoring_impl(const wb_model* mm, const void* enc_out_bf16
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
     RsPlan P;
     RsDevPtrs dp;
+    static const bool dedup_off = getenv("WB_NO_PREFIX_SHARING") != nullptr;
     RC(prepare(m, enc_rows, seq_start_host, seq_len_host, batch, n_hyp, hyp_utt_host, hyp_len_host, hyp_tok0_host,
-               hyp_tokens, tokens_on_device, ctc_score_host, sos, eos, ws, workspace_bytes, &P, &dp, st));
-    RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, nullptr, 0, dp.tgt_l2r, tok_logp_l2r_dev, st));
+               hyp_tokens, tokens_on_device, !dedup_off, ctc_score_host, sos, eos, ws, workspace_bytes, &P, &dp, st));
+    auto rows_of = [&](int dir) {
+        DirRows Q;
+        if (P.dedup) {
+            Q.n = P.U[dir];
+            Q.tok = dp.tok_u[dir];
+            Q.pos = dp.pos_u[dir];
+            Q.utt_q0 = dp.utt_q0_u[dir];
+            Q.utt_qn = dp.utt_qn_u[dir];
+            Q.max_utt_rows = P.max_utt_u[dir];
+            Q.uniq_of_row = dp.uniq[dir];
+            Q.rep_row = dp.rep[dir];
+        } else {
+            Q.n = (int)P.R;
+            Q.tok = dir ? dp.tok_r2l : dp.tok_l2r;
+            Q.pos = dp.pos;
+            Q.utt_q0 = dp.utt_q0;
+            Q.utt_qn = dp.utt_qn;
+            Q.max_utt_rows = P.max_utt_rows;
+            Q.uniq_of_row = nullptr;
+            Q.rep_row = nullptr;
+        }
+        return Q;
+    };
+    RC(run_decoder(m, m->left, P, dp, rows_of(0), enc_out_bf16_dev, enc_rows, ws, nullptr, 0, dp.tgt_l2r, tok_logp_l2r_dev,
+                   st));
     const bool use_r2l = reverse_weight > 0.f && m->cfg.rdec_layers > 0;
     if (use_r2l) {
         WB_REQUIRE(tok_logp_r2l_dev, WB_ERR_BAD_ARG, "attention_rescoring: r2l output buffer missing");
-        RC(run_decoder(m, m->right, P, dp, dp.tok_r2l, enc_out_bf16_dev, enc_rows, ws, nullptr, 0, dp.tgt_r2l, tok_logp_r2l_dev,
-                       st));
+        RC(run_decoder(m, m->right, P, dp, rows_of(1), enc_out_bf16_dev, enc_rows, ws, nullptr, 0, dp.tgt_r2l,
+                       tok_logp_r2l_dev, st));
     }
     RescoreArgs a;
     a.l2r = tok_logp_l2r_dev;
@@ -353,11 +493,15 @@ int wb_decoder_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_
     RsPlan P;
     RsDevPtrs dp;
     RC(prepare(m, enc_rows, seq_start_host, seq_len_host, batch, n_hyp, hyp_utt_host, hyp_len_host, hyp_tok0_host,
-               hyp_tokens_host, false, nullptr, sos, eos, ws, workspace_bytes, &P, &dp, st));
-    RC(run_decoder(m, m->left, P, dp, dp.tok_l2r, enc_out_bf16_dev, enc_rows, ws, logp_dev, ldl, nullptr, nullptr, st));
+               hyp_tokens_host, false, false, nullptr, sos, eos, ws, workspace_bytes, &P, &dp, st));
+    DirRows Q;
+    Q.n = (int)P.R; Q.tok = dp.tok_l2r; Q.pos = dp.pos; Q.utt_q0 = dp.utt_q0; Q.utt_qn = dp.utt_qn;
+    Q.max_utt_rows = P.max_utt_rows; Q.uniq_of_row = nullptr; Q.rep_row = nullptr;
+    RC(run_decoder(m, m->left, P, dp, Q, enc_out_bf16_dev, enc_rows, ws, logp_dev, ldl, nullptr, nullptr, st));
     RC(ctc_logsoftmax_topk(logp_dev, ldl, (int)P.R, m->cfg.vocab, -1, 0.f, 0, nullptr, nullptr, st));
     if (use_r2l && m->cfg.rdec_layers > 0 && r_logp_dev) {
-        RC(run_decoder(m, m->right, P, dp, dp.tok_r2l, enc_out_bf16_dev, enc_rows, ws, r_logp_dev, ldl, nullptr, nullptr, st));
+        Q.tok = dp.tok_r2l;
+        RC(run_decoder(m, m->right, P, dp, Q, enc_out_bf16_dev, enc_rows, ws, r_logp_dev, ldl, nullptr, nullptr, st));
         RC(ctc_logsoftmax_topk(r_logp_dev, ldl, (int)P.R, m->cfg.vocab, -1, 0.f, 0, nullptr, nullptr, st));
     }
     return WB_OK;
