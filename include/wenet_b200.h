@@ -210,7 +210,9 @@ int wb_ctc_prefix_beam_search(const float* topk_val_dev, const int32_t* topk_idx
 /* ------------------------------------------------------------------------------------------
  * E. attention rescoring — replaces attention_rescoring (search.py:374-458) and
  *    ASRModel.forward_attention_decoder (asr_model.py:453-547): (Bi)TransformerDecoder over all
- *    hypotheses of all utterances in one batch, cross-attention K/V projected once per utterance.
+ *    hypotheses of all utterances in one batch, cross-attention K/V projected once per utterance; with
+ *    host-side tokens (wb_attention_rescoring) decoder rows of an utterance that share an input prefix are
+ *    computed once (bit-identical to computing every row, which wb_attention_rescoring_dev does).
  *    Hypotheses are given flattened, utterance-major: hyp h belongs to utterance hyp_utt[h]
  *    (non-decreasing), has hyp_len[h] tokens at hyp_tokens[hyp_tok0[h] ...].
  *    Outputs: tok_logp_l2r/r2l [R] with R = sum_h (len_h + 1): log p of token j of hyp h at row
