@@ -24,41 +24,6 @@ __global__ void embed_kernel(const int* __restrict__ tokens, const int* __restri
     }
 }
 
-constexpr int GL_THREADS = 256;
-__global__ void __launch_bounds__(GL_THREADS)
-gather_logprob_kernel(const float* __restrict__ logits, long long ldl, int V, const int* __restrict__ target,
-                      float* __restrict__ tok_logp) {
-    __shared__ float s_red[GL_THREADS / 32];
-    __shared__ float s_b;
-    const long long row = blockIdx.x;
-    const float* g = logits + row * ldl;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float mx = -INFINITY;
-    for (int i = threadIdx.x; i < V; i += GL_THREADS) mx = fmaxf(mx, g[i]);
-    mx = warp_max(mx);
-    if (lane == 0) s_red[warp] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float m = s_red[0];
-        for (int w = 1; w < GL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
-        s_b = m;
-    }
-    __syncthreads();
-    mx = s_b;
-    float sum = 0.f;
-    for (int i = threadIdx.x; i < V; i += GL_THREADS) sum += expf(g[i] - mx);
-    sum = warp_sum(sum);
-    __syncthreads();
-    if (lane == 0) s_red[warp] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < GL_THREADS / 32; ++w) s += s_red[w];
-        const int tg = target[row];
-        tok_logp[row] = (tg >= 0 && tg < V) ? (g[tg] - (mx + logf(s))) : 0.f;
-    }
-}
-
 // warp per row: combine the partial (max, sum) pairs of gemm_lse_partials into the log-sum-exp of the row and subtract it
 // from the target logit, recomputed here as a 1 x d dot product (a[r] . W[target] + bias) - the [R, V] logits are never
 // materialised (1.5 GB per decoder direction at 64 x 30 s x 10 hypotheses).
@@ -188,16 +153,6 @@ int embed_tokens(const int* tokens, const int* pos, int R, int d, const float* e
     const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
     ProfScope _ps(PT_EMBED, stream, (double)R * d * 12.0);
     embed_kernel<<<grid, 256, 0, stream>>>(tokens, pos, R, d, emb, pe, xscale, x);
-    count_launch();
-    WB_CHECK_LAUNCH();
-    return WB_OK;
-}
-
-int gather_logprob(const float* logits, long long ldl, int R, int V, const int* target, float* tok_logp,
-                   cudaStream_t stream) {
-    if (R <= 0) return WB_OK;
-    ProfScope _ps(PT_GATHER_LOGPROB, stream, (double)R * V * 4.0);
-    gather_logprob_kernel<<<R, GL_THREADS, 0, stream>>>(logits, ldl, V, target, tok_logp);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

@@ -165,9 +165,6 @@ int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream);
 // x[r] = emb[token[r]] * xscale + pe[pos[r]]
 int embed_tokens(const int* tokens, const int* pos, int R, int d, const float* emb /*[V,d]*/,
                  const float* pe /*[maxlen,d]*/, float xscale, float* x, cudaStream_t stream);
-// tok_logp[r] = logits[r, target[r]] - logsumexp(logits[r, :V])   (target < 0 -> 0)
-int gather_logprob(const float* logits, long long ldl, int R, int V, const int* target, float* tok_logp,
-                   cudaStream_t stream);
 // tok_logp[r] = (a[r] . W[target[r]] + bias[target[r]]) - logsumexp_r, the latter from gemm_lse_partials (target < 0 -> 0)
 int lse_target_logprob(const float2* part, int n_parts, const void* a_bf16, long long lda, const void* w_bf16, int d,
                        const float* bias, const int* target, const int* row_map /*null: identity*/, int R, int V,
