@@ -326,13 +326,22 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
         }
         // rel-pos multi-headed self-attention (:231-238)
         RC(layernorm_rows(x, d, Mi, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, Mi, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
-        RC(relpos_kprep(reinterpret_cast<const uint8_t*>(qkv) + (size_t)d * 2, 3 * d, L.pos_proj, d_row_pos, L.pos_u,
-                        L.pos_v, Mi, H, kp, d, kbias, st));
+        // rel-pos key preparation (K' = K + P[pos], c = u.K + v.P) either fused into the QKV GEMM epilogue
+        // (WB_QKV_RELPOS_FUSION=1, d % 256 == 0) or as its own HBM-bound kernel
+        static const bool qkv_fuse = getenv("WB_QKV_RELPOS_FUSION") != nullptr;
+        const bool fuse_kp = qkv_fuse && d % 256 == 0 && c.precise == 0;
+        if (fuse_kp) {
+            RC(gemm_qkv_relpos(a, d, &L.qkv.tmap, L.qkv.w, Mi, d, H, L.qkv.b, L.pos_proj, d_row_pos, L.pos_u, L.pos_v, qkv,
+                               kbias, st));
+        } else {
+            RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, Mi, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
+            RC(relpos_kprep(reinterpret_cast<const uint8_t*>(qkv) + (size_t)d * 2, 3 * d, L.pos_proj, d_row_pos, L.pos_u,
+                            L.pos_v, Mi, H, kp, d, kbias, st));
+        }
         {
             AttnArgs A;
             A.q = qkv; A.ldq = 3 * d; A.q_rows = M; A.q_col0 = 0;
-            A.k = kp; A.ldk = d; A.k_rows = M; A.k_col0 = 0;
+            A.k = fuse_kp ? qkv : kp; A.ldk = fuse_kp ? 3 * d : d; A.k_rows = M; A.k_col0 = fuse_kp ? d : 0;
             A.v = qkv; A.ldv = 3 * d; A.v_rows = M; A.v_col0 = 2 * d;
             A.kbias = kbias; A.ld_kbias = H;
             A.q_start = d_ss; A.q_len = d_tp; A.k_start = d_ss; A.k_len = d_tp;

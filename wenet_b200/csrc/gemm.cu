@@ -68,6 +68,13 @@ struct GemmParams {
     int cblocks;            // d / 64
     const int4* tile_tab;   // per m-tile: .x t coordinate of tap kh = 0, .y first output row, .z valid rows (<= 114)
     float2* lse_part;       // EPI_LSE: [M][2 * num_n_tiles]
+    // EPI_QKV_RELPOS
+    const float* rp_table;  // [max_pos][rp_d] projected positions
+    const int* rp_row_pos;  // [M]
+    const float* rp_u;      // [rp_d]
+    const float* rp_v;      // [rp_d]
+    float* rp_kbias;        // [M][rp_heads]
+    int rp_d, rp_heads;
 };
 constexpr int kConvRows = 114;   // 6 x 19
 
@@ -293,6 +300,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // goes through bias / activation / staging (two register sets, loop fully unrolled)
             uint32_t rbuf[2][32];
             float lse_m = -INFINITY, lse_s = 0.f;   // EPI_LSE: running (max, sum) over this warp's columns, log2 domain
+            float rp_carry = 0.f;                   // EPI_QKV_RELPOS: u.k + v.p over the first half of the current head
             constexpr int c_begin_rel = 0;
             const int c0 = half * kChunksPerWarp;
             if (n_tile * BN + c0 * 32 < p.N) tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c0 * 32), rbuf[0]);
@@ -386,6 +394,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         flush = ((c & 3) == 3) || (n0 + 32 >= p.N);
                         out_col = (n_tile * BN + (c & ~3) * 32) >> 1;
                     } else {
+                        if (epi == EPI_QKV_RELPOS && n0 >= p.rp_d && n0 < 2 * p.rp_d) {
+                            // K columns: same arithmetic as relpos_kprep_kernel on the bf16-rounded key
+                            const int kc = n0 - p.rp_d;                 // column inside the K third (multiple of 32)
+                            float cacc = (kc & 32) ? rp_carry : 0.f;    // second half of a 64-wide head continues
+                            if (row_ok) {
+                                const float* prow = p.rp_table + (long long)__ldg(p.rp_row_pos + row) * p.rp_d + kc;
+#pragma unroll
+                                for (int i = 0; i < 32; i += 4) {
+                                    const float4 p4 = __ldg(reinterpret_cast<const float4*>(prow + i));
+                                    const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.rp_u + kc + i));
+                                    const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.rp_v + kc + i));
+                                    const float k0 = __bfloat162float(__float2bfloat16_rn(v[i]));
+                                    const float k1 = __bfloat162float(__float2bfloat16_rn(v[i + 1]));
+                                    const float k2 = __bfloat162float(__float2bfloat16_rn(v[i + 2]));
+                                    const float k3 = __bfloat162float(__float2bfloat16_rn(v[i + 3]));
+                                    cacc = fmaf(u4.x, k0, cacc); cacc = fmaf(v4.x, p4.x, cacc);
+                                    cacc = fmaf(u4.y, k1, cacc); cacc = fmaf(v4.y, p4.y, cacc);
+                                    cacc = fmaf(u4.z, k2, cacc); cacc = fmaf(v4.z, p4.z, cacc);
+                                    cacc = fmaf(u4.w, k3, cacc); cacc = fmaf(v4.w, p4.w, cacc);
+                                    v[i] = k0 + p4.x;
+                                    v[i + 1] = k1 + p4.y;
+                                    v[i + 2] = k2 + p4.z;
+                                    v[i + 3] = k3 + p4.w;
+                                }
+                                if (kc & 32) p.rp_kbias[row * p.rp_heads + (kc >> 6)] = cacc;
+                            }
+                            rp_carry = cacc;
+                        }
                         if (epi == EPI_BF16_SILU) {
                             silu_inplace(v);
                         } else if (epi == EPI_BF16_RELU) {
@@ -611,9 +647,18 @@ int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K) {
     return make_tmap_2d_bf16(out, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)gemm_bn_for(N), BK);
 }
 
+struct RelposArgs {
+    const float* table;
+    const int* row_pos;
+    const float* u;
+    const float* v;
+    float* kbias;
+    int d, heads;
+};
+
 static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
                      int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
-                     float2* lse_part, cudaStream_t stream) {
+                     float2* lse_part, cudaStream_t stream, const RelposArgs* rp = nullptr) {
     if (M <= 0) return WB_OK;
     WB_REQUIRE(N > 0 && K > 0, WB_ERR_BAD_ARG, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     WB_REQUIRE((K % 8) == 0 && (lda % 8) == 0, WB_ERR_BAD_ARG,
@@ -654,6 +699,7 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
     const int out_cols = (epi == EPI_GLU_BF16) ? N / 2 : N;
     const int eb = f32_out ? 4 : 2;
     p.use_tma_out = (epi != EPI_LSE && !split3 && (ldc * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    WB_REQUIRE(epi != EPI_QKV_RELPOS || p.use_tma_out, WB_ERR_BAD_ARG, "gemm_qkv_relpos: output must be 16-byte aligned");
     if (p.use_tma_out) {
         rc = make_tmap_2d(&tc, out, eb, (uint64_t)M, (uint64_t)out_cols, (uint64_t)ldc, 32, f32_out ? 32 : 64);
         if (rc != WB_OK) return rc;
@@ -662,6 +708,13 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
     p.cblocks = 0;
     p.tile_tab = nullptr;
     p.lse_part = lse_part;
+    p.rp_table = rp ? rp->table : nullptr;
+    p.rp_row_pos = rp ? rp->row_pos : nullptr;
+    p.rp_u = rp ? rp->u : nullptr;
+    p.rp_v = rp ? rp->v : nullptr;
+    p.rp_kbias = rp ? rp->kbias : nullptr;
+    p.rp_d = rp ? rp->d : 0;
+    p.rp_heads = rp ? rp->heads : 0;
     const int num_kb = ceil_div(K, BK);
     if (bn == 256) {
         const bool res = num_kb <= GemmCfg<256>::kResMaxKB;
@@ -677,6 +730,7 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
             WB_GEMM_CASE(EPI_GLU_BF16)
             WB_GEMM_CASE(EPI_F32)
             WB_GEMM_CASE(EPI_LSE)
+            WB_GEMM_CASE(EPI_QKV_RELPOS)
 #undef WB_GEMM_CASE
             default:
                 WB_REQUIRE(false, WB_ERR_BAD_ARG, "gemm: unknown epilogue %d", epi);
@@ -689,8 +743,16 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
 int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
               int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
               cudaStream_t stream) {
-    WB_REQUIRE(epi != EPI_LSE, WB_ERR_BAD_ARG, "gemm: EPI_LSE goes through gemm_lse_partials");
+    WB_REQUIRE(epi != EPI_LSE && epi != EPI_QKV_RELPOS, WB_ERR_BAD_ARG, "gemm: this epilogue has its own entry point");
     return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, epi, alpha, out, ldc, split3, nullptr, stream);
+}
+
+int gemm_qkv_relpos(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int d, int heads,
+                    const float* bias, const float* pos_table, const int* row_pos, const float* pos_u, const float* pos_v,
+                    void* qkv, float* kbias, cudaStream_t stream) {
+    WB_REQUIRE(d % 256 == 0 && heads * 64 == d, WB_ERR_UNSUPPORTED, "gemm_qkv_relpos: d=%d heads=%d unsupported", d, heads);
+    RelposArgs rp{pos_table, row_pos, pos_u, pos_v, kbias, d, heads};
+    return gemm_impl(A, lda, tmap_b_opt, B, M, 3 * d, d, bias, EPI_QKV_RELPOS, 1.0f, qkv, 3 * d, 0, nullptr, stream, &rp);
 }
 
 int lse_parts(int N) { return 2 * ceil_div(N, gemm_bn_for(N)); }
@@ -732,6 +794,8 @@ int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, con
     p.num_m_tiles = num_tiles;
     p.num_n_tiles = d / 256;
     p.lse_part = nullptr;
+    p.rp_table = nullptr; p.rp_row_pos = nullptr; p.rp_u = nullptr; p.rp_v = nullptr; p.rp_kbias = nullptr;
+    p.rp_d = 0; p.rp_heads = 0;
     p.conv = 1;
     p.cblocks = d / 64;
     p.tile_tab = reinterpret_cast<const int4*>(tile_tab_dev);

@@ -15,6 +15,8 @@ enum GemmEpi : int {
     EPI_RESID_F32 = 3,  // out_f32 += alpha * (acc + bias)      (in-place residual stream update)
     EPI_GLU_BF16 = 4,   // out_bf16[:, N/2] = a * sigmoid(g), weight rows packed [16 a | 16 g] x N/32
     EPI_F32 = 5,        // out_f32  = alpha * (acc + bias)
+    EPI_QKV_RELPOS = 7, // out_bf16 = acc + bias, except the K third [d, 2d): K' = bf16(bf16(k) + P[pos[row]]) and the
+                        // per-(row, head) bias c = u . k + v . P is written to kbias (relpos_kprep fused into the QKV GEMM)
     EPI_LSE = 6,        // no matrix output: per (row, 128-column half tile) partial log-sum-exp (max2, sum) of acc + bias
 };
 
@@ -34,6 +36,11 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
 int lse_parts(int N);
 int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream);
+
+// fused QKV projection + rel-pos key preparation (see EPI_QKV_RELPOS); qkv [M][3d] bf16, kbias [M][heads] fp32
+int gemm_qkv_relpos(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int d, int heads,
+                    const float* bias, const float* pos_table /*[max_pos][d]*/, const int* row_pos, const float* pos_u,
+                    const float* pos_v, void* qkv, float* kbias, cudaStream_t stream);
 
 // stall accounting of gemm_tcgen05_kernel (see gemm.cu); out8 may be null
 int gemm_diag(unsigned long long* out8, int reset);
