@@ -242,6 +242,14 @@ int wb_attention_rescoring_dev(const wb_model* m, const void* enc_out_bf16_dev, 
                                float reverse_weight, float* tok_logp_l2r_dev, float* tok_logp_r2l_dev,
                                float* hyp_score_dev, int32_t* best_dev, void* workspace_dev,
                                size_t workspace_bytes, wb_stream_t stream);
+/* Host-only helper (no CUDA call): the prefix-sharing tables wb_attention_rescoring builds for one decoder direction
+ * (dir 0 = left-to-right, 1 = right-to-left).  Rows are hypothesis-major, (len_h + 1) per hypothesis.  Outputs:
+ * uniq_of_row [R], rep_row / tok_u / pos_u [<= R], utt_q0_u / utt_qn_u [batch].  Returns the number of unique rows
+ * (>= 0) or a negative error code.  Exposed for the CPU unit tests. */
+int wb_prefix_share_tables(int dir, int batch, int n_hyp, const int32_t* hyp_utt_host, const int32_t* hyp_len_host,
+                           const int32_t* hyp_tok0_host, const int32_t* hyp_tokens_host, int sos,
+                           int32_t* uniq_of_row, int32_t* rep_row, int32_t* tok_u, int32_t* pos_u,
+                           int32_t* utt_q0_u, int32_t* utt_qn_u);
 /* full decoder posteriors for API parity with forward_attention_decoder: logp [R][ldl] (l2r) and
  * r_logp [R][ldl] (r2l, may be NULL) */
 int wb_decoder_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t enc_rows,

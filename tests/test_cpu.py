@@ -198,3 +198,75 @@ print("rank", rank, "ok", mine)
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_prefix_share_tables_host_logic():
+    """wb_prefix_share_tables (host-only part of wb_attention_rescoring): every decoder row maps to the first row of its
+    utterance with the same input prefix (direction-aware), unique rows are numbered hypothesis-major, and the unique
+    rows carry the right (token, position) inputs."""
+    import numpy as np
+    from wenet_b200 import _lib
+    from wenet_b200._lib import ptr
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    sos = 99
+    hyps_per_utt = []
+    for b in range(5):
+        base = rng.integers(1, 9, size=int(rng.integers(3, 12))).tolist()
+        hs = [base]
+        for _ in range(int(rng.integers(0, 6))):
+            h = list(base)
+            for _ in range(int(rng.integers(1, 3))):       # substitute / delete / insert somewhere
+                p = int(rng.integers(0, len(h) + 1))
+                op = int(rng.integers(0, 3))
+                if op == 0 and p < len(h):
+                    h[p] = int(rng.integers(1, 9))
+                elif op == 1 and len(h) > 1 and p < len(h):
+                    del h[p]
+                else:
+                    h.insert(p, int(rng.integers(1, 9)))
+            hs.append(h)
+        hyps_per_utt.append(hs)
+    hyps_per_utt.append([[]])                               # an utterance whose only hypothesis is empty
+    hyp_utt, hyp_len, hyp_tok0, toks = [], [], [], []
+    for b, hs in enumerate(hyps_per_utt):
+        for h in hs:
+            hyp_utt.append(b)
+            hyp_len.append(len(h))
+            hyp_tok0.append(len(toks))
+            toks.extend(h)
+    i32 = lambda x: np.ascontiguousarray(np.array(x if len(x) else [0], dtype=np.int32))
+    hyp_utt_a, hyp_len_a, hyp_tok0_a, toks_a = i32(hyp_utt), i32(hyp_len), i32(hyp_tok0), i32(toks)
+    B, n_hyp = len(hyps_per_utt), len(hyp_utt)
+    R = sum(hyp_len) + n_hyp
+    flat = [h for hs in hyps_per_utt for h in hs]
+    for direction in (0, 1):
+        uniq = np.full(R, -1, np.int32)
+        rep, tok_u, pos_u = np.full(R, -1, np.int32), np.full(R, -1, np.int32), np.full(R, -1, np.int32)
+        q0, qn = np.zeros(B, np.int32), np.zeros(B, np.int32)
+        U = lib.wb_prefix_share_tables(direction, B, n_hyp, ptr(hyp_utt_a), ptr(hyp_len_a), ptr(hyp_tok0_a), ptr(toks_a), sos,
+                                       ptr(uniq), ptr(rep), ptr(tok_u), ptr(pos_u), ptr(q0), ptr(qn))
+        assert U > 0
+        # reference: dictionary from (utterance, input prefix) to unique id, in row order
+        seen, want, rows = {}, [], []
+        for h, (b, y) in enumerate(zip(hyp_utt, flat)):
+            s = y if direction == 0 else y[::-1]
+            for j in range(len(s) + 1):
+                key = (b, tuple(s[:j]))
+                if key not in seen:
+                    seen[key] = len(seen)
+                    rows.append((sos if j == 0 else s[j - 1], j))
+                want.append(seen[key])
+        assert U == len(seen)
+        assert uniq.tolist() == want
+        assert tok_u[:U].tolist() == [t for t, _ in rows] and pos_u[:U].tolist() == [j for _, j in rows]
+        assert (uniq[rep[:U]] == np.arange(U)).all()
+        # unique rows of an utterance are contiguous and cover [q0, q0 + qn)
+        r = 0
+        for b, hs in enumerate(hyps_per_utt):
+            ids = set()
+            for h in hs:
+                ids.update(uniq[r:r + len(h) + 1].tolist())
+                r += len(h) + 1
+            assert ids == set(range(int(q0[b]), int(q0[b]) + int(qn[b])))
+        assert int(qn.sum()) == U

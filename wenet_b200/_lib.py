@@ -65,6 +65,7 @@ _PROTOS = {
     "wb_gemm_diag": (i32, [vp, i32]),
     "wb_attention_rescoring_dev": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, f32,
                                           f32, vp, vp, vp, vp, vp, sz, vp]),
+    "wb_prefix_share_tables": (i32, [i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "wb_decoder_logprobs": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp,
                                    i64, vp, sz, vp]),
     "wb_probe_tma3d": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, C.c_uint32, C.c_uint32, vp, vp, vp]),

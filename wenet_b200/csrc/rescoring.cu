@@ -201,6 +201,54 @@ __global__ void build_decoder_inputs_kernel(int n_hyp, const int* __restrict__ h
     }
 }
 
+// Prefix sharing tables of one decoder direction (0 = l2r, 1 = r2l: hypotheses reversed).
+// Row (h, j) of a direction sees the input prefix [sos, s_0 .. s_{j-1}] (s = the hypothesis in that direction) and
+// the utterance's encoder memory, nothing else: rows of the SAME utterance with equal prefixes are the same
+// computation.  Hypothesis h shares rows 0 .. lcp with the earlier hypothesis g* of its utterance that has the
+// longest common prefix; those rows point at g*'s unique rows, the rest get new unique rows (hypothesis-major, so
+// the unique rows of an utterance are contiguous).  Returns the number of unique rows.
+int build_prefix_share(int dir, int batch, const int* utt_hyp0, const int* utt_nhyp, const int* hyp_row0,
+                       const int32_t* hyp_len, const int32_t* hyp_tok0, const int32_t* hyp_tokens, int sos, int* uniq,
+                       int* rep, int* tok_u, int* pos_u, int* utt_q0_u, int* utt_qn_u, int* max_utt_u) {
+    int U = 0;
+    auto tokat = [&](int h, int i) {   // i-th token of the sequence hypothesis h presents in this direction
+        const int32_t* y = hyp_tokens + hyp_tok0[h];
+        return dir == 0 ? y[i] : y[hyp_len[h] - 1 - i];
+    };
+    *max_utt_u = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int hb = utt_hyp0[b], he = hb + utt_nhyp[b];
+        utt_q0_u[b] = U;
+        for (int h = hb; h < he; ++h) {
+            const int n = hyp_len[h], r0 = hyp_row0[h];
+            int best = -1, best_g = -1;   // rows 0 .. best are shared with hypothesis best_g
+            for (int g = hb; g < h; ++g) {
+                const int lim = n < hyp_len[g] ? n : hyp_len[g];
+                int l = 0;
+                while (l < lim && tokat(h, l) == tokat(g, l)) ++l;
+                if (l > best) {
+                    best = l;
+                    best_g = g;
+                }
+            }
+            for (int j = 0; j <= n; ++j) {
+                if (best_g >= 0 && j <= best) {
+                    uniq[r0 + j] = uniq[hyp_row0[best_g] + j];
+                } else {
+                    uniq[r0 + j] = U;
+                    rep[U] = r0 + j;
+                    tok_u[U] = (j == 0) ? sos : tokat(h, j - 1);
+                    pos_u[U] = j;
+                    ++U;
+                }
+            }
+        }
+        utt_qn_u[b] = U - utt_q0_u[b];
+        if (utt_qn_u[b] > *max_utt_u) *max_utt_u = utt_qn_u[b];
+    }
+    return U;
+}
+
 // builds the flattened decoder inputs on the host and uploads them (one copy)
 int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, const int32_t* seq_len_host, int batch,
             int n_hyp, const int32_t* hyp_utt, const int32_t* hyp_len, const int32_t* hyp_tok0,
@@ -280,48 +328,10 @@ int prepare(const Model* m, long long enc_rows, const int32_t* seq_start_host, c
     for (int b = 0; b < batch; ++b)
         if (utt_qn[b] > P->max_utt_rows) P->max_utt_rows = utt_qn[b];
     if (P->dedup) {
-        // Row (h, j) of a direction sees the input prefix [sos, s_0 .. s_{j-1}] (s = the hypothesis, reversed for
-        // r2l) and the utterance's encoder memory, nothing else: rows of the SAME utterance with equal prefixes are
-        // the same computation.  Hypothesis h shares rows 0 .. lcp with the earlier hypothesis g* of its utterance
-        // that has the longest common prefix; those rows point at g*'s unique rows, the rest get new unique rows.
-        for (int dir = 0; dir < 2; ++dir) {
-            int U = 0;
-            auto tokat = [&](int h, int i) {   // i-th token of the sequence hypothesis h presents in this direction
-                const int32_t* y = hyp_tokens + hyp_tok0[h];
-                return dir == 0 ? y[i] : y[hyp_len[h] - 1 - i];
-            };
-            for (int b = 0; b < batch; ++b) {
-                const int hb = utt_hyp0[b], he = hb + utt_nhyp[b];
-                h_q0_u[dir][b] = U;
-                for (int h = hb; h < he; ++h) {
-                    const int n = hyp_len[h], r0 = hyp_row0[h];
-                    int best = -1, best_g = -1;   // rows 0 .. best are shared with hypothesis best_g
-                    for (int g = hb; g < h; ++g) {
-                        const int lim = n < hyp_len[g] ? n : hyp_len[g];
-                        int l = 0;
-                        while (l < lim && tokat(h, l) == tokat(g, l)) ++l;
-                        if (l > best) {
-                            best = l;
-                            best_g = g;
-                        }
-                    }
-                    for (int j = 0; j <= n; ++j) {
-                        if (best_g >= 0 && j <= best) {
-                            h_uniq[dir][r0 + j] = h_uniq[dir][hyp_row0[best_g] + j];
-                        } else {
-                            h_uniq[dir][r0 + j] = U;
-                            h_rep[dir][U] = r0 + j;
-                            h_tok_u[dir][U] = (j == 0) ? sos : tokat(h, j - 1);
-                            h_pos_u[dir][U] = j;
-                            ++U;
-                        }
-                    }
-                }
-                h_qn_u[dir][b] = U - h_q0_u[dir][b];
-                if (h_qn_u[dir][b] > P->max_utt_u[dir]) P->max_utt_u[dir] = h_qn_u[dir][b];
-            }
-            P->U[dir] = U;
-        }
+        for (int dir = 0; dir < 2; ++dir)
+            P->U[dir] = build_prefix_share(dir, batch, utt_hyp0, utt_nhyp, hyp_row0, hyp_len, hyp_tok0, hyp_tokens, sos,
+                                           h_uniq[dir], h_rep[dir], h_tok_u[dir], h_pos_u[dir], h_q0_u[dir], h_qn_u[dir],
+                                           &P->max_utt_u[dir]);
     }
     WB_REQUIRE(P->max_hyp_rows <= m->cfg.max_pos, WB_ERR_UNSUPPORTED, "hypothesis longer than the positional table");
     WB_CHECK_CUDA(cudaMemcpyAsync(ws + P->o_int, buf.data(), P->n_int * 4, cudaMemcpyHostToDevice, st));
@@ -476,6 +486,30 @@ int wb_attention_rescoring_dev(const wb_model* mm, const void* enc_out_bf16_dev,
                                     hyp_utt_host, hyp_len_host, hyp_tok0_host, hyp_tokens_dev, true, ctc_score_host, sos,
                                     eos, ctc_weight, reverse_weight, tok_logp_l2r_dev, tok_logp_r2l_dev, hyp_score_dev,
                                     best_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int wb_prefix_share_tables(int dir, int batch, int n_hyp, const int32_t* hyp_utt_host, const int32_t* hyp_len_host,
+                           const int32_t* hyp_tok0_host, const int32_t* hyp_tokens_host, int sos, int32_t* uniq_of_row,
+                           int32_t* rep_row, int32_t* tok_u, int32_t* pos_u, int32_t* utt_q0_u, int32_t* utt_qn_u) {
+    WB_REQUIRE(batch > 0 && n_hyp >= 0 && hyp_utt_host && hyp_len_host && hyp_tok0_host && hyp_tokens_host && uniq_of_row &&
+                   rep_row && tok_u && pos_u && utt_q0_u && utt_qn_u && (dir == 0 || dir == 1),
+               WB_ERR_BAD_ARG, "prefix_share_tables: bad argument");
+    std::vector<int> utt_hyp0(batch, 0), utt_nhyp(batch, 0), hyp_row0(n_hyp > 0 ? n_hyp : 1, 0);
+    int prev = -1, r = 0;
+    for (int h = 0; h < n_hyp; ++h) {
+        const int b = hyp_utt_host[h];
+        WB_REQUIRE(b >= 0 && b < batch && b >= prev, WB_ERR_BAD_ARG, "prefix_share_tables: hyp_utt must be non-decreasing");
+        if (b != prev) {
+            utt_hyp0[b] = h;
+            prev = b;
+        }
+        utt_nhyp[b] += 1;
+        hyp_row0[h] = r;
+        r += hyp_len_host[h] + 1;
+    }
+    int max_u = 0;
+    return build_prefix_share(dir, batch, utt_hyp0.data(), utt_nhyp.data(), hyp_row0.data(), hyp_len_host, hyp_tok0_host,
+                              hyp_tokens_host, sos, uniq_of_row, rep_row, tok_u, pos_u, utt_q0_u, utt_qn_u, &max_u);
 }
 
 int wb_decoder_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows,
