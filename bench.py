@@ -152,6 +152,10 @@ def _cpu_worker_init(wl_name, threads):
     _W.update(wl=wl, cfg=cfg, sd=sd, rows=rows)
 
 
+def _cpu_worker_ready(i):
+    return os.getpid()
+
+
 def _cpu_worker_step(i):
     toks = cpu_oracle_step(_W["sd"], _W["cfg"], [_W["rows"][i % len(_W["rows"])]], _W["wl"])
     return len(toks[0])
@@ -168,6 +172,8 @@ class CpuArm:
         self.wl = workload(wl_name)
         self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_cpu_worker_init,
                                                  initargs=(wl_name, self.threads))
+        # worker start-up (interpreter, torch import, weight synthesis) is not part of any timed step
+        self.pool.map(_cpu_worker_ready, range(4 * self.procs), chunksize=1)
 
     def step(self, utts_per_proc=1):
         """one pass over procs x utts_per_proc utterances; returns (audio seconds, wall seconds)"""
@@ -210,7 +216,7 @@ def run_reference_arm(args):
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     arm.close()
-    print(json.dumps(line), flush=True)
+    args.emit(line)
     return 0
 
 
@@ -235,6 +241,17 @@ def main():
                     help="batches in flight per GPU (host threads x CUDA streams sharing one weight replica); "
                          "1 = strictly sequential steps")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything else that lands on fd 1 while the benchmark runs
+    # (NCCL prints its version banner there from native code) is sent to stderr instead
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(_json_fd, (json.dumps(line) + "\n").encode())
+
+    args.emit = emit
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -464,7 +481,7 @@ def main():
                                 "sample": arm.describe()}
         arm.close()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        args.emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
