@@ -237,7 +237,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event profiler")
     ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the GEMM / FFN kernels leave free (-1: 8 when in flight > 1)")
-    ap.add_argument("--inflight", type=int, default=3,
+    ap.add_argument("--inflight", type=int, default=4,
                     help="batches in flight per GPU (host threads x CUDA streams sharing one weight replica); "
                          "1 = strictly sequential steps")
     args = ap.parse_args()

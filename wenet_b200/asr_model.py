@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import check, cur_stream, ptr
-from .search import DecodeResult
+from .search import DecodeResult, LazyDecodeResult
 from .weights import DeviceModel, ModelSpec
 
 
@@ -516,27 +516,16 @@ class B200ASRModel:
         th, mh, ev = fetch
         ev.synchronize()
         L = th.shape[2]
-        th = th.reshape(-1, L)[meta.slot]                                           # (n_hyp, L)
+        th = th.reshape(-1, L)[meta.slot]            # (n_hyp, L) copies: the pinned staging is reused by the next decode
         mh = mh.reshape(-1, L)[meta.slot]
-        tok_mask = np.arange(L)[None, :] < meta.hyp_len[:, None]
-        tok_list, time_list = th[tok_mask].tolist(), mh[tok_mask].tolist()
-        ends = np.cumsum(meta.hyp_len).tolist()
         score_list = meta.scores.tolist()
+        ends = np.cumsum(meta.nh).tolist()
         out = []
         h = 0
-        a = 0
         for b in range(bd.B):
-            n = int(meta.nh[b])
-            nbest, ntimes = [], []
-            for r in range(n):
-                e = ends[h + r]
-                nbest.append(tuple(tok_list[a:e]))
-                ntimes.append(time_list[a:e])
-                a = e
-            nscores = score_list[h:h + n]
-            out.append(DecodeResult(tokens=nbest[0], score=nscores[0], times=ntimes[0], nbest=nbest,
-                                    nbest_scores=nscores, nbest_times=ntimes))
-            h += n
+            e = ends[b]
+            out.append(LazyDecodeResult(score_list[h], score_list[h:e], th[h:e], mh[h:e], meta.hyp_len[h:e]))
+            h = e
         return out
 
     def _flatten_hyps(self, hyps_per_utt):
@@ -597,33 +586,39 @@ class B200ASRModel:
     def _rescore_results(self, rs, meta, beam_out: List[DecodeResult], reverse_weight: float):
         rs.ev.synchronize()
         B = len(beam_out)
-        l2r_h, r2l_h, hs, bh = rs.l2r, rs.r2l, rs.hs, rs.best
         use_r2l = rs.use_r2l
         hyp_len = meta.hyp_len
+        hs = rs.hs.copy()                        # pinned staging buffers are reused by the next decode
+        bh = rs.best.tolist()
         row0 = np.concatenate([[0], np.cumsum(hyp_len.astype(np.int64) + 1)])
-        nb_per_utt = np.bincount(meta.hyp_utt, minlength=B)
-        h0s = np.concatenate([[0], np.cumsum(nb_per_utt)[:-1]])
+        ends = np.cumsum(meta.nh).tolist()
+        hs_list = hs.tolist()
         out = []
+        h0 = 0
         for b in range(B):
-            nb = int(nb_per_utt[b])
-            bi = int(bh[b])
-            h = int(h0s[b]) + bi
+            bi = bh[b]
+            h = h0 + bi
             n = int(hyp_len[h])
             r0 = int(row0[h])
-            seg = l2r_h[r0:r0 + n + 1]
-            tc = np.exp(seg[:n].astype(np.float64))
-            score = np.cumsum(seg, dtype=np.float32)[-1]          # sequential fp32 sum, as the reference
-            if use_r2l:
-                rseg = r2l_h[r0:r0 + n + 1]
-                # r_decoder_out[i][len-j-1][hyp[j]] (search.py:438-441): position n-1-j scores token j
-                tc = (tc + np.exp(rseg[:n][::-1].astype(np.float64))) / 2
-                r_score = np.cumsum(np.concatenate([rseg[:n][::-1], rseg[n:n + 1]]), dtype=np.float32)[-1]
-                score = np.float32(score * np.float32(1 - reverse_weight) + r_score * np.float32(reverse_weight))
-            conf = math.exp(float(score) / (n + 1))
-            res = DecodeResult(beam_out[b].nbest[bi], float(hs[h]), confidence=conf,
-                               times=beam_out[b].nbest_times[bi], tokens_confidence=tc.tolist())
-            res.nbest_scores = hs[int(h0s[b]):int(h0s[b]) + nb].tolist()   # extra: all rescored hypotheses
-            out.append(res)
+            seg = rs.l2r[r0:r0 + n + 1].copy()
+            rseg = rs.r2l[r0:r0 + n + 1].copy() if use_r2l else None
+
+            def conf_fn(seg=seg, rseg=rseg, n=n):
+                tc = np.exp(seg[:n].astype(np.float64))
+                score = np.cumsum(seg, dtype=np.float32)[-1]          # sequential fp32 sum, as the reference
+                if rseg is not None:
+                    # r_decoder_out[i][len-j-1][hyp[j]] (search.py:438-441): position n-1-j scores token j
+                    tc = (tc + np.exp(rseg[:n][::-1].astype(np.float64))) / 2
+                    r_score = np.cumsum(np.concatenate([rseg[:n][::-1], rseg[n:n + 1]]), dtype=np.float32)[-1]
+                    score = np.float32(score * np.float32(1 - reverse_weight) + r_score * np.float32(reverse_weight))
+                return math.exp(float(score) / (n + 1)), tc.tolist()
+
+            bo = beam_out[b]
+            # tokens / times of the chosen hypothesis come from the beam result's packed rows; nbest_scores carries all
+            # rescored hypotheses of the utterance (extra over the reference, which returns only the best)
+            out.append(LazyDecodeResult(hs_list[h], hs_list[h0:ends[b]], bo._tok_rows, bo._time_rows, bo._lens, best=bi,
+                                        conf_fn=conf_fn))
+            h0 = ends[b]
         return out
 
     # ----- asr_model.py:453-547 -----
