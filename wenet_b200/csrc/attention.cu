@@ -831,33 +831,42 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tmem_ld_32x32b_x32(tmem_s + lane_sel, r0);
         tmem_ld_32x32b_x32(tmem_s + lane_sel + 32u, r1);
         tmem_ld_wait();
-        // scores (log2 domain) in place, tile maximum
+        // scores (log2 domain) in place, tile maximum.  Two explicit loops: with the mask test inside one loop the
+        // compiler predicates the compares instead of branching around them, and they cost issue slots on every tile.
         float mt0 = -INFINITY, mt1 = -INFINITY, mt2 = -INFINITY, mt3 = -INFINITY;
+        if (tile_full) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            uint32_t* r = hh ? r1 : r0;
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t* r = hh ? r1 : r0;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 c4 = *reinterpret_cast<const float4*>(cc + hh * 32 + i);
-                float s0 = fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x);
-                float s1 = fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y);
-                float s2 = fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z);
-                float s3 = fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w);
-                if (!tile_full) {
-                    const int key = j0 + hh * 32 + i;
-                    if (key < row_lo || key >= row_hi) s0 = -INFINITY;
-                    if (key + 1 < row_lo || key + 1 >= row_hi) s1 = -INFINITY;
-                    if (key + 2 < row_lo || key + 2 >= row_hi) s2 = -INFINITY;
-                    if (key + 3 < row_lo || key + 3 >= row_hi) s3 = -INFINITY;
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(cc + hh * 32 + i);
+                    const float s0 = fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x);
+                    const float s1 = fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y);
+                    const float s2 = fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z);
+                    const float s3 = fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w);
+                    mt0 = fmaxf(mt0, s0);
+                    mt1 = fmaxf(mt1, s1);
+                    mt2 = fmaxf(mt2, s2);
+                    mt3 = fmaxf(mt3, s3);
+                    r[i] = __float_as_uint(s0);
+                    r[i + 1] = __float_as_uint(s1);
+                    r[i + 2] = __float_as_uint(s2);
+                    r[i + 3] = __float_as_uint(s3);
                 }
-                mt0 = fmaxf(mt0, s0);
-                mt1 = fmaxf(mt1, s1);
-                mt2 = fmaxf(mt2, s2);
-                mt3 = fmaxf(mt3, s3);
-                r[i] = __float_as_uint(s0);
-                r[i + 1] = __float_as_uint(s1);
-                r[i + 2] = __float_as_uint(s2);
-                r[i + 3] = __float_as_uint(s3);
+            }
+        } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t* r = hh ? r1 : r0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int key = j0 + hh * 32 + i;
+                    float sv = fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[hh * 32 + i]);
+                    if (key < row_lo || key >= row_hi) sv = -INFINITY;
+                    mt0 = fmaxf(mt0, sv);
+                    r[i] = __float_as_uint(sv);
+                }
             }
         }
         const float mt = fmaxf(fmaxf(mt0, mt1), fmaxf(mt2, mt3));
