@@ -808,8 +808,8 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     for (int kt = kt0; kt < kt1; ++kt) {
         const int j0 = kt * KN;
         const float c_next = fetch_c(kt + 1);
-        if (tid == 0) {
-            if (kt == kt0) mbar_wait(bar_q, 0);
+        if (tid == 0 && kt == kt0) {   // later score MMAs are issued one tile ahead, together with the P V MMA (below)
+            mbar_wait(bar_q, 0);
             mbar_wait(bar_k, ph);
             tc_fence_after();
             const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
@@ -926,6 +926,19 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 umma_f16(tmem_o, make_smem_desc_sw128(pa + ks * 32, 16, 1024),
                          make_smem_desc_sw128(va + ks * 2048, 1024, 1024), idesc_o, (kt != kt0 || ks != 0) ? 1u : 0u);
             umma_commit(bar_pv);
+            if (kt + 1 < kt1) {
+                // S(kt+1) = Q K'(kt+1)^T right behind the P V MMAs: every thread pulled S(kt) out of TMEM before the
+                // barrier above and K'(kt+1) was requested when S(kt) completed, so the next tile's scores are ready
+                // (or nearly) when the threads come back from waiting for P V - one MMA round trip per tile less.
+                mbar_wait(bar_k, ph ^ 1);
+                tc_fence_after();
+                const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+                for (int k2 = 0; k2 < DK / 16; ++k2)
+                    umma_f16(tmem_s, make_smem_desc_sw128(qa + k2 * 32, 16, 1024),
+                             make_smem_desc_sw128(ka + k2 * 32, 16, 1024), idesc_s, k2 != 0);
+                umma_commit(bar_s);
+            }
         }
         // P / V buffers, the S accumulator and O (possible rescale) are touched again next tile: wait for the P V MMAs
         mbar_wait(bar_pv, ph);
