@@ -270,3 +270,34 @@ def test_prefix_share_tables_host_logic():
                 r += len(h) + 1
             assert ids == set(range(int(q0[b]), int(q0[b]) + int(qn[b])))
         assert int(qn.sum()) == U
+
+
+def test_lazy_decode_result_matches_eager_fields():
+    """LazyDecodeResult (what decode() returns) exposes the reference DecodeResult fields with the same Python types,
+    materialised from the packed rows on first access; copies and pickles behave like plain objects."""
+    import copy
+    import pickle
+
+    import numpy as np
+    from wenet_b200.search import DecodeResult, LazyDecodeResult
+    toks = np.array([[5, 6, 7, 0], [5, 9, 0, 0], [8, 8, 8, 8]], dtype=np.int32)
+    times = np.array([[1, 4, 9, 0], [1, 5, 0, 0], [2, 3, 4, 6]], dtype=np.int32)
+    lens = np.array([3, 2, 4], dtype=np.int32)
+    r = LazyDecodeResult(-1.5, [-1.5, -2.0, -3.25], toks, times, lens, best=1, conf_fn=lambda: (0.75, [0.5, 0.25]))
+    assert isinstance(r, DecodeResult)
+    assert "tokens" not in r.__dict__ and "nbest" not in r.__dict__
+    assert r.tokens == (5, 9) and isinstance(r.tokens, tuple) and all(isinstance(t, int) for t in r.tokens)
+    assert r.times == [1, 5]
+    assert r.nbest == [(5, 6, 7), (5, 9), (8, 8, 8, 8)]
+    assert r.nbest_times == [[1, 4, 9], [1, 5], [2, 3, 4, 6]]
+    assert r.nbest_scores == [-1.5, -2.0, -3.25] and r.score == -1.5 and r.text == ''
+    assert r.confidence == 0.75 and r.tokens_confidence == [0.5, 0.25]
+    assert "tokens" in r.__dict__                      # cached after the first read
+    with pytest.raises(AttributeError):
+        r.no_such_field
+    r2 = LazyDecodeResult(0.0, [0.0], toks[:1], times[:1], lens[:1])
+    assert r2.confidence == 0.0 and r2.tokens_confidence is None and r2.tokens == (5, 6, 7)
+    c = copy.deepcopy(LazyDecodeResult(-1.0, [-1.0], toks, times, lens))
+    assert c.nbest[2] == (8, 8, 8, 8)
+    p = pickle.loads(pickle.dumps(LazyDecodeResult(-1.0, [-1.0], toks, times, lens, best=2)))
+    assert p.tokens == (8, 8, 8, 8)
