@@ -7,18 +7,23 @@
 //    convolution.py:46-53,88-95, subsampling.py:194-195,203-228, ctc.py:44, decoder.py:96-103).
 //
 // Structure (one persistent CTA per SM, 320 threads):
-//   warp 0      : TMA producer   — cp.async.bulk.tensor 2-D loads of A (128x64) and B (BNx64)
-//                                  tiles, SWIZZLE_128B, ring of kStages smem slots (mbarrier
-//                                  full/empty)
-//   warp 1      : MMA issuer     — one lane issues tcgen05.mma.cta_group::1.kind::f16
-//                                  (M=128, N=BN, K=16) x4 per k-block into a TMEM accumulator;
-//                                  tcgen05.commit frees smem slots / publishes the accumulator
-//   warps 2..9  : epilogue       — two warps per TMEM lane quarter, tcgen05.ld 32x32b.x32 (thread ==
-//                                  accumulator row), bias + activation / GLU / alpha, staged through
-//                                  SWIZZLE_128B shared memory and written by TMA store (bf16, fp32) or
-//                                  TMA reduce-add (fp32 residual stream: no read-modify-write in the SM).
-//                                  TMEM holds two accumulator stages so the epilogue of tile i
-//                                  overlaps the main loop of tile i+1.
+//   warp 0      : TMA producer   — cp.async.bulk.tensor loads of A (128x64) and B (BNx64) tiles, SWIZZLE_128B, ring of
+//                                  kStages smem slots (mbarrier full/empty).  K <= 256: the [BN x K] weight panel of
+//                                  the current n-tile stays resident and only A streams.  conv mode: the A tile is
+//                                  one strided 3-D TMA box of the channels-last conv1 output (implicit im2col).
+//   warp 1      : MMA issuer     — one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per
+//                                  k-block into a TMEM accumulator; tcgen05.commit frees smem slots / publishes the
+//                                  accumulator
+//   warps 2..9  : epilogue       — two warps per TMEM lane quarter; tcgen05.ld 32x32b.x32 (thread == accumulator
+//                                  row) software-pipelined one 32-column chunk ahead; bias slice prefetched before the
+//                                  accumulator wait and read back from shared memory; activation / GLU / alpha;
+//                                  staged through SWIZZLE_128B shared memory and written by TMA store (bf16, fp32) or
+//                                  TMA reduce-add (fp32 residual stream: no read-modify-write in the SM); EPI_LSE keeps
+//                                  only per-row log-sum-exp partials.  TMEM holds two accumulator stages so the
+//                                  epilogue of tile i overlaps the main loop of tile i+1.
+// The epilogue variant is a template parameter for BN = 256 (one specialised kernel per variant; the generic kernel
+// with a run-time switch is ~150 KB of SASS and stalls on instruction fetch) and a run-time switch for BN = 128.
+// wb_gemm_diag reads the in-kernel stall accounting (clock64 around every mbarrier wait) used to tune this file.
 #include "common.cuh"
 #include "kernels.h"
 #include <string.h>
