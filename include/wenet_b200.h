@@ -64,7 +64,9 @@ int wb_prof_collect(double* ms, double* work, long long* launches);
  * out8 = {producer waits for a ring slot, MMA waits for operands, MMA waits for a drained accumulator stage,
  * epilogue waits for an accumulator, epilogue waits for its staging buffer, epilogue loop time (one warp),
  * CTA lifetime, tiles, epilogue tcgen05.ld wait, epilogue bias + activation, epilogue staging stores + TMA issue, 0}
- * (12 values).  Tuning aid used by tools/bench_ops.py; out12 may be NULL (reset only). */
+ * (12 values).  Tuning aid used by tools/bench_ops.py; out12 may be NULL (reset only).  The accounting is compiled
+ * into the kernel only when the library is built with -DWB_GEMM_DIAG (NVCC_EXTRA=-DWB_GEMM_DIAG python -m
+ * wenet_b200.build --force); the default build returns WB_ERR_UNSUPPORTED. */
 int wb_gemm_diag(uint64_t* out12, int reset);
 
 /* ------------------------------------------------------------------------------------------
@@ -112,7 +114,12 @@ typedef struct {
   int32_t dec_ffn_dim;
   int32_t max_pos;     /* positional-encoding table length (5000) */
   int32_t has_cmvn;    /* GlobalCMVN present */
-  int32_t precise;     /* 0: bf16 operands; 1: bf16x3 split operands (fp32-grade GEMMs) */
+  int32_t precise;     /* 0: bf16 operands (throughput mode).  1: PARITY mode - every encoder / CTC GEMM runs as bf16x3
+                          (activations [hi | lo | hi], weights [hi | hi | lo] along K: the packer must deliver the
+                          encoder, conv2, embed and CTC weights as [N][3K]), q/k/v, attention and the depthwise conv
+                          in fp32 on CUDA cores: encoder_out / CTC log-probs within 1e-3 of the fp32 reference.
+                          enc_out_bf16_dev then has 3 * d_model columns ([hi | lo | hi]) everywhere in this API;
+                          the rescoring decoder reads its hi block and stays bf16.  Full forward only. */
   float ln_eps;        /* 1e-5 */
 } wb_model_config;
 
@@ -269,14 +276,12 @@ int wb_decoder_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t
 int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K,
                const float* bias_dev, int epi, float alpha, void* c_dev, int64_t ldc, int split3,
                wb_stream_t stream);
-/* fused feed-forward (d_model == 256): x += alpha * (act(a W1^T + b1) W2^T + b2); W1 [ff][d], W2 [d][ff] bf16;
- * act 0 = SiLU (encoder), 1 = ReLU (decoder) */
-int wb_op_ffn(const void* a_dev, int64_t lda, const void* w1_dev, const float* b1_dev, const void* w2_dev,
-              const float* b2_dev, int M, int d, int ff, float alpha, int act, float* x_dev, int64_t ldx,
-              wb_stream_t stream);
 int wb_op_layernorm(const float* x_dev, int64_t ldx, int M, int d, const float* gamma_dev,
                     const float* beta_dev, float eps, void* out_bf16_dev, int64_t ld_bf16, int split3,
                     float* out_f32_dev, int64_t ld_f32, wb_stream_t stream);
+/* fp32 rows -> bf16 rows; split3 != 0 writes [hi | lo | hi] blocks of width d (row pitch ld_bf16 >= 3 d) */
+int wb_op_cast_bf16(const float* x_dev, int64_t ldx, int M, int d, void* out_bf16_dev, int64_t ld_bf16, int split3,
+                    wb_stream_t stream);
 int wb_op_attention(const void* q_dev, int64_t ldq, int64_t q_rows, int q_col0, const void* k_dev,
                     int64_t ldk, int64_t k_rows, int k_col0, const void* v_dev, int64_t ldv,
                     int64_t v_rows, int v_col0, const float* kbias_dev, int ld_kbias,
@@ -299,11 +304,6 @@ int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blan
                           wb_stream_t stream);
 int wb_op_lse_topk(const float* logits_dev, int64_t ldl, int M, int V, int blank_id, float blank_penalty,
                    int topk, float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream);
-
-/* hardware probe (tools/tests only): one 3-D TMA tiled load with element strides; see csrc/probe.cu */
-int wb_probe_tma3d(const void* base_dev, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                   const uint32_t* estr, int c0, int c1, int c2, uint32_t expect_bytes, uint32_t copy_bytes,
-                   uint8_t* out_dev, int* status_dev, wb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -112,9 +112,103 @@ def model_goldens(name, recipe, ns, beam=4, ctc_weight=0.5, store_logp=True, chu
           "nbest0", out["nbest0_0"].tolist()[:12], "size %.0f KB" % (os.path.getsize(os.path.join(GOLD, name + ".npz")) / 1024))
 
 
+def _ref_model(recipe):
+    cfg = synth.recipe(recipe)
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    ref_cfg = dict(cfg, cmvn=None)
+    ref_cfg.pop("cmvn_conf", None)
+    model = shim.init_reference_model(ref_cfg)
+    from wenet.models.transformer.cmvn import GlobalCMVN
+    model.encoder.global_cmvn = GlobalCMVN(torch.zeros(80), torch.ones(80))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing)
+    model.eval()
+    return cfg, model
+
+
+def _ref_batch(ns):
+    pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
+    feats = [ref_fbank(pcm[b], n) for b, n in enumerate(ns)]
+    lens = torch.tensor([f.shape[0] for f in feats])
+    xs = torch.zeros(len(ns), int(lens.max()), 80)
+    for b, f in enumerate(feats):
+        xs[b, :f.shape[0]] = f
+    return xs, lens
+
+
+def long_goldens(name, recipe, ns, beam=10, ctc_weight=0.5, row_stride=4):
+    """BASELINE-sized utterances (30 s / 17 s on the 12L/256d recipe, 10 s on 24L/512d): encoder_out rows
+    [::row_stride] of the valid frames, CTC top-k (values + ids), greedy / n-best / rescoring results.  No [T', V]
+    log-prob matrix (12.7 MB per 30 s utterance)."""
+    torch.manual_seed(0)
+    cfg, model = _ref_model(recipe)
+    xs, lens = _ref_batch(ns)
+    out = {"num_samples": np.array(ns), "beam": np.array(beam), "ctc_weight": np.array(ctc_weight),
+           "row_stride": np.array(row_stride)}
+    from wenet.models.transformer.search import (attention_rescoring, ctc_greedy_search, ctc_prefix_beam_search)
+    with torch.no_grad():
+        enc, mask = model.encoder(xs, lens, decoding_chunk_size=-1, num_decoding_left_chunks=-1)
+        enc_lens = mask.squeeze(1).sum(1)
+        out["enc_lens"] = enc_lens.numpy()
+        logp = model.ctc_logprobs(enc)
+        tv, ti = logp.topk(beam, dim=-1)
+        g = ctc_greedy_search(logp, enc_lens)
+        pb = ctc_prefix_beam_search(logp, enc_lens, beam)
+        rw = cfg["model_conf"].get("reverse_weight", 0.0)
+        rs = attention_rescoring(model, pb, enc, enc_lens, ctc_weight, rw)
+        for b in range(len(ns)):
+            n = int(enc_lens[b])
+            out["enc_rows%d" % b] = enc[b, :n:row_stride].numpy()
+            out["topk_val%d" % b] = tv[b, :n].numpy()
+            out["topk_idx%d" % b] = ti[b, :n].numpy().astype(np.int32)
+            out["greedy%d" % b] = np.array(g[b].tokens, dtype=np.int32)
+            r = pb[b]
+            out["nbest_n%d" % b] = np.array(len(r.nbest))
+            for i, (h, t) in enumerate(zip(r.nbest, r.nbest_times)):
+                out["nbest%d_%d" % (b, i)] = np.array(h, dtype=np.int32)
+                out["nbest_time%d_%d" % (b, i)] = np.array(t, dtype=np.int32)
+            out["nbest_scores%d" % b] = np.array(r.nbest_scores, dtype=np.float64)
+            out["resc_tokens%d" % b] = np.array(rs[b].tokens, dtype=np.int32)
+            out["resc_score%d" % b] = np.array(rs[b].score, dtype=np.float64)
+            out["resc_conf%d" % b] = np.array(rs[b].confidence, dtype=np.float64)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "enc_lens", enc_lens.tolist(), "greedy tokens", [len(out["greedy%d" % b]) for b in range(len(ns))],
+          "blank frac %.2f" % float((ti[..., 0] == 0).float().mean()), "size %.0f KB" % (os.path.getsize(path) / 1024))
+
+
+def stream_goldens(name, recipe, n_samples, chunk=16, left=4, row_stride=2, cache_layers=(0, -1)):
+    """BASELINE configs[3]: encoder.forward_chunk with chunk_size 16 / num_left_chunks 4 over a whole utterance
+    (>= 20 chunks) by the reference's own forward_chunk_by_chunk loop (encoder.py:302-362), plus the caches after
+    the last chunk (attention cache of the first / last layer only, to keep the fixture small)."""
+    torch.manual_seed(0)
+    cfg, model = _ref_model(recipe)
+    xs, lens = _ref_batch([n_samples])
+    with torch.no_grad():
+        ys, _ = model.encoder.forward_chunk_by_chunk(xs[0:1, :lens[0]], chunk, left)
+        # the same loop by hand, to capture the final caches
+        win, stride = (chunk - 1) * 4 + 7, 4 * chunk
+        att = torch.zeros(0, 0, 0, 0)
+        cnn = torch.zeros(0, 0, 0, 0)
+        off, outs = 0, []
+        for cur in range(0, int(lens[0]) - 7 + 1, stride):
+            y, att, cnn = model.encoder.forward_chunk(xs[0:1, cur:min(cur + win, int(lens[0]))], off, chunk * left, att, cnn)
+            outs.append(y)
+            off += y.size(1)
+        assert torch.equal(torch.cat(outs, 1), ys)
+    out = {"num_samples": np.array(n_samples), "chunk": np.array([chunk, left]), "row_stride": np.array(row_stride),
+           "n_chunks": np.array(len(outs)), "n_out": np.array(ys.size(1)),
+           "stream_rows": ys[0, ::row_stride].numpy(), "att_last": att[list(cache_layers)].numpy(),
+           "att_layers": np.array([c % att.size(0) for c in cache_layers]), "cnn_last": cnn.numpy()}
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "chunks", len(outs), "frames", ys.size(1), "size %.0f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["fbank", "tiny", "tiny_bn", "u2pp_small"]
+    which = sys.argv[1:] or ["fbank", "tiny", "tiny_bn", "u2pp_small", "u2pp_small_long", "u2pp_large_10s",
+                             "u2pp_small_stream"]
     if "fbank" in which:
         fbank_goldens()
     if "tiny" in which:
@@ -123,3 +217,9 @@ if __name__ == "__main__":
         model_goldens("tiny_bn", "tiny_bn", [32000 + 123, 20800, 48000], stream=False)
     if "u2pp_small" in which:
         model_goldens("u2pp_small", "u2pp_small", [48000, 30000], beam=10, store_logp=False, chunk=(16, 4), stream=False)
+    if "u2pp_small_long" in which:      # BASELINE configs[1] utterance size: 30 s + a ragged 17 s companion
+        long_goldens("u2pp_small_long", "u2pp_small", [480000, 272000], beam=10, row_stride=4)
+    if "u2pp_large_10s" in which:       # BASELINE configs[2] model (24L/512d/8h) at depth
+        long_goldens("u2pp_large_10s", "u2pp_large", [160000], beam=10, row_stride=2)
+    if "u2pp_small_stream" in which:    # BASELINE configs[3]: chunk 16 / left 4, 21 chunks on the 12-layer model
+        stream_goldens("u2pp_small_stream", "u2pp_small", 224000)

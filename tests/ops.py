@@ -1,14 +1,14 @@
 """Operator-level Python wrappers over the C ABI (torch tensors in, torch tensors out).
 
-These exist for the parity tests and micro-benchmarks; the model path (encoder.py / asr_model.py)
-calls the stage-level entry points.  Every function requires CUDA tensors — there is no fallback.
+TEST / BENCH infrastructure (tests/test_ops_gpu.py, tools/bench_ops.py): the model path (wenet_b200/asr_model.py) calls
+the stage-level entry points, never these.  Every function requires CUDA tensors — there is no fallback.
 """
 import math
 
 import torch
 
-from . import _lib
-from ._lib import check, cur_stream, ptr
+from wenet_b200 import _lib
+from wenet_b200._lib import check, cur_stream, ptr
 
 EPI_BF16, EPI_BF16_SILU, EPI_BF16_RELU, EPI_RESID_F32, EPI_GLU_BF16, EPI_F32 = range(6)
 
@@ -35,16 +35,6 @@ def gemm(a, b, bias=None, epi=EPI_BF16, alpha=1.0, out=None, split3=False):
     check(_lib.load().wb_op_gemm(ptr(a), a.stride(0), ptr(b), M, N, K, ptr(bias), epi, float(alpha),
                                  ptr(out), out.stride(0), int(split3), cur_stream()), "wb_op_gemm")
     return out
-
-
-def ffn_fused(a, w1, b1, w2, b2, x, alpha=0.5, act=0):
-    """x += alpha * (silu(a @ w1.T + b1) @ w2.T + b2) in one kernel (d_model == 256)."""
-    _need_cuda(a, w1, w2, x)
-    M, d = a.shape
-    ff = w1.shape[0]
-    check(_lib.load().wb_op_ffn(ptr(a), a.stride(0), ptr(w1), ptr(b1), ptr(w2), ptr(b2), M, d, ff, float(alpha), int(act),
-                                ptr(x), x.stride(0), cur_stream()), "wb_op_ffn")
-    return x
 
 
 def layernorm(x, gamma, beta, eps=1e-5, want_bf16=True, want_f32=False, split3=False):

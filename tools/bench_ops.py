@@ -7,10 +7,13 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import ctypes as C  # noqa: E402
 
-from wenet_b200 import _lib, ops  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ops  # noqa: E402
+from wenet_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 
@@ -32,7 +35,7 @@ def timeit(name, fn, flops=0.0, bytes_=0.0, iters=8):
     for _ in range(2):
         fn()
     ts = []
-    lib.wb_gemm_diag(None, 1)
+    have_diag = lib.wb_gemm_diag(None, 1) == 0     # only in a -DWB_GEMM_DIAG build
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         flush.zero_()    # ~45 us of GPU work: the host enqueues the timed launch behind it, so no launch gap is timed
@@ -42,7 +45,7 @@ def timeit(name, fn, flops=0.0, bytes_=0.0, iters=8):
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
-    if name.startswith("gemm"):
+    if name.startswith("gemm") and have_diag:
         dg = (C.c_uint64 * 12)()
         lib.wb_gemm_diag(dg, 1)
         n_l = iters

@@ -18,7 +18,8 @@ def __getattr__(name):
         "compute_fbank": ("fbank", "compute_fbank"),
         "FbankExtractor": ("fbank", "FbankExtractor"),
         "B200ASRModel": ("asr_model", "B200ASRModel"),
-        "B200ConformerEncoder": ("encoder", "B200ConformerEncoder"),
+        "B200ConformerEncoder": ("asr_model", "B200ConformerEncoder"),
+        "StreamingSession": ("asr_model", "StreamingSession"),
         "DecodeResult": ("search", "DecodeResult"),
         "install": ("plugin", "install"),
         "DeviceModel": ("weights", "DeviceModel"),

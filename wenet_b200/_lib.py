@@ -68,10 +68,9 @@ _PROTOS = {
     "wb_prefix_share_tables": (i32, [i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "wb_decoder_logprobs": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp,
                                    i64, vp, sz, vp]),
-    "wb_probe_tma3d": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, C.c_uint32, C.c_uint32, vp, vp, vp]),
     "wb_op_gemm": (i32, [vp, i64, vp, i32, i32, i32, vp, i32, f32, vp, i64, i32, vp]),
-    "wb_op_ffn": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, i64, vp]),
     "wb_op_layernorm": (i32, [vp, i64, i32, i32, vp, vp, f32, vp, i64, i32, vp, i64, vp]),
+    "wb_op_cast_bf16": (i32, [vp, i64, i32, i32, vp, i64, i32, vp]),
     "wb_op_attention": (i32, [vp, i64, i64, i32, vp, i64, i64, i32, vp, i64, i64, i32, vp, i32, vp, vp,
                                vp, vp, i32, i32, i32, i32, i32, f32, vp, i64, i32, i32, vp]),
     "wb_op_relpos_kprep": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp]),

@@ -76,30 +76,22 @@ class B200ConformerEncoder:
     def forward_chunk(self, xs, offset, required_cache_size, att_cache=None, cnn_cache=None, att_mask=None):
         return self._o._forward_chunk(xs, offset, required_cache_size, att_cache, cnn_cache)
 
-    # encoder.py:302-362
     def forward_chunk_by_chunk(self, xs: torch.Tensor, decoding_chunk_size: int,
                                num_decoding_left_chunks: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
-        assert decoding_chunk_size > 0
-        assert self.static_chunk_size > 0 or self.use_dynamic_chunk
-        subsampling = self.embed.subsampling_rate
-        context = self.embed.right_context + 1
-        stride = subsampling * decoding_chunk_size
-        decoding_window = (decoding_chunk_size - 1) * subsampling + context
-        num_frames = xs.size(1)
-        att_cache = torch.zeros((0, 0, 0, 0), device=xs.device)
-        cnn_cache = torch.zeros((0, 0, 0, 0), device=xs.device)
-        outputs = []
-        offset = 0
-        required_cache_size = decoding_chunk_size * num_decoding_left_chunks
-        for cur in range(0, num_frames - context + 1, stride):
-            end = min(cur + decoding_window, num_frames)
-            chunk_xs = xs[:, cur:end, :]
-            (y, att_cache, cnn_cache) = self.forward_chunk(chunk_xs, offset, required_cache_size, att_cache, cnn_cache)
-            outputs.append(y)
-            offset += y.size(1)
-        ys = torch.cat(outputs, 1)
-        masks = torch.ones((1, 1, ys.size(1)), device=ys.device, dtype=torch.bool)
-        return ys, masks
+        """Whole-utterance streaming simulation, same contract as BaseEncoder.forward_chunk_by_chunk
+        (wenet/models/transformer/encoder.py:302-362): windows of (chunk-1)*4+7 frames every 4*chunk frames, the last
+        one possibly shorter.  The steady-state steps are replayed as a CUDA graph by StreamingSession."""
+        if decoding_chunk_size <= 0:
+            raise ValueError("forward_chunk_by_chunk needs decoding_chunk_size > 0")
+        if not (self.static_chunk_size > 0 or self.use_dynamic_chunk):
+            raise ValueError("forward_chunk_by_chunk needs a model trained with chunk masks")
+        sess = StreamingSession(self._o, decoding_chunk_size, num_decoding_left_chunks)
+        hop = sess.window - self.embed.right_context - 1 + self.embed.subsampling_rate   # = 4 * chunk
+        total = xs.size(1)
+        pieces = [sess.step(xs[:, lo:lo + sess.window]).clone()
+                  for lo in range(0, total - self.embed.right_context, hop)]
+        ys = torch.cat(pieces, 1)
+        return ys, torch.ones((1, 1, ys.size(1)), device=ys.device, dtype=torch.bool)
 
 
 class StreamingSession:
@@ -132,7 +124,7 @@ class StreamingSession:
         dev = m.device
         L, H, d, K = spec.enc_layers, spec.heads, spec.d_model, spec.cnn_kernel
         T, c1 = self.window, self.required
-        self.s_xs = torch.zeros(T, 80, device=dev, dtype=torch.float32)
+        self.s_xs = torch.zeros(T, spec.input_dim, device=dev, dtype=torch.float32)
         self.s_att = self.att.to(torch.float32).contiguous().clone()          # (L, H, c1, 128)
         self.s_cnn = self.cnn.to(torch.float32).contiguous().clone()          # (L, 1, d, K-1)
         self.s_ratt = torch.empty_like(self.s_att)
@@ -162,14 +154,28 @@ class StreamingSession:
         self.graph = g
 
     def step(self, xs: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(self.m.device):
+            return self._step(xs)
+
+    def _step(self, xs: torch.Tensor) -> torch.Tensor:
         m = self.m
-        assert xs.size(0) == 1 and xs.size(1) == self.window, "steady streaming expects full windows"
-        steady = self.use_graph and self.att.numel() > 0 and self.att.size(2) == self.required
+        assert xs.size(0) == 1 and xs.size(1) <= self.window
+        # only full windows with a full attention cache go through the graph; the first chunks and a shorter last
+        # window (encoder.py:350 `end = min(cur + decoding_window, num_frames)`) take the regular call
+        steady = (self.use_graph and xs.size(1) == self.window and self.att.numel() > 0
+                  and self.att.size(2) == self.required)
         if steady and self.offset + self.chunk > m.spec.max_pos:
             raise _lib.WbError("utterance longer than the positional table")
         if not steady:
+            if self.graph is not None:       # leaving the graph: its static buffers hold the current caches
+                self.att, self.cnn = self.s_att, self.s_cnn
             y, self.att, self.cnn = m._forward_chunk(xs, self.offset, self.required, self.att, self.cnn)
             self.offset += y.size(1)
+            if self.graph is not None:
+                if self.att.shape == self.s_att.shape:
+                    self.s_att.copy_(self.att)
+                    self.s_cnn.copy_(self.cnn)
+                self.s_off.fill_(self.offset)
             return y
         if self.graph is None:
             self._capture()
@@ -182,13 +188,18 @@ class StreamingSession:
 class B200ASRModel:
     """U2 / U2++ model (ConformerEncoder + CTC + (Bi)TransformerDecoder) on libwenet_b200.so."""
 
-    def __init__(self, configs: dict, state_dict: Dict[str, torch.Tensor], device=None, with_decoder: bool = True):
+    def __init__(self, configs: dict, state_dict: Dict[str, torch.Tensor], device=None, with_decoder: bool = True,
+                 precise: bool = False):
+        """precise=True builds the PARITY mode (include/wenet_b200.h, wb_model_config.precise): bf16x3 encoder / CTC
+        GEMMs + fp32 attention and depthwise conv; encoder_out and CTC log-probs within 1e-3 of the fp32 reference
+        (tests/test_model_gpu.py).  The default is the bf16-operand throughput mode."""
         if not torch.cuda.is_available():
             raise _lib.WbError("B200ASRModel needs a CUDA device (there is no CPU fallback)")
         self.spec = ModelSpec(configs)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         with torch.cuda.device(self.device):
-            self.dm = DeviceModel(self.spec, state_dict, with_decoder=with_decoder)
+            self.dm = DeviceModel(self.spec, state_dict, with_decoder=with_decoder, precise=precise)
+        self.precise = bool(precise)
         self.vocab_size = self.spec.vocab
         self.sos = self.vocab_size - 1      # asr_model.py:62-64
         self.eos = self.vocab_size - 1
@@ -245,6 +256,18 @@ class B200ASRModel:
         """Wrap a loaded reference ASRModel (same weights, same results, B200 kernels)."""
         return cls(configs, {k: v.detach().cpu() for k, v in model.state_dict().items()}, device=device)
 
+    def _operand(self, x: torch.Tensor) -> torch.Tensor:
+        """fp32 rows [R, d] -> the GEMM A operand the library expects for encoder output: bf16 [R, d], or in precise
+        mode bf16 [R, 3d] = [hi | lo | hi]."""
+        x = x.to(torch.float32).contiguous()
+        R, d = x.shape
+        p3 = 3 if self.precise else 1
+        out = torch.empty(max(R, 1), d * p3, device=self.device, dtype=torch.bfloat16)
+        if R > 0:
+            check(self._lib.wb_op_cast_bf16(ptr(x), d, R, d, ptr(out), d * p3, int(self.precise), cur_stream()),
+                  "wb_op_cast_bf16")
+        return out
+
     def _host(self, t: torch.Tensor) -> np.ndarray:
         """device -> host copy of a result tensor (counted)."""
         self.d2h_bytes += t.numel() * t.element_size()
@@ -266,13 +289,17 @@ class B200ASRModel:
                 num_decoding_left_chunks: int) -> _EncOut:
         if not speech.is_cuda:
             raise _lib.WbError("speech must be a CUDA tensor (no CPU fallback)")
-        if decoding_chunk_size == 0:
-            raise NotImplementedError("decoding_chunk_size=0 selects the random *training* chunk "
-                                      "(wenet/utils/mask.py:167-180); pass <0 (full) or >0")
-        if not (self.spec.use_dynamic_chunk or self.spec.static_chunk_size > 0):
-            decoding_chunk_size = -1  # add_optional_chunk_mask ignores the argument (mask.py:193-195)
-        elif not self.spec.use_dynamic_chunk and self.spec.static_chunk_size > 0:
-            decoding_chunk_size = self.spec.static_chunk_size
+        # add_optional_chunk_mask (wenet/utils/mask.py:162-198): the argument only matters for use_dynamic_chunk models
+        if self.spec.use_dynamic_chunk:
+            if decoding_chunk_size == 0:
+                raise NotImplementedError("decoding_chunk_size=0 on a use_dynamic_chunk model selects the random "
+                                          "*training* chunk (wenet/utils/mask.py:173-187); pass <0 (full) or >0")
+            if decoding_chunk_size < 0:
+                num_decoding_left_chunks = -1
+        elif self.spec.static_chunk_size > 0:
+            decoding_chunk_size = self.spec.static_chunk_size      # mask.py:188-194
+        else:
+            decoding_chunk_size, num_decoding_left_chunks = -1, -1  # mask.py:195-196: key-padding mask only
         x = speech.to(torch.float32).contiguous()
         B, T, D = x.shape
         assert D == self.spec.input_dim
@@ -284,7 +311,7 @@ class B200ASRModel:
         eo = _EncOut()
         eo.rows = rows
         eo.f32 = torch.empty(max(rows, 1), d, device=self.device, dtype=torch.float32)
-        eo.bf16 = torch.empty(max(rows, 1), d, device=self.device, dtype=torch.bfloat16)
+        eo.bf16 = torch.empty(max(rows, 1), d * (3 if self.precise else 1), device=self.device, dtype=torch.bfloat16)
         eo.seq_start = torch.zeros(B, device=self.device, dtype=torch.int32)
         eo.seq_len = torch.zeros(B, device=self.device, dtype=torch.int32)
         tp = np.where(lens_host >= 7, ((lens_host - 1) // 2 - 1) // 2, 0).astype(np.int32)
@@ -353,10 +380,11 @@ class B200ASRModel:
         wsb = lib.wb_encoder_chunk_workspace_bytes(self.dm.handle, T, cache_t1)
         ws = self._workspace(wsb)
         oc, on = C.c_int(0), C.c_int(0)
-        check(lib.wb_encoder_forward_chunk(self.dm.handle, ptr(x), T, int(offset), int(required_cache_size), ptr(ac),
-                                           cache_t1, ptr(cc), ptr(y), ptr(r_att), ptr(r_cnn) if spec.cnn_causal else None,
-                                           C.byref(oc), C.byref(on), ptr(ws), ws.numel(), cur_stream()),
-              "wb_encoder_forward_chunk")
+        with torch.cuda.device(self.device):
+            check(lib.wb_encoder_forward_chunk(self.dm.handle, ptr(x), T, int(offset), int(required_cache_size), ptr(ac),
+                                               cache_t1, ptr(cc), ptr(y), ptr(r_att),
+                                               ptr(r_cnn) if spec.cnn_causal else None, C.byref(oc), C.byref(on),
+                                               ptr(ws), ws.numel(), cur_stream()), "wb_encoder_forward_chunk")
         return y, r_att, r_cnn
 
     # ----- CTC -----
@@ -382,8 +410,9 @@ class B200ASRModel:
         B, Tp, d = encoder_out.shape
         eo = _EncOut()
         eo.rows = B * Tp
-        eo.bf16 = encoder_out.reshape(B * Tp, d).to(torch.bfloat16).contiguous()
-        logp, _, _ = self._ctc(eo, 1, blank_id, blank_penalty)
+        with torch.cuda.device(self.device):
+            eo.bf16 = self._operand(encoder_out.reshape(B * Tp, d))
+            logp, _, _ = self._ctc(eo, 1, blank_id, blank_penalty)
         return logp[:, :self.spec.vocab].reshape(B, Tp, self.spec.vocab)
 
     # ----- decode (asr_model.py:267-343) -----
@@ -431,7 +460,7 @@ class B200ASRModel:
         eo = _EncOut()
         eo.rows = B * Tp
         eo.f32 = ys.reshape(B * Tp, d).contiguous()
-        eo.bf16 = eo.f32.to(torch.bfloat16)
+        eo.bf16 = self._operand(eo.f32)
         eo.lens_host = np.full(B, Tp, dtype=np.int32)
         eo.starts_host = (np.arange(B) * Tp).astype(np.int32)
         eo.seq_start = torch.from_numpy(eo.starts_host).to(self.device)
@@ -638,7 +667,7 @@ class B200ASRModel:
         hyp_list = [hy[i, 1:1 + lens[i]].tolist() for i in range(N)]
         hyp_utt, hyp_len, hyp_tok0, toks = self._flatten_hyps([hyp_list])
         Tp = encoder_out.size(1)
-        enc_bf16 = encoder_out[0].to(torch.bfloat16).contiguous()
+        enc_bf16 = self._operand(encoder_out[0])
         R = int(hyp_len.sum()) + N
         ldl = (V + 7) // 8 * 8
         use_r2l = reverse_weight > 0 and self.is_bidirectional_decoder()
@@ -647,10 +676,11 @@ class B200ASRModel:
         wsb = lib.wb_rescoring_workspace_bytes(self.dm.handle, Tp, R)
         ws = self._workspace(wsb)
         starts, slens = _i32([0]), _i32([Tp])   # keep the host arrays alive across the call
-        check(lib.wb_decoder_logprobs(self.dm.handle, ptr(enc_bf16), Tp, ptr(starts), ptr(slens), 1, N,
-                                      ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks), int(hy[0, 0]), self.eos,
-                                      int(use_r2l), ptr(lp), ptr(rlp), ldl, ptr(ws), ws.numel(), cur_stream()),
-              "wb_decoder_logprobs")
+        with torch.cuda.device(self.device):
+            check(lib.wb_decoder_logprobs(self.dm.handle, ptr(enc_bf16), Tp, ptr(starts), ptr(slens), 1, N,
+                                          ptr(hyp_utt), ptr(hyp_len), ptr(hyp_tok0), ptr(toks), int(hy[0, 0]), self.eos,
+                                          int(use_r2l), ptr(lp), ptr(rlp), ldl, ptr(ws), ws.numel(), cur_stream()),
+                  "wb_decoder_logprobs")
         out = torch.zeros(N, L, V, device=self.device, dtype=torch.float32)
         r_out = torch.zeros(N, L, V, device=self.device, dtype=torch.float32) if use_r2l else torch.tensor(0.0)
         r0 = 0

@@ -20,7 +20,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-diag-suppress", "550",
-]
+] + os.environ.get("NVCC_EXTRA", "").split()
 
 
 def _sources():

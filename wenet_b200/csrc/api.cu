@@ -82,7 +82,6 @@ static int finalize_decoder(Model* m, const std::string& pfx, int nlayers, Decod
 
 static int model_finalize(Model* m, cudaStream_t stream) {
     const wb_model_config& c = m->cfg;
-    WB_REQUIRE(c.precise == 0, WB_ERR_UNSUPPORTED, "precise (bf16x3) mode is not wired into the model path yet");
     WB_REQUIRE(c.d_model % 128 == 0 && c.d_model == c.heads * 64, WB_ERR_UNSUPPORTED,
                "unsupported attention geometry: d_model=%d heads=%d (d_k must be 64, d_model %% 128 == 0)", c.d_model,
                c.heads);
@@ -93,6 +92,8 @@ static int model_finalize(Model* m, cudaStream_t stream) {
         WB_REQUIRE(c.dec_heads * 64 == c.d_model && c.dec_ffn_dim % 64 == 0, WB_ERR_UNSUPPORTED,
                    "unsupported decoder geometry (heads=%d)", c.dec_heads);
     const int d = c.d_model, ff = c.ffn_dim;
+    // precise mode: every encoder / CTC weight arrives packed [hi | hi | lo] along K (weights.py split3), K -> 3K
+    const int p3 = c.precise ? 3 : 1;
     m->F1 = (c.input_dim - 3) / 2 + 1;
     m->F2 = (m->F1 - 3) / 2 + 1;
     const void* p;
@@ -106,8 +107,8 @@ static int model_finalize(Model* m, cudaStream_t stream) {
     m->conv1_w = (const float*)p;
     RC(model_get(m, "embed.conv1.b", WB_F32, d, &p));
     m->conv1_b = (const float*)p;
-    RC(get_linear(m, "embed.conv2", d, 9 * d, true, &m->conv2));
-    RC(get_linear(m, "embed.out", d, m->F2 * d, true, &m->embed_out));
+    RC(get_linear(m, "embed.conv2", d, 9 * d * p3, true, &m->conv2));
+    RC(get_linear(m, "embed.out", d, m->F2 * d * p3, true, &m->embed_out));
     RC(model_get(m, "embed.pe", WB_F32, (int64_t)c.max_pos * d, &p));
     m->pe = (const float*)p;
 
@@ -125,14 +126,14 @@ static int model_finalize(Model* m, cudaStream_t stream) {
         RC(get_norm(m, b + ".norm_conv", d, &L.n_conv));
         RC(get_norm(m, b + ".norm_ff", d, &L.n_ff));
         RC(get_norm(m, b + ".norm_final", d, &L.n_final));
-        RC(get_linear(m, b + ".ffm.w1", ff, d, true, &L.ffm1));
-        RC(get_linear(m, b + ".ffm.w2", d, ff, true, &L.ffm2));
-        RC(get_linear(m, b + ".ff.w1", ff, d, true, &L.ff1));
-        RC(get_linear(m, b + ".ff.w2", d, ff, true, &L.ff2));
-        RC(get_linear(m, b + ".att.qkv", 3 * d, d, true, &L.qkv));
-        RC(get_linear(m, b + ".att.out", d, d, true, &L.out));
-        RC(get_linear(m, b + ".conv.pw1", 2 * d, d, true, &L.pw1));
-        RC(get_linear(m, b + ".conv.pw2", d, d, true, &L.pw2));
+        RC(get_linear(m, b + ".ffm.w1", ff, d * p3, true, &L.ffm1));
+        RC(get_linear(m, b + ".ffm.w2", d, ff * p3, true, &L.ffm2));
+        RC(get_linear(m, b + ".ff.w1", ff, d * p3, true, &L.ff1));
+        RC(get_linear(m, b + ".ff.w2", d, ff * p3, true, &L.ff2));
+        RC(get_linear(m, b + ".att.qkv", 3 * d, d * p3, true, &L.qkv));
+        RC(get_linear(m, b + ".att.out", d, d * p3, true, &L.out));
+        RC(get_linear(m, b + ".conv.pw1", 2 * d, d * p3, true, &L.pw1));
+        RC(get_linear(m, b + ".conv.pw2", d, d * p3, true, &L.pw2));
         RC(model_get(m, b + ".att.pos_u", WB_F32, d, &p));
         L.pos_u = (const float*)p;
         RC(model_get(m, b + ".att.pos_v", WB_F32, d, &p));
@@ -153,7 +154,7 @@ static int model_finalize(Model* m, cudaStream_t stream) {
                      stream));
     }
     RC(get_norm(m, "after_norm", d, &m->after));
-    RC(get_linear(m, "ctc", c.vocab, d, true, &m->ctc));
+    RC(get_linear(m, "ctc", c.vocab, d * p3, true, &m->ctc));
     if (c.dec_layers > 0) RC(finalize_decoder(m, "dec.left", c.dec_layers, &m->left));
     if (c.rdec_layers > 0) RC(finalize_decoder(m, "dec.right", c.rdec_layers, &m->right));
     WB_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -172,10 +173,7 @@ const char* wb_last_error(void) { return get_last_error(); }
 const char* wb_version(void) { return "wenet_b200 0.1 (sm_100a)"; }
 unsigned long long wb_launch_count(void) { return g_launch_count.load(); }
 
-void wb_set_sm_reserve(int n) {
-    gemm_set_sm_reserve(n);
-    ffn_set_sm_reserve(n);
-}
+void wb_set_sm_reserve(int n) { gemm_set_sm_reserve(n); }
 void wb_prof_enable(int on) { g_prof_on = on; }
 void wb_prof_reset(void) { wb::prof_reset(); }
 int wb_prof_num_tags(void) { return PT_COUNT; }
@@ -183,7 +181,7 @@ const char* wb_prof_tag_name(int tag) {
     static const char* names[PT_COUNT] = {"gemm_tcgen05", "attention", "layernorm", "dwconv_norm_silu", "conv1",
                                           "im2col", "relpos_kprep", "fbank", "logsoftmax_topk", "ctc_greedy",
                                           "ctc_prefix_beam", "embed_tokens", "gather_logprob", "rescore_combine",
-                                          "misc", "ffn_fused_tcgen05"};
+                                          "misc", "ffn_fused_tcgen05 (removed)"};
     return (tag >= 0 && tag < PT_COUNT) ? names[tag] : "?";
 }
 int wb_prof_collect(double* ms, double* work, long long* launches) { return wb::prof_collect(ms, work, launches); }
@@ -265,7 +263,7 @@ int wb_ctc_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_t ro
     WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "ctc_logprobs: model not finalized");
     WB_REQUIRE(ldl >= m->cfg.vocab, WB_ERR_BAD_ARG, "ctc_logprobs: ldl < vocab");
     cudaStream_t st = (cudaStream_t)stream;
-    RC(gemm_bf16(enc_out_bf16_dev, m->cfg.d_model, &m->ctc.tmap, m->ctc.w, (int)rows, m->cfg.vocab, m->cfg.d_model,
+    RC(gemm_bf16(enc_out_bf16_dev, m->ctc.K, &m->ctc.tmap, m->ctc.w, (int)rows, m->cfg.vocab, m->ctc.K,
                  m->ctc.b, EPI_F32, 1.0f, logp_dev, ldl, 0, st));
     return ctc_logsoftmax_topk(logp_dev, ldl, (int)rows, m->cfg.vocab, blank_id, blank_penalty, topk, topk_val_dev,
                                topk_idx_dev, st);
@@ -279,7 +277,7 @@ int wb_ctc_topk(const wb_model* mm, const void* enc_out_bf16_dev, int64_t rows, 
     WB_REQUIRE(ldl >= m->cfg.vocab && topk_val_dev && topk_idx_dev && logits_scratch_dev, WB_ERR_BAD_ARG,
                "ctc_topk: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    RC(gemm_bf16(enc_out_bf16_dev, m->cfg.d_model, &m->ctc.tmap, m->ctc.w, (int)rows, m->cfg.vocab, m->cfg.d_model,
+    RC(gemm_bf16(enc_out_bf16_dev, m->ctc.K, &m->ctc.tmap, m->ctc.w, (int)rows, m->cfg.vocab, m->ctc.K,
                  m->ctc.b, EPI_F32, 1.0f, logits_scratch_dev, ldl, 0, st));
     return ctc_lse_topk(logits_scratch_dev, ldl, (int)rows, m->cfg.vocab, blank_id, blank_penalty, topk, topk_val_dev,
                         topk_idx_dev, st);
@@ -327,15 +325,15 @@ int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, 
     return gemm_bf16(a_dev, lda, nullptr, b_dev, M, N, K, bias_dev, epi, alpha, c_dev, ldc, split3,
                      (cudaStream_t)stream);
 }
-int wb_op_ffn(const void* a_dev, int64_t lda, const void* w1_dev, const float* b1_dev, const void* w2_dev,
-              const float* b2_dev, int M, int d, int ff, float alpha, int act, float* x_dev, int64_t ldx, wb_stream_t stream) {
-    return ffn_fused(a_dev, lda, w1_dev, b1_dev, w2_dev, b2_dev, M, d, ff, alpha, act, x_dev, ldx, (cudaStream_t)stream);
-}
 int wb_op_layernorm(const float* x_dev, int64_t ldx, int M, int d, const float* gamma_dev, const float* beta_dev,
                     float eps, void* out_bf16_dev, int64_t ld_bf16, int split3, float* out_f32_dev, int64_t ld_f32,
                     wb_stream_t stream) {
     return layernorm_rows(x_dev, ldx, M, d, gamma_dev, beta_dev, eps, out_bf16_dev, ld_bf16, split3, out_f32_dev,
                           ld_f32, (cudaStream_t)stream);
+}
+int wb_op_cast_bf16(const float* x_dev, int64_t ldx, int M, int d, void* out_bf16_dev, int64_t ld_bf16, int split3,
+                    wb_stream_t stream) {
+    return cast_rows_bf16(x_dev, ldx, M, d, out_bf16_dev, ld_bf16, split3, (cudaStream_t)stream);
 }
 int wb_op_attention(const void* q_dev, int64_t ldq, int64_t q_rows, int q_col0, const void* k_dev, int64_t ldk,
                     int64_t k_rows, int k_col0, const void* v_dev, int64_t ldv, int64_t v_rows, int v_col0,

@@ -9,15 +9,13 @@
 // Masks are generated in-kernel from (k_len, chunk_size, num_left_chunks): key-padding mask, the
 // streaming chunk mask (mask.py:subsequent_chunk_mask) and the causal mask (chunk_size = 1).
 //
-// One CTA = 128 queries of one (sequence, head); 128 threads, thread r owns query row r
-// (TMEM lane r), so softmax needs no cross-thread reduction.
-//   pass 1: S = Q K'^T per 128-key tile (tcgen05.mma 128x128x64 into TMEM), row max only
-//   pass 2: S again, p = exp2(.), P (bf16) -> shared memory in the canonical K-major SWIZZLE_128B
-//           layout, O += P V (tcgen05.mma 128x64x128) — exact max known => no rescaling of O.
-// Q/K'/V tiles arrive by TMA (SWIZZLE_128B); V is consumed directly as an MN-major B operand.
-// The softmax normaliser is produced by the tensor core too (P times an all-ones operand -> TMEM),
-// and mask comparisons are only executed on tiles that cross a mask boundary: the kernel is bound by
-// instruction issue in the softmax loops, so every per-element instruction counts (ncu: profiles/).
+// One CTA = 128 queries of one (sequence, head); 128 threads, thread r owns query row r (TMEM lane r), so the softmax
+// needs no cross-thread reduction.  Single pass over 64-key tiles with an online softmax (see the kernel comment):
+// S = Q K'^T (tcgen05.mma 128x64x64 into TMEM) -> p = exp2(.) -> P (bf16) into shared memory in the canonical K-major
+// SWIZZLE_128B layout -> O += P V (tcgen05.mma 128x64x64).  Q / K' / V tiles arrive by TMA (SWIZZLE_128B); V is consumed
+// directly as an MN-major B operand.  Mask comparisons are executed only on tiles that cross a mask boundary.
+// (Round 1 carried three earlier schedules - two-pass serial, two-pass pipelined, two threads per row - behind env
+// switches; they measured 142 / 177 / 167 us per layer against 108 us for this one and were removed.)
 #include "common.cuh"
 #include "kernels.h"
 #include <stdlib.h>
@@ -58,647 +56,6 @@ struct AttnCfg {
     static constexpr int kSmem = 1024 /*align*/ + TILE_BYTES /*Q*/ + 2 * kKVBytes /*K,V*/ + kPBytes + 2048 /*ones*/ +
                                  2 * KN * 4 /*c*/ + 128 /*barriers*/;
 };
-
-template <int KN>
-__global__ void __launch_bounds__(128, (KN == 128) ? 2 : 4)
-attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                 const __grid_constant__ CUtensorMap tmap_v, AttnDev P) {
-    const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
-    const int q_len = P.q_len[b];
-    if (qt * AT_M >= q_len) return;
-    const int q_start = P.q_start[b];
-    const int k_start = P.k_start[b];
-    const int k_len = P.k_len[b];
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    using Cfg = AttnCfg<KN>;
-    constexpr int AT_N = KN;
-    uint8_t* sK = smem + TILE_BYTES;
-    uint8_t* sV = sK + Cfg::kKVBytes;
-    uint8_t* sP = sV + Cfg::kKVBytes;
-    uint8_t* sVt = sP + Cfg::kPBytes;   // 2 KB of bf16 ones
-    float* sC = reinterpret_cast<float*>(sVt + 2048);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sVt + 2048 + 2 * KN * 4);
-    uint64_t* bar_q = bars + 0;
-    uint64_t* bar_k = bars + 1;
-    uint64_t* bar_v = bars + 2;
-    uint64_t* bar_s = bars + 3;
-    uint64_t* bar_pv = bars + 4;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int qi = qt * AT_M + tid;  // query index inside the sequence
-
-    if (tid == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_k);
-        tma_prefetch_desc(&tmap_v);
-        mbar_init(bar_q, 1);
-        mbar_init(bar_k, 1);
-        mbar_init(bar_v, 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_pv, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) {
-        tmem_alloc(tmem_holder, Cfg::kTmemCols);
-        tmem_relinquish();
-    }
-    // all-ones bf16 operand (layout-agnostic): P x ones accumulates the softmax normaliser in TMEM
-    for (int i = tid; i < 2048 / 16; i += 128)
-        reinterpret_cast<uint4*>(sVt)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_s = tmem_base;             // columns [0,KN)
-    const uint32_t tmem_o = tmem_base + KN;        // columns [KN,KN+64)
-    const uint32_t tmem_l = tmem_base + KN + 64;   // KN == 128 only: columns [192,208), row sums of P
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-
-    // visible key range for this row, and the tile range for the CTA
-    int row_lo = 0, row_hi = k_len;
-    int cta_lo = 0, cta_hi = k_len;
-    if (P.chunk_size > 0) {
-        const int c = P.chunk_size;
-        row_hi = min((qi / c + 1) * c, k_len);
-        row_lo = (P.num_left_chunks < 0) ? 0 : max((qi / c - P.num_left_chunks) * c, 0);
-        const int q_first = qt * AT_M, q_last = min(qt * AT_M + AT_M - 1, q_len - 1);
-        cta_hi = min((q_last / c + 1) * c, k_len);
-        cta_lo = (P.num_left_chunks < 0) ? 0 : max((q_first / c - P.num_left_chunks) * c, 0);
-    }
-    const int kt0 = cta_lo / AT_N;
-    const int kt1 = (cta_hi + AT_N - 1) / AT_N;
-    // keys in [full_lo, full_hi) are visible to EVERY row of this CTA -> no per-element mask tests there
-    int full_lo = 0, full_hi = k_len;
-    if (P.chunk_size > 0) {
-        const int c = P.chunk_size;
-        const int q_first = qt * AT_M, q_last = qt * AT_M + AT_M - 1;
-        full_hi = min((q_first / c + 1) * c, k_len);
-        full_lo = (P.num_left_chunks < 0) ? 0 : max((q_last / c - P.num_left_chunks) * c, 0);
-    }
-
-    uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_pv = 0;
-    constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, AT_N, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, DK, 1);   // V: MN-major B operand
-    constexpr uint32_t idesc_l = make_idesc_bf16(AT_M, 16, 1);
-
-    if (tid == 0 && kt0 < kt1) {
-        mbar_expect_tx(bar_q, TILE_BYTES);
-        tma_load_2d(sQ, &tmap_q, bar_q, P.q_col0 + h * DK, q_start + qt * AT_M);
-        mbar_expect_tx(bar_k, Cfg::kKVBytes);
-        tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + kt0 * AT_N);
-    }
-
-    float m_run = -INFINITY;
-    // ------------------------------- pass 1: row max -------------------------------
-    for (int kt = kt0; kt < kt1; ++kt) {
-        const int j0 = kt * AT_N;
-        {
-            const int j = j0 + tid;
-            float cv = 0.f;
-            if (P.kbias != nullptr && j < k_len)
-                cv = P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e;
-            if (tid < KN) sC[(kt & 1) * KN + tid] = cv;
-        }
-        if (tid == 0) {
-            if (kt == kt0) mbar_wait(bar_q, 0);
-            mbar_wait(bar_k, ph_k);
-            tc_fence_after();
-            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
-#pragma unroll
-            for (int k = 0; k < DK / 16; ++k)
-                umma_f16(tmem_s, make_smem_desc_sw128(qa + k * 32, 16, 1024),
-                         make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k != 0);
-            umma_commit(bar_s);
-        }
-        ph_k ^= 1;
-        __syncthreads();  // sC visible
-        mbar_wait(bar_s, ph_s);
-        ph_s ^= 1;
-        tc_fence_after();
-        if (tid == 0) {
-            // K smem is free again: prefetch next K tile (or the first tile again for pass 2, plus V)
-            const int nk = (kt + 1 < kt1) ? kt + 1 : kt0;
-            mbar_expect_tx(bar_k, Cfg::kKVBytes);
-            tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + nk * AT_N);
-            if (kt + 1 == kt1) {
-                mbar_expect_tx(bar_v, Cfg::kKVBytes);
-                tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + kt0 * AT_N);
-            }
-        }
-        const float* cc = sC + (kt & 1) * KN;
-        const bool tile_full = (j0 >= full_lo) && (j0 + AT_N <= full_hi);
-#pragma unroll 1
-        for (int c = 0; c < KN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            if (tile_full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(cc + c * 32 + i);
-                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x));
-                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y));
-                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z));
-                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w));
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int j = j0 + c * 32 + i;
-                    const float s = fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]);
-                    if (j >= row_lo && j < row_hi) m_run = fmaxf(m_run, s);
-                }
-            }
-        }
-        tc_fence_before();
-        __syncthreads();  // everyone done reading S before the next MMA overwrites it
-    }
-    const float m_fin = (m_run == -INFINITY) ? 0.f : m_run;
-
-    // ------------------------------- pass 2: P, O -------------------------------
-    float l_acc = 0.f;
-    for (int kt = kt0; kt < kt1; ++kt) {
-        const int j0 = kt * AT_N;
-        {
-            const int j = j0 + tid;
-            float cv = 0.f;
-            if (P.kbias != nullptr && j < k_len)
-                cv = P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e;
-            if (tid < KN) sC[(kt & 1) * KN + tid] = cv;
-        }
-        if (tid == 0) {
-            mbar_wait(bar_k, ph_k);
-            tc_fence_after();
-            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
-#pragma unroll
-            for (int k = 0; k < DK / 16; ++k)
-                umma_f16(tmem_s, make_smem_desc_sw128(qa + k * 32, 16, 1024),
-                         make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k != 0);
-            umma_commit(bar_s);
-        }
-        ph_k ^= 1;
-        __syncthreads();
-        mbar_wait(bar_s, ph_s);
-        ph_s ^= 1;
-        tc_fence_after();
-        if (tid == 0 && kt + 1 < kt1) {
-            mbar_expect_tx(bar_k, Cfg::kKVBytes);
-            tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + (kt + 1) * AT_N);
-        }
-        const float* cc = sC + (kt & 1) * KN;
-        const bool tile_full = (j0 >= full_lo) && (j0 + AT_N <= full_hi);
-#pragma unroll 1
-        for (int c = 0; c < KN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            uint32_t pk[16];
-            if (tile_full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(cc + c * 32 + i);
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x) - m_fin);
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y) - m_fin);
-                    const float p2 = fast_exp2(fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z) - m_fin);
-                    const float p3 = fast_exp2(fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w) - m_fin);
-                    pk[i >> 1] = pack_bf16x2(p0, p1);
-                    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-                    if (KN != 128) l_acc += (p0 + p1) + (p2 + p3);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const int j = j0 + c * 32 + i;
-                    float p0 = 0.f, p1 = 0.f;
-                    if (j >= row_lo && j < row_hi)
-                        p0 = fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]) - m_fin);
-                    if (j + 1 >= row_lo && j + 1 < row_hi)
-                        p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[c * 32 + i + 1]) - m_fin);
-                    pk[i >> 1] = pack_bf16x2(p0, p1);
-                    if (KN != 128) l_acc += p0 + p1;
-                }
-            }
-            // canonical K-major SWIZZLE_128B: row r, 16-byte chunk cidx -> chunk (cidx ^ (r & 7))
-            uint8_t* prow = sP + (c >> 1) * TILE_BYTES + tid * 128;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int cidx = (c & 1) * 4 + u;
-                *reinterpret_cast<uint4*>(prow + ((cidx ^ (tid & 7)) << 4)) =
-                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-            }
-        }
-        ph_v ^= 1;
-        fence_proxy_async_smem();  // generic-proxy smem writes (P) -> visible to the tensor core
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(bar_v, ph_v ^ 1);
-            tc_fence_after();
-            const uint32_t pa = smem_u32(sP), va = smem_u32(sV), oa = smem_u32(sVt);
-#pragma unroll
-            for (int ks = 0; ks < AT_N / 16; ++ks) {
-                const uint64_t adesc =
-                    make_smem_desc_sw128(pa + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024);
-                const uint32_t acc = (kt != kt0 || ks != 0) ? 1u : 0u;
-                umma_f16(tmem_o, adesc, make_smem_desc_sw128(va + ks * 2048, 1024, 1024), idesc_o, acc);
-                // row sums of the (bf16-rounded) probabilities: P x ones, 16 columns wide
-                if (KN == 128)
-                    umma_f16(tmem_l, adesc, make_smem_desc_sw128(oa, 1024, 1024), idesc_l, acc);  // same 2 KB of ones
-            }
-            umma_commit(bar_pv);
-        }
-        // P / V / Vt buffers and the S accumulator are reused next iteration: wait for the PV MMAs
-        mbar_wait(bar_pv, ph_pv);
-        ph_pv ^= 1;
-        tc_fence_after();
-        if (tid == 0 && kt + 1 < kt1) {
-            mbar_expect_tx(bar_v, Cfg::kKVBytes);
-            tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + (kt + 1) * AT_N);
-        }
-    }
-
-    // ------------------------------- epilogue -------------------------------
-    if (kt0 < kt1) {
-        float l_run = l_acc;
-        if (KN == 128) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_l + lane_sel, r);
-            tmem_ld_wait();
-            l_run = __uint_as_float(r[0]);
-        }
-        const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_sel + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            if (qi < q_len) {
-                __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK + c * 32;
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    reinterpret_cast<uint4*>(o)[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                if (P.split3_out) {
-                    uint32_t lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        lo[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv - bf16_lo(pk[i]),
-                                            __uint_as_float(r[2 * i + 1]) * inv - bf16_hi(pk[i]));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        reinterpret_cast<uint4*>(o + P.split_width)[u] =
-                            make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
-                        reinterpret_cast<uint4*>(o + 2 * P.split_width)[u] =
-                            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                    }
-                }
-            }
-        }
-    } else if (qi < q_len) {
-        __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK;
-        for (int i = 0; i < DK; ++i) o[i] = __float2bfloat16_rn(0.f);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
-    }
-}
-
-// Two threads per query row (default): same schedule as attention_kernel<64>, but 256 threads - warps w and w + 4 share
-// TMEM lane quarter w and take columns [0,32) / [32,64) of every 64-key score tile, halves of the P row and of the
-// output columns; the row max / row sum halves are combined through shared memory once per pass.  Twice the warps
-// per SM (32) at the same shared-memory / TMEM footprint: the kernel is latency-bound (ncu: 42 % issue-active with
-// 16 warps), not MUFU- or tensor-bound.
-__global__ void __launch_bounds__(256, 4)
-attention_split_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                 const __grid_constant__ CUtensorMap tmap_v, AttnDev P) {
-    const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
-    const int q_len = P.q_len[b];
-    if (qt * AT_M >= q_len) return;
-    const int q_start = P.q_start[b];
-    const int k_start = P.k_start[b];
-    const int k_len = P.k_len[b];
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    constexpr int KN = 64;
-    using Cfg = AttnCfg<KN>;
-    constexpr int AT_N = KN;
-    uint8_t* sK = smem + TILE_BYTES;
-    uint8_t* sV = sK + Cfg::kKVBytes;
-    uint8_t* sP = sV + Cfg::kKVBytes;
-    uint8_t* sVt = sP + Cfg::kPBytes;   // 2 KB of bf16 ones
-    float* sC = reinterpret_cast<float*>(sVt + 2048);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sVt + 2048 + 2 * KN * 4);
-    uint64_t* bar_q = bars + 0;
-    uint64_t* bar_k = bars + 1;
-    uint64_t* bar_v = bars + 2;
-    uint64_t* bar_s = bars + 3;
-    uint64_t* bar_pv = bars + 4;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int half = warp >> 2;              // column half of every score tile / of the output row
-    const int row = tid & 127;               // query row inside the CTA tile (= TMEM lane)
-    const int qi = qt * AT_M + row;          // query index inside the sequence
-
-    if (tid == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_k);
-        tma_prefetch_desc(&tmap_v);
-        mbar_init(bar_q, 1);
-        mbar_init(bar_k, 1);
-        mbar_init(bar_v, 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_pv, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) {
-        tmem_alloc(tmem_holder, Cfg::kTmemCols);
-        tmem_relinquish();
-    }
-    // all-ones bf16 operand (layout-agnostic): P x ones accumulates the softmax normaliser in TMEM
-    for (int i = tid; i < 2048 / 16; i += 256)
-        reinterpret_cast<uint4*>(sVt)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_s = tmem_base;             // columns [0,KN)
-    const uint32_t tmem_o = tmem_base + KN;        // columns [KN,KN+64)
-    const uint32_t tmem_l = tmem_base + KN + 64;   // KN == 128 only: columns [192,208), row sums of P
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-
-    // visible key range for this row, and the tile range for the CTA
-    int row_lo = 0, row_hi = k_len;
-    int cta_lo = 0, cta_hi = k_len;
-    if (P.chunk_size > 0) {
-        const int c = P.chunk_size;
-        row_hi = min((qi / c + 1) * c, k_len);
-        row_lo = (P.num_left_chunks < 0) ? 0 : max((qi / c - P.num_left_chunks) * c, 0);
-        const int q_first = qt * AT_M, q_last = min(qt * AT_M + AT_M - 1, q_len - 1);
-        cta_hi = min((q_last / c + 1) * c, k_len);
-        cta_lo = (P.num_left_chunks < 0) ? 0 : max((q_first / c - P.num_left_chunks) * c, 0);
-    }
-    const int kt0 = cta_lo / AT_N;
-    const int kt1 = (cta_hi + AT_N - 1) / AT_N;
-    // keys in [full_lo, full_hi) are visible to EVERY row of this CTA -> no per-element mask tests there
-    int full_lo = 0, full_hi = k_len;
-    if (P.chunk_size > 0) {
-        const int c = P.chunk_size;
-        const int q_first = qt * AT_M, q_last = qt * AT_M + AT_M - 1;
-        full_hi = min((q_first / c + 1) * c, k_len);
-        full_lo = (P.num_left_chunks < 0) ? 0 : max((q_last / c - P.num_left_chunks) * c, 0);
-    }
-
-    uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_pv = 0;
-    constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, AT_N, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, DK, 1);   // V: MN-major B operand
-    constexpr uint32_t idesc_l = make_idesc_bf16(AT_M, 16, 1);
-
-    if (tid == 0 && kt0 < kt1) {
-        mbar_expect_tx(bar_q, TILE_BYTES);
-        tma_load_2d(sQ, &tmap_q, bar_q, P.q_col0 + h * DK, q_start + qt * AT_M);
-        mbar_expect_tx(bar_k, Cfg::kKVBytes);
-        tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + kt0 * AT_N);
-    }
-
-    float m_run = -INFINITY, m_b = -INFINITY, m_c = -INFINITY, m_d = -INFINITY;
-    float* s_red = reinterpret_cast<float*>(sP);   // [2][128] halves of the row max / row sum (P buffer is idle then)
-    // ------------------------------- pass 1: row max -------------------------------
-    for (int kt = kt0; kt < kt1; ++kt) {
-        const int j0 = kt * AT_N;
-        {
-            const int j = j0 + tid;
-            float cv = 0.f;
-            if (P.kbias != nullptr && j < k_len)
-                cv = P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e;
-            if (tid < KN) sC[(kt & 1) * KN + tid] = cv;
-        }
-        if (tid == 0) {
-            if (kt == kt0) mbar_wait(bar_q, 0);
-            mbar_wait(bar_k, ph_k);
-            tc_fence_after();
-            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
-#pragma unroll
-            for (int k = 0; k < DK / 16; ++k)
-                umma_f16(tmem_s, make_smem_desc_sw128(qa + k * 32, 16, 1024),
-                         make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k != 0);
-            umma_commit(bar_s);
-        }
-        ph_k ^= 1;
-        __syncthreads();  // sC visible
-        mbar_wait(bar_s, ph_s);
-        ph_s ^= 1;
-        tc_fence_after();
-        if (tid == 0) {
-            // K smem is free again: prefetch next K tile (or the first tile again for pass 2, plus V)
-            const int nk = (kt + 1 < kt1) ? kt + 1 : kt0;
-            mbar_expect_tx(bar_k, Cfg::kKVBytes);
-            tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + nk * AT_N);
-            if (kt + 1 == kt1) {
-                mbar_expect_tx(bar_v, Cfg::kKVBytes);
-                tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + kt0 * AT_N);
-            }
-        }
-        const float* cc = sC + (kt & 1) * KN;
-        const bool tile_full = (j0 >= full_lo) && (j0 + AT_N <= full_hi);
-        {
-            const int c = half;
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            if (tile_full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(cc + c * 32 + i);
-                    m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x));
-                    m_b = fmaxf(m_b, fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y));
-                    m_c = fmaxf(m_c, fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z));
-                    m_d = fmaxf(m_d, fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w));
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int j = j0 + c * 32 + i;
-                    const float s = fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]);
-                    if (j >= row_lo && j < row_hi) m_run = fmaxf(m_run, s);
-                }
-            }
-        }
-        tc_fence_before();
-        __syncthreads();  // everyone done reading S before the next MMA overwrites it
-    }
-    m_run = fmaxf(fmaxf(m_run, m_b), fmaxf(m_c, m_d));
-    s_red[half * 128 + row] = m_run;
-    __syncthreads();
-    m_run = fmaxf(s_red[row], s_red[128 + row]);
-    __syncthreads();   // s_red (= P buffer) is rewritten by pass 2
-    const float m_fin = (m_run == -INFINITY) ? 0.f : m_run;
-
-    // ------------------------------- pass 2: P, O -------------------------------
-    float l_acc = 0.f;
-    for (int kt = kt0; kt < kt1; ++kt) {
-        const int j0 = kt * AT_N;
-        {
-            const int j = j0 + tid;
-            float cv = 0.f;
-            if (P.kbias != nullptr && j < k_len)
-                cv = P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e;
-            if (tid < KN) sC[(kt & 1) * KN + tid] = cv;
-        }
-        if (tid == 0) {
-            mbar_wait(bar_k, ph_k);
-            tc_fence_after();
-            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
-#pragma unroll
-            for (int k = 0; k < DK / 16; ++k)
-                umma_f16(tmem_s, make_smem_desc_sw128(qa + k * 32, 16, 1024),
-                         make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k != 0);
-            umma_commit(bar_s);
-        }
-        ph_k ^= 1;
-        __syncthreads();
-        mbar_wait(bar_s, ph_s);
-        ph_s ^= 1;
-        tc_fence_after();
-        if (tid == 0 && kt + 1 < kt1) {
-            mbar_expect_tx(bar_k, Cfg::kKVBytes);
-            tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + (kt + 1) * AT_N);
-        }
-        const float* cc = sC + (kt & 1) * KN;
-        const bool tile_full = (j0 >= full_lo) && (j0 + AT_N <= full_hi);
-        {
-            const int c = half;
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_s + lane_sel + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            uint32_t pk[16];
-            if (tile_full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(cc + c * 32 + i);
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x) - m_fin);
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y) - m_fin);
-                    const float p2 = fast_exp2(fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z) - m_fin);
-                    const float p3 = fast_exp2(fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w) - m_fin);
-                    pk[i >> 1] = pack_bf16x2(p0, p1);
-                    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-                    if (KN != 128) l_acc += (p0 + p1) + (p2 + p3);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const int j = j0 + c * 32 + i;
-                    float p0 = 0.f, p1 = 0.f;
-                    if (j >= row_lo && j < row_hi)
-                        p0 = fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[c * 32 + i]) - m_fin);
-                    if (j + 1 >= row_lo && j + 1 < row_hi)
-                        p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[c * 32 + i + 1]) - m_fin);
-                    pk[i >> 1] = pack_bf16x2(p0, p1);
-                    if (KN != 128) l_acc += p0 + p1;
-                }
-            }
-            // canonical K-major SWIZZLE_128B: row r, 16-byte chunk cidx -> chunk (cidx ^ (r & 7))
-            uint8_t* prow = sP + row * 128;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int cidx = (c & 1) * 4 + u;
-                *reinterpret_cast<uint4*>(prow + ((cidx ^ (row & 7)) << 4)) =
-                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-            }
-        }
-        ph_v ^= 1;
-        fence_proxy_async_smem();  // generic-proxy smem writes (P) -> visible to the tensor core
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(bar_v, ph_v ^ 1);
-            tc_fence_after();
-            const uint32_t pa = smem_u32(sP), va = smem_u32(sV), oa = smem_u32(sVt);
-#pragma unroll
-            for (int ks = 0; ks < AT_N / 16; ++ks) {
-                const uint64_t adesc =
-                    make_smem_desc_sw128(pa + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024);
-                const uint32_t acc = (kt != kt0 || ks != 0) ? 1u : 0u;
-                umma_f16(tmem_o, adesc, make_smem_desc_sw128(va + ks * 2048, 1024, 1024), idesc_o, acc);
-                // row sums of the (bf16-rounded) probabilities: P x ones, 16 columns wide
-                if (KN == 128)
-                    umma_f16(tmem_l, adesc, make_smem_desc_sw128(oa, 1024, 1024), idesc_l, acc);  // same 2 KB of ones
-            }
-            umma_commit(bar_pv);
-        }
-        // P / V / Vt buffers and the S accumulator are reused next iteration: wait for the PV MMAs
-        mbar_wait(bar_pv, ph_pv);
-        ph_pv ^= 1;
-        tc_fence_after();
-        if (tid == 0 && kt + 1 < kt1) {
-            mbar_expect_tx(bar_v, Cfg::kKVBytes);
-            tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + (kt + 1) * AT_N);
-        }
-    }
-
-    // ------------------------------- epilogue -------------------------------
-    if (kt0 < kt1) {
-        s_red[half * 128 + row] = l_acc;   // all P V MMAs have retired: the P buffer is free
-        __syncthreads();
-        const float l_run = s_red[row] + s_red[128 + row];
-        const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-        {
-            const int c = half;
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_sel + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            if (qi < q_len) {
-                __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK + c * 32;
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    reinterpret_cast<uint4*>(o)[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                if (P.split3_out) {
-                    uint32_t lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        lo[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv - bf16_lo(pk[i]),
-                                            __uint_as_float(r[2 * i + 1]) * inv - bf16_hi(pk[i]));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        reinterpret_cast<uint4*>(o + P.split_width)[u] =
-                            make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
-                        reinterpret_cast<uint4*>(o + 2 * P.split_width)[u] =
-                            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                    }
-                }
-            }
-        }
-    } else if (qi < q_len && half == 0) {
-        __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK;
-        for (int i = 0; i < DK; ++i) o[i] = __float2bfloat16_rn(0.f);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
-    }
-}
 
 // ----------------------------------------------------------------------------------------------
 // Single-pass variant (default): online softmax, so Q K'^T is computed ONCE per key tile (the two-pass kernels spend a
@@ -995,287 +352,6 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
 }
 
-// ----------------------------------------------------------------------------------------------
-// Pipelined variant (WB_ATTN_PIPE=1): same math, same thread-per-row softmax, 64-key tiles, but the tensor core never
-// waits for the softmax and vice versa:
-//   * K and V tiles are double-buffered in shared memory;
-//   * the score MMA of tile j+1 is issued as soon as every thread has pulled S(j) out of TMEM into registers, so
-//     it runs under the exp / max arithmetic of tile j (both passes form ONE stream of 2n score MMAs);
-//   * the P·V MMA of tile t runs under the arithmetic of tile t+1; its completion is only awaited right before the
-//     P buffer is overwritten.
-// 67 KB of shared memory, 128 TMEM columns (S 64 | O 64) -> 3 CTAs per SM.
-constexpr int PK = 64;                       // keys per tile
-constexpr int P_KV_BYTES = PK * 128;         // 8 KB
-constexpr int P_PBYTES = 128 * PK * 2;       // 16 KB
-constexpr int P_SMEM = 1024 + TILE_BYTES + 4 * P_KV_BYTES + P_PBYTES + 2 * PK * 4 + 128;
-
-__global__ void __launch_bounds__(128, 3)
-attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                      const __grid_constant__ CUtensorMap tmap_v, AttnDev P) {
-    const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
-    const int q_len = P.q_len[b];
-    if (qt * AT_M >= q_len) return;
-    const int q_start = P.q_start[b];
-    const int k_start = P.k_start[b];
-    const int k_len = P.k_len[b];
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + TILE_BYTES;            // [2][8 KB]
-    uint8_t* sV = sK + 2 * P_KV_BYTES;        // [2][8 KB]
-    uint8_t* sP = sV + 2 * P_KV_BYTES;        // 16 KB
-    float* sC = reinterpret_cast<float*>(sP + P_PBYTES);   // [2][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sC + 2 * PK);
-    uint64_t* bar_q = bars + 0;
-    uint64_t* bar_k = bars + 1;   // [2]
-    uint64_t* bar_v = bars + 3;   // [2]
-    uint64_t* bar_s = bars + 5;
-    uint64_t* bar_pv = bars + 6;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int qi = qt * AT_M + tid;
-
-    if (tid == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_k);
-        tma_prefetch_desc(&tmap_v);
-        mbar_init(bar_q, 1);
-        mbar_init(&bar_k[0], 1);
-        mbar_init(&bar_k[1], 1);
-        mbar_init(&bar_v[0], 1);
-        mbar_init(&bar_v[1], 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_pv, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) {
-        tmem_alloc(tmem_holder, 128);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_s = tmem_base;          // columns [0, 64)
-    const uint32_t tmem_o = tmem_base + PK;     // columns [64, 128)
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-
-    // visible key range for this row, and the tile range for the CTA (as in attention_kernel)
-    int row_lo = 0, row_hi = k_len;
-    int cta_lo = 0, cta_hi = k_len;
-    int full_lo = 0, full_hi = k_len;
-    if (P.chunk_size > 0) {
-        const int c = P.chunk_size;
-        row_hi = min((qi / c + 1) * c, k_len);
-        row_lo = (P.num_left_chunks < 0) ? 0 : max((qi / c - P.num_left_chunks) * c, 0);
-        const int q_first = qt * AT_M, q_last = min(qt * AT_M + AT_M - 1, q_len - 1), q_last_all = qt * AT_M + AT_M - 1;
-        cta_hi = min((q_last / c + 1) * c, k_len);
-        cta_lo = (P.num_left_chunks < 0) ? 0 : max((q_first / c - P.num_left_chunks) * c, 0);
-        full_hi = min((q_first / c + 1) * c, k_len);
-        full_lo = (P.num_left_chunks < 0) ? 0 : max((q_last_all / c - P.num_left_chunks) * c, 0);
-    }
-    const int kt0 = cta_lo / PK;
-    const int kt1 = (cta_hi + PK - 1) / PK;
-    const int n = kt1 - kt0;          // key tiles
-    const int nj = 2 * n;             // score MMAs: pass 1 (row max) then pass 2 (probabilities)
-
-    constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, PK, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, DK, 1);   // V: MN-major B operand
-
-    auto load_k = [&](int j) {   // operand of score MMA j -> K buffer j & 1
-        mbar_expect_tx(&bar_k[j & 1], P_KV_BYTES);
-        tma_load_2d(sK + (j & 1) * P_KV_BYTES, &tmap_k, &bar_k[j & 1], P.k_col0 + h * DK, k_start + (kt0 + (j % n)) * PK);
-    };
-    auto load_v = [&](int t) {   // V of tile t -> V buffer t & 1
-        mbar_expect_tx(&bar_v[t & 1], P_KV_BYTES);
-        tma_load_2d(sV + (t & 1) * P_KV_BYTES, &tmap_v, &bar_v[t & 1], P.v_col0 + h * DK, k_start + (kt0 + t) * PK);
-    };
-    auto issue_s = [&](int j) {  // S = Q K'(j)^T, 128 x 64 x 64
-        mbar_wait(&bar_k[j & 1], (uint32_t)((j >> 1) & 1));
-        tc_fence_after();
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + (j & 1) * P_KV_BYTES);
-#pragma unroll
-        for (int k = 0; k < DK / 16; ++k)
-            umma_f16(tmem_s, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024),
-                     idesc_s, k != 0);
-        umma_commit(bar_s);
-    };
-
-    if (n > 0 && tid == 0) {
-        mbar_expect_tx(bar_q, TILE_BYTES);
-        tma_load_2d(sQ, &tmap_q, bar_q, P.q_col0 + h * DK, q_start + qt * AT_M);
-        load_k(0);
-        if (nj > 1) load_k(1);
-        load_v(0);
-        if (n > 1) load_v(1);
-        mbar_wait(bar_q, 0);
-        issue_s(0);
-    }
-
-    float m_run = -INFINITY, m_fin = 0.f, l_acc = 0.f;
-    float m_b = -INFINITY, m_c = -INFINITY, m_d = -INFINITY;   // independent max chains (pass 1)
-    // per-key bias of the tile of score MMA j, fetched one iteration ahead (an L2 / HBM round trip otherwise sits
-    // right in front of the CTA barrier)
-    auto fetch_c = [&](int j) -> float {
-        if (j >= nj || tid >= PK || P.kbias == nullptr) return 0.f;
-        const int key = (kt0 + (j % n)) * PK + tid;
-        return (key < k_len) ? P.kbias[(long long)(k_start + key) * P.ld_kbias + h] * P.scale_log2e : 0.f;
-    };
-    float c_next = (n > 0) ? fetch_c(0) : 0.f;
-    for (int j = 0; j < nj; ++j) {
-        const int t = (j < n) ? j : j - n;          // key tile (relative)
-        const int j0 = (kt0 + t) * PK;
-        if (tid < PK) sC[(j & 1) * PK + tid] = c_next;
-        c_next = fetch_c(j + 1);
-        mbar_wait(bar_s, (uint32_t)(j & 1));
-        tc_fence_after();
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_sel, r0);
-        tmem_ld_32x32b_x32(tmem_s + lane_sel + 32u, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncthreads();   // every thread holds its S row in registers; sC visible
-        if (tid == 0) {
-            if (j + 1 < nj) issue_s(j + 1);        // runs under the arithmetic below
-            if (j + 2 < nj) load_k(j + 2);         // K buffer j & 1 was released by score MMA j
-        }
-        const float* cc = sC + (j & 1) * PK;
-        const bool tile_full = (j0 >= full_lo) && (j0 + PK <= full_hi);
-        if (j < n) {
-            // ---------------- pass 1: running row max ----------------
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const uint32_t* r = hh ? r1 : r0;
-                if (tile_full) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 c4 = *reinterpret_cast<const float4*>(cc + hh * 32 + i);
-                        m_run = fmaxf(m_run, fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x));
-                        m_b = fmaxf(m_b, fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y));
-                        m_c = fmaxf(m_c, fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z));
-                        m_d = fmaxf(m_d, fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w));
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int key = j0 + hh * 32 + i;
-                        const float sc = fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[hh * 32 + i]);
-                        if (key >= row_lo && key < row_hi) m_run = fmaxf(m_run, sc);
-                    }
-                }
-            }
-            if (j == n - 1) {
-                m_run = fmaxf(fmaxf(m_run, m_b), fmaxf(m_c, m_d));
-                m_fin = (m_run == -INFINITY) ? 0.f : m_run;
-            }
-        } else {
-            // ---------------- pass 2: probabilities, O += P V ----------------
-            uint32_t pk[32];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const uint32_t* r = hh ? r1 : r0;
-                if (tile_full) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 c4 = *reinterpret_cast<const float4*>(cc + hh * 32 + i);
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2e, c4.x) - m_fin);
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, c4.y) - m_fin);
-                        const float p2 = fast_exp2(fmaf(__uint_as_float(r[i + 2]), P.scale_log2e, c4.z) - m_fin);
-                        const float p3 = fast_exp2(fmaf(__uint_as_float(r[i + 3]), P.scale_log2e, c4.w) - m_fin);
-                        pk[hh * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
-                        pk[hh * 16 + (i >> 1) + 1] = pack_bf16x2(p2, p3);
-                        l_acc += (p0 + p1) + (p2 + p3);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const int key = j0 + hh * 32 + i;
-                        float p0 = 0.f, p1 = 0.f;
-                        if (key >= row_lo && key < row_hi)
-                            p0 = fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2e, cc[hh * 32 + i]) - m_fin);
-                        if (key + 1 >= row_lo && key + 1 < row_hi)
-                            p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2e, cc[hh * 32 + i + 1]) - m_fin);
-                        pk[hh * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
-                        l_acc += p0 + p1;
-                    }
-                }
-            }
-            if (t > 0) {   // P buffer and V buffer (t-1)&1 are free once the previous P V MMA retired
-                mbar_wait(bar_pv, (uint32_t)((t - 1) & 1));
-                tc_fence_after();
-                if (tid == 0 && t + 1 < n) load_v(t + 1);
-            }
-            // canonical K-major SWIZZLE_128B: row r, 16-byte chunk cidx -> chunk (cidx ^ (r & 7))
-            uint8_t* prow = sP + tid * 128;
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                *reinterpret_cast<uint4*>(prow + ((u ^ (tid & 7)) << 4)) =
-                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                mbar_wait(&bar_v[t & 1], (uint32_t)((t >> 1) & 1));
-                tc_fence_after();
-                const uint32_t pa = smem_u32(sP), va = smem_u32(sV + (t & 1) * P_KV_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < PK / 16; ++ks)
-                    umma_f16(tmem_o, make_smem_desc_sw128(pa + ks * 32, 16, 1024),
-                             make_smem_desc_sw128(va + ks * 2048, 1024, 1024), idesc_o, (t != 0 || ks != 0) ? 1u : 0u);
-                umma_commit(bar_pv);
-            }
-        }
-    }
-
-    // ------------------------------- epilogue -------------------------------
-    if (n > 0) {
-        mbar_wait(bar_pv, (uint32_t)((n - 1) & 1));
-        tc_fence_after();
-        const float inv = (l_acc > 0.f) ? 1.0f / l_acc : 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_sel + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            if (qi < q_len) {
-                __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK + c * 32;
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    reinterpret_cast<uint4*>(o)[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                if (P.split3_out) {
-                    uint32_t lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        lo[i] = pack_bf16x2(__uint_as_float(r[2 * i]) * inv - bf16_lo(pk[i]),
-                                            __uint_as_float(r[2 * i + 1]) * inv - bf16_hi(pk[i]));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        reinterpret_cast<uint4*>(o + P.split_width)[u] =
-                            make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
-                        reinterpret_cast<uint4*>(o + 2 * P.split_width)[u] =
-                            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                    }
-                }
-            }
-        }
-    } else if (qi < q_len) {
-        __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK;
-        for (int i = 0; i < DK; ++i) o[i] = __float2bfloat16_rn(0.f);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
-    }
-}
 
 // ----------------------------------------------------------------------------------------------
 __global__ void relpos_kprep_kernel(const __nv_bfloat16* __restrict__ k, long long ldk,
@@ -1306,19 +382,7 @@ __global__ void relpos_kprep_kernel(const __nv_bfloat16* __restrict__ k, long lo
 
 int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     if (a.batch <= 0 || a.max_q_len <= 0) return WB_OK;
-    static int kn_cfg = 0;
-    // default: single-pass online softmax; WB_ATTN_PIPE=1 software-pipelined two-pass, WB_ATTN_SPLIT=1 two threads per
-    // row, WB_ATTN_V1=1 the original serial two-pass kernel (tile width WB_ATTN_KN)
-    static int pipe_cfg = 0, split_cfg = 0, online_cfg = 1;
-    if (kn_cfg == 0) {
-        const char* e = getenv("WB_ATTN_KN");
-        kn_cfg = (e && atoi(e) == 128) ? 128 : 64;
-        pipe_cfg = getenv("WB_ATTN_PIPE") != nullptr;
-        split_cfg = !pipe_cfg && getenv("WB_ATTN_SPLIT") != nullptr;
-        online_cfg = !pipe_cfg && !split_cfg && getenv("WB_ATTN_V1") == nullptr;
-        if (pipe_cfg || split_cfg || online_cfg) kn_cfg = 64;
-    }
-    const int KN = kn_cfg;
+    constexpr int KN = 64;
     CUtensorMap tq, tk, tv;
     int rc;
     // the maps cover the whole row width so that column offsets select the head
@@ -1345,31 +409,10 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     P.split_width = a.heads * DK;
     P.v_mode = a.v_mode;
     WB_REQUIRE((a.ldo % 8) == 0 && (a.out_col0 % 8) == 0, WB_ERR_BAD_ARG, "attention: output pitch/offset must be %%8");
-    static bool attr_set = false;
-    if (!attr_set) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           AttnCfg<128>::kSmem));
-        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           AttnCfg<64>::kSmem));
-        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           AttnCfg<64>::kSmem));
-        WB_CHECK_CUDA(cudaFuncSetAttribute(attention_online_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           AttnCfg<64>::kSmem));
-        attr_set = true;
-    }
+    WB_SET_MAX_DYN_SMEM(attention_online_kernel, AttnCfg<KN>::kSmem);
     dim3 grid(ceil_div(a.max_q_len, AT_M), a.heads, a.batch);
     ProfScope _ps(PT_ATTENTION, stream, 0.0);
-    if (online_cfg)
-        attention_online_kernel<<<grid, 128, AttnCfg<64>::kSmem, stream>>>(tq, tk, tv, P);
-    else if (split_cfg)
-        attention_split_kernel<<<grid, 256, AttnCfg<64>::kSmem, stream>>>(tq, tk, tv, P);
-    else if (pipe_cfg)
-        attention_pipe_kernel<<<grid, 128, P_SMEM, stream>>>(tq, tk, tv, P);
-    else if (KN == 128)
-        attention_kernel<128><<<grid, 128, AttnCfg<128>::kSmem, stream>>>(tq, tk, tv, P);
-    else
-        attention_kernel<64><<<grid, 128, AttnCfg<64>::kSmem, stream>>>(tq, tk, tv, P);
+    attention_online_kernel<<<grid, 128, AttnCfg<KN>::kSmem, stream>>>(tq, tk, tv, P);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

@@ -66,6 +66,24 @@ struct ProfScope {
     }
 };
 
+// Opt a kernel into > 48 KB of dynamic shared memory.  Function attributes are PER DEVICE: the "done" bits are kept
+// per device ordinal (a process may drive several GPUs, e.g. one B200ASRModel per device) and updated atomically
+// (entry points may be called from several host threads).
+#define WB_SET_MAX_DYN_SMEM(kernel, bytes)                                                                        \
+    do {                                                                                                          \
+        static std::atomic<unsigned long long> _done[2] = {};                                                     \
+        int _dev = 0;                                                                                             \
+        WB_CHECK_CUDA(cudaGetDevice(&_dev));                                                                      \
+        const unsigned long long _bit = 1ull << (_dev & 63);                                                      \
+        std::atomic<unsigned long long>& _w = _done[(_dev >> 6) & 1];                                             \
+        if (!(_w.load(std::memory_order_acquire) & _bit)) {                                                       \
+            WB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _w.fetch_or(_bit, std::memory_order_release);                                                         \
+        }                                                                                                         \
+    } while (0)
+// number of SMs of the CURRENT device (cached per device ordinal)
+int current_device_sms();
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

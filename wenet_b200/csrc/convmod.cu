@@ -234,12 +234,10 @@ int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream) {
     ProfScope _ps(PT_DWCONV, stream, (double)a.batch * a.max_len * a.d * 4.0);
 #define WB_DW(KT, NP)                                                                                              \
     do {                                                                                                           \
-        static size_t smem_set = 0;                                                                                \
-        if (smem > 48 * 1024 && smem > smem_set) {                                                                 \
+        /* function attributes are per device and the size depends on (K, d): set it whenever the opt-in is needed */ \
+        if (smem > 48 * 1024)                                                                                      \
             WB_CHECK_CUDA(cudaFuncSetAttribute(dwconv_kernel<KT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                (int)smem));                                                        \
-            smem_set = smem;                                                                                       \
-        }                                                                                                          \
         dwconv_kernel<KT, NP><<<grid, DW_THREADS, smem, stream>>>(P);                                              \
     } while (0)
 #define WB_DW_NP(KT)                  \

@@ -131,7 +131,8 @@ void make_plan(const Model* m, int batch, const int32_t* feat_lens, EncPlan* P) 
     }
     P->M = M;
     P->rows1 = r1;
-    P->implicit_conv = implicit_conv_enabled(m);
+    const size_t p3 = m->cfg.precise ? 3 : 1;   // precise mode: bf16 activations are [hi | lo | hi] (3x wide)
+    P->implicit_conv = implicit_conv_enabled(m) && !m->cfg.precise;
     P->conv_tiles = 0;
     if (P->implicit_conv)
         for (int b = 0; b < batch; ++b) P->conv_tiles += (P->tp[b] + kConvTileT - 1) / kConvTileT;
@@ -144,16 +145,17 @@ void make_plan(const Model* m, int batch, const int32_t* feat_lens, EncPlan* P) 
     P->o_tiles = o;
     o += align_up((size_t)P->conv_tiles * 16 + 16);
     P->o_out1 = o;
-    o += align_up((size_t)r1 * d * 2);
+    o += align_up((size_t)r1 * d * 2 * p3);
     P->o_a2 = o;
     // the im2col matrix is the largest buffer; all per-layer activations alias it afterwards
-    const size_t a2_bytes = P->implicit_conv ? 0 : (size_t)M * m->F2 * 9 * d * 2;
-    const size_t layer_bytes = align_up((size_t)M * d * 2) * 4 /*a, ctx, g, g2*/ +
-                               align_up((size_t)M * m->cfg.ffn_dim * 2) + align_up((size_t)M * 3 * d * 2) +
+    const size_t a2_bytes = P->implicit_conv ? 0 : (size_t)M * m->F2 * 9 * d * 2 * p3;
+    const size_t layer_bytes = align_up((size_t)M * d * 2 * p3) * 4 /*a, ctx, g, g2*/ +
+                               align_up((size_t)M * m->cfg.ffn_dim * 2 * p3) +
+                               align_up((size_t)M * 3 * d * (m->cfg.precise ? 4 : 2)) /*qkv (fp32 when precise)*/ +
                                align_up((size_t)M * d * 2) /*kp*/ + align_up((size_t)M * m->cfg.heads * 4);
     o += align_up(a2_bytes > layer_bytes ? a2_bytes : layer_bytes);
     P->o_out2 = o;
-    o += align_up((size_t)M * m->F2 * d * 2);
+    o += align_up((size_t)M * m->F2 * d * 2 * p3);
     P->o_x = o;
     o += align_up((size_t)M * d * 4);
     P->total = o + 256;
@@ -258,8 +260,12 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
     float* x = reinterpret_cast<float*>(ws + P.o_x);
 
     // ---- Conv2dSubsampling4 (subsampling.py:203-228) ----
+    // precise mode (c.precise): bf16 activations are [hi | lo | hi] column blocks (bf16x3 against weights packed
+    // [hi | hi | lo]), the QKV projection leaves fp32 and attention / depthwise conv run on the fp32 kernels of precise.cu
+    const int sp = c.precise ? 1 : 0;
+    const int p3 = sp ? 3 : 1;
     RC(subsample_conv1(feats_dev, feats_stride_b, c.input_dim, d_t1n, d_off1, batch, P.max_t1, m->cmvn_mean,
-                       m->cmvn_istd, m->conv1_w, m->conv1_b, d, out1, 0, st));
+                       m->cmvn_istd, m->conv1_w, m->conv1_b, d, out1, sp, st));
     if (P.implicit_conv) {
         // tile table: (t1 row of tap kh = 0, first output row, valid rows) per 6-frame tile, never crossing utterances
         std::vector<int> tiles((size_t)P.conv_tiles * 4);
@@ -279,12 +285,13 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
         RC(gemm_conv2_implicit(out1, P.rows1 / m->F1, m->F1, d, &m->conv2.tmap, m->conv2.b, ws + P.o_tiles, P.conv_tiles,
                                M * m->F2, out2, st));
     } else {
-        RC(subsample_im2col(out1, d_off1, d_tp, d_off2, batch, P.max_tp, m->F1, m->F2, d, a2, 0, st));
-        RC(gemm_bf16(a2, 9 * d, &m->conv2.tmap, m->conv2.w, (int)(M * m->F2), d, 9 * d, m->conv2.b, EPI_BF16_RELU, 1.0f,
-                     out2, d, 0, st));
+        // (precise: the 3d-wide [hi|lo|hi] rows are gathered as if they were 3d channels; the weights are packed to match)
+        RC(subsample_im2col(out1, d_off1, d_tp, d_off2, batch, P.max_tp, m->F1, m->F2, d * p3, a2, 0, st));
+        RC(gemm_bf16(a2, m->conv2.K, &m->conv2.tmap, m->conv2.w, (int)(M * m->F2), d, m->conv2.K, m->conv2.b,
+                     EPI_BF16_RELU, 1.0f, out2, d * p3, sp, st));
     }
     // Linear(F2*d -> d), x * sqrt(d)  (embedding.py:141-147: RelPositionalEncoding scales, no add)
-    RC(gemm_bf16(out2, (long long)m->F2 * d, &m->embed_out.tmap, m->embed_out.w, (int)M, d, m->F2 * d, m->embed_out.b,
+    RC(gemm_bf16(out2, m->embed_out.K, &m->embed_out.tmap, m->embed_out.w, (int)M, d, m->embed_out.K, m->embed_out.b,
                  EPI_F32, sqrtf((float)d), x, d, 0, st));
     if (layer_dump_dev)
         WB_CHECK_CUDA(cudaMemcpyAsync(layer_dump_dev, x, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, st));
@@ -298,88 +305,84 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
         lo += align_up(bytes);
         return p;
     };
-    void* a = carve((size_t)M * d * 2);
-    void* ctx = carve((size_t)M * d * 2);
-    void* g = carve((size_t)M * d * 2);
-    void* g2 = carve((size_t)M * d * 2);
-    void* h = carve((size_t)M * ff * 2);
-    void* qkv = carve((size_t)M * 3 * d * 2);
+    void* a = carve((size_t)M * d * 2 * p3);
+    void* ctx = carve((size_t)M * d * 2 * p3);
+    void* g = carve((size_t)M * d * 2 * p3);
+    void* g2 = carve((size_t)M * d * 2 * p3);
+    void* h = carve((size_t)M * ff * 2 * p3);
+    void* qkv = carve((size_t)M * 3 * d * (sp ? 4 : 2));
     void* kp = carve((size_t)M * d * 2);
     float* kbias = reinterpret_cast<float*>(carve((size_t)M * H * 4));
 
     const int chunk = decoding_chunk_size > 0 ? decoding_chunk_size : 0;
     const float att_scale = 1.0f / sqrtf(64.0f);
     const int Mi = (int)M;
-    // fused FFN (h stays on chip, ffn.cu) is opt-in (WB_FFN_FUSION=1): it is bound by shared-memory bandwidth (every
-    // 128-row tile streams the full 2 MB of W1/W2 through smem) and measures slower than the two pipelined GEMMs
-    static const bool ffn_fusion_on = (getenv("WB_FFN_FUSION") != nullptr);
-    const bool fuse_ffn = ffn_fusion_on && ffn_fused_supported(d, ff) && Mi >= 1024;
+    const long long lda = (long long)d * p3, ldh = (long long)ff * p3;
     for (int li = 0; li < c.enc_layers; ++li) {
         const EncLayer& L = m->layers[li];
         // macaron feed-forward (encoder_layer.py:221-228)
-        RC(layernorm_rows(x, d, Mi, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        if (fuse_ffn) {
-            RC(ffn_fused(a, d, L.ffm1.w, L.ffm1.b, L.ffm2.w, L.ffm2.b, Mi, d, ff, 0.5f, 0, x, d, st));
-        } else {
-            RC(gemm_bf16(a, d, &L.ffm1.tmap, L.ffm1.w, Mi, ff, d, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
-            RC(gemm_bf16(h, ff, &L.ffm2.tmap, L.ffm2.w, Mi, d, ff, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
-        }
+        RC(layernorm_rows(x, d, Mi, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        RC(gemm_bf16(a, lda, &L.ffm1.tmap, L.ffm1.w, Mi, ff, L.ffm1.K, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
+        RC(gemm_bf16(h, ldh, &L.ffm2.tmap, L.ffm2.w, Mi, d, L.ffm2.K, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
         // rel-pos multi-headed self-attention (:231-238)
-        RC(layernorm_rows(x, d, Mi, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        // rel-pos key preparation (K' = K + P[pos], c = u.K + v.P) either fused into the QKV GEMM epilogue
-        // (WB_QKV_RELPOS_FUSION=1, d % 256 == 0) or as its own HBM-bound kernel
-        static const bool qkv_fuse = getenv("WB_QKV_RELPOS_FUSION") != nullptr;
-        const bool fuse_kp = qkv_fuse && d % 256 == 0 && c.precise == 0;
-        if (fuse_kp) {
-            RC(gemm_qkv_relpos(a, d, &L.qkv.tmap, L.qkv.w, Mi, d, H, L.qkv.b, L.pos_proj, d_row_pos, L.pos_u, L.pos_v, qkv,
-                               kbias, st));
-        } else {
-            RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, Mi, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
-            RC(relpos_kprep(reinterpret_cast<const uint8_t*>(qkv) + (size_t)d * 2, 3 * d, L.pos_proj, d_row_pos, L.pos_u,
-                            L.pos_v, Mi, H, kp, d, kbias, st));
-        }
-        {
-            AttnArgs A;
-            A.q = qkv; A.ldq = 3 * d; A.q_rows = M; A.q_col0 = 0;
-            A.k = fuse_kp ? qkv : kp; A.ldk = fuse_kp ? 3 * d : d; A.k_rows = M; A.k_col0 = fuse_kp ? d : 0;
-            A.v = qkv; A.ldv = 3 * d; A.v_rows = M; A.v_col0 = 2 * d;
-            A.kbias = kbias; A.ld_kbias = H;
+        RC(layernorm_rows(x, d, Mi, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        if (sp) {
+            // precise: q, k, v stay fp32; scores = ((q + u) . k + (q + v) . p) / sqrt(d_k) and the softmax on CUDA cores
+            float* qf = reinterpret_cast<float*>(qkv);
+            RC(gemm_bf16(a, lda, &L.qkv.tmap, L.qkv.w, Mi, 3 * d, L.qkv.K, L.qkv.b, EPI_F32, 1.0f, qf, 3 * d, 0, st));
+            AttnF32Args A;
+            A.q = qf; A.ldq = 3 * d; A.k = qf + d; A.ldk = 3 * d; A.v = qf + 2 * d; A.ldv = 3 * d;
+            A.pos_proj = L.pos_proj; A.row_pos = d_row_pos; A.pos_u = L.pos_u; A.pos_v = L.pos_v;
             A.q_start = d_ss; A.q_len = d_tp; A.k_start = d_ss; A.k_len = d_tp;
             A.batch = batch; A.heads = H; A.max_q_len = P.max_tp;
             A.chunk_size = chunk; A.num_left_chunks = num_decoding_left_chunks; A.scale = att_scale;
-            A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
-            RC(attention_forward(A, st));
+            A.out = ctx; A.ldo = lda; A.split3_out = 1;
+            RC(attention_f32(A, st));
+        } else {
+            // rel-pos key preparation: K' = bf16(K + P[pos]), c = u.K + v.P (an HBM-bound pass; folding it into the QKV
+            // GEMM epilogue was measured in round 1 and lost 0.8 ms of GEMM time per step to save 0.39 ms here)
+            RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, Mi, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
+            RC(relpos_kprep(reinterpret_cast<const uint8_t*>(qkv) + (size_t)d * 2, 3 * d, L.pos_proj, d_row_pos, L.pos_u,
+                            L.pos_v, Mi, H, kp, d, kbias, st));
+            {
+                AttnArgs A;
+                A.q = qkv; A.ldq = 3 * d; A.q_rows = M; A.q_col0 = 0;
+                A.k = kp; A.ldk = d; A.k_rows = M; A.k_col0 = 0;
+                A.v = qkv; A.ldv = 3 * d; A.v_rows = M; A.v_col0 = 2 * d;
+                A.kbias = kbias; A.ld_kbias = H;
+                A.q_start = d_ss; A.q_len = d_tp; A.k_start = d_ss; A.k_len = d_tp;
+                A.batch = batch; A.heads = H; A.max_q_len = P.max_tp;
+                A.chunk_size = chunk; A.num_left_chunks = num_decoding_left_chunks; A.scale = att_scale;
+                A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
+                RC(attention_forward(A, st));
+            }
         }
-        RC(gemm_bf16(ctx, d, &L.out.tmap, L.out.w, Mi, d, d, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(gemm_bf16(ctx, lda, &L.out.tmap, L.out.w, Mi, d, L.out.K, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // convolution module (:243-251)
-        RC(layernorm_rows(x, d, Mi, d, L.n_conv.g, L.n_conv.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.pw1.tmap, L.pw1.w, Mi, 2 * d, d, L.pw1.b, EPI_GLU_BF16, 1.0f, g, d, 0, st));
+        RC(layernorm_rows(x, d, Mi, d, L.n_conv.g, L.n_conv.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        RC(gemm_bf16(a, lda, &L.pw1.tmap, L.pw1.w, Mi, 2 * d, L.pw1.K, L.pw1.b, EPI_GLU_BF16, 1.0f, g, lda, sp, st));
         {
             DwConvArgs D;
-            D.g = g; D.ldg = d; D.seq_start = d_ss; D.seq_len = d_tp; D.out_start = d_ss;
+            D.g = g; D.ldg = lda; D.in_split3 = sp; D.seq_start = d_ss; D.seq_len = d_tp; D.out_start = d_ss;
             D.batch = batch; D.max_len = P.max_tp; D.lead = 0; D.d = d; D.ksize = c.cnn_kernel;
             D.causal = c.cnn_causal; D.w = L.dw_w; D.bias = L.dw_b; D.norm_type = c.cnn_norm;
             D.gamma = L.n_cnn.g; D.beta = L.n_cnn.b; D.eps = c.ln_eps; D.pad_vec = L.pad_vec;
             D.pad_until = pad_to_frames > 0 ? pad_to_frames : P.max_tp;
-            D.out = g2; D.ldo = d; D.split3 = 0;
-            RC(dwconv_norm_silu(D, st));
+            D.out = g2; D.ldo = lda; D.split3 = sp;
+            RC(sp ? dwconv_norm_silu_f32(D, st) : dwconv_norm_silu(D, st));
         }
-        RC(gemm_bf16(g2, d, &L.pw2.tmap, L.pw2.w, Mi, d, d, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(gemm_bf16(g2, lda, &L.pw2.tmap, L.pw2.w, Mi, d, L.pw2.K, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // feed-forward (:254-259) and norm_final (:262-263)
-        RC(layernorm_rows(x, d, Mi, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        if (fuse_ffn) {
-            RC(ffn_fused(a, d, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, Mi, d, ff, 0.5f, 0, x, d, st));
-        } else {
-            RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, Mi, ff, d, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
-            RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, Mi, d, ff, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
-        }
+        RC(layernorm_rows(x, d, Mi, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        RC(gemm_bf16(a, lda, &L.ff1.tmap, L.ff1.w, Mi, ff, L.ff1.K, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
+        RC(gemm_bf16(h, ldh, &L.ff2.tmap, L.ff2.w, Mi, d, L.ff2.K, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
         RC(layernorm_rows(x, d, Mi, d, L.n_final.g, L.n_final.b, c.ln_eps, nullptr, 0, 0, x, d, st));
         if (layer_dump_dev)
             WB_CHECK_CUDA(cudaMemcpyAsync(layer_dump_dev + (size_t)(li + 1) * M * d, x, (size_t)M * d * 4,
                                           cudaMemcpyDeviceToDevice, st));
     }
     // after_norm (encoder.py:176-177): fp32 result + bf16 copy for the CTC / decoder GEMMs
-    RC(layernorm_rows(x, d, Mi, d, m->after.g, m->after.b, c.ln_eps, enc_out_bf16_dev, d, 0, enc_out_dev, d, st));
+    RC(layernorm_rows(x, d, Mi, d, m->after.g, m->after.b, c.ln_eps, enc_out_bf16_dev, lda, sp, enc_out_dev, d, st));
     return WB_OK;
 }
 
@@ -442,6 +445,7 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
     const Model* m = reinterpret_cast<const Model*>(mm);
     WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "forward_chunk: model not finalized");
     WB_REQUIRE(xs_dev && y_dev && r_att_cache_dev && workspace_dev, WB_ERR_BAD_ARG, "forward_chunk: null argument");
+    WB_REQUIRE(m->cfg.precise == 0, WB_ERR_UNSUPPORTED, "forward_chunk: the precise (bf16x3) mode covers the full forward only");
     WB_REQUIRE(cache_t1 == 0 || att_cache_dev, WB_ERR_BAD_ARG, "forward_chunk: att_cache missing");
     cudaStream_t st = (cudaStream_t)stream;
     const wb_model_config& c = m->cfg;

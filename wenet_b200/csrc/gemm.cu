@@ -23,7 +23,8 @@
 //                                  epilogue of tile i overlaps the main loop of tile i+1.
 // The epilogue variant is a template parameter for BN = 256 (one specialised kernel per variant; the generic kernel
 // with a run-time switch is ~150 KB of SASS and stalls on instruction fetch) and a run-time switch for BN = 128.
-// wb_gemm_diag reads the in-kernel stall accounting (clock64 around every mbarrier wait) used to tune this file.
+// The in-kernel stall accounting (clock64 around every mbarrier wait, read by wb_gemm_diag) that was used to tune this
+// file is compiled in only with -DWB_GEMM_DIAG.
 #include "common.cuh"
 #include "kernels.h"
 #include <string.h>
@@ -73,13 +74,6 @@ struct GemmParams {
     int cblocks;            // d / 64
     const int4* tile_tab;   // per m-tile: .x t coordinate of tap kh = 0, .y first output row, .z valid rows (<= 114)
     float2* lse_part;       // EPI_LSE: [M][2 * num_n_tiles]
-    // EPI_QKV_RELPOS
-    const float* rp_table;  // [max_pos][rp_d] projected positions
-    const int* rp_row_pos;  // [M]
-    const float* rp_u;      // [rp_d]
-    const float* rp_v;      // [rp_d]
-    float* rp_kbias;        // [M][rp_heads]
-    int rp_d, rp_heads;
 };
 constexpr int kConvRows = 114;   // 6 x 19
 
@@ -87,6 +81,9 @@ constexpr int kConvRows = 114;   // 6 x 19
 //   0 producer: ring slot not free      1 MMA: operands not landed     2 MMA: accumulator stage not drained
 //   3 epilogue: accumulator not ready   4 epilogue: staging buffer still being read by a TMA store
 //   5 epilogue: total time in the tile loop (warp 2)   6 CTA lifetime   7 tiles
+// Compiled in only with -DWB_GEMM_DIAG (tools/bench_ops.py builds that way); the production kernel carries no clock reads
+// and no atomics.
+#ifdef WB_GEMM_DIAG
 __device__ unsigned long long g_gemm_diag[12];   // 8: epilogue tcgen05.ld wait, 9: bias + activation, 10: staging stores + TMA issue
 #define WB_TIMED_WAIT(slot, call)            \
     do {                                     \
@@ -94,6 +91,14 @@ __device__ unsigned long long g_gemm_diag[12];   // 8: epilogue tcgen05.ld wait,
         call;                                \
         diag[slot] += clock64() - _t0;       \
     } while (0)
+#define WB_DIAG(...) __VA_ARGS__
+#else
+#define WB_TIMED_WAIT(slot, call) \
+    do {                          \
+        call;                     \
+    } while (0)
+#define WB_DIAG(...)
+#endif
 
 // EPI >= 0 fixes the epilogue at compile time (the kernel is ~150 KB of SASS with all six variants behind a runtime
 // switch and then stalls on instruction fetch); EPI = -1 keeps the runtime switch (BN = 128: small / test models only).
@@ -127,8 +132,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int num_kb = (p.K + BK - 1) / BK;
     const int epi = (EPI >= 0) ? EPI : p.epi;
-    long long diag[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const long long cta_t0 = clock64();
+    WB_DIAG(long long diag[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long cta_t0 = clock64();)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -267,7 +271,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t acc_phase = 0;
         bool need_wait = false;
         int tile_par = 0;
-        const long long epi_t0 = clock64();
+        WB_DIAG(const long long epi_t0 = clock64();)
         for (int t = t_begin; t < t_end; t += t_step) {
             WB_TILE_COORDS(t)
             long long row_base = (long long)m_tile * BM;
@@ -305,7 +309,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // goes through bias / activation / staging (two register sets, loop fully unrolled)
             uint32_t rbuf[2][32];
             float lse_m = -INFINITY, lse_s = 0.f;   // EPI_LSE: running (max, sum) over this warp's columns, log2 domain
-            float rp_carry = 0.f;                   // EPI_QKV_RELPOS: u.k + v.p over the first half of the current head
             constexpr int c_begin_rel = 0;
             const int c0 = half * kChunksPerWarp;
             if (n_tile * BN + c0 * 32 < p.N) tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c0 * 32), rbuf[0]);
@@ -316,7 +319,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (n0 >= p.N) break;  // warp-uniform
                 uint32_t (&r)[32] = rbuf[ci & 1];
                 WB_TIMED_WAIT(8, tmem_ld_wait_regs(r));
-                const long long t_math0 = clock64();
+                WB_DIAG(const long long t_math0 = clock64();)
                 if (ci + 1 < kChunksPerWarp && n0 + 32 < p.N)
                     tmem_ld_32x32b_x32(taddr0 + (uint32_t)((c + 1) * 32), rbuf[(ci + 1) & 1]);
                 float v[32];
@@ -364,13 +367,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         }
                     };
                     const int sw = lane & 7;
-                    long long t_st0 = 0;
+                    WB_DIAG(long long t_st0 = 0;)
                     bool flush = false;
                     int out_col = 0;
                     if (epi == EPI_F32 || epi == EPI_RESID_F32) {
-                        diag[9] += clock64() - t_math0;
+                        WB_DIAG(diag[9] += clock64() - t_math0;)
                         staging_ready();
-                        t_st0 = clock64();
+                        WB_DIAG(t_st0 = clock64();)
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
                             *reinterpret_cast<float4*>(sbuf + ((u ^ sw) << 4)) =
@@ -388,9 +391,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             g[i + 2] *= v[i + 2];
                             g[i + 3] *= v[i + 3];
                         }
-                        diag[9] += clock64() - t_math0;
+                        WB_DIAG(diag[9] += clock64() - t_math0;)
                         staging_ready();
-                        t_st0 = clock64();
+                        WB_DIAG(t_st0 = clock64();)
 #pragma unroll
                         for (int u = 0; u < 2; ++u)
                             *reinterpret_cast<uint4*>(sbuf + ((((c & 3) * 2 + u) ^ sw) << 4)) =
@@ -399,34 +402,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         flush = ((c & 3) == 3) || (n0 + 32 >= p.N);
                         out_col = (n_tile * BN + (c & ~3) * 32) >> 1;
                     } else {
-                        if (epi == EPI_QKV_RELPOS && n0 >= p.rp_d && n0 < 2 * p.rp_d) {
-                            // K columns: same arithmetic as relpos_kprep_kernel on the bf16-rounded key
-                            const int kc = n0 - p.rp_d;                 // column inside the K third (multiple of 32)
-                            float cacc = (kc & 32) ? rp_carry : 0.f;    // second half of a 64-wide head continues
-                            if (row_ok) {
-                                const float* prow = p.rp_table + (long long)__ldg(p.rp_row_pos + row) * p.rp_d + kc;
-#pragma unroll
-                                for (int i = 0; i < 32; i += 4) {
-                                    const float4 p4 = __ldg(reinterpret_cast<const float4*>(prow + i));
-                                    const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.rp_u + kc + i));
-                                    const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.rp_v + kc + i));
-                                    const float k0 = __bfloat162float(__float2bfloat16_rn(v[i]));
-                                    const float k1 = __bfloat162float(__float2bfloat16_rn(v[i + 1]));
-                                    const float k2 = __bfloat162float(__float2bfloat16_rn(v[i + 2]));
-                                    const float k3 = __bfloat162float(__float2bfloat16_rn(v[i + 3]));
-                                    cacc = fmaf(u4.x, k0, cacc); cacc = fmaf(v4.x, p4.x, cacc);
-                                    cacc = fmaf(u4.y, k1, cacc); cacc = fmaf(v4.y, p4.y, cacc);
-                                    cacc = fmaf(u4.z, k2, cacc); cacc = fmaf(v4.z, p4.z, cacc);
-                                    cacc = fmaf(u4.w, k3, cacc); cacc = fmaf(v4.w, p4.w, cacc);
-                                    v[i] = k0 + p4.x;
-                                    v[i + 1] = k1 + p4.y;
-                                    v[i + 2] = k2 + p4.z;
-                                    v[i + 3] = k3 + p4.w;
-                                }
-                                if (kc & 32) p.rp_kbias[row * p.rp_heads + (kc >> 6)] = cacc;
-                            }
-                            rp_carry = cacc;
-                        }
                         if (epi == EPI_BF16_SILU) {
                             silu_inplace(v);
                         } else if (epi == EPI_BF16_RELU) {
@@ -437,9 +412,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
                         }
-                        diag[9] += clock64() - t_math0;
+                        WB_DIAG(diag[9] += clock64() - t_math0;)
                         staging_ready();
-                        t_st0 = clock64();
+                        WB_DIAG(t_st0 = clock64();)
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             *reinterpret_cast<uint4*>(sbuf + ((((c & 1) * 4 + u) ^ sw) << 4)) = make_uint4(
@@ -462,7 +437,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         }
                         need_wait = true;
                     }
-                    diag[10] += clock64() - t_st0;
+                    WB_DIAG(diag[10] += clock64() - t_st0;)
                     continue;
                 }
                 if (!row_ok) continue;
@@ -592,10 +567,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
         }
         if (p.use_tma_out && lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores
-        diag[5] = clock64() - epi_t0;
+        WB_DIAG(diag[5] = clock64() - epi_t0;)
     }
 
 #undef WB_TILE_COORDS
+#ifdef WB_GEMM_DIAG
     if (lane == 0 && warp <= 2) {   // one lane per role: producer (0), MMA issuer (1), first epilogue warp (2)
         for (int i = 0; i < 12; ++i)
             if (i != 6 && i != 7 && diag[i] != 0) atomicAdd(&g_gemm_diag[i], (unsigned long long)diag[i]);
@@ -606,6 +582,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             atomicAdd(&g_gemm_diag[7], (unsigned long long)nt);
         }
     }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -614,26 +591,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
 }
 
-int g_num_sms = 0;
 int g_sm_reserve = 0;  // SMs left free for concurrently running latency-bound kernels on other streams
 
 template <int BN, bool BRES, int EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
                 const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, BRES, EPI>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        WB_CHECK_CUDA(cudaGetDevice(&dev));
-        WB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    WB_SET_MAX_DYN_SMEM((gemm_tcgen05_kernel<BN, BRES, EPI>), Cfg::kSmemBytes);
+    const int num_sms = current_device_sms();
+    WB_REQUIRE(num_sms > 0, WB_ERR_CUDA, "gemm: cannot query the SM count of the current device");
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int usable = (g_num_sms - g_sm_reserve) > 1 ? (g_num_sms - g_sm_reserve) : 1;
+    const int usable = (num_sms - g_sm_reserve) > 1 ? (num_sms - g_sm_reserve) : 1;
     const int grid = tiles < usable ? tiles : usable;
     ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
     gemm_tcgen05_kernel<BN, BRES, EPI><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
@@ -652,18 +620,9 @@ int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K) {
     return make_tmap_2d_bf16(out, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)gemm_bn_for(N), BK);
 }
 
-struct RelposArgs {
-    const float* table;
-    const int* row_pos;
-    const float* u;
-    const float* v;
-    float* kbias;
-    int d, heads;
-};
-
 static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
                      int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
-                     float2* lse_part, cudaStream_t stream, const RelposArgs* rp = nullptr) {
+                     float2* lse_part, cudaStream_t stream) {
     if (M <= 0) return WB_OK;
     WB_REQUIRE(N > 0 && K > 0, WB_ERR_BAD_ARG, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     WB_REQUIRE((K % 8) == 0 && (lda % 8) == 0, WB_ERR_BAD_ARG,
@@ -704,7 +663,6 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
     const int out_cols = (epi == EPI_GLU_BF16) ? N / 2 : N;
     const int eb = f32_out ? 4 : 2;
     p.use_tma_out = (epi != EPI_LSE && !split3 && (ldc * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
-    WB_REQUIRE(epi != EPI_QKV_RELPOS || p.use_tma_out, WB_ERR_BAD_ARG, "gemm_qkv_relpos: output must be 16-byte aligned");
     if (p.use_tma_out) {
         rc = make_tmap_2d(&tc, out, eb, (uint64_t)M, (uint64_t)out_cols, (uint64_t)ldc, 32, f32_out ? 32 : 64);
         if (rc != WB_OK) return rc;
@@ -713,13 +671,6 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
     p.cblocks = 0;
     p.tile_tab = nullptr;
     p.lse_part = lse_part;
-    p.rp_table = rp ? rp->table : nullptr;
-    p.rp_row_pos = rp ? rp->row_pos : nullptr;
-    p.rp_u = rp ? rp->u : nullptr;
-    p.rp_v = rp ? rp->v : nullptr;
-    p.rp_kbias = rp ? rp->kbias : nullptr;
-    p.rp_d = rp ? rp->d : 0;
-    p.rp_heads = rp ? rp->heads : 0;
     const int num_kb = ceil_div(K, BK);
     if (bn == 256) {
         const bool res = num_kb <= GemmCfg<256>::kResMaxKB;
@@ -735,7 +686,6 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
             WB_GEMM_CASE(EPI_GLU_BF16)
             WB_GEMM_CASE(EPI_F32)
             WB_GEMM_CASE(EPI_LSE)
-            WB_GEMM_CASE(EPI_QKV_RELPOS)
 #undef WB_GEMM_CASE
             default:
                 WB_REQUIRE(false, WB_ERR_BAD_ARG, "gemm: unknown epilogue %d", epi);
@@ -748,16 +698,8 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
 int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
               int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
               cudaStream_t stream) {
-    WB_REQUIRE(epi != EPI_LSE && epi != EPI_QKV_RELPOS, WB_ERR_BAD_ARG, "gemm: this epilogue has its own entry point");
+    WB_REQUIRE(epi != EPI_LSE, WB_ERR_BAD_ARG, "gemm: this epilogue has its own entry point");
     return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, epi, alpha, out, ldc, split3, nullptr, stream);
-}
-
-int gemm_qkv_relpos(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int d, int heads,
-                    const float* bias, const float* pos_table, const int* row_pos, const float* pos_u, const float* pos_v,
-                    void* qkv, float* kbias, cudaStream_t stream) {
-    WB_REQUIRE(d % 256 == 0 && heads * 64 == d, WB_ERR_UNSUPPORTED, "gemm_qkv_relpos: d=%d heads=%d unsupported", d, heads);
-    RelposArgs rp{pos_table, row_pos, pos_u, pos_v, kbias, d, heads};
-    return gemm_impl(A, lda, tmap_b_opt, B, M, 3 * d, d, bias, EPI_QKV_RELPOS, 1.0f, qkv, 3 * d, 0, nullptr, stream, &rp);
 }
 
 int lse_parts(int N) { return 2 * ceil_div(N, gemm_bn_for(N)); }
@@ -799,8 +741,6 @@ int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, con
     p.num_m_tiles = num_tiles;
     p.num_n_tiles = d / 256;
     p.lse_part = nullptr;
-    p.rp_table = nullptr; p.rp_row_pos = nullptr; p.rp_u = nullptr; p.rp_v = nullptr; p.rp_kbias = nullptr;
-    p.rp_d = 0; p.rp_heads = 0;
     p.conv = 1;
     p.cblocks = d / 64;
     p.tile_tab = reinterpret_cast<const int4*>(tile_tab_dev);
@@ -808,12 +748,19 @@ int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, con
 }
 
 int gemm_diag(unsigned long long* out8, int reset) {
+#ifdef WB_GEMM_DIAG
     if (out8) WB_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_gemm_diag, sizeof(unsigned long long) * 12));
     if (reset) {
         unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         WB_CHECK_CUDA(cudaMemcpyToSymbol(g_gemm_diag, z, sizeof(z)));
     }
     return WB_OK;
+#else
+    (void)out8;
+    (void)reset;
+    set_last_error("gemm_diag: the stall accounting is compiled out (build with NVCC_EXTRA=-DWB_GEMM_DIAG)");
+    return WB_ERR_UNSUPPORTED;
+#endif
 }
 
 }  // namespace wb

@@ -15,8 +15,6 @@ enum GemmEpi : int {
     EPI_RESID_F32 = 3,  // out_f32 += alpha * (acc + bias)      (in-place residual stream update)
     EPI_GLU_BF16 = 4,   // out_bf16[:, N/2] = a * sigmoid(g), weight rows packed [16 a | 16 g] x N/32
     EPI_F32 = 5,        // out_f32  = alpha * (acc + bias)
-    EPI_QKV_RELPOS = 7, // out_bf16 = acc + bias, except the K third [d, 2d): K' = bf16(bf16(k) + P[pos[row]]) and the
-                        // per-(row, head) bias c = u . k + v . P is written to kbias (relpos_kprep fused into the QKV GEMM)
     EPI_LSE = 6,        // no matrix output: per (row, 128-column half tile) partial log-sum-exp (max2, sum) of acc + bias
 };
 
@@ -37,11 +35,6 @@ int lse_parts(int N);
 int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream);
 
-// fused QKV projection + rel-pos key preparation (see EPI_QKV_RELPOS); qkv [M][3d] bf16, kbias [M][heads] fp32
-int gemm_qkv_relpos(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int d, int heads,
-                    const float* bias, const float* pos_table /*[max_pos][d]*/, const int* row_pos, const float* pos_u,
-                    const float* pos_v, void* qkv, float* kbias, cudaStream_t stream);
-
 // stall accounting of gemm_tcgen05_kernel (see gemm.cu); out8 may be null
 int gemm_diag(unsigned long long* out8, int reset);
 
@@ -49,12 +42,6 @@ int gemm_diag(unsigned long long* out8, int reset);
 int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, const CUtensorMap* tmap_w, const float* bias,
                         const void* tile_tab_dev /*int4 per tile*/, int num_tiles, long long rows_out, void* out2,
                         cudaStream_t stream);
-
-// ---- fused feed-forward (ffn.cu): x += alpha * (SiLU(a W1^T + b1) W2^T + b2), d_model == 256 only ------------
-bool ffn_fused_supported(int d, int ff);
-void ffn_set_sm_reserve(int n);
-int ffn_fused(const void* a_bf16, long long lda, const void* w1, const float* b1, const void* w2, const float* b2, int M,
-              int d, int ff, float alpha, int act /*0 SiLU, 1 ReLU*/, float* x, long long ldx, cudaStream_t stream);
 
 // ---- fbank (fbank.cu) ------------------------------------------------------------------------
 struct FbankPlan {  // device-resident constants, built once by fbank_plan_create
@@ -94,7 +81,7 @@ int cast_rows_bf16(const float* x, long long ldx, int M, int d, void* out_bf16, 
 int subsample_conv1(const float* feats, long long feat_stride_b, int idim, const int* t1_len,
                     const long long* off1, int batch, int max_t1, const float* cmvn_mean,
                     const float* cmvn_istd, const float* w /*[9][d] fp32*/, const float* bias, int d,
-                    void* out1_bf16, int split_unused, cudaStream_t stream);
+                    void* out1_bf16, int split3 /*rows become [hi|lo|hi], 3d wide*/, cudaStream_t stream);
 // im2col for conv2 (3x3 stride 2) from channels-last conv1 output.
 // out row (off2[b] + t2 * F2 + f2) has K = 9*d entries ordered (kh, kw, c).
 int subsample_im2col(const void* out1_bf16, const long long* off1, const int* t2_len,
@@ -140,8 +127,27 @@ struct DwConvArgs {
     int pad_until;          // padded batch length (reference zero-masks *before* pointwise_conv1)
     void* out; long long ldo; int split3;   // bf16 [rows_out, ldo]; out row = out_start[b] + t
     const int* out_start;
+    int in_split3 = 0;   // precise mode: g rows are [hi | lo | hi] blocks of width d (value = hi + lo)
 };
 int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream);
+// fp32 CUDA-core version for the precise parity mode (precise.cu); honours in_split3
+int dwconv_norm_silu_f32(const DwConvArgs& a, cudaStream_t stream);
+
+// ---- fp32 attention for the precise parity mode (precise.cu) ------------------------------------
+struct AttnF32Args {
+    const float* q; long long ldq;          // fp32 [q_rows, ldq]; head h at col 64h
+    const float* k; long long ldk;
+    const float* v; long long ldv;
+    const float* pos_proj;                  // [max_pos][heads*64] projected positions or null (plain attention)
+    const int* row_pos;                     // [k_rows] position of each key row
+    const float* pos_u; const float* pos_v; // [heads*64]
+    const int* q_start; const int* q_len; const int* k_start; const int* k_len;
+    int batch, heads, max_q_len;
+    int chunk_size, num_left_chunks;        // same meaning as AttnArgs
+    float scale;
+    void* out; long long ldo; int split3_out;   // bf16 [q_rows, ldo], optionally [hi|lo|hi]
+};
+int attention_f32(const AttnF32Args& a, cudaStream_t stream);
 
 // ---- CTC head + searches (ctc.cu, search.cu) ---------------------------------------------------
 // in-place log-softmax over V of logits [M, ldl] (+ optional blank penalty), plus per-row top-k.

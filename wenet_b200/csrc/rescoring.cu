@@ -143,7 +143,7 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
         // cross-attention over the utterance's encoder frames, decoder_layer.py:120-139
         RC(layernorm_rows(x, d, N, d, L.n2.g, L.n2.b, c.ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.ca_q.tmap, L.ca_q.w, N, d, d, L.ca_q.b, EPI_BF16, 1.0f, q, d, 0, st));
-        RC(gemm_bf16(enc_bf16, d, &L.ca_kv.tmap, L.ca_kv.w, (int)enc_rows, 2 * d, d, L.ca_kv.b, EPI_BF16, 1.0f, memkv,
+        RC(gemm_bf16(enc_bf16, m->cfg.precise ? 3 * d : d /*precise: rows are [hi|lo|hi]; the decoder reads hi*/, &L.ca_kv.tmap, L.ca_kv.w, (int)enc_rows, 2 * d, d, L.ca_kv.b, EPI_BF16, 1.0f, memkv,
                      2 * d, 0, st));
         {
             AttnArgs A;
@@ -160,13 +160,8 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
         RC(gemm_bf16(ctx, d, &L.ca_out.tmap, L.ca_out.w, N, d, d, L.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // feed-forward (ReLU), decoder_layer.py:141-147
         RC(layernorm_rows(x, d, N, d, L.n3.g, L.n3.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        static const bool ffn_fusion_on = (getenv("WB_FFN_FUSION") != nullptr);   // see encoder.cu
-        if (ffn_fusion_on && ffn_fused_supported(d, ff) && N >= 1024) {
-            RC(ffn_fused(a, d, L.ff1.w, L.ff1.b, L.ff2.w, L.ff2.b, N, d, ff, 1.0f, 1, x, d, st));
-        } else {
-            RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, N, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
-            RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, N, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
-        }
+        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, N, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
+        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, N, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
     }
     RC(layernorm_rows(x, d, N, d, D.after.g, D.after.b, c.ln_eps, a, d, 0, nullptr, 0, st));
     if (logits != nullptr) {

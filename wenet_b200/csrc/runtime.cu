@@ -22,6 +22,19 @@ void set_last_error(const char* fmt, ...) {
 const char* get_last_error() { return g_err; }
 
 // ---------------------------------------------------------------- profiler
+int current_device_sms() {
+    static std::atomic<int> cache[128] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    std::atomic<int>& slot = cache[dev & 127];
+    int n = slot.load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        slot.store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 int g_prof_on = 0;
 namespace {
 struct ProfRec {

@@ -534,11 +534,7 @@ int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream) {
     P.out_nhyp = a.out_nhyp;
     P.pool = reinterpret_cast<int*>(a.workspace);
     const size_t smem = sizeof(WarpState) * PB_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    WB_SET_MAX_DYN_SMEM(prefix_beam_kernel, smem);
     ProfScope _ps(PT_PREFIX_BEAM, stream, 0.0);
     prefix_beam_kernel<<<ceil_div(a.batch, PB_WARPS), PB_THREADS, smem, stream>>>(P, a.batch);
     count_launch();

@@ -17,7 +17,7 @@ __global__ void conv1_kernel(const float* __restrict__ feats, long long feat_str
                              const int* __restrict__ t1_len, const long long* __restrict__ off1,
                              const float* __restrict__ mean, const float* __restrict__ istd,
                              const float* __restrict__ w, const float* __restrict__ bias, int d,
-                             __nv_bfloat16* __restrict__ out1) {
+                             __nv_bfloat16* __restrict__ out1, int split3) {
     extern __shared__ float s_in[];  // [3][idim]
     const int b = blockIdx.y, t1 = blockIdx.x;
     if (t1 >= t1_len[b]) return;
@@ -41,7 +41,8 @@ __global__ void conv1_kernel(const float* __restrict__ feats, long long feat_str
         w1[k] = w[k * d + c0 + 1];
     }
     const float b0 = bias[c0], b1 = bias[c0 + 1];
-    __nv_bfloat16* orow = out1 + (off1[b] + (long long)t1 * F1) * d + c0;
+    const int ldo = split3 ? 3 * d : d;
+    __nv_bfloat16* orow = out1 + (off1[b] + (long long)t1 * F1) * ldo + c0;
     for (int f1 = 0; f1 < F1; ++f1) {
         float a0 = b0, a1 = b1;
 #pragma unroll
@@ -52,7 +53,14 @@ __global__ void conv1_kernel(const float* __restrict__ feats, long long feat_str
                 a0 = fmaf(w0[kh * 3 + kw], x, a0);
                 a1 = fmaf(w1[kh * 3 + kw], x, a1);
             }
-        *reinterpret_cast<uint32_t*>(orow + (long long)f1 * d) = pack_bf16x2(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+        a0 = fmaxf(a0, 0.f);
+        a1 = fmaxf(a1, 0.f);
+        const uint32_t hi = pack_bf16x2(a0, a1);
+        *reinterpret_cast<uint32_t*>(orow + (long long)f1 * ldo) = hi;
+        if (split3) {
+            *reinterpret_cast<uint32_t*>(orow + (long long)f1 * ldo + d) = pack_bf16x2(a0 - bf16_lo(hi), a1 - bf16_hi(hi));
+            *reinterpret_cast<uint32_t*>(orow + (long long)f1 * ldo + 2 * d) = hi;
+        }
     }
 }
 
@@ -82,15 +90,14 @@ __global__ void im2col_kernel(const uint4* __restrict__ out1, const long long* _
 int subsample_conv1(const float* feats, long long feat_stride_b, int idim, const int* t1_len,
                     const long long* off1, int batch, int max_t1, const float* cmvn_mean,
                     const float* cmvn_istd, const float* w, const float* bias, int d, void* out1_bf16,
-                    int split_unused, cudaStream_t stream) {
-    (void)split_unused;
+                    int split3, cudaStream_t stream) {
     if (batch <= 0 || max_t1 <= 0) return WB_OK;
     WB_REQUIRE(d % 64 == 0 && d <= 2048, WB_ERR_UNSUPPORTED, "conv1: d=%d unsupported", d);
     dim3 grid(max_t1, batch);
     ProfScope _ps(PT_CONV1, stream, (double)batch * max_t1 * (((idim - 3) / 2 + 1) * (double)d * 2.0 + 2.0 * idim * 4.0));
     conv1_kernel<<<grid, d / 2, 3 * idim * sizeof(float), stream>>>(
         feats, feat_stride_b, idim, t1_len, off1, cmvn_mean, cmvn_istd, w, bias, d,
-        reinterpret_cast<__nv_bfloat16*>(out1_bf16));
+        reinterpret_cast<__nv_bfloat16*>(out1_bf16), split3);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

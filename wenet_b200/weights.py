@@ -117,8 +117,13 @@ class ModelSpec:
         self.has_cmvn = configs.get("cmvn", None) is not None
 
 
-def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """Returns {lib tensor name: CPU tensor (fp32 or bf16)}."""
+def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor], precise: bool = False) -> Dict[str, torch.Tensor]:
+    """Returns {lib tensor name: CPU tensor (fp32 or bf16)}.
+
+    precise=True (wb_model_config.precise, the <= 1e-3 parity mode): every encoder / CTC GEMM weight is delivered as
+    bf16 [N, 3K] = per K-block [hi | hi | lo] (bf16x3 against activations written as [hi | lo | hi]); the K-blocks are
+    the d-wide channel groups the activations are split by (one block for a Linear, one per (kh, kw) tap for conv2,
+    one per frequency bin for the embed Linear)."""
     d, F1 = spec.d_model, (spec.input_dim - 3) // 2 + 1
     F2 = (F1 - 3) // 2 + 1
     out: Dict[str, torch.Tensor] = {}
@@ -129,8 +134,17 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Dict[str, t
     def bf(t):
         return t.detach().float().to(torch.bfloat16).contiguous().cpu()
 
-    def lin(dst, src):
-        out[dst + ".w"] = bf(sd[src + ".weight"])
+    def ebf(t, block=None):
+        """encoder-side GEMM weight [N, K]: bf16, or (precise) [hi | hi | lo] per `block` columns of K"""
+        t = t.detach().float()
+        if not precise:
+            return bf(t)
+        N, K = t.shape
+        block = K if block is None else block
+        return split3_weight(t.reshape(N * (K // block), block)).reshape(N, 3 * K).contiguous().cpu()
+
+    def lin(dst, src, enc=False):
+        out[dst + ".w"] = ebf(sd[src + ".weight"]) if enc else bf(sd[src + ".weight"])
         out[dst + ".b"] = f32(sd[src + ".bias"])
 
     def norm(dst, src):
@@ -144,11 +158,11 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Dict[str, t
     out["embed.conv1.w"] = f32(w1.reshape(d, 9).t())
     out["embed.conv1.b"] = f32(sd["encoder.embed.conv.0.bias"])
     w2 = sd["encoder.embed.conv.2.weight"]          # (d, d, 3, 3) -> (d, kh, kw, c_in)
-    out["embed.conv2.w"] = bf(w2.permute(0, 2, 3, 1).reshape(d, 9 * d))
+    out["embed.conv2.w"] = ebf(w2.permute(0, 2, 3, 1).reshape(d, 9 * d), block=d)
     out["embed.conv2.b"] = f32(sd["encoder.embed.conv.2.bias"])
     wo = sd["encoder.embed.out.0.weight"]           # (d, c * F2 + f) -> (d, f * d + c)
     assert wo.shape[1] == d * F2, "embed.out expects %d input features, got %d" % (d * F2, wo.shape[1])
-    out["embed.out.w"] = bf(wo.view(d, d, F2).permute(0, 2, 1).reshape(d, F2 * d))
+    out["embed.out.w"] = ebf(wo.view(d, d, F2).permute(0, 2, 1).reshape(d, F2 * d), block=d)
     out["embed.out.b"] = f32(sd["encoder.embed.out.0.bias"])
     pe = sd.get("encoder.embed.pos_enc.pe")
     pe = sinusoid_pe(spec.max_pos, d) if pe is None else pe.reshape(-1, d)[:spec.max_pos]
@@ -157,16 +171,16 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Dict[str, t
         s, t = "encoder.encoders.%d" % i, "enc.%d" % i
         for n in ("norm_ff_macaron", "norm_mha", "norm_conv", "norm_ff", "norm_final"):
             norm(t + "." + n, s + "." + n)
-        lin(t + ".ffm.w1", s + ".feed_forward_macaron.w_1")
-        lin(t + ".ffm.w2", s + ".feed_forward_macaron.w_2")
-        lin(t + ".ff.w1", s + ".feed_forward.w_1")
-        lin(t + ".ff.w2", s + ".feed_forward.w_2")
+        lin(t + ".ffm.w1", s + ".feed_forward_macaron.w_1", enc=True)
+        lin(t + ".ffm.w2", s + ".feed_forward_macaron.w_2", enc=True)
+        lin(t + ".ff.w1", s + ".feed_forward.w_1", enc=True)
+        lin(t + ".ff.w2", s + ".feed_forward.w_2", enc=True)
         a = s + ".self_attn"
-        out[t + ".att.qkv.w"] = bf(torch.cat([sd[a + ".linear_q.weight"], sd[a + ".linear_k.weight"],
+        out[t + ".att.qkv.w"] = ebf(torch.cat([sd[a + ".linear_q.weight"], sd[a + ".linear_k.weight"],
                                               sd[a + ".linear_v.weight"]], 0))
         out[t + ".att.qkv.b"] = f32(torch.cat([sd[a + ".linear_q.bias"], sd[a + ".linear_k.bias"],
                                                sd[a + ".linear_v.bias"]], 0))
-        lin(t + ".att.out", a + ".linear_out")
+        lin(t + ".att.out", a + ".linear_out", enc=True)
         out[t + ".att.pos.w3"] = split3_weight(sd[a + ".linear_pos.weight"]).cpu()
         out[t + ".att.pos_u"] = f32(sd[a + ".pos_bias_u"].reshape(-1))
         out[t + ".att.pos_v"] = f32(sd[a + ".pos_bias_v"].reshape(-1))
@@ -174,7 +188,7 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Dict[str, t
         pw1_w = sd[c + ".pointwise_conv1.weight"].reshape(2 * d, d)
         pw1_b = sd[c + ".pointwise_conv1.bias"]
         wi, bi = interleave_glu(pw1_w, pw1_b)
-        out[t + ".conv.pw1.w"], out[t + ".conv.pw1.b"] = bf(wi), f32(bi)
+        out[t + ".conv.pw1.w"], out[t + ".conv.pw1.b"] = ebf(wi), f32(bi)
         out[t + ".conv.pad_vec"] = f32(pw1_b[:d].float() * torch.sigmoid(pw1_b[d:].float()))
         out[t + ".conv.dw.w"] = f32(sd[c + ".depthwise_conv.weight"].reshape(d, spec.cnn_kernel))
         out[t + ".conv.dw.b"] = f32(sd[c + ".depthwise_conv.bias"])
@@ -184,10 +198,10 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Dict[str, t
             scale = sd[c + ".norm.weight"].float() / torch.sqrt(sd[c + ".norm.running_var"].float() + spec.ln_eps)
             out[t + ".conv.norm.g"] = f32(scale)
             out[t + ".conv.norm.b"] = f32(sd[c + ".norm.bias"].float() - sd[c + ".norm.running_mean"].float() * scale)
-        out[t + ".conv.pw2.w"] = bf(sd[c + ".pointwise_conv2.weight"].reshape(d, d))
+        out[t + ".conv.pw2.w"] = ebf(sd[c + ".pointwise_conv2.weight"].reshape(d, d))
         out[t + ".conv.pw2.b"] = f32(sd[c + ".pointwise_conv2.bias"])
     norm("after_norm", "encoder.after_norm")
-    lin("ctc", "ctc.ctc_lo")
+    lin("ctc", "ctc.ctc_lo", enc=True)
 
     def decoder(dst, src, n_layers):
         out[dst + ".emb"] = f32(sd[src + ".embed.0.weight"])
@@ -225,8 +239,9 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Dict[str, t
 class DeviceModel:
     """Owns a wb_model handle (weights resident in HBM)."""
 
-    def __init__(self, spec: ModelSpec, sd: Dict[str, torch.Tensor], with_decoder: bool = True):
+    def __init__(self, spec: ModelSpec, sd: Dict[str, torch.Tensor], with_decoder: bool = True, precise: bool = False):
         self.spec = spec
+        self.precise = bool(precise)
         lib = _lib.load()
         has_dec = with_decoder and any(k.startswith("decoder.") for k in sd)
         cfg = WbModelConfig(
@@ -235,10 +250,10 @@ class DeviceModel:
             cnn_norm=0 if spec.cnn_norm == "layer_norm" else 1, vocab=spec.vocab,
             dec_layers=spec.dec_layers if has_dec else 0, rdec_layers=spec.rdec_layers if has_dec else 0,
             dec_heads=spec.dec_heads, dec_ffn_dim=spec.dec_ffn_dim, max_pos=spec.max_pos,
-            has_cmvn=int(spec.has_cmvn), precise=0, ln_eps=spec.ln_eps)
+            has_cmvn=int(spec.has_cmvn), precise=int(self.precise), ln_eps=spec.ln_eps)
         self._h = C.c_void_p()
         check(lib.wb_model_create(C.byref(self._h), C.byref(cfg)), "wb_model_create")
-        packed = pack_state_dict(spec, sd)
+        packed = pack_state_dict(spec, sd, precise=self.precise)
         for name, t in packed.items():
             if not has_dec and name.startswith("dec."):
                 continue
