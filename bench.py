@@ -35,6 +35,31 @@ sys.path.insert(0, ROOT)
 METRIC = "RTFx (audio-s/s) U2++ Conformer attention_rescoring at 1/2/4/8 B200"
 
 
+def host_cores():
+    """CPU cores this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the container)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, int(float(parts[0]) / float(parts[1]) + 0.5)))
+            else:
+                q = int(parts[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                        n = min(n, max(1, int(q / float(f2.read().split()[0]) + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -103,7 +128,7 @@ def workload(name):
 # ----------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline and --impl reference)
 # ----------------------------------------------------------------------------------------------
-def cpu_oracle_step(sd, cfg, pcm_rows, wl):
+def cpu_oracle_step(sd, cfg, pcm_rows, wl, want_enc=False):
     """One pass of the reference path on the CPU (oracle port): fbank -> encoder -> ctc -> prefix beam
     search -> attention rescoring, as wenet/bin/recognize.py:282-303 does per batch."""
     import torch
@@ -125,6 +150,8 @@ def cpu_oracle_step(sd, cfg, pcm_rows, wl):
         pb = O.ctc_prefix_beam_search(lp, el, wl["beam"])
         V = cfg["output_dim"]
         rs = O.attention_rescoring(sd, dcfg, pb, enc, el, V - 1, V - 1, wl["ctc_weight"], wl["reverse_weight"])
+    if want_enc:
+        return [r["tokens"] for r in rs], [enc[b, :int(el[b])] for b in range(len(feats))]
     return [r["tokens"] for r in rs]
 
 
@@ -144,12 +171,46 @@ def cpu_sample(wl, n_utts, seed=777):
 _W = {}
 
 
+def reference_available():
+    """the UNMODIFIED reference (wenet-e2e/wenet) importable on this box: /root/reference in the build container, or its
+    pip --target install under baseline/_ref, which travels with the repo snapshot"""
+    from oracle import shim
+    return shim.have_reference()
+
+
 def _cpu_worker_init(wl_name, threads):
     import torch
     torch.set_num_threads(threads)
     wl = workload(wl_name)
     cfg, sd, rows = cpu_sample(wl, 4)
-    _W.update(wl=wl, cfg=cfg, sd=sd, rows=rows)
+    _W.update(wl=wl, cfg=cfg, sd=sd, rows=rows, ref=None)
+    if reference_available():
+        # the reference's own modules and search code (wenet/bin/recognize.py:289-303 calls exactly model.decode)
+        from oracle import shim
+        ref_cfg = dict(cfg, cmvn=None)
+        ref_cfg.pop("cmvn_conf", None)
+        model = shim.init_reference_model(ref_cfg)
+        from wenet.models.transformer.cmvn import GlobalCMVN
+        model.encoder.global_cmvn = GlobalCMVN(torch.zeros(80), torch.ones(80))
+        model.load_state_dict(sd, strict=False)
+        model.eval()
+        _W["ref"] = model
+
+
+def reference_step(model, pcm_rows, wl):
+    """the reference path itself on the CPU: processor.compute_fbank -> ASRModel.decode(attention_rescoring)"""
+    import torch
+    from wenet.dataset import processor
+    feats = [processor.compute_fbank(dict(key="k", wav=(r.float() / 32768.0).unsqueeze(0), sample_rate=16000),
+                                     num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0)["feat"] for r in pcm_rows]
+    lens = torch.tensor([f.shape[0] for f in feats])
+    xs = torch.zeros(len(feats), int(lens.max()), 80)
+    for b, f in enumerate(feats):
+        xs[b, :f.shape[0]] = f
+    with torch.no_grad():
+        res = model.decode(["attention_rescoring"], xs, lens, wl["beam"], ctc_weight=wl["ctc_weight"],
+                           reverse_weight=wl["reverse_weight"])
+    return [r.tokens for r in res["attention_rescoring"]]
 
 
 def _cpu_worker_ready(i):
@@ -157,7 +218,11 @@ def _cpu_worker_ready(i):
 
 
 def _cpu_worker_step(i):
-    toks = cpu_oracle_step(_W["sd"], _W["cfg"], [_W["rows"][i % len(_W["rows"])]], _W["wl"])
+    rows = [_W["rows"][i % len(_W["rows"])]]
+    if _W["ref"] is not None:
+        toks = reference_step(_W["ref"], rows, _W["wl"])
+    else:
+        toks = cpu_oracle_step(_W["sd"], _W["cfg"], rows, _W["wl"])
     return len(toks[0])
 
 
@@ -166,10 +231,11 @@ class CpuArm:
 
     def __init__(self, wl_name):
         import multiprocessing as mp
-        ncpu = os.cpu_count() or 1
+        ncpu = host_cores()
         self.threads = min(8, ncpu)
         self.procs = max(1, min(16, ncpu // self.threads))
         self.wl = workload(wl_name)
+        self.kind = "reference" if reference_available() else "port"
         self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_cpu_worker_init,
                                                  initargs=(wl_name, self.threads))
         # worker start-up (interpreter, torch import, weight synthesis) is not part of any timed step
@@ -183,9 +249,13 @@ class CpuArm:
         return n * self.wl["seconds"], time.perf_counter() - t0
 
     def describe(self, utts_per_proc=1):
+        impl = ("the UNMODIFIED reference (wenet processor.compute_fbank + ASRModel.decode, fp32; /root/reference or its pip --target copy baseline/_ref)"
+                if self.kind == "reference" else
+                "oracle port of the reference path: torch-CPU ops + the reference's Python search loops")
         return ("%d x %.0f s utterance(s) per step (%d worker processes x %d threads, one utterance each), same "
-                "model/mode/beam; oracle port of the reference path: torch-CPU ops + the reference's Python search "
-                "loops" % (self.procs * utts_per_proc, self.wl["seconds"], self.procs, self.threads))
+                "model/mode/beam; %s; %d usable host cores (affinity / cgroup quota), os.cpu_count() = %d"
+                % (self.procs * utts_per_proc, self.wl["seconds"], self.procs, self.threads, impl, host_cores(),
+                   os.cpu_count() or 0))
 
     def close(self):
         self.pool.close()
@@ -211,8 +281,8 @@ def run_reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "recipe": wl["recipe"], "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": arm.procs * arm.threads, "kind": "port",
-                             "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": host_cores(),
+                             "threads_used": arm.procs * arm.threads, "kind": arm.kind, "sample": sample},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     arm.close()
@@ -235,6 +305,9 @@ def main():
     ap.add_argument("--mode", default="attention_rescoring",
                     choices=["attention_rescoring", "ctc_prefix_beam_search", "ctc_greedy_search"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the token / encoder_out check against the CPU oracle")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the extra block (ragged global list, configs[2] large model, configs[3] streaming latency)")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event profiler")
     ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the GEMM / FFN kernels leave free (-1: 8 when in flight > 1)")
     ap.add_argument("--inflight", type=int, default=4,
@@ -314,11 +387,11 @@ def main():
     slot_models = [model] + [model.clone_shared() for _ in range(n_slots - 1)]
     slot_streams = [torch.cuda.Stream(device=dev) for _ in range(n_slots)]
 
-    def run_steps(fn, steps):
+    def run_steps(fn, steps, slot_models=slot_models):
         """fn(i, mdl) for i in range(steps), distributed over the slots."""
         if n_slots == 1:
             for i in range(steps):
-                fn(i, model)
+                fn(i, slot_models[0])
             return
         nxt = [0]
         lock = threading.Lock()
@@ -353,11 +426,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, slot_models=slot_models):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        run_steps(fn, steps)
+        run_steps(fn, steps, slot_models)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -384,32 +457,44 @@ def main():
 
     # ---- per-kernel pass (roofline / kernel table): CUDA events around every launch, ONE batch in flight so that the
     #      durations are not stretched by kernels of other batches sharing the SMs ----
-    prof = None
-    prof_steps = 0
-    if not args.no_profile:
-        prof_steps = max(2, min(args.steps, 4))
+    def profile_pass(step_fn, mdl, steps):
+        """per-kernel-family CUDA-event times over `steps` extra steps with ONE batch in flight"""
         lib.wb_set_sm_reserve(0)
         lib.wb_prof_reset()
         lib.wb_prof_enable(1)
         torch.cuda.synchronize()
         t_p0 = time.perf_counter()
-        for i in range(prof_steps):
-            step(dev_pcm[i % NROT], model)
+        for i in range(steps):
+            step_fn(i, mdl)
         torch.cuda.synchronize()
-        prof_ms = 1e3 * (time.perf_counter() - t_p0)
+        wall_ms = 1e3 * (time.perf_counter() - t_p0)
         lib.wb_prof_enable(0)
         nt = lib.wb_prof_num_tags()
         pms, pwork, pl = (C.c_double * nt)(), (C.c_double * nt)(), (C.c_longlong * nt)()
         lib.wb_prof_collect(pms, pwork, pl)
-        prof = {lib.wb_prof_tag_name(t).decode(): {"ms": pms[t], "work": pwork[t], "launches": int(pl[t])}
-                for t in range(nt) if pl[t] > 0}
+        out = {lib.wb_prof_tag_name(t).decode(): {"ms": pms[t], "work": pwork[t], "launches": int(pl[t])}
+               for t in range(nt) if pl[t] > 0}
         lib.wb_prof_reset()
         lib.wb_set_sm_reserve(args.sm_reserve if args.sm_reserve >= 0 else (8 if n_slots > 1 else 0))
+        return out, wall_ms
+
+    prof = None
+    prof_steps = 0
+    if not args.no_profile:
+        prof_steps = max(2, min(args.steps, 4))
+        prof, prof_ms = profile_pass(lambda i, mdl: step(dev_pcm[i % NROT], mdl), model, prof_steps)
 
     # ---- end to end: pinned host PCM -> H2D -> decode -> results on host ----
     def e2e_step(i, mdl):
         pcm = host_pcm[i % NROT].to(dev, non_blocking=True)
-        return step(pcm, mdl)
+        res = step(pcm, mdl)
+        # what recognize.py:296-311 reads of every result: the token list (and the cli the confidence) as Python objects
+        n = 0
+        for r in res[args.mode]:
+            n += len(r.tokens)
+            if r.confidence < 0.0:
+                raise RuntimeError("negative confidence")
+        return n
 
     if n_slots == 1:
         for i in range(2):
@@ -445,8 +530,8 @@ def main():
         "gpu_launches": int(launches),
     }
     if prof is not None and "gemm_tcgen05" in prof:
-        # dominant kernel family = the tcgen05 GEMMs (plain + the fused FFN, which is two chained GEMMs)
-        fam = [prof[k] for k in ("gemm_tcgen05", "ffn_fused_tcgen05") if k in prof]
+        # dominant kernel family = the tcgen05 GEMMs
+        fam = [prof[k] for k in ("gemm_tcgen05",) if k in prof]
         g = {"ms": sum(v["ms"] for v in fam), "work": sum(v["work"] for v in fam),
              "launches": sum(v["launches"] for v in fam)}
         ach = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
@@ -457,8 +542,7 @@ def main():
             traffic, traffic_of = tj["traffic_bytes_per_launch"], tj["kernel"]
         except (OSError, KeyError, ValueError):
             pass
-        line["roofline"] = {"kernel": "tcgen05 GEMM family: gemm_tcgen05_kernel (Linear / pointwise-conv / im2col-conv) + "
-                                      "ffn_fused_kernel (W1+SiLU+W2)",
+        line["roofline"] = {"kernel": "tcgen05 GEMM family: gemm_tcgen05_kernel (Linear / pointwise-conv / implicit-GEMM conv2)",
                             "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                             "frac": ach / peaks["tf_sust"], "traffic": traffic, "traffic_of": traffic_of,
                             "peak_source": peaks["src"] + " (sustained bf16)",
@@ -473,12 +557,129 @@ def main():
                                **({"GBps": v["work"] / (v["ms"] * 1e-3) / 1e9} if (v["work"] > 0 and "tcgen05" not in k) else {}),
                                **({"TFLOPs": v["work"] / (v["ms"] * 1e-3) / 1e12} if (v["work"] > 0 and "tcgen05" in k) else {})}
                            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-    if rank == 0 and not args.no_cpu_baseline:
+    # ---- extra block: ragged global list (all N); BASELINE configs[2] and configs[3] (N = 1) ----
+    if not args.no_extra:
+        extra = {}
+        # (iii) a fixed GLOBAL list of world x B utterances with lengths U[5 s, 30 s], sharded by shard_utterances
+        #       (LPT on the attention-aware cost): scaling efficiency on it measures the partition balance
+        rs = np.random.Generator(np.random.PCG64(20260923))
+        g_secs = np.round(rs.uniform(5.0, 30.0, size=world * B), 2)
+        g_frames = [fb.num_frames(int(sec * 16000)) for sec in g_secs]
+        mine_r = shard_utterances(g_frames, world, rank, d_model=cfg["encoder_conf"]["output_size"])
+        my_n = [int(g_secs[i] * 16000) for i in mine_r]
+        order = sorted(range(len(my_n)), key=lambda k: -my_n[k])           # processor.padding sorts by length
+        my_n = [my_n[k] for k in order]
+        Br = len(my_n)
+        nmax = max(my_n)
+        rag_pcm = []
+        for r in range(NROT):
+            t = dev_pcm[r][torch.arange(Br, device=dev) % B, :nmax].clone()
+            for b, nb in enumerate(my_n):
+                t[b, nb:] = 0
+            rag_pcm.append(t)
+        ns_r = torch.tensor(my_n, dtype=torch.int32, device=dev)
+        flens_r = torch.tensor([fb.num_frames(x) for x in my_n], dtype=torch.int64, device=dev)
+
+        def step_r(i, mdl):
+            feats = fb(rag_pcm[i % NROT], ns_r)
+            return mdl.decode(methods, feats, flens_r, beam_size=wl["beam"], ctc_weight=wl["ctc_weight"],
+                              reverse_weight=wl["reverse_weight"])
+
+        run_steps(step_r, 2 * n_slots)
+        ms_r = timed(step_r, args.steps)
+        my_audio = float(sum(my_n)) / 16000.0
+        aud = torch.tensor([my_audio], device=dev, dtype=torch.float64)
+        if world > 1:
+            allaud = [torch.zeros_like(aud) for _ in range(world)]
+            dist.all_gather(allaud, aud)
+            per_rank = [float(a.item()) for a in allaud]
+        else:
+            per_rank = [my_audio]
+        extra["ragged"] = {"value": sum(per_rank) * args.steps / (ms_r / 1e3), "unit": "audio-s/s",
+                           "ms_per_step": ms_r / args.steps, "utterances": world * B,
+                           "lengths": "U[5 s, 30 s], seed 20260923, fixed global list sharded by shard_utterances (LPT)",
+                           "audio_s_per_rank": per_rank, "utts_on_rank0": Br}
+        if world == 1 and args.workload == "small":
+            # (ii) BASELINE configs[3]: forward_chunk chunk 16 / 4 left chunks, batch 1, steady state as a CUDA graph
+            from wenet_b200.asr_model import StreamingSession
+            chunk, left, n_chunks, n_warm = 16, 4, 200, 20
+            window, hop = (chunk - 1) * 4 + 7, 4 * chunk
+            gen = torch.Generator().manual_seed(777)
+            sfeats = torch.randn(1, hop * (n_chunks + n_warm) + window, 80, generator=gen).to(dev)
+            sess = StreamingSession(model, chunk, left)
+            evs = []
+            for i in range(n_chunks + n_warm):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sess.step(sfeats[:, i * hop:i * hop + window])
+                e1.record()
+                torch.cuda.synchronize()      # one chunk in flight: a latency measurement
+                evs.append((e0, e1))
+            lat = np.array([a.elapsed_time(b) for a, b in evs[n_warm:]])
+            extra["streaming"] = {"config": "S U2++ 12L/256d forward_chunk, chunk 16, num_left_chunks 4, batch 1, CUDA graph",
+                                  "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                                  "chunks": n_chunks, "audio_s_per_chunk": chunk * 0.04,
+                                  "chunk_rtf": float(np.percentile(lat, 50)) / 1e3 / (chunk * 0.04)}
+            # (i) BASELINE configs[2] model: U2++ large 24L/512d/8h, 32 x 30 s, attention_rescoring
+            wl_l = workload("large")
+            cfg_l = synth.recipe(wl_l["recipe"])
+            model_l = B200ASRModel(cfg_l, synth.synth_state_dict(cfg_l, seed=777), device=dev)
+            Bl = wl_l["batch"]
+            slots_l = [model_l] + [model_l.clone_shared() for _ in range(n_slots - 1)]
+            ns_l, flens_l = ns[:Bl], flens[:Bl]
+
+            def step_l(i, mdl):
+                feats = fb(dev_pcm[i % NROT][:Bl], ns_l)
+                return mdl.decode(methods, feats, flens_l, beam_size=wl_l["beam"], ctc_weight=wl_l["ctc_weight"],
+                                  reverse_weight=wl_l["reverse_weight"])
+
+            for i in range(3):
+                step_l(i, model_l)
+            run_steps(step_l, 2 * n_slots, slots_l)
+            steps_l = max(4, args.steps // 2)
+            ms_l = timed(step_l, steps_l, slots_l)
+            pl_, plw = profile_pass(step_l, model_l, 2)
+            gl = pl_.get("gemm_tcgen05", {"ms": 0.0, "work": 0.0})
+            ach_l = gl["work"] / (gl["ms"] * 1e-3) / 1e12 if gl["ms"] > 0 else 0.0
+            extra["large"] = {"workload": wl_l["label"], "value": Bl * wl_l["seconds"] * steps_l / (ms_l / 1e3),
+                              "unit": "audio-s/s", "ms_per_step": ms_l / steps_l, "steps": steps_l,
+                              "gemm_tflops": ach_l, "gemm_frac": ach_l / peaks["tf_sust"],
+                              "kernels_ms_per_step": {k: v["ms"] / 2 for k, v in sorted(pl_.items(), key=lambda kv: -kv[1]["ms"])}}
+            del slots_l, model_l
+        line["extra"] = extra
+
+    # ---- verification against the CPU oracle (rank 0, N = 1): tokens of two utterances of batch 0 ----
+    if rank == 0 and world == 1 and not args.no_verify and args.mode == "attention_rescoring":
+        from wenet_b200.asr_model import B200ASRModel as _M
+        n_v = 2
+        rows = [host_pcm[0][b, :n] for b in range(n_v)]
+        t_v0 = time.perf_counter()
+        ref_tok, ref_enc = cpu_oracle_step(sd, cfg, rows, wl, want_enc=True)
+        t_oracle = time.perf_counter() - t_v0
+        ver = {"utterances": n_v, "checker": "oracle/wenet_oracle.py (fp32, pinned to the reference), %.1f s" % t_oracle}
+        for tag, mdl in (("bf16", model), ("precise", _M(cfg, sd, device=dev, precise=True))):
+            feats_v = fb(dev_pcm[0][:n_v], ns[:n_v])
+            out_v = mdl.decode(methods, feats_v, flens[:n_v], beam_size=wl["beam"], ctc_weight=wl["ctc_weight"],
+                               reverse_weight=wl["reverse_weight"])[args.mode]
+            enc_v, _ = mdl.encoder(feats_v, flens[:n_v], -1, -1)
+            dmax = max(float((enc_v[b, :ref_enc[b].shape[0]].cpu() - ref_enc[b]).abs().max()) for b in range(n_v))
+            dmean = float(np.mean([float((enc_v[b, :ref_enc[b].shape[0]].cpu() - ref_enc[b]).abs().mean()) for b in range(n_v)]))
+            same = [list(out_v[b].tokens) == list(ref_tok[b]) for b in range(n_v)]
+            ver[tag] = {"tokens_identical": int(sum(same)), "encoder_out_max_abs": dmax, "encoder_out_mean_abs": dmean}
+        line["parity"] = {"mode": "precise", "max": ver["precise"]["encoder_out_max_abs"],
+                          "mean": ver["precise"]["encoder_out_mean_abs"],
+                          "bf16_mode": {"max": ver["bf16"]["encoder_out_max_abs"], "mean": ver["bf16"]["encoder_out_mean_abs"]},
+                          "what": "encoder_out of %d x %.0f s utterances vs the fp32 CPU oracle" % (n_v, wl["seconds"])}
+        line["verify"] = ver
+        line["verified"] = bool(ver["precise"]["tokens_identical"] == n_v and ver["precise"]["encoder_out_max_abs"] <= 1e-3
+                                and ver["bf16"]["encoder_out_max_abs"] < 5.9e-2)
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         arm = CpuArm(args.workload)
         arm.step()                      # warm-up pass (worker start-up, lazy torch init)
         audio, dt = arm.step()
-        line["cpu_baseline"] = {"value": audio / dt, "unit": "audio-s/s", "cores": arm.procs * arm.threads, "kind": "port",
-                                "sample": arm.describe()}
+        line["cpu_baseline"] = {"value": audio / dt, "unit": "audio-s/s", "cores": host_cores(),
+                                "threads_used": arm.procs * arm.threads, "kind": arm.kind, "sample": arm.describe()}
         arm.close()
     if rank == 0:
         args.emit(line)

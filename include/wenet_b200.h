@@ -107,7 +107,7 @@ typedef struct {
   int32_t cnn_kernel;  /* cnn_module_kernel */
   int32_t cnn_causal;  /* causal */
   int32_t cnn_norm;    /* 0 = layer_norm, 1 = batch_norm (folded, eval) */
-  int32_t vocab;       /* output_dim */
+  int32_t vocab;       /* output_dim; 0 = encoder-only handle (no CTC head, no decoder) */
   int32_t dec_layers;  /* left (l2r) decoder blocks, 0 = no decoder */
   int32_t rdec_layers; /* right (r2l) decoder blocks, 0 = none */
   int32_t dec_heads;
@@ -120,7 +120,8 @@ typedef struct {
                           in fp32 on CUDA cores: encoder_out / CTC log-probs within 1e-3 of the fp32 reference.
                           enc_out_bf16_dev then has 3 * d_model columns ([hi | lo | hi]) everywhere in this API;
                           the rescoring decoder reads its hi block and stays bf16.  Full forward only. */
-  float ln_eps;        /* 1e-5 */
+  float ln_eps;        /* encoder LayerNorm eps (encoder_conf.norm_eps, 1e-5) */
+  float dec_ln_eps;    /* decoder LayerNorm eps (decoder_conf.norm_eps, decoder.py:83); <= 0 means "same as ln_eps" */
 } wb_model_config;
 
 enum { WB_F32 = 0, WB_BF16 = 1, WB_I32 = 2 };

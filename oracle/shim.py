@@ -20,7 +20,17 @@ import types
 import typing
 import wave
 
-REFERENCE_ROOT = os.environ.get("WENET_REFERENCE_ROOT", "/root/reference")
+def _find_reference():
+    """WENET_REFERENCE_ROOT, else the read-only tree of the build container, else the pip --target install of the
+    same unmodified sources under baseline/_ref (git-ignored; it travels to the GPU box with the snapshot)."""
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for c in (os.environ.get("WENET_REFERENCE_ROOT"), "/root/reference", os.path.join(repo, "baseline", "_ref")):
+        if c and os.path.isdir(os.path.join(c, "wenet")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def have_reference() -> bool:

@@ -138,16 +138,35 @@ def test_plugin_config_reconstruction_and_registry():
               "use_dynamic_chunk", "bidirectional", "dec_layers", "rdec_layers", "dec_heads", "dec_ffn_dim", "has_cmvn"):
         assert getattr(a, k) == getattr(b, k), k
     cls = plugin.install()
-    from wenet.utils import init_model as im
-    import wenet.dataset.processor as processor
-    from wenet_b200.fbank import compute_fbank
-    assert im.WENET_MODEL_CLASSES["asr_model"] is cls and processor.compute_fbank is compute_fbank
-    m2 = shim.init_reference_model(dict(ref_cfg))
-    assert type(m2).__name__ == "B200ASRModelPlugin"
-    assert set(m2.state_dict().keys()) == set(model.state_dict().keys())
-    import wenet_b200._lib as L
-    with pytest.raises(L.WbError):          # CPU model -> loud failure, never a fallback
-        m2.decode(["ctc_greedy_search"], torch.zeros(1, 50, 80), torch.tensor([50]))
-    # restore the registry for other tests in this process
+    try:
+        from wenet.utils import init_model as im
+        import wenet.dataset.processor as processor
+        assert im.WENET_MODEL_CLASSES["asr_model"] is cls and processor.compute_fbank is plugin._fbank_dropin
+        assert plugin.install() is cls                      # idempotent
+        m2 = shim.init_reference_model(dict(ref_cfg))
+        assert type(m2).__name__ == "B200ASRModelPlugin"
+        assert type(m2.encoder).__name__ == "B200ConformerEncoderPlugin" and type(m2.ctc).__name__ == "B200CTCPlugin"
+        assert set(m2.state_dict().keys()) == set(model.state_dict().keys())
+        import wenet_b200._lib as L
+        x, n = torch.zeros(1, 50, 80), torch.tensor([50])
+        for call in (lambda: m2.decode(["ctc_greedy_search"], x, n), lambda: m2.encoder(x, n),
+                     lambda: m2.forward_encoder_chunk(x, 0, -1), lambda: m2.ctc_activation(torch.zeros(1, 4, 128))):
+            with pytest.raises(L.WbError):      # CPU model -> loud failure, never a fallback
+                call()
+        # training mode keeps the reference's autograd path
+        m2.train()
+        y, _ = m2.encoder(x, n)
+        assert y.requires_grad
+        m2.eval()
+        # dither / DataLoader-worker cases of compute_fbank keep the reference function
+        s = processor.compute_fbank(dict(key="k", wav=torch.zeros(1, 1600), sample_rate=16000), num_mel_bins=80, dither=1.0)
+        assert s["feat"].shape == (8, 80)
+        # configurations outside the implemented set fail at construction
+        bad = dict(ref_cfg, encoder_conf=dict(ref_cfg["encoder_conf"], pos_enc_layer_type="abs_pos",
+                                              selfattention_layer_type="selfattn"))
+        with pytest.raises(NotImplementedError):
+            shim.init_reference_model(bad)
+    finally:
+        plugin.uninstall()      # restore the registries for other tests in this process
     from wenet.models.transformer.asr_model import ASRModel
-    im.WENET_MODEL_CLASSES["asr_model"] = ASRModel
+    assert im.WENET_MODEL_CLASSES["asr_model"] is ASRModel

@@ -1,0 +1,200 @@
+"""The drop-in boundary end to end (BASELINE configs[0] plumbing + SURVEY.md section 8b): the reference's own
+`wenet/bin/recognize.py`, UNMODIFIED, run once on the CPU with the reference classes and once on the GPU after
+`wenet_b200.install()`, on the same synthetic 8 x 10 s wav files / data.list / units.txt / train.yaml / final.pt.
+
+Needs a reference tree: /root/reference in the build container, or the pip --target install of the same sources under
+baseline/_ref (git-ignored, travels to the GPU box) - skipped otherwise.
+
+Gates: in precise mode the `text` files of ctc_greedy_search and ctc_prefix_beam_search equal the CPU reference's
+line for line (attention_rescoring: the decoder stays bf16, >= 0.95 token agreement); in bf16 mode the token agreement
+(1 - edit distance / length) is printed and must be >= 0.9.
+"""
+import json
+import os
+import sys
+import wave
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+from helpers import SEED
+from oracle import shim
+from wenet_b200 import synth
+
+needs_ref = pytest.mark.skipif(not shim.have_reference(), reason="no reference tree (baseline/_ref or /root/reference)")
+
+MODES = ["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"]
+
+
+def _write_fixture(root, recipe="u2_small", n_utt=8, seconds=10):
+    cfg = synth.recipe(recipe)
+    V = cfg["output_dim"]
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    ns = [16000 * seconds - 37 * i for i in range(n_utt)]          # slightly ragged lengths
+    pcm = synth.synth_pcm(n_utt, ns, seed=SEED)
+    os.makedirs(os.path.join(root, "wav"), exist_ok=True)
+    with open(os.path.join(root, "data.list"), "w") as fl:
+        for i, n in enumerate(ns):
+            path = os.path.join(root, "wav", "utt%02d.wav" % i)
+            with wave.open(path, "wb") as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(16000)
+                w.writeframes(pcm[i, :n].numpy().astype("<i2").tobytes())
+            fl.write(json.dumps({"key": "utt%02d" % i, "wav": path, "txt": "ab"}) + "\n")
+    syms = ["<blank>", "<unk>"] + ["a", "b"] + ["t%d;" % i for i in range(4, V - 1)] + ["<sos/eos>"]
+    assert len(syms) == V
+    with open(os.path.join(root, "units.txt"), "w") as fu:
+        for i, s in enumerate(syms):
+            fu.write("%s %d\n" % (s, i))
+    with open(os.path.join(root, "global_cmvn"), "w") as fc:     # placeholder statistics; final.pt carries the real buffers
+        json.dump({"mean_stat": [0.0] * 80, "var_stat": [1.0] * 80, "frame_num": 1}, fc)
+    conf = dict(cfg)
+    conf["cmvn_conf"] = {"cmvn_file": os.path.join(root, "global_cmvn"), "is_json_cmvn": True}
+    conf["tokenizer"] = "char"
+    conf["tokenizer_conf"] = {"symbol_table_path": os.path.join(root, "units.txt"), "split_with_space": False,
+                              "bpe_path": None, "non_lang_syms_path": None, "is_multilingual": False, "num_languages": 1,
+                              "special_tokens": {"<blank>": 0, "<unk>": 1, "<sos>": V - 1, "<eos>": V - 1}}
+    conf["dataset"] = "asr"
+    conf["dataset_conf"] = {
+        "filter_conf": {"max_length": 40960, "min_length": 0, "token_max_length": 200, "token_min_length": 1},
+        "resample_conf": {"resample_rate": 16000}, "speed_perturb": False,
+        "fbank_conf": {"num_mel_bins": 80, "frame_shift": 10, "frame_length": 25, "dither": 0.1},
+        "spec_aug": False, "shuffle": False, "sort": False,
+        "batch_conf": {"batch_type": "static", "batch_size": 8}}
+    with open(os.path.join(root, "train.yaml"), "w") as fy:
+        yaml.safe_dump(conf, fy)
+    torch.save(sd, os.path.join(root, "final.pt"))
+    return cfg
+
+
+def _recognize(root, result_dir, extra):
+    from wenet.bin import recognize
+    argv = ["recognize.py", "--config", os.path.join(root, "train.yaml"), "--test_data", os.path.join(root, "data.list"),
+            "--checkpoint", os.path.join(root, "final.pt"), "--result_dir", result_dir, "--batch_size", "8",
+            "--beam_size", "10", "--ctc_weight", "0.3", "--modes"] + MODES + extra
+    old = sys.argv
+    sys.argv = argv
+    try:
+        recognize.main()
+    finally:
+        sys.argv = old
+    out = {}
+    for m in MODES:
+        with open(os.path.join(result_dir, m, "text")) as f:
+            out[m] = dict(line.rstrip("\n").split(" ", 1) if " " in line.rstrip("\n") else (line.rstrip("\n"), "")
+                          for line in f)
+    return out
+
+
+def _toks(text):
+    return [t for t in text.replace(";", "; ").split() if t] if ";" in text else list(text)
+
+
+def _agree(a, b):
+    from test_parity_gpu import _agreement
+    return _agreement(_toks(a), _toks(b))
+
+
+@needs_ref
+def test_recognize_py_runs_unmodified_through_install(tmp_path):
+    shim.install()
+    from wenet_b200 import plugin
+    root = str(tmp_path)
+    _write_fixture(root)
+    plugin.uninstall()
+    ref = _recognize(root, os.path.join(root, "res_cpu"), ["--device", "cpu"])
+    assert all(len(ref[m]) == 8 for m in MODES)
+    plugin.install()
+    try:
+        os.environ["WENET_B200_PRECISE"] = "1"
+        l0 = __import__("wenet_b200")._lib.load().wb_launch_count()
+        got = _recognize(root, os.path.join(root, "res_gpu_precise"), ["--gpu", "0"])
+        assert __import__("wenet_b200")._lib.load().wb_launch_count() > l0, "the B200 library did not run"
+        for m in MODES:
+            rates = [_agree(got[m][k], ref[m][k]) for k in sorted(ref[m])]
+            print("recognize.py through install() [precise] %s: token agreement with the CPU reference min %.4f mean %.4f"
+                  % (m, min(rates), float(np.mean(rates))))
+            if m != "attention_rescoring":
+                assert got[m] == ref[m], m
+            else:
+                assert min(rates) >= 0.95
+        os.environ["WENET_B200_PRECISE"] = "0"
+        got = _recognize(root, os.path.join(root, "res_gpu_bf16"), ["--gpu", "0"])
+        for m in MODES:
+            rates = [_agree(got[m][k], ref[m][k]) for k in sorted(ref[m])]
+            print("recognize.py through install() [bf16] %s: token agreement with the CPU reference min %.4f mean %.4f, "
+                  "identical lines %d / 8" % (m, min(rates), float(np.mean(rates)),
+                                              sum(got[m][k] == ref[m][k] for k in ref[m])))
+            assert float(np.mean(rates)) >= 0.9
+    finally:
+        os.environ.pop("WENET_B200_PRECISE", None)
+        plugin.uninstall()
+
+
+@needs_ref
+def test_plugin_entry_points_run_the_library(tmp_path):
+    """model.encoder(...), encoder.forward_chunk, forward_encoder_chunk, ctc_activation, ctc_logprobs on a model built by
+    the reference's init_model after install(): every call must launch library kernels and agree with the reference
+    modules' own fp32 result (bf16 budget)."""
+    shim.install()
+    from wenet_b200 import _lib, plugin
+    from test_parity_gpu import _gpu_fbank
+    cfg = synth.recipe("tiny")
+    ref_cfg = dict(cfg, cmvn=None)
+    ref_cfg.pop("cmvn_conf", None)
+    plugin.uninstall()
+    ref = shim.init_reference_model(dict(ref_cfg))
+    plugin.install()
+    try:
+        m = shim.init_reference_model(dict(ref_cfg))
+    finally:
+        plugin.uninstall()
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    from wenet.models.transformer.cmvn import GlobalCMVN
+    for mm in (ref, m):
+        mm.encoder.global_cmvn = GlobalCMVN(torch.zeros(80), torch.ones(80))
+        mm.load_state_dict(sd, strict=False)
+        mm.eval()
+    m = m.cuda()
+    lib = _lib.load()
+    feats, lens = _gpu_fbank([32000 + 123, 20800])
+
+    def launched(fn):
+        l0 = lib.wb_launch_count()
+        out = fn()
+        assert lib.wb_launch_count() > l0, "no library kernel launched"
+        return out
+
+    with torch.no_grad():
+        y, mask = launched(lambda: m.encoder(feats, lens.cuda(), -1, -1))
+        yr, maskr = ref.encoder(feats.cpu(), lens, -1, -1)
+        assert torch.equal(mask.cpu(), maskr)
+        el = maskr.squeeze(1).sum(1).tolist()
+        for b, n in enumerate(el):
+            assert (y[b, :n].cpu() - yr[b, :n]).abs().max() < 5.9e-2
+        act = launched(lambda: m.ctc_activation(y))
+        actr = ref.ctc_activation(y.cpu())
+        assert act.shape == actr.shape and (act.cpu() - actr).abs().max() < 5e-2
+        lp = launched(lambda: m.ctc_logprobs(y, 1.5, 0))
+        lpr = ref.ctc_logprobs(y.cpu(), 1.5, 0)
+        assert (lp.cpu() - lpr).abs().max() < 5e-2
+        win = (4 - 1) * 4 + 7
+        c1 = launched(lambda: m.forward_encoder_chunk(feats[0:1, :win], 0, 8))
+        r1 = ref.forward_encoder_chunk(feats[0:1, :win].cpu(), 0, 8)
+        for a, b in zip(c1, r1):
+            assert a.shape == b.shape and (a.cpu() - b).abs().max() < 5.9e-2
+        c2 = launched(lambda: m.encoder.forward_chunk(feats[0:1, 16:16 + win], 4, 8, c1[1], c1[2]))
+        r2 = ref.encoder.forward_chunk(feats[0:1, 16:16 + win].cpu(), 4, 8, r1[1], r1[2])
+        for a, b in zip(c2, r2):
+            assert a.shape == b.shape and (a.cpu() - b).abs().max() < 5.9e-2
+    # a stand-alone encoder (no owning model) packs its own encoder-only weights
+    enc_only = type(m.encoder).__new__(type(m.encoder))
+    enc_only.__dict__.update({k: v for k, v in m.encoder.__dict__.items() if not k.startswith("_b200")})
+    with torch.no_grad():
+        y2, _ = launched(lambda: enc_only(feats, lens.cuda(), -1, -1))
+    assert torch.equal(y2, y)

@@ -24,7 +24,7 @@ class WbModelConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "input_dim", "d_model", "heads", "ffn_dim", "enc_layers", "cnn_kernel", "cnn_causal",
         "cnn_norm", "vocab", "dec_layers", "rdec_layers", "dec_heads", "dec_ffn_dim", "max_pos",
-        "has_cmvn", "precise")] + [("ln_eps", C.c_float)]
+        "has_cmvn", "precise")] + [("ln_eps", C.c_float), ("dec_ln_eps", C.c_float)]
 
 
 # name -> (restype, argtypes); mirrors include/wenet_b200.h one to one

@@ -201,8 +201,8 @@ class B200ASRModel:
             self.dm = DeviceModel(self.spec, state_dict, with_decoder=with_decoder, precise=precise)
         self.precise = bool(precise)
         self.vocab_size = self.spec.vocab
-        self.sos = self.vocab_size - 1      # asr_model.py:62-64
-        self.eos = self.vocab_size - 1
+        self.sos = self.spec.sos            # asr_model.py:60-63 (tokenizer_conf.special_tokens or vocab - 1)
+        self.eos = self.spec.eos
         self.ignore_id = -1
         self.reverse_weight = self.spec.reverse_weight
         self.ctc_weight = self.spec.ctc_weight
@@ -252,9 +252,10 @@ class B200ASRModel:
         return other
 
     @classmethod
-    def from_reference(cls, model, configs: dict, device=None):
+    def from_reference(cls, model, configs: dict, device=None, precise: bool = False):
         """Wrap a loaded reference ASRModel (same weights, same results, B200 kernels)."""
-        return cls(configs, {k: v.detach().cpu() for k, v in model.state_dict().items()}, device=device)
+        return cls(configs, {k: v.detach().cpu() for k, v in model.state_dict().items()}, device=device,
+                   precise=precise)
 
     def _operand(self, x: torch.Tensor) -> torch.Tensor:
         """fp32 rows [R, d] -> the GEMM A operand the library expects for encoder output: bf16 [R, d], or in precise

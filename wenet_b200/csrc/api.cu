@@ -88,6 +88,7 @@ static int model_finalize(Model* m, cudaStream_t stream) {
     WB_REQUIRE(c.input_dim >= 7 && c.ffn_dim % 64 == 0, WB_ERR_UNSUPPORTED, "unsupported input_dim/ffn_dim");
     WB_REQUIRE(c.cnn_kernel >= 1 && c.cnn_kernel <= 31 && (c.cnn_causal || c.cnn_kernel % 2 == 1), WB_ERR_UNSUPPORTED,
                "unsupported cnn_module_kernel %d", c.cnn_kernel);
+    WB_REQUIRE(c.vocab > 0 || c.dec_layers == 0, WB_ERR_BAD_ARG, "a decoder needs a vocabulary");
     if (c.dec_layers > 0)
         WB_REQUIRE(c.dec_heads * 64 == c.d_model && c.dec_ffn_dim % 64 == 0, WB_ERR_UNSUPPORTED,
                    "unsupported decoder geometry (heads=%d)", c.dec_heads);
@@ -154,7 +155,8 @@ static int model_finalize(Model* m, cudaStream_t stream) {
                      stream));
     }
     RC(get_norm(m, "after_norm", d, &m->after));
-    RC(get_linear(m, "ctc", c.vocab, d * p3, true, &m->ctc));
+    if (c.vocab > 0) RC(get_linear(m, "ctc", c.vocab, d * p3, true, &m->ctc));
+    if (m->cfg.dec_ln_eps <= 0.f) m->cfg.dec_ln_eps = m->cfg.ln_eps;
     if (c.dec_layers > 0) RC(finalize_decoder(m, "dec.left", c.dec_layers, &m->left));
     if (c.rdec_layers > 0) RC(finalize_decoder(m, "dec.right", c.rdec_layers, &m->right));
     WB_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -260,7 +262,7 @@ int wb_ctc_logprobs(const wb_model* mm, const void* enc_out_bf16_dev, int64_t ro
                     float* logp_dev, int64_t ldl, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
                     wb_stream_t stream) {
     const Model* m = reinterpret_cast<const Model*>(mm);
-    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "ctc_logprobs: model not finalized");
+    WB_REQUIRE(m && m->finalized && m->ctc.w, WB_ERR_NOT_LOADED, "ctc_logprobs: model not finalized / no CTC head");
     WB_REQUIRE(ldl >= m->cfg.vocab, WB_ERR_BAD_ARG, "ctc_logprobs: ldl < vocab");
     cudaStream_t st = (cudaStream_t)stream;
     RC(gemm_bf16(enc_out_bf16_dev, m->ctc.K, &m->ctc.tmap, m->ctc.w, (int)rows, m->cfg.vocab, m->ctc.K,
@@ -273,7 +275,7 @@ int wb_ctc_topk(const wb_model* mm, const void* enc_out_bf16_dev, int64_t rows, 
                 float* logits_scratch_dev, int64_t ldl, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
                 wb_stream_t stream) {
     const Model* m = reinterpret_cast<const Model*>(mm);
-    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "ctc_topk: model not finalized");
+    WB_REQUIRE(m && m->finalized && m->ctc.w, WB_ERR_NOT_LOADED, "ctc_topk: model not finalized / no CTC head");
     WB_REQUIRE(ldl >= m->cfg.vocab && topk_val_dev && topk_idx_dev && logits_scratch_dev, WB_ERR_BAD_ARG,
                "ctc_topk: bad argument");
     cudaStream_t st = (cudaStream_t)stream;

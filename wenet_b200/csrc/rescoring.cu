@@ -123,7 +123,7 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
     for (size_t li = 0; li < D.layers.size(); ++li) {
         const DecLayer& L = D.layers[li];
         // masked (causal) self-attention, decoder_layer.py:101-118
-        RC(layernorm_rows(x, d, N, d, L.n1.g, L.n1.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(layernorm_rows(x, d, N, d, L.n1.g, L.n1.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.sa_qkv.tmap, L.sa_qkv.w, N, 3 * d, d, L.sa_qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
         if (shared) RC(gather_rows(qkv, Q.uniq_of_row, R, 3 * d * 2, qkv_full, st));
         {
@@ -141,7 +141,7 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
         if (shared) RC(gather_rows(ctx_full, Q.rep_row, N, d * 2, ctx, st));
         RC(gemm_bf16(ctx, d, &L.sa_out.tmap, L.sa_out.w, N, d, d, L.sa_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // cross-attention over the utterance's encoder frames, decoder_layer.py:120-139
-        RC(layernorm_rows(x, d, N, d, L.n2.g, L.n2.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(layernorm_rows(x, d, N, d, L.n2.g, L.n2.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.ca_q.tmap, L.ca_q.w, N, d, d, L.ca_q.b, EPI_BF16, 1.0f, q, d, 0, st));
         RC(gemm_bf16(enc_bf16, m->cfg.precise ? 3 * d : d /*precise: rows are [hi|lo|hi]; the decoder reads hi*/, &L.ca_kv.tmap, L.ca_kv.w, (int)enc_rows, 2 * d, d, L.ca_kv.b, EPI_BF16, 1.0f, memkv,
                      2 * d, 0, st));
@@ -159,11 +159,11 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
         }
         RC(gemm_bf16(ctx, d, &L.ca_out.tmap, L.ca_out.w, N, d, d, L.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // feed-forward (ReLU), decoder_layer.py:141-147
-        RC(layernorm_rows(x, d, N, d, L.n3.g, L.n3.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(layernorm_rows(x, d, N, d, L.n3.g, L.n3.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, N, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
         RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, N, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
     }
-    RC(layernorm_rows(x, d, N, d, D.after.g, D.after.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+    RC(layernorm_rows(x, d, N, d, D.after.g, D.after.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
     if (logits != nullptr) {
         WB_REQUIRE(!shared, WB_ERR_BAD_ARG, "decoder logits are only produced without prefix sharing");
         RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, N, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, ldl, 0, st));

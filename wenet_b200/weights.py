@@ -105,11 +105,15 @@ class ModelSpec:
         self.rdec_layers = int(dec.get("r_num_blocks", 0)) if self.bidirectional else 0
         self.dec_heads = int(dec.get("attention_heads", 4))
         self.dec_ffn_dim = int(dec.get("linear_units", 2048))
+        self.dec_ln_eps = float(dec.get("norm_eps", 1e-5))      # decoder.py:83, independent of the encoder's
         if dec.get("activation_type", "relu") != "relu" or dec.get("input_layer", "embed") != "embed" \
                 or not dec.get("normalize_before", True) or dec.get("tie_word_embedding", False):
             raise NotImplementedError("decoder_conf outside the implemented set (relu / embed / pre-norm / untied)")
         if self.d_model != self.dec_heads * 64:
             raise NotImplementedError("decoder head size must be 64")
+        st = (configs.get("tokenizer_conf") or {}).get("special_tokens") or {}
+        self.sos = int(st.get("<sos>", self.vocab - 1))         # asr_model.py:60-63
+        self.eos = int(st.get("<eos>", self.vocab - 1))
         mc = dict(configs.get("model_conf", {}))
         self.reverse_weight = float(mc.get("reverse_weight", 0.0))
         self.ctc_weight = float(mc.get("ctc_weight", 0.5))
@@ -201,7 +205,8 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor], precise: bool 
         out[t + ".conv.pw2.w"] = ebf(sd[c + ".pointwise_conv2.weight"].reshape(d, d))
         out[t + ".conv.pw2.b"] = f32(sd[c + ".pointwise_conv2.bias"])
     norm("after_norm", "encoder.after_norm")
-    lin("ctc", "ctc.ctc_lo", enc=True)
+    if spec.vocab > 0:      # encoder-only handles (plugin: a stand-alone ConformerEncoder) carry no CTC head
+        lin("ctc", "ctc.ctc_lo", enc=True)
 
     def decoder(dst, src, n_layers):
         out[dst + ".emb"] = f32(sd[src + ".embed.0.weight"])
@@ -250,7 +255,7 @@ class DeviceModel:
             cnn_norm=0 if spec.cnn_norm == "layer_norm" else 1, vocab=spec.vocab,
             dec_layers=spec.dec_layers if has_dec else 0, rdec_layers=spec.rdec_layers if has_dec else 0,
             dec_heads=spec.dec_heads, dec_ffn_dim=spec.dec_ffn_dim, max_pos=spec.max_pos,
-            has_cmvn=int(spec.has_cmvn), precise=int(self.precise), ln_eps=spec.ln_eps)
+            has_cmvn=int(spec.has_cmvn), precise=int(self.precise), ln_eps=spec.ln_eps, dec_ln_eps=spec.dec_ln_eps)
         self._h = C.c_void_p()
         check(lib.wb_model_create(C.byref(self._h), C.byref(cfg)), "wb_model_create")
         packed = pack_state_dict(spec, sd, precise=self.precise)
