@@ -60,6 +60,16 @@ def host_cores():
     return max(1, n)
 
 
+def _edit_distance(a, b):
+    prev = list(range(len(b) + 1))
+    for i, x in enumerate(a, 1):
+        cur = [i]
+        for j, y in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (x != y)))
+        prev = cur
+    return prev[-1]
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -665,14 +675,18 @@ def main():
             dmax = max(float((enc_v[b, :ref_enc[b].shape[0]].cpu() - ref_enc[b]).abs().max()) for b in range(n_v))
             dmean = float(np.mean([float((enc_v[b, :ref_enc[b].shape[0]].cpu() - ref_enc[b]).abs().mean()) for b in range(n_v)]))
             same = [list(out_v[b].tokens) == list(ref_tok[b]) for b in range(n_v)]
-            ver[tag] = {"tokens_identical": int(sum(same)), "encoder_out_max_abs": dmax, "encoder_out_mean_abs": dmean}
+            agree = [1.0 - _edit_distance(list(out_v[b].tokens), list(ref_tok[b])) / max(len(ref_tok[b]), 1) for b in range(n_v)]
+            ver[tag] = {"tokens_identical": int(sum(same)), "token_agreement": float(np.mean(agree)),
+                        "encoder_out_max_abs": dmax, "encoder_out_mean_abs": dmean}
         line["parity"] = {"mode": "precise", "max": ver["precise"]["encoder_out_max_abs"],
                           "mean": ver["precise"]["encoder_out_mean_abs"],
                           "bf16_mode": {"max": ver["bf16"]["encoder_out_max_abs"], "mean": ver["bf16"]["encoder_out_mean_abs"]},
                           "what": "encoder_out of %d x %.0f s utterances vs the fp32 CPU oracle" % (n_v, wl["seconds"])}
         line["verify"] = ver
+        # precise mode: identical token ids and encoder_out within 1e-3; bf16 mode (the one timed above): encoder_out inside
+        # the reference's own bf16-autocast budget and >= 90 % token agreement (near-tie frames may flip)
         line["verified"] = bool(ver["precise"]["tokens_identical"] == n_v and ver["precise"]["encoder_out_max_abs"] <= 1e-3
-                                and ver["bf16"]["encoder_out_max_abs"] < 5.9e-2)
+                                and ver["bf16"]["encoder_out_max_abs"] < 5.9e-2 and ver["bf16"]["token_agreement"] >= 0.9)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         arm = CpuArm(args.workload)
