@@ -12,8 +12,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "lib", "libwenet_b200.so")
+# WB_BUILD_VARIANT=<name> builds a side-by-side variant (e.g. NVCC_EXTRA=-DWB_GEMM_DIAG WB_BUILD_VARIANT=diag) into
+# lib/libwenet_b200_<name>.so; WENET_B200_LIB selects it at load time (tools only - the product loads the default)
+_VAR = os.environ.get("WB_BUILD_VARIANT", "")
+OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + _VAR if _VAR else ""))
+LIB = os.path.join(HERE, "lib", "libwenet_b200%s.so" % ("_" + _VAR if _VAR else ""))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

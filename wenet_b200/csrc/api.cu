@@ -22,7 +22,7 @@ int model_get(const Model* m, const std::string& name, int dtype, int64_t numel,
     return WB_OK;
 }
 
-static int get_linear(Model* m, const std::string& base, int N, int K, bool bias, Linear* L) {
+static int get_linear(Model* m, const std::string& base, int N, int K, bool bias, Linear* L, int epi = EPI_BF16) {
     const void* p;
     int rc = model_get(m, base + ".w", WB_BF16, (int64_t)N * K, &p);
     if (rc != WB_OK) return rc;
@@ -35,7 +35,7 @@ static int get_linear(Model* m, const std::string& base, int N, int K, bool bias
         if (rc != WB_OK) return rc;
         L->b = (const float*)p;
     }
-    return make_weight_tmap(&L->tmap, L->w, N, K);
+    return make_weight_tmap(&L->tmap, L->w, N, K, epi);
 }
 
 static int get_norm(Model* m, const std::string& base, int d, Norm* n) {
@@ -133,7 +133,7 @@ static int model_finalize(Model* m, cudaStream_t stream) {
         RC(get_linear(m, b + ".ff.w2", d, ff * p3, true, &L.ff2));
         RC(get_linear(m, b + ".att.qkv", 3 * d, d * p3, true, &L.qkv));
         RC(get_linear(m, b + ".att.out", d, d * p3, true, &L.out));
-        RC(get_linear(m, b + ".conv.pw1", 2 * d, d * p3, true, &L.pw1));
+        RC(get_linear(m, b + ".conv.pw1", 2 * d, d * p3, true, &L.pw1, EPI_GLU_BF16));
         RC(get_linear(m, b + ".conv.pw2", d, d * p3, true, &L.pw2));
         RC(model_get(m, b + ".att.pos_u", WB_F32, d, &p));
         L.pos_u = (const float*)p;

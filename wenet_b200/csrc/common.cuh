@@ -143,18 +143,67 @@ __device__ __forceinline__ void sigmoid4(const float x0, const float x1, const f
     s2 = r23 * y3;
     s3 = r23 * y2;
 }
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 retire two fp32 operations per issue slot) ----------------
+// The activation epilogues are bound by instruction issue and by the 16-lane MUFU pipe, not by the FMA pipe: every pair
+// of multiplies / adds that shares one issue slot shortens them.
+__device__ __forceinline__ float2 f2_mul(const float2 a, const float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_add(const float2 a, const float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_fma(const float2 a, const float2 b, const float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+// Four sigmoids, packed: same algebra as sigmoid4 (one reciprocal of y0 y1 y2 y3, y_i = 1 + min(2^(-x_i log2 e), 2^30)),
+// arranged so that every product except two is a two-wide instruction:
+//   (pa, pb) = (y0 y2, y1 y3);  r = 1 / (pa pb);  (qa, qb) = (r pb, r pa);
+//   (1/y0, 1/y1) = (qa y2, qb y3);  (1/y2, 1/y3) = (qa y0, qb y1).
+// 5 MUFU + 4 FMNMX + 9 FMA-pipe issue slots per four values (scalar form: 5 + 4 + 17).
+__device__ __forceinline__ void sigmoid4_f2(const float2 xa, const float2 xb, float2& sa, float2& sb) {
+    constexpr float kNegLog2e = -1.4426950408889634f;
+    constexpr float kCap = 1073741824.0f;   // 2^30
+    const float2 ta = f2_mul(xa, make_float2(kNegLog2e, kNegLog2e));
+    const float2 tb = f2_mul(xb, make_float2(kNegLog2e, kNegLog2e));
+    const float2 ea = make_float2(fminf(fast_exp2(ta.x), kCap), fminf(fast_exp2(ta.y), kCap));
+    const float2 eb = make_float2(fminf(fast_exp2(tb.x), kCap), fminf(fast_exp2(tb.y), kCap));
+    const float2 ya = f2_add(ea, make_float2(1.0f, 1.0f));
+    const float2 yb = f2_add(eb, make_float2(1.0f, 1.0f));
+    const float2 p = f2_mul(ya, yb);
+    const float r = fast_rcp(p.x * p.y);
+    const float2 q = make_float2(r * p.y, r * p.x);
+    sa = f2_mul(q, yb);
+    sb = f2_mul(q, ya);
+}
 // in-place SiLU over a register array whose length is a multiple of 4
 template <int N>
 __device__ __forceinline__ void silu_inplace(float (&v)[N]) {
     static_assert(N % 4 == 0, "silu_inplace: N % 4");
 #pragma unroll
     for (int i = 0; i < N; i += 4) {
-        float s0, s1, s2, s3;
-        sigmoid4(v[i], v[i + 1], v[i + 2], v[i + 3], s0, s1, s2, s3);
-        v[i] *= s0;
-        v[i + 1] *= s1;
-        v[i + 2] *= s2;
-        v[i + 3] *= s3;
+        const float2 xa = make_float2(v[i], v[i + 1]), xb = make_float2(v[i + 2], v[i + 3]);
+        float2 sa, sb;
+        sigmoid4_f2(xa, xb, sa, sb);
+        const float2 oa = f2_mul(xa, sa), ob = f2_mul(xb, sb);
+        v[i] = oa.x;
+        v[i + 1] = oa.y;
+        v[i + 2] = ob.x;
+        v[i + 3] = ob.y;
     }
 }
 // One-MUFU variants: sigmoid(x) = 0.5 + 0.5 tanh(x/2) with tanh.approx.f32 (max rel. error 2^-11, i.e. <= 2.5e-4

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace wb {
@@ -207,6 +208,236 @@ fbank_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, const 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Register-resident variant for the front-end every recipe uses (25 ms / 10 ms at 16 kHz: frame 400, hop 160, 512-point
+// real FFT = 256-point complex FFT of z[n] = y[2n] + i y[2n+1]).  One warp per frame, 8 complex points per lane, the FFT
+// as three in-register stages (radix 8, 8, 4) with two conflict-free transposes through shared memory:
+//   n = 32 a + b, k = c + 8 d, d = g + 8 h, b = 4 e + f:
+//   X[c + 8 (g + 8 h)] = sum_f W4^(f h) W32^(f g) sum_e W8^(e g) [ W256^(b c) sum_a W8^(a c) z[32 a + b] ]
+//   stage A  lane b,         registers a -> c   (twiddle W256^(b c), per-lane constants)
+//   stage B  lane (c, f),    registers e -> g   (twiddle W32^(f g))
+//   stage C  lane (c, g>>1), registers (g&1, f) -> (g&1, h)
+// Window, twiddles and the frame's samples live in registers; the round-1 kernel ran four radix-4 passes over a
+// shared-memory buffer (2190 warp instructions and ~700 bank conflicts per frame, ncu profiles/r2_ncu_fbank.txt).
+// Shared-memory index maps (float2 units) are chosen so that every 64-bit access of a warp touches each bank pair
+// exactly twice (the minimum):  T1[36 c + b],  T2[c + 36 g + 8 f],  Z[24 (k >> 4) + (k & 15)].
+constexpr int F5_FR = 16;          // frames per CTA (4 per warp)
+constexpr int F5_THREADS = 128;
+constexpr int F5_T1 = 384;         // float2 slots of the T1 / Z buffer (Z rows are padded to 24)
+constexpr int F5_WARP_FLOATS = 2 * F5_T1 + 2 * 288;   // T1 / Z + T2 / power spectrum (288 float2)
+
+__device__ __forceinline__ float2 cmul(const float2 a, const float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(const float2 a, const float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(const float2 a, const float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul_mi(const float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// in-place 4-point DFT, natural order in and out: y[m] = sum_j x[j] W4^(j m)
+__device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = cmul_mi(csub(x1, x3));
+    x0 = cadd(t0, t2);
+    x1 = cadd(t1, t3);
+    x2 = csub(t0, t2);
+    x3 = csub(t1, t3);
+}
+// in-place 8-point DFT, natural order in and out: y[c] = sum_a x[a] W8^(a c)
+__device__ __forceinline__ void dft8(float2 (&x)[8]) {
+    constexpr float kR = 0.70710678118654752440f;
+    float2 s0 = cadd(x[0], x[4]), s1 = cadd(x[1], x[5]), s2 = cadd(x[2], x[6]), s3 = cadd(x[3], x[7]);
+    float2 d0 = csub(x[0], x[4]), d1 = csub(x[1], x[5]), d2 = csub(x[2], x[6]), d3 = csub(x[3], x[7]);
+    // d_a * W8^a:  W8 = (1 - i) / sqrt 2,  W8^2 = -i,  W8^3 = (-1 - i) / sqrt 2
+    d1 = make_float2(kR * (d1.x + d1.y), kR * (d1.y - d1.x));
+    d2 = cmul_mi(d2);
+    d3 = make_float2(kR * (d3.y - d3.x), -kR * (d3.x + d3.y));
+    dft4(s0, s1, s2, s3);   // even outputs
+    dft4(d0, d1, d2, d3);   // odd outputs
+    x[0] = s0; x[2] = s1; x[4] = s2; x[6] = s3;
+    x[1] = d0; x[3] = d1; x[5] = d2; x[7] = d3;
+}
+
+template <typename T>
+struct PcmPair;   // the sample pair (2 n, 2 n + 1) of a frame as floats
+template <>
+struct PcmPair<int16_t> {
+    static __device__ __forceinline__ float2 load(const int16_t* x, int n) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(x + 2 * n);
+        return make_float2((float)(int16_t)(w & 0xffffu), (float)(int16_t)(w >> 16));
+    }
+};
+template <>
+struct PcmPair<float> {
+    static __device__ __forceinline__ float2 load(const float* x, int n) {
+        return *reinterpret_cast<const float2*>(x + 2 * n);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(F5_THREADS)
+fbank512_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, const int* __restrict__ num_samples,
+                float scale, float* __restrict__ out, long long out_frames_stride, int max_frames) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int b_utt = blockIdx.y;
+    const int f0 = blockIdx.x * F5_FR;
+    const int ns = num_samples[b_utt];
+    const int flen = P.frame_len, shift = P.frame_shift;
+    const int n_frames = (ns >= flen) ? 1 + (ns - flen) / shift : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* out_b = out + (long long)b_utt * out_frames_stride * P.num_mel;
+    if (f0 >= n_frames) {   // frames past the utterance: zeros (processor.padding)
+        for (int i = threadIdx.x; i < F5_FR * P.num_mel; i += F5_THREADS) {
+            const int f = f0 + i / P.num_mel;
+            if (f < max_frames) out_b[(long long)f * P.num_mel + (i % P.num_mel)] = 0.f;
+        }
+        return;
+    }
+    const int span = (F5_FR - 1) * shift + flen;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    T* s_pcm = reinterpret_cast<T*>(smem_raw + 16);
+    const int pcm_bytes = (span * (int)sizeof(T) + 15) & ~15;
+    float2* s_t1 = reinterpret_cast<float2*>(smem_raw + 16 + pcm_bytes) + warp * (F5_WARP_FLOATS / 2);
+    float2* s_t2 = s_t1 + F5_T1;
+    float* s_pow = reinterpret_cast<float*>(s_t2);   // the power spectrum reuses T2 once stage C has read it
+
+    const int nf_here = min(F5_FR, n_frames - f0);
+    const int need = (nf_here - 1) * shift + flen;
+    const T* src = pcm + (long long)b_utt * pcm_stride + (long long)f0 * shift;
+    const uint32_t bytes = (uint32_t)need * (uint32_t)sizeof(T);
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0);
+    if (bulk_ok) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, bytes);
+            bulk_load_1d(s_pcm, src, bytes, bar);
+        }
+    }
+    // per-lane constants, computed while the samples are in flight
+    const int cB = lane >> 2, fB = lane & 3;      // stage B / C lane coordinates: c, and f (B) or g >> 1 (C)
+    float2 win[8];      // window[64 a + 2 b], window[64 a + 2 b + 1]
+    float2 twA[8];      // W256^(b c)
+    float2 twB[8];      // W32^(f g)
+    const float2* twh = reinterpret_cast<const float2*>(P.twiddle);   // W256^k, k < 256
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int j = 64 * a + 2 * lane;
+        win[a] = make_float2(j < flen ? __ldg(P.window + j) : 0.f, j + 1 < flen ? __ldg(P.window + j + 1) : 0.f);
+        twA[a] = __ldg(twh + ((lane * a) & 255));
+        twB[a] = __ldg(twh + ((8 * fB * a) & 255));
+    }
+    if (bulk_ok) {
+        mbar_wait(bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < need; i += F5_THREADS) s_pcm[i] = src[i];
+        __syncthreads();
+    }
+
+    const float inv_len = 1.0f / (float)flen;
+    const int nw = (flen + 1) >> 1;     // sample pairs per frame (200)
+    for (int fi = warp; fi < F5_FR; fi += F5_THREADS / 32) {
+        const int f = f0 + fi;
+        if (f >= max_frames) break;
+        float* orow = out_b + (long long)f * P.num_mel;
+        if (fi >= nf_here) {
+            for (int m = lane; m < P.num_mel; m += 32) orow[m] = 0.f;
+            continue;
+        }
+        const T* x = s_pcm + fi * shift;
+        // 1. samples -> registers; mean (remove_dc_offset, kaldi.py:184-186)
+        float2 v[8];
+        float prev[8];   // sample 2 n - 1 (replicate pad at n = 0, kaldi.py:194-198)
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int n = 32 * a + lane;
+            v[a] = make_float2(0.f, 0.f);
+            prev[a] = 0.f;
+            if (n < nw) {
+                float2 cur = PcmPair<T>::load(x, n);
+                if (2 * n + 1 >= flen) cur.y = 0.f;     // odd frame length: the last pair is half empty
+                const float pv = (n > 0) ? PcmPair<T>::load(x, n - 1).y : cur.x;
+                v[a] = make_float2(cur.x * scale, cur.y * scale);
+                prev[a] = pv * scale;
+                acc += v[a].x + ((2 * n + 1 < flen) ? v[a].y : 0.f);
+            }
+        }
+        const float mean = warp_sum(acc) * inv_len;
+        // 2. DC removal, pre-emphasis, window  ->  z[n] = y[2 n] + i y[2 n + 1]
+        float2 z[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const float x0 = v[a].x - mean, x1 = v[a].y - mean, xm = prev[a] - mean;
+            z[a] = make_float2((x0 - P.preemph * xm) * win[a].x, (x1 - P.preemph * x0) * win[a].y);   // win = 0 past the frame
+        }
+        // 3. stage A: 8-point DFT over a, twiddle W256^(b c), transpose
+        dft8(z);
+        s_t1[lane] = z[0];
+#pragma unroll
+        for (int c = 1; c < 8; ++c) s_t1[36 * c + lane] = cmul(z[c], twA[c]);
+        __syncwarp();
+        // stage B: lane (c, f): 8-point DFT over e, twiddle W32^(f g), transpose
+#pragma unroll
+        for (int e = 0; e < 8; ++e) z[e] = s_t1[36 * cB + 4 * e + fB];
+        dft8(z);
+        s_t2[cB + 8 * fB] = z[0];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) s_t2[cB + 36 * g + 8 * fB] = cmul(z[g], twB[g]);
+        __syncwarp();
+        // stage C: lane (c, gh): two 4-point DFTs over f;  k = c + 8 g + 64 h
+#pragma unroll
+        for (int gl = 0; gl < 2; ++gl) {
+            const int g = 2 * fB + gl;
+            float2 y0 = s_t2[cB + 36 * g], y1 = s_t2[cB + 36 * g + 8], y2 = s_t2[cB + 36 * g + 16], y3 = s_t2[cB + 36 * g + 24];
+            dft4(y0, y1, y2, y3);
+            z[4 * gl + 0] = y0;
+            z[4 * gl + 1] = y1;
+            z[4 * gl + 2] = y2;
+            z[4 * gl + 3] = y3;
+        }
+        __syncwarp();   // all T1 / T2 reads done: T1 becomes Z, T2 becomes the power spectrum
+#pragma unroll
+        for (int gl = 0; gl < 2; ++gl)
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int k = cB + 8 * (2 * fB + gl) + 64 * h;
+                s_t1[24 * (k >> 4) + (k & 15)] = z[4 * gl + h];
+            }
+        __syncwarp();
+        // 4. real-FFT split + power:  X[k] = (Z[k] + conj(Z[256 - k])) / 2 - i W512^k (Z[k] - conj(Z[256 - k])) / 2
+        const float2* twr = reinterpret_cast<const float2*>(P.twiddle_r);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const int k = lane + 32 * j;
+            if (k <= 256) {
+                const int ka = k & 255, kb = (256 - k) & 255;
+                const float2 za = s_t1[24 * (ka >> 4) + (ka & 15)];
+                const float2 zb = s_t1[24 * (kb >> 4) + (kb & 15)];
+                const float er = 0.5f * (za.x + zb.x), ei = 0.5f * (za.y - zb.y);
+                const float orr = 0.5f * (za.x - zb.x), oi = 0.5f * (za.y + zb.y);
+                const float2 w = __ldg(twr + k);
+                // -i (or + i oi) = oi - i or
+                const float xr = er + (oi * w.x + orr * w.y);
+                const float xi = ei + (oi * w.y - orr * w.x);
+                s_pow[k] = xr * xr + xi * xi;
+            }
+        }
+        __syncwarp();
+        // 5. mel + log (kaldi.py:620-633)
+        for (int m = lane; m < P.num_mel; m += 32) {
+            const int st = __ldg(P.mel_start + m), ln = __ldg(P.mel_len + m);
+            const float* w = P.mel_w + __ldg(P.mel_off + m);
+            float e = 0.f;
+            for (int i = 0; i < ln; ++i) e = fmaf(s_pow[st + i], __ldg(w + i), e);
+            orow[m] = logf(fmaxf(e, 1.1920928955078125e-07f));
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 int fbank_plan_create(FbankPlan** out, int sample_rate, int num_mel, int frame_len, int frame_shift,
@@ -302,14 +533,36 @@ int fbank_forward(const FbankPlan* plan, const void* pcm, int is_int16, long lon
     P.frame_shift = plan->frame_shift;
     P.nfft = plan->nfft;
     P.preemph = plan->preemph;
+    const int esz = is_int16 ? 2 : 4;
+    ProfScope _ps(PT_FBANK, stream,
+                  (double)batch * ((double)max_frames * plan->frame_shift * esz + (double)max_frames * plan->num_mel * 4.0));
+    // the recipes' front-end (512-point FFT, even hop so that sample pairs stay aligned): register-resident kernel
+    static const bool no_fast = getenv("WB_FBANK_GENERIC") != nullptr;
+    if (plan->nfft == 512 && plan->frame_shift % 2 == 0 && plan->frame_len > 256 && !no_fast) {
+        const int span = (F5_FR - 1) * plan->frame_shift + plan->frame_len;
+        const int pcm_bytes = (span * esz + 15) & ~15;
+        const size_t smem = 16 + pcm_bytes + (size_t)(F5_THREADS / 32) * F5_WARP_FLOATS * sizeof(float);
+        dim3 grid(ceil_div(max_frames, F5_FR), batch);
+        if (is_int16) {
+            if (smem > 48 * 1024)
+                WB_CHECK_CUDA(cudaFuncSetAttribute(fbank512_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fbank512_kernel<int16_t><<<grid, F5_THREADS, smem, stream>>>(P, (const int16_t*)pcm, pcm_stride, num_samples_dev,
+                                                                         scale, out, out_frames_stride, max_frames);
+        } else {
+            if (smem > 48 * 1024)
+                WB_CHECK_CUDA(cudaFuncSetAttribute(fbank512_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fbank512_kernel<float><<<grid, F5_THREADS, smem, stream>>>(P, (const float*)pcm, pcm_stride, num_samples_dev, scale,
+                                                                       out, out_frames_stride, max_frames);
+        }
+        count_launch();
+        WB_CHECK_LAUNCH();
+        return WB_OK;
+    }
     const int half = plan->nfft / 2;
     const int span = (FR - 1) * plan->frame_shift + plan->frame_len;
-    const int esz = is_int16 ? 2 : 4;
     const int pcm_bytes = (span * esz + 15) & ~15;
     const size_t smem = 16 + pcm_bytes + (size_t)(FB_THREADS / 32) * (2 * half + half + 8) * sizeof(float);
     dim3 grid(ceil_div(max_frames, FR), batch);
-    ProfScope _ps(PT_FBANK, stream,
-                  (double)batch * ((double)max_frames * plan->frame_shift * esz + (double)max_frames * plan->num_mel * 4.0));
     if (is_int16) {
         if (smem > 48 * 1024)
             WB_CHECK_CUDA(cudaFuncSetAttribute(fbank_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -27,6 +27,7 @@
 // file is compiled in only with -DWB_GEMM_DIAG.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 #include <string.h>
 
 namespace wb {
@@ -53,8 +54,14 @@ struct GemmCfg {
     // stays in shared memory while the CTA streams A tiles past it -> per tile only the 128 x K A tile is
     // fetched from L2 (the per-SM L2 path, ~80 GB/s, is what bounds the K = 256 GEMMs otherwise)
     static constexpr int kResMaxKB = (BN == 256) ? 4 : 8;
-    static constexpr int kResBBytes = kResMaxKB * kBBytes;
-    static constexpr int kResAStages = (kStages * kStageBytes - kResBBytes) / kABytes;
+    // the A ring takes whatever the resident panel of num_kb k-blocks leaves of the stage area (at most 8 slots: K = 256
+    // gives 4 slots = ONE A tile with BN = 256 but 8 slots = TWO A tiles with BN = 128 - the depth that hides the
+    // L2 -> SM latency of the next tile's A loads behind the current tile's MMAs)
+    static constexpr int kMaxRing = 8;
+    static constexpr int res_ring(int num_kb) {
+        const int r = (kStages * kStageBytes - num_kb * kBBytes) / kABytes;
+        return r > kMaxRing ? kMaxRing : r;
+    }
 };
 
 struct GemmParams {
@@ -66,6 +73,7 @@ struct GemmParams {
     long long ldc;
     int split3;
     int use_tma_out;  // epilogue through shared memory + TMA store / reduce-add (all non-split3 cases)
+    int res_ring;     // weight-stationary mode: A ring depth (GemmCfg::res_ring(num_kb))
     int num_m_tiles, num_n_tiles;
     // conv mode (Conv2d 3x3 stride 2 as an implicit GEMM): the A tile of k-block (kh, kw, c-block) is one 3-D TMA box
     // {64 channels, 19 frequency taps (element stride 2), 6 time taps (element stride 2)} of the channels-last conv1
@@ -112,8 +120,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-B alignment
-    constexpr int kRing = BRES ? Cfg::kResAStages : Cfg::kStages;   // A (or A+B) ring depth
-    uint8_t* smem_a = BRES ? smem + Cfg::kResBBytes : smem;
+    const int num_kb = (p.K + BK - 1) / BK;
+    const int kRing = BRES ? p.res_ring : Cfg::kStages;   // A (or A+B) ring depth
+    uint8_t* smem_a = BRES ? smem + num_kb * Cfg::kBBytes : smem;
     uint8_t* smem_b = BRES ? smem : smem + Cfg::kStages * Cfg::kABytes;
     uint8_t* smem_out = smem + Cfg::kStages * Cfg::kStageBytes;   // 1024-aligned (stage sizes are multiples of 1024)
     float* smem_bias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes);
@@ -125,12 +134,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint64_t* b_full = bars + 20;             // resident weight panel landed
     uint64_t* b_empty = bars + 21;            // all MMAs reading the resident panel retired
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 22);
-    static_assert(kRing <= 8, "barrier layout");
+    static_assert(Cfg::kStages <= 8 && Cfg::kMaxRing <= 8, "barrier layout");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int num_kb = (p.K + BK - 1) / BK;
     const int epi = (EPI >= 0) ? EPI : p.epi;
     WB_DIAG(long long diag[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long cta_t0 = clock64();)
 
@@ -329,10 +337,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(sb + i);
-                        v[i] = __uint_as_float(r[i]) + b4.x;
-                        v[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
-                        v[i + 2] = __uint_as_float(r[i + 2]) + b4.z;
-                        v[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
+                        const float2 lo = f2_add(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                                 make_float2(b4.x, b4.y));
+                        const float2 hi = f2_add(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
+                                                 make_float2(b4.z, b4.w));
+                        v[i] = lo.x;
+                        v[i + 1] = lo.y;
+                        v[i + 2] = hi.x;
+                        v[i + 3] = hi.y;
                     }
                 } else {
 #pragma unroll
@@ -385,11 +397,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         float g[16];
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
-                            sigmoid4(v[16 + i], v[17 + i], v[18 + i], v[19 + i], g[i], g[i + 1], g[i + 2], g[i + 3]);
-                            g[i] *= v[i];
-                            g[i + 1] *= v[i + 1];
-                            g[i + 2] *= v[i + 2];
-                            g[i + 3] *= v[i + 3];
+                            float2 sa, sb2;
+                            sigmoid4_f2(make_float2(v[16 + i], v[17 + i]), make_float2(v[18 + i], v[19 + i]), sa, sb2);
+                            const float2 ga = f2_mul(sa, make_float2(v[i], v[i + 1]));
+                            const float2 gb = f2_mul(sb2, make_float2(v[i + 2], v[i + 3]));
+                            g[i] = ga.x;
+                            g[i + 1] = ga.y;
+                            g[i + 2] = gb.x;
+                            g[i + 3] = gb.y;
                         }
                         WB_DIAG(diag[9] += clock64() - t_math0;)
                         staging_ready();
@@ -614,10 +629,24 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 
 void gemm_set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 
-int gemm_bn_for(int N) { return (N % 256 == 0 || N >= 1024) ? 256 : 128; }
+// Tile width: 256 columns wherever N allows.  (A 128-column tile for K <= 256 would leave room for an 8-slot A ring -
+// two A tiles in flight - but tcgen05.mma 128x128x16 takes as long as 128x256x16 with cta_group::1 (~170 SM cycles under
+// the power cap, profiles/r2_ops_v18_diag.txt): FFN1 92 vs 86 us, QKV 39 vs 31 us.  WB_GEMM_BN128=1 re-enables the
+// experiment.)
+static int g_bn128_small_k = -1;
+int gemm_bn_for(int N, int K, int epi) {
+    // the GLU epilogue packs four 32-column chunks (= 64 output columns, one 128-byte TMA box row) per warp: 256-wide tiles
+    if (epi == EPI_GLU_BF16) return 256;
+    if (g_bn128_small_k < 0) {
+        const char* e = getenv("WB_GEMM_BN128");
+        g_bn128_small_k = (e != nullptr && atoi(e) != 0) ? 1 : 0;   // measured slower (r2_ops_v18_diag.txt): off by default
+    }
+    if (g_bn128_small_k && K <= 256) return 128;
+    return (N % 256 == 0 || N >= 1024) ? 256 : 128;
+}
 
-int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K) {
-    return make_tmap_2d_bf16(out, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)gemm_bn_for(N), BK);
+int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K, int epi) {
+    return make_tmap_2d_bf16(out, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)gemm_bn_for(N, K, epi), BK);
 }
 
 static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
@@ -634,7 +663,7 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
     if (epi == EPI_RESID_F32 || epi == EPI_F32) {
         WB_REQUIRE(!split3, WB_ERR_BAD_ARG, "gemm: split3 only for bf16 outputs");
     }
-    const int bn = gemm_bn_for(N);
+    const int bn = gemm_bn_for(N, K, epi);
     CUtensorMap ta, tb_local;
     int rc = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
     if (rc != WB_OK) return rc;
@@ -672,6 +701,7 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
     p.tile_tab = nullptr;
     p.lse_part = lse_part;
     const int num_kb = ceil_div(K, BK);
+    p.res_ring = (bn == 256) ? GemmCfg<256>::res_ring(num_kb) : GemmCfg<128>::res_ring(num_kb);
     if (bn == 256) {
         const bool res = num_kb <= GemmCfg<256>::kResMaxKB;
         switch (epi) {
@@ -691,7 +721,23 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
                 WB_REQUIRE(false, WB_ERR_BAD_ARG, "gemm: unknown epilogue %d", epi);
         }
     }
-    if (num_kb <= GemmCfg<128>::kResMaxKB) return launch_gemm<128, true, -1>(ta, *tb, tc, tc, p, stream);
+    if (num_kb <= GemmCfg<128>::kResMaxKB) {
+        switch (epi) {
+#define WB_GEMM_CASE(E) \
+    case E:             \
+        return launch_gemm<128, true, E>(ta, *tb, tc, tc, p, stream);
+            WB_GEMM_CASE(EPI_BF16)
+            WB_GEMM_CASE(EPI_BF16_SILU)
+            WB_GEMM_CASE(EPI_BF16_RELU)
+            WB_GEMM_CASE(EPI_RESID_F32)
+            WB_GEMM_CASE(EPI_GLU_BF16)
+            WB_GEMM_CASE(EPI_F32)
+            WB_GEMM_CASE(EPI_LSE)
+#undef WB_GEMM_CASE
+            default:
+                WB_REQUIRE(false, WB_ERR_BAD_ARG, "gemm: unknown epilogue %d", epi);
+        }
+    }
     return launch_gemm<128, false, -1>(ta, *tb, tc, tc, p, stream);
 }
 
@@ -702,7 +748,7 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
     return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, epi, alpha, out, ldc, split3, nullptr, stream);
 }
 
-int lse_parts(int N) { return 2 * ceil_div(N, gemm_bn_for(N)); }
+int lse_parts(int N, int K) { return 2 * ceil_div(N, gemm_bn_for(N, K, EPI_LSE)); }
 
 int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream) {
@@ -738,6 +784,7 @@ int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, con
     p.ldc = d;
     p.split3 = 0;
     p.use_tma_out = 1;
+    p.res_ring = 0;
     p.num_m_tiles = num_tiles;
     p.num_n_tiles = d / 256;
     p.lse_part = nullptr;

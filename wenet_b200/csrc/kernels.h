@@ -18,10 +18,11 @@ enum GemmEpi : int {
     EPI_LSE = 6,        // no matrix output: per (row, 128-column half tile) partial log-sum-exp (max2, sum) of acc + bias
 };
 
-int gemm_bn_for(int N);
+int gemm_bn_for(int N, int K, int epi = EPI_BF16);
 void gemm_set_sm_reserve(int n);
-// tensor map for a [N, K] bf16 weight (B operand), box rows = gemm_bn_for(N)
-int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K);
+// tensor map for a [N, K] bf16 weight (B operand), box rows = gemm_bn_for(N, K)
+// (epi: the epilogue the weight will be used with - only EPI_GLU_BF16 changes the tile width)
+int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K, int epi = EPI_BF16);
 // C = epi(A[M,K](lda) * B[N,K]^T + bias). tmap_b_opt may be null (then built from B).
 // split3: bf16 outputs are written as [hi | lo | hi] column blocks of width N (N/2 for GLU) so the
 // next GEMM can run in "bf16x3" mode against weights packed as [hi | hi | lo].
@@ -31,7 +32,7 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
 
 // log-softmax denominators without the logits: part[row][2 * n_tiles] = (max of v log2 e, sum 2^(v log2 e - max)) over each
 // 128-column half of each n-tile of v = A B^T + bias.  lse_parts() = entries per row for a given N.
-int lse_parts(int N);
+int lse_parts(int N, int K);
 int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream);
 

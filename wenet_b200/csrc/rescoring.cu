@@ -45,7 +45,7 @@ void rs_layout(const Model* m, long long enc_rows, long long R, int batch, int n
     P->o_qkv_full = o; o += align_up((size_t)R * 3 * d * 2);   // self-attention runs on every row of every hypothesis
     P->o_ctx_full = o; o += align_up((size_t)R * d * 2);
     // rescoring never materialises the [R, V] logits: the output GEMM leaves per-tile log-sum-exp partials only
-    P->o_logits = o; o += align_up((size_t)R * lse_parts(m->cfg.vocab) * sizeof(float2));
+    P->o_logits = o; o += align_up((size_t)R * lse_parts(m->cfg.vocab, m->cfg.d_model) * sizeof(float2));
     P->total = o + 256;
 }
 
@@ -170,7 +170,7 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
     } else {
         float2* part = reinterpret_cast<float2*>(ws + P.o_logits);
         RC(gemm_lse_partials(a, d, &D.out.tmap, D.out.w, N, c.vocab, d, D.out.b, part, st));
-        RC(lse_target_logprob(part, lse_parts(c.vocab), a, d, D.out.w, d, D.out.b, target, Q.uniq_of_row, R, c.vocab,
+        RC(lse_target_logprob(part, lse_parts(c.vocab, d), a, d, D.out.w, d, D.out.b, target, Q.uniq_of_row, R, c.vocab,
                               tok_logp, st));
     }
     return WB_OK;

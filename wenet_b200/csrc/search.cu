@@ -1,20 +1,28 @@
-// CTC prefix beam search on the GPU: one CTA per utterance, frames sequential, all (token, prefix)
-// pairs of a frame in parallel.  Bit-level restatement of the reference's host loop
+// CTC prefix beam search on the GPU: ONE CTA (9 warps) PER UTTERANCE, frames sequential, all (token, prefix) pairs
+// and all candidates of a frame in parallel.  Bit-level restatement of the reference's host loop
 //   wenet/models/transformer/search.py:127-249 (ctc_prefix_beam_search, PrefixScore :64-106)
 //   wenet/utils/common.py:302-310 (log_add, Python float == IEEE double)
-// including: double-precision scores, Viterbi scores / token times (times_s / times_ns /
-// cur_token_prob rules of :166-219), dict insertion order as the tie-break of the stable
-// `sorted(..., reverse=True)` (:222-225), first-max-wins comparisons.
+// including: double-precision scores, Viterbi scores / token times (times_s / times_ns / cur_token_prob rules of
+// :166-219), dict insertion order as the tie-break of the stable `sorted(..., reverse=True)` (:222-225),
+// first-max-wins comparisons.
 //
 // Data structures
-//   * prefixes are nodes of a trie (parent, token) kept in a per-utterance pool in HBM; identity of
-//     a prefix inside a frame is (64-bit rolling hash, length, last token)
-//   * times lists are persistent (immutable) linked lists (prev, frame) in a second pool, so
-//     `list.copy()` / `append` / `[-1] = t` of the reference are O(1) pointer operations
+//   * prefixes are nodes of a CANONICAL trie kept in a per-utterance pool in HBM: every distinct prefix string has
+//     exactly one node (a new beam entry first looks its (parent node, token) up in the parent's child list and only
+//     creates a node when none exists), so "prefix + u is already in the beam" is the exact integer test
+//     parent_node[q] == node[p] && last[q] == u.  (Round 1 used a 64-bit rolling hash of the string as identity.)
+//   * times lists are persistent (immutable) linked lists (prev, frame) in a second pool, so `list.copy()` / `append`
+//     / `[-1] = t` of the reference are O(1) pointer operations
 //   * the beam (<= 16 entries) and the <= beam + beam^2 candidates of a frame live in shared memory.
-// Each "unchanged prefix" candidate receives at most three updates per frame (blank, repeat,
-// extension-of-its-parent) — they are replayed in the reference's loop order (token-major,
-// prefix-minor) so every floating-point operation happens in the same order as on the host.
+// Thread mapping per frame (288 threads = 9 warps; thread c owns candidate slot c):
+//   P1  thread (ui, pi) = (tid / 16, tid % 16): extension candidate of prefix pi by top-k token ui
+//   P2  thread q < beam size: the "unchanged prefix" candidate q; its (<= 3) updates (blank, repeat, extension of its
+//       parent landing on it) are replayed in the reference's loop order (token-major, prefix-minor), so every
+//       floating-point operation happens in the same order as on the host
+//   P3  thread c = candidate slot: rank inside its warp by 31 shuffle rotations on an order-preserving integer image
+//       of the fp64 total score; every warp publishes its beam-th best as a pruning bound, the (typically 10-15)
+//       survivors are ranked by warp 0 the same way -> exact top-beam in the reference's stable-sort order
+//   P4  thread r < new beam size: materialise entry r (canonical trie node, times lists)
 #include "common.cuh"
 #include "kernels.h"
 #include <limits.h>
@@ -27,10 +35,6 @@ namespace {
 
 constexpr int MAXB = 16;
 constexpr int NCAND = MAXB + MAXB * MAXB;
-constexpr int PB_WARPS = 8;             // utterances per CTA: one warp each, every barrier is a __syncwarp, so the
-                                        // whole batch occupies only batch/8 SMs and other streams keep the rest
-constexpr int PB_THREADS = 32 * PB_WARPS;
-constexpr int MAXPL = (NCAND + 31) / 32;  // candidates per lane in the selection step
 
 __device__ __forceinline__ double neg_inf() { return -CUDART_INF; }
 
@@ -64,32 +68,24 @@ __device__ __forceinline__ double log_add2(double a, double b) {
     return m + softplus_neg(lo - m);
 }
 
-__device__ __forceinline__ uint64_t mix_hash(uint64_t h, int tok) {
-    uint64_t z = h ^ ((uint64_t)(uint32_t)(tok + 1) * 0x9E3779B97F4A7C15ull);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-
 struct Beam {
     double s[MAXB], ns[MAXB], vs[MAXB], vns[MAXB];
     double score[MAXB], vit[MAXB];
-    uint64_t hash[MAXB];
-    int len[MAXB], last[MAXB], node[MAXB], ts[MAXB], tns[MAXB], times[MAXB];
+    int len[MAXB], last[MAXB], node[MAXB], par[MAXB], ts[MAXB], tns[MAXB], times[MAXB];
     int n;
 };
 
 struct Cand {
     double s[NCAND], ns[NCAND], vs[NCAND], vns[NCAND], total[NCAND];
-    uint64_t hash[NCAND];
     int len[NCAND], last[NCAND];
-    int node[NCAND];       // existing trie node (unchanged prefix) or parent node (extension)
-    int new_tok[NCAND];    // >= 0: extension by this token (needs a new trie node)
+    int node[NCAND];       // existing trie node (unchanged prefix) or PARENT node (extension)
+    int par[NCAND];        // parent node of an unchanged prefix
+    int new_tok[NCAND];    // >= 0: extension by this token (needs a trie node)
     int ts[NCAND];         // times_s head
     int tns[NCAND];        // times_ns head if tns_new == 0, else prev pointer of the node to create
     int tns_new[NCAND];    // 1: times_ns = list(tns) + [t]
     int first[NCAND];      // first-touch sequence number == dict insertion order
-    int valid[NCAND];
+    int valid[NCAND];      // frame stamp (t + 1)
 };
 
 struct PbDev {
@@ -104,50 +100,70 @@ struct PbDev {
     int* out_lens;
     double* out_scores;
     int* out_nhyp;
-    int* pool;  // per utterance: [4][max_len * beam] ints: trie parent, trie token, time prev, time frame
+    int* pool;  // per utterance: [6][max_len * beam] ints: trie parent, token, first child, next sibling; time prev, frame
 };
 
-__device__ __forceinline__ bool cand_better(double ta, int fa, double tb, int fb) {
-    return ta > tb || (ta == tb && fa < fb);
+// order-preserving image of a double in the unsigned integers (-inf < ... < -0 == +0 < ... ; no NaNs occur)
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);   // -0.0 + 0.0 == +0.0
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+// candidate a ranks before b: total desc, then dict insertion order asc
+__device__ __forceinline__ bool key_better(unsigned long long ka, int fa, unsigned long long kb, int fb) {
+    return ka > kb || (ka == kb && fa < fb);
+}
+// rank of this lane's (key, first) among the 32 lanes' (empty lanes carry key 0 / first INT_MAX: never better than a
+// real candidate, and real candidates have pairwise different `first`)
+__device__ __forceinline__ int warp_rank(unsigned long long key, int first, int lane) {
+    const unsigned klo = (unsigned)key, khi = (unsigned)(key >> 32);
+    int rk = 0;
+#pragma unroll
+    for (int r = 1; r < 32; ++r) {
+        const int src = (lane + r) & 31;
+        const unsigned olo = __shfl_sync(0xffffffffu, klo, src);
+        const unsigned ohi = __shfl_sync(0xffffffffu, khi, src);
+        const int of = __shfl_sync(0xffffffffu, first, src);
+        const unsigned long long ok = ((unsigned long long)ohi << 32) | olo;
+        rk += key_better(ok, of, key, first) ? 1 : 0;
+    }
+    return rk;
 }
 
-struct WarpState {
-    Beam Bs[2];
-    Cand C;
-    float tk_val[MAXB];
-    int tk_idx[MAXB];
-    int dest[MAXB * MAXB];
-    int rank_slot[MAXB];
-    int vlist[NCAND];
-};
+constexpr int PB_SLOT_WARPS = (NCAND + 31) / 32;   // warps that own candidate slots in P3 (9: 272 slots at beam 16)
+constexpr int PB_THREADS = 32 * PB_SLOT_WARPS;     // 288: thread c owns candidate slot c; threads < 256 are the (ui, pi) pairs
 
-__global__ void __launch_bounds__(PB_THREADS)
-prefix_beam_kernel(PbDev P, int batch) {
-    extern __shared__ __align__(16) uint8_t pb_smem[];
-    const int utt = blockIdx.x * PB_WARPS + (threadIdx.x >> 5);
-    if (utt >= batch) return;  // whole warp; no block-level barriers are used anywhere below
-    WarpState& W = reinterpret_cast<WarpState*>(pb_smem)[threadIdx.x >> 5];
-    Beam* Bs = W.Bs;
-    Cand& C = W.C;
-    float* tk_val = W.tk_val;
-    int* tk_idx = W.tk_idx;
-    int* dest = W.dest;
-    int* rank_slot = W.rank_slot;
-    int* vlist = W.vlist;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
+__global__ void __launch_bounds__(PB_THREADS, 3)
+prefix_beam_kernel(PbDev P) {
+    __shared__ Beam Bs[2];
+    __shared__ Cand C;
+    __shared__ float tk_val[2][MAXB];
+    __shared__ int tk_idx[2][MAXB];
+    __shared__ int dest[MAXB * MAXB];
+    __shared__ int rank_slot[MAXB];
+    __shared__ unsigned long long thr_key[PB_SLOT_WARPS];
+    __shared__ int thr_first[PB_SLOT_WARPS];
+    __shared__ int warp_valid[PB_SLOT_WARPS];
+    __shared__ unsigned long long sv_key[NCAND];
+    __shared__ int sv_first[NCAND], sv_slot[NCAND];
+    __shared__ int n_surv;
+    __shared__ int root_child;      // head of the root's child list (the root has no pool entry)
+
+    const int utt = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int beam = P.beam;
     const int T = P.seq_len[utt];
     const long long f0 = P.seq_start[utt];
     const long long pool_n = (long long)P.max_len * beam;
-    int* trie_parent = P.pool + (long long)utt * 4 * pool_n;
+    int* trie_parent = P.pool + (long long)utt * 6 * pool_n;
     int* trie_tok = trie_parent + pool_n;
-    int* time_prev = trie_tok + pool_n;
+    int* trie_child = trie_tok + pool_n;     // first child
+    int* trie_sib = trie_child + pool_n;     // next sibling
+    int* time_prev = trie_sib + pool_n;
     int* time_t = time_prev + pool_n;
-    const int ncs = MAXB + beam * MAXB;  // candidate slots in use
+    const int ncs = MAXB + beam * MAXB;      // candidate slots in use
 
-    for (int c = lane; c < NCAND; c += 32) C.valid[c] = 0;
-    if (lane == 0) {
+    for (int c = tid; c < NCAND; c += PB_THREADS) C.valid[c] = 0;
+    if (tid == 0) {
         Beam& B = Bs[0];
         B.n = 1;
         B.s[0] = 0.0;
@@ -157,94 +173,91 @@ prefix_beam_kernel(PbDev P, int batch) {
         B.score[0] = 0.0;   // log_add(0, -inf)
         B.vit[0] = 0.0;     // v_s > v_ns is false -> v_ns
         B.times[0] = -1;
-        B.hash[0] = 0x1234567ull;
         B.len[0] = 0;
         B.last[0] = -1;
-        B.node[0] = -1;
+        B.node[0] = -1;     // the root
+        B.par[0] = -2;      // the root is nobody's child
         B.ts[0] = -1;
         B.tns[0] = -1;
+        root_child = -1;
+        n_surv = 0;
     }
-    int cur = 0;
-    float pf_val = 0.f;
-    int pf_idx = 0;
-    if (lane < beam && T > 0) {
-        pf_val = P.topk_val[f0 * P.topk + lane];
-        pf_idx = P.topk_idx[f0 * P.topk + lane];
+    if (tid < beam && T > 0) {
+        tk_val[0][tid] = P.topk_val[f0 * P.topk + tid];
+        tk_idx[0][tid] = P.topk_idx[f0 * P.topk + tid];
     }
-    __syncwarp();
+    __syncthreads();
 
+    int cur = 0;
     for (int t = 0; t < T; ++t) {
-        if (lane < beam) {
-            tk_val[lane] = pf_val;
-            tk_idx[lane] = pf_idx;
-        }
-        __syncwarp();
-        if (lane < beam && t + 1 < T) {  // prefetch the next frame's top-k behind this frame's work
-            pf_val = P.topk_val[(f0 + t + 1) * P.topk + lane];
-            pf_idx = P.topk_idx[(f0 + t + 1) * P.topk + lane];
+        const float* tkv = tk_val[t & 1];
+        const int* tki = tk_idx[t & 1];
+        if (tid < beam && t + 1 < T) {   // next frame's top-k lands in the other buffer behind this frame's work
+            tk_val[(t + 1) & 1][tid] = P.topk_val[(f0 + t + 1) * P.topk + tid];
+            tk_idx[(t + 1) & 1][tid] = P.topk_idx[(f0 + t + 1) * P.topk + tid];
         }
         Beam& B = Bs[cur];
         const int nb = B.n;
 
-        // ---- extensions: (token ui, prefix pi) pairs strided over the lanes ----
-        for (int pr = lane; pr < beam * nb; pr += 32) {
-            const int ui = pr / nb, pi = pr - ui * nb;
-            const int u = tk_idx[ui];
-            int d = -1;
-            if (u != P.blank_id) {
-                const uint64_t h = mix_hash(B.hash[pi], u);
-                const int ln = B.len[pi] + 1;
-                d = MAXB + ui * MAXB + pi;
-                for (int q = 0; q < nb; ++q)
-                    if (B.last[q] == u && B.len[q] == ln && B.hash[q] == h) d = q;
-                if (d >= MAXB) {
-                    const double prob = (double)tk_val[ui];
-                    const bool rep = (u == B.last[pi]);
-                    C.s[d] = neg_inf();
-                    C.vs[d] = neg_inf();
-                    C.ts[d] = -1;
-                    // log_add(-inf, x) == x exactly
-                    const double nsv = (rep ? B.s[pi] : B.score[pi]) + prob;
-                    double vn = (rep ? B.vs[pi] : B.vit[pi]) + prob;
-                    // reference: `if next.v_ns < y` with next.v_ns = -inf: false only when y == -inf
-                    if (vn > neg_inf()) {
-                        C.tns[d] = rep ? B.ts[pi] : B.times[pi];
-                        C.tns_new[d] = 1;
-                    } else {
-                        vn = neg_inf();
-                        C.tns[d] = -1;
-                        C.tns_new[d] = 0;
+        // ---- P1: extension candidates, one thread per (token ui, prefix pi) ----
+        {
+            const int ui = tid >> 4, pi = tid & (MAXB - 1);
+            if (tid < MAXB * MAXB && ui < beam && pi < nb) {
+                const int u = tki[ui];
+                int d = -1;
+                if (u != P.blank_id) {
+                    const int np = B.node[pi];
+                    d = MAXB + ui * MAXB + pi;
+                    for (int q = 0; q < nb; ++q)
+                        if (B.par[q] == np && B.last[q] == u) d = q;   // prefix pi + u is beam entry q (canonical trie)
+                    if (d >= MAXB) {
+                        const double prob = (double)tkv[ui];
+                        const bool rep = (u == B.last[pi]);
+                        C.s[d] = neg_inf();
+                        C.vs[d] = neg_inf();
+                        C.ts[d] = -1;
+                        // log_add(-inf, x) == x exactly
+                        const double nsv = (rep ? B.s[pi] : B.score[pi]) + prob;
+                        double vn = (rep ? B.vs[pi] : B.vit[pi]) + prob;
+                        // reference: `if next.v_ns < y` with next.v_ns = -inf: false only when y == -inf
+                        if (vn > neg_inf()) {
+                            C.tns[d] = rep ? B.ts[pi] : B.times[pi];
+                            C.tns_new[d] = 1;
+                        } else {
+                            vn = neg_inf();
+                            C.tns[d] = -1;
+                            C.tns_new[d] = 0;
+                        }
+                        C.ns[d] = nsv;
+                        C.vns[d] = vn;
+                        C.len[d] = B.len[pi] + 1;
+                        C.last[d] = u;
+                        C.node[d] = np;
+                        C.new_tok[d] = u;
+                        C.first[d] = (ui * nb + pi) * 2 + (rep ? 1 : 0);
+                        C.total[d] = nsv;  // log_add(-inf, ns)
+                        C.valid[d] = t + 1;   // frame stamp: no per-frame reset of the flags
                     }
-                    C.ns[d] = nsv;
-                    C.vns[d] = vn;
-                    C.hash[d] = h;
-                    C.len[d] = ln;
-                    C.last[d] = u;
-                    C.node[d] = B.node[pi];
-                    C.new_tok[d] = u;
-                    C.first[d] = (ui * nb + pi) * 2 + (rep ? 1 : 0);
-                    C.total[d] = nsv;  // log_add(-inf, ns)
-                    C.valid[d] = t + 1;   // frame stamp: no per-frame reset of the flags
                 }
+                dest[ui * MAXB + pi] = d;
             }
-            dest[ui * MAXB + pi] = d;
         }
-        __syncwarp();
+        __syncthreads();
 
-        // ---- unchanged prefixes: lane q replays its (<= 3) updates in the reference's loop order ----
-        if (lane < nb) {
-            const int q = lane;
+        // ---- P2: unchanged prefixes: thread q replays its (<= 3) updates in the reference's loop order ----
+        if (tid < nb) {
+            const int q = tid;
             const int lastq = B.last[q];
             int ui_blank = -1, ui_last = -1;
             for (int ui = 0; ui < beam; ++ui) {
-                const int u = tk_idx[ui];
+                const int u = tki[ui];
                 if (u == P.blank_id) ui_blank = ui;
                 else if (u == lastq) ui_last = ui;
             }
             double s = neg_inf(), ns = neg_inf(), vs = neg_inf(), vns = neg_inf();
             int ts = -1, tns = -1, tns_new = 0, first = INT_MAX, any = 0;
             if (ui_blank >= 0) {
-                const double prob = (double)tk_val[ui_blank];
+                const double prob = (double)tkv[ui_blank];
                 s = B.score[q] + prob;          // log_add(-inf, x)
                 vs = B.vit[q] + prob;
                 ts = B.times[q];
@@ -252,7 +265,7 @@ prefix_beam_kernel(PbDev P, int batch) {
                 any = 1;
             }
             if (ui_last >= 0) {
-                const double prob = (double)tk_val[ui_last];
+                const double prob = (double)tkv[ui_last];
                 int pe = -1;  // parent prefix whose extension by last(q) lands on q
                 for (int pi = 0; pi < nb; ++pi)
                     if (pi != q && dest[ui_last * MAXB + pi] == q) pe = pi;
@@ -298,146 +311,92 @@ prefix_beam_kernel(PbDev P, int batch) {
                 C.ts[q] = ts;
                 C.tns[q] = tns;
                 C.tns_new[q] = tns_new;
-                C.hash[q] = B.hash[q];
                 C.len[q] = B.len[q];
                 C.last[q] = lastq;
                 C.node[q] = B.node[q];
+                C.par[q] = B.par[q];
                 C.new_tok[q] = -1;
                 C.first[q] = first;
                 C.total[q] = log_add2(s, ns);
                 C.valid[q] = t + 1;
             }
         }
-        __syncwarp();
+        __syncthreads();
 
-        // ---- second beam prune: stable sort by total desc == top-beam by (total, insertion order) ----
+        // ---- P3: second beam prune: stable sort by total desc == top-beam by (total, insertion order) ----
+        // (a) every slot-owning warp ranks its 32 slots; a slot outside its warp's top-beam cannot be in the global
+        //     top-beam; the warp's beam-th best is a lower bound of the global beam-th best
+        unsigned long long my_key = 0ull;
+        int my_first = INT_MAX, my_rank = 32;
+        bool my_valid = false;
+        if (warp < PB_SLOT_WARPS) {
+            const int c = tid;
+            my_valid = (c < ncs) && (C.valid[c] == t + 1);
+            if (my_valid) {
+                my_key = order_key(C.total[c]);
+                my_first = C.first[c];
+            }
+            const unsigned vm = __ballot_sync(0xffffffffu, my_valid);
+            if (vm) {   // warp-uniform
+                my_rank = warp_rank(my_key, my_first, lane);
+                const unsigned bm = __ballot_sync(0xffffffffu, my_valid && my_rank == beam - 1);
+                if (lane == 0) {
+                    warp_valid[warp] = __popc(vm);
+                    if (!bm) thr_key[warp] = 0ull, thr_first[warp] = INT_MAX;   // fewer than beam candidates here: no bound
+                }
+                if (my_valid && my_rank == beam - 1) thr_key[warp] = my_key, thr_first[warp] = my_first;
+            } else if (lane == 0) {
+                warp_valid[warp] = 0;
+                thr_key[warp] = 0ull;
+                thr_first[warp] = INT_MAX;
+            }
+        }
+        __syncthreads();
+        // (b) survivors: inside their warp's top-beam and not below the best bound
+        if (warp < PB_SLOT_WARPS && my_valid && my_rank < beam) {
+            unsigned long long bk = 0ull;
+            int bf = INT_MAX;
+#pragma unroll
+            for (int w = 0; w < PB_SLOT_WARPS; ++w)
+                if (key_better(thr_key[w], thr_first[w], bk, bf)) bk = thr_key[w], bf = thr_first[w];
+            if (!key_better(bk, bf, my_key, my_first)) {
+                const int pos = atomicAdd(&n_surv, 1);
+                sv_key[pos] = my_key;
+                sv_first[pos] = my_first;
+                sv_slot[pos] = tid;
+            }
+        }
+        __syncthreads();
+        // (c) warp 0 ranks the survivors (any order in the list: the rank is a function of the keys only)
         int nvalid = 0;
-        for (int base = 0; base < ncs; base += 32) {
-            const int c = base + lane;
-            const bool v = (c < ncs) && (C.valid[c] == t + 1);
-            const unsigned m = __ballot_sync(0xffffffffu, v);
-            if (v) vlist[nvalid + __popc(m & lt_mask)] = c;
-            nvalid += __popc(m);
-        }
-        __syncwarp();
-        // Exact top-`beam` of <= beam + beam^2 candidates without serial arg-max rounds:
-        //  (1) every lane reduces its own <= MAXPL candidates to a local best; the `beam`-th best of the 32 local
-        //      bests is a lower bound of the true `beam`-th best total, so everything strictly below it is pruned
-        //      (ranks among lanes by 31 independent shuffle rotations);
-        //  (2) the survivors (>= beam, typically 10-15) are compacted one per lane and ranked the same way.
-        //  Order = the reference's stable descending sort: (total desc, dict insertion order asc).
-        const int kmax = (nvalid + 31) >> 5;  // warp-uniform
-        double my_tot[MAXPL];
-        int my_first[MAXPL], my_slot[MAXPL];
-        double lt = neg_inf();
-        int lf = INT_MAX;
 #pragma unroll
-        for (int k = 0; k < MAXPL; ++k) {
-            my_slot[k] = -1;
-            my_tot[k] = neg_inf();
-            my_first[k] = INT_MAX;
-            if (k < kmax) {
-                const int i = lane + 32 * k;
-                if (i < nvalid) {
-                    const int c = vlist[i];
-                    my_slot[k] = c;
-                    my_tot[k] = C.total[c];
-                    my_first[k] = C.first[c];
-                    if (cand_better(my_tot[k], my_first[k], lt, lf)) {
-                        lt = my_tot[k];
-                        lf = my_first[k];
-                    }
-                }
-            }
-        }
-        double thr_t = neg_inf();
-        int thr_f = INT_MAX;  // default: nothing is pruned
-        if (nvalid > 32) {
-            int rk = 0;
-#pragma unroll
-            for (int r = 1; r < 32; ++r) {
-                const double ot = __shfl_sync(0xffffffffu, lt, (lane + r) & 31);
-                const int of = __shfl_sync(0xffffffffu, lf, (lane + r) & 31);
-                rk += cand_better(ot, of, lt, lf) ? 1 : 0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, rk == beam - 1);  // all 32 lanes hold a candidate here
-            if (m) {
-                const int src = __ffs(m) - 1;
-                thr_t = __shfl_sync(0xffffffffu, lt, src);
-                thr_f = __shfl_sync(0xffffffffu, lf, src);
-            }
-        }
-        __syncwarp();  // vlist fully consumed -> reuse it for the survivor list
-        int ns = 0;
-#pragma unroll
-        for (int k = 0; k < MAXPL; ++k) {
-            if (k < kmax) {
-                const bool sv = my_slot[k] >= 0 && !cand_better(thr_t, thr_f, my_tot[k], my_first[k]);
-                const unsigned m = __ballot_sync(0xffffffffu, sv);
-                if (sv) vlist[ns + __popc(m & lt_mask)] = my_slot[k];
-                ns += __popc(m);
-            }
-        }
-        __syncwarp();
+        for (int w = 0; w < PB_SLOT_WARPS; ++w) nvalid += warp_valid[w];
         const int nnew = nvalid < beam ? nvalid : beam;
-        if (ns <= 32) {
-            const int c = lane < ns ? vlist[lane] : -1;
-            const double t_ = c >= 0 ? C.total[c] : neg_inf();
-            const int f_ = c >= 0 ? C.first[c] : INT_MAX;
-            int rk = 0;
-#pragma unroll
-            for (int r = 1; r < 32; ++r) {
-                const double ot = __shfl_sync(0xffffffffu, t_, (lane + r) & 31);
-                const int of = __shfl_sync(0xffffffffu, f_, (lane + r) & 31);
-                rk += cand_better(ot, of, t_, f_) ? 1 : 0;   // empty lanes carry (-inf, INT_MAX): never better
-            }
-            if (c >= 0 && rk < beam) rank_slot[rk] = c;
-        } else {
-            // rare fallback (many candidates tie with / exceed the bound): serial arg-max rounds over the survivors
-            const int kmax2 = (ns + 31) >> 5;
-#pragma unroll
-            for (int k = 0; k < MAXPL; ++k) {
-                my_slot[k] = -1;
-                if (k < kmax2 && lane + 32 * k < ns) {
-                    const int c = vlist[lane + 32 * k];
-                    my_slot[k] = c;
-                    my_tot[k] = C.total[c];
-                    my_first[k] = C.first[c];
+        if (warp == 0) {
+            const int nsv = n_surv;
+            if (nsv <= 32) {
+                const unsigned long long k = lane < nsv ? sv_key[lane] : 0ull;
+                const int f = lane < nsv ? sv_first[lane] : INT_MAX;
+                const int rk = warp_rank(k, f, lane);
+                if (lane < nsv && rk < beam) rank_slot[rk] = sv_slot[lane];
+            } else {
+                // many candidates tie with / exceed the bound: rank by counting over the list
+                for (int i = lane; i < nsv; i += 32) {
+                    const unsigned long long k = sv_key[i];
+                    const int f = sv_first[i];
+                    int rk = 0;
+                    for (int j = 0; j < nsv; ++j) rk += key_better(sv_key[j], sv_first[j], k, f) ? 1 : 0;
+                    if (rk < beam) rank_slot[rk] = sv_slot[i];
                 }
-            }
-            for (int r = 0; r < nnew; ++r) {
-                double bt = neg_inf();
-                int bf = INT_MAX, bs = -1;
-#pragma unroll
-                for (int k = 0; k < MAXPL; ++k)
-                    if (k < kmax2 && my_slot[k] >= 0 && cand_better(my_tot[k], my_first[k], bt, bf)) {
-                        bt = my_tot[k];
-                        bf = my_first[k];
-                        bs = my_slot[k];
-                    }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ot = __shfl_xor_sync(0xffffffffu, bt, o);
-                    const int of = __shfl_xor_sync(0xffffffffu, bf, o);
-                    const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-                    if (cand_better(ot, of, bt, bf)) {
-                        bt = ot;
-                        bf = of;
-                        bs = os;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < MAXPL; ++k)
-                    if (k < kmax2 && my_slot[k] == bs) my_slot[k] = -1;
-                if (lane == 0) rank_slot[r] = bs;
             }
         }
-        __syncwarp();
+        __syncthreads();
 
-        // ---- materialise the new beam ----
+        // ---- P4: materialise the new beam ----
         Beam& NB = Bs[cur ^ 1];
-        if (lane < nnew) {
-            const int r = lane;
+        int new_node = -1, new_parent = -1;   // P4b: node this thread has to link into its parent's child list
+        if (tid < nnew) {
+            const int r = tid;
             const int c = rank_slot[r];
             const int pool_i = t * beam + r;
             const double vs = C.vs[c], vns = C.vns[c];
@@ -446,15 +405,27 @@ prefix_beam_kernel(PbDev P, int batch) {
             NB.vs[r] = vs;
             NB.vns[r] = vns;
             NB.score[r] = C.total[c];
-            NB.hash[r] = C.hash[c];
             NB.len[r] = C.len[c];
             NB.last[r] = C.last[c];
-            if (C.new_tok[c] >= 0) {
-                trie_parent[pool_i] = C.node[c];
-                trie_tok[pool_i] = C.new_tok[c];
-                NB.node[r] = pool_i;
+            const int tok = C.new_tok[c];
+            if (tok >= 0) {
+                // canonical node of (parent, tok): reuse the parent's existing child if the string was in a beam before
+                const int par = C.node[c];
+                int ch = (par >= 0) ? trie_child[par] : root_child;
+                while (ch >= 0 && trie_tok[ch] != tok) ch = trie_sib[ch];
+                if (ch < 0) {
+                    ch = pool_i;
+                    trie_parent[ch] = par;
+                    trie_tok[ch] = tok;
+                    trie_child[ch] = -1;
+                    new_node = ch;
+                    new_parent = par;
+                }
+                NB.node[r] = ch;
+                NB.par[r] = par;
             } else {
                 NB.node[r] = C.node[c];
+                NB.par[r] = C.par[c];
             }
             const int tsv = C.ts[c];
             int tnsv;
@@ -471,19 +442,39 @@ prefix_beam_kernel(PbDev P, int batch) {
             NB.vit[r] = sb ? vs : vns;
             NB.times[r] = sb ? tsv : tnsv;
         }
-        if (lane == 0) NB.n = nnew;
-        __syncwarp();
+        if (tid == 0) {
+            NB.n = nnew;
+            n_surv = 0;
+        }
+        // P4b: link the new nodes (after every look-up of this frame has finished; siblings of one parent are linked
+        // one after the other by the lanes of warp 0 in lane order)
+        if (warp == 0) {
+            __syncwarp();
+            const unsigned nm = __ballot_sync(0xffffffffu, new_node >= 0);
+            for (unsigned m = nm; m; m &= m - 1) {
+                const int src = __ffs(m) - 1;
+                if (lane == src) {
+                    if (new_parent >= 0) {
+                        trie_sib[new_node] = trie_child[new_parent];
+                        trie_child[new_parent] = new_node;
+                    } else {
+                        trie_sib[new_node] = root_child;
+                        root_child = new_node;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
         cur ^= 1;
     }
 
     // ---- emit n-best ----
-    __threadfence_block();
-    __syncwarp();
     const Beam& B = Bs[cur];
     const int nb = B.n;
-    if (lane == 0) P.out_nhyp[utt] = nb;
-    if (lane < nb) {
-        const int r = lane;
+    if (tid == 0) P.out_nhyp[utt] = nb;
+    if (tid < nb) {
+        const int r = tid;
         const long long o = ((long long)utt * beam + r) * P.max_len;
         const int ln = B.len[r];
         P.out_lens[utt * beam + r] = ln;
@@ -500,16 +491,16 @@ prefix_beam_kernel(PbDev P, int batch) {
         for (int h = head; h >= 0 && k >= 0; h = time_prev[h], --k)
             if (k < P.max_len) P.out_times[o + k] = time_t[h];
         for (int z = cnt; z < ln; ++z) P.out_times[o + z] = -1;
-    } else if (lane < beam) {
-        P.out_lens[utt * beam + lane] = 0;
-        P.out_scores[utt * beam + lane] = neg_inf();
+    } else if (tid < beam) {
+        P.out_lens[utt * beam + tid] = 0;
+        P.out_scores[utt * beam + tid] = neg_inf();
     }
 }
 
 }  // namespace
 
 size_t prefix_beam_workspace_bytes(int batch, int beam, int max_len) {
-    return (size_t)batch * 4 * (size_t)max_len * beam * sizeof(int) + 256;
+    return (size_t)batch * 6 * (size_t)max_len * beam * sizeof(int) + 256;
 }
 
 int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream) {
@@ -533,10 +524,9 @@ int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream) {
     P.out_scores = a.out_scores;
     P.out_nhyp = a.out_nhyp;
     P.pool = reinterpret_cast<int*>(a.workspace);
-    const size_t smem = sizeof(WarpState) * PB_WARPS;
-    WB_SET_MAX_DYN_SMEM(prefix_beam_kernel, smem);
+    WB_REQUIRE((long long)a.max_len * a.beam < 2147483647LL / 8, WB_ERR_UNSUPPORTED, "prefix beam search: pool too large");
     ProfScope _ps(PT_PREFIX_BEAM, stream, 0.0);
-    prefix_beam_kernel<<<ceil_div(a.batch, PB_WARPS), PB_THREADS, smem, stream>>>(P, a.batch);
+    prefix_beam_kernel<<<a.batch, PB_THREADS, 0, stream>>>(P);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
