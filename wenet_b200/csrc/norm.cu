@@ -66,6 +66,71 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int M, int d, const
     }
 }
 
+// Two LayerNorms back to back on the same row, one read of x:  y = LN1(x) (fp32, optional write-back: the residual
+// stream after norm_final, encoder_layer.py:262-263),  z = LN2(y) (bf16 and / or fp32): norm_final of layer l fused with
+// norm_ff_macaron of layer l + 1, and norm_final of the last layer with after_norm (encoder.py:176-177).
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm2_kernel(const float* __restrict__ x, long long ldx, int M, int d, const float* __restrict__ g1,
+                  const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, float eps,
+                  float* y_f32, long long ld_y, __nv_bfloat16* __restrict__ z_bf16, long long ld_zb, int split3,
+                  float* __restrict__ z_f32, long long ld_zf) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * LN_WARPS + warp;
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    float4 v[VPL];
+    const float inv_d = 1.0f / (float)d;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            if (pass == 0) v[i] = xr[lane + 32 * i];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) * inv_d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            v[i].x -= mean;
+            v[i].y -= mean;
+            v[i].z -= mean;
+            v[i].w -= mean;
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+        const float* gamma = pass == 0 ? g1 : g2;
+        const float* beta = pass == 0 ? b1 : b2;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c4 = lane + 32 * i;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+            v[i].x = v[i].x * rstd * g.x + b.x;
+            v[i].y = v[i].y * rstd * g.y + b.y;
+            v[i].z = v[i].z * rstd * g.z + b.z;
+            v[i].w = v[i].w * rstd * g.w + b.w;
+            if (pass == 0) {
+                if (y_f32) reinterpret_cast<float4*>(y_f32 + row * ld_y)[c4] = v[i];
+            } else {
+                if (z_f32) reinterpret_cast<float4*>(z_f32 + row * ld_zf)[c4] = v[i];
+                if (z_bf16) {
+                    __nv_bfloat16* o = z_bf16 + row * ld_zb + 4 * c4;
+                    const uint32_t p0 = pack_bf16x2(v[i].x, v[i].y), p1 = pack_bf16x2(v[i].z, v[i].w);
+                    *reinterpret_cast<uint2*>(o) = make_uint2(p0, p1);
+                    if (split3) {
+                        const uint32_t l0 = pack_bf16x2(v[i].x - bf16_lo(p0), v[i].y - bf16_hi(p0));
+                        const uint32_t l1 = pack_bf16x2(v[i].z - bf16_lo(p1), v[i].w - bf16_hi(p1));
+                        *reinterpret_cast<uint2*>(o + d) = make_uint2(l0, l1);
+                        *reinterpret_cast<uint2*>(o + 2 * d) = make_uint2(p0, p1);
+                    }
+                }
+            }
+        }
+    }
+}
+
 __global__ void cast_rows_kernel(const float* __restrict__ x, long long ldx, int M, int d,
                                  __nv_bfloat16* __restrict__ out, long long ldo, int split3) {
     const long long n4 = (long long)M * (d / 4);
@@ -125,6 +190,37 @@ int layernorm_rows(const float* x, long long ldx, int M, int d, const float* gam
             return WB_ERR_UNSUPPORTED;
     }
 #undef WB_LN
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
+}
+
+int layernorm2_rows(const float* x, long long ldx, int M, int d, const float* g1, const float* b1, const float* g2,
+                    const float* b2, float eps, float* y_f32, long long ld_y, void* z_bf16, long long ld_zb, int split3,
+                    float* z_f32, long long ld_zf, cudaStream_t stream) {
+    if (M <= 0) return WB_OK;
+    WB_REQUIRE(d % 128 == 0 && d <= 1024, WB_ERR_UNSUPPORTED, "layernorm2: d=%d must be a multiple of 128, <= 1024", d);
+    WB_REQUIRE(ldx % 4 == 0 && ld_y % 4 == 0 && ld_zb % 4 == 0 && ld_zf % 4 == 0, WB_ERR_BAD_ARG, "layernorm2: pitches must be %%4");
+    const int grid = ceil_div(M, LN_WARPS);
+    ProfScope _ps(PT_LAYERNORM, stream,
+                  (double)M * d * (4.0 + (y_f32 ? 4.0 : 0.0) + (z_bf16 ? 2.0 : 0.0) + (z_f32 ? 4.0 : 0.0)));
+    __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(z_bf16);
+#define WB_LN2(V)                                                                                                   \
+    layernorm2_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(x, ldx, M, d, g1, b1, g2, b2, eps, y_f32, ld_y, zb, ld_zb, \
+                                                             split3, z_f32, ld_zf)
+    switch (d / 128) {
+        case 1: WB_LN2(1); break;
+        case 2: WB_LN2(2); break;
+        case 3: WB_LN2(3); break;
+        case 4: WB_LN2(4); break;
+        case 5: WB_LN2(5); break;
+        case 6: WB_LN2(6); break;
+        case 8: WB_LN2(8); break;
+        default:
+            set_last_error("layernorm2: d=%d unsupported", d);
+            return WB_ERR_UNSUPPORTED;
+    }
+#undef WB_LN2
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

@@ -19,9 +19,11 @@
 //   P2  thread q < beam size: the "unchanged prefix" candidate q; its (<= 3) updates (blank, repeat, extension of its
 //       parent landing on it) are replayed in the reference's loop order (token-major, prefix-minor), so every
 //       floating-point operation happens in the same order as on the host
-//   P3  thread c = candidate slot: rank inside its warp by 31 shuffle rotations on an order-preserving integer image
-//       of the fp64 total score; every warp publishes its beam-th best as a pruning bound, the (typically 10-15)
-//       survivors are ranked by warp 0 the same way -> exact top-beam in the reference's stable-sort order
+//   P3  warp 0 ranks its own candidates (unchanged prefixes + extensions by the best token) by shuffle rotations on an
+//       order-preserving integer image of the fp64 total score and publishes its beam-th best as a pruning bound;
+//       thread c = candidate slot of the other warps only compares with the bound; the (typically 10-15) survivors
+//       are ranked by warp 0 the same way -> exact top-beam in the reference's stable-sort order.  P2 and the key
+//       set-up of the other warps overlap.
 //   P4  thread r < new beam size: materialise entry r (canonical trie node, times lists)
 #include "common.cuh"
 #include "kernels.h"
@@ -48,13 +50,18 @@ __device__ __forceinline__ double softplus_neg(double d) {
     idx = idx > WB_SOFTPLUS_NINT - 1 ? WB_SOFTPLUS_NINT - 1 : idx;
     const double t = fma(4.0, d, 2.0 * (double)idx + 1.0);   // (d - mid) / 0.25, mid = -(idx + 0.5) / 2
     const double* c = g_softplus_tab[idx];
-    double coef[WB_SOFTPLUS_DEG + 1];
+    double k[WB_SOFTPLUS_DEG + 1];
 #pragma unroll
-    for (int j = 0; j <= WB_SOFTPLUS_DEG; ++j) coef[j] = __ldg(c + j);
-    double v = coef[WB_SOFTPLUS_DEG];
-#pragma unroll
-    for (int j = WB_SOFTPLUS_DEG - 1; j >= 0; --j) v = fma(v, t, coef[j]);
-    return v;
+    for (int j = 0; j <= WB_SOFTPLUS_DEG; ++j) k[j] = __ldg(c + j);
+    // Estrin's scheme (5 dependent fma levels instead of 12: this chain sits on the per-frame critical path of the beam
+    // search); the polynomial is accurate to 1.1e-16, the evaluation order changes the result by at most an ulp
+    static_assert(WB_SOFTPLUS_DEG == 12, "Estrin scheme below is written for degree 12");
+    const double t2 = t * t, t4 = t2 * t2, t8 = t4 * t4;
+    const double p01 = fma(k[1], t, k[0]), p23 = fma(k[3], t, k[2]), p45 = fma(k[5], t, k[4]), p67 = fma(k[7], t, k[6]);
+    const double p89 = fma(k[9], t, k[8]), pab = fma(k[11], t, k[10]);
+    const double q0 = fma(p23, t2, p01), q1 = fma(p67, t2, p45), q2 = fma(pab, t2, p89);
+    const double r0 = fma(q1, t4, q0), r1 = fma(k[12], t4, q2);
+    return fma(r1, t8, r0);
 }
 
 // log_add of wenet/utils/common.py:302-310 for two arguments:
@@ -112,14 +119,16 @@ __device__ __forceinline__ unsigned long long order_key(double v) {
 __device__ __forceinline__ bool key_better(unsigned long long ka, int fa, unsigned long long kb, int fb) {
     return ka > kb || (ka == kb && fa < fb);
 }
-// rank of this lane's (key, first) among the 32 lanes' (empty lanes carry key 0 / first INT_MAX: never better than a
-// real candidate, and real candidates have pairwise different `first`)
-__device__ __forceinline__ int warp_rank(unsigned long long key, int first, int lane) {
+// rank of this lane's (key, first) among lanes [0, n) of the warp (n warp-uniform; lanes >= n get a meaningless value).
+// Real candidates have pairwise different `first`; empty lanes carry key 0 / first INT_MAX and are never better.
+// n - 1 independent shuffle rotations (not a sorting network: no dependent stages).
+__device__ __forceinline__ int warp_rank(unsigned long long key, int first, int lane, int n) {
     const unsigned klo = (unsigned)key, khi = (unsigned)(key >> 32);
     int rk = 0;
-#pragma unroll
-    for (int r = 1; r < 32; ++r) {
-        const int src = (lane + r) & 31;
+#pragma unroll 4
+    for (int r = 1; r < n; ++r) {
+        int src = lane + r;
+        src = src >= n ? src - n : src;
         const unsigned olo = __shfl_sync(0xffffffffu, klo, src);
         const unsigned ohi = __shfl_sync(0xffffffffu, khi, src);
         const int of = __shfl_sync(0xffffffffu, first, src);
@@ -140,13 +149,17 @@ prefix_beam_kernel(PbDev P) {
     __shared__ int tk_idx[2][MAXB];
     __shared__ int dest[MAXB * MAXB];
     __shared__ int rank_slot[MAXB];
-    __shared__ unsigned long long thr_key[PB_SLOT_WARPS];
-    __shared__ int thr_first[PB_SLOT_WARPS];
+    __shared__ unsigned long long thr_key[1];
+    __shared__ int thr_first[1];
     __shared__ int warp_valid[PB_SLOT_WARPS];
     __shared__ unsigned long long sv_key[NCAND];
     __shared__ int sv_first[NCAND], sv_slot[NCAND];
     __shared__ int n_surv;
     __shared__ int root_child;      // head of the root's child list (the root has no pool entry)
+    // P1 -> P2 hand-over, frame-stamped ((t + 1) * 32 + index) so that nothing has to be cleared per frame:
+    __shared__ int s_ui_blank;      // top-k position of <blank>
+    __shared__ int s_ui_last[MAXB]; // top-k position of prefix q's last token
+    __shared__ int s_pe[MAXB];      // the prefix whose extension lands on beam entry q
 
     const int utt = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -181,6 +194,11 @@ prefix_beam_kernel(PbDev P) {
         B.tns[0] = -1;
         root_child = -1;
         n_surv = 0;
+        s_ui_blank = 0;
+    }
+    if (tid < MAXB) {
+        s_ui_last[tid] = 0;
+        s_pe[tid] = 0;
     }
     if (tid < beam && T > 0) {
         tk_val[0][tid] = P.topk_val[f0 * P.topk + tid];
@@ -204,12 +222,18 @@ prefix_beam_kernel(PbDev P) {
             const int ui = tid >> 4, pi = tid & (MAXB - 1);
             if (tid < MAXB * MAXB && ui < beam && pi < nb) {
                 const int u = tki[ui];
+                const int stamp = (t + 1) * 32;
                 int d = -1;
-                if (u != P.blank_id) {
+                if (u == P.blank_id) {
+                    if (pi == 0) s_ui_blank = stamp + ui;
+                } else {
                     const int np = B.node[pi];
+                    if (u == B.last[pi]) s_ui_last[pi] = stamp + ui;
                     d = MAXB + ui * MAXB + pi;
-                    for (int q = 0; q < nb; ++q)
-                        if (B.par[q] == np && B.last[q] == u) d = q;   // prefix pi + u is beam entry q (canonical trie)
+#pragma unroll
+                    for (int q = 0; q < MAXB; ++q)   // (fixed trip count: all loads issue up front)
+                        if (q < nb && B.par[q] == np && B.last[q] == u) d = q;   // prefix pi + u is beam entry q (canonical trie)
+                    if (d < MAXB) s_pe[d] = stamp + pi;    // at most one (prefix, token) pair lands on a given entry
                     if (d >= MAXB) {
                         const double prob = (double)tkv[ui];
                         const bool rep = (u == B.last[pi]);
@@ -244,130 +268,129 @@ prefix_beam_kernel(PbDev P) {
         }
         __syncthreads();
 
-        // ---- P2: unchanged prefixes: thread q replays its (<= 3) updates in the reference's loop order ----
-        if (tid < nb) {
-            const int q = tid;
-            const int lastq = B.last[q];
-            int ui_blank = -1, ui_last = -1;
-            for (int ui = 0; ui < beam; ++ui) {
-                const int u = tki[ui];
-                if (u == P.blank_id) ui_blank = ui;
-                else if (u == lastq) ui_last = ui;
-            }
-            double s = neg_inf(), ns = neg_inf(), vs = neg_inf(), vns = neg_inf();
-            int ts = -1, tns = -1, tns_new = 0, first = INT_MAX, any = 0;
-            if (ui_blank >= 0) {
-                const double prob = (double)tkv[ui_blank];
-                s = B.score[q] + prob;          // log_add(-inf, x)
-                vs = B.vit[q] + prob;
-                ts = B.times[q];
-                first = (ui_blank * nb + q) * 2;
-                any = 1;
-            }
-            if (ui_last >= 0) {
-                const double prob = (double)tkv[ui_last];
-                int pe = -1;  // parent prefix whose extension by last(q) lands on q
-                for (int pi = 0; pi < nb; ++pi)
-                    if (pi != q && dest[ui_last * MAXB + pi] == q) pe = pi;
-                bool cur_set = false;
-                // two possible events on ns, in prefix order: extension from pe, repeat from q itself
-                for (int ev = 0; ev < 2; ++ev) {
-                    const bool do_ext = (pe >= 0) && ((ev == 0) == (pe < q));
-                    const bool do_rep = (ev == 0) == !(pe >= 0 && pe < q);
-                    if (do_ext) {
-                        const bool rep = (lastq == B.last[pe]);
-                        ns = log_add2(ns, (rep ? B.s[pe] : B.score[pe]) + prob);
-                        const double y = (rep ? B.vs[pe] : B.vit[pe]) + prob;
-                        if (vns < y) {
-                            vns = y;
-                            cur_set = true;
-                            tns = rep ? B.ts[pe] : B.times[pe];
-                            tns_new = 1;
-                        }
-                        first = min(first, (ui_last * nb + pe) * 2 + (rep ? 1 : 0));
-                    } else if (do_rep) {
-                        ns = log_add2(ns, B.ns[q] + prob);
-                        const double y = B.vns[q] + prob;
-                        if (vns < y) {
-                            vns = y;
-                            if (!cur_set) {
+        // ---- P2 (warp 0 only) + P3: second beam prune = top-beam by (total desc, dict insertion order asc) ----
+        // Warp 0 owns the unchanged prefixes (slots 0..15) and the extensions by the best token (slots 16..31): it runs
+        // P2, ranks its own <= 2 nb candidates and publishes its beam-th best as THE pruning bound (a lower bound of the
+        // global beam-th best; with blank-dominated CTC posteriors it is nearly tight).  The other warps meanwhile
+        // load and key their slots; after the barrier they only compare against the bound.
+        unsigned long long my_key = 0ull;
+        int my_first = INT_MAX;
+        bool my_valid = false;
+        if (warp == 0) {
+            if (tid < nb) {
+                const int q = tid;
+                const int lastq = B.last[q];
+                const int stamp = (t + 1) * 32;
+                const int vb = s_ui_blank, vl = s_ui_last[q], vp = s_pe[q];
+                const int ui_blank = (vb >= stamp) ? vb - stamp : -1;
+                const int ui_last = (vl >= stamp) ? vl - stamp : -1;
+                double s = neg_inf(), ns = neg_inf(), vs = neg_inf(), vns = neg_inf();
+                int ts = -1, tns = -1, tns_new = 0, first = INT_MAX, any = 0;
+                if (ui_blank >= 0) {
+                    const double prob = (double)tkv[ui_blank];
+                    s = B.score[q] + prob;          // log_add(-inf, x)
+                    vs = B.vit[q] + prob;
+                    ts = B.times[q];
+                    first = (ui_blank * nb + q) * 2;
+                    any = 1;
+                }
+                if (ui_last >= 0) {
+                    const double prob = (double)tkv[ui_last];
+                    const int pe = (vp >= stamp) ? vp - stamp : -1;  // parent prefix whose extension by last(q) lands on q
+                    bool cur_set = false;
+                    // two possible events on ns, in prefix order: extension from pe, repeat from q itself
+                    for (int ev = 0; ev < 2; ++ev) {
+                        const bool do_ext = (pe >= 0) && ((ev == 0) == (pe < q));
+                        const bool do_rep = (ev == 0) == !(pe >= 0 && pe < q);
+                        if (do_ext) {
+                            const bool rep = (lastq == B.last[pe]);
+                            ns = log_add2(ns, (rep ? B.s[pe] : B.score[pe]) + prob);
+                            const double y = (rep ? B.vs[pe] : B.vit[pe]) + prob;
+                            if (vns < y) {
+                                vns = y;
                                 cur_set = true;
-                                // times_ns = prefix.times_ns.copy(); times_ns[-1] = t
-                                const int hd = B.tns[q];
-                                tns = (hd >= 0) ? time_prev[hd] : -1;
+                                tns = rep ? B.ts[pe] : B.times[pe];
                                 tns_new = 1;
                             }
+                            first = min(first, (ui_last * nb + pe) * 2 + (rep ? 1 : 0));
+                        } else if (do_rep) {
+                            ns = log_add2(ns, B.ns[q] + prob);
+                            const double y = B.vns[q] + prob;
+                            if (vns < y) {
+                                vns = y;
+                                if (!cur_set) {
+                                    cur_set = true;
+                                    // times_ns = prefix.times_ns.copy(); times_ns[-1] = t
+                                    const int hd = B.tns[q];
+                                    tns = (hd >= 0) ? time_prev[hd] : -1;
+                                    tns_new = 1;
+                                }
+                            }
+                            first = min(first, (ui_last * nb + q) * 2);
                         }
-                        first = min(first, (ui_last * nb + q) * 2);
                     }
+                    any = 1;
                 }
-                any = 1;
+                if (any) {
+                    C.s[q] = s;
+                    C.ns[q] = ns;
+                    C.vs[q] = vs;
+                    C.vns[q] = vns;
+                    C.ts[q] = ts;
+                    C.tns[q] = tns;
+                    C.tns_new[q] = tns_new;
+                    C.len[q] = B.len[q];
+                    C.last[q] = lastq;
+                    C.node[q] = B.node[q];
+                    C.par[q] = B.par[q];
+                    C.new_tok[q] = -1;
+                    C.first[q] = first;
+                    C.total[q] = log_add2(s, ns);
+                    C.valid[q] = t + 1;
+                }
             }
-            if (any) {
-                C.s[q] = s;
-                C.ns[q] = ns;
-                C.vs[q] = vs;
-                C.vns[q] = vns;
-                C.ts[q] = ts;
-                C.tns[q] = tns;
-                C.tns_new[q] = tns_new;
-                C.len[q] = B.len[q];
-                C.last[q] = lastq;
-                C.node[q] = B.node[q];
-                C.par[q] = B.par[q];
-                C.new_tok[q] = -1;
-                C.first[q] = first;
-                C.total[q] = log_add2(s, ns);
-                C.valid[q] = t + 1;
+            __syncwarp();
+            // compact view of warp 0's candidates: lane l < nb -> slot l, nb <= l < 2 nb -> slot 16 + (l - nb)
+            const int n0 = 2 * nb;
+            const int c = lane < nb ? lane : (MAXB + lane - nb);
+            my_valid = lane < n0 && C.valid[c] == t + 1;
+            if (my_valid) {
+                my_key = order_key(C.total[c]);
+                my_first = C.first[c];
             }
-        }
-        __syncthreads();
-
-        // ---- P3: second beam prune: stable sort by total desc == top-beam by (total, insertion order) ----
-        // (a) every slot-owning warp ranks its 32 slots; a slot outside its warp's top-beam cannot be in the global
-        //     top-beam; the warp's beam-th best is a lower bound of the global beam-th best
-        unsigned long long my_key = 0ull;
-        int my_first = INT_MAX, my_rank = 32;
-        bool my_valid = false;
-        if (warp < PB_SLOT_WARPS) {
-            const int c = tid;
+            const int rk = warp_rank(my_key, my_first, lane, n0);
+            const unsigned vm = __ballot_sync(0xffffffffu, my_valid);
+            const unsigned bm = __ballot_sync(0xffffffffu, my_valid && rk == beam - 1);
+            if (lane == 0) {
+                warp_valid[0] = __popc(vm);
+                if (!bm) thr_key[0] = 0ull, thr_first[0] = INT_MAX;   // fewer than beam candidates in warp 0: no bound
+            }
+            if (my_valid && rk == beam - 1) thr_key[0] = my_key, thr_first[0] = my_first;
+            if (my_valid && rk < beam) {   // warp 0's survivors
+                const int pos = atomicAdd(&n_surv, 1);
+                sv_key[pos] = my_key;
+                sv_first[pos] = my_first;
+                sv_slot[pos] = c;
+            }
+        } else {
+            const int c = tid;     // slots 32 .. ncs - 1
             my_valid = (c < ncs) && (C.valid[c] == t + 1);
             if (my_valid) {
                 my_key = order_key(C.total[c]);
                 my_first = C.first[c];
             }
             const unsigned vm = __ballot_sync(0xffffffffu, my_valid);
-            if (vm) {   // warp-uniform
-                my_rank = warp_rank(my_key, my_first, lane);
-                const unsigned bm = __ballot_sync(0xffffffffu, my_valid && my_rank == beam - 1);
-                if (lane == 0) {
-                    warp_valid[warp] = __popc(vm);
-                    if (!bm) thr_key[warp] = 0ull, thr_first[warp] = INT_MAX;   // fewer than beam candidates here: no bound
-                }
-                if (my_valid && my_rank == beam - 1) thr_key[warp] = my_key, thr_first[warp] = my_first;
-            } else if (lane == 0) {
-                warp_valid[warp] = 0;
-                thr_key[warp] = 0ull;
-                thr_first[warp] = INT_MAX;
-            }
+            if (lane == 0) warp_valid[warp] = __popc(vm);
         }
         __syncthreads();
-        // (b) survivors: inside their warp's top-beam and not below the best bound
-        if (warp < PB_SLOT_WARPS && my_valid && my_rank < beam) {
-            unsigned long long bk = 0ull;
-            int bf = INT_MAX;
-#pragma unroll
-            for (int w = 0; w < PB_SLOT_WARPS; ++w)
-                if (key_better(thr_key[w], thr_first[w], bk, bf)) bk = thr_key[w], bf = thr_first[w];
-            if (!key_better(bk, bf, my_key, my_first)) {
-                const int pos = atomicAdd(&n_surv, 1);
-                sv_key[pos] = my_key;
-                sv_first[pos] = my_first;
-                sv_slot[pos] = tid;
-            }
+        if (warp != 0 && my_valid && !key_better(thr_key[0], thr_first[0], my_key, my_first)) {
+            const int pos = atomicAdd(&n_surv, 1);
+            sv_key[pos] = my_key;
+            sv_first[pos] = my_first;
+            sv_slot[pos] = tid;
         }
         __syncthreads();
-        // (c) warp 0 ranks the survivors (any order in the list: the rank is a function of the keys only)
+        // warp 0 ranks the survivors (any order in the list: the rank is a function of the keys only)
         int nvalid = 0;
 #pragma unroll
         for (int w = 0; w < PB_SLOT_WARPS; ++w) nvalid += warp_valid[w];
@@ -377,7 +400,7 @@ prefix_beam_kernel(PbDev P) {
             if (nsv <= 32) {
                 const unsigned long long k = lane < nsv ? sv_key[lane] : 0ull;
                 const int f = lane < nsv ? sv_first[lane] : INT_MAX;
-                const int rk = warp_rank(k, f, lane);
+                const int rk = warp_rank(k, f, lane, nsv);
                 if (lane < nsv && rk < beam) rank_slot[rk] = sv_slot[lane];
             } else {
                 // many candidates tie with / exceed the bound: rank by counting over the list
@@ -395,18 +418,26 @@ prefix_beam_kernel(PbDev P) {
         // ---- P4: materialise the new beam ----
         Beam& NB = Bs[cur ^ 1];
         int new_node = -1, new_parent = -1;   // P4b: node this thread has to link into its parent's child list
+        {   // plain field copies, one (entry, field) per thread of warps 1..4 (warp 0 does the pointer work below)
+            const int r = tid & (MAXB - 1), fld = (tid >> 4) - 2;
+            if (fld >= 0 && fld < 7 && r < nnew) {
+                const int c = rank_slot[r];
+                switch (fld) {
+                    case 0: NB.s[r] = C.s[c]; break;
+                    case 1: NB.ns[r] = C.ns[c]; break;
+                    case 2: NB.vs[r] = C.vs[c]; break;
+                    case 3: NB.vns[r] = C.vns[c]; break;
+                    case 4: NB.score[r] = C.total[c]; break;
+                    case 5: NB.len[r] = C.len[c]; break;
+                    default: NB.last[r] = C.last[c]; break;
+                }
+            }
+        }
         if (tid < nnew) {
             const int r = tid;
             const int c = rank_slot[r];
             const int pool_i = t * beam + r;
             const double vs = C.vs[c], vns = C.vns[c];
-            NB.s[r] = C.s[c];
-            NB.ns[r] = C.ns[c];
-            NB.vs[r] = vs;
-            NB.vns[r] = vns;
-            NB.score[r] = C.total[c];
-            NB.len[r] = C.len[c];
-            NB.last[r] = C.last[c];
             const int tok = C.new_tok[c];
             if (tok >= 0) {
                 // canonical node of (parent, tok): reuse the parent's existing child if the string was in a beam before
