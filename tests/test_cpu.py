@@ -301,3 +301,34 @@ def test_lazy_decode_result_matches_eager_fields():
     assert c.nbest[2] == (8, 8, 8, 8)
     p = pickle.loads(pickle.dumps(LazyDecodeResult(-1.0, [-1.0], toks, times, lens, best=2)))
     assert p.tokens == (8, 8, 8, 8)
+
+
+def test_ingest_batch_plan_and_wav_reader(tmp_path):
+    """wenet_b200.ingest host logic: every utterance lands in exactly one batch, batches respect the padded-seconds
+    budget and the size limit, longest first; the wav reader returns the file's int16 samples."""
+    import wave
+    from wenet_b200 import ingest
+    rs = np.random.default_rng(3)
+    ns = [int(x) for x in rs.integers(16000 * 2, 16000 * 30, size=300)]
+    bs = ingest.plan_batches(ns, max_batch_seconds=600.0, max_batch_size=64)
+    flat = [i for b in bs for i in b]
+    assert sorted(flat) == list(range(len(ns)))
+    prev_longest = None
+    for b in bs:
+        longest = max(ns[i] for i in b)
+        assert len(b) <= 64 and (len(b) == 1 or len(b) * longest <= 600 * 16000)
+        assert longest == ns[b[0]]                      # sorted by length inside and across batches
+        assert prev_longest is None or longest <= prev_longest
+        prev_longest = longest
+    assert ingest.plan_batches([5, 5, 5], max_batch_seconds=1e9, max_batch_size=2) == [[0, 1], [2]]
+    pcm = synth.synth_pcm(1, 12345, seed=SEED)[0, :12345].numpy()
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(16000)
+        w.writeframes(pcm.astype("<i2").tobytes())
+    assert ingest.wav_num_samples(path) == 12345
+    assert np.array_equal(ingest.read_wav_int16(path), pcm)
+    with pytest.raises(ValueError):
+        ingest.read_wav_int16(path, sample_rate=8000)

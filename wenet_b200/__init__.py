@@ -22,6 +22,7 @@ def __getattr__(name):
         "StreamingSession": ("asr_model", "StreamingSession"),
         "DecodeResult": ("search", "DecodeResult"),
         "install": ("plugin", "install"),
+        "transcribe_files": ("ingest", "transcribe_files"),
         "DeviceModel": ("weights", "DeviceModel"),
         "ModelSpec": ("weights", "ModelSpec"),
     }

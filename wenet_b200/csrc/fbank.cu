@@ -34,6 +34,9 @@ struct FbankDev {
     const int* mel_len;
     const int* mel_off;
     const float* mel_w;
+    const int* tap_km;
+    const float* tap_w;
+    int taps_per_lane;
     int num_mel, frame_len, frame_shift, nfft;
     float preemph;
 };
@@ -298,7 +301,16 @@ fbank512_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, con
     const int pcm_bytes = (span * (int)sizeof(T) + 15) & ~15;
     float2* s_t1 = reinterpret_cast<float2*>(smem_raw + 16 + pcm_bytes) + warp * (F5_WARP_FLOATS / 2);
     float2* s_t2 = s_t1 + F5_T1;
-    float* s_pow = reinterpret_cast<float*>(s_t2);   // the power spectrum reuses T2 once stage C has read it
+    float* s_pow = reinterpret_cast<float*>(s_t2);   // the power spectrum reuses T2 once stage C has read it (264 floats)
+    float* s_mel = s_pow + 288;                       // mel accumulators of this warp's frame (<= 288 floats of T2 remain)
+    // CTA-wide: the tap list, staged once
+    const int n_taps = 32 * P.taps_per_lane;
+    int* s_tap_km = reinterpret_cast<int*>(smem_raw + 16 + pcm_bytes + (F5_THREADS / 32) * F5_WARP_FLOATS * (int)sizeof(float));
+    float* s_tap_w = reinterpret_cast<float*>(s_tap_km + n_taps);
+    for (int i = threadIdx.x; i < n_taps; i += F5_THREADS) {
+        s_tap_km[i] = __ldg(P.tap_km + i);
+        s_tap_w[i] = __ldg(P.tap_w + i);
+    }
 
     const int nf_here = min(F5_FR, n_frames - f0);
     const int need = (nf_here - 1) * shift + flen;
@@ -426,14 +438,31 @@ fbank512_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, con
             }
         }
         __syncwarp();
-        // 5. mel + log (kaldi.py:620-633)
-        for (int m = lane; m < P.num_mel; m += 32) {
-            const int st = __ldg(P.mel_start + m), ln = __ldg(P.mel_len + m);
-            const float* w = P.mel_w + __ldg(P.mel_off + m);
+        // 5. mel + log (kaldi.py:620-633).  The ~2 x 257 non-zero filter weights form a mel-major tap list; every lane
+        //    accumulates the same number of consecutive taps (the triangles of the upper bins are 8 x wider than those of
+        //    the lower ones: one-bin-per-lane loops would run 45 iterations on some lanes and 15 on others) and adds its
+        //    per-bin partial sums to the shared accumulators.
+        for (int m = lane; m < P.num_mel; m += 32) s_mel[m] = 0.f;
+        __syncwarp();
+        {
+            const int* km = s_tap_km + lane * P.taps_per_lane;
+            const float* tw = s_tap_w + lane * P.taps_per_lane;
+            int cur = km[0] >> 16;
             float e = 0.f;
-            for (int i = 0; i < ln; ++i) e = fmaf(s_pow[st + i], __ldg(w + i), e);
-            orow[m] = logf(fmaxf(e, 1.1920928955078125e-07f));
+            for (int i = 0; i < P.taps_per_lane; ++i) {
+                const int v = km[i];
+                const int m = v >> 16;
+                if (m != cur) {
+                    atomicAdd(s_mel + cur, e);
+                    cur = m;
+                    e = 0.f;
+                }
+                e = fmaf(s_pow[v & 0xffff], tw[i], e);
+            }
+            atomicAdd(s_mel + cur, e);
         }
+        __syncwarp();
+        for (int m = lane; m < P.num_mel; m += 32) orow[m] = logf(fmaxf(s_mel[m], 1.1920928955078125e-07f));
         __syncwarp();
     }
 }
@@ -487,6 +516,21 @@ int fbank_plan_create(FbankPlan** out, int sample_rate, int num_mel, int frame_l
     }
     if (w.empty()) w.push_back(0.f);
     p->mel_nnz = (int)w.size();
+    // balanced tap list (mel-major): lane l of fbank512_kernel owns taps [l * tpl, (l + 1) * tpl)
+    std::vector<int> tkm;
+    std::vector<float> tw_;
+    for (int m = 0; m < num_mel; ++m)
+        for (int i = 0; i < ln[m]; ++i) {
+            tkm.push_back((m << 16) | (st[m] + i));
+            tw_.push_back(w[off[m] + i]);
+        }
+    int tpl = ((int)tkm.size() + 31) / 32;
+    if ((tpl & 1) == 0) ++tpl;     // odd stride: lane-strided reads of the staged list hit 32 different banks
+    while ((int)tkm.size() < 32 * tpl) {
+        tkm.push_back(((num_mel - 1) << 16) | 0);
+        tw_.push_back(0.f);
+    }
+    p->taps_per_lane = tpl;
 #define WB_UP(dst, vec, T)                                                                       \
     WB_CHECK_CUDA(cudaMalloc((void**)&dst, (vec).size() * sizeof(T)));                             \
     WB_CHECK_CUDA(cudaMemcpy(dst, (vec).data(), (vec).size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -498,6 +542,8 @@ int fbank_plan_create(FbankPlan** out, int sample_rate, int num_mel, int frame_l
     WB_UP(p->mel_len, ln, int);
     WB_UP(p->mel_off, off, int);
     WB_UP(p->mel_w, w, float);
+    WB_UP(p->tap_km, tkm, int);
+    WB_UP(p->tap_w, tw_, float);
 #undef WB_UP
     *out = p;
     return WB_OK;
@@ -512,6 +558,8 @@ void fbank_plan_destroy(FbankPlan* p) {
     cudaFree(p->mel_len);
     cudaFree(p->mel_off);
     cudaFree(p->mel_w);
+    cudaFree(p->tap_km);
+    cudaFree(p->tap_w);
     delete p;
 }
 
@@ -528,6 +576,9 @@ int fbank_forward(const FbankPlan* plan, const void* pcm, int is_int16, long lon
     P.mel_len = plan->mel_len;
     P.mel_off = plan->mel_off;
     P.mel_w = plan->mel_w;
+    P.tap_km = plan->tap_km;
+    P.tap_w = plan->tap_w;
+    P.taps_per_lane = plan->taps_per_lane;
     P.num_mel = plan->num_mel;
     P.frame_len = plan->frame_len;
     P.frame_shift = plan->frame_shift;
@@ -538,10 +589,11 @@ int fbank_forward(const FbankPlan* plan, const void* pcm, int is_int16, long lon
                   (double)batch * ((double)max_frames * plan->frame_shift * esz + (double)max_frames * plan->num_mel * 4.0));
     // the recipes' front-end (512-point FFT, even hop so that sample pairs stay aligned): register-resident kernel
     static const bool no_fast = getenv("WB_FBANK_GENERIC") != nullptr;
-    if (plan->nfft == 512 && plan->frame_shift % 2 == 0 && plan->frame_len > 256 && !no_fast) {
+    if (plan->nfft == 512 && plan->frame_shift % 2 == 0 && plan->frame_len > 256 && plan->num_mel <= 288 && !no_fast) {
         const int span = (F5_FR - 1) * plan->frame_shift + plan->frame_len;
         const int pcm_bytes = (span * esz + 15) & ~15;
-        const size_t smem = 16 + pcm_bytes + (size_t)(F5_THREADS / 32) * F5_WARP_FLOATS * sizeof(float);
+        const size_t smem = 16 + pcm_bytes + (size_t)(F5_THREADS / 32) * F5_WARP_FLOATS * sizeof(float) +
+                            (size_t)32 * plan->taps_per_lane * 8;
         dim3 grid(ceil_div(max_frames, F5_FR), batch);
         if (is_int16) {
             if (smem > 48 * 1024)

@@ -109,7 +109,7 @@ class ModelSpec:
         if dec.get("activation_type", "relu") != "relu" or dec.get("input_layer", "embed") != "embed" \
                 or not dec.get("normalize_before", True) or dec.get("tie_word_embedding", False):
             raise NotImplementedError("decoder_conf outside the implemented set (relu / embed / pre-norm / untied)")
-        if self.d_model != self.dec_heads * 64:
+        if self.vocab > 0 and self.d_model != self.dec_heads * 64:      # (vocab 0: encoder-only handle, no decoder at all)
             raise NotImplementedError("decoder head size must be 64")
         st = (configs.get("tokenizer_conf") or {}).get("special_tokens") or {}
         self.sos = int(st.get("<sos>", self.vocab - 1))         # asr_model.py:60-63
