@@ -215,6 +215,29 @@ int wb_ctc_prefix_beam_search(const float* topk_val_dev, const int32_t* topk_idx
                               int32_t* nhyp_dev, void* workspace_dev, size_t workspace_bytes,
                               wb_stream_t stream);
 
+/* D2 with context biasing - replaces ctc_prefix_beam_search(..., context_graph) (search.py:127-249 incl. :171-173,
+ *     :200-203, :229-234) with wenet/utils/context_graph.py:212-265 walked inside the kernel.  The graph is the
+ *     reference's Aho-Corasick trie flattened by the host (wenet_b200/context.py): node 0 = root (token -1), children of
+ *     node n = entries [child_off[n], child_off[n+1]) of (child_tok, child_node) sorted by token, fail arcs, and the
+ *     per-node token / node / output scores as doubles.  All pointers are DEVICE pointers.  cg == NULL or
+ *     num_nodes == 0: identical to wb_ctc_prefix_beam_search.  scores_dev then holds total_score() after finalize(). */
+typedef struct {
+  int32_t num_nodes;
+  const int32_t* child_off;   /* [num_nodes + 1] */
+  const int32_t* child_tok;   /* [num_edges] */
+  const int32_t* child_node;  /* [num_edges] */
+  const int32_t* fail;        /* [num_nodes] */
+  const int32_t* token;       /* [num_nodes] */
+  const double* node_score;   /* [num_nodes] */
+  const double* token_score;  /* [num_nodes] */
+  const double* output_score; /* [num_nodes] */
+} wb_context_graph;
+int wb_ctc_prefix_beam_search_ctx(const float* topk_val_dev, const int32_t* topk_idx_dev, int topk,
+                                  const int32_t* seq_start_dev, const int32_t* seq_len_dev, int batch, int beam,
+                                  int blank_id, int max_len, const wb_context_graph* cg, int32_t* tokens_dev,
+                                  int32_t* times_dev, int32_t* lens_dev, double* scores_dev, int32_t* nhyp_dev,
+                                  void* workspace_dev, size_t workspace_bytes, wb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * E. attention rescoring — replaces attention_rescoring (search.py:374-458) and
  *    ASRModel.forward_attention_decoder (asr_model.py:453-547): (Bi)TransformerDecoder over all

@@ -335,12 +335,14 @@ def ctc_greedy_search(ctc_probs: torch.Tensor, ctc_lens: torch.Tensor, blank_id:
 
 
 class _PS:
-    __slots__ = ("s", "ns", "v_s", "v_ns", "cur_token_prob", "times_s", "times_ns")
+    """PrefixScore, search.py:64-106 (context fields :76-78, :91-106)."""
 
-    def __init__(self, s=-float("inf"), ns=-float("inf"), v_s=-float("inf"), v_ns=-float("inf")):
+    def __init__(self, s=-float("inf"), ns=-float("inf"), v_s=-float("inf"), v_ns=-float("inf"), context_state=0,
+                 context_score=0.0):
         self.s, self.ns, self.v_s, self.v_ns = s, ns, v_s, v_ns
         self.cur_token_prob = -float("inf")
         self.times_s, self.times_ns = [], []
+        self.context_state, self.context_score, self.has_context = context_state, context_score, False
 
     def score(self):
         return log_add(self.s, self.ns)
@@ -351,15 +353,50 @@ class _PS:
     def times(self):
         return self.times_s if self.v_s > self.v_ns else self.times_ns
 
+    def total_score(self):
+        return self.score() + self.context_score
 
-def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens, beam_size: int, blank_id: int = 0):
-    """search.py:127-249 without context graph.  Returns per utterance a dict with nbest, nbest_scores,
-    nbest_times (lists, best first)."""
+
+def context_forward_one_step(cg, state: int, token: int):
+    """ContextGraph.forward_one_step (wenet/utils/context_graph.py:212-247) on a flattened graph
+    (wenet_b200.context.ContextArrays: children / fail arcs / scores by node index, root = 0)."""
+    c = cg.child(state, token)
+    if c >= 0:
+        node = c
+        score = float(cg.token_score[node])
+    else:
+        node = int(cg.fail[state])
+        while cg.child(node, token) < 0:
+            node = int(cg.fail[node])
+            if int(cg.token[node]) == -1:
+                break
+        c2 = cg.child(node, token)
+        if c2 >= 0:
+            node = c2
+        score = float(cg.node_score[node]) - float(cg.node_score[state])
+    return score + float(cg.output_score[node]), node
+
+
+def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens, beam_size: int, blank_id: int = 0, context=None):
+    """search.py:127-249.  `context`: None or a flattened context graph (the reference's ContextGraph restated on
+    arrays: update_context / copy_context :97-106, finalize context_graph.py:249-265 - NB the reference REPLACES the
+    accumulated context score by finalize()'s score at the end, search.py:229-234).  Returns per utterance a dict with
+    nbest, nbest_scores, nbest_times (lists, best first)."""
     results = []
     for i in range(ctc_probs.shape[0]):
         ctc_prob = ctc_probs[i]
         num_t = int(ctc_lens[i])
         cur_hyps = [(tuple(), _PS(s=0.0, ns=-float("inf"), v_s=0.0, v_ns=0.0))]
+
+        def copy_ctx(n, ps):
+            if context is not None and not n.has_context:
+                n.context_score, n.context_state, n.has_context = ps.context_score, ps.context_state, True
+
+        def update_ctx(n, ps, u):
+            if context is not None and not n.has_context:
+                sc, st = context_forward_one_step(context, ps.context_state, u)
+                n.context_score, n.context_state, n.has_context = ps.context_score + sc, st, True
+
         for t in range(num_t):
             logp = ctc_prob[t]
             next_hyps = defaultdict(_PS)
@@ -373,6 +410,7 @@ def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens, beam_size: int, bl
                         n.s = log_add(n.s, ps.score() + prob)
                         n.v_s = ps.viterbi_score() + prob
                         n.times_s = ps.times().copy()
+                        copy_ctx(n, ps)
                     elif u == last:
                         n1 = next_hyps[prefix]
                         n1.ns = log_add(n1.ns, ps.ns + prob)
@@ -382,6 +420,7 @@ def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens, beam_size: int, bl
                                 n1.cur_token_prob = prob
                                 n1.times_ns = ps.times_ns.copy()
                                 n1.times_ns[-1] = t
+                        copy_ctx(n1, ps)
                         n2 = next_hyps[prefix + (u,)]
                         n2.ns = log_add(n2.ns, ps.s + prob)
                         if n2.v_ns < ps.v_s + prob:
@@ -389,6 +428,7 @@ def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens, beam_size: int, bl
                             n2.cur_token_prob = prob
                             n2.times_ns = ps.times_s.copy()
                             n2.times_ns.append(t)
+                        update_ctx(n2, ps, u)
                     else:
                         n = next_hyps[prefix + (u,)]
                         n.ns = log_add(n.ns, ps.score() + prob)
@@ -397,10 +437,15 @@ def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens, beam_size: int, bl
                             n.cur_token_prob = prob
                             n.times_ns = ps.times().copy()
                             n.times_ns.append(t)
-            nxt = sorted(next_hyps.items(), key=lambda kv: kv[1].score(), reverse=True)
+                        update_ctx(n, ps, u)
+            nxt = sorted(next_hyps.items(), key=lambda kv: kv[1].total_score(), reverse=True)
             cur_hyps = nxt[:beam_size]
+        if context is not None:
+            for _, ps in cur_hyps:
+                ps.context_score = -float(context.node_score[ps.context_state])   # finalize(): replaces, not adds
+                ps.context_state = 0
         results.append(dict(nbest=[list(y[0]) for y in cur_hyps],
-                            nbest_scores=[y[1].score() for y in cur_hyps],
+                            nbest_scores=[y[1].total_score() for y in cur_hyps],
                             nbest_times=[list(y[1].times()) for y in cur_hyps]))
     return results
 

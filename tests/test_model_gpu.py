@@ -329,3 +329,39 @@ def test_rescoring_host_and_device_token_entry_points_agree(setup):
         assert np.array_equal(np.array(r.nbest_scores, np.float32), hs[h:h + n]), (b, r.nbest_scores, hs[h:h + n])
         assert tuple(r.tokens) == tuple(nbest[b][int(best[b])])
         h += n
+
+
+def test_decode_with_context_graph(setup):
+    """decode(context_graph=...): the Aho-Corasick biasing graph is walked inside the CUDA beam
+    search; ids / times exact and scores to 1e-9 against the (reference-pinned) oracle on the GPU path's own
+    log-probabilities; phrases are taken from the un-biased n-best so that they actually fire."""
+    from wenet_b200 import context as CX
+    name, cfg, sd, model, feats, lens, g = setup
+    beam = int(g["beam"])
+    el = g["enc_lens"].tolist()
+    out, _ = model.encoder(feats, lens.cuda(), -1, -1)
+    lp = model.ctc_logprobs(out).cpu()
+    plain = O.ctc_prefix_beam_search(lp, torch.tensor(el), beam)
+    phrases = []
+    for r in plain:
+        best = r["nbest"][0]
+        alt = r["nbest"][-1]
+        if len(best) >= 3:
+            phrases.append(best[1:4])
+        if len(alt) >= 2:
+            phrases.append(alt[-2:])
+            phrases.append(alt[:1] + alt[-1:])
+    phrases = [p for p in phrases if len(p) > 0] or [[3, 5]]
+    arr = CX.build(phrases, 3.0)
+    ref = O.ctc_prefix_beam_search(lp, torch.tensor(el), beam, 0, arr)
+    res = model.decode(["ctc_prefix_beam_search", "attention_rescoring"], feats, lens.cuda(), beam_size=beam, ctc_weight=0.5,
+                       reverse_weight=cfg["model_conf"].get("reverse_weight", 0.0), context_graph=arr)
+    changed = 0
+    for b in range(len(el)):
+        r = res["ctc_prefix_beam_search"][b]
+        assert [list(h) for h in r.nbest] == ref[b]["nbest"], ("nbest", b)
+        assert r.nbest_times == ref[b]["nbest_times"], ("times", b)
+        assert np.allclose(r.nbest_scores, ref[b]["nbest_scores"], rtol=1e-9, atol=1e-9)
+        changed += int(ref[b]["nbest"] != plain[b]["nbest"] or ref[b]["nbest_scores"] != plain[b]["nbest_scores"])
+    assert changed > 0, "the context graph did not influence any utterance"
+    assert len(res["attention_rescoring"]) == len(el)

@@ -170,3 +170,42 @@ def test_plugin_config_reconstruction_and_registry():
         plugin.uninstall()      # restore the registries for other tests in this process
     from wenet.models.transformer.asr_model import ASRModel
     assert im.WENET_MODEL_CLASSES["asr_model"] is ASRModel
+
+
+@needs_ref
+def test_context_graph_restated_vs_reference(tmp_path):
+    """Context biasing: wenet_b200.context.flatten / build reproduce the reference's
+    ContextGraph (context_graph.py:103-200), and the oracle's prefix beam search with the flattened graph equals the
+    reference's ctc_prefix_beam_search(..., context_graph) - prefixes, float64 scores (incl. the finalize() rule) and
+    times - while differing from the un-biased search."""
+    import numpy as np
+    shim.install()
+    from wenet.models.transformer.search import ctc_prefix_beam_search as ref_pbs
+    from wenet.utils.context_graph import ContextGraph
+    from wenet_b200 import context as CX
+    V = 30
+    sym = {"<blank>": 0, "<unk>": 1}
+    for i in range(2, V):
+        sym[chr(ord("a") + i - 2) if i < 28 else "z%d" % i] = i
+    words = ["abc", "bcd", "ab", "cdeab", "xyz", "qrs q"]
+    f = tmp_path / "ctx.txt"
+    f.write_text("\n".join(words) + "\n")
+    cg = ContextGraph(str(f), sym, None, 3.0)
+    arr = CX.flatten(cg)
+    arr2 = CX.build([[sym.get(c if c != " " else "▁", sym["<unk>"]) for c in w] for w in words], 3.0)
+    for n in ("child_off", "child_tok", "child_node", "fail", "token", "node_score", "token_score", "output_score"):
+        assert np.array_equal(getattr(arr, n), getattr(arr2, n)), n
+    torch.manual_seed(1)
+    T = 60
+    logits = torch.randn(3, T, V) * 2
+    logits[:, :, 0] += 2.0
+    lp = logits.log_softmax(-1)
+    lens = torch.tensor([T, 41, 7])
+    ref = ref_pbs(lp, lens, 6, cg, 0)
+    got = O.ctc_prefix_beam_search(lp, lens, 6, 0, arr)
+    plain = O.ctc_prefix_beam_search(lp, lens, 6, 0)
+    for a, b in zip(ref, got):
+        assert [list(x) for x in a.nbest] == b["nbest"]
+        assert a.nbest_scores == b["nbest_scores"]
+        assert a.nbest_times == b["nbest_times"]
+    assert any(g["nbest"] != p["nbest"] for g, p in zip(got, plain))

@@ -27,6 +27,11 @@ class WbModelConfig(C.Structure):
         "has_cmvn", "precise")] + [("ln_eps", C.c_float), ("dec_ln_eps", C.c_float)]
 
 
+class WbContextGraph(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "child_off", "child_tok", "child_node", "fail", "token", "node_score", "token_score", "output_score")]
+
+
 # name -> (restype, argtypes); mirrors include/wenet_b200.h one to one
 _PROTOS = {
     "wb_last_error": (C.c_char_p, []),
@@ -59,6 +64,8 @@ _PROTOS = {
     "wb_prefix_beam_workspace_bytes": (sz, [i32, i32, i32]),
     "wb_ctc_prefix_beam_search": (i32, [vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
                                          vp, sz, vp]),
+    "wb_ctc_prefix_beam_search_ctx": (i32, [vp, vp, i32, vp, vp, i32, i32, i32, i32, C.POINTER(WbContextGraph), vp, vp, vp,
+                                             vp, vp, vp, sz, vp]),
     "wb_rescoring_workspace_bytes": (sz, [vp, i64, i64]),
     "wb_attention_rescoring": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, f32,
                                       f32, vp, vp, vp, vp, vp, sz, vp]),

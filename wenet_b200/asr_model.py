@@ -424,8 +424,10 @@ class B200ASRModel:
                infos: Dict[str, List[str]] = None) -> Dict[str, List[DecodeResult]]:
         assert speech.shape[0] == speech_lengths.shape[0]
         assert decoding_chunk_size != 0
+        cg = None
         if context_graph is not None:
-            raise NotImplementedError("context_graph biasing is not implemented (SURVEY.md section 8f #3)")
+            from . import context as _ctx
+            cg = _ctx.flatten(context_graph)      # the reference's ContextGraph object, or ContextArrays
         if "attention" in methods:
             raise NotImplementedError("autoregressive 'attention' decoding is not implemented (section 8f #1)")
         with torch.cuda.device(self.device):
@@ -443,7 +445,7 @@ class B200ASRModel:
             if need_beam:
                 # device-resident pipeline: only the per-hypothesis lengths / scores cross to the host before the
                 # rescoring pass is enqueued; the Python result objects are built while the decoder runs
-                bd = self._prefix_beam_launch(eo, tv, ti, beam_size, blank_id)
+                bd = self._prefix_beam_launch(eo, tv, ti, beam_size, blank_id, cg)
                 meta = self._beam_meta(bd)
                 fetch = self._beam_fetch_async(bd, meta)
                 rs = None
@@ -497,7 +499,7 @@ class B200ASRModel:
         self.d2h_bytes += t.numel() * t.element_size()
         return dst.numpy().reshape(tuple(t.shape))
 
-    def _prefix_beam_launch(self, eo: _EncOut, tv, ti, beam_size: int, blank_id: int):
+    def _prefix_beam_launch(self, eo: _EncOut, tv, ti, beam_size: int, blank_id: int, cg=None):
         B = eo.seq_start.numel()
         max_len = max(eo.max_len, 1)
         lib = self._lib
@@ -510,9 +512,13 @@ class B200ASRModel:
         bd.nhyp = torch.zeros(B, device=self.device, dtype=torch.int32)
         wsb = lib.wb_prefix_beam_workspace_bytes(B, beam_size, max_len)
         ws = self._workspace(wsb, 1)
-        check(lib.wb_ctc_prefix_beam_search(ptr(tv), ptr(ti), tv.stride(0), ptr(eo.seq_start), ptr(eo.seq_len), B,
-                                            int(beam_size), int(blank_id), max_len, ptr(bd.toks), ptr(bd.times),
-                                            ptr(bd.lens), ptr(bd.scores), ptr(bd.nhyp), ptr(ws), wsb, cur_stream()),
+        cgs = None
+        if cg is not None:
+            from . import context as _ctx
+            cgs = C.byref(_ctx.to_device(cg, self.device))
+        check(lib.wb_ctc_prefix_beam_search_ctx(ptr(tv), ptr(ti), tv.stride(0), ptr(eo.seq_start), ptr(eo.seq_len), B,
+                                                int(beam_size), int(blank_id), max_len, cgs, ptr(bd.toks), ptr(bd.times),
+                                                ptr(bd.lens), ptr(bd.scores), ptr(bd.nhyp), ptr(ws), wsb, cur_stream()),
               "wb_ctc_prefix_beam_search")
         return bd
 

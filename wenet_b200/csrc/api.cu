@@ -301,7 +301,28 @@ int wb_ctc_prefix_beam_search(const float* topk_val_dev, const int32_t* topk_idx
                               int blank_id, int max_len, int32_t* tokens_dev, int32_t* times_dev, int32_t* lens_dev,
                               double* scores_dev, int32_t* nhyp_dev, void* workspace_dev, size_t workspace_bytes,
                               wb_stream_t stream) {
+    return wb_ctc_prefix_beam_search_ctx(topk_val_dev, topk_idx_dev, topk, seq_start_dev, seq_len_dev, batch, beam, blank_id,
+                                         max_len, nullptr, tokens_dev, times_dev, lens_dev, scores_dev, nhyp_dev,
+                                         workspace_dev, workspace_bytes, stream);
+}
+
+int wb_ctc_prefix_beam_search_ctx(const float* topk_val_dev, const int32_t* topk_idx_dev, int topk,
+                                  const int32_t* seq_start_dev, const int32_t* seq_len_dev, int batch, int beam,
+                                  int blank_id, int max_len, const wb_context_graph* cg, int32_t* tokens_dev,
+                                  int32_t* times_dev, int32_t* lens_dev, double* scores_dev, int32_t* nhyp_dev,
+                                  void* workspace_dev, size_t workspace_bytes, wb_stream_t stream) {
     PrefixBeamArgs a;
+    if (cg != nullptr && cg->num_nodes > 0) {
+        a.cg_nodes = cg->num_nodes;
+        a.cg_child_off = cg->child_off;
+        a.cg_child_tok = cg->child_tok;
+        a.cg_child_node = cg->child_node;
+        a.cg_fail = cg->fail;
+        a.cg_token = cg->token;
+        a.cg_node_score = cg->node_score;
+        a.cg_token_score = cg->token_score;
+        a.cg_output_score = cg->output_score;
+    }
     a.topk_val = topk_val_dev;
     a.topk_idx = topk_idx_dev;
     a.topk = topk;

@@ -303,14 +303,6 @@ fbank512_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, con
     float2* s_t2 = s_t1 + F5_T1;
     float* s_pow = reinterpret_cast<float*>(s_t2);   // the power spectrum reuses T2 once stage C has read it (264 floats)
     float* s_mel = s_pow + 288;                       // mel accumulators of this warp's frame (<= 288 floats of T2 remain)
-    // CTA-wide: the tap list, staged once
-    const int n_taps = 32 * P.taps_per_lane;
-    int* s_tap_km = reinterpret_cast<int*>(smem_raw + 16 + pcm_bytes + (F5_THREADS / 32) * F5_WARP_FLOATS * (int)sizeof(float));
-    float* s_tap_w = reinterpret_cast<float*>(s_tap_km + n_taps);
-    for (int i = threadIdx.x; i < n_taps; i += F5_THREADS) {
-        s_tap_km[i] = __ldg(P.tap_km + i);
-        s_tap_w[i] = __ldg(P.tap_w + i);
-    }
 
     const int nf_here = min(F5_FR, n_frames - f0);
     const int need = (nf_here - 1) * shift + flen;
@@ -445,19 +437,22 @@ fbank512_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, con
         for (int m = lane; m < P.num_mel; m += 32) s_mel[m] = 0.f;
         __syncwarp();
         {
-            const int* km = s_tap_km + lane * P.taps_per_lane;
-            const float* tw = s_tap_w + lane * P.taps_per_lane;
-            int cur = km[0] >> 16;
+            // taps are stored [tap i][lane]: one coalesced 128-byte read-only load per i (L1-resident after the first frame)
+            const int* km = P.tap_km + lane;
+            const float* tw = P.tap_w + lane;
+            int cur = __ldg(km) >> 16;
             float e = 0.f;
+#pragma unroll 4
             for (int i = 0; i < P.taps_per_lane; ++i) {
-                const int v = km[i];
+                const int v = __ldg(km + 32 * i);
+                const float w = __ldg(tw + 32 * i);
                 const int m = v >> 16;
                 if (m != cur) {
                     atomicAdd(s_mel + cur, e);
                     cur = m;
                     e = 0.f;
                 }
-                e = fmaf(s_pow[v & 0xffff], tw[i], e);
+                e = fmaf(s_pow[v & 0xffff], w, e);
             }
             atomicAdd(s_mel + cur, e);
         }
@@ -525,12 +520,22 @@ int fbank_plan_create(FbankPlan** out, int sample_rate, int num_mel, int frame_l
             tw_.push_back(w[off[m] + i]);
         }
     int tpl = ((int)tkm.size() + 31) / 32;
-    if ((tpl & 1) == 0) ++tpl;     // odd stride: lane-strided reads of the staged list hit 32 different banks
     while ((int)tkm.size() < 32 * tpl) {
         tkm.push_back(((num_mel - 1) << 16) | 0);
         tw_.push_back(0.f);
     }
     p->taps_per_lane = tpl;
+    {   // lane-major [lane][tap] -> device layout [tap][lane]
+        std::vector<int> a(tkm.size());
+        std::vector<float> b(tw_.size());
+        for (int l = 0; l < 32; ++l)
+            for (int i = 0; i < tpl; ++i) {
+                a[(size_t)i * 32 + l] = tkm[(size_t)l * tpl + i];
+                b[(size_t)i * 32 + l] = tw_[(size_t)l * tpl + i];
+            }
+        tkm.swap(a);
+        tw_.swap(b);
+    }
 #define WB_UP(dst, vec, T)                                                                       \
     WB_CHECK_CUDA(cudaMalloc((void**)&dst, (vec).size() * sizeof(T)));                             \
     WB_CHECK_CUDA(cudaMemcpy(dst, (vec).data(), (vec).size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -592,8 +597,7 @@ int fbank_forward(const FbankPlan* plan, const void* pcm, int is_int16, long lon
     if (plan->nfft == 512 && plan->frame_shift % 2 == 0 && plan->frame_len > 256 && plan->num_mel <= 288 && !no_fast) {
         const int span = (F5_FR - 1) * plan->frame_shift + plan->frame_len;
         const int pcm_bytes = (span * esz + 15) & ~15;
-        const size_t smem = 16 + pcm_bytes + (size_t)(F5_THREADS / 32) * F5_WARP_FLOATS * sizeof(float) +
-                            (size_t)32 * plan->taps_per_lane * 8;
+        const size_t smem = 16 + pcm_bytes + (size_t)(F5_THREADS / 32) * F5_WARP_FLOATS * sizeof(float);
         dim3 grid(ceil_div(max_frames, F5_FR), batch);
         if (is_int16) {
             if (smem > 48 * 1024)

@@ -180,6 +180,11 @@ struct PrefixBeamArgs {
     double* out_scores;  // [batch, beam]   log_add(s, ns)
     int* out_nhyp;       // [batch]
     void* workspace; size_t workspace_bytes;
+    // optional context graph (cg_nodes == 0: none); see include/wenet_b200.h wb_context_graph
+    int cg_nodes = 0;
+    const int* cg_child_off = nullptr; const int* cg_child_tok = nullptr; const int* cg_child_node = nullptr;
+    const int* cg_fail = nullptr; const int* cg_token = nullptr;
+    const double* cg_node_score = nullptr; const double* cg_token_score = nullptr; const double* cg_output_score = nullptr;
 };
 size_t prefix_beam_workspace_bytes(int batch, int beam, int max_len);
 int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream);

@@ -79,6 +79,8 @@ struct Beam {
     double s[MAXB], ns[MAXB], vs[MAXB], vns[MAXB];
     double score[MAXB], vit[MAXB];
     int len[MAXB], last[MAXB], node[MAXB], par[MAXB], ts[MAXB], tns[MAXB], times[MAXB];
+    double ctx_score[MAXB];   // context-graph biasing (search.py:76-78): accumulated bonus and graph state
+    int ctx_state[MAXB];
     int n;
 };
 
@@ -93,6 +95,8 @@ struct Cand {
     int tns_new[NCAND];    // 1: times_ns = list(tns) + [t]
     int first[NCAND];      // first-touch sequence number == dict insertion order
     int valid[NCAND];      // frame stamp (t + 1)
+    double ctx_score[NCAND];
+    int ctx_state[NCAND];
 };
 
 struct PbDev {
@@ -108,7 +112,49 @@ struct PbDev {
     double* out_scores;
     int* out_nhyp;
     int* pool;  // per utterance: [6][max_len * beam] ints: trie parent, token, first child, next sibling; time prev, frame
+    // context graph (num_nodes == 0: no biasing): wenet/utils/context_graph.py flattened, node 0 = root
+    int cg_nodes;
+    const int* cg_child_off;
+    const int* cg_child_tok;
+    const int* cg_child_node;
+    const int* cg_fail;
+    const int* cg_token;
+    const double* cg_node_score;
+    const double* cg_token_score;
+    const double* cg_output_score;
 };
+
+// child of `node` labelled `token` (children are sorted by token), -1 if none
+__device__ __forceinline__ int cg_child(const PbDev& P, int node, int token) {
+    int lo = __ldg(P.cg_child_off + node), hi = __ldg(P.cg_child_off + node + 1);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int tk = __ldg(P.cg_child_tok + mid);
+        if (tk == token) return __ldg(P.cg_child_node + mid);
+        if (tk < token) lo = mid + 1;
+        else hi = mid;
+    }
+    return -1;
+}
+// ContextGraph.forward_one_step (context_graph.py:212-247): score of moving from `state` by `token`, and the new state
+__device__ __forceinline__ double cg_step(const PbDev& P, int state, int token, int* next_state) {
+    int node = cg_child(P, state, token);
+    double score;
+    if (node >= 0) {
+        score = __ldg(P.cg_token_score + node);
+    } else {
+        node = __ldg(P.cg_fail + state);
+        while (cg_child(P, node, token) < 0) {
+            node = __ldg(P.cg_fail + node);
+            if (__ldg(P.cg_token + node) == -1) break;   // root
+        }
+        const int c2 = cg_child(P, node, token);
+        if (c2 >= 0) node = c2;
+        score = __ldg(P.cg_node_score + node) - __ldg(P.cg_node_score + state);   // the score of the fail path
+    }
+    *next_state = node;
+    return score + __ldg(P.cg_output_score + node);
+}
 
 // order-preserving image of a double in the unsigned integers (-inf < ... < -0 == +0 < ... ; no NaNs occur)
 __device__ __forceinline__ unsigned long long order_key(double v) {
@@ -192,6 +238,8 @@ prefix_beam_kernel(PbDev P) {
         B.par[0] = -2;      // the root is nobody's child
         B.ts[0] = -1;
         B.tns[0] = -1;
+        B.ctx_score[0] = 0.0;
+        B.ctx_state[0] = 0;
         root_child = -1;
         n_surv = 0;
         s_ui_blank = 0;
@@ -260,6 +308,12 @@ prefix_beam_kernel(PbDev P) {
                         C.new_tok[d] = u;
                         C.first[d] = (ui * nb + pi) * 2 + (rep ? 1 : 0);
                         C.total[d] = nsv;  // log_add(-inf, ns)
+                        if (P.cg_nodes > 0) {   // update_context (search.py:101-106): the only touch of a new prefix
+                            int nst;
+                            const double sc = cg_step(P, B.ctx_state[pi], u, &nst);
+                            C.ctx_score[d] = B.ctx_score[pi] + sc;
+                            C.ctx_state[d] = nst;
+                        }
                         C.valid[d] = t + 1;   // frame stamp: no per-frame reset of the flags
                     }
                 }
@@ -346,6 +400,23 @@ prefix_beam_kernel(PbDev P) {
                     C.new_tok[q] = -1;
                     C.first[q] = first;
                     C.total[q] = log_add2(s, ns);
+                    if (P.cg_nodes > 0) {
+                        // `has_context`: the FIRST touch of next_hyps[prefix] fixes its context (search.py:171-173,
+                        // 200-203).  Touches by q itself (blank, repeat) copy q's context; the extension of its parent
+                        // pe by last(q) runs update_context(pe) - it is first iff its sequence number is the minimum.
+                        const int pe = (vp >= stamp) ? vp - stamp : -1;
+                        const bool rep_pe = pe >= 0 && lastq == B.last[pe];
+                        const int f_ext = pe >= 0 ? (ui_last * nb + pe) * 2 + (rep_pe ? 1 : 0) : INT_MAX;
+                        if (pe >= 0 && ui_last >= 0 && f_ext == first) {
+                            int nst;
+                            const double sc = cg_step(P, B.ctx_state[pe], lastq, &nst);
+                            C.ctx_score[q] = B.ctx_score[pe] + sc;
+                            C.ctx_state[q] = nst;
+                        } else {
+                            C.ctx_score[q] = B.ctx_score[q];
+                            C.ctx_state[q] = B.ctx_state[q];
+                        }
+                    }
                     C.valid[q] = t + 1;
                 }
             }
@@ -355,7 +426,7 @@ prefix_beam_kernel(PbDev P) {
             const int c = lane < nb ? lane : (MAXB + lane - nb);
             my_valid = lane < n0 && C.valid[c] == t + 1;
             if (my_valid) {
-                my_key = order_key(C.total[c]);
+                my_key = order_key(P.cg_nodes > 0 ? C.total[c] + C.ctx_score[c] : C.total[c]);   // total_score()
                 my_first = C.first[c];
             }
             const int rk = warp_rank(my_key, my_first, lane, n0);
@@ -376,7 +447,7 @@ prefix_beam_kernel(PbDev P) {
             const int c = tid;     // slots 32 .. ncs - 1
             my_valid = (c < ncs) && (C.valid[c] == t + 1);
             if (my_valid) {
-                my_key = order_key(C.total[c]);
+                my_key = order_key(P.cg_nodes > 0 ? C.total[c] + C.ctx_score[c] : C.total[c]);
                 my_first = C.first[c];
             }
             const unsigned vm = __ballot_sync(0xffffffffu, my_valid);
@@ -458,6 +529,10 @@ prefix_beam_kernel(PbDev P) {
                 NB.node[r] = C.node[c];
                 NB.par[r] = C.par[c];
             }
+            if (P.cg_nodes > 0) {
+                NB.ctx_score[r] = C.ctx_score[c];
+                NB.ctx_state[r] = C.ctx_state[c];
+            }
             const int tsv = C.ts[c];
             int tnsv;
             if (C.tns_new[c]) {
@@ -509,7 +584,10 @@ prefix_beam_kernel(PbDev P) {
         const long long o = ((long long)utt * beam + r) * P.max_len;
         const int ln = B.len[r];
         P.out_lens[utt * beam + r] = ln;
-        P.out_scores[utt * beam + r] = B.score[r];
+        // search.py:229-248: finalize() REPLACES the accumulated context score by the implicit fail arc to the root
+        // (-node_score of the final state); without a graph total_score() == score()
+        P.out_scores[utt * beam + r] =
+            P.cg_nodes > 0 ? B.score[r] + (-__ldg(P.cg_node_score + B.ctx_state[r])) : B.score[r];
         int node = B.node[r];
         for (int k = ln - 1; k >= 0 && node >= 0; --k) {
             P.out_tokens[o + k] = trie_tok[node];
@@ -555,6 +633,18 @@ int ctc_prefix_beam_search(const PrefixBeamArgs& a, cudaStream_t stream) {
     P.out_scores = a.out_scores;
     P.out_nhyp = a.out_nhyp;
     P.pool = reinterpret_cast<int*>(a.workspace);
+    P.cg_nodes = a.cg_nodes;
+    P.cg_child_off = a.cg_child_off;
+    P.cg_child_tok = a.cg_child_tok;
+    P.cg_child_node = a.cg_child_node;
+    P.cg_fail = a.cg_fail;
+    P.cg_token = a.cg_token;
+    P.cg_node_score = a.cg_node_score;
+    P.cg_token_score = a.cg_token_score;
+    P.cg_output_score = a.cg_output_score;
+    WB_REQUIRE(a.cg_nodes == 0 || (a.cg_child_off && a.cg_fail && a.cg_token && a.cg_node_score && a.cg_token_score &&
+                                   a.cg_output_score),
+               WB_ERR_BAD_ARG, "prefix beam search: incomplete context graph");
     WB_REQUIRE((long long)a.max_len * a.beam < 2147483647LL / 8, WB_ERR_UNSUPPORTED, "prefix beam search: pool too large");
     ProfScope _ps(PT_PREFIX_BEAM, stream, 0.0);
     prefix_beam_kernel<<<a.batch, PB_THREADS, 0, stream>>>(P);
