@@ -82,6 +82,57 @@ __global__ void cnn_cache_kernel(const float* __restrict__ cnn_cache, const floa
     }
 }
 
+// precise mode: the same concatenation with fp32 q / k / v (qkv fp32 [chunk][3d]) and fp32 kcat / vcat [key_size][d]
+__global__ void att_cache_concat_f32_kernel(const float* __restrict__ att_cache, int cache_t1, const float* __restrict__ qkv,
+                                            int chunk, int d, int H, float* __restrict__ kcat, float* __restrict__ vcat,
+                                            float* __restrict__ r_att, int nxt) {
+    const int key_size = cache_t1 + chunk;
+    const int total = key_size * d;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int j = i / d, c = i - j * d;
+        const int h = c >> 6, e = c & 63;
+        float kv, vv;
+        if (j < cache_t1) {
+            const float* src = att_cache + ((size_t)h * cache_t1 + j) * 128;
+            kv = src[e];
+            vv = src[64 + e];
+        } else {
+            const float* row = qkv + (size_t)(j - cache_t1) * 3 * d;
+            kv = row[d + c];
+            vv = row[2 * d + c];
+        }
+        kcat[i] = kv;
+        vcat[i] = vv;
+        if (j >= nxt) {
+            float* dst = r_att + ((size_t)h * (key_size - nxt) + (j - nxt)) * 128;
+            dst[e] = kv;
+            dst[64 + e] = vv;
+        }
+    }
+}
+
+// precise mode of cnn_cache_kernel: history rows of `acat` are written as [hi | lo | hi] (row pitch 3d)
+__global__ void cnn_cache_split3_kernel(const float* __restrict__ cnn_cache, const float* __restrict__ a_f32, int chunk,
+                                        int d, int lead, __nv_bfloat16* __restrict__ acat, float* __restrict__ r_cnn) {
+    const int total = lead * d;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / d, c = i - r * d;
+        const float old = cnn_cache ? cnn_cache[(size_t)c * lead + r] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(old);
+        __nv_bfloat16* o = acat + (size_t)r * 3 * d + c;
+        o[0] = hi;
+        o[d] = __float2bfloat16_rn(old - __bfloat162float(hi));
+        o[2 * d] = hi;
+        const int src = chunk + r;
+        float v;
+        if (src < lead)
+            v = cnn_cache ? cnn_cache[(size_t)c * lead + src] : 0.f;
+        else
+            v = a_f32[(size_t)(src - lead) * d + c];
+        r_cnn[(size_t)c * lead + r] = v;
+    }
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 inline int sub4_len(int T) { return T >= 7 ? ((T - 1) / 2 - 1) / 2 : 0; }
@@ -414,22 +465,24 @@ void chunk_plan(const Model* m, int T, int cache_t1, ChunkPlan* P) {
         o += align_up(bytes + 16);
         return at;
     };
+    const size_t p3 = c.precise ? 3 : 1;     // precise: bf16 activations are [hi | lo | hi]
+    const size_t kvb = c.precise ? 4 : 2;    // precise: q / k / v (and the concatenated history) stay fp32
     P->o_meta = take(256);
-    P->o_out1 = take((size_t)P->t1n * m->F1 * d * 2);
-    P->o_a2 = take((size_t)P->chunk * m->F2 * 9 * d * 2);
-    P->o_out2 = take((size_t)P->chunk * m->F2 * d * 2);
+    P->o_out1 = take((size_t)P->t1n * m->F1 * d * 2 * p3);
+    P->o_a2 = take((size_t)P->chunk * m->F2 * 9 * d * 2 * p3);
+    P->o_out2 = take((size_t)P->chunk * m->F2 * d * 2 * p3);
     P->o_x = take((size_t)P->chunk * d * 4);
-    P->o_acat = take((size_t)(P->lead + P->chunk) * d * 2);
+    P->o_acat = take((size_t)(P->lead + P->chunk) * d * 2 * p3);
     P->o_af32 = take((size_t)P->chunk * d * 4);
-    P->o_h = take((size_t)P->chunk * c.ffn_dim * 2);
-    P->o_qkv = take((size_t)P->chunk * 3 * d * 2);
-    P->o_kcat = take((size_t)P->key_size * d * 2);
-    P->o_vcat = take((size_t)P->key_size * d * 2);
+    P->o_h = take((size_t)P->chunk * c.ffn_dim * 2 * p3);
+    P->o_qkv = take((size_t)P->chunk * 3 * d * kvb);
+    P->o_kcat = take((size_t)P->key_size * d * kvb);
+    P->o_vcat = take((size_t)P->key_size * d * kvb);
     P->o_kp = take((size_t)P->key_size * d * 2);
     P->o_kbias = take((size_t)P->key_size * c.heads * 4);
-    P->o_ctx = take((size_t)P->chunk * d * 2);
-    P->o_g = take((size_t)(P->lead + P->chunk) * d * 2);
-    P->o_g2 = take((size_t)P->chunk * d * 2);
+    P->o_ctx = take((size_t)P->chunk * d * 2 * p3);
+    P->o_g = take((size_t)(P->lead + P->chunk) * d * 2 * p3);
+    P->o_g2 = take((size_t)P->chunk * d * 2 * p3);
     P->o_rowpos = take((size_t)P->key_size * 4);
     P->total = o + 256;
 }
@@ -454,7 +507,6 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
     const Model* m = reinterpret_cast<const Model*>(mm);
     WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "forward_chunk: model not finalized");
     WB_REQUIRE(xs_dev && y_dev && r_att_cache_dev && workspace_dev, WB_ERR_BAD_ARG, "forward_chunk: null argument");
-    WB_REQUIRE(m->cfg.precise == 0, WB_ERR_UNSUPPORTED, "forward_chunk: the precise (bf16x3) mode covers the full forward only");
     WB_REQUIRE(cache_t1 == 0 || att_cache_dev, WB_ERR_BAD_ARG, "forward_chunk: att_cache missing");
     cudaStream_t st = (cudaStream_t)stream;
     const wb_model_config& c = m->cfg;
@@ -496,11 +548,13 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
     void* out2 = ws + P.o_out2;
     float* x = reinterpret_cast<float*>(ws + P.o_x);
     __nv_bfloat16* acat = reinterpret_cast<__nv_bfloat16*>(ws + P.o_acat);
-    __nv_bfloat16* a = acat + (size_t)lead * d;   // LayerNorm output rows of this chunk
+    const int sp = c.precise ? 1 : 0, p3 = sp ? 3 : 1;      // precise mode: see wb_encoder_forward
+    const long long lda = (long long)d * p3, ldh = (long long)ff * p3;
+    __nv_bfloat16* a = acat + (size_t)lead * lda;   // LayerNorm output rows of this chunk
     float* af32 = reinterpret_cast<float*>(ws + P.o_af32);
     void* h = ws + P.o_h;
     void* qkv = ws + P.o_qkv;
-    __nv_bfloat16* kcat = reinterpret_cast<__nv_bfloat16*>(ws + P.o_kcat);
+    __nv_bfloat16* kcat = reinterpret_cast<__nv_bfloat16*>(ws + P.o_kcat);   // (fp32 buffers in precise mode)
     __nv_bfloat16* vcat = reinterpret_cast<__nv_bfloat16*>(ws + P.o_vcat);
     void* kp = ws + P.o_kp;
     float* kbias = reinterpret_cast<float*>(ws + P.o_kbias);
@@ -510,11 +564,11 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
     int* d_row_pos = reinterpret_cast<int*>(ws + P.o_rowpos);
 
     RC(subsample_conv1(xs_dev, 0, c.input_dim, d_t1n, d_zero64, 1, P.t1n, m->cmvn_mean, m->cmvn_istd, m->conv1_w,
-                       m->conv1_b, d, out1, 0, st));
-    RC(subsample_im2col(out1, d_zero64, d_chunk, d_zero64, 1, chunk, m->F1, m->F2, d, a2, 0, st));
-    RC(gemm_bf16(a2, 9 * d, &m->conv2.tmap, m->conv2.w, chunk * m->F2, d, 9 * d, m->conv2.b, EPI_BF16_RELU, 1.0f, out2,
-                 d, 0, st));
-    RC(gemm_bf16(out2, (long long)m->F2 * d, &m->embed_out.tmap, m->embed_out.w, chunk, d, m->F2 * d, m->embed_out.b,
+                       m->conv1_b, d, out1, sp, st));
+    RC(subsample_im2col(out1, d_zero64, d_chunk, d_zero64, 1, chunk, m->F1, m->F2, d * p3, a2, 0, st));
+    RC(gemm_bf16(a2, m->conv2.K, &m->conv2.tmap, m->conv2.w, chunk * m->F2, d, m->conv2.K, m->conv2.b, EPI_BF16_RELU, 1.0f,
+                 out2, d * p3, sp, st));
+    RC(gemm_bf16(out2, m->embed_out.K, &m->embed_out.tmap, m->embed_out.w, chunk, d, m->embed_out.K, m->embed_out.b,
                  EPI_F32, sqrtf((float)d), x, d, 0, st));
     RC(fill_row_pos(d_zero, d_key, 1, (offset_dev ? 0 : offset) - cache_t1, d_row_pos, key_size, st, offset_dev, c.max_pos));
     const float att_scale = 1.0f / sqrtf(64.0f);
@@ -522,57 +576,83 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
     const size_t cnn_l = (size_t)d * lead;
     for (int li = 0; li < c.enc_layers; ++li) {
         const EncLayer& L = m->layers[li];
-        if (li == 0) RC(layernorm_rows(x, d, chunk, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.ffm1.tmap, L.ffm1.w, chunk, ff, d, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
-        RC(gemm_bf16(h, ff, &L.ffm2.tmap, L.ffm2.w, chunk, d, ff, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
-        RC(layernorm_rows(x, d, chunk, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, chunk, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
-        att_cache_concat_kernel<<<ceil_div(key_size * d, 256), 256, 0, st>>>(
-            cache_t1 > 0 ? att_cache_dev + li * att_l : nullptr, cache_t1, reinterpret_cast<const __nv_bfloat16*>(qkv),
-            chunk, d, H, kcat, vcat, r_att_cache_dev + li * ratt_l, nxt);
-        count_launch();
-        WB_CHECK_LAUNCH();
-        RC(relpos_kprep(kcat, d, L.pos_proj, d_row_pos, L.pos_u, L.pos_v, key_size, H, kp, d, kbias, st));
-        {
-            AttnArgs A;
-            A.q = qkv; A.ldq = 3 * d; A.q_rows = chunk; A.q_col0 = 0;
-            A.k = kp; A.ldk = d; A.k_rows = key_size; A.k_col0 = 0;
-            A.v = vcat; A.ldv = d; A.v_rows = key_size; A.v_col0 = 0;
-            A.kbias = kbias; A.ld_kbias = H;
+        if (li == 0) RC(layernorm_rows(x, d, chunk, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        RC(gemm_bf16(a, lda, &L.ffm1.tmap, L.ffm1.w, chunk, ff, L.ffm1.K, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
+        RC(gemm_bf16(h, ldh, &L.ffm2.tmap, L.ffm2.w, chunk, d, L.ffm2.K, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        RC(layernorm_rows(x, d, chunk, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        if (sp) {
+            // precise: fp32 q / k / v, fp32 history, fp32 attention (precise.cu); the cache handed back is exact fp32
+            float* qf = reinterpret_cast<float*>(qkv);
+            float* kf = reinterpret_cast<float*>(kcat);
+            float* vf = reinterpret_cast<float*>(vcat);
+            RC(gemm_bf16(a, lda, &L.qkv.tmap, L.qkv.w, chunk, 3 * d, L.qkv.K, L.qkv.b, EPI_F32, 1.0f, qf, 3 * d, 0, st));
+            att_cache_concat_f32_kernel<<<ceil_div(key_size * d, 256), 256, 0, st>>>(
+                cache_t1 > 0 ? att_cache_dev + li * att_l : nullptr, cache_t1, qf, chunk, d, H, kf, vf,
+                r_att_cache_dev + li * ratt_l, nxt);
+            count_launch();
+            WB_CHECK_LAUNCH();
+            AttnF32Args A;
+            A.q = qf; A.ldq = 3 * d; A.k = kf; A.ldk = d; A.v = vf; A.ldv = d;
+            A.pos_proj = L.pos_proj; A.row_pos = d_row_pos; A.pos_u = L.pos_u; A.pos_v = L.pos_v;
             A.q_start = d_zero; A.q_len = d_chunk; A.k_start = d_zero; A.k_len = d_key;
             A.batch = 1; A.heads = H; A.max_q_len = chunk;
             A.chunk_size = 0; A.num_left_chunks = -1; A.scale = att_scale;   // att_mask is all-ones (encoder.py:243-247)
-            A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
-            RC(attention_forward(A, st));
+            A.out = ctx; A.ldo = lda; A.split3_out = 1;
+            RC(attention_f32(A, st));
+        } else {
+            RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, chunk, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
+            att_cache_concat_kernel<<<ceil_div(key_size * d, 256), 256, 0, st>>>(
+                cache_t1 > 0 ? att_cache_dev + li * att_l : nullptr, cache_t1, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                chunk, d, H, kcat, vcat, r_att_cache_dev + li * ratt_l, nxt);
+            count_launch();
+            WB_CHECK_LAUNCH();
+            RC(relpos_kprep(kcat, d, L.pos_proj, d_row_pos, L.pos_u, L.pos_v, key_size, H, kp, d, kbias, st));
+            {
+                AttnArgs A;
+                A.q = qkv; A.ldq = 3 * d; A.q_rows = chunk; A.q_col0 = 0;
+                A.k = kp; A.ldk = d; A.k_rows = key_size; A.k_col0 = 0;
+                A.v = vcat; A.ldv = d; A.v_rows = key_size; A.v_col0 = 0;
+                A.kbias = kbias; A.ld_kbias = H;
+                A.q_start = d_zero; A.q_len = d_chunk; A.k_start = d_zero; A.k_len = d_key;
+                A.batch = 1; A.heads = H; A.max_q_len = chunk;
+                A.chunk_size = 0; A.num_left_chunks = -1; A.scale = att_scale;   // att_mask is all-ones (encoder.py:243-247)
+                A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
+                RC(attention_forward(A, st));
+            }
         }
-        RC(gemm_bf16(ctx, d, &L.out.tmap, L.out.w, chunk, d, d, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(gemm_bf16(ctx, lda, &L.out.tmap, L.out.w, chunk, d, L.out.K, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // conv module with left-context cache (convolution.py:122-130)
-        RC(layernorm_rows(x, d, chunk, d, L.n_conv.g, L.n_conv.b, c.ln_eps, a, d, 0, af32, d, st));
+        RC(layernorm_rows(x, d, chunk, d, L.n_conv.g, L.n_conv.b, c.ln_eps, a, lda, sp, af32, d, st));
         if (lead > 0) {
-            cnn_cache_kernel<<<ceil_div(lead * d, 256), 256, 0, st>>>(cnn_cache_dev ? cnn_cache_dev + li * cnn_l : nullptr,
-                                                                      af32, chunk, d, lead, acat,
-                                                                      r_cnn_cache_dev + li * cnn_l);
+            if (sp)
+                cnn_cache_split3_kernel<<<ceil_div(lead * d, 256), 256, 0, st>>>(
+                    cnn_cache_dev ? cnn_cache_dev + li * cnn_l : nullptr, af32, chunk, d, lead, acat,
+                    r_cnn_cache_dev + li * cnn_l);
+            else
+                cnn_cache_kernel<<<ceil_div(lead * d, 256), 256, 0, st>>>(cnn_cache_dev ? cnn_cache_dev + li * cnn_l : nullptr,
+                                                                          af32, chunk, d, lead, acat,
+                                                                          r_cnn_cache_dev + li * cnn_l);
             count_launch();
             WB_CHECK_LAUNCH();
         }
-        RC(gemm_bf16(acat, d, &L.pw1.tmap, L.pw1.w, lead + chunk, 2 * d, d, L.pw1.b, EPI_GLU_BF16, 1.0f, g, d, 0, st));
+        RC(gemm_bf16(acat, lda, &L.pw1.tmap, L.pw1.w, lead + chunk, 2 * d, L.pw1.K, L.pw1.b, EPI_GLU_BF16, 1.0f, g, lda, sp, st));
         {
             DwConvArgs D;
-            D.g = g; D.ldg = d; D.seq_start = d_zero; D.seq_len = d_cin; D.out_start = d_zero;
+            D.g = g; D.ldg = lda; D.in_split3 = sp; D.seq_start = d_zero; D.seq_len = d_cin; D.out_start = d_zero;
             D.batch = 1; D.max_len = chunk; D.lead = lead; D.d = d; D.ksize = c.cnn_kernel;
             D.causal = c.cnn_causal; D.w = L.dw_w; D.bias = L.dw_b; D.norm_type = c.cnn_norm;
             D.gamma = L.n_cnn.g; D.beta = L.n_cnn.b; D.eps = c.ln_eps; D.pad_vec = L.pad_vec; D.pad_until = chunk;
-            D.out = g2; D.ldo = d; D.split3 = 0;
-            RC(dwconv_norm_silu(D, st));
+            D.out = g2; D.ldo = lda; D.split3 = sp;
+            RC(sp ? dwconv_norm_silu_f32(D, st) : dwconv_norm_silu(D, st));
         }
-        RC(gemm_bf16(g2, d, &L.pw2.tmap, L.pw2.w, chunk, d, d, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
-        RC(layernorm_rows(x, d, chunk, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, chunk, ff, d, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ff, 0, st));
-        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, chunk, d, ff, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        RC(gemm_bf16(g2, lda, &L.pw2.tmap, L.pw2.w, chunk, d, L.pw2.K, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(layernorm_rows(x, d, chunk, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        RC(gemm_bf16(a, lda, &L.ff1.tmap, L.ff1.w, chunk, ff, L.ff1.K, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
+        RC(gemm_bf16(h, ldh, &L.ff2.tmap, L.ff2.w, chunk, d, L.ff2.K, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
         // norm_final fused with the next layer's norm_ff_macaron, or (last layer) with after_norm
         if (li + 1 < c.enc_layers) {
             const EncLayer& Ln = m->layers[li + 1];
-            RC(layernorm2_rows(x, d, chunk, d, L.n_final.g, L.n_final.b, Ln.n_ffm.g, Ln.n_ffm.b, c.ln_eps, x, d, a, d, 0,
+            RC(layernorm2_rows(x, d, chunk, d, L.n_final.g, L.n_final.b, Ln.n_ffm.g, Ln.n_ffm.b, c.ln_eps, x, d, a, lda, sp,
                                nullptr, 0, st));
         } else {
             RC(layernorm2_rows(x, d, chunk, d, L.n_final.g, L.n_final.b, m->after.g, m->after.b, c.ln_eps, nullptr, 0,

@@ -302,7 +302,6 @@ fbank512_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, con
     float2* s_t1 = reinterpret_cast<float2*>(smem_raw + 16 + pcm_bytes) + warp * (F5_WARP_FLOATS / 2);
     float2* s_t2 = s_t1 + F5_T1;
     float* s_pow = reinterpret_cast<float*>(s_t2);   // the power spectrum reuses T2 once stage C has read it (264 floats)
-    float* s_mel = s_pow + 288;                       // mel accumulators of this warp's frame (<= 288 floats of T2 remain)
 
     const int nf_here = min(F5_FR, n_frames - f0);
     const int need = (nf_here - 1) * shift + flen;
@@ -430,34 +429,21 @@ fbank512_kernel(FbankDev P, const T* __restrict__ pcm, long long pcm_stride, con
             }
         }
         __syncwarp();
-        // 5. mel + log (kaldi.py:620-633).  The ~2 x 257 non-zero filter weights form a mel-major tap list; every lane
-        //    accumulates the same number of consecutive taps (the triangles of the upper bins are 8 x wider than those of
-        //    the lower ones: one-bin-per-lane loops would run 45 iterations on some lanes and 15 on others) and adds its
-        //    per-bin partial sums to the shared accumulators.
-        for (int m = lane; m < P.num_mel; m += 32) s_mel[m] = 0.f;
-        __syncwarp();
-        {
-            // taps are stored [tap i][lane]: one coalesced 128-byte read-only load per i (L1-resident after the first frame)
-            const int* km = P.tap_km + lane;
-            const float* tw = P.tap_w + lane;
-            int cur = __ldg(km) >> 16;
-            float e = 0.f;
+        // 5. mel + log (kaldi.py:620-633).  The triangles of the upper bins are 8 x wider than those of the lower ones, so
+        //    the bins are dealt to the lanes by a longest-first greedy partition made at plan creation (<= 4 bins per
+        //    lane, ~equal tap counts) instead of bin m -> lane m % 32.
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = __ldg(P.tap_km + lane * 4 + j);     // this lane's j-th mel bin or -1
+            if (m >= 0) {
+                const int st = __ldg(P.mel_start + m), ln = __ldg(P.mel_len + m);
+                const float* w = P.mel_w + __ldg(P.mel_off + m);
+                float e = 0.f;
 #pragma unroll 4
-            for (int i = 0; i < P.taps_per_lane; ++i) {
-                const int v = __ldg(km + 32 * i);
-                const float w = __ldg(tw + 32 * i);
-                const int m = v >> 16;
-                if (m != cur) {
-                    atomicAdd(s_mel + cur, e);
-                    cur = m;
-                    e = 0.f;
-                }
-                e = fmaf(s_pow[v & 0xffff], w, e);
+                for (int i = 0; i < ln; ++i) e = fmaf(s_pow[st + i], __ldg(w + i), e);
+                orow[m] = logf(fmaxf(e, 1.1920928955078125e-07f));
             }
-            atomicAdd(s_mel + cur, e);
         }
-        __syncwarp();
-        for (int m = lane; m < P.num_mel; m += 32) orow[m] = logf(fmaxf(s_mel[m], 1.1920928955078125e-07f));
         __syncwarp();
     }
 }
@@ -511,31 +497,25 @@ int fbank_plan_create(FbankPlan** out, int sample_rate, int num_mel, int frame_l
     }
     if (w.empty()) w.push_back(0.f);
     p->mel_nnz = (int)w.size();
-    // balanced tap list (mel-major): lane l of fbank512_kernel owns taps [l * tpl, (l + 1) * tpl)
-    std::vector<int> tkm;
-    std::vector<float> tw_;
-    for (int m = 0; m < num_mel; ++m)
-        for (int i = 0; i < ln[m]; ++i) {
-            tkm.push_back((m << 16) | (st[m] + i));
-            tw_.push_back(w[off[m] + i]);
+    // fbank512_kernel: mel bins dealt to the 32 lanes, longest filter first, always to the least loaded lane that still
+    // has a free slot (4 per lane): tap_km[lane * 4 + j] = j-th bin of the lane or -1
+    std::vector<int> tkm(32 * 4, -1);
+    std::vector<float> tw_(1, 0.f);
+    if (num_mel <= 128) {   // (the fast kernel is only dispatched for <= 128 bins)
+        std::vector<int> order(num_mel), load(32, 0), cnt(32, 0);
+        for (int m = 0; m < num_mel; ++m) order[m] = m;
+        for (int i = 0; i < num_mel; ++i)          // selection sort by length desc (num_mel is small)
+            for (int j = i + 1; j < num_mel; ++j)
+                if (ln[order[j]] > ln[order[i]]) std::swap(order[i], order[j]);
+        for (int i = 0; i < num_mel; ++i) {
+            int best = -1;
+            for (int l = 0; l < 32; ++l)
+                if (cnt[l] < 4 && (best < 0 || load[l] < load[best])) best = l;
+            tkm[best * 4 + cnt[best]++] = order[i];
+            load[best] += ln[order[i]] + 4;        // + fixed cost per bin (loads of start / len / off, log, store)
         }
-    int tpl = ((int)tkm.size() + 31) / 32;
-    while ((int)tkm.size() < 32 * tpl) {
-        tkm.push_back(((num_mel - 1) << 16) | 0);
-        tw_.push_back(0.f);
     }
-    p->taps_per_lane = tpl;
-    {   // lane-major [lane][tap] -> device layout [tap][lane]
-        std::vector<int> a(tkm.size());
-        std::vector<float> b(tw_.size());
-        for (int l = 0; l < 32; ++l)
-            for (int i = 0; i < tpl; ++i) {
-                a[(size_t)i * 32 + l] = tkm[(size_t)l * tpl + i];
-                b[(size_t)i * 32 + l] = tw_[(size_t)l * tpl + i];
-            }
-        tkm.swap(a);
-        tw_.swap(b);
-    }
+    p->taps_per_lane = 4;
 #define WB_UP(dst, vec, T)                                                                       \
     WB_CHECK_CUDA(cudaMalloc((void**)&dst, (vec).size() * sizeof(T)));                             \
     WB_CHECK_CUDA(cudaMemcpy(dst, (vec).data(), (vec).size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -594,7 +574,7 @@ int fbank_forward(const FbankPlan* plan, const void* pcm, int is_int16, long lon
                   (double)batch * ((double)max_frames * plan->frame_shift * esz + (double)max_frames * plan->num_mel * 4.0));
     // the recipes' front-end (512-point FFT, even hop so that sample pairs stay aligned): register-resident kernel
     static const bool no_fast = getenv("WB_FBANK_GENERIC") != nullptr;
-    if (plan->nfft == 512 && plan->frame_shift % 2 == 0 && plan->frame_len > 256 && plan->num_mel <= 288 && !no_fast) {
+    if (plan->nfft == 512 && plan->frame_shift % 2 == 0 && plan->frame_len > 256 && plan->num_mel <= 128 && !no_fast) {
         const int span = (F5_FR - 1) * plan->frame_shift + plan->frame_len;
         const int pcm_bytes = (span * esz + 15) & ~15;
         const size_t smem = 16 + pcm_bytes + (size_t)(F5_THREADS / 32) * F5_WARP_FLOATS * sizeof(float);

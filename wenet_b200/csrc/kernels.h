@@ -53,11 +53,10 @@ struct FbankPlan {  // device-resident constants, built once by fbank_plan_creat
     int* mel_len;       // [num_mel]
     int* mel_off;       // [num_mel] offset into mel_w
     float* mel_w;       // flat non-zero weights
-    // the same non-zero weights as a flat, mel-major "tap" list padded to 32 x taps_per_lane entries (fbank512_kernel:
-    // every lane accumulates the same number of taps; pad taps have weight 0 and point at mel bin num_mel - 1)
-    int* tap_km;        // (mel bin << 16) | fft bin
-    float* tap_w;
-    int taps_per_lane;
+    // fbank512_kernel: balanced assignment of mel bins to lanes: tap_km[lane * 4 + j] = j-th bin of the lane or -1
+    int* tap_km;
+    float* tap_w;       // (unused placeholder)
+    int taps_per_lane;  // 4
     int num_mel, frame_len, frame_shift, nfft, mel_nnz;
     float preemph;
 };
