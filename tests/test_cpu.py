@@ -332,3 +332,33 @@ def test_ingest_batch_plan_and_wav_reader(tmp_path):
     assert np.array_equal(ingest.read_wav_int16(path), pcm)
     with pytest.raises(ValueError):
         ingest.read_wav_int16(path, sample_rate=8000)
+
+
+def test_export_model_file_layout(tmp_path):
+    """wenet_b200.export writes what runtime/b200_asr_model.cc::Read parses: magic, the wb_model_config struct, sos / eos /
+    bidirectional / tensor count, then (name, dtype, numel, data) records."""
+    import ctypes as C
+    import struct
+    from wenet_b200._lib import WbModelConfig
+    from wenet_b200.export import MAGIC, export_model
+    cfg = synth.recipe("tiny")
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    path = str(tmp_path / "m.wbm")
+    n = export_model(cfg, sd, path)
+    raw = open(path, "rb").read()
+    assert raw[:8] == MAGIC
+    c = WbModelConfig.from_buffer_copy(raw[8:8 + C.sizeof(WbModelConfig)])
+    assert (c.d_model, c.heads, c.enc_layers, c.vocab, c.precise) == (128, 2, 2, 37, 0)
+    off = 8 + C.sizeof(WbModelConfig)
+    sos, eos, bi, cnt = struct.unpack_from("<4i", raw, off)
+    assert (sos, eos, bi, cnt) == (36, 36, 1, n)
+    off += 16
+    seen = 0
+    while off < len(raw):
+        ln, = struct.unpack_from("<i", raw, off)
+        name = raw[off + 4:off + 4 + ln].decode()
+        dt, numel = struct.unpack_from("<iq", raw, off + 4 + ln)
+        off += 4 + ln + 12 + numel * (2 if dt == 1 else 4)
+        seen += 1
+        assert name and numel > 0
+    assert seen == n and off == len(raw)

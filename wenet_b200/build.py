@@ -80,5 +80,31 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+def build_runtime(verbose: bool = True) -> str:
+    """The C++ AsrModel back-end over the C ABI (runtime/b200_asr_model.cc) and its command-line driver."""
+    root = os.path.join(HERE, "..", "runtime")
+    lib = os.path.join(HERE, "lib", "libwenet_b200_runtime.so")
+    exe = os.path.join(root, "b200_asr_main")
+    src = [os.path.join(root, "b200_asr_model.cc"), os.path.join(root, "b200_asr_model.h"),
+           os.path.join(HERE, "..", "include", "wenet_b200.h")]
+    newest = max(os.path.getmtime(p) for p in src + [os.path.join(root, "b200_asr_main.cc"), LIB])
+    if os.path.exists(lib) and os.path.exists(exe) and min(os.path.getmtime(lib), os.path.getmtime(exe)) >= newest:
+        return exe
+    cuda = os.path.dirname(os.path.dirname(NVCC))
+    common = ["g++", "-O2", "-std=c++17", "-fPIC", "-I" + os.path.join(cuda, "include")]
+    link = ["-L" + os.path.dirname(LIB), "-lwenet_b200", "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+            "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../wenet_b200/lib", "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+    cmds = [common + ["-shared", "-o", lib, src[0]] + link,
+            common + ["-o", exe, os.path.join(root, "b200_asr_main.cc"), src[0]] + link]
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("runtime build failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    if verbose:
+        print("[wenet_b200.build] built %s and %s" % (lib, exe), file=sys.stderr)
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_runtime())
