@@ -37,11 +37,15 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 
-template <int BN>
+// NC = CTAs per tile: 1, or 2 = a CTA pair (cluster of two) computing a 256 x BN tile with ONE tcgen05.mma.cta_group::2 per
+// k-step: each CTA holds its own 128 A rows and HALF of the B tile (and half of a resident weight panel), so a stage is
+// 32 KB instead of 48 KB (6 instead of 4 stages), every SM ingests half the B bytes per MMA, and the K <= 256
+// weight-stationary mode has room for an 8-slot A ring (two A tiles in flight) next to its 64 KB half panel.
+template <int BN, int NC = 1>
 struct GemmCfg {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kStages = (BN == 256) ? (NC == 2 ? 6 : 4) : 6;
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2 / NC;   // per CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator (power of two)
     // epilogue staging: 8 warps x (32 rows x 128 B), SWIZZLE_128B, read back by TMA stores
@@ -53,7 +57,7 @@ struct GemmCfg {
     // weight-stationary mode (K <= kResMaxKB * 64): the whole [BN x K] weight panel of the current n-tile
     // stays in shared memory while the CTA streams A tiles past it -> per tile only the 128 x K A tile is
     // fetched from L2 (the per-SM L2 path, ~80 GB/s, is what bounds the K = 256 GEMMs otherwise)
-    static constexpr int kResMaxKB = (BN == 256) ? 4 : 8;
+    static constexpr int kResMaxKB = (BN == 256) ? (NC == 2 ? 8 : 4) : 8;
     // the A ring takes whatever the resident panel of num_kb k-blocks leaves of the stage area (at most 8 slots: K = 256
     // gives 4 slots = ONE A tile with BN = 256 but 8 slots = TWO A tiles with BN = 128 - the depth that hides the
     // L2 -> SM latency of the next tile's A loads behind the current tile's MMAs)
@@ -110,13 +114,16 @@ __device__ unsigned long long g_gemm_diag[12];   // 8: epilogue tcgen05.ld wait,
 
 // EPI >= 0 fixes the epilogue at compile time (the kernel is ~150 KB of SASS with all six variants behind a runtime
 // switch and then stalls on instruction fetch); EPI = -1 keeps the runtime switch (BN = 128: small / test models only).
-template <int BN, bool BRES, int EPI>
+template <int BN, bool BRES, int EPI, int NC>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                     GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, NC>;
+    const int rank = (NC == 2) ? (int)cluster_ctarank() : 0;          // 0 = leader (issues the MMAs)
+    const int cta_id = (NC == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-schedule id of this CTA (pair)
+    const int num_ctas = (NC == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-B alignment
@@ -138,7 +145,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_mt = (NC == 2) ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;   // m-tiles of the schedule (pairs of 128-row tiles)
+    const int num_tiles = num_mt * p.num_n_tiles;
     const int epi = (EPI >= 0) ? EPI : p.epi;
     WB_DIAG(long long diag[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long cta_t0 = clock64();)
 
@@ -155,35 +163,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_init(b_empty, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 8);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[s], 8 * NC);  // one arrive per epilogue warp (of both CTAs of a pair, on the leader's)
         }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_holder, Cfg::kTmemCols);
-        tmem_relinquish();
+        if (NC == 2) {
+            tmem_alloc_pair(tmem_holder, Cfg::kTmemCols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_holder, Cfg::kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (NC == 2) cluster_sync_all();   // the peer's barriers must exist before anything is signalled across the pair
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     // tile schedule.  streaming mode: t = blockIdx.x + i * gridDim.x, n fastest.  weight-stationary mode: each
     // CTA owns a contiguous range of the n-major tile list, so its weight panel changes at most a few times.
-    const int per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
-    const int t_begin = BRES ? blockIdx.x * per_cta : blockIdx.x;
+    const int per_cta = (num_tiles + num_ctas - 1) / num_ctas;
+    const int t_begin = BRES ? cta_id * per_cta : cta_id;
     const int t_end = BRES ? min(num_tiles, t_begin + per_cta) : num_tiles;
-    const int t_step = BRES ? 1 : gridDim.x;
+    const int t_step = BRES ? 1 : num_ctas;
+    // (pair mode: this CTA's 128-row tile is 2 x (schedule m-tile) + rank; an odd last tile leaves the peer with rows past
+    //  M: its TMA loads are zero-filled and its stores clipped)
 #define WB_TILE_COORDS(t)                                                      \
-    const int n_tile = BRES ? (t) / p.num_m_tiles : (t) % p.num_n_tiles;      \
-    const int m_tile = BRES ? (t) % p.num_m_tiles : (t) / p.num_n_tiles;
+    const int n_tile = BRES ? (t) / num_mt : (t) % p.num_n_tiles;             \
+    const int m_tile = (BRES ? (t) % num_mt : (t) / p.num_n_tiles) * NC + rank;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        // pair mode: both CTAs load (their A rows, their half of B); every load completes on the LEADER's barrier, on which
+        // the leader alone posts the expected bytes of both; each CTA waits for its own (multicast-released) slots
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int cur_n = -1;
             uint32_t bemp_phase = 0;
+            const int b_row0 = (NC == 2) ? rank * (BN / 2) : 0;
             for (int t = t_begin; t < t_end; t += t_step) {
                 WB_TILE_COORDS(t)
                 if (BRES && n_tile != cur_n) {
@@ -191,28 +210,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         mbar_wait(b_empty, bemp_phase);
                         bemp_phase ^= 1;
                     }
-                    mbar_expect_tx(b_full, (uint32_t)num_kb * Cfg::kBBytes);
-                    for (int kb = 0; kb < num_kb; ++kb)
-                        tma_load_2d(smem_b + kb * Cfg::kBBytes, &tmap_b, b_full, kb * BK, n_tile * BN);
+                    if (rank == 0) mbar_expect_tx(b_full, (uint32_t)num_kb * Cfg::kBBytes * NC);
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        if (NC == 2)
+                            tma_load_2d_pair(smem_b + kb * Cfg::kBBytes, &tmap_b, mapa_u32(b_full, 0), kb * BK,
+                                             n_tile * BN + b_row0);
+                        else
+                            tma_load_2d(smem_b + kb * Cfg::kBBytes, &tmap_b, b_full, kb * BK, n_tile * BN);
+                    }
                     cur_n = n_tile;
                 }
                 int conv_t = 0;
-                if (!BRES && p.conv) conv_t = __ldg(&p.tile_tab[m_tile]).x;
+                if (!BRES && p.conv) conv_t = (m_tile < p.num_m_tiles) ? __ldg(&p.tile_tab[m_tile]).x : 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     WB_TIMED_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
+                    const uint32_t full_addr = (NC == 2) ? mapa_u32(&full_bar[stage], 0) : 0u;
                     if (!BRES && p.conv) {
                         const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                         const int kh = tap / 3, kw = tap - 3 * kh;
-                        mbar_expect_tx(&full_bar[stage], kConvRows * 128 + Cfg::kBBytes);
-                        tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], cb * BK, kw, conv_t + kh);
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], (kConvRows * 128 + Cfg::kBBytes) * NC);
+                        if (NC == 2)
+                            tma_load_3d_pair(smem_a + stage * Cfg::kABytes, &tmap_a, full_addr, cb * BK, kw, conv_t + kh);
+                        else
+                            tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], cb * BK, kw, conv_t + kh);
                     } else {
-                        mbar_expect_tx(&full_bar[stage], BRES ? Cfg::kABytes : Cfg::kStageBytes);
-                        tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK,
-                                    m_tile * BM);
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], (BRES ? Cfg::kABytes : Cfg::kStageBytes) * NC);
+                        if (NC == 2)
+                            tma_load_2d_pair(smem_a + stage * Cfg::kABytes, &tmap_a, full_addr, kb * BK, m_tile * BM);
+                        else
+                            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
                     }
-                    if (!BRES)
-                        tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK,
-                                    n_tile * BN);
+                    if (!BRES) {
+                        if (NC == 2)
+                            tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, full_addr, kb * BK, n_tile * BN + b_row0);
+                        else
+                            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
+                    }
                     if (++stage == kRing) {
                         stage = 0;
                         phase ^= 1;
@@ -222,8 +255,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        if (lane == 0 && rank == 0) {   // (pair mode: the leader issues the M = 256 MMAs for both CTAs)
+            constexpr uint32_t idesc = make_idesc_bf16(BM * NC, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -250,18 +283,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (NC == 2) umma_f16_pair(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                    // smem slot free (in both CTAs of a pair) once these MMAs retire
+                    if (NC == 2) umma_commit_pair(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == kRing) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full[acc]);  // accumulator complete
+                if (NC == 2) umma_commit_pair(&tmem_full[acc]);   // accumulator complete
+                else umma_commit(&tmem_full[acc]);
                 if (BRES && t + t_step < t_end) {
-                    const int next_n = (t + t_step) / p.num_m_tiles;
-                    if (next_n != n_tile) umma_commit(b_empty);  // panel may be replaced once these MMAs retire
+                    const int next_n = (t + t_step) / num_mt;
+                    if (next_n != n_tile) {   // panel may be replaced once these MMAs retire
+                        if (NC == 2) umma_commit_pair(b_empty);
+                        else umma_commit(b_empty);
+                    }
                 }
                 if (++acc == 2) {
                     acc = 0;
@@ -285,7 +325,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             long long row_base = (long long)m_tile * BM;
             int n_in = 32;   // valid rows in this warp's 32-row slice
             if (!BRES && p.conv) {
-                const int4 tt = __ldg(&p.tile_tab[m_tile]);
+                const int4 tt = (m_tile < p.num_m_tiles) ? __ldg(&p.tile_tab[m_tile]) : make_int4(0, 0, 0, 0);
                 row_base = tt.y;
                 n_in = min(32, max(0, tt.z - q * 32));
             }
@@ -575,7 +615,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (NC == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));   // the leader's barrier
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -599,30 +642,66 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
 #endif
     tc_fence_before();
-    __syncthreads();
+    if (NC == 2) cluster_sync_all();   // neither CTA may leave while the pair's MMAs still read its shared memory
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if (NC == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
 int g_sm_reserve = 0;  // SMs left free for concurrently running latency-bound kernels on other streams
 
-template <int BN, bool BRES, int EPI>
+template <int BN, bool BRES, int EPI, int NC>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc2,
                 const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
-    WB_SET_MAX_DYN_SMEM((gemm_tcgen05_kernel<BN, BRES, EPI>), Cfg::kSmemBytes);
+    using Cfg = GemmCfg<BN, NC>;
+    WB_SET_MAX_DYN_SMEM((gemm_tcgen05_kernel<BN, BRES, EPI, NC>), Cfg::kSmemBytes);
     const int num_sms = current_device_sms();
     WB_REQUIRE(num_sms > 0, WB_ERR_CUDA, "gemm: cannot query the SM count of the current device");
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int usable = (num_sms - g_sm_reserve) > 1 ? (num_sms - g_sm_reserve) : 1;
-    const int grid = tiles < usable ? tiles : usable;
     ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
-    gemm_tcgen05_kernel<BN, BRES, EPI><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
+    if (NC == 2) {
+        // one CTA pair (cluster of two, same TPC) per two SMs; the schedule walks pairs of 128-row tiles
+        const int tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+        const int pairs = tiles < usable / 2 ? tiles : (usable / 2 > 0 ? usable / 2 : 1);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(320);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        WB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, BRES, EPI, NC>, ta, tb, tc, tc2, p));
+    } else {
+        const int tiles = p.num_m_tiles * p.num_n_tiles;
+        const int grid = tiles < usable ? tiles : usable;
+        gemm_tcgen05_kernel<BN, BRES, EPI, NC><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
+    }
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
+}
+
+// CTA-pair (cta_group::2) tiles for the 256-column GEMMs with more than one 128-row tile.  Measured
+// (profiles/r2_ops_gemm_2cta.txt): the streaming K > 256 shapes gain (FFN2 67.6 -> 63.5 us), the weight-stationary
+// K <= 256 shapes lose (FFN1 82 -> 94 us, QKV 33 -> 35 us: the leader's MMAs wait for the slower of two epilogues /
+// producers every tile), so the default is pair tiles for K > 256 only.  WB_GEMM_2CTA=0: never, =2: always.
+int g_gemm_2cta = -1;
+bool gemm_use_pair(int M, int bn, int K) {
+    if (g_gemm_2cta < 0) {
+        const char* e = getenv("WB_GEMM_2CTA");
+        g_gemm_2cta = (e == nullptr) ? 1 : atoi(e);
+    }
+    if (g_gemm_2cta == 0 || bn != 256 || M <= BM) return false;
+    return g_gemm_2cta >= 2 || K > 4 * BK;
 }
 
 }  // namespace
@@ -645,11 +724,15 @@ int gemm_bn_for(int N, int K, int epi) {
     return (N % 256 == 0 || N >= 1024) ? 256 : 128;
 }
 
-int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K, int epi) {
-    return make_tmap_2d_bf16(out, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)gemm_bn_for(N, K, epi), BK);
+int make_weight_tmap(WeightMaps* out, const void* w, int N, int K, int epi) {
+    const int bn = gemm_bn_for(N, K, epi);
+    int rc = make_tmap_2d_bf16(&out->one, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, BK);
+    if (rc != WB_OK) return rc;
+    // CTA-pair mode: each CTA of the pair fetches half of the tile's weight rows
+    return make_tmap_2d_bf16(&out->pair, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(bn / 2), BK);
 }
 
-static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
+static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N,
                      int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
                      float2* lse_part, cudaStream_t stream) {
     if (M <= 0) return WB_OK;
@@ -664,12 +747,13 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
         WB_REQUIRE(!split3, WB_ERR_BAD_ARG, "gemm: split3 only for bf16 outputs");
     }
     const int bn = gemm_bn_for(N, K, epi);
+    const bool pair = gemm_use_pair(M, bn, K);
     CUtensorMap ta, tb_local;
     int rc = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
     if (rc != WB_OK) return rc;
-    const CUtensorMap* tb = tmap_b_opt;
+    const CUtensorMap* tb = tmap_b_opt ? (pair ? &tmap_b_opt->pair : &tmap_b_opt->one) : nullptr;
     if (tb == nullptr) {
-        rc = make_tmap_2d_bf16(&tb_local, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)bn, BK);
+        rc = make_tmap_2d_bf16(&tb_local, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(pair ? bn / 2 : bn), BK);
         if (rc != WB_OK) return rc;
         tb = &tb_local;
     }
@@ -701,14 +785,18 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
     p.tile_tab = nullptr;
     p.lse_part = lse_part;
     const int num_kb = ceil_div(K, BK);
-    p.res_ring = (bn == 256) ? GemmCfg<256>::res_ring(num_kb) : GemmCfg<128>::res_ring(num_kb);
+    p.res_ring = (bn == 256) ? (pair ? GemmCfg<256, 2>::res_ring(num_kb) : GemmCfg<256>::res_ring(num_kb))
+                             : GemmCfg<128>::res_ring(num_kb);
     if (bn == 256) {
-        const bool res = num_kb <= GemmCfg<256>::kResMaxKB;
+        const bool res = num_kb <= 4;   // K <= 256: weight-stationary
         switch (epi) {
-#define WB_GEMM_CASE(E)                                                                  \
-    case E:                                                                              \
-        return res ? launch_gemm<256, true, E>(ta, *tb, tc, tc, p, stream)               \
-                   : launch_gemm<256, false, E>(ta, *tb, tc, tc, p, stream);
+#define WB_GEMM_CASE(E)                                                                              \
+    case E:                                                                                          \
+        if (pair)                                                                                    \
+            return res ? launch_gemm<256, true, E, 2>(ta, *tb, tc, tc, p, stream)                    \
+                       : launch_gemm<256, false, E, 2>(ta, *tb, tc, tc, p, stream);                  \
+        return res ? launch_gemm<256, true, E, 1>(ta, *tb, tc, tc, p, stream)                        \
+                   : launch_gemm<256, false, E, 1>(ta, *tb, tc, tc, p, stream);
             WB_GEMM_CASE(EPI_BF16)
             WB_GEMM_CASE(EPI_BF16_SILU)
             WB_GEMM_CASE(EPI_BF16_RELU)
@@ -725,7 +813,7 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
         switch (epi) {
 #define WB_GEMM_CASE(E) \
     case E:             \
-        return launch_gemm<128, true, E>(ta, *tb, tc, tc, p, stream);
+        return launch_gemm<128, true, E, 1>(ta, *tb, tc, tc, p, stream);
             WB_GEMM_CASE(EPI_BF16)
             WB_GEMM_CASE(EPI_BF16_SILU)
             WB_GEMM_CASE(EPI_BF16_RELU)
@@ -738,10 +826,10 @@ static int gemm_impl(const void* A, long long lda, const CUtensorMap* tmap_b_opt
                 WB_REQUIRE(false, WB_ERR_BAD_ARG, "gemm: unknown epilogue %d", epi);
         }
     }
-    return launch_gemm<128, false, -1>(ta, *tb, tc, tc, p, stream);
+    return launch_gemm<128, false, -1, 1>(ta, *tb, tc, tc, p, stream);
 }
 
-int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
+int gemm_bf16(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N,
               int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
               cudaStream_t stream) {
     WB_REQUIRE(epi != EPI_LSE, WB_ERR_BAD_ARG, "gemm: this epilogue has its own entry point");
@@ -750,7 +838,7 @@ int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const
 
 int lse_parts(int N, int K) { return 2 * ceil_div(N, gemm_bn_for(N, K, EPI_LSE)); }
 
-int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N, int K,
+int gemm_lse_partials(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream) {
     WB_REQUIRE(part != nullptr, WB_ERR_BAD_ARG, "gemm_lse_partials: null output");
     return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, EPI_LSE, 1.0f, part /*unused as matrix*/, 0, 0, part, stream);
@@ -760,7 +848,7 @@ int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_op
 //   out2[(tile row), n] = relu(bias[n] + sum_{kh,kw,c} out1[t1 = 2 t2 + kh][f1 = 2 f2 + kw][c] * W[n][(kh,kw,c)])
 // out1: [T1_total][F1][d] bf16 (utterances stacked along t), out2: [rows_out][d] bf16, tile_tab_dev: one int4 per
 // 114-row tile (see GemmParams).
-int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, const CUtensorMap* tmap_w, const float* bias,
+int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, const WeightMaps* tmap_w, const float* bias,
                         const void* tile_tab_dev, int num_tiles, long long rows_out, void* out2, cudaStream_t stream) {
     if (num_tiles <= 0) return WB_OK;
     WB_REQUIRE(d % 256 == 0 && F1 == 39, WB_ERR_UNSUPPORTED, "conv2 implicit GEMM: d=%d F1=%d unsupported", d, F1);
@@ -791,7 +879,9 @@ int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, con
     p.conv = 1;
     p.cblocks = d / 64;
     p.tile_tab = reinterpret_cast<const int4*>(tile_tab_dev);
-    return launch_gemm<256, false, EPI_BF16_RELU>(ta, *tmap_w, tc, tc18, p, stream);
+    if (gemm_use_pair(2 * BM, 256, 9 * d) && num_tiles > 1)
+        return launch_gemm<256, false, EPI_BF16_RELU, 2>(ta, tmap_w->pair, tc, tc18, p, stream);
+    return launch_gemm<256, false, EPI_BF16_RELU, 1>(ta, tmap_w->one, tc, tc18, p, stream);
 }
 
 int gemm_diag(unsigned long long* out8, int reset) {

@@ -19,28 +19,33 @@ enum GemmEpi : int {
 };
 
 int gemm_bn_for(int N, int K, int epi = EPI_BF16);
+// tensor maps of a [N, K] bf16 weight (B operand): `one` fetches a whole tile's rows (gemm_bn_for), `pair` half of them
+// (CTA-pair tiles: each CTA of the pair holds half of B)
+struct WeightMaps {
+    CUtensorMap one, pair;
+};
 void gemm_set_sm_reserve(int n);
 // tensor map for a [N, K] bf16 weight (B operand), box rows = gemm_bn_for(N, K)
 // (epi: the epilogue the weight will be used with - only EPI_GLU_BF16 changes the tile width)
-int make_weight_tmap(CUtensorMap* out, const void* w, int N, int K, int epi = EPI_BF16);
+int make_weight_tmap(WeightMaps* out, const void* w, int N, int K, int epi = EPI_BF16);
 // C = epi(A[M,K](lda) * B[N,K]^T + bias). tmap_b_opt may be null (then built from B).
 // split3: bf16 outputs are written as [hi | lo | hi] column blocks of width N (N/2 for GLU) so the
 // next GEMM can run in "bf16x3" mode against weights packed as [hi | hi | lo].
-int gemm_bf16(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N,
+int gemm_bf16(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N,
               int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
               cudaStream_t stream);
 
 // log-softmax denominators without the logits: part[row][2 * n_tiles] = (max of v log2 e, sum 2^(v log2 e - max)) over each
 // 128-column half of each n-tile of v = A B^T + bias.  lse_parts() = entries per row for a given N.
 int lse_parts(int N, int K);
-int gemm_lse_partials(const void* A, long long lda, const CUtensorMap* tmap_b_opt, const void* B, int M, int N, int K,
+int gemm_lse_partials(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream);
 
 // stall accounting of gemm_tcgen05_kernel (see gemm.cu); out8 may be null
 int gemm_diag(unsigned long long* out8, int reset);
 
 // Conv2d(d->d, 3x3, s2) + ReLU as an implicit GEMM whose A tiles are fetched by 3-D strided TMA boxes (no im2col buffer)
-int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, const CUtensorMap* tmap_w, const float* bias,
+int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, const WeightMaps* tmap_w, const float* bias,
                         const void* tile_tab_dev /*int4 per tile*/, int num_tiles, long long rows_out, void* out2,
                         cudaStream_t stream);
 

@@ -19,7 +19,7 @@ struct Linear {
     const void* w = nullptr;   // bf16 [N][K]
     const float* b = nullptr;  // [N] or null
     int N = 0, K = 0;
-    CUtensorMap tmap;
+    WeightMaps tmap;
 };
 
 struct Norm {
