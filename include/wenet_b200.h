@@ -300,6 +300,14 @@ int wb_decoder_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t
 int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K,
                const float* bias_dev, int epi, float alpha, void* c_dev, int64_t ldc, int split3,
                wb_stream_t stream);
+/* x += alpha * (a b^T + bias) and ln_out = LayerNorm(x) * gamma + beta (bf16) in one kernel; N must be 256.  Replaces a
+ * residual-update Linear followed by the next module's LayerNorm (wenet/models/transformer/encoder_layer.py:221-263).
+ * gamma1_dev / beta1_dev non-null: the layer boundary (:262-263 then the next layer's :221-223) -
+ * x = LayerNorm(gamma1, beta1)(x + ...) is stored (fp32) and ln_out = LayerNorm(gamma, beta)(x). */
+int wb_op_gemm_resid_ln(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K,
+                        const float* bias_dev, float alpha, float* x_dev, int64_t ldx, const float* gamma1_dev,
+                        const float* beta1_dev, const float* gamma_dev, const float* beta_dev, float eps,
+                        void* ln_out_bf16_dev, int64_t ld_ln, wb_stream_t stream);
 int wb_op_layernorm(const float* x_dev, int64_t ldx, int M, int d, const float* gamma_dev,
                     const float* beta_dev, float eps, void* out_bf16_dev, int64_t ld_bf16, int split3,
                     float* out_f32_dev, int64_t ld_f32, wb_stream_t stream);

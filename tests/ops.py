@@ -37,6 +37,19 @@ def gemm(a, b, bias=None, epi=EPI_BF16, alpha=1.0, out=None, split3=False):
     return out
 
 
+def gemm_resid_ln(a, b, bias, x, gamma, beta, alpha=1.0, eps=1e-5, gamma1=None, beta1=None):
+    """x += alpha * (a @ b.T + bias) in place; returns bf16 LayerNorm(x).  With gamma1 / beta1: x = LayerNorm_1(x + ...)
+    in place and the result is LayerNorm(gamma, beta)(x)."""
+    _need_cuda(a, b, bias, x, gamma, beta, gamma1, beta1)
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    check(_lib.load().wb_op_gemm_resid_ln(ptr(a), a.stride(0), ptr(b), M, N, K, ptr(bias), float(alpha), ptr(x), x.stride(0),
+                                          ptr(gamma1), ptr(beta1), ptr(gamma), ptr(beta), float(eps), ptr(out), out.stride(0), cur_stream()),
+          "wb_op_gemm_resid_ln")
+    return out
+
+
 def layernorm(x, gamma, beta, eps=1e-5, want_bf16=True, want_f32=False, split3=False):
     _need_cuda(x, gamma, beta)
     M, d = x.shape

@@ -57,6 +57,60 @@ def test_gemm(M, N, K, epi):
         _close(out, ref, 2 ** -8, 2e-4)
 
 
+@pytest.mark.parametrize("M,K", [(300, 256), (47872, 256), (257, 2048), (5000, 2048), (67, 256), (128, 2048)])
+def test_gemm_resid_layernorm(M, K):
+    """Residual-update GEMM with the next module's LayerNorm fused into its epilogue (N = d = 256): x in place and
+    the bf16 normalised rows against x + alpha (a b^T + bias) and torch's layer_norm of that."""
+    import ops
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    N = 256
+    a = _rb(torch.randn(M, K, generator=g)).to(_dev())
+    b = _rb(torch.randn(N, K, generator=g) / math.sqrt(K)).to(_dev())
+    bias = torch.randn(N, generator=g).to(_dev())
+    gamma = (1.0 + 0.2 * torch.randn(N, generator=g)).to(_dev())
+    beta = (0.3 * torch.randn(N, generator=g)).to(_dev())
+    # rows with a large common offset exercise the variance formula (mean >> spread)
+    x0 = (torch.randn(M, N, generator=g) * 2.0 + 3.0 * torch.randn(M, 1, generator=g)).to(_dev())
+    alpha = 0.5
+    ref_x = x0 + alpha * (a.float() @ b.float().T + bias)
+    ref_ln = torch.nn.functional.layer_norm(ref_x, (N,), gamma, beta, 1e-5)
+    x = x0.clone()
+    out = ops.gemm_resid_ln(a, b, bias, x, gamma, beta, alpha=alpha, eps=1e-5)
+    torch.cuda.synchronize()
+    _close(x, ref_x, 1e-5, 2e-4)
+    assert out.dtype == torch.bfloat16
+    _close(out, ref_ln, 2 ** -8, 1e-3)
+    # and the same rows as the unfused pair of kernels produces them (bf16 rounding of nearly equal fp32 values)
+    x2 = ops.gemm(a, b, bias, 3, alpha, out=x0.clone())
+    ln2 = ops.layernorm(x2, gamma, beta, 1e-5)[0]
+    assert ((out.float() - ln2.float()).abs() <= 2 ** -7 * ln2.float().abs() + 1e-3).all()
+
+
+@pytest.mark.parametrize("M,K", [(300, 2048), (47872, 2048), (67, 2048), (1000, 256)])
+def test_gemm_resid_two_layernorms(M, K):
+    """Layer boundary: x = norm_final(x + alpha (a b^T + bias)) stored in fp32 and the next layer's norm_ff_macaron of
+    it in bf16, both inside the GEMM epilogue."""
+    import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 3 + K)
+    N = 256
+    a = _rb(torch.randn(M, K, generator=g)).to(_dev())
+    b = _rb(torch.randn(N, K, generator=g) / math.sqrt(K)).to(_dev())
+    bias = torch.randn(N, generator=g).to(_dev())
+    g1 = (1.0 + 0.2 * torch.randn(N, generator=g)).to(_dev())
+    b1 = (0.3 * torch.randn(N, generator=g)).to(_dev())
+    g2 = (1.0 + 0.2 * torch.randn(N, generator=g)).to(_dev())
+    b2 = (0.3 * torch.randn(N, generator=g)).to(_dev())
+    x0 = (torch.randn(M, N, generator=g) * 2.0 + 3.0 * torch.randn(M, 1, generator=g)).to(_dev())
+    ref_y = x0 + 0.5 * (a.float() @ b.float().T + bias)
+    ref_x = torch.nn.functional.layer_norm(ref_y, (N,), g1, b1, 1e-5)
+    ref_z = torch.nn.functional.layer_norm(ref_x, (N,), g2, b2, 1e-5)
+    x = x0.clone()
+    out = ops.gemm_resid_ln(a, b, bias, x, g2, b2, alpha=0.5, eps=1e-5, gamma1=g1, beta1=b1)
+    torch.cuda.synchronize()
+    _close(x, ref_x, 1e-5, 3e-4)
+    _close(out, ref_z, 2 ** -8, 1e-3)
+
+
 def test_gemm_glu_and_tail():
     import ops
     g = torch.Generator().manual_seed(5)

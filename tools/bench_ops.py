@@ -88,6 +88,11 @@ for name, N, K, epi, A in [("gemm ffn1 silu N2048 K256", ff, d, ops.EPI_BF16_SIL
     timeit(name, lambda A=A, w=w, b=b, epi=epi, out=out: ops.gemm(A, w, b, epi, 1.0, out=out), flops=2.0 * M * N * K)
 
 gamma, beta = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+for name, K, A in [("gemm+ln out resid N256 K256", d, a256), ("gemm+ln ffn2 resid N256 K2048", ff, a2048)]:
+    w = rb(d, K, scale=1.0 / math.sqrt(K))
+    b = torch.randn(d, device=dev, generator=g)
+    xx = torch.zeros(M, d, device=dev)
+    timeit(name, lambda A=A, w=w, b=b, xx=xx: ops.gemm_resid_ln(A, w, b, xx, gamma, beta, alpha=1e-3), flops=2.0 * M * d * K)
 timeit("layernorm M x 256 -> bf16", lambda: ops.layernorm(x, gamma, beta), bytes_=M * d * 6.0)
 
 B, T = 64, 748

@@ -183,7 +183,7 @@ const char* wb_prof_tag_name(int tag) {
     static const char* names[PT_COUNT] = {"gemm_tcgen05", "attention", "layernorm", "dwconv_norm_silu", "conv1",
                                           "im2col", "relpos_kprep", "fbank", "logsoftmax_topk", "ctc_greedy",
                                           "ctc_prefix_beam", "embed_tokens", "gather_logprob", "rescore_combine",
-                                          "misc", "ffn_fused_tcgen05 (removed)"};
+                                          "misc", "gemm_tcgen05+layernorm"};
     return (tag >= 0 && tag < PT_COUNT) ? names[tag] : "?";
 }
 int wb_prof_collect(double* ms, double* work, long long* launches) { return wb::prof_collect(ms, work, launches); }
@@ -347,6 +347,13 @@ int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, 
                float alpha, void* c_dev, int64_t ldc, int split3, wb_stream_t stream) {
     return gemm_bf16(a_dev, lda, nullptr, b_dev, M, N, K, bias_dev, epi, alpha, c_dev, ldc, split3,
                      (cudaStream_t)stream);
+}
+int wb_op_gemm_resid_ln(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K, const float* bias_dev,
+                        float alpha, float* x_dev, int64_t ldx, const float* gamma1_dev, const float* beta1_dev,
+                        const float* gamma_dev, const float* beta_dev, float eps, void* ln_out_bf16_dev, int64_t ld_ln,
+                        wb_stream_t stream) {
+    return gemm_resid_ln(a_dev, lda, nullptr, b_dev, M, N, K, bias_dev, alpha, x_dev, ldx, gamma1_dev, beta1_dev, gamma_dev,
+                         beta_dev, eps, ln_out_bf16_dev, ld_ln, (cudaStream_t)stream);
 }
 int wb_op_layernorm(const float* x_dev, int64_t ldx, int M, int d, const float* gamma_dev, const float* beta_dev,
                     float eps, void* out_bf16_dev, int64_t ld_bf16, int split3, float* out_f32_dev, int64_t ld_f32,

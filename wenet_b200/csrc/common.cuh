@@ -48,7 +48,7 @@ static inline void count_launch(int n = 1) { g_launch_count.fetch_add((unsigned 
 // Off by default; bench.py switches it on to obtain live per-kernel durations and roofline numbers.
 enum ProfTag : int {
     PT_GEMM = 0, PT_ATTENTION, PT_LAYERNORM, PT_DWCONV, PT_CONV1, PT_IM2COL, PT_KPREP, PT_FBANK, PT_LOGSOFTMAX_TOPK,
-    PT_GREEDY, PT_PREFIX_BEAM, PT_EMBED, PT_GATHER_LOGPROB, PT_RESCORE, PT_MISC, PT_FFN_FUSED, PT_COUNT
+    PT_GREEDY, PT_PREFIX_BEAM, PT_EMBED, PT_GATHER_LOGPROB, PT_RESCORE, PT_MISC, PT_GEMM_LN, PT_COUNT
 };
 extern int g_prof_on;
 void prof_begin(int tag, cudaStream_t st, double work);
@@ -288,6 +288,10 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 // of A and HALF of the B tile from its own shared memory and receives its 128 accumulator lanes in its own TMEM.  The
 // leader (rank 0) issues the MMAs; TMA loads of both CTAs complete on the LEADER's mbarrier; tcgen05.commit multicasts
 // its arrival to the same barrier offset in both CTAs.
+// named barrier over `nthreads` threads of the CTA (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -224,6 +224,17 @@ using namespace wb;
         if (_rc != WB_OK) return _rc; \
     } while (0)
 
+// x += alpha * (A W^T + b); out = LayerNorm_n(x) (bf16, or [hi | lo | hi] in precise mode).  One kernel when the row fits
+// an output tile (d == 256, bf16 mode), else the residual GEMM followed by the LayerNorm kernel.
+static int resid_then_norm(const void* A, long long lda_in, const Linear& W, int M, int d, float alpha, float* x,
+                           const Norm& n, float eps, void* out, long long ld_out, int split3, cudaStream_t st) {
+    if (!split3 && W.b != nullptr && gemm_resid_ln_supported(d))
+        return gemm_resid_ln(A, lda_in, &W.tmap, W.w, M, d, W.K, W.b, alpha, x, d, nullptr, nullptr, n.g, n.b, eps, out, ld_out,
+                             st);
+    RC(gemm_bf16(A, lda_in, &W.tmap, W.w, M, d, W.K, W.b, EPI_RESID_F32, alpha, x, d, 0, st));
+    return layernorm_rows(x, d, M, d, n.g, n.b, eps, out, ld_out, split3, nullptr, 0, st);
+}
+
 extern "C" {
 
 int64_t wb_encoder_out_rows(int batch, const int32_t* feat_lens_host) {
@@ -375,9 +386,9 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
         // norm_final (one read of x for both)
         if (li == 0) RC(layernorm_rows(x, d, Mi, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
         RC(gemm_bf16(a, lda, &L.ffm1.tmap, L.ffm1.w, Mi, ff, L.ffm1.K, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
-        RC(gemm_bf16(h, ldh, &L.ffm2.tmap, L.ffm2.w, Mi, d, L.ffm2.K, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
+        // (each residual-update GEMM carries the LayerNorm of the module that follows in its epilogue when d == 256)
+        RC(resid_then_norm(h, ldh, L.ffm2, Mi, d, 0.5f, x, L.n_mha, c.ln_eps, a, lda, sp, st));
         // rel-pos multi-headed self-attention (:231-238)
-        RC(layernorm_rows(x, d, Mi, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
         if (sp) {
             // precise: q, k, v stay fp32; scores = ((q + u) . k + (q + v) . p) / sqrt(d_k) and the softmax on CUDA cores
             float* qf = reinterpret_cast<float*>(qkv);
@@ -409,9 +420,8 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
                 RC(attention_forward(A, st));
             }
         }
-        RC(gemm_bf16(ctx, lda, &L.out.tmap, L.out.w, Mi, d, L.out.K, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(resid_then_norm(ctx, lda, L.out, Mi, d, 1.0f, x, L.n_conv, c.ln_eps, a, lda, sp, st));
         // convolution module (:243-251)
-        RC(layernorm_rows(x, d, Mi, d, L.n_conv.g, L.n_conv.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
         RC(gemm_bf16(a, lda, &L.pw1.tmap, L.pw1.w, Mi, 2 * d, L.pw1.K, L.pw1.b, EPI_GLU_BF16, 1.0f, g, lda, sp, st));
         {
             DwConvArgs D;
@@ -423,17 +433,22 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
             D.out = g2; D.ldo = lda; D.split3 = sp;
             RC(sp ? dwconv_norm_silu_f32(D, st) : dwconv_norm_silu(D, st));
         }
-        RC(gemm_bf16(g2, lda, &L.pw2.tmap, L.pw2.w, Mi, d, L.pw2.K, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(resid_then_norm(g2, lda, L.pw2, Mi, d, 1.0f, x, L.n_ff, c.ln_eps, a, lda, sp, st));
         // feed-forward (:254-259) and norm_final (:262-263)
-        RC(layernorm_rows(x, d, Mi, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
         RC(gemm_bf16(a, lda, &L.ff1.tmap, L.ff1.w, Mi, ff, L.ff1.K, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
-        RC(gemm_bf16(h, ldh, &L.ff2.tmap, L.ff2.w, Mi, d, L.ff2.K, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
-        if (li + 1 < c.enc_layers) {
+        if (li + 1 < c.enc_layers && !sp && L.ff2.b != nullptr && gemm_resid_ln_supported(d)) {
+            // x = norm_final(x + 0.5 ff(x)) and a = norm_ff_macaron_{l+1}(x), both in the epilogue of the w_2 GEMM
+            const EncLayer& Ln = m->layers[li + 1];
+            RC(gemm_resid_ln(h, ldh, &L.ff2.tmap, L.ff2.w, Mi, d, L.ff2.K, L.ff2.b, 0.5f, x, d, L.n_final.g, L.n_final.b,
+                             Ln.n_ffm.g, Ln.n_ffm.b, c.ln_eps, a, lda, st));
+        } else if (li + 1 < c.enc_layers) {
+            RC(gemm_bf16(h, ldh, &L.ff2.tmap, L.ff2.w, Mi, d, L.ff2.K, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
             // x = norm_final(x) and a = norm_ff_macaron_{l+1}(x) in one pass
             const EncLayer& Ln = m->layers[li + 1];
             RC(layernorm2_rows(x, d, Mi, d, L.n_final.g, L.n_final.b, Ln.n_ffm.g, Ln.n_ffm.b, c.ln_eps, x, d, a, lda, sp,
                                nullptr, 0, st));
         } else {
+            RC(gemm_bf16(h, ldh, &L.ff2.tmap, L.ff2.w, Mi, d, L.ff2.K, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
             // last layer: norm_final, then after_norm (encoder.py:176-177): fp32 result + bf16 copy for the CTC / decoder
             // GEMMs; the intermediate only leaves the chip when a layer dump was requested
             RC(layernorm2_rows(x, d, Mi, d, L.n_final.g, L.n_final.b, m->after.g, m->after.b, c.ln_eps,
@@ -578,8 +593,7 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
         const EncLayer& L = m->layers[li];
         if (li == 0) RC(layernorm_rows(x, d, chunk, d, L.n_ffm.g, L.n_ffm.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
         RC(gemm_bf16(a, lda, &L.ffm1.tmap, L.ffm1.w, chunk, ff, L.ffm1.K, L.ffm1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
-        RC(gemm_bf16(h, ldh, &L.ffm2.tmap, L.ffm2.w, chunk, d, L.ffm2.K, L.ffm2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
-        RC(layernorm_rows(x, d, chunk, d, L.n_mha.g, L.n_mha.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        RC(resid_then_norm(h, ldh, L.ffm2, chunk, d, 0.5f, x, L.n_mha, c.ln_eps, a, lda, sp, st));
         if (sp) {
             // precise: fp32 q / k / v, fp32 history, fp32 attention (precise.cu); the cache handed back is exact fp32
             float* qf = reinterpret_cast<float*>(qkv);
@@ -645,11 +659,17 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
             D.out = g2; D.ldo = lda; D.split3 = sp;
             RC(sp ? dwconv_norm_silu_f32(D, st) : dwconv_norm_silu(D, st));
         }
-        RC(gemm_bf16(g2, lda, &L.pw2.tmap, L.pw2.w, chunk, d, L.pw2.K, L.pw2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
-        RC(layernorm_rows(x, d, chunk, d, L.n_ff.g, L.n_ff.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        RC(resid_then_norm(g2, lda, L.pw2, chunk, d, 1.0f, x, L.n_ff, c.ln_eps, a, lda, sp, st));
         RC(gemm_bf16(a, lda, &L.ff1.tmap, L.ff1.w, chunk, ff, L.ff1.K, L.ff1.b, EPI_BF16_SILU, 1.0f, h, ldh, sp, st));
+        // norm_final fused with the next layer's norm_ff_macaron (both in the w_2 GEMM's epilogue when d == 256), or (last
+        // layer) with after_norm
+        if (li + 1 < c.enc_layers && !sp && L.ff2.b != nullptr && gemm_resid_ln_supported(d)) {
+            const EncLayer& Ln = m->layers[li + 1];
+            RC(gemm_resid_ln(h, ldh, &L.ff2.tmap, L.ff2.w, chunk, d, L.ff2.K, L.ff2.b, 0.5f, x, d, L.n_final.g, L.n_final.b,
+                             Ln.n_ffm.g, Ln.n_ffm.b, c.ln_eps, a, lda, st));
+            continue;
+        }
         RC(gemm_bf16(h, ldh, &L.ff2.tmap, L.ff2.w, chunk, d, L.ff2.K, L.ff2.b, EPI_RESID_F32, 0.5f, x, d, 0, st));
-        // norm_final fused with the next layer's norm_ff_macaron, or (last layer) with after_norm
         if (li + 1 < c.enc_layers) {
             const EncLayer& Ln = m->layers[li + 1];
             RC(layernorm2_rows(x, d, chunk, d, L.n_final.g, L.n_final.b, Ln.n_ffm.g, Ln.n_ffm.b, c.ln_eps, x, d, a, lda, sp,

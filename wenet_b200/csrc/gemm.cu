@@ -86,6 +86,13 @@ struct GemmParams {
     int cblocks;            // d / 64
     const int4* tile_tab;   // per m-tile: .x t coordinate of tap kh = 0, .y first output row, .z valid rows (<= 114)
     float2* lse_part;       // EPI_LSE: [M][2 * num_n_tiles]
+    // EPI_RESID_LN: LayerNorm applied to the updated residual rows (bf16 result through tmap_c2)
+    const float* ln_g;
+    const float* ln_b;
+    float ln_eps;
+    // EPI_RESID_LN2: x = LayerNorm(ln1_g, ln1_b)(updated rows) (fp32), bf16 result = LayerNorm(ln_g, ln_b)(x)
+    const float* ln1_g;
+    const float* ln1_b;
 };
 constexpr int kConvRows = 114;   // 6 x 19
 
@@ -154,7 +161,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if (p.use_tma_out) tma_prefetch_desc(&tmap_c);
-        if (p.conv) tma_prefetch_desc(&tmap_c2);
+        if (p.conv || EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2) tma_prefetch_desc(&tmap_c2);
         for (int s = 0; s < kRing; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -335,6 +342,193 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // last tile of an utterance falls back to guarded register stores
             const bool warp_tma = p.use_tma_out && (n_in == 32 || n_in == 18);
             const CUtensorMap* cmap = (n_in == 18) ? &tmap_c2 : &tmap_c;
+            if (EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2) {
+                // ---- residual update + LayerNorm(s) of the updated row in one epilogue (N == BN == 256: the tile holds whole
+                // rows).  Thread = one row x 128 columns (its TMEM lane, this warp's column half).
+                //   pass 1: y = x_old + alpha * (acc + bias), parked back in TMEM in place of the accumulator; running
+                //           (mean, M2) merged chunk by chunk (Chan's update).  EPI_RESID_LN: x = y (fp32, staged, TMA store)
+                //   exchange (mean, M2) with the warp that owns the other column half (named barrier of the two warps)
+                //   EPI_RESID_LN2 only - pass 2: x = LayerNorm_1(y) (fp32 store), again parked in TMEM, statistics of x
+                //   last pass: tcgen05.ld -> (v - mean) * rstd * gamma + beta -> bf16 -> staged -> TMA store
+                constexpr bool kTwo = (EPI == EPI_RESID_LN2);
+                const uint32_t taddr0 =
+                    tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN) + (uint32_t)(half * 128);
+                // x_old is fetched coalesced (instruction j: lane l reads 16 bytes of row 4 j + l / 8, a warp covers 4 rows x
+                // 128 B), one chunk ahead, and transposed to "thread = row" through this warp's staging buffer
+                const int sub_r = lane >> 3, sub_c = lane & 7;
+                const long long wrow0 = row_base + q * 32;
+                const float* xwarp = reinterpret_cast<const float*>(p.out) + wrow0 * p.ldc + half * 128;
+                float4 xo[8];
+                auto load_x = [&](int ci) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int rr = 4 * j + sub_r;
+                        xo[j] = (wrow0 + rr < p.M)
+                                    ? __ldcg(reinterpret_cast<const float4*>(xwarp + (long long)rr * p.ldc + ci * 32) + sub_c)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                };
+                load_x(0);
+                WB_TIMED_WAIT(3, mbar_wait(&tmem_full[acc], acc_phase));
+                tc_fence_after();
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr0, r);
+                const int sw = lane & 7;
+                uint8_t* sbuf_warp = smem_out + (warp - 2) * 4096;
+                uint8_t* sbuf = sbuf_warp + lane * 128;
+                const int row0 = (int)wrow0;
+                auto staging_ready = [&]() {
+                    if (need_wait) {
+                        WB_TIMED_WAIT(4, if (lane == 0) tma_store_wait_read<0>(); __syncwarp());
+                        need_wait = false;
+                    }
+                };
+                // running statistics over the chunks seen so far (ci is a compile-time constant after unrolling)
+                auto stats_merge = [&](const uint32_t (&v)[32], int ci, float& mean, float& m2) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        s0 += __uint_as_float(v[i]);
+                        s1 += __uint_as_float(v[i + 1]);
+                        s2 += __uint_as_float(v[i + 2]);
+                        s3 += __uint_as_float(v[i + 3]);
+                    }
+                    const float cm = ((s0 + s1) + (s2 + s3)) * (1.0f / 32.0f);
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float d0 = __uint_as_float(v[i]) - cm, d1 = __uint_as_float(v[i + 1]) - cm;
+                        const float d2 = __uint_as_float(v[i + 2]) - cm, d3 = __uint_as_float(v[i + 3]) - cm;
+                        q0 = fmaf(d0, d0, q0);
+                        q1 = fmaf(d1, d1, q1);
+                        q2 = fmaf(d2, d2, q2);
+                        q3 = fmaf(d3, d3, q3);
+                    }
+                    const float na = 32.0f * ci, nt = na + 32.0f;
+                    const float delta = cm - mean;
+                    mean += delta * (32.0f / nt);
+                    m2 += ((q0 + q1) + (q2 + q3)) + delta * delta * (na * 32.0f / nt);
+                };
+                // fp32 chunk (thread = row) -> staging -> TMA store into x
+                auto store_x = [&](const uint32_t (&v)[32], int n0) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        *reinterpret_cast<uint4*>(sbuf + ((u ^ sw) << 4)) =
+                            make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_c, sbuf_warp, n0, row0);
+                        tma_store_commit();
+                    }
+                    need_wait = true;
+                };
+                float2* sx = reinterpret_cast<float2*>(smem_bias);   // [column half][tile row] (no bias staging in this variant)
+                auto row_stats = [&](float mean, float m2, float& mu, float& rstd) {
+                    sx[half * 128 + q * 32 + lane] = make_float2(mean, m2);
+                    named_bar_sync(1 + q, 64);
+                    const float2 oth = sx[(half ^ 1) * 128 + q * 32 + lane];
+                    named_bar_sync(1 + q, 64);   // the slot is rewritten by the next exchange
+                    const float dm = oth.x - mean;
+                    mu = 0.5f * (mean + oth.x);
+                    rstd = rsqrtf((m2 + oth.y + dm * dm * 64.0f) * (1.0f / 256.0f) + p.ln_eps);
+                };
+                float mean = 0.f, m2 = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int n0 = half * 128 + ci * 32;
+                    staging_ready();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int rr = 4 * j + sub_r;
+                        *reinterpret_cast<float4*>(sbuf_warp + rr * 128 + ((sub_c ^ (rr & 7)) << 4)) = xo[j];
+                    }
+                    __syncwarp();
+                    if (ci + 1 < 4) load_x(ci + 1);
+                    tmem_ld_wait_regs(r);
+                    uint32_t y[32];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + u);
+                        const float4 x4 = *reinterpret_cast<const float4*>(sbuf + ((u ^ sw) << 4));
+                        y[4 * u] = __float_as_uint(fmaf(p.alpha, __uint_as_float(r[4 * u]) + b4.x, x4.x));
+                        y[4 * u + 1] = __float_as_uint(fmaf(p.alpha, __uint_as_float(r[4 * u + 1]) + b4.y, x4.y));
+                        y[4 * u + 2] = __float_as_uint(fmaf(p.alpha, __uint_as_float(r[4 * u + 2]) + b4.z, x4.z));
+                        y[4 * u + 3] = __float_as_uint(fmaf(p.alpha, __uint_as_float(r[4 * u + 3]) + b4.w, x4.w));
+                    }
+                    tmem_st_32x32b_x32(taddr0 + (uint32_t)(ci * 32), y);
+                    if (ci + 1 < 4) tmem_ld_32x32b_x32(taddr0 + (uint32_t)((ci + 1) * 32), r);
+                    stats_merge(y, ci, mean, m2);
+                    // (a thread reads and rewrites only its own row of the buffer: no barrier between the two)
+                    if (!kTwo) store_x(y, n0);
+                    else __syncwarp();   // every lane has read its row before the next chunk's x_old overwrites the buffer
+                }
+                float mu, rstd;
+                row_stats(mean, m2, mu, rstd);
+                tmem_st_wait();
+                tmem_ld_32x32b_x32(taddr0, r);
+                if (kTwo) {
+                    mean = 0.f;
+                    m2 = 0.f;
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const int n0 = half * 128 + ci * 32;
+                        tmem_ld_wait_regs(r);
+                        uint32_t y[32];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln1_g + n0) + u);
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln1_b + n0) + u);
+                            const float a0 = rstd * g4.x, a1 = rstd * g4.y, a2 = rstd * g4.z, a3 = rstd * g4.w;
+                            y[4 * u] = __float_as_uint(fmaf(__uint_as_float(r[4 * u]), a0, fmaf(-mu, a0, b4.x)));
+                            y[4 * u + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * u + 1]), a1, fmaf(-mu, a1, b4.y)));
+                            y[4 * u + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * u + 2]), a2, fmaf(-mu, a2, b4.z)));
+                            y[4 * u + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * u + 3]), a3, fmaf(-mu, a3, b4.w)));
+                        }
+                        tmem_st_32x32b_x32(taddr0 + (uint32_t)(ci * 32), y);
+                        if (ci + 1 < 4) tmem_ld_32x32b_x32(taddr0 + (uint32_t)((ci + 1) * 32), r);
+                        stats_merge(y, ci, mean, m2);
+                        staging_ready();
+                        store_x(y, n0);
+                    }
+                    row_stats(mean, m2, mu, rstd);
+                    tmem_st_wait();
+                    tmem_ld_32x32b_x32(taddr0, r);
+                }
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int n0 = half * 128 + ci * 32;
+                    tmem_ld_wait_regs(r);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + n0) + u);
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + n0) + u);
+                        const float a0 = rstd * g4.x, a1 = rstd * g4.y, a2 = rstd * g4.z, a3 = rstd * g4.w;
+                        const float o0 = fmaf(__uint_as_float(r[4 * u]), a0, fmaf(-mu, a0, b4.x));
+                        const float o1 = fmaf(__uint_as_float(r[4 * u + 1]), a1, fmaf(-mu, a1, b4.y));
+                        const float o2 = fmaf(__uint_as_float(r[4 * u + 2]), a2, fmaf(-mu, a2, b4.z));
+                        const float o3 = fmaf(__uint_as_float(r[4 * u + 3]), a3, fmaf(-mu, a3, b4.w));
+                        pk[2 * u] = pack_bf16x2(o0, o1);
+                        pk[2 * u + 1] = pack_bf16x2(o2, o3);
+                    }
+                    if (ci + 1 < 4) tmem_ld_32x32b_x32(taddr0 + (uint32_t)((ci + 1) * 32), r);
+                    if ((ci & 1) == 0) staging_ready();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(sbuf + ((((ci & 1) * 4 + u) ^ sw) << 4)) =
+                            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    if (ci & 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmap_c2, sbuf_warp, half * 128 + (ci & ~1) * 32, row0);
+                            tma_store_commit();
+                        }
+                        need_wait = true;
+                    }
+                }
+            } else {
             // this warp's slice of the bias (kChunksPerWarp x 32 columns) is fetched before the accumulator wait and
             // parked in shared memory (one copy per tile parity; the four warps of a column half write identical
             // values), so the chunk loop reads it with broadcast LDS instead of an L2 round trip per chunk
@@ -612,6 +806,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             if (epi == EPI_LSE && row_ok)
                 p.lse_part[row * (2 * p.num_n_tiles) + n_tile * 2 + half] = make_float2(lse_m, lse_s);
+            }   // EPI != EPI_RESID_LN / EPI_RESID_LN2
             // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -661,7 +856,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     const int num_sms = current_device_sms();
     WB_REQUIRE(num_sms > 0, WB_ERR_CUDA, "gemm: cannot query the SM count of the current device");
     const int usable = (num_sms - g_sm_reserve) > 1 ? (num_sms - g_sm_reserve) : 1;
-    ProfScope _ps(PT_GEMM, stream, 2.0 * (double)p.M * (double)p.N * (double)p.K);
+    ProfScope _ps((EPI == EPI_RESID_LN || EPI == EPI_RESID_LN2) ? PT_GEMM_LN : PT_GEMM, stream,
+                  2.0 * (double)p.M * (double)p.N * (double)p.K);
     if (NC == 2) {
         // one CTA pair (cluster of two, same TPC) per two SMs; the schedule walks pairs of 128-row tiles
         const int tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
@@ -732,9 +928,19 @@ int make_weight_tmap(WeightMaps* out, const void* w, int N, int K, int epi) {
     return make_tmap_2d_bf16(&out->pair, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(bn / 2), BK);
 }
 
+struct LnFuse {
+    const float* gamma1;   // EPI_RESID_LN2: the LayerNorm whose fp32 result replaces x
+    const float* beta1;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    void* out_bf16;
+    long long ld;
+};
+
 static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N,
                      int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
-                     float2* lse_part, cudaStream_t stream) {
+                     float2* lse_part, cudaStream_t stream, const LnFuse* ln = nullptr) {
     if (M <= 0) return WB_OK;
     WB_REQUIRE(N > 0 && K > 0, WB_ERR_BAD_ARG, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     WB_REQUIRE((K % 8) == 0 && (lda % 8) == 0, WB_ERR_BAD_ARG,
@@ -743,10 +949,21 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
     if (epi == EPI_GLU_BF16) {
         WB_REQUIRE((N % 256) == 0 && (ldc % 8) == 0, WB_ERR_BAD_ARG, "gemm GLU: N %% 256 and ldc %% 8 required");
     }
-    if (epi == EPI_RESID_F32 || epi == EPI_F32) {
+    const bool ln_epi = (epi == EPI_RESID_LN || epi == EPI_RESID_LN2);
+    if (epi == EPI_RESID_F32 || epi == EPI_F32 || ln_epi) {
         WB_REQUIRE(!split3, WB_ERR_BAD_ARG, "gemm: split3 only for bf16 outputs");
     }
     const int bn = gemm_bn_for(N, K, epi);
+    if (ln_epi) {
+        WB_REQUIRE(ln != nullptr && N == 256 && bn == 256 && bias != nullptr, WB_ERR_BAD_ARG,
+                   "gemm: the fused residual + LayerNorm epilogue needs N == 256 and a bias");
+        WB_REQUIRE(((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(ln->gamma) |
+                     reinterpret_cast<uintptr_t>(ln->beta) | reinterpret_cast<uintptr_t>(out) |
+                     reinterpret_cast<uintptr_t>(ln->gamma1) | reinterpret_cast<uintptr_t>(ln->beta1)) & 15) == 0 &&
+                       (epi == EPI_RESID_LN || (ln->gamma1 != nullptr && ln->beta1 != nullptr)) &&
+                       (ldc % 4) == 0 && (ln->ld % 8) == 0 && (reinterpret_cast<uintptr_t>(ln->out_bf16) & 15) == 0,
+                   WB_ERR_BAD_ARG, "gemm: fused residual + LayerNorm operands must be 16-byte aligned");
+    }
     const bool pair = gemm_use_pair(M, bn, K);
     CUtensorMap ta, tb_local;
     int rc = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
@@ -772,7 +989,7 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
     // output tensor map: 32-row x 128-byte boxes (one per epilogue warp and column group)
     CUtensorMap tc;
     memset(&tc, 0, sizeof(tc));
-    const bool f32_out = (epi == EPI_RESID_F32 || epi == EPI_F32);
+    const bool f32_out = (epi == EPI_RESID_F32 || epi == EPI_F32 || ln_epi);
     const int out_cols = (epi == EPI_GLU_BF16) ? N / 2 : N;
     const int eb = f32_out ? 4 : 2;
     p.use_tma_out = (epi != EPI_LSE && !split3 && (ldc * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
@@ -784,6 +1001,17 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
     p.cblocks = 0;
     p.tile_tab = nullptr;
     p.lse_part = lse_part;
+    p.ln_g = ln ? ln->gamma : nullptr;
+    p.ln_b = ln ? ln->beta : nullptr;
+    p.ln_eps = ln ? ln->eps : 0.f;
+    p.ln1_g = ln ? ln->gamma1 : nullptr;
+    p.ln1_b = ln ? ln->beta1 : nullptr;
+    CUtensorMap tc2 = tc;
+    if (ln_epi) {
+        WB_REQUIRE(p.use_tma_out, WB_ERR_BAD_ARG, "gemm: fused residual + LayerNorm needs a TMA-compatible x");
+        rc = make_tmap_2d(&tc2, ln->out_bf16, 2, (uint64_t)M, (uint64_t)N, (uint64_t)ln->ld, 32, 64);
+        if (rc != WB_OK) return rc;
+    }
     const int num_kb = ceil_div(K, BK);
     p.res_ring = (bn == 256) ? (pair ? GemmCfg<256, 2>::res_ring(num_kb) : GemmCfg<256>::res_ring(num_kb))
                              : GemmCfg<128>::res_ring(num_kb);
@@ -793,10 +1021,10 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
 #define WB_GEMM_CASE(E)                                                                              \
     case E:                                                                                          \
         if (pair)                                                                                    \
-            return res ? launch_gemm<256, true, E, 2>(ta, *tb, tc, tc, p, stream)                    \
-                       : launch_gemm<256, false, E, 2>(ta, *tb, tc, tc, p, stream);                  \
-        return res ? launch_gemm<256, true, E, 1>(ta, *tb, tc, tc, p, stream)                        \
-                   : launch_gemm<256, false, E, 1>(ta, *tb, tc, tc, p, stream);
+            return res ? launch_gemm<256, true, E, 2>(ta, *tb, tc, tc2, p, stream)                   \
+                       : launch_gemm<256, false, E, 2>(ta, *tb, tc, tc2, p, stream);                 \
+        return res ? launch_gemm<256, true, E, 1>(ta, *tb, tc, tc2, p, stream)                       \
+                   : launch_gemm<256, false, E, 1>(ta, *tb, tc, tc2, p, stream);
             WB_GEMM_CASE(EPI_BF16)
             WB_GEMM_CASE(EPI_BF16_SILU)
             WB_GEMM_CASE(EPI_BF16_RELU)
@@ -804,11 +1032,14 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
             WB_GEMM_CASE(EPI_GLU_BF16)
             WB_GEMM_CASE(EPI_F32)
             WB_GEMM_CASE(EPI_LSE)
+            WB_GEMM_CASE(EPI_RESID_LN)
+            WB_GEMM_CASE(EPI_RESID_LN2)
 #undef WB_GEMM_CASE
             default:
                 WB_REQUIRE(false, WB_ERR_BAD_ARG, "gemm: unknown epilogue %d", epi);
         }
     }
+    WB_REQUIRE(!ln_epi, WB_ERR_BAD_ARG, "gemm: fused residual + LayerNorm needs 256-column tiles");
     if (num_kb <= GemmCfg<128>::kResMaxKB) {
         switch (epi) {
 #define WB_GEMM_CASE(E) \
@@ -832,8 +1063,34 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
 int gemm_bf16(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N,
               int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
               cudaStream_t stream) {
-    WB_REQUIRE(epi != EPI_LSE, WB_ERR_BAD_ARG, "gemm: this epilogue has its own entry point");
+    WB_REQUIRE(epi != EPI_LSE && epi != EPI_RESID_LN && epi != EPI_RESID_LN2, WB_ERR_BAD_ARG, "gemm: this epilogue has its own entry point");
     return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, epi, alpha, out, ldc, split3, nullptr, stream);
+}
+
+static int g_fuse_ln = -1;
+bool gemm_resid_ln_supported(int N) {
+    if (g_fuse_ln < 0) {
+        const char* e = getenv("WB_FUSE_LN");
+        g_fuse_ln = (e == nullptr) ? 1 : atoi(e);
+    }
+    return g_fuse_ln != 0 && N == 256;
+}
+
+int gemm_resid_ln(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
+                  const float* bias, float alpha, float* x, long long ldx, const float* gamma1, const float* beta1,
+                  const float* gamma, const float* beta, float eps, void* ln_out_bf16, long long ld_ln,
+                  cudaStream_t stream) {
+    WB_REQUIRE(N == 256, WB_ERR_UNSUPPORTED, "gemm_resid_ln: N = %d (only 256)", N);
+    LnFuse ln;
+    ln.gamma1 = gamma1;
+    ln.beta1 = beta1;
+    ln.gamma = gamma;
+    ln.beta = beta;
+    ln.eps = eps;
+    ln.out_bf16 = ln_out_bf16;
+    ln.ld = ld_ln;
+    return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, gamma1 ? EPI_RESID_LN2 : EPI_RESID_LN, alpha, x, ldx, 0, nullptr,
+                     stream, &ln);
 }
 
 int lse_parts(int N, int K) { return 2 * ceil_div(N, gemm_bn_for(N, K, EPI_LSE)); }

@@ -16,6 +16,8 @@ enum GemmEpi : int {
     EPI_GLU_BF16 = 4,   // out_bf16[:, N/2] = a * sigmoid(g), weight rows packed [16 a | 16 g] x N/32
     EPI_F32 = 5,        // out_f32  = alpha * (acc + bias)
     EPI_LSE = 6,        // no matrix output: per (row, 128-column half tile) partial log-sum-exp (max2, sum) of acc + bias
+    EPI_RESID_LN = 7,   // EPI_RESID_F32 + LayerNorm of the updated rows -> bf16 (gemm_resid_ln only; N == 256)
+    EPI_RESID_LN2 = 8,  // x = LayerNorm_1(x + alpha (acc + bias)) (fp32), out_bf16 = LayerNorm(x) (gemm_resid_ln with gamma1)
 };
 
 int gemm_bn_for(int N, int K, int epi = EPI_BF16);
@@ -38,6 +40,18 @@ int gemm_bf16(const void* A, long long lda, const WeightMaps* tmap_b_opt, const 
 // log-softmax denominators without the logits: part[row][2 * n_tiles] = (max of v log2 e, sum 2^(v log2 e - max)) over each
 // 128-column half of each n-tile of v = A B^T + bias.  lse_parts() = entries per row for a given N.
 int lse_parts(int N, int K);
+// x[M,N] (fp32, pitch ldx) += alpha * (A * B^T + bias), then ln_out_bf16 = LayerNorm(x) * gamma + beta, in ONE kernel:
+// the residual-update GEMMs of a Conformer layer (positionwise FFN w_2, attention linear_out, pointwise_conv2) are each
+// followed by the LayerNorm of the next module (encoder_layer.py:221-263), and with N = d = 256 an output tile holds whole
+// rows.  Supported when gemm_resid_ln_supported(N); callers fall back to gemm_bf16(EPI_RESID_F32) + layernorm_rows.
+// gamma1 / beta1 != null: the layer boundary - x = LayerNorm(gamma1, beta1)(x + ...) (norm_final, fp32, stored) and
+// ln_out_bf16 = LayerNorm(gamma, beta)(x) (the next layer's norm_ff_macaron), as layernorm2_rows.
+bool gemm_resid_ln_supported(int N);
+int gemm_resid_ln(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
+                  const float* bias, float alpha, float* x, long long ldx, const float* gamma1, const float* beta1,
+                  const float* gamma, const float* beta, float eps, void* ln_out_bf16, long long ld_ln,
+                  cudaStream_t stream);
+
 int gemm_lse_partials(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream);
 
