@@ -122,6 +122,16 @@ typedef struct {
                           the rescoring decoder reads its hi block and stays bf16.  Full forward only. */
   float ln_eps;        /* encoder LayerNorm eps (encoder_conf.norm_eps, 1e-5) */
   float dec_ln_eps;    /* decoder LayerNorm eps (decoder_conf.norm_eps, decoder.py:83); <= 0 means "same as ln_eps" */
+  int32_t arch;        /* 0: ConformerEncoder (conv2d subsampling, rel-pos attention, conv module) - everything above.
+                          1: Whisper = TransformerEncoder with input_layer conv1d2 (Conv1dSubsampling2, subsampling.py:117-171),
+                             pos_enc abs_pos_whisper (embedding.py:150-164), gelu FFN, key_bias false, pre-norm
+                             (wenet/models/whisper/whisper.py:28-96, encoder.py:365-440, encoder_layer.py:28-135);
+                             cnn_* / has_cmvn / precise are ignored (must be 0) */
+  int32_t dec_flavor;  /* 0: wenet TransformerDecoder input_layer "embed" (sinusoid PE, x*sqrt(d), relu).
+                          1: Whisper decoder: input_layer embed_learnable_pe (embedding.py:167-176, xscale 1), gelu;
+                             key_bias false and tie_word_embedding are weight-level properties (the packer delivers a zero
+                             key bias and the tied output matrix) */
+  int32_t dec_max_len; /* dec_flavor 1: rows of the learnable decoder position table (448) */
 } wb_model_config;
 
 enum { WB_F32 = 0, WB_BF16 = 1, WB_I32 = 2 };
@@ -291,12 +301,61 @@ int wb_decoder_logprobs(const wb_model* m, const void* enc_out_bf16_dev, int64_t
                         size_t workspace_bytes, wb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * F. autoregressive attention decoding — replaces attention_beam_search (wenet/models/transformer/search.py:252-371)
+ *    over TransformerDecoder.forward_one_step (decoder.py:226-281) with its self / cross attention caches
+ *    (decoder_layer.py:68-153, attention.py:431-520): decode mode "attention" of ASRModel.decode (asr_model.py:315-318)
+ *    and the only mode of Whisper (whisper.py:31).  Rows are utterance-major (b * beam + n).  The cross-attention K/V of
+ *    every layer are projected once per utterance; the self-attention cache is never re-ordered (a per-row ancestry
+ *    table replaces the reference's index_select of every layer's K/V, search.py:315-323).
+ *    prefix_host [batch][prefix_len]: the forced start of every hypothesis — {sos} for wenet models, {sot, language, task,
+ *    no_timestamps} for Whisper (common.py:159-238 add_whisper_tokens).  max_len = encoder_out.size(1) + 1 of the padded
+ *    reference batch = the token capacity incl. the prefix (the loop `for i in range(prefix_len, maxlen + 1)`).
+ *    Outputs: tokens_dev [batch][out_stride] = the best hypothesis of every utterance after the prefix with every <eos>
+ *    removed (search.py:357-371), lens_dev [batch], scores_dev [batch] (may be NULL) its score / len^length_penalty.
+ *    The call polls the "every hypothesis ended" flag (search.py:301-302) on the stream every 8 steps, i.e. it
+ *    synchronises the stream; *steps_run_host (may be NULL) receives the number of beam steps taken.
+ * ------------------------------------------------------------------------------------------ */
+size_t wb_attention_beam_workspace_bytes(const wb_model* m, int64_t enc_rows, int batch, int beam, int max_len);
+int wb_attention_beam_search(const wb_model* m, const void* enc_out_bf16_dev, int64_t enc_rows,
+                             const int32_t* seq_start_host, const int32_t* seq_len_host, int batch, int beam,
+                             const int32_t* prefix_host, int prefix_len, int eos, int max_len, float length_penalty,
+                             int32_t* tokens_dev, int out_stride, int32_t* lens_dev, float* scores_dev,
+                             int32_t* steps_run_host, void* workspace_dev, size_t workspace_bytes, wb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * G. Whisper (wb_model_config.arch = 1) — SURVEY section 8f-1, BASELINE configs[4]
+ *    log-mel: replaces compute_log_mel_spectrogram (wenet/dataset/processor.py:320-369): torch.stft(n_fft, hop, hann,
+ *    center / reflect) -> |.|^2 (last frame dropped) -> mel filterbank -> log10(clamp 1e-10) -> max(., utterance max - 8)
+ *    -> (. + 4) / 4.  window_host [n_fft] (torch.hann_window) and mel_host [num_mel][n_fft/2+1]
+ *    (librosa.filters.mel: slaney scale + slaney norm) are computed by the caller.  pcm_dev [batch][pcm_stride] float32 in
+ *    [-1, 1); feats_dev [batch][frames_stride][num_mel]; utterance b has num_samples[b] / hop frames, the rest of its
+ *    max_frames rows are zeroed (processor.padding); scratch_dev: batch int32.
+ *    encoder: replaces TransformerEncoder.forward (encoder.py:122-181 with encoder.py:365-440) for input_layer conv1d2
+ *    (subsampling.py:117-171), abs_pos_whisper (embedding.py:150-164), gelu.  padded_frames = xs.size(1) of the padded
+ *    reference batch (it fixes the sub-sampled mask parity, subsampling.py:171).  Output rows are packed as in section B:
+ *    utterance b owns T'_b = len_b / 2 (padded_frames even) or (len_b + 1) / 2 (odd) rows.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct wb_logmel wb_logmel;
+int wb_logmel_create(wb_logmel** out, int n_fft, int hop_length, int num_mel, const float* window_host,
+                     const float* mel_host);
+void wb_logmel_destroy(wb_logmel* lm);
+int wb_logmel_forward(const wb_logmel* lm, const float* pcm_dev, int64_t pcm_stride, const int32_t* num_samples_dev,
+                      int batch, float* feats_dev, int64_t frames_stride, int max_frames, int32_t* scratch_dev,
+                      wb_stream_t stream);
+int64_t wb_whisper_encoder_out_rows(int batch, const int32_t* feat_lens_host, int padded_frames);
+size_t wb_whisper_encoder_workspace_bytes(const wb_model* m, int batch, const int32_t* feat_lens_host, int padded_frames);
+int wb_whisper_encoder_forward(const wb_model* m, const float* feats_dev, int64_t feats_stride_b,
+                               const int32_t* feat_lens_host, int batch, int padded_frames, float* enc_out_dev,
+                               void* enc_out_bf16_dev, int32_t* seq_start_dev, int32_t* seq_len_dev, void* workspace_dev,
+                               size_t workspace_bytes, wb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Operator-level entry points (used by the parity tests and micro-benchmarks; same kernels the
  * stage entry points launch).
  * ------------------------------------------------------------------------------------------ */
 /* C = epi(A[M,K] * B[N,K]^T + bias); A, B bf16 row-major (lda, K); epi: 0 bf16, 1 bf16+SiLU,
  * 2 bf16+ReLU, 3 fp32 residual add (C += alpha*(.)), 4 GLU->bf16 (weights packed [16 value|16 gate]
- * per 32 rows), 5 fp32 */
+ * per 32 rows), 5 fp32, 9 bf16+GELU (erf) */
 int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K,
                const float* bias_dev, int epi, float alpha, void* c_dev, int64_t ldc, int split3,
                wb_stream_t stream);
@@ -331,6 +390,14 @@ int wb_op_dwconv(const void* g_dev, int64_t ldg, const int32_t* seq_start_dev,
                  int norm_type, const float* gamma_dev, const float* beta_dev, float eps,
                  const float* pad_vec_dev, int pad_until, void* out_dev, int64_t ldo,
                  wb_stream_t stream);
+/* one step of attention_beam_search after the decoder call (search.py:309-355 + mask.py:258-310): rows are b * beam + n;
+ * topk_* [R][beam] log-softmax top-`beam` of every row; score / end flags [R]; hyp / anc [R][max_len] (tokens, ancestry of
+ * the self-attention cache); pos = position of the token just consumed.  Candidates are ranked (score desc, index asc). */
+int wb_op_attention_beam_step(const float* topk_val_dev, const int32_t* topk_idx_dev, const float* score_in_dev,
+                              const int32_t* end_in_dev, const int32_t* hyp_in_dev, const int32_t* anc_in_dev, int batch,
+                              int beam, int max_len, int pos, int eos, float* score_out_dev, int32_t* end_out_dev,
+                              int32_t* hyp_out_dev, int32_t* anc_out_dev, int32_t* next_tok_dev, int32_t* next_pos_dev,
+                              int32_t* utt_ended_dev, wb_stream_t stream);
 int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blank_id,
                           float blank_penalty, int topk, float* topk_val_dev, int32_t* topk_idx_dev,
                           wb_stream_t stream);

@@ -205,10 +205,71 @@ def stream_goldens(name, recipe, n_samples, chunk=16, left=4, row_stride=2, cach
     print(name, "chunks", len(outs), "frames", ys.size(1), "size %.0f KB" % (os.path.getsize(path) / 1024))
 
 
+def attention_goldens(name, recipe, ns, beam=4, length_penalty=0.0):
+    """decode mode "attention" (asr_model.py:315-318 -> search.py:252-371) of a Conformer recipe: the reference's best
+    hypothesis per utterance on the reference's own encoder output."""
+    cfg, model = _ref_model(recipe)
+    xs, lens = _ref_batch(ns)
+    out = {"num_samples": np.array(ns), "beam": np.array(beam), "length_penalty": np.array(length_penalty)}
+    with torch.no_grad():
+        res = model.decode(["attention"], xs, lens, beam_size=beam, length_penalty=length_penalty)["attention"]
+    for b, r in enumerate(res):
+        out["att%d" % b] = np.array(r.tokens, dtype=np.int32)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "attention tokens", [len(r.tokens) for r in res], res[0].tokens[:10])
+
+
+def whisper_goldens(name="whisper_tiny", recipe="whisper_tiny", ns=(32000 + 77, 24000, 11200), beam=4):
+    """Whisper (wenet/models/whisper/whisper.py) at test size: the reference's compute_log_mel_spectrogram (with the
+    restated slaney filterbank injected as librosa.filters.mel - librosa is not installed), encoder output on the zero
+    padded batch, and attention decoding with the forced [sot, language, task, no_timestamps] prefix."""
+    import types
+    from oracle import wenet_oracle as O
+    cfg = synth.recipe(recipe)
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    model = shim.init_reference_model(dict(cfg))
+    model.load_state_dict(sd, strict=True)
+    import wenet.dataset.processor as processor
+    sys.modules["librosa"].filters = types.SimpleNamespace(
+        mel=lambda sr, n_fft, n_mels: O.slaney_mel_filters(sr, n_fft, n_mels).numpy())
+    mel = cfg["input_dim"]
+    pcm = synth.synth_pcm(len(ns), list(ns), seed=SEED)
+    feats = []
+    for b, n in enumerate(ns):
+        wav = (pcm[b, :n].float() / 32768.0).unsqueeze(0)
+        feats.append(processor.compute_log_mel_spectrogram(dict(key="k", wav=wav, sample_rate=16000), n_fft=400, hop_length=160,
+                                                           num_mel_bins=mel)["feat"])
+    lens = torch.tensor([f.shape[0] for f in feats])
+    xs = torch.zeros(len(ns), int(lens.max()), mel)
+    for b, f in enumerate(feats):
+        xs[b, :f.shape[0]] = f
+    infos = {"tasks": ["transcribe", "translate", "transcribe"][:len(ns)], "langs": ["en", "zh", "zh"][:len(ns)]}
+    out = {"num_samples": np.array(ns), "beam": np.array(beam), "feats": xs.numpy(), "feat_lens": lens.numpy(),
+           "tasks": np.array(infos["tasks"]), "langs": np.array(infos["langs"])}
+    with torch.no_grad():
+        enc, mask = model.encoder(xs, lens)
+        out["enc_out"] = enc.numpy()
+        out["enc_lens"] = mask.squeeze(1).sum(1).numpy()
+        res = model.decode(["attention"], xs, lens, beam_size=beam, infos=infos)["attention"]
+        for b, r in enumerate(res):
+            out["att%d" % b] = np.array(r.tokens, dtype=np.int32)
+        # odd padded length: the other parity of subsampling.py:171
+        xs_odd = xs[:, :xs.shape[1] - 1]
+        lens_odd = torch.minimum(lens, torch.tensor(xs_odd.shape[1]))
+        enc_o, mask_o = model.encoder(xs_odd, lens_odd)
+        out["enc_out_odd"] = enc_o.numpy()
+        out["enc_lens_odd"] = mask_o.squeeze(1).sum(1).numpy()
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "feats", tuple(xs.shape), "enc", tuple(enc.shape), "attention tokens", [len(r.tokens) for r in res],
+          "size %.0f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["fbank", "tiny", "tiny_bn", "u2pp_small", "u2pp_small_long", "u2pp_large_10s",
-                             "u2pp_small_stream"]
+                             "u2pp_small_stream", "tiny_attention", "whisper_tiny"]
     if "fbank" in which:
         fbank_goldens()
     if "tiny" in which:
@@ -221,5 +282,10 @@ if __name__ == "__main__":
         long_goldens("u2pp_small_long", "u2pp_small", [480000, 272000], beam=10, row_stride=4)
     if "u2pp_large_10s" in which:       # BASELINE configs[2] model (24L/512d/8h) at depth
         long_goldens("u2pp_large_10s", "u2pp_large", [160000], beam=10, row_stride=2)
+    if "tiny_attention" in which:       # decode mode "attention" on the test-sized recipes
+        attention_goldens("tiny_attention", "tiny", [32000 + 123, 20800, 48000], beam=4)
+        attention_goldens("tiny_bn_attention", "tiny_bn", [32000 + 123, 20800, 48000], beam=3, length_penalty=0.5)
+    if "whisper_tiny" in which:         # SURVEY section 8f-1 at test size
+        whisper_goldens()
     if "u2pp_small_stream" in which:    # BASELINE configs[3]: chunk 16 / left 4, 21 chunks on the 12-layer model
         stream_goldens("u2pp_small_stream", "u2pp_small", 224000)

@@ -123,7 +123,7 @@ def _ln(x, p, name, eps=1e-5):
 
 def _linear(x, p, name, quant=None, bias=True):
     w = _q(quant, p[name + ".weight"])
-    return F.linear(_q(quant, x), w, p[name + ".bias"] if bias else None)
+    return F.linear(_q(quant, x), w, p.get(name + ".bias") if bias else None)   # key_bias=False: no bias key
 
 
 def _ffn(x, p, pre, act, quant):
@@ -555,4 +555,173 @@ def attention_rescoring(p, dcfg, beam_results, encoder_outs, encoder_lens, sos, 
                 best_index = i
         out.append(dict(best_index=best_index, best_score=best_score, scores=scores,
                         tokens=hyps[best_index] if hyps else []))
+    return out
+
+
+# =============================================================================================
+# Whisper: log-mel front-end, TransformerEncoder with Conv1dSubsampling2, and the
+# autoregressive attention_beam_search shared with ASRModel.decode(mode "attention")
+# =============================================================================================
+def slaney_mel_filters(sr: int = 16000, n_fft: int = 400, n_mels: int = 128) -> torch.Tensor:
+    """librosa.filters.mel(sr, n_fft, n_mels) (slaney scale, slaney norm) restated from its published algorithm; the
+    reference calls it at processor.py:360-361.  PARITY UNPINNED for this one function: librosa is not installed in the
+    build container, so only its call site is pinned (tests/test_oracle_pin.py injects this restatement as
+    librosa.filters.mel and compares everything around it with the reference's own compute_log_mel_spectrogram)."""
+    def hz_to_mel(f):
+        f_sp, min_log_hz = 200.0 / 3, 1000.0
+        if f >= min_log_hz:
+            return min_log_hz / f_sp + math.log(f / min_log_hz) / (math.log(6.4) / 27.0)
+        return f / f_sp
+
+    def mel_to_hz(m):
+        f_sp, min_log_hz = 200.0 / 3, 1000.0
+        min_log_mel = min_log_hz / f_sp
+        if m >= min_log_mel:
+            return min_log_hz * math.exp(math.log(6.4) / 27.0 * (m - min_log_mel))
+        return f_sp * m
+
+    nb = 1 + n_fft // 2
+    fft = [i * (sr / 2.0) / (nb - 1) for i in range(nb)]
+    lo, hi = hz_to_mel(0.0), hz_to_mel(sr / 2.0)
+    mel_f = [mel_to_hz(lo + (hi - lo) * i / (n_mels + 1)) for i in range(n_mels + 2)]
+    w = torch.zeros(n_mels, nb, dtype=torch.float64)
+    for i in range(n_mels):
+        for k in range(nb):
+            lower = (fft[k] - mel_f[i]) / (mel_f[i + 1] - mel_f[i])
+            upper = (mel_f[i + 2] - fft[k]) / (mel_f[i + 2] - mel_f[i + 1])
+            w[i, k] = max(0.0, min(lower, upper)) * 2.0 / (mel_f[i + 2] - mel_f[i])
+    return w.float()
+
+
+def log_mel_spectrogram(waveform: torch.Tensor, n_fft: int = 400, hop_length: int = 160, num_mel_bins: int = 80,
+                        sample_rate: int = 16000) -> torch.Tensor:
+    """processor.py:320-369 with padding = 0, pad_or_trim = False.  waveform (n,) float in [-1, 1) -> (n // hop, mel)."""
+    window = torch.hann_window(n_fft)
+    stft = torch.stft(waveform, n_fft, hop_length, window=window, return_complex=True)
+    magnitudes = stft[..., :-1].abs() ** 2
+    mel_spec = slaney_mel_filters(sample_rate, n_fft, num_mel_bins) @ magnitudes
+    log_spec = torch.clamp(mel_spec, min=1e-10).log10()
+    log_spec = torch.maximum(log_spec, log_spec.max() - 8.0)
+    log_spec = (log_spec + 4.0) / 4.0
+    return log_spec.transpose(0, 1)
+
+
+def whisper_sinusoids(max_len: int, d: int) -> torch.Tensor:
+    # embedding.py:150-164
+    inc = math.log(10000) / (d // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(d // 2))
+    st = torch.arange(max_len)[:, None] * inv[None, :]
+    return torch.cat([torch.sin(st), torch.cos(st)], dim=1)
+
+
+def whisper_encoder_forward(p, heads: int, xs: torch.Tensor, xs_lens: torch.Tensor, quant=None):
+    """TransformerEncoder.forward (encoder.py:122-181) for conv1d2 / abs_pos_whisper / gelu / pre-norm:
+    Conv1dSubsampling2 (subsampling.py:117-171), layers (encoder_layer.py:28-135), after_norm.
+    xs (B, T, idim) zero padded, xs_lens (B,).  Returns (B, T', d), masks (B, 1, T')."""
+    B, T, _ = xs.shape
+    masks = ~make_pad_mask(xs_lens, T).unsqueeze(1)
+    x = xs.transpose(1, 2)
+    x = F.gelu(F.conv1d(_q(quant, x), _q(quant, p["encoder.embed.conv.0.weight"]), p["encoder.embed.conv.0.bias"], padding=1))
+    x = F.gelu(F.conv1d(_q(quant, x), _q(quant, p["encoder.embed.conv.2.weight"]), p["encoder.embed.conv.2.bias"], stride=2,
+                        padding=1))
+    x = _q(quant, x.transpose(1, 2))
+    d = x.shape[-1]
+    pe = p.get("encoder.embed.pos_enc.pe")
+    pe = whisper_sinusoids(1500, d) if pe is None else pe.reshape(-1, d)
+    x = x + pe[:x.shape[1]].unsqueeze(0)                      # xscale = 1
+    masks = masks[:, :, (T + 1) % 2::2]
+    n_layers = 0
+    while "encoder.encoders.%d.norm1.weight" % n_layers in p:
+        n_layers += 1
+    for i in range(n_layers):
+        lp = "encoder.encoders.%d" % i
+        xn = _ln(x, p, lp + ".norm1")
+        x = x + _mha(xn, xn, masks, p, lp + ".self_attn", heads, quant)
+        x = x + _ffn(_ln(x, p, lp + ".norm2"), p, lp + ".feed_forward", F.gelu, quant)
+    return _ln(x, p, "encoder.after_norm"), masks
+
+
+def decoder_last_logp(p, pre, n_layers, heads, memory, mem_mask, hyps, flavor: str, quant=None):
+    """TransformerDecoder.forward_one_step (decoder.py:226-281) WITHOUT the caches: the decoder is re-run on the whole
+    prefix and the last position kept - the caches (decoder_layer.py:101-139) only memoise exactly these values.
+    memory (Bm, T, d) with Bm == B or B % Bm == 0 (the beams of an utterance share it, attention.py:488-497).
+    flavor "wenet": emb * sqrt(d) + sinusoid PE, relu; "whisper": emb + learnable PE, gelu."""
+    R, L = hyps.shape
+    d = memory.shape[-1]
+    if memory.shape[0] != R:
+        rep = R // memory.shape[0]
+        memory = memory.repeat_interleave(rep, dim=0)
+        mem_mask = mem_mask.repeat_interleave(rep, dim=0)
+    emb = F.embedding(hyps, p[pre + ".embed.0.weight"])
+    if flavor == "whisper":
+        x = emb + p[pre + ".embed.1.pe"].reshape(-1, d)[:L].unsqueeze(0)
+        act = F.gelu
+    else:
+        x = emb * math.sqrt(d) + sinusoid_pe(5000, d)[:L].unsqueeze(0)
+        act = F.relu
+    tgt_mask = torch.tril(torch.ones(L, L, dtype=torch.bool)).unsqueeze(0).expand(R, L, L)
+    if quant is not None:
+        memory = quant(memory)
+    for i in range(n_layers):
+        lp = "%s.decoders.%d" % (pre, i)
+        xn = _ln(x, p, lp + ".norm1")
+        x = x + _mha(xn, xn, tgt_mask, p, lp + ".self_attn", heads, quant)
+        x = x + _mha(_ln(x, p, lp + ".norm2"), memory, mem_mask, p, lp + ".src_attn", heads, quant)
+        x = x + _ffn(_ln(x, p, lp + ".norm3"), p, lp + ".feed_forward", act, quant)
+    y = _ln(x[:, -1], p, pre + ".after_norm")
+    return torch.log_softmax(_linear(y, p, pre + ".output_layer", quant), dim=-1)
+
+
+def beam_step(top_k_logp, top_k_index, scores, end_flag, hyps, beam_size: int, eos: int):
+    """One iteration of search.py:309-355 after the decoder call: masks (mask.py:258-310), second prune, hypothesis
+    update.  Shapes as the reference: (B*N, N), (B*N, N), (B*N, 1), (B*N, 1) bool, (B*N, i)."""
+    running = top_k_logp.shape[0]
+    batch = running // beam_size
+    top_k_logp = top_k_logp.clone()
+    top_k_index = top_k_index.clone()
+    for r in range(running):
+        if bool(end_flag[r]):
+            top_k_logp[r, 0] = 0.0
+            top_k_logp[r, 1:] = -float("inf")
+            top_k_index[r, :] = eos
+    cand = (scores + top_k_logp).view(batch, beam_size * beam_size)
+    new_scores = torch.zeros(batch, beam_size)
+    new_hyps = torch.zeros(running, hyps.shape[1] + 1, dtype=torch.long)
+    parents = torch.zeros(running, dtype=torch.long)
+    for b in range(batch):
+        order = sorted(range(beam_size * beam_size), key=lambda c: (-float(cand[b, c]), c))[:beam_size]
+        for n, c in enumerate(order):
+            pr = b * beam_size + c // beam_size
+            new_scores[b, n] = cand[b, c]
+            new_hyps[b * beam_size + n, :-1] = hyps[pr]
+            new_hyps[b * beam_size + n, -1] = top_k_index[pr, c % beam_size]
+            parents[b * beam_size + n] = pr
+    new_end = new_hyps[:, -1].eq(eos).view(-1, 1)
+    return new_scores.view(-1, 1), new_end, new_hyps, parents
+
+
+def attention_beam_search(p, pre, n_layers, heads, encoder_out, encoder_mask, beam_size: int, prefix, eos: int,
+                          length_penalty: float = 0.0, flavor: str = "wenet", quant=None) -> List[List[int]]:
+    """search.py:252-371.  prefix: (B, P) long - [[sos]] * B for wenet models, add_whisper_tokens' forced start for
+    Whisper (common.py:198-226).  Returns the best hypothesis of every utterance (prefix and eos stripped)."""
+    B, maxlen = encoder_out.shape[0], encoder_out.shape[1]
+    running = B * beam_size
+    hyps = torch.as_tensor(prefix, dtype=torch.long).repeat_interleave(beam_size, dim=0)
+    P = hyps.shape[1]
+    scores = torch.tensor([0.0] + [-float("inf")] * (beam_size - 1)).repeat(B).unsqueeze(1)
+    end_flag = torch.zeros_like(scores, dtype=torch.bool)
+    for i in range(P, maxlen + 1):
+        if int(end_flag.sum()) == running:
+            break
+        logp = decoder_last_logp(p, pre, n_layers, heads, encoder_out, encoder_mask, hyps, flavor, quant)
+        top_k_logp, top_k_index = logp.topk(beam_size)
+        scores, end_flag, hyps, _ = beam_step(top_k_logp, top_k_index, scores, end_flag, hyps, beam_size, eos)
+    scores = scores.view(B, beam_size)
+    lengths = hyps.ne(eos).sum(dim=1).view(B, beam_size).float()
+    scores = scores / lengths.pow(length_penalty)
+    best = scores.argmax(dim=-1)
+    out = []
+    for b in range(B):
+        h = hyps[b * beam_size + int(best[b])][P:]
+        out.append(h[h != eos].tolist())
     return out

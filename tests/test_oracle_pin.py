@@ -209,3 +209,77 @@ def test_context_graph_restated_vs_reference(tmp_path):
         assert a.nbest_scores == b["nbest_scores"]
         assert a.nbest_times == b["nbest_times"]
     assert any(g["nbest"] != p["nbest"] for g, p in zip(got, plain))
+
+
+@needs_ref
+def test_attention_beam_search_oracle_matches_reference_conformer():
+    """decode mode "attention" of a U2++ model (asr_model.py:315-318 -> search.py:252-371, left decoder,
+    decoder.py:466-488): the cache-free restatement equals the reference's cached forward_one_step loop."""
+    from wenet_b200 import synth
+    cfg = synth.recipe("tiny")
+    sd = synth.synth_state_dict(cfg, seed=777)
+    model = shim.init_reference_model(dict(cfg, cmvn=None))
+    model.load_state_dict({k: v for k, v in sd.items() if k in model.state_dict()}, strict=False)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    torch.manual_seed(5)
+    enc = torch.randn(2, 21, 128)
+    lens = torch.tensor([21, 13])
+    mask = ~O.make_pad_mask(lens, 21).unsqueeze(1)
+    from wenet.models.transformer.search import attention_beam_search
+    for beam, lp in ((4, 0.0), (3, 0.6)):
+        with torch.no_grad():
+            ref = attention_beam_search(model, enc, mask, beam, lp)
+            got = O.attention_beam_search(p, "decoder.left_decoder", 2, 2, enc, mask, beam,
+                                          [[model.sos_symbol()]] * 2, model.eos_symbol(), lp, "wenet")
+        assert [list(r.tokens) for r in ref] == got
+
+
+@needs_ref
+def test_whisper_oracle_matches_reference():
+    """Whisper (wenet/models/whisper/whisper.py): log-mel call site, TransformerEncoder (conv1d2 / abs_pos_whisper / gelu),
+    attention_beam_search with the forced Whisper prefix."""
+    import sys as _sys
+    from wenet_b200 import synth
+    cfg = synth.recipe("whisper_tiny")
+    sd = synth.synth_state_dict(cfg, seed=777)
+    model = shim.init_reference_model(dict(cfg))
+    model.load_state_dict(sd, strict=True)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    # log-mel: the reference's own function with the restated filterbank injected as librosa.filters.mel
+    import types
+    import wenet.dataset.processor as processor
+    lib = _sys.modules["librosa"]
+    lib.filters = types.SimpleNamespace(mel=lambda sr, n_fft, n_mels: O.slaney_mel_filters(sr, n_fft, n_mels).numpy())
+    pcm = synth.synth_pcm(1, [16000 * 2 + 77], seed=3)[0, :16000 * 2 + 77].float() / 32768.0
+    ref = processor.compute_log_mel_spectrogram(dict(key="k", wav=pcm.unsqueeze(0), sample_rate=16000), n_fft=400,
+                                                hop_length=160, num_mel_bins=32)["feat"]
+    got = O.log_mel_spectrogram(pcm, 400, 160, 32)
+    assert got.shape == ref.shape and (got - ref).abs().max().item() < 1e-5
+    # slaney filterbank sanity: every filter is a non-negative triangle of area ~ 1 Hz^-1 * df (slaney norm), rows overlap
+    fb = O.slaney_mel_filters(16000, 400, 128)
+    assert fb.shape == (128, 201) and float(fb.min()) >= 0.0 and int((fb.sum(1) > 0).sum()) == 128
+    assert abs(float((fb.sum(1) * 40.0)[100:].mean()) - 1.0) < 0.05        # bin spacing 40 Hz: area normalised filters
+    # encoder, odd and even padded lengths (subsampling.py:171 mask parity)
+    torch.manual_seed(1)
+    for T, lens in ((150, [150, 111, 64]), (151, [151, 100, 37])):
+        xs = torch.randn(3, T, 32) * 0.5
+        xl = torch.tensor(lens)
+        for b in range(3):
+            xs[b, lens[b]:] = 0.0
+        with torch.no_grad():
+            r_out, r_mask = model.encoder(xs, xl)
+            g_out, g_mask = O.whisper_encoder_forward(p, 2, xs, xl)
+        assert torch.equal(r_mask, g_mask)
+        for b in range(3):
+            n = int(r_mask[b].sum())
+            assert (r_out[b, :n] - g_out[b, :n]).abs().max().item() < 2e-5
+    # attention decoding
+    from wenet.models.transformer.search import attention_beam_search
+    from wenet_b200.whisper import whisper_prefix
+    infos = {"tasks": ["transcribe", "transcribe", "translate"], "langs": ["en", "zh", "en"]}
+    with torch.no_grad():
+        ref = attention_beam_search(model, r_out, r_mask, 4, 0.0, infos)
+        prefix = whisper_prefix(cfg["tokenizer_conf"]["special_tokens"], infos["tasks"], infos["langs"])
+        got = O.attention_beam_search(p, "decoder", 2, 2, r_out, r_mask, 4, prefix.tolist(), model.eos, 0.0, "whisper")
+    assert [list(r.tokens) for r in ref] == got
+    assert sum(len(g) for g in got) > 0

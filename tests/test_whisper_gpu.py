@@ -1,0 +1,178 @@
+"""Whisper path and decode mode "attention" on the GPU (through the C ABI) against the committed goldens produced by the
+UNMODIFIED reference (oracle/make_goldens.py: tiny_attention, tiny_bn_attention, whisper_tiny) and the CPU oracle.
+
+Tolerances:
+  * log-mel: |GPU - reference| <= 2e-3 in the normalised (x + 4) / 4 domain (two fp32 DFTs; values floor at max - 8 decades)
+  * Whisper encoder_out (bf16 GEMM operands) vs the fp32 reference: max <= 6e-2, mean <= 8.2e-3 (the reference's own bf16
+    autocast yard-stick used for the Conformer path) AND within 3x of the bf16-emulating oracle's
+    own distance from fp32
+  * attention decoding: best-hypothesis token ids identical to the reference's (the bf16-emulating oracle reproduces the
+    goldens, i.e. the margins of these fixtures exceed the operand-rounding noise)
+  * one beam step on given inputs (op-level): exact
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import SEED, err, load_golden
+from oracle import wenet_oracle as O
+from wenet_b200 import synth
+
+
+def _whisper_model():
+    from wenet_b200.whisper import B200Whisper
+    cfg = synth.recipe("whisper_tiny")
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    return cfg, sd, B200Whisper(cfg, sd)
+
+
+def test_logmel_golden():
+    from wenet_b200.whisper import LogMelExtractor
+    g = load_golden("whisper_tiny")
+    ns = g["num_samples"].tolist()
+    pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
+    ex = LogMelExtractor(32, 400, 160)
+    x = (pcm.float() / 32768.0).cuda()
+    feats = ex(x, torch.tensor(ns, dtype=torch.int32, device="cuda"), max_frames=g["feats"].shape[1]).cpu()
+    ref = torch.from_numpy(g["feats"])
+    for b, n in enumerate(ns):
+        m = int(g["feat_lens"][b])
+        assert m == ex.num_frames(n)
+        mx, mean = err(feats[b, :m], ref[b, :m])
+        print("log-mel utt %d: max %.2e mean %.2e" % (b, mx, mean))
+        assert mx <= 2e-3 and mean <= 5e-5
+        assert float(feats[b, m:].abs().max()) == 0.0 if m < feats.shape[1] else True
+    # the oracle restatement on the same audio (runs everywhere, no reference needed)
+    o = O.log_mel_spectrogram(pcm[0, :ns[0]].float() / 32768.0, 400, 160, 32)
+    assert err(feats[0, :o.shape[0]], o)[0] <= 2e-3
+
+
+@pytest.mark.parametrize("parity", ["even", "odd"])
+def test_whisper_encoder_golden(parity):
+    g = load_golden("whisper_tiny")
+    cfg, sd, model = _whisper_model()
+    xs = torch.from_numpy(g["feats"])
+    lens = torch.from_numpy(g["feat_lens"]).long()
+    key_o, key_l = "enc_out", "enc_lens"
+    if parity == "odd":
+        xs = xs[:, :xs.shape[1] - 1]
+        lens = torch.minimum(lens, torch.tensor(xs.shape[1]))
+        key_o, key_l = "enc_out_odd", "enc_lens_odd"
+    out, masks = model.encoder(xs.cuda(), lens.cuda())
+    ref = torch.from_numpy(g[key_o])
+    assert out.shape == ref.shape
+    assert masks.squeeze(1).sum(1).cpu().tolist() == g[key_l].tolist()
+    with torch.no_grad():
+        emu, _ = O.whisper_encoder_forward(sd, 2, xs, lens, O.bf16_round)
+    for b in range(xs.shape[0]):
+        n = int(g[key_l][b])
+        mx, mean = err(out[b, :n].cpu(), ref[b, :n])
+        emx, emean = err(emu[b, :n], ref[b, :n])
+        print("whisper enc (%s) utt %d: GPU vs fp32 reference max %.2e mean %.2e | bf16-emulating oracle max %.2e mean %.2e"
+              % (parity, b, mx, mean, emx, emean))
+        assert mx <= 6e-2 and mean <= 8.2e-3
+        assert mean <= 3.0 * emean + 1e-4
+        assert float(out[b, n:].abs().max()) == 0.0 if n < out.shape[1] else True
+
+
+def test_whisper_attention_decode_golden():
+    g = load_golden("whisper_tiny")
+    cfg, sd, model = _whisper_model()
+    xs = torch.from_numpy(g["feats"]).cuda()
+    lens = torch.from_numpy(g["feat_lens"]).cuda()
+    infos = {"tasks": [str(t) for t in g["tasks"]], "langs": [str(t) for t in g["langs"]]}
+    res = model.decode(["attention"], xs, lens, beam_size=int(g["beam"]), infos=infos)["attention"]
+    got = [list(r.tokens) for r in res]
+    want = [g["att%d" % b].tolist() for b in range(len(got))]
+    print("whisper attention decode: steps", model.last_attention_steps, "lens", [len(t) for t in got], "reference",
+          [len(t) for t in want])
+    assert got == want
+    # default infos (search.py:270-275) and beam 1 run through
+    r1 = model.decode(["attention"], xs, lens, beam_size=1)["attention"]
+    assert len(r1) == len(got)
+
+
+def test_whisper_ctc_modes_and_api():
+    g = load_golden("whisper_tiny")
+    cfg, sd, model = _whisper_model()
+    xs = torch.from_numpy(g["feats"]).cuda()
+    lens = torch.from_numpy(g["feat_lens"]).cuda()
+    blank = cfg["ctc_conf"]["ctc_blank_id"]
+    res = model.decode(["ctc_greedy_search", "ctc_prefix_beam_search"], xs, lens, beam_size=3, blank_id=blank)
+    out, masks = model.encoder(xs, lens)
+    lp = model.ctc_logprobs(out).cpu()
+    el = masks.squeeze(1).sum(1).cpu()
+    assert [list(r.tokens) for r in res["ctc_greedy_search"]] == O.ctc_greedy_search(lp, el, blank)
+    ob = O.ctc_prefix_beam_search(lp, el, 3, blank)
+    for b in range(xs.shape[0]):
+        assert [list(h) for h in res["ctc_prefix_beam_search"][b].nbest] == ob[b]["nbest"]
+    with pytest.raises(NotImplementedError):
+        model.decode(["attention_rescoring"], xs, lens, beam_size=3)
+    assert model.sos_symbol() == 100 and model.eos_symbol() == 99 and model.default_decode_method == "attention"
+
+
+@pytest.mark.parametrize("name,recipe", [("tiny_attention", "tiny"), ("tiny_bn_attention", "tiny_bn")])
+def test_attention_mode_conformer_golden(name, recipe):
+    """ASRModel.decode(["attention"]) (asr_model.py:315-318) on the U2++ / non-streaming test recipes."""
+    from wenet_b200.asr_model import B200ASRModel
+    from wenet_b200.fbank import FbankExtractor
+    g = load_golden(name)
+    ns = g["num_samples"].tolist()
+    cfg = synth.recipe(recipe)
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    model = B200ASRModel(cfg, sd)
+    pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
+    ex = FbankExtractor(80)
+    feats = ex(pcm.cuda(), torch.tensor(ns, dtype=torch.int32, device="cuda"))
+    lens = torch.tensor([ex.num_frames(n) for n in ns], dtype=torch.int64)
+    feats = feats[:, :int(lens.max())].contiguous()
+    res = model.decode(["attention", "ctc_greedy_search"], feats, lens.cuda(), beam_size=int(g["beam"]),
+                       length_penalty=float(g["length_penalty"]))
+    got = [list(r.tokens) for r in res["attention"]]
+    want = [g["att%d" % b].tolist() for b in range(len(ns))]
+    print(name, "steps", model.last_attention_steps, "lens", [len(t) for t in got])
+    assert got == want
+    assert len(res["ctc_greedy_search"]) == len(ns)
+
+
+def test_beam_step_exact():
+    """beam_step_kernel against the oracle's restatement of search.py:309-355 on random tables (finished rows, -inf scores,
+    the first step's [0, -inf, ...] initial scores): scores, tokens, end flags and ancestry exact."""
+    from wenet_b200 import _lib
+    from wenet_b200._lib import check, cur_stream, ptr
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    for B, N, pos in ((3, 4, 5), (2, 10, 0), (5, 1, 2), (1, 7, 9)):
+        R, L, eos, V = B * N, 16, 7, 50
+        logp = torch.randn(R, V, generator=g).log_softmax(-1)
+        topv, topi = logp.topk(N)
+        scores = torch.randn(R, 1, generator=g) * 3
+        if pos == 0:
+            scores = torch.tensor([0.0] + [-float("inf")] * (N - 1)).repeat(B).unsqueeze(1)
+        end = (torch.rand(R, 1, generator=g) < 0.3) if pos > 0 else torch.zeros(R, 1, dtype=torch.bool)
+        hyps = torch.randint(0, V, (R, pos + 1), generator=g)
+        hyps[end.squeeze(1), -1] = eos
+        anc = torch.randint(0, N, (R, L), generator=g) + (torch.arange(R) // N * N).unsqueeze(1)
+        ns, ne, nh, par = O.beam_step(topv, topi, scores, end, hyps, N, eos)
+        d = lambda t, dt: t.to(dt).contiguous().cuda()
+        hyp_in = torch.zeros(R, L, dtype=torch.int32)
+        hyp_in[:, :pos + 1] = hyps.int()
+        so, eo = torch.zeros(R, device="cuda"), torch.zeros(R, dtype=torch.int32, device="cuda")
+        ho, ao = torch.zeros(R, L, dtype=torch.int32, device="cuda"), torch.zeros(R, L, dtype=torch.int32, device="cuda")
+        nt, npz = torch.zeros(R, dtype=torch.int32, device="cuda"), torch.zeros(R, dtype=torch.int32, device="cuda")
+        ue = torch.zeros(B, dtype=torch.int32, device="cuda")
+        a = [d(topv, torch.float32), d(topi, torch.int32), d(scores.view(-1), torch.float32), d(end.view(-1), torch.int32),
+             hyp_in.cuda(), d(anc, torch.int32)]
+        check(lib.wb_op_attention_beam_step(ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), ptr(a[4]), ptr(a[5]), B, N, L, pos, eos,
+                                            ptr(so), ptr(eo), ptr(ho), ptr(ao), ptr(nt), ptr(npz), ptr(ue), cur_stream()),
+              "wb_op_attention_beam_step")
+        torch.cuda.synchronize()
+        assert torch.equal(so.cpu(), ns.view(-1))
+        assert eo.cpu().bool().tolist() == ne.view(-1).tolist()
+        assert torch.equal(ho.cpu()[:, :pos + 2].long(), nh)
+        assert nt.cpu().long().tolist() == nh[:, -1].tolist() and npz.cpu().tolist() == [pos + 1] * R
+        want_anc = torch.cat([anc[par][:, :pos], par.view(-1, 1)], dim=1)
+        assert torch.equal(ao.cpu()[:, :pos + 1].long(), want_anc)
+        assert ue.cpu().tolist() == ne.view(B, N).sum(1).tolist()

@@ -24,7 +24,8 @@ class WbModelConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "input_dim", "d_model", "heads", "ffn_dim", "enc_layers", "cnn_kernel", "cnn_causal",
         "cnn_norm", "vocab", "dec_layers", "rdec_layers", "dec_heads", "dec_ffn_dim", "max_pos",
-        "has_cmvn", "precise")] + [("ln_eps", C.c_float), ("dec_ln_eps", C.c_float)]
+        "has_cmvn", "precise")] + [("ln_eps", C.c_float), ("dec_ln_eps", C.c_float)] + [(n, C.c_int32) for n in (
+        "arch", "dec_flavor", "dec_max_len")]
 
 
 class WbContextGraph(C.Structure):
@@ -75,6 +76,15 @@ _PROTOS = {
     "wb_prefix_share_tables": (i32, [i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "wb_decoder_logprobs": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp,
                                    i64, vp, sz, vp]),
+    "wb_attention_beam_workspace_bytes": (sz, [vp, i64, i32, i32, i32]),
+    "wb_attention_beam_search": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, i32, i32, i32, f32, vp, i32, vp, vp, vp, vp, sz, vp]),
+    "wb_logmel_create": (i32, [C.POINTER(vp), i32, i32, i32, vp, vp]),
+    "wb_logmel_destroy": (None, [vp]),
+    "wb_logmel_forward": (i32, [vp, vp, i64, vp, i32, vp, i64, i32, vp, vp]),
+    "wb_whisper_encoder_out_rows": (i64, [i32, vp, i32]),
+    "wb_whisper_encoder_workspace_bytes": (sz, [vp, i32, vp, i32]),
+    "wb_whisper_encoder_forward": (i32, [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
+    "wb_op_attention_beam_step": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "wb_op_gemm": (i32, [vp, i64, vp, i32, i32, i32, vp, i32, f32, vp, i64, i32, vp]),
     "wb_op_gemm_resid_ln": (i32, [vp, i64, vp, i32, i32, i32, vp, f32, vp, i64, vp, vp, vp, vp, f32, vp, i64, vp]),
     "wb_op_layernorm": (i32, [vp, i64, i32, i32, vp, vp, f32, vp, i64, i32, vp, i64, vp]),

@@ -428,8 +428,6 @@ class B200ASRModel:
         if context_graph is not None:
             from . import context as _ctx
             cg = _ctx.flatten(context_graph)      # the reference's ContextGraph object, or ContextArrays
-        if "attention" in methods:
-            raise NotImplementedError("autoregressive 'attention' decoding is not implemented (section 8f #1)")
         with torch.cuda.device(self.device):
             if simulate_streaming and decoding_chunk_size > 0:
                 ys, _ = self.encoder.forward_chunk_by_chunk(speech, decoding_chunk_size, num_decoding_left_chunks)
@@ -438,8 +436,17 @@ class B200ASRModel:
                 eo = self._encode(speech, speech_lengths, decoding_chunk_size, num_decoding_left_chunks)
             need_beam = ("ctc_prefix_beam_search" in methods) or ("attention_rescoring" in methods)
             topk = beam_size if need_beam else 1
-            logp, tv, ti = self._ctc(eo, topk, blank_id, blank_penalty, full=False)
             results = {}
+            if "attention" in methods:
+                # asr_model.py:315-318 -> search.py:252-371; maxlen = encoder_out.size(1) of the padded batch
+                T_in = speech.size(1)
+                maxlen = (((T_in - 1) // 2 - 1) // 2 if T_in >= 7 else 0) if not (simulate_streaming and decoding_chunk_size > 0) \
+                    else eo.max_len
+                prefix = np.full((speech.shape[0], 1), self.sos, dtype=np.int32)
+                results["attention"] = self._attention_beam(eo, beam_size, length_penalty, prefix, self.eos, maxlen)
+                if len(methods) == 1:
+                    return results
+            logp, tv, ti = self._ctc(eo, topk, blank_id, blank_penalty, full=False)
             if "ctc_greedy_search" in methods:
                 results["ctc_greedy_search"] = self._greedy(eo, ti, blank_id)
             if need_beam:
@@ -457,6 +464,34 @@ class B200ASRModel:
                 if rs is not None:
                     results["attention_rescoring"] = self._rescore_results(rs, meta, beam_out, reverse_weight)
         return results
+
+    def _attention_beam(self, eo: _EncOut, beam_size: int, length_penalty: float, prefix: np.ndarray, eos: int,
+                        maxlen: int) -> List[DecodeResult]:
+        """attention_beam_search (search.py:252-371) on the library: prefix [B, P] forced start tokens, maxlen =
+        encoder_out.size(1) of the padded batch (the reference's step bound)."""
+        if not self.dm.has_decoder:
+            raise _lib.WbError("decode mode 'attention' needs a decoder")
+        lib = self._lib
+        B, P = prefix.shape
+        max_tok = int(maxlen) + 1
+        if eo.rows == 0 or max_tok <= P:
+            return [DecodeResult([]) for _ in range(B)]
+        pe_len = self.spec.dec_max_len if self.spec.dec_flavor == 1 else self.spec.max_pos
+        max_tok = min(max_tok, pe_len + 1)     # the decoder's position table bounds the hypothesis length
+        stride = max_tok - P
+        toks = torch.zeros(B, stride, device=self.device, dtype=torch.int32)
+        lens = torch.zeros(B, device=self.device, dtype=torch.int32)
+        scores = torch.zeros(B, device=self.device, dtype=torch.float32)
+        wsb = lib.wb_attention_beam_workspace_bytes(self.dm.handle, eo.rows, B, int(beam_size), max_tok)
+        ws = self._workspace(wsb, 1)
+        steps = C.c_int32(0)
+        check(lib.wb_attention_beam_search(self.dm.handle, ptr(eo.bf16), eo.rows, ptr(_i32(eo.starts_host)),
+                                           ptr(_i32(eo.lens_host)), B, int(beam_size), ptr(_i32(prefix)), P, int(eos), max_tok,
+                                           float(length_penalty), ptr(toks), stride, ptr(lens), ptr(scores), C.byref(steps),
+                                           ptr(ws), wsb, cur_stream()), "wb_attention_beam_search")
+        self.last_attention_steps = int(steps.value)
+        th, lh = self._host(toks), self._host(lens)
+        return [DecodeResult(th[b, :lh[b]].tolist()) for b in range(B)]
 
     def _pack_padded(self, ys: torch.Tensor) -> _EncOut:
         B, Tp, d = ys.shape

@@ -1,6 +1,7 @@
 // C-ABI of libwenet_b200.so (see include/wenet_b200.h): handle management, weight upload,
 // operator-level entry points.  Stage orchestration lives in encoder.cu / rescoring.cu.
 #include "model.h"
+#include <math.h>
 #include <string.h>
 
 namespace wb {
@@ -77,6 +78,49 @@ static int finalize_decoder(Model* m, const std::string& pfx, int nlayers, Decod
     }
     RC(get_norm(m, pfx + ".after_norm", d, &D->after));
     RC(get_linear(m, pfx + ".out", V, d, true, &D->out));
+    if (m->cfg.dec_flavor == 1) {
+        // Whisper: embed_learnable_pe (embedding.py:167-176: xscale 1, learnable table), gelu FFN
+        WB_REQUIRE(m->cfg.dec_max_len > 0, WB_ERR_BAD_ARG, "dec_flavor 1 needs dec_max_len");
+        RC(model_get(m, pfx + ".pe", WB_F32, (int64_t)m->cfg.dec_max_len * d, &p));
+        D->pe = (const float*)p;
+        D->pe_len = m->cfg.dec_max_len;
+        D->xscale = 1.0f;
+        D->act_epi = EPI_BF16_GELU;
+    } else {
+        D->pe = nullptr;   // the encoder's sinusoid table (embedding.py:50-59)
+        D->pe_len = m->cfg.max_pos;
+        D->xscale = sqrtf((float)d);
+        D->act_epi = EPI_BF16_RELU;
+    }
+    return WB_OK;
+}
+
+// cfg.arch == 1: TransformerEncoder with Conv1dSubsampling2 / abs_pos_whisper (whisper.cu)
+static int finalize_whisper_encoder(Model* m) {
+    const wb_model_config& c = m->cfg;
+    const int d = c.d_model, ff = c.ffn_dim;
+    WB_REQUIRE(c.input_dim % 8 == 0 && c.input_dim > 0, WB_ERR_UNSUPPORTED, "whisper: input_dim %d must be a multiple of 8", c.input_dim);
+    WB_REQUIRE(!c.precise && !c.has_cmvn, WB_ERR_UNSUPPORTED, "whisper: precise mode / global CMVN are not part of this path");
+    WhisperEnc& E = m->wenc;
+    const void* p;
+    RC(get_linear(m, "wenc.conv1", d, 3 * c.input_dim, true, &E.conv1));
+    RC(get_linear(m, "wenc.conv2", d, 3 * d, true, &E.conv2));
+    RC(model_get(m, "wenc.pe", WB_F32, (int64_t)c.max_pos * d, &p));
+    E.pe = (const float*)p;
+    m->pe = E.pe;
+    E.layers.resize(c.enc_layers);
+    for (int i = 0; i < c.enc_layers; ++i) {
+        const std::string b = "wenc." + std::to_string(i);
+        TrLayer& L = E.layers[i];
+        RC(get_norm(m, b + ".norm1", d, &L.n1));
+        RC(get_norm(m, b + ".norm2", d, &L.n2));
+        RC(get_linear(m, b + ".att.qkv", 3 * d, d, true, &L.qkv));
+        RC(get_linear(m, b + ".att.out", d, d, true, &L.out));
+        RC(get_linear(m, b + ".ff.w1", ff, d, true, &L.ff1));
+        RC(get_linear(m, b + ".ff.w2", d, ff, true, &L.ff2));
+    }
+    RC(get_norm(m, "after_norm", d, &E.after));
+    m->after = E.after;
     return WB_OK;
 }
 
@@ -86,6 +130,19 @@ static int model_finalize(Model* m, cudaStream_t stream) {
                "unsupported attention geometry: d_model=%d heads=%d (d_k must be 64, d_model %% 128 == 0)", c.d_model,
                c.heads);
     WB_REQUIRE(c.input_dim >= 7 && c.ffn_dim % 64 == 0, WB_ERR_UNSUPPORTED, "unsupported input_dim/ffn_dim");
+    WB_REQUIRE(c.arch == 0 || c.arch == 1, WB_ERR_UNSUPPORTED, "unknown arch %d", c.arch);
+    if (c.arch == 1) {
+        if (c.dec_layers > 0)
+            WB_REQUIRE(c.dec_heads * 64 == c.d_model && c.dec_ffn_dim % 64 == 0, WB_ERR_UNSUPPORTED,
+                       "unsupported decoder geometry (heads=%d)", c.dec_heads);
+        RC(finalize_whisper_encoder(m));
+        if (c.vocab > 0 && m->tensors.count("ctc.w")) RC(get_linear(m, "ctc", c.vocab, c.d_model, true, &m->ctc));
+        if (m->cfg.dec_ln_eps <= 0.f) m->cfg.dec_ln_eps = m->cfg.ln_eps;
+        if (c.dec_layers > 0) RC(finalize_decoder(m, "dec.left", c.dec_layers, &m->left));
+        WB_CHECK_CUDA(cudaStreamSynchronize(stream));
+        m->finalized = true;
+        return WB_OK;
+    }
     WB_REQUIRE(c.cnn_kernel >= 1 && c.cnn_kernel <= 31 && (c.cnn_causal || c.cnn_kernel % 2 == 1), WB_ERR_UNSUPPORTED,
                "unsupported cnn_module_kernel %d", c.cnn_kernel);
     WB_REQUIRE(c.vocab > 0 || c.dec_layers == 0, WB_ERR_BAD_ARG, "a decoder needs a vocabulary");
@@ -409,6 +466,82 @@ int wb_op_lse_topk(const float* logits_dev, int64_t ldl, int M, int V, int blank
                    float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream) {
     return ctc_lse_topk(logits_dev, ldl, M, V, blank_id, blank_penalty, topk, topk_val_dev, topk_idx_dev,
                         (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- Whisper log-mel
+struct wb_logmel {
+    LogMelPlan* plan;
+};
+int wb_logmel_create(wb_logmel** out, int n_fft, int hop_length, int num_mel, const float* window_host, const float* mel_host) {
+    WB_REQUIRE(out && window_host && mel_host, WB_ERR_BAD_ARG, "logmel_create: null argument");
+    LogMelPlan* plan = nullptr;
+    int rc = logmel_plan_create(&plan, n_fft, hop_length, num_mel, window_host, mel_host);
+    if (rc != WB_OK) return rc;
+    wb_logmel* lm = new wb_logmel();
+    lm->plan = plan;
+    *out = lm;
+    return WB_OK;
+}
+void wb_logmel_destroy(wb_logmel* lm) {
+    if (!lm) return;
+    logmel_plan_destroy(lm->plan);
+    delete lm;
+}
+int wb_logmel_forward(const wb_logmel* lm, const float* pcm_dev, int64_t pcm_stride, const int32_t* num_samples_dev, int batch,
+                      float* feats_dev, int64_t frames_stride, int max_frames, int32_t* scratch_dev, wb_stream_t stream) {
+    WB_REQUIRE(lm && pcm_dev && num_samples_dev && feats_dev && scratch_dev, WB_ERR_BAD_ARG, "logmel_forward: null argument");
+    return logmel_forward(lm->plan, pcm_dev, pcm_stride, num_samples_dev, batch, feats_dev, frames_stride, max_frames, scratch_dev,
+                          (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- Whisper encoder, attention decoding
+int64_t wb_whisper_encoder_out_rows(int batch, const int32_t* feat_lens_host, int padded_frames) {
+    return whisper_encoder_out_rows(batch, feat_lens_host, padded_frames);
+}
+size_t wb_whisper_encoder_workspace_bytes(const wb_model* mm, int batch, const int32_t* feat_lens_host, int padded_frames) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    if (!m || !feat_lens_host) return 0;
+    return whisper_encoder_workspace_bytes(m, batch, feat_lens_host, padded_frames);
+}
+int wb_whisper_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats_stride_b, const int32_t* feat_lens_host,
+                               int batch, int padded_frames, float* enc_out_dev, void* enc_out_bf16_dev, int32_t* seq_start_dev,
+                               int32_t* seq_len_dev, void* workspace_dev, size_t workspace_bytes, wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "whisper_encoder_forward: model not finalized");
+    WB_REQUIRE(feats_dev && feat_lens_host && enc_out_dev && enc_out_bf16_dev && seq_start_dev && seq_len_dev && workspace_dev,
+               WB_ERR_BAD_ARG, "whisper_encoder_forward: null argument");
+    return whisper_encoder_forward(m, feats_dev, feats_stride_b, feat_lens_host, batch, padded_frames, enc_out_dev,
+                                   enc_out_bf16_dev, seq_start_dev, seq_len_dev, workspace_dev, workspace_bytes,
+                                   (cudaStream_t)stream);
+}
+size_t wb_attention_beam_workspace_bytes(const wb_model* mm, int64_t enc_rows, int batch, int beam, int max_len) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    if (!m || !m->finalized) return 0;
+    return attention_beam_workspace_bytes(m, enc_rows, batch, beam, max_len);
+}
+int wb_attention_beam_search(const wb_model* mm, const void* enc_out_bf16_dev, int64_t enc_rows, const int32_t* seq_start_host,
+                             const int32_t* seq_len_host, int batch, int beam, const int32_t* prefix_host, int prefix_len,
+                             int eos, int max_len, float length_penalty, int32_t* tokens_dev, int out_stride, int32_t* lens_dev,
+                             float* scores_dev, int32_t* steps_run_host, void* workspace_dev, size_t workspace_bytes,
+                             wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "attention_beam_search: model not finalized");
+    WB_REQUIRE(enc_out_bf16_dev && seq_start_host && seq_len_host && prefix_host && tokens_dev && lens_dev && workspace_dev,
+               WB_ERR_BAD_ARG, "attention_beam_search: null argument");
+    WB_REQUIRE(out_stride >= max_len - prefix_len, WB_ERR_BAD_ARG, "attention_beam_search: out_stride %d < %d", out_stride,
+               max_len - prefix_len);
+    return attention_beam_search(m, enc_out_bf16_dev, enc_rows, seq_start_host, seq_len_host, batch, beam, prefix_host, prefix_len,
+                                 eos, max_len, length_penalty, tokens_dev, out_stride, lens_dev, scores_dev, steps_run_host,
+                                 workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+int wb_op_attention_beam_step(const float* topk_val_dev, const int32_t* topk_idx_dev, const float* score_in_dev,
+                              const int32_t* end_in_dev, const int32_t* hyp_in_dev, const int32_t* anc_in_dev, int batch, int beam,
+                              int max_len, int pos, int eos, float* score_out_dev, int32_t* end_out_dev, int32_t* hyp_out_dev,
+                              int32_t* anc_out_dev, int32_t* next_tok_dev, int32_t* next_pos_dev, int32_t* utt_ended_dev,
+                              wb_stream_t stream) {
+    return attention_beam_step_op(topk_val_dev, topk_idx_dev, score_in_dev, end_in_dev, hyp_in_dev, anc_in_dev, batch, beam,
+                                  max_len, pos, eos, score_out_dev, end_out_dev, hyp_out_dev, anc_out_dev, next_tok_dev,
+                                  next_pos_dev, utt_ended_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

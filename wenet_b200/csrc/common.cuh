@@ -222,6 +222,9 @@ __device__ __forceinline__ float silu_t(float x) {
     return fmaf(h, fast_tanh(h), h);
 }
 
+// exact (erf) GELU of torch.nn.GELU(): 0.5 x (1 + erf(x / sqrt 2)); erff is libdevice's polynomial form (FMA pipe)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

@@ -656,6 +656,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         } else if (epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        } else if (epi == EPI_BF16_GELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
                         }
                         if (p.alpha != 1.0f) {
 #pragma unroll
@@ -694,12 +697,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 switch (epi) {
                     case EPI_BF16:
                     case EPI_BF16_SILU:
-                    case EPI_BF16_RELU: {
+                    case EPI_BF16_RELU:
+                    case EPI_BF16_GELU: {
                         if (epi == EPI_BF16_SILU) {
                             silu_inplace(v);
                         } else if (epi == EPI_BF16_RELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        } else if (epi == EPI_BF16_GELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
                         }
                         if (p.alpha != 1.0f) {
 #pragma unroll
@@ -1028,6 +1035,7 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
             WB_GEMM_CASE(EPI_BF16)
             WB_GEMM_CASE(EPI_BF16_SILU)
             WB_GEMM_CASE(EPI_BF16_RELU)
+            WB_GEMM_CASE(EPI_BF16_GELU)
             WB_GEMM_CASE(EPI_RESID_F32)
             WB_GEMM_CASE(EPI_GLU_BF16)
             WB_GEMM_CASE(EPI_F32)
@@ -1048,6 +1056,7 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
             WB_GEMM_CASE(EPI_BF16)
             WB_GEMM_CASE(EPI_BF16_SILU)
             WB_GEMM_CASE(EPI_BF16_RELU)
+            WB_GEMM_CASE(EPI_BF16_GELU)
             WB_GEMM_CASE(EPI_RESID_F32)
             WB_GEMM_CASE(EPI_GLU_BF16)
             WB_GEMM_CASE(EPI_F32)

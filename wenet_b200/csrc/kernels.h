@@ -18,6 +18,7 @@ enum GemmEpi : int {
     EPI_LSE = 6,        // no matrix output: per (row, 128-column half tile) partial log-sum-exp (max2, sum) of acc + bias
     EPI_RESID_LN = 7,   // EPI_RESID_F32 + LayerNorm of the updated rows -> bf16 (gemm_resid_ln only; N == 256)
     EPI_RESID_LN2 = 8,  // x = LayerNorm_1(x + alpha (acc + bias)) (fp32), out_bf16 = LayerNorm(x) (gemm_resid_ln with gamma1)
+    EPI_BF16_GELU = 9,  // out_bf16 = alpha * gelu(acc + bias), exact erf form (torch.nn.GELU(); Whisper FFN / Conv1dSubsampling2)
 };
 
 int gemm_bn_for(int N, int K, int epi = EPI_BF16);

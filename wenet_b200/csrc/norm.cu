@@ -169,7 +169,7 @@ int layernorm_rows(const float* x, long long ldx, int M, int d, const float* gam
                    float eps, void* out_bf16, long long ld_bf16, int split3, float* out_f32, long long ld_f32,
                    cudaStream_t stream) {
     if (M <= 0) return WB_OK;
-    WB_REQUIRE(d % 128 == 0 && d <= 1024, WB_ERR_UNSUPPORTED, "layernorm: d=%d must be a multiple of 128, <= 1024", d);
+    WB_REQUIRE(d % 128 == 0 && d <= 1280, WB_ERR_UNSUPPORTED, "layernorm: d=%d must be a multiple of 128, <= 1280", d);
     WB_REQUIRE(ldx % 4 == 0 && ld_bf16 % 4 == 0 && ld_f32 % 4 == 0, WB_ERR_BAD_ARG, "layernorm: pitches must be %%4");
     const int grid = ceil_div(M, LN_WARPS);
     ProfScope _ps(PT_LAYERNORM, stream, (double)M * d * (4.0 + (out_bf16 ? 2.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
@@ -185,6 +185,7 @@ int layernorm_rows(const float* x, long long ldx, int M, int d, const float* gam
         case 5: WB_LN(5); break;
         case 6: WB_LN(6); break;
         case 8: WB_LN(8); break;
+        case 10: WB_LN(10); break;   // Whisper-large (d = 1280)
         default:
             set_last_error("layernorm: d=%d unsupported", d);
             return WB_ERR_UNSUPPORTED;

@@ -119,7 +119,7 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
     void* qkv_full = shared ? ws + P.o_qkv_full : qkv;
     void* ctx_full = shared ? ws + P.o_ctx_full : ctx;
     const float scale = 1.0f / sqrtf(64.0f);
-    RC(embed_tokens(Q.tok, Q.pos, N, d, D.emb, m->pe, sqrtf((float)d), x, st));
+    RC(embed_tokens(Q.tok, Q.pos, N, d, D.emb, D.pe ? D.pe : m->pe, D.xscale, x, st));
     for (size_t li = 0; li < D.layers.size(); ++li) {
         const DecLayer& L = D.layers[li];
         // masked (causal) self-attention, decoder_layer.py:101-118
@@ -160,7 +160,7 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
         RC(gemm_bf16(ctx, d, &L.ca_out.tmap, L.ca_out.w, N, d, d, L.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
         // feed-forward (ReLU), decoder_layer.py:141-147
         RC(layernorm_rows(x, d, N, d, L.n3.g, L.n3.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, N, ff, d, L.ff1.b, EPI_BF16_RELU, 1.0f, h, ff, 0, st));
+        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, N, ff, d, L.ff1.b, D.act_epi, 1.0f, h, ff, 0, st));
         RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, N, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
     }
     RC(layernorm_rows(x, d, N, d, D.after.g, D.after.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));

@@ -26,7 +26,8 @@ def export_model(configs: dict, state_dict: Dict[str, torch.Tensor], path: str, 
         cnn_norm=0 if spec.cnn_norm == "layer_norm" else 1, vocab=spec.vocab,
         dec_layers=spec.dec_layers if has_dec else 0, rdec_layers=spec.rdec_layers if has_dec else 0,
         dec_heads=spec.dec_heads, dec_ffn_dim=spec.dec_ffn_dim, max_pos=spec.max_pos, has_cmvn=int(spec.has_cmvn),
-        precise=int(precise), ln_eps=spec.ln_eps, dec_ln_eps=spec.dec_ln_eps)
+        precise=int(precise), ln_eps=spec.ln_eps, dec_ln_eps=spec.dec_ln_eps,
+        arch=int(spec.arch), dec_flavor=int(spec.dec_flavor), dec_max_len=int(spec.dec_max_len))
     packed = {k: v for k, v in pack_state_dict(spec, state_dict, precise=precise).items()
               if has_dec or not k.startswith("dec.")}
     with open(path, "wb") as f:

@@ -39,8 +39,80 @@ def sinusoid_pe(max_len: int, d: int) -> torch.Tensor:
     return pe
 
 
+def whisper_sinusoids(max_len: int, d: int) -> torch.Tensor:
+    """WhisperPositionalEncoding (wenet/models/transformer/embedding.py:150-164)"""
+    inc = np.log(10000) / (d // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(d // 2))
+    st = torch.arange(max_len)[:, np.newaxis] * inv[np.newaxis, :]
+    return torch.cat([torch.sin(st), torch.cos(st)], dim=1)
+
+
+def synth_whisper_state_dict(configs: dict, seed: int = 777, emb_bound: float = 1.5, eos_beta: float = 12.0,
+                             pe_bound: float = 0.3) -> Dict[str, torch.Tensor]:
+    """Whisper-shaped weights under the reference's key names (TransformerEncoder with Conv1dSubsampling2 /
+    WhisperPositionalEncoding, TransformerDecoder with LearnablePositionalEncoding, tied output embedding; key_bias and
+    src_key_bias false: no linear_k.bias keys).  The <eot> output bias is raised by eos_beta so that beam search ends
+    after a few tens of tokens as it does with a trained model."""
+    enc, dec = configs["encoder_conf"], configs["decoder_conf"]
+    d, h, ff, L = int(enc["output_size"]), int(enc["attention_heads"]), int(enc["linear_units"]), int(enc["num_blocks"])
+    idim, V = int(configs["input_dim"]), int(configs["output_dim"])
+    dff, DL = int(dec["linear_units"]), int(dec["num_blocks"])
+    st = configs["tokenizer_conf"]["special_tokens"]
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out_f, in_f, extra_shape=(), bias=True):
+        b = 1.0 / math.sqrt(in_f * int(np.prod(extra_shape)) if extra_shape else in_f)
+        sd[name + ".weight"] = _uniform(seed, name + ".weight", (out_f, in_f) + tuple(extra_shape), b)
+        if bias:
+            sd[name + ".bias"] = _uniform(seed, name + ".bias", (out_f,), b)
+
+    def norm(name):
+        sd[name + ".weight"] = 1.0 + _uniform(seed, name + ".weight", (d,), 0.1)
+        sd[name + ".bias"] = _uniform(seed, name + ".bias", (d,), 0.1)
+
+    def attn(p, key_bias):
+        lin(p + ".linear_q", d, d)
+        lin(p + ".linear_k", d, d, bias=key_bias)
+        lin(p + ".linear_v", d, d)
+        lin(p + ".linear_out", d, d)
+
+    lin("encoder.embed.conv.0", d, idim, (3,))
+    lin("encoder.embed.conv.2", d, d, (3,))
+    sd["encoder.embed.pos_enc.pe"] = whisper_sinusoids(1500, d).unsqueeze(0)
+    norm("encoder.after_norm")
+    for i in range(L):
+        p = "encoder.encoders.%d" % i
+        attn(p + ".self_attn", bool(enc.get("key_bias", True)))
+        lin(p + ".feed_forward.w_1", ff, d)
+        lin(p + ".feed_forward.w_2", d, ff)
+        norm(p + ".norm1")
+        norm(p + ".norm2")
+    lin("ctc.ctc_lo", V, d)
+    sd["decoder.embed.0.weight"] = _uniform(seed, "decoder.emb", (V, d), emb_bound)
+    sd["decoder.embed.1.pe"] = _uniform(seed, "decoder.pe", (1, 448, d), pe_bound)
+    norm("decoder.after_norm")
+    if dec.get("tie_word_embedding", False):
+        sd["decoder.output_layer.weight"] = sd["decoder.embed.0.weight"]
+    else:
+        sd["decoder.output_layer.weight"] = _uniform(seed, "decoder.out", (V, d), emb_bound)
+    ob = _uniform(seed, "decoder.output_layer.bias", (V,), 0.1)
+    ob[int(st["eot"])] += eos_beta
+    sd["decoder.output_layer.bias"] = ob
+    for i in range(DL):
+        p = "decoder.decoders.%d" % i
+        attn(p + ".self_attn", bool(dec.get("key_bias", True)))
+        attn(p + ".src_attn", bool(dec.get("src_key_bias", True)))
+        lin(p + ".feed_forward.w_1", dff, d)
+        lin(p + ".feed_forward.w_2", d, dff)
+        for n in ("norm1", "norm2", "norm3"):
+            norm(p + "." + n)
+    return sd
+
+
 def synth_state_dict(configs: dict, seed: int = 777, ctc_alpha: float = 8.0, ctc_blank_beta: float = None,
                      with_pe: bool = True) -> Dict[str, torch.Tensor]:
+    if configs.get("model") == "whisper":
+        return synth_whisper_state_dict(configs, seed)
     enc = configs["encoder_conf"]
     dec = configs.get("decoder_conf", {})
     d = int(enc.get("output_size", 256))
@@ -217,4 +289,32 @@ def recipe(name: str) -> dict:
         return dict(base, output_dim=61, encoder_conf=enc(512, 8, 1024, 2, 15, True, "layer_norm", True),
                     decoder="bitransformer", decoder_conf=dec(8, 1024, 1, 1),
                     model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False, reverse_weight=0.3))
+    if name in ("whisper_tiny", "whisper_large_v3"):
+        # examples/aishell/whisper/conf/finetune_whisper_largev3.yaml (32 + 32 L, d 1280, 20 heads, ff 5120, V 51866, 128 mel);
+        # whisper_tiny: the same structure at test size
+        big = name == "whisper_large_v3"
+        d, h, ff, L, V, mel = (1280, 20, 5120, 32, 51866, 128) if big else (128, 2, 256, 2, 120, 32)
+        st = dict(eot=50257, no_speech=50363, no_timestamps=50364, sot=50258, sot_prev=50362, timestamp_begin=50365,
+                  transcribe=50360, translate=50359) if big else \
+            dict(eot=99, sot=100, translate=104, transcribe=105, no_speech=106, no_timestamps=107, sot_prev=108,
+                 timestamp_begin=109)
+        return dict(
+            input_dim=mel, output_dim=V, cmvn=None, cmvn_conf={"cmvn_file": None, "is_json_cmvn": None},
+            encoder="transformer",
+            encoder_conf=dict(activation_type="gelu", attention_dropout_rate=0.0, attention_heads=h, dropout_rate=0.0,
+                              gradient_checkpointing=False, input_layer="conv1d2", key_bias=False, linear_units=ff,
+                              normalize_before=True, num_blocks=L, output_size=d, pos_enc_layer_type="abs_pos_whisper",
+                              positional_dropout_rate=0.0, static_chunk_size=-1, use_dynamic_chunk=False,
+                              use_dynamic_left_chunk=False),
+            decoder="transformer",
+            decoder_conf=dict(activation_type="gelu", attention_heads=h, dropout_rate=0.0, gradient_checkpointing=False,
+                              input_layer="embed_learnable_pe", key_bias=False, src_key_bias=False, linear_units=ff,
+                              normalize_before=True, num_blocks=L, positional_dropout_rate=0.0,
+                              self_attention_dropout_rate=0.0, src_attention=True, src_attention_dropout_rate=0.0,
+                              tie_word_embedding=big, use_output_layer=True),   # tied weights make a random-init decoder repeat its input token
+            tokenizer="whisper",
+            tokenizer_conf=dict(bpe_path=None, is_multilingual=True, non_lang_syms_path=None, num_languages=100,
+                                special_tokens=st, split_with_space=False, symbol_table_path=None),
+            ctc="ctc", ctc_conf=dict(ctc_blank_id=st["no_speech"]),
+            model="whisper", model_conf=dict(ctc_weight=0.3, length_normalized_loss=False, lsm_weight=0.1))
     raise KeyError(name)

@@ -59,8 +59,15 @@ class ModelSpec:
 
     def __init__(self, configs: dict):
         enc = dict(configs.get("encoder_conf", {}))
+        self.arch = 0            # 0 Conformer, 1 Whisper (TransformerEncoder conv1d2 / abs_pos_whisper / gelu)
+        self.dec_flavor = 0      # 0 wenet "embed" + relu, 1 Whisper "embed_learnable_pe" + gelu
+        self.dec_max_len = 0
+        if configs.get("encoder", "conformer") == "transformer":
+            self._init_whisper(configs, enc)
+            return
         if configs.get("encoder", "conformer") != "conformer":
-            raise NotImplementedError("encoder '%s' is outside the implemented set (conformer)" % configs.get("encoder"))
+            raise NotImplementedError("encoder '%s' is outside the implemented set (conformer, whisper-style transformer)"
+                                      % configs.get("encoder"))
 
         def need(key, allowed, default):
             v = enc.get(key, default)
@@ -120,6 +127,157 @@ class ModelSpec:
         self.max_pos = 5000
         self.has_cmvn = configs.get("cmvn", None) is not None
 
+    def _init_whisper(self, configs: dict, enc: dict):
+        """encoder: transformer in the Whisper configuration (examples/aishell/whisper/conf/finetune_whisper_largev3.yaml):
+        conv1d2 / abs_pos_whisper / gelu / key_bias false / pre-norm; decoder: transformer with embed_learnable_pe / gelu."""
+        def need(conf, key, allowed, default, what):
+            v = conf.get(key, default)
+            if v not in allowed:
+                raise NotImplementedError("%s.%s=%r is outside the implemented set %r" % (what, key, v, allowed))
+            return v
+
+        need(enc, "input_layer", ("conv1d2",), "conv2d", "encoder_conf")
+        need(enc, "pos_enc_layer_type", ("abs_pos_whisper",), "abs_pos", "encoder_conf")
+        need(enc, "activation_type", ("gelu",), "relu", "encoder_conf")
+        need(enc, "normalize_before", (True,), True, "encoder_conf")
+        need(enc, "selfattention_layer_type", ("selfattn",), "selfattn", "encoder_conf")
+        need(enc, "layer_norm_type", ("layer_norm",), "layer_norm", "encoder_conf")
+        need(enc, "mlp_type", ("position_wise_feed_forward",), "position_wise_feed_forward", "encoder_conf")
+        if enc.get("use_dynamic_chunk", False) or int(enc.get("static_chunk_size", 0)) > 0:
+            raise NotImplementedError("chunk masks are not part of the Whisper path")
+        for k in ("n_kv_head", "head_dim"):
+            if enc.get(k) is not None:
+                raise NotImplementedError("encoder_conf.%s is not supported" % k)
+        self.arch = 1
+        self.input_dim = int(configs["input_dim"])
+        self.vocab = int(configs["output_dim"])
+        self.d_model = int(enc.get("output_size", 256))
+        self.heads = int(enc.get("attention_heads", 4))
+        self.ffn_dim = int(enc.get("linear_units", 2048))
+        self.enc_layers = int(enc.get("num_blocks", 6))
+        self.cnn_kernel, self.cnn_causal, self.cnn_norm = 1, False, "layer_norm"
+        self.use_dynamic_chunk, self.static_chunk_size = False, 0
+        self.ln_eps = float(enc.get("norm_eps", 1e-5))
+        if self.d_model != self.heads * 64:
+            raise NotImplementedError("attention head size must be 64 (d_model=%d heads=%d)" % (self.d_model, self.heads))
+        if configs.get("decoder", "transformer") != "transformer":
+            raise NotImplementedError("decoder '%s' is outside the implemented set for Whisper" % configs.get("decoder"))
+        dec = dict(configs.get("decoder_conf", {}))
+        need(dec, "input_layer", ("embed_learnable_pe",), "embed", "decoder_conf")
+        need(dec, "activation_type", ("gelu",), "relu", "decoder_conf")
+        need(dec, "normalize_before", (True,), True, "decoder_conf")
+        need(dec, "src_attention", (True,), True, "decoder_conf")
+        self.bidirectional = False
+        self.dec_layers = int(dec.get("num_blocks", 6))
+        self.rdec_layers = 0
+        self.dec_heads = int(dec.get("attention_heads", 4))
+        self.dec_ffn_dim = int(dec.get("linear_units", 2048))
+        self.dec_ln_eps = float(dec.get("norm_eps", 1e-5))
+        self.dec_flavor = 1
+        self.dec_max_len = int(dec.get("max_len", 448))          # LearnablePositionalEncoding default (embedding.py:171)
+        if self.d_model != self.dec_heads * 64:
+            raise NotImplementedError("decoder head size must be 64")
+        st = (configs.get("tokenizer_conf") or {}).get("special_tokens") or {}
+        self.special_tokens = dict(st)
+        self.sos = int(st.get("sot", self.vocab - 1))             # whisper.py:51-52
+        self.eos = int(st.get("eot", self.vocab - 1))
+        mc = dict(configs.get("model_conf", {}))
+        self.reverse_weight = 0.0
+        self.ctc_weight = float(mc.get("ctc_weight", 0.3))
+        self.max_pos = int(enc.get("max_len", 1500))              # WhisperPositionalEncoding default (embedding.py:154)
+        self.has_cmvn = False
+
+
+def whisper_sinusoids(max_len: int, d: int) -> torch.Tensor:
+    """WhisperPositionalEncoding table, wenet/models/transformer/embedding.py:150-164"""
+    import math
+    inc = math.log(10000) / (d // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(d // 2))
+    st = torch.arange(max_len)[:, None] * inv[None, :]
+    return torch.cat([torch.sin(st), torch.cos(st)], dim=1)
+
+
+def _pack_whisper(spec: "ModelSpec", sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Whisper (wenet/models/whisper/whisper.py; key names of TransformerEncoder / TransformerDecoder):
+      * Conv1d(k=3) weights (out, in, 3) -> [out][(tap, in)] for the im2col GEMMs of whisper.cu
+      * q/k/v fused; key_bias=False (attention.py:74-77) -> a zero bias slice
+      * tie_word_embedding: output_layer.weight is the embedding matrix (decoder.py:283-311) - whatever the state_dict holds
+        is packed, so tied and cloned checkpoints both work; a missing output bias packs as zeros"""
+    d = spec.d_model
+    out: Dict[str, torch.Tensor] = {}
+
+    def f32(t):
+        return t.detach().float().contiguous().cpu()
+
+    def bf(t):
+        return t.detach().float().to(torch.bfloat16).contiguous().cpu()
+
+    def lin(dst, src, n_out=None):
+        w = sd[src + ".weight"]
+        out[dst + ".w"] = bf(w)
+        b = sd.get(src + ".bias")
+        out[dst + ".b"] = f32(b) if b is not None else torch.zeros(w.shape[0] if n_out is None else n_out)
+
+    def norm(dst, src):
+        out[dst + ".g"] = f32(sd[src + ".weight"])
+        out[dst + ".b"] = f32(sd[src + ".bias"])
+
+    def qkv(dst, a):
+        ws, bs = [], []
+        for n in ("linear_q", "linear_k", "linear_v"):
+            w = sd[a + "." + n + ".weight"]
+            b = sd.get(a + "." + n + ".bias")
+            ws.append(w)
+            bs.append(b.float() if b is not None else torch.zeros(w.shape[0]))
+        out[dst + ".w"] = bf(torch.cat(ws, 0))
+        out[dst + ".b"] = f32(torch.cat(bs, 0))
+
+    w1 = sd["encoder.embed.conv.0.weight"]            # (d, idim, 3)
+    out["wenc.conv1.w"] = bf(w1.permute(0, 2, 1).reshape(d, 3 * spec.input_dim))
+    out["wenc.conv1.b"] = f32(sd["encoder.embed.conv.0.bias"])
+    w2 = sd["encoder.embed.conv.2.weight"]            # (d, d, 3)
+    out["wenc.conv2.w"] = bf(w2.permute(0, 2, 1).reshape(d, 3 * d))
+    out["wenc.conv2.b"] = f32(sd["encoder.embed.conv.2.bias"])
+    pe = sd.get("encoder.embed.pos_enc.pe")
+    pe = whisper_sinusoids(spec.max_pos, d) if pe is None else pe.reshape(-1, d)
+    assert pe.shape[0] == spec.max_pos, (pe.shape, spec.max_pos)
+    out["wenc.pe"] = f32(pe)
+    for i in range(spec.enc_layers):
+        s_, t = "encoder.encoders.%d" % i, "wenc.%d" % i
+        norm(t + ".norm1", s_ + ".norm1")
+        norm(t + ".norm2", s_ + ".norm2")
+        qkv(t + ".att.qkv", s_ + ".self_attn")
+        lin(t + ".att.out", s_ + ".self_attn.linear_out")
+        lin(t + ".ff.w1", s_ + ".feed_forward.w_1")
+        lin(t + ".ff.w2", s_ + ".feed_forward.w_2")
+    norm("after_norm", "encoder.after_norm")
+    if spec.vocab > 0 and "ctc.ctc_lo.weight" in sd:
+        lin("ctc", "ctc.ctc_lo")
+    if any(k.startswith("decoder.") for k in sd):
+        dst, src = "dec.left", "decoder"
+        out[dst + ".emb"] = f32(sd[src + ".embed.0.weight"])
+        out[dst + ".pe"] = f32(sd[src + ".embed.1.pe"].reshape(-1, d))
+        assert out[dst + ".pe"].shape[0] == spec.dec_max_len
+        for i in range(spec.dec_layers):
+            s_, t = "%s.decoders.%d" % (src, i), "%s.%d" % (dst, i)
+            for n in ("norm1", "norm2", "norm3"):
+                norm(t + "." + n, s_ + "." + n)
+            qkv(t + ".sa.qkv", s_ + ".self_attn")
+            lin(t + ".sa.out", s_ + ".self_attn.linear_out")
+            a = s_ + ".src_attn"
+            lin(t + ".ca.q", a + ".linear_q")
+            wk, wv = sd[a + ".linear_k.weight"], sd[a + ".linear_v.weight"]
+            bk, bv = sd.get(a + ".linear_k.bias"), sd.get(a + ".linear_v.bias")
+            out[t + ".ca.kv.w"] = bf(torch.cat([wk, wv], 0))
+            out[t + ".ca.kv.b"] = f32(torch.cat([bk.float() if bk is not None else torch.zeros(d),
+                                                 bv.float() if bv is not None else torch.zeros(d)], 0))
+            lin(t + ".ca.out", a + ".linear_out")
+            lin(t + ".ff.w1", s_ + ".feed_forward.w_1")
+            lin(t + ".ff.w2", s_ + ".feed_forward.w_2")
+        norm(dst + ".after_norm", src + ".after_norm")
+        lin(dst + ".out", src + ".output_layer")
+    return out
+
 
 def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor], precise: bool = False) -> Dict[str, torch.Tensor]:
     """Returns {lib tensor name: CPU tensor (fp32 or bf16)}.
@@ -128,6 +286,10 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor], precise: bool 
     bf16 [N, 3K] = per K-block [hi | hi | lo] (bf16x3 against activations written as [hi | lo | hi]); the K-blocks are
     the d-wide channel groups the activations are split by (one block for a Linear, one per (kh, kw) tap for conv2,
     one per frequency bin for the embed Linear)."""
+    if spec.arch == 1:
+        if precise:
+            raise NotImplementedError("the precise parity mode is not built for the Whisper path")
+        return _pack_whisper(spec, sd)
     d, F1 = spec.d_model, (spec.input_dim - 3) // 2 + 1
     F2 = (F1 - 3) // 2 + 1
     out: Dict[str, torch.Tensor] = {}
@@ -255,7 +417,8 @@ class DeviceModel:
             cnn_norm=0 if spec.cnn_norm == "layer_norm" else 1, vocab=spec.vocab,
             dec_layers=spec.dec_layers if has_dec else 0, rdec_layers=spec.rdec_layers if has_dec else 0,
             dec_heads=spec.dec_heads, dec_ffn_dim=spec.dec_ffn_dim, max_pos=spec.max_pos,
-            has_cmvn=int(spec.has_cmvn), precise=int(self.precise), ln_eps=spec.ln_eps, dec_ln_eps=spec.dec_ln_eps)
+            has_cmvn=int(spec.has_cmvn), precise=int(self.precise), ln_eps=spec.ln_eps, dec_ln_eps=spec.dec_ln_eps,
+            arch=int(spec.arch), dec_flavor=int(spec.dec_flavor), dec_max_len=int(spec.dec_max_len))
         self._h = C.c_void_p()
         check(lib.wb_model_create(C.byref(self._h), C.byref(cfg)), "wb_model_create")
         packed = pack_state_dict(spec, sd, precise=self.precise)
