@@ -318,6 +318,7 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="skip the token / encoder_out check against the CPU oracle")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the extra block (ragged global list, configs[2] large model, configs[3] streaming latency)")
+    ap.add_argument("--no-whisper", action="store_true", help="skip the Whisper-large-v3 extra (BASELINE configs[4] geometry)")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel CUDA-event profiler")
     ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the GEMM / FFN kernels leave free (-1: 8 when in flight > 1)")
     ap.add_argument("--inflight", type=int, default=4,
@@ -659,6 +660,51 @@ def main():
                               "gemm_tflops": ach_l, "gemm_frac": ach_l / peaks["tf_sust"],
                               "kernels_ms_per_step": {k: v["ms"] / 2 for k, v in sorted(pl_.items(), key=lambda kv: -kv[1]["ms"])}}
             del slots_l, model_l
+            torch.cuda.empty_cache()
+        if world == 1 and args.workload == "small" and not args.no_whisper:
+            # (iv) BASELINE configs[4] / SURVEY 8f-1: Whisper-large-v3 geometry (32 + 32 layers, d 1280, 20 heads, ff 5120,
+            #      V 51866, 128 mel), 32 x 30 s, log-mel -> encoder -> attention decoding (beam 10) through B200Whisper.decode.
+            #      Random-init weights with <eot> suppressed: exactly `dec_steps` beam steps per batch (~3.2 tokens per audio s).
+            from wenet_b200.whisper import B200Whisper, LogMelExtractor
+            t_w0 = time.perf_counter()
+            cfg_w = synth.recipe("whisper_large_v3")
+            model_w = B200Whisper(cfg_w, synth.synth_whisper_state_dict_fast(cfg_w, seed=777), device=dev)
+            t_build = time.perf_counter() - t_w0
+            Bw, beam_w, dec_steps = 32, 10, 96
+            model_w.max_decode_len = dec_steps + 4          # 4 forced prefix tokens
+            lm = LogMelExtractor(128, 400, 160)
+            pcm_w = [(dev_pcm[r][:Bw].float() / 32768.0).contiguous() for r in range(NROT)]
+            ns_w = ns[:Bw]
+            flens_w = torch.tensor([lm.num_frames(int(x)) for x in ns_w.tolist()], dtype=torch.int64, device=dev)
+
+            def step_w(i, mdl):
+                feats = lm(pcm_w[i % NROT], ns_w)
+                return mdl.decode(["attention"], feats, flens_w, beam_size=beam_w)
+
+            for i in range(2):
+                step_w(i, model_w)
+            torch.cuda.synchronize()
+            steps_w = 3
+            evw0, evw1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            evw0.record()
+            for i in range(steps_w):
+                out_w = step_w(i, model_w)
+            evw1.record()
+            torch.cuda.synchronize()
+            ms_w = evw0.elapsed_time(evw1)
+            pw_, _ = profile_pass(step_w, model_w, 1)
+            gw = pw_.get("gemm_tcgen05", {"ms": 0.0, "work": 0.0})
+            ach_w = gw["work"] / (gw["ms"] * 1e-3) / 1e12 if gw["ms"] > 0 else 0.0
+            secs_w = float(ns_w.sum().item()) / 16000.0
+            extra["whisper"] = {"workload": "Whisper-large-v3 geometry (32+32L, d 1280, 20 heads, ff 5120, V 51866, 128 mel), "
+                                            "%d x 30 s, log-mel + encoder + attention decoding beam %d, %d decoding steps" % (Bw, beam_w, dec_steps),
+                                "value": secs_w * steps_w / (ms_w / 1e3), "unit": "audio-s/s", "ms_per_step": ms_w / steps_w,
+                                "steps": steps_w, "decode_steps": int(model_w.last_attention_steps),
+                                "tokens_out": int(sum(len(r.tokens) for r in out_w["attention"])),
+                                "gemm_tflops": ach_w, "gemm_frac": ach_w / peaks["tf_sust"], "model_build_s": t_build,
+                                "kernels_ms_per_step": {k: v["ms"] for k, v in sorted(pw_.items(), key=lambda kv: -kv[1]["ms"])}}
+            del model_w
+            torch.cuda.empty_cache()
         line["extra"] = extra
 
     # ---- verification against the CPU oracle (rank 0, N = 1): tokens of two utterances of batch 0 ----

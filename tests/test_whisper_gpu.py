@@ -176,3 +176,43 @@ def test_beam_step_exact():
         want_anc = torch.cat([anc[par][:, :pos], par.view(-1, 1)], dim=1)
         assert torch.equal(ao.cpu()[:, :pos + 1].long(), want_anc)
         assert ue.cpu().tolist() == ne.view(B, N).sum(1).tolist()
+
+
+def test_whisper_through_install():
+    """The reference's own init_model / Whisper.decode / processor.compute_log_mel_spectrogram after wenet_b200.install()
+    (the `wenet.cli` path: cli/model.py loads the model through init_model and features through processor): same tokens as
+    the CPU reference's goldens.  Needs a reference tree (baseline/_ref on the GPU box)."""
+    from oracle import shim
+    if not shim.have_reference():
+        pytest.skip("no reference tree (baseline/_ref or /root/reference)")
+    import types
+    shim.install()
+    from wenet_b200 import plugin
+    plugin.install()
+    try:
+        import wenet.dataset.processor as processor
+        from wenet.utils import init_model as im
+        g = load_golden("whisper_tiny")
+        cfg = synth.recipe("whisper_tiny")
+        model = shim.init_reference_model(dict(cfg))
+        assert type(model).__name__ == "B200WhisperPlugin" and isinstance(model, im.Whisper)
+        model.load_state_dict(synth.synth_state_dict(cfg, seed=SEED), strict=True)
+        model = model.cuda().eval()
+        # features through the rebound processor function
+        ns = g["num_samples"].tolist()
+        pcm = synth.synth_pcm(len(ns), ns, seed=SEED)
+        feats = []
+        for b, n in enumerate(ns):
+            s = processor.compute_log_mel_spectrogram(dict(key="k", wav=(pcm[b, :n].float() / 32768.0).unsqueeze(0),
+                                                           sample_rate=16000), n_fft=400, hop_length=160, num_mel_bins=32)
+            feats.append(s["feat"])
+            assert err(s["feat"], torch.from_numpy(g["feats"][b, :s["feat"].shape[0]]))[0] <= 2e-3
+        lens = torch.tensor([f.shape[0] for f in feats])
+        xs = torch.nn.utils.rnn.pad_sequence(feats, batch_first=True, padding_value=0)
+        infos = {"tasks": [str(t) for t in g["tasks"]], "langs": [str(t) for t in g["langs"]]}
+        with torch.no_grad():
+            res = model.decode(["attention"], xs.cuda(), lens.cuda(), beam_size=int(g["beam"]), infos=infos)["attention"]
+        assert [list(r.tokens) for r in res] == [g["att%d" % b].tolist() for b in range(len(ns))]
+        assert type(res[0]).__module__.startswith("wenet.")        # the reference's DecodeResult type
+    finally:
+        plugin.uninstall()

@@ -14,6 +14,9 @@ path unmodified:
     reference's parameters; the packed device weights are (re)built lazily from `state_dict()` when parameters change.
   * wenet.dataset.processor.compute_fbank (processor.py:226-256; looked up by attribute at dataset.py:96 and
     cli/model.py:58) -> the fused CUDA fbank (dither == 0 in the main process; see `_fbank_dropin`).
+  * WENET_MODEL_CLASSES["whisper"] (init_model.py:91) -> a subclass of the reference Whisper whose `decode` runs the B200
+    Whisper path (wenet_b200/whisper.py), and processor.compute_log_mel_spectrogram (processor.py:320-369) -> the CUDA
+    log-mel kernel.
 
 Training mode (`module.training`) always takes the reference implementation (autograd); eval mode needs CUDA tensors and
 raises otherwise - there is no CPU fallback.  Configurations outside the implemented set raise NotImplementedError when
@@ -112,6 +115,41 @@ def configs_from_reference_model(model) -> dict:
     return cfg
 
 
+def configs_from_reference_whisper(model) -> dict:
+    """train.yaml subset of a constructed reference Whisper (wenet/models/whisper/whisper.py); raises NotImplementedError for
+    anything outside the implemented set (conv1d2 / abs_pos_whisper / gelu / pre-norm, embed_learnable_pe decoder)."""
+    enc, dec = model.encoder, model.decoder
+    if type(enc).__name__ != "TransformerEncoder" or type(enc.embed).__name__ != "Conv1dSubsampling2":
+        raise NotImplementedError("Whisper encoder %s / %s is outside the implemented set (transformer / conv1d2)"
+                                  % (type(enc).__name__, type(enc.embed).__name__))
+    if type(enc.embed.pos_enc).__name__ != "WhisperPositionalEncoding":
+        raise NotImplementedError("positional encoding %s is outside the implemented set (abs_pos_whisper)"
+                                  % type(enc.embed.pos_enc).__name__)
+    if type(dec).__name__ != "TransformerDecoder" or type(dec.embed[1]).__name__ != "LearnablePositionalEncoding":
+        raise NotImplementedError("Whisper decoder outside the implemented set (transformer / embed_learnable_pe)")
+    el, dl = enc.encoders[0], dec.decoders[0]
+    for lyr in (el, dl):
+        if type(lyr.feed_forward.activation).__name__ != "GELU" or not lyr.normalize_before:
+            raise NotImplementedError("Whisper layers must be pre-norm with GELU")
+    d = enc.output_size()
+    return {
+        "input_dim": int(enc.embed.conv[0].in_channels), "output_dim": int(model.vocab_size), "cmvn": None,
+        "encoder": "transformer",
+        "encoder_conf": dict(output_size=d, attention_heads=int(el.self_attn.h), linear_units=int(el.feed_forward.w_1.out_features),
+                             num_blocks=len(enc.encoders), input_layer="conv1d2", pos_enc_layer_type="abs_pos_whisper",
+                             activation_type="gelu", normalize_before=True, key_bias=el.self_attn.linear_k.bias is not None,
+                             norm_eps=float(enc.after_norm.eps), max_len=int(enc.embed.pos_enc.pe.shape[1]),
+                             use_dynamic_chunk=bool(enc.use_dynamic_chunk), static_chunk_size=max(int(enc.static_chunk_size), 0)),
+        "decoder": "transformer",
+        "decoder_conf": dict(attention_heads=int(dl.self_attn.h), linear_units=int(dl.feed_forward.w_1.out_features),
+                             num_blocks=len(dec.decoders), input_layer="embed_learnable_pe", activation_type="gelu",
+                             normalize_before=True, src_attention=True, norm_eps=float(dec.after_norm.eps),
+                             max_len=int(dec.embed[1].pe.shape[1])),
+        "tokenizer": "whisper", "tokenizer_conf": dict(special_tokens=dict(model.special_tokens)),
+        "model": "whisper", "model_conf": dict(ctc_weight=float(model.ctc_weight)),
+    }
+
+
 def wrap(model, device=None, precise: bool = False) -> B200ASRModel:
     """B200 core object sharing the weights of a loaded reference model."""
     core = B200ASRModel.from_reference(model, configs_from_reference_model(model), device=device, precise=precise)
@@ -132,6 +170,20 @@ def _cuda_device_of(module):
 
 _classes = None
 _orig_compute_fbank = None
+_orig_compute_logmel = None
+
+
+def _logmel_dropin(sample, n_fft=400, hop_length=160, num_mel_bins=80, padding=0, pad_or_trim: bool = False,
+                   max_duration: int = 30):
+    """wenet.dataset.processor.compute_log_mel_spectrogram after install() (processor.py:320-369; looked up by attribute at
+    dataset.py and cli/model.py): the CUDA log-mel kernel in the main process, the reference's own function inside DataLoader
+    workers (CUDA cannot be initialised in a forked worker)."""
+    if torch.utils.data.get_worker_info() is not None:
+        return _orig_compute_logmel(sample, n_fft=n_fft, hop_length=hop_length, num_mel_bins=num_mel_bins, padding=padding,
+                                    pad_or_trim=pad_or_trim, max_duration=max_duration)
+    from .whisper import compute_log_mel_spectrogram as b200_logmel
+    return b200_logmel(sample, n_fft=n_fft, hop_length=hop_length, num_mel_bins=num_mel_bins, padding=padding,
+                       pad_or_trim=pad_or_trim, max_duration=max_duration)
 
 
 def _fbank_dropin(sample, num_mel_bins=23, frame_length=25, frame_shift=10, dither=0.0, window_type="povey"):
@@ -266,38 +318,80 @@ def _make_classes():
                                         nbest_scores=r.nbest_scores, nbest_times=r.nbest_times) for r in v]
                     for k, v in res.items()}
 
-    return B200ASRModelPlugin, B200ConformerEncoderPlugin, B200CTCPlugin
+    from wenet.models.whisper.whisper import Whisper
+    from wenet.utils.common import WHISPER_LANGS as REF_WHISPER_LANGS
+
+    class B200WhisperPlugin(Whisper):
+        """Reference Whisper (same constructor / parameters / state_dict); `decode` (and with it `transcribe`, the
+        wenet.cli path) runs log-mel features -> TransformerEncoder -> attention_beam_search on libwenet_b200.so."""
+
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
+            configs_from_reference_whisper(self)      # unsupported configurations fail here, at construction
+
+        def _b200(self):
+            from .whisper import B200Whisper
+            dev = _cuda_device_of(self)
+            core = self.__dict__.get("_b200_core")
+            ver = _version(self)
+            if core is None or self.__dict__.get("_b200_ver") != ver or core.device != dev:
+                sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+                core = B200Whisper(configs_from_reference_whisper(self), sd, device=dev, lang_table=REF_WHISPER_LANGS)
+                self.__dict__["_b200_core"], self.__dict__["_b200_ver"] = core, ver
+            return core
+
+        def decode(self, methods, speech, speech_lengths, beam_size=1, decoding_chunk_size=-1,
+                   num_decoding_left_chunks=-1, ctc_weight=0.0, simulate_streaming=False, reverse_weight=0.0,
+                   context_graph=None, blank_id=0, blank_penalty=0.0, length_penalty=0.0, infos=None):
+            res = self._b200().decode(methods, speech, speech_lengths, beam_size, decoding_chunk_size,
+                                      num_decoding_left_chunks, ctc_weight, simulate_streaming, reverse_weight,
+                                      context_graph, blank_id, blank_penalty, length_penalty, infos)
+            return {k: [RefDecodeResult(tokens=r.tokens, score=r.score, confidence=r.confidence,
+                                        tokens_confidence=r.tokens_confidence, times=r.times, nbest=r.nbest,
+                                        nbest_scores=r.nbest_scores, nbest_times=r.nbest_times) for r in v]
+                    for k, v in res.items()}
+
+    return B200ASRModelPlugin, B200ConformerEncoderPlugin, B200CTCPlugin, B200WhisperPlugin
 
 
 def install(fbank: bool = True):
     """Rebind WeNet's registries (needs `wenet` importable).  Idempotent.  Returns the plugin model class.
     fbank=False leaves wenet.dataset.processor.compute_fbank alone."""
-    global _classes, _orig_compute_fbank
+    global _classes, _orig_compute_fbank, _orig_compute_logmel
     import wenet.dataset.processor as processor
     from wenet.utils import init_model as im
     if _classes is None:
         _classes = _make_classes()
-    model_cls, enc_cls, ctc_cls = _classes
+    model_cls, enc_cls, ctc_cls, whisper_cls = _classes
     im.WENET_MODEL_CLASSES["asr_model"] = model_cls
+    im.WENET_MODEL_CLASSES["whisper"] = whisper_cls
     im.WENET_ENCODER_CLASSES["conformer"] = enc_cls
     im.WENET_CTC_CLASSES["ctc"] = ctc_cls
     if fbank and processor.compute_fbank is not _fbank_dropin:
         _orig_compute_fbank = processor.compute_fbank
         processor.compute_fbank = _fbank_dropin
+    if fbank and processor.compute_log_mel_spectrogram is not _logmel_dropin:
+        _orig_compute_logmel = processor.compute_log_mel_spectrogram
+        processor.compute_log_mel_spectrogram = _logmel_dropin
     return model_cls
 
 
 def uninstall():
     """Restore the reference's own classes / compute_fbank (used by the tests)."""
-    global _orig_compute_fbank
+    global _orig_compute_fbank, _orig_compute_logmel
     import wenet.dataset.processor as processor
     from wenet.models.transformer.asr_model import ASRModel
     from wenet.models.transformer.ctc import CTC
     from wenet.models.transformer.encoder import ConformerEncoder
     from wenet.utils import init_model as im
+    from wenet.models.whisper.whisper import Whisper
     im.WENET_MODEL_CLASSES["asr_model"] = ASRModel
+    im.WENET_MODEL_CLASSES["whisper"] = Whisper
     im.WENET_ENCODER_CLASSES["conformer"] = ConformerEncoder
     im.WENET_CTC_CLASSES["ctc"] = CTC
     if _orig_compute_fbank is not None and processor.compute_fbank is _fbank_dropin:
         processor.compute_fbank = _orig_compute_fbank
         _orig_compute_fbank = None
+    if _orig_compute_logmel is not None and processor.compute_log_mel_spectrogram is _logmel_dropin:
+        processor.compute_log_mel_spectrogram = _orig_compute_logmel
+        _orig_compute_logmel = None

@@ -109,6 +109,68 @@ def synth_whisper_state_dict(configs: dict, seed: int = 777, emb_bound: float = 
     return sd
 
 
+def synth_whisper_state_dict_fast(configs: dict, seed: int = 777, eos_beta: float = -1e4) -> Dict[str, torch.Tensor]:
+    """Benchmark-only variant for Whisper-large-sized models (1.5 B parameters): same keys / shapes / distributions as
+    synth_whisper_state_dict but drawn with torch's CPU generator (seconds instead of minutes; not bit-reproducible across
+    torch versions, which a throughput run does not need).  eos_beta = -1e4 suppresses <eot>, so attention decoding runs a
+    fixed number of steps."""
+    tmpl_cfg = dict(configs)
+    g = torch.Generator().manual_seed(seed)
+    enc, dec = configs["encoder_conf"], configs["decoder_conf"]
+    d, ff, L = int(enc["output_size"]), int(enc["linear_units"]), int(enc["num_blocks"])
+    idim, V = int(configs["input_dim"]), int(configs["output_dim"])
+    dff, DL = int(dec["linear_units"]), int(dec["num_blocks"])
+    st = configs["tokenizer_conf"]["special_tokens"]
+    sd: Dict[str, torch.Tensor] = {}
+
+    def uni(shape, bound):
+        return (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
+
+    def lin(name, out_f, in_f, extra=(), bias=True):
+        b = 1.0 / math.sqrt(in_f * int(np.prod(extra)) if extra else in_f)
+        sd[name + ".weight"] = uni((out_f, in_f) + tuple(extra), b)
+        if bias:
+            sd[name + ".bias"] = uni((out_f,), b)
+
+    def norm(name):
+        sd[name + ".weight"] = 1.0 + uni((d,), 0.1)
+        sd[name + ".bias"] = uni((d,), 0.1)
+
+    def attn(p, key_bias):
+        lin(p + ".linear_q", d, d)
+        lin(p + ".linear_k", d, d, bias=key_bias)
+        lin(p + ".linear_v", d, d)
+        lin(p + ".linear_out", d, d)
+
+    lin("encoder.embed.conv.0", d, idim, (3,))
+    lin("encoder.embed.conv.2", d, d, (3,))
+    sd["encoder.embed.pos_enc.pe"] = whisper_sinusoids(1500, d).unsqueeze(0)
+    norm("encoder.after_norm")
+    for i in range(L):
+        p = "encoder.encoders.%d" % i
+        attn(p + ".self_attn", bool(enc.get("key_bias", True)))
+        lin(p + ".feed_forward.w_1", ff, d)
+        lin(p + ".feed_forward.w_2", d, ff)
+        norm(p + ".norm1")
+        norm(p + ".norm2")
+    sd["decoder.embed.0.weight"] = uni((V, d), 0.5)
+    sd["decoder.embed.1.pe"] = uni((1, 448, d), 0.3)
+    norm("decoder.after_norm")
+    sd["decoder.output_layer.weight"] = sd["decoder.embed.0.weight"] if dec.get("tie_word_embedding", False) else uni((V, d), 0.5)
+    ob = uni((V,), 0.1)
+    ob[int(st["eot"])] += eos_beta
+    sd["decoder.output_layer.bias"] = ob
+    for i in range(DL):
+        p = "decoder.decoders.%d" % i
+        attn(p + ".self_attn", bool(dec.get("key_bias", True)))
+        attn(p + ".src_attn", bool(dec.get("src_key_bias", True)))
+        lin(p + ".feed_forward.w_1", dff, d)
+        lin(p + ".feed_forward.w_2", d, dff)
+        for n in ("norm1", "norm2", "norm3"):
+            norm(p + "." + n)
+    return sd
+
+
 def synth_state_dict(configs: dict, seed: int = 777, ctc_alpha: float = 8.0, ctc_blank_beta: float = None,
                      with_pe: bool = True) -> Dict[str, torch.Tensor]:
     if configs.get("model") == "whisper":

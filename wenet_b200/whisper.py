@@ -192,6 +192,9 @@ class B200Whisper(B200ASRModel):
         self.encoder = B200TransformerEncoder(self)
         self.ctc = B200CTC(self)
         self.lang_table = tuple(lang_table)
+        # optional cap on the hypothesis length of decode mode "attention" (None: the reference's bound, encoder frames
+        # + 1); an extension used by bench.py to pin the number of decoding steps of a synthetic-weight run
+        self.max_decode_len = None
         self._has_ctc = "ctc.ctc_lo.weight" in state_dict
 
     @property
@@ -285,8 +288,10 @@ class B200Whisper(B200ASRModel):
                 else:
                     tasks, langs = infos["tasks"], infos["langs"]
                 prefix = whisper_prefix(self.special_tokens, tasks, langs, self.lang_table)
-                results["attention"] = self._attention_beam(eo, beam_size, length_penalty, prefix, self.eos,
-                                                            self._out_frames(speech.size(1)))
+                maxlen = self._out_frames(speech.size(1))
+                if self.max_decode_len is not None:
+                    maxlen = min(maxlen, int(self.max_decode_len))
+                results["attention"] = self._attention_beam(eo, beam_size, length_penalty, prefix, self.eos, maxlen)
             rest = [m_ for m_ in methods if m_ != "attention"]
             if rest:
                 if not self.spec_has_ctc():
