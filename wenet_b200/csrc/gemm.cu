@@ -960,7 +960,19 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
     if (epi == EPI_RESID_F32 || epi == EPI_F32 || ln_epi) {
         WB_REQUIRE(!split3, WB_ERR_BAD_ARG, "gemm: split3 only for bf16 outputs");
     }
-    const int bn = gemm_bn_for(N, K, epi);
+    int bn = gemm_bn_for(N, K, epi);
+    // Few-row GEMMs (autoregressive decoding: M = batch x beam rows): with 256-column tiles only ceil(M/128) * N/256 CTAs
+    // stream the whole weight matrix (15 CTAs for M = 320, N = 1280); 128-column tiles double the CTAs that share it.
+    // The prebuilt `pair` map of a weight (128-row boxes) is exactly the B map such a tile needs.
+    bool narrow = false;
+    if (bn == 256 && epi != EPI_GLU_BF16 && epi != EPI_LSE && !ln_epi && !split3) {
+        const int tiles256 = ceil_div(M, BM) * ceil_div(N, 256);
+        const int sms = current_device_sms();
+        if (M <= 4 * BM && 2 * tiles256 <= sms) {
+            bn = 128;
+            narrow = true;
+        }
+    }
     if (ln_epi) {
         WB_REQUIRE(ln != nullptr && N == 256 && bn == 256 && bias != nullptr, WB_ERR_BAD_ARG,
                    "gemm: the fused residual + LayerNorm epilogue needs N == 256 and a bias");
@@ -975,7 +987,7 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
     CUtensorMap ta, tb_local;
     int rc = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
     if (rc != WB_OK) return rc;
-    const CUtensorMap* tb = tmap_b_opt ? (pair ? &tmap_b_opt->pair : &tmap_b_opt->one) : nullptr;
+    const CUtensorMap* tb = tmap_b_opt ? ((pair || narrow) ? &tmap_b_opt->pair : &tmap_b_opt->one) : nullptr;
     if (tb == nullptr) {
         rc = make_tmap_2d_bf16(&tb_local, B, (uint64_t)N, (uint64_t)K, (uint64_t)K, (uint32_t)(pair ? bn / 2 : bn), BK);
         if (rc != WB_OK) return rc;
