@@ -200,6 +200,9 @@ static int model_finalize(Model* m, cudaStream_t stream) {
         L.pos_w3 = p;
         RC(model_get(m, b + ".conv.dw.w", WB_F32, (int64_t)d * c.cnn_kernel, &p));
         L.dw_w = (const float*)p;
+        WB_CHECK_CUDA(cudaMalloc((void**)&L.dw_wt, (size_t)d * c.cnn_kernel * sizeof(float)));
+        m->owned.push_back(L.dw_wt);
+        RC(dwconv_transpose_weights(L.dw_w, d, c.cnn_kernel, L.dw_wt, stream));
         RC(model_get(m, b + ".conv.dw.b", WB_F32, d, &p));
         L.dw_b = (const float*)p;
         RC(get_norm(m, b + ".conv.norm", d, &L.n_cnn));
@@ -455,7 +458,18 @@ int wb_op_dwconv(const void* g_dev, int64_t ldg, const int32_t* seq_start_dev, c
     a.batch = batch; a.max_len = max_len; a.lead = lead; a.d = d; a.ksize = ksize; a.causal = causal;
     a.w = w_dev; a.bias = bias_dev; a.norm_type = norm_type; a.gamma = gamma_dev; a.beta = beta_dev; a.eps = eps;
     a.pad_vec = pad_vec_dev; a.pad_until = pad_until; a.out = out_dev; a.ldo = ldo; a.split3 = 0;
-    return dwconv_norm_silu(a, (cudaStream_t)stream);
+    // the tap-major weight copy the model keeps per layer is built here per call (stream-ordered scratch)
+    cudaStream_t st = (cudaStream_t)stream;
+    float* wt = nullptr;
+    if (ksize == 8 || ksize == 15) {
+        WB_CHECK_CUDA(cudaMallocAsync((void**)&wt, (size_t)d * ksize * sizeof(float), st));
+        int rc = dwconv_transpose_weights(w_dev, d, ksize, wt, st);
+        if (rc != WB_OK) return rc;
+        a.w_t = wt;
+    }
+    const int rc = dwconv_norm_silu(a, st);
+    if (wt != nullptr) cudaFreeAsync(wt, st);
+    return rc;
 }
 int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blank_id, float blank_penalty, int topk,
                           float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream) {

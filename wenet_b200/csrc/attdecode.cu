@@ -263,6 +263,16 @@ void ab_layout(const Model* m, long long enc_rows, int batch, int beam, int max_
 
 }  // namespace
 
+// x += A W^T + b, then a = LayerNorm(x): one kernel when the tile holds whole rows (d == 256), else GEMM + LayerNorm
+static int resid_then_norm(const void* A, long long lda, const Linear& W, int M, int d, float* x, const Norm& n, float eps,
+                           void* a_out, cudaStream_t st) {
+    if (W.b != nullptr && gemm_resid_ln_supported(d))
+        return gemm_resid_ln(A, lda, &W.tmap, W.w, M, d, W.K, W.b, 1.0f, x, d, nullptr, nullptr, n.g, n.b, eps, a_out, d, st);
+    int rc = gemm_bf16(A, lda, &W.tmap, W.w, M, d, W.K, W.b, EPI_RESID_F32, 1.0f, x, d, 0, st);
+    if (rc != WB_OK) return rc;
+    return layernorm_rows(x, d, M, d, n.g, n.b, eps, a_out, d, 0, nullptr, 0, st);
+}
+
 // op-level entry (tests): one beam step on caller-provided tables
 int attention_beam_step_op(const float* topv, const int* topi, const float* score_in, const int* end_in, const int* hyp_in,
                            const int* anc_in, int batch, int beam, int L, int pos, int eos, float* score_out, int* end_out,
@@ -381,10 +391,11 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
     for (pos = 0; pos + 1 < max_len; ++pos) {
         const bool beam_update = pos >= prefix_len - 1;
         RC(embed_tokens(cur_tok, cur_pos, R, d, D.emb, D.pe ? D.pe : m->pe, D.xscale, x, st));
+        // every LayerNorm but the first rides in the epilogue of the residual GEMM in front of it when d == 256
+        RC(layernorm_rows(x, d, R, d, D.layers[0].n1.g, D.layers[0].n1.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
         for (int li = 0; li < nl; ++li) {
             const DecLayer& Ly = D.layers[li];
             __nv_bfloat16* kvl = reinterpret_cast<__nv_bfloat16*>(ws + P.o_kv) + (size_t)li * L * R * 2 * d;
-            RC(layernorm_rows(x, d, R, d, Ly.n1.g, Ly.n1.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
             RC(gemm_bf16(a, d, &Ly.sa_qkv.tmap, Ly.sa_qkv.w, R, 3 * d, d, Ly.sa_qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
             {
                 ProfScope _ps(PT_ATTENTION, st, 0.0);
@@ -394,8 +405,7 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
                 count_launch();
                 WB_CHECK_LAUNCH();
             }
-            RC(gemm_bf16(ctx, d, &Ly.sa_out.tmap, Ly.sa_out.w, R, d, d, Ly.sa_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
-            RC(layernorm_rows(x, d, R, d, Ly.n2.g, Ly.n2.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
+            RC(resid_then_norm(ctx, d, Ly.sa_out, R, d, x, Ly.n2, c.dec_ln_eps, a, st));
             RC(gemm_bf16(a, d, &Ly.ca_q.tmap, Ly.ca_q.w, R, d, d, Ly.ca_q.b, EPI_BF16, 1.0f, q, d, 0, st));
             {
                 const void* memkv = ws + P.o_memkv + (size_t)li * enc_rows * 2 * d * 2;
@@ -410,10 +420,10 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
                 A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
                 RC(attention_forward(A, st));
             }
-            RC(gemm_bf16(ctx, d, &Ly.ca_out.tmap, Ly.ca_out.w, R, d, d, Ly.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
-            RC(layernorm_rows(x, d, R, d, Ly.n3.g, Ly.n3.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
+            RC(resid_then_norm(ctx, d, Ly.ca_out, R, d, x, Ly.n3, c.dec_ln_eps, a, st));
             RC(gemm_bf16(a, d, &Ly.ff1.tmap, Ly.ff1.w, R, ff, d, Ly.ff1.b, D.act_epi, 1.0f, hbuf, ff, 0, st));
-            RC(gemm_bf16(hbuf, ff, &Ly.ff2.tmap, Ly.ff2.w, R, d, ff, Ly.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+            // the next layer's norm1, or after_norm behind the last layer (decoder.py:272-273)
+            RC(resid_then_norm(hbuf, ff, Ly.ff2, R, d, x, (li + 1 < nl) ? D.layers[li + 1].n1 : D.after, c.dec_ln_eps, a, st));
         }
         if (!beam_update) {
             prefix_step_kernel<<<ceil_div(R, 128), 128, 0, st>>>(prefix_dev, prefix_len, N, L, pos, R, hyp[0], hyp[1], anc[0],
@@ -422,7 +432,6 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
             WB_CHECK_LAUNCH();
             continue;
         }
-        RC(layernorm_rows(x, d, R, d, D.after.g, D.after.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, P.ldl, 0, st));
         RC(ctc_lse_topk(logits, P.ldl, R, c.vocab, -1, 0.0f, N, topv, topi, st));
         {

@@ -35,6 +35,7 @@ struct EncLayer {
     const void* pos_w3 = nullptr;  // bf16 [d][3d] packed hi|hi|lo
     float* pos_proj = nullptr;     // [max_pos][d] fp32, built by finalize
     const float* dw_w = nullptr;
+    float* dw_wt = nullptr;        // [K][d] tap-major copy, built by finalize (convmod.cu direct kernel)
     const float* dw_b = nullptr;
     Norm n_cnn;                    // LayerNorm gamma/beta or folded BatchNorm scale/shift
     const float* pad_vec = nullptr;

@@ -95,6 +95,16 @@ int gather_rows(const void* src, const int* idx, int n, int row_bytes, void* dst
     return WB_OK;
 }
 
+// x += A W^T + b, then a = LayerNorm(x): one kernel when the tile holds whole rows (d == 256), else GEMM + LayerNorm
+static int dec_resid_then_norm(const void* A, long long lda, const Linear& W, int M, int d, float* x, const Norm& n, float eps,
+                               void* a_out, cudaStream_t st) {
+    if (W.b != nullptr && gemm_resid_ln_supported(d))
+        return gemm_resid_ln(A, lda, &W.tmap, W.w, M, d, W.K, W.b, 1.0f, x, d, nullptr, nullptr, n.g, n.b, eps, a_out, d, st);
+    int rc = gemm_bf16(A, lda, &W.tmap, W.w, M, d, W.K, W.b, EPI_RESID_F32, 1.0f, x, d, 0, st);
+    if (rc != WB_OK) return rc;
+    return layernorm_rows(x, d, M, d, n.g, n.b, eps, a_out, d, 0, nullptr, 0, st);
+}
+
 // one direction of the decoder: x = embed(tokens); layers; after_norm; logits = out(x)
 // Output: either the raw logits [R][ldl] (logits != null; decoder_logprobs API) or, for rescoring, only
 // tok_logp[r] = log_softmax(logits[r])[target[r]] via LSE partials (logits == null).
@@ -120,10 +130,14 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
     void* ctx_full = shared ? ws + P.o_ctx_full : ctx;
     const float scale = 1.0f / sqrtf(64.0f);
     RC(embed_tokens(Q.tok, Q.pos, N, d, D.emb, D.pe ? D.pe : m->pe, D.xscale, x, st));
+    // every LayerNorm after the first rides in the epilogue of the residual GEMM in front of it (decoder_layer.py:101-147:
+    // norm2 after the self-attention output projection, norm3 after the cross-attention one, the next layer's norm1 - or
+    // after_norm - after the feed-forward w_2)
+    if (!D.layers.empty())
+        RC(layernorm_rows(x, d, N, d, D.layers[0].n1.g, D.layers[0].n1.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
     for (size_t li = 0; li < D.layers.size(); ++li) {
         const DecLayer& L = D.layers[li];
         // masked (causal) self-attention, decoder_layer.py:101-118
-        RC(layernorm_rows(x, d, N, d, L.n1.g, L.n1.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.sa_qkv.tmap, L.sa_qkv.w, N, 3 * d, d, L.sa_qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
         if (shared) RC(gather_rows(qkv, Q.uniq_of_row, R, 3 * d * 2, qkv_full, st));
         {
@@ -139,9 +153,8 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
             RC(attention_forward(A, st));
         }
         if (shared) RC(gather_rows(ctx_full, Q.rep_row, N, d * 2, ctx, st));
-        RC(gemm_bf16(ctx, d, &L.sa_out.tmap, L.sa_out.w, N, d, d, L.sa_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(dec_resid_then_norm(ctx, d, L.sa_out, N, d, x, L.n2, c.dec_ln_eps, a, st));
         // cross-attention over the utterance's encoder frames, decoder_layer.py:120-139
-        RC(layernorm_rows(x, d, N, d, L.n2.g, L.n2.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
         RC(gemm_bf16(a, d, &L.ca_q.tmap, L.ca_q.w, N, d, d, L.ca_q.b, EPI_BF16, 1.0f, q, d, 0, st));
         RC(gemm_bf16(enc_bf16, m->cfg.precise ? 3 * d : d /*precise: rows are [hi|lo|hi]; the decoder reads hi*/, &L.ca_kv.tmap, L.ca_kv.w, (int)enc_rows, 2 * d, d, L.ca_kv.b, EPI_BF16, 1.0f, memkv,
                      2 * d, 0, st));
@@ -157,13 +170,12 @@ int run_decoder(const Model* m, const Decoder& D, const RsPlan& P, const RsDevPt
             A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
             RC(attention_forward(A, st));
         }
-        RC(gemm_bf16(ctx, d, &L.ca_out.tmap, L.ca_out.w, N, d, d, L.ca_out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
-        // feed-forward (ReLU), decoder_layer.py:141-147
-        RC(layernorm_rows(x, d, N, d, L.n3.g, L.n3.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
+        RC(dec_resid_then_norm(ctx, d, L.ca_out, N, d, x, L.n3, c.dec_ln_eps, a, st));
+        // feed-forward (ReLU / GELU), decoder_layer.py:141-147
         RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, N, ff, d, L.ff1.b, D.act_epi, 1.0f, h, ff, 0, st));
-        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, N, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        const Norm& nn = (li + 1 < D.layers.size()) ? D.layers[li + 1].n1 : D.after;
+        RC(dec_resid_then_norm(h, ff, L.ff2, N, d, x, nn, c.dec_ln_eps, a, st));
     }
-    RC(layernorm_rows(x, d, N, d, D.after.g, D.after.b, c.dec_ln_eps, a, d, 0, nullptr, 0, st));
     if (logits != nullptr) {
         WB_REQUIRE(!shared, WB_ERR_BAD_ARG, "decoder logits are only produced without prefix sharing");
         RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, N, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, ldl, 0, st));
