@@ -634,6 +634,27 @@ def main():
                                   "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
                                   "chunks": n_chunks, "audio_s_per_chunk": chunk * 0.04,
                                   "chunk_rtf": float(np.percentile(lat, 50)) / 1e3 / (chunk * 0.04)}
+            # (ii-b) SURVEY 8f-4: the same streaming step for 64 concurrent sessions in lockstep (batched caches), CUDA graph
+            from wenet_b200.asr_model import BatchedStreamingSessions
+            S_b, n_b, n_bw = 64, 60, 12
+            bfeats = torch.randn(S_b, hop * (n_b + n_bw) + window, 80, generator=gen).to(dev)
+            bs = BatchedStreamingSessions(model, S_b, chunk, left)
+            evb = []
+            for i in range(n_b + n_bw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                bs.step(bfeats[:, i * hop:i * hop + window])
+                e1.record()
+                torch.cuda.synchronize()
+                evb.append((e0, e1))
+            latb = np.array([a.elapsed_time(b) for a, b in evb[n_bw:]])
+            extra["streaming_batched"] = {"config": "S U2++ 12L/256d, %d concurrent forward_chunk sessions in lockstep "
+                                                    "(wb_encoder_forward_chunk_batch), chunk 16, num_left_chunks 4, CUDA graph" % S_b,
+                                          "p50_ms": float(np.percentile(latb, 50)), "p99_ms": float(np.percentile(latb, 99)),
+                                          "steps": n_b, "sessions": S_b,
+                                          "value": S_b * chunk * 0.04 / (float(np.percentile(latb, 50)) / 1e3),
+                                          "unit": "audio-s/s (all sessions)"}
+            del bs, bfeats
             # (i) BASELINE configs[2] model: U2++ large 24L/512d/8h, 32 x 30 s, attention_rescoring
             wl_l = workload("large")
             cfg_l = synth.recipe(wl_l["recipe"])

@@ -187,6 +187,26 @@ int wb_encoder_forward_chunk_static(const wb_model* m, const float* xs_dev, int 
                                     float* r_cnn_cache_dev, void* workspace_dev, size_t workspace_bytes,
                                     wb_stream_t stream);
 
+/* Batched streaming - `sessions` concurrent forward_chunk streams advanced in lockstep by one encoder pass (SURVEY
+ * section 8f-4; the batched-cache design of wenet/bin/export_onnx_gpu.py:83-232 StreamingEncoder).  Per session the
+ * arithmetic is that of wb_encoder_forward_chunk (encoder.py:204-300), row for row; the GEMMs see sessions x chunk rows.
+ * All sessions share T and cache_t1; each has its own position offset.  bf16 mode only.
+ * xs_dev [S][T][input_dim]; att_cache_dev [S][layers][heads][cache_t1][128] (NULL when cache_t1 = 0); cnn_cache_dev
+ * [S][layers][d][cnn_kernel-1] (NULL: first chunk); y_dev [S][chunk][d]; r_att_cache_dev [S][layers][heads][new_t1][128];
+ * r_cnn_cache_dev like cnn_cache_dev.  The _static form is capture-safe (offsets read from the device, no copy, no
+ * synchronisation; the workspace must have been used by a regular call with the same T / cache_t1 / sessions before). */
+size_t wb_encoder_chunk_batch_workspace_bytes(const wb_model* m, int T, int cache_t1, int sessions);
+int wb_encoder_forward_chunk_batch(const wb_model* m, const float* xs_dev, int T, int sessions,
+                                   const int32_t* offsets_host, int required_cache_size, const float* att_cache_dev,
+                                   int cache_t1, const float* cnn_cache_dev, float* y_dev, float* r_att_cache_dev,
+                                   float* r_cnn_cache_dev, int* out_chunk, int* out_new_cache_t1, void* workspace_dev,
+                                   size_t workspace_bytes, wb_stream_t stream);
+int wb_encoder_forward_chunk_batch_static(const wb_model* m, const float* xs_dev, int T, int sessions,
+                                          const int32_t* offsets_dev, int required_cache_size,
+                                          const float* att_cache_dev, int cache_t1, const float* cnn_cache_dev,
+                                          float* y_dev, float* r_att_cache_dev, float* r_cnn_cache_dev,
+                                          void* workspace_dev, size_t workspace_bytes, wb_stream_t stream);
+
 /* packed [M][d] -> padded [batch][t_stride][d] (rows past seq_len zeroed) and back */
 int wb_unpack_rows(const float* packed_dev, const int32_t* seq_start_dev, const int32_t* seq_len_dev,
                    int batch, int max_len, int d, float* padded_dev, int64_t t_stride, wb_stream_t stream);

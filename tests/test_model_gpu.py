@@ -126,8 +126,16 @@ def test_encoder_and_ctc(setup):
         assert mn < 1.5 * mnlo + 1e-3 and mx < 3 * mxlo + 1e-2
     # top-1 agreement with the reference on (almost) every frame
     ref_top = _packed(torch.from_numpy(g["ctc_topk_idx"][:, :, 0].astype(np.int64)), el)
-    agree = float((_packed(lp, el).argmax(-1) == ref_top).float().mean())
-    assert agree > 0.98, agree
+    same = _packed(lp, el).argmax(-1) == ref_top
+    agree = float(same.float().mean())
+    # a frame can only flip when the reference's top-1 / top-2 margin is inside twice the log-prob error measured above
+    # (operand-rounding noise): every clear-margin frame must agree, near-tie frames are counted and printed
+    tv = torch.from_numpy(g["ctc_topk_val"])
+    margin = _packed(tv[:, :, 0] - tv[:, :, 1], el)
+    clear = margin > 2.0 * mxl32
+    print("%s top-1 agreement with the reference %.4f (%d frames, %d near ties inside 2 x %.3f)"
+          % (name, agree, same.numel(), int((~clear).sum()), mxl32))
+    assert bool(same[clear].all()) and agree > 0.95, agree
 
 
 def test_chunk_mask(setup):

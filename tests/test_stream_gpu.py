@@ -77,3 +77,38 @@ def test_streaming_session_graph_replay_is_bit_identical():
         assert torch.equal(y, y_ref), (i, (y - y_ref).abs().max().item())
     assert replayed >= n_chunks - left - 1      # everything after the cache filled up went through the graph
     assert torch.equal(sess.s_att, att) and torch.equal(sess.s_cnn, cnn)
+
+
+def test_batched_sessions_equal_single_sessions():
+    """wb_encoder_forward_chunk_batch: S sessions in lockstep == S independent forward_chunk streams, bit for bit (per-row
+    arithmetic does not depend on how many rows a GEMM sees), including the CUDA-graph steady state."""
+    from wenet_b200.asr_model import B200ASRModel, BatchedStreamingSessions
+    cfg = synth.recipe("u2pp_small")
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    model = B200ASRModel(cfg, sd)
+    S, chunk, left, n_chunks = 3, 16, 2, 6
+    window, hop = (chunk - 1) * 4 + 7, 4 * chunk
+    g = torch.Generator().manual_seed(5)
+    feats = (torch.randn(S, hop * n_chunks + window, 80, generator=g) * 2 + 10).cuda()
+    # reference: one stream at a time through forward_chunk
+    singles = []
+    for s in range(S):
+        att = torch.zeros(0, 0, 0, 0, device="cuda")
+        cnn = torch.zeros(0, 0, 0, 0, device="cuda")
+        off, ys = 0, []
+        for i in range(n_chunks):
+            y, att, cnn = model.encoder.forward_chunk(feats[s:s + 1, i * hop:i * hop + window], off, chunk * left, att, cnn)
+            off += y.size(1)
+            ys.append(y)
+        singles.append((torch.cat(ys, 1), att, cnn))
+    for use_graph in (False, True):
+        sess = BatchedStreamingSessions(model, S, chunk, left, use_graph=use_graph)
+        ys = [sess.step(feats[:, i * hop:i * hop + window]).clone() for i in range(n_chunks)]
+        yb = torch.cat(ys, 1)
+        att_b = sess.s_att if sess.graph is not None else sess.att
+        cnn_b = sess.s_cnn if sess.graph is not None else sess.cnn
+        assert (sess.graph is not None) == use_graph
+        for s in range(S):
+            assert torch.equal(yb[s], singles[s][0][0]), (use_graph, s, float((yb[s] - singles[s][0][0]).abs().max()))
+            assert torch.equal(att_b[s], singles[s][1])
+            assert torch.equal(cnn_b[s], singles[s][2].reshape(cnn_b[s].shape))

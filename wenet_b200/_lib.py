@@ -58,6 +58,10 @@ _PROTOS = {
     "wb_encoder_forward_chunk": (i32, [vp, vp, i32, i32, i32, vp, i32, vp, vp, vp, vp,
                                         C.POINTER(C.c_int), C.POINTER(C.c_int), vp, sz, vp]),
     "wb_encoder_forward_chunk_static": (i32, [vp, vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, sz, vp]),
+    "wb_encoder_chunk_batch_workspace_bytes": (sz, [vp, i32, i32, i32]),
+    "wb_encoder_forward_chunk_batch": (i32, [vp, vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, vp, C.POINTER(C.c_int),
+                                              C.POINTER(C.c_int), vp, sz, vp]),
+    "wb_encoder_forward_chunk_batch_static": (i32, [vp, vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, sz, vp]),
     "wb_unpack_rows": (i32, [vp, vp, vp, i32, i32, i32, vp, i64, vp]),
     "wb_ctc_logprobs": (i32, [vp, vp, i64, i32, f32, vp, i64, i32, vp, vp, vp]),
     "wb_ctc_topk": (i32, [vp, vp, i64, i32, f32, vp, i64, i32, vp, vp, vp]),

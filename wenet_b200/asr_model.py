@@ -76,6 +76,11 @@ class B200ConformerEncoder:
     def forward_chunk(self, xs, offset, required_cache_size, att_cache=None, cnn_cache=None, att_mask=None):
         return self._o._forward_chunk(xs, offset, required_cache_size, att_cache, cnn_cache)
 
+    def forward_chunk_batch(self, xs, offsets, required_cache_size, att_cache=None, cnn_cache=None):
+        """forward_chunk for S sessions in lockstep (batched caches, export_onnx_gpu.py:83-232): see
+        B200ASRModel._forward_chunk_batch."""
+        return self._o._forward_chunk_batch(xs, offsets, required_cache_size, att_cache, cnn_cache)
+
     def forward_chunk_by_chunk(self, xs: torch.Tensor, decoding_chunk_size: int,
                                num_decoding_left_chunks: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
         """Whole-utterance streaming simulation, same contract as BaseEncoder.forward_chunk_by_chunk
@@ -183,6 +188,79 @@ class StreamingSession:
         self.graph.replay()
         self.offset += self.chunk
         return self.s_y            # static buffer: consume (or clone) before the next step
+
+
+class BatchedStreamingSessions:
+    """S concurrent streaming sessions advanced in lockstep (the batched caches of the reference's GPU
+    export, wenet/bin/export_onnx_gpu.py:83-232): step(xs) takes the (S, (chunk-1)*4+7, idim) feature windows of all sessions
+    and returns y (S, chunk, d); per session the arithmetic is forward_chunk's (encoder.py:204-300).  All sessions start at
+    the same time (the attention caches grow together); once the caches have their final size the step is captured as a
+    CUDA graph with static buffers (caches fed back, offsets advanced inside the graph)."""
+
+    def __init__(self, model: "B200ASRModel", sessions: int, decoding_chunk_size: int, num_decoding_left_chunks: int,
+                 use_graph: bool = True):
+        assert decoding_chunk_size > 0 and sessions >= 1
+        self.m, self.S = model, int(sessions)
+        self.chunk = decoding_chunk_size
+        self.required = decoding_chunk_size * num_decoding_left_chunks
+        self.window = (decoding_chunk_size - 1) * 4 + 7
+        self.use_graph = use_graph and self.required > 0 and model.spec.cnn_causal
+        self.offsets = np.zeros(self.S, dtype=np.int32)
+        self.att = None
+        self.cnn = None
+        self.graph = None
+
+    def _capture(self):
+        m, lib, S = self.m, self.m._lib, self.S
+        dev, d = m.device, m.spec.d_model
+        T, c1 = self.window, self.required
+        self.s_xs = torch.zeros(S, T, m.spec.input_dim, device=dev, dtype=torch.float32)
+        self.s_att, self.s_cnn = self.att.clone(), self.cnn.clone()
+        self.s_ratt, self.s_rcnn = torch.empty_like(self.s_att), torch.empty_like(self.s_cnn)
+        self.s_y = torch.empty(S, self.chunk, d, device=dev, dtype=torch.float32)
+        self.s_off = torch.from_numpy(self.offsets.copy()).to(dev)
+        wsb = lib.wb_encoder_chunk_batch_workspace_bytes(m.dm.handle, T, c1, S)
+        self.s_ws = torch.empty(int(wsb) + 1024, device=dev, dtype=torch.uint8)
+        oc, on = C.c_int(0), C.c_int(0)
+        check(lib.wb_encoder_forward_chunk_batch(m.dm.handle, ptr(self.s_xs), T, S, ptr(_i32(self.offsets)), int(self.required),
+                                                 ptr(self.s_att), c1, ptr(self.s_cnn), ptr(self.s_y), ptr(self.s_ratt),
+                                                 ptr(self.s_rcnn), C.byref(oc), C.byref(on), ptr(self.s_ws),
+                                                 self.s_ws.numel(), cur_stream()), "wb_encoder_forward_chunk_batch")
+        assert oc.value == self.chunk and on.value == c1
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            check(lib.wb_encoder_forward_chunk_batch_static(m.dm.handle, ptr(self.s_xs), T, S, ptr(self.s_off),
+                                                            int(self.required), ptr(self.s_att), c1, ptr(self.s_cnn),
+                                                            ptr(self.s_y), ptr(self.s_ratt), ptr(self.s_rcnn), ptr(self.s_ws),
+                                                            self.s_ws.numel(), cur_stream()),
+                  "wb_encoder_forward_chunk_batch_static")
+            self.s_att.copy_(self.s_ratt)
+            self.s_cnn.copy_(self.s_rcnn)
+            self.s_off.add_(self.chunk)
+        self.graph = g
+
+    def step(self, xs: torch.Tensor) -> torch.Tensor:
+        m = self.m
+        assert xs.size(0) == self.S
+        with torch.cuda.device(m.device):
+            steady = (self.use_graph and xs.size(1) == self.window and self.att is not None
+                      and self.att.size(3) == self.required)
+            if steady:
+                if int(self.offsets.max()) + self.chunk > m.spec.max_pos:
+                    raise _lib.WbError("utterance longer than the positional table")
+                if self.graph is None:
+                    self._capture()
+                self.s_xs.copy_(xs, non_blocking=True)
+                self.graph.replay()
+                self.offsets += self.chunk
+                return self.s_y        # static buffer: consume (or clone) before the next step
+            if self.graph is not None:
+                raise _lib.WbError("a window shorter than the steady-state one after graph capture: finish such sessions "
+                                   "through forward_chunk / a fresh BatchedStreamingSessions")
+            y, self.att, self.cnn = m._forward_chunk_batch(xs, self.offsets, self.required, self.att, self.cnn)
+            self.offsets += y.size(1)
+            return y
 
 
 class B200ASRModel:
@@ -386,6 +464,40 @@ class B200ASRModel:
                                                cache_t1, ptr(cc), ptr(y), ptr(r_att),
                                                ptr(r_cnn) if spec.cnn_causal else None, C.byref(oc), C.byref(on),
                                                ptr(ws), ws.numel(), cur_stream()), "wb_encoder_forward_chunk")
+        return y, r_att, r_cnn
+
+    def _forward_chunk_batch(self, xs, offsets, required_cache_size, att_cache, cnn_cache):
+        """S sessions in lockstep: xs (S, T, idim); offsets (S,) ints; att_cache (S, L, H, cache_t1, 128) or None;
+        cnn_cache (S, L, d, K-1) or None.  Returns (y (S, chunk, d), r_att_cache, r_cnn_cache) with the same layouts."""
+        if not xs.is_cuda:
+            raise _lib.WbError("xs must be a CUDA tensor (no CPU fallback)")
+        spec, lib = self.spec, self._lib
+        x = xs.to(torch.float32).contiguous()
+        S, T, _ = x.shape
+        L, H, d, K = spec.enc_layers, spec.heads, spec.d_model, spec.cnn_kernel
+        cache_t1 = att_cache.size(3) if (att_cache is not None and att_cache.numel() > 0) else 0
+        chunk = ((T - 1) // 2 - 1) // 2
+        key_size = cache_t1 + chunk
+        if required_cache_size < 0:
+            nxt = 0
+        elif required_cache_size == 0:
+            nxt = key_size
+        else:
+            nxt = max(key_size - required_cache_size, 0)
+        lead = K - 1 if spec.cnn_causal else 0
+        y = torch.empty(S, chunk, d, device=self.device, dtype=torch.float32)
+        r_att = torch.empty(S, L, H, key_size - nxt, 128, device=self.device, dtype=torch.float32)
+        r_cnn = torch.empty(S, L, d, max(lead, 0), device=self.device, dtype=torch.float32)
+        ac = att_cache.to(torch.float32).contiguous() if cache_t1 > 0 else None
+        cc = cnn_cache.to(torch.float32).contiguous() if (cnn_cache is not None and cnn_cache.numel() > 0) else None
+        wsb = lib.wb_encoder_chunk_batch_workspace_bytes(self.dm.handle, T, cache_t1, S)
+        ws = self._workspace(wsb)
+        oc, on = C.c_int(0), C.c_int(0)
+        with torch.cuda.device(self.device):
+            check(lib.wb_encoder_forward_chunk_batch(self.dm.handle, ptr(x), T, S, ptr(_i32(offsets)), int(required_cache_size),
+                                                     ptr(ac), cache_t1, ptr(cc), ptr(y), ptr(r_att),
+                                                     ptr(r_cnn) if lead > 0 else None, C.byref(oc), C.byref(on), ptr(ws),
+                                                     ws.numel(), cur_stream()), "wb_encoder_forward_chunk_batch")
         return y, r_att, r_cnn
 
     # ----- CTC -----

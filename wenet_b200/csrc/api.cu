@@ -200,9 +200,6 @@ static int model_finalize(Model* m, cudaStream_t stream) {
         L.pos_w3 = p;
         RC(model_get(m, b + ".conv.dw.w", WB_F32, (int64_t)d * c.cnn_kernel, &p));
         L.dw_w = (const float*)p;
-        WB_CHECK_CUDA(cudaMalloc((void**)&L.dw_wt, (size_t)d * c.cnn_kernel * sizeof(float)));
-        m->owned.push_back(L.dw_wt);
-        RC(dwconv_transpose_weights(L.dw_w, d, c.cnn_kernel, L.dw_wt, stream));
         RC(model_get(m, b + ".conv.dw.b", WB_F32, d, &p));
         L.dw_b = (const float*)p;
         RC(get_norm(m, b + ".conv.norm", d, &L.n_cnn));
@@ -458,18 +455,7 @@ int wb_op_dwconv(const void* g_dev, int64_t ldg, const int32_t* seq_start_dev, c
     a.batch = batch; a.max_len = max_len; a.lead = lead; a.d = d; a.ksize = ksize; a.causal = causal;
     a.w = w_dev; a.bias = bias_dev; a.norm_type = norm_type; a.gamma = gamma_dev; a.beta = beta_dev; a.eps = eps;
     a.pad_vec = pad_vec_dev; a.pad_until = pad_until; a.out = out_dev; a.ldo = ldo; a.split3 = 0;
-    // the tap-major weight copy the model keeps per layer is built here per call (stream-ordered scratch)
-    cudaStream_t st = (cudaStream_t)stream;
-    float* wt = nullptr;
-    if (ksize == 8 || ksize == 15) {
-        WB_CHECK_CUDA(cudaMallocAsync((void**)&wt, (size_t)d * ksize * sizeof(float), st));
-        int rc = dwconv_transpose_weights(w_dev, d, ksize, wt, st);
-        if (rc != WB_OK) return rc;
-        a.w_t = wt;
-    }
-    const int rc = dwconv_norm_silu(a, st);
-    if (wt != nullptr) cudaFreeAsync(wt, st);
-    return rc;
+    return dwconv_norm_silu(a, (cudaStream_t)stream);
 }
 int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blank_id, float blank_penalty, int topk,
                           float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream) {
@@ -556,6 +542,38 @@ int wb_op_attention_beam_step(const float* topk_val_dev, const int32_t* topk_idx
     return attention_beam_step_op(topk_val_dev, topk_idx_dev, score_in_dev, end_in_dev, hyp_in_dev, anc_in_dev, batch, beam,
                                   max_len, pos, eos, score_out_dev, end_out_dev, hyp_out_dev, anc_out_dev, next_tok_dev,
                                   next_pos_dev, utt_ended_dev, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- batched streaming
+size_t wb_encoder_chunk_batch_workspace_bytes(const wb_model* mm, int T, int cache_t1, int sessions) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    if (!m || !m->finalized || sessions < 1) return 0;
+    return encoder_chunk_batch_workspace_bytes(m, T, cache_t1, sessions);
+}
+int wb_encoder_forward_chunk_batch(const wb_model* mm, const float* xs_dev, int T, int sessions, const int32_t* offsets_host,
+                                   int required_cache_size, const float* att_cache_dev, int cache_t1, const float* cnn_cache_dev,
+                                   float* y_dev, float* r_att_cache_dev, float* r_cnn_cache_dev, int* out_chunk,
+                                   int* out_new_cache_t1, void* workspace_dev, size_t workspace_bytes, wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "forward_chunk_batch: model not finalized");
+    WB_REQUIRE(xs_dev && offsets_host && y_dev && r_att_cache_dev && workspace_dev, WB_ERR_BAD_ARG,
+               "forward_chunk_batch: null argument");
+    return encoder_forward_chunk_batch(m, xs_dev, T, sessions, offsets_host, nullptr, required_cache_size, att_cache_dev, cache_t1,
+                                       cnn_cache_dev, y_dev, r_att_cache_dev, r_cnn_cache_dev, out_chunk, out_new_cache_t1,
+                                       workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+int wb_encoder_forward_chunk_batch_static(const wb_model* mm, const float* xs_dev, int T, int sessions,
+                                          const int32_t* offsets_dev, int required_cache_size, const float* att_cache_dev,
+                                          int cache_t1, const float* cnn_cache_dev, float* y_dev, float* r_att_cache_dev,
+                                          float* r_cnn_cache_dev, void* workspace_dev, size_t workspace_bytes,
+                                          wb_stream_t stream) {
+    const Model* m = reinterpret_cast<const Model*>(mm);
+    WB_REQUIRE(m && m->finalized, WB_ERR_NOT_LOADED, "forward_chunk_batch_static: model not finalized");
+    WB_REQUIRE(xs_dev && offsets_dev && y_dev && r_att_cache_dev && workspace_dev, WB_ERR_BAD_ARG,
+               "forward_chunk_batch_static: null argument");
+    return encoder_forward_chunk_batch(m, xs_dev, T, sessions, nullptr, offsets_dev, required_cache_size, att_cache_dev, cache_t1,
+                                       cnn_cache_dev, y_dev, r_att_cache_dev, r_cnn_cache_dev, nullptr, nullptr, workspace_dev,
+                                       workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -199,148 +199,7 @@ dwconv_kernel(DwDev P) {
     }
 }
 
-// ---- direct (no shared memory, no CTA barrier) form for the recipe kernel sizes --------------------------------------
-// A warp owns FP consecutive output frames of one utterance for ALL channels (NP passes of 128 channels, 4 per lane).  Its
-// (FP + K - 1) input rows are read straight from global memory as 8-byte loads (256 B per warp and row, rows shared with
-// the neighbouring warps come out of L1 / L2), the taps from a tap-major copy of the weights ([K][d]: one float4 per lane
-// and tap), every multiply-add / normalisation step is a packed fp32x2 instruction and the activation is the packed quad
-// sigmoid.  Compared with the staged kernel above this drops the shared-memory round trip of inputs and weights (with its
-// index divisions) and the CTA barrier: ~2.7x fewer issued instructions per frame.
-template <int KT, int NP, int FP>
-__global__ void __launch_bounds__(DW_THREADS)
-dwconv_direct_kernel(DwDev P, const float* __restrict__ wt) {
-    const int b = blockIdx.y;
-    const int n_in = P.seq_len[b];
-    const int n_out = n_in - P.lead;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = (blockIdx.x * (DW_THREADS / 32) + warp) * FP;   // first output frame of this warp
-    if (t0 >= n_out) return;
-    const int d = P.d;
-    constexpr int K = KT;
-    const int left = P.causal ? (K - 1) : (K - 1) / 2;
-    const long long base = P.seq_start[b];
-    const int nf = min(FP, n_out - t0);
-    float2 acc[NP][FP][2];
-#pragma unroll
-    for (int ps = 0; ps < NP; ++ps) {
-        const int c0 = ps * 128 + 4 * lane;
-        const bool act = c0 < d;
-        float2 w01[K], w23[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float4 w4 = act ? __ldg(reinterpret_cast<const float4*>(wt + (size_t)k * d + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            w01[k] = make_float2(w4.x, w4.y);
-            w23[k] = make_float2(w4.z, w4.w);
-        }
-        const float4 bb = act ? __ldg(reinterpret_cast<const float4*>(P.bias + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int f = 0; f < FP; ++f) {
-            acc[ps][f][0] = make_float2(bb.x, bb.y);
-            acc[ps][f][1] = make_float2(bb.z, bb.w);
-        }
-        uint2 pad = make_uint2(0u, 0u);
-        if (act && P.pad_vec != nullptr) {
-            const float4 pv = __ldg(reinterpret_cast<const float4*>(P.pad_vec + c0));
-            pad = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
-        }
-#pragma unroll
-        for (int r = 0; r < FP + K - 1; ++r) {
-            const int p = P.lead + t0 - left + r;    // input position of this row
-            uint2 xx = make_uint2(0u, 0u);
-            if (act) {
-                if (p >= 0 && p < n_in) {
-                    xx = __ldg(reinterpret_cast<const uint2*>(P.g + (base + p) * P.ldg + c0));
-                } else if (P.pad_vec != nullptr &&
-                           ((p < 0 && P.causal) || (p >= n_in && !P.causal && p < P.pad_until + P.lead))) {
-                    xx = pad;    // frames zero-filled BEFORE pointwise_conv1 arrive as GLU(bias) (see the staged kernel)
-                }
-            }
-            const float2 x01 = make_float2(bf16_lo(xx.x), bf16_hi(xx.x)), x23 = make_float2(bf16_lo(xx.y), bf16_hi(xx.y));
-#pragma unroll
-            for (int f = 0; f < FP; ++f) {
-                const int k = r - f;   // tap of input row r for output frame t0 + f (compile-time after unrolling)
-                if (k >= 0 && k < K) {
-                    acc[ps][f][0] = f2_fma(w01[k], x01, acc[ps][f][0]);
-                    acc[ps][f][1] = f2_fma(w23[k], x23, acc[ps][f][1]);
-                }
-            }
-        }
-    }
-    float4 g4[NP], b4[NP];
-#pragma unroll
-    for (int ps = 0; ps < NP; ++ps) {
-        const int c0 = ps * 128 + 4 * lane;
-        g4[ps] = (c0 < d) ? __ldg(reinterpret_cast<const float4*>(P.gamma + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        b4[ps] = (c0 < d) ? __ldg(reinterpret_cast<const float4*>(P.beta + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const float inv_d = 1.0f / (float)d;
-#pragma unroll
-    for (int f = 0; f < FP; ++f) {
-        if (f >= nf) break;   // warp-uniform
-        float mean = 0.f, rstd = 1.f;
-        if (P.norm_type == 0) {
-            float sm = 0.f;
-#pragma unroll
-            for (int ps = 0; ps < NP; ++ps)
-                sm += (acc[ps][f][0].x + acc[ps][f][0].y) + (acc[ps][f][1].x + acc[ps][f][1].y);
-            mean = warp_sum(sm) * inv_d;
-            float q = 0.f;
-            const float2 m2 = make_float2(-mean, -mean);
-#pragma unroll
-            for (int ps = 0; ps < NP; ++ps) {
-                if (ps * 128 + 4 * lane < d) {
-                    const float2 z0 = f2_add(acc[ps][f][0], m2), z1 = f2_add(acc[ps][f][1], m2);
-                    q = fmaf(z0.x, z0.x, q);
-                    q = fmaf(z0.y, z0.y, q);
-                    q = fmaf(z1.x, z1.x, q);
-                    q = fmaf(z1.y, z1.y, q);
-                }
-            }
-            rstd = rsqrtf(warp_sum(q) * inv_d + P.eps);
-        }
-        __nv_bfloat16* o = P.out + ((long long)P.out_start[b] + t0 + f) * P.ldo;
-#pragma unroll
-        for (int ps = 0; ps < NP; ++ps) {
-            const int c0 = ps * 128 + 4 * lane;
-            if (c0 < d) {
-                float2 ya, yb;
-                const float2 ga = make_float2(g4[ps].x, g4[ps].y), gb = make_float2(g4[ps].z, g4[ps].w);
-                const float2 ba = make_float2(b4[ps].x, b4[ps].y), bbv = make_float2(b4[ps].z, b4[ps].w);
-                if (P.norm_type == 0) {
-                    const float2 m2 = make_float2(-mean, -mean), r2 = make_float2(rstd, rstd);
-                    ya = f2_fma(f2_mul(f2_add(acc[ps][f][0], m2), r2), ga, ba);
-                    yb = f2_fma(f2_mul(f2_add(acc[ps][f][1], m2), r2), gb, bbv);
-                } else {   // folded BatchNorm (eval): y = x * scale + shift
-                    ya = f2_fma(acc[ps][f][0], ga, ba);
-                    yb = f2_fma(acc[ps][f][1], gb, bbv);
-                }
-                float2 sa, sb;
-                sigmoid4_f2(ya, yb, sa, sb);
-                ya = f2_mul(ya, sa);
-                yb = f2_mul(yb, sb);
-                *reinterpret_cast<uint2*>(o + c0) = make_uint2(pack_bf16x2(ya.x, ya.y), pack_bf16x2(yb.x, yb.y));
-            }
-        }
-    }
-}
-
-// [d][K] -> [K][d]
-__global__ void dw_transpose_kernel(const float* __restrict__ w, int d, int K, float* __restrict__ wt) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < d * K) {
-        const int c = i / K, k = i - c * K;
-        wt[(size_t)k * d + c] = w[i];
-    }
-}
-
 }  // namespace
-
-int dwconv_transpose_weights(const float* w_dk, int d, int K, float* wt_kd, cudaStream_t stream) {
-    dw_transpose_kernel<<<ceil_div(d * K, 256), 256, 0, stream>>>(w_dk, d, K, wt_kd);
-    count_launch();
-    WB_CHECK_LAUNCH();
-    return WB_OK;
-}
 
 int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream) {
     if (a.batch <= 0 || a.max_len <= 0) return WB_OK;
@@ -369,28 +228,6 @@ int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream) {
     P.out = reinterpret_cast<__nv_bfloat16*>(a.out);
     P.ldo = a.ldo;
     P.split3 = a.split3;
-    // direct form: recipe kernel sizes, bf16 output, tap-major weights provided (the model prepares them at finalize)
-    if (a.w_t != nullptr && !a.split3 && (a.ksize == 8 || a.ksize == 15) && a.d % 4 == 0 && a.ldg % 4 == 0) {
-        ProfScope _ps(PT_DWCONV, stream, (double)a.batch * a.max_len * a.d * 4.0);
-#define WB_DWD(KT, NP, FP)                                                                                  \
-    do {                                                                                                     \
-        dim3 grid(ceil_div(a.max_len, (DW_THREADS / 32) * FP), a.batch);                                     \
-        dwconv_direct_kernel<KT, NP, FP><<<grid, DW_THREADS, 0, stream>>>(P, a.w_t);                         \
-    } while (0)
-        if (a.ksize == 8) {
-            if (a.d <= 128) WB_DWD(8, 1, 4);
-            else if (a.d <= 256) WB_DWD(8, 2, 4);
-            else WB_DWD(8, 4, 2);
-        } else {
-            if (a.d <= 128) WB_DWD(15, 1, 4);
-            else if (a.d <= 256) WB_DWD(15, 2, 4);
-            else WB_DWD(15, 4, 2);
-        }
-#undef WB_DWD
-        count_launch();
-        WB_CHECK_LAUNCH();
-        return WB_OK;
-    }
     const int rows_in = TT + a.ksize - 1;
     const size_t smem = ((size_t)rows_in * a.d * 2 + 15) / 16 * 16 + (size_t)a.ksize * a.d * sizeof(float);
     dim3 grid(ceil_div(a.max_len, TT), a.batch);

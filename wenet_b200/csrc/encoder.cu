@@ -427,7 +427,7 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
             DwConvArgs D;
             D.g = g; D.ldg = lda; D.in_split3 = sp; D.seq_start = d_ss; D.seq_len = d_tp; D.out_start = d_ss;
             D.batch = batch; D.max_len = P.max_tp; D.lead = 0; D.d = d; D.ksize = c.cnn_kernel;
-            D.causal = c.cnn_causal; D.w = L.dw_w; D.w_t = L.dw_wt; D.bias = L.dw_b; D.norm_type = c.cnn_norm;
+            D.causal = c.cnn_causal; D.w = L.dw_w; D.bias = L.dw_b; D.norm_type = c.cnn_norm;
             D.gamma = L.n_cnn.g; D.beta = L.n_cnn.b; D.eps = c.ln_eps; D.pad_vec = L.pad_vec;
             D.pad_until = pad_to_frames > 0 ? pad_to_frames : P.max_tp;
             D.out = g2; D.ldo = lda; D.split3 = sp;
@@ -654,7 +654,7 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
             DwConvArgs D;
             D.g = g; D.ldg = lda; D.in_split3 = sp; D.seq_start = d_zero; D.seq_len = d_cin; D.out_start = d_zero;
             D.batch = 1; D.max_len = chunk; D.lead = lead; D.d = d; D.ksize = c.cnn_kernel;
-            D.causal = c.cnn_causal; D.w = L.dw_w; D.w_t = L.dw_wt; D.bias = L.dw_b; D.norm_type = c.cnn_norm;
+            D.causal = c.cnn_causal; D.w = L.dw_w; D.bias = L.dw_b; D.norm_type = c.cnn_norm;
             D.gamma = L.n_cnn.g; D.beta = L.n_cnn.b; D.eps = c.ln_eps; D.pad_vec = L.pad_vec; D.pad_until = chunk;
             D.out = g2; D.ldo = lda; D.split3 = sp;
             RC(sp ? dwconv_norm_silu_f32(D, st) : dwconv_norm_silu(D, st));

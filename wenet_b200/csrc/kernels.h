@@ -157,11 +157,8 @@ struct DwConvArgs {
     void* out; long long ldo; int split3;   // bf16 [rows_out, ldo]; out row = out_start[b] + t
     const int* out_start;
     int in_split3 = 0;   // precise mode: g rows are [hi | lo | hi] blocks of width d (value = hi + lo)
-    const float* w_t = nullptr;   // optional tap-major copy of w ([ksize][d]): selects the direct (no shared memory) kernel
 };
 int dwconv_norm_silu(const DwConvArgs& a, cudaStream_t stream);
-// wt_kd[k][c] = w_dk[c][k]
-int dwconv_transpose_weights(const float* w_dk, int d, int K, float* wt_kd, cudaStream_t stream);
 // fp32 CUDA-core version for the precise parity mode (precise.cu); honours in_split3
 int dwconv_norm_silu_f32(const DwConvArgs& a, cudaStream_t stream);
 
@@ -232,7 +229,9 @@ struct RescoreArgs {
 int rescore_combine(const RescoreArgs& a, cudaStream_t stream);
 
 // small utility kernels (util.cu)
+// row_pos[seq_start[b] + t] = clamp(pos_offset + (pos_offset_dev ? pos_offset_dev[per_seq_offset ? b : 0] : 0) + t)
 int fill_row_pos(const int* seq_start, const int* seq_len, int batch, int pos_offset, int* row_pos,
-                 int max_len, cudaStream_t stream, const int* pos_offset_dev = nullptr, int max_pos = 0x7fffffff);
+                 int max_len, cudaStream_t stream, const int* pos_offset_dev = nullptr, int max_pos = 0x7fffffff,
+                 int per_seq_offset = 0);
 
 }  // namespace wb

@@ -35,7 +35,6 @@ struct EncLayer {
     const void* pos_w3 = nullptr;  // bf16 [d][3d] packed hi|hi|lo
     float* pos_proj = nullptr;     // [max_pos][d] fp32, built by finalize
     const float* dw_w = nullptr;
-    float* dw_wt = nullptr;        // [K][d] tap-major copy, built by finalize (convmod.cu direct kernel)
     const float* dw_b = nullptr;
     Norm n_cnn;                    // LayerNorm gamma/beta or folded BatchNorm scale/shift
     const float* pad_vec = nullptr;
@@ -103,6 +102,13 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
 int attention_beam_step_op(const float* topv, const int* topi, const float* score_in, const int* end_in, const int* hyp_in,
                            const int* anc_in, int batch, int beam, int L, int pos, int eos, float* score_out, int* end_out,
                            int* hyp_out, int* anc_out, int* cur_tok, int* cur_pos, int* utt_ended, cudaStream_t st);
+
+// ---- batched streaming (stream_batch.cu) ------------------------------------------------------------------------------
+size_t encoder_chunk_batch_workspace_bytes(const Model* m, int T, int cache_t1, int sessions);
+int encoder_forward_chunk_batch(const Model* m, const float* xs, int T, int S, const int32_t* offsets_host,
+                                const int32_t* offsets_dev, int required_cache_size, const float* att_cache, int cache_t1,
+                                const float* cnn_cache, float* y, float* r_att, float* r_cnn, int* out_chunk,
+                                int* out_new_cache_t1, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // ---- Whisper front-end + encoder (whisper.cu) ------------------------------------------------------------------------
 struct LogMelPlan;

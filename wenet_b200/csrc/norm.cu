@@ -154,11 +154,11 @@ __global__ void cast_rows_kernel(const float* __restrict__ x, long long ldx, int
 // pos_offset_dev (optional): the offset is read from device memory and added to pos_offset - lets a captured CUDA
 // graph of the streaming chunk step advance through the utterance; positions are clamped to [0, max_pos)
 __global__ void fill_row_pos_kernel(const int* __restrict__ seq_start, const int* __restrict__ seq_len,
-                                    int pos_offset, const int* __restrict__ pos_offset_dev, int max_pos,
+                                    int pos_offset, const int* __restrict__ pos_offset_dev, int per_seq, int max_pos,
                                     int* __restrict__ row_pos) {
     const int b = blockIdx.y;
     const int s = seq_start[b], n = seq_len[b];
-    const int off = pos_offset + (pos_offset_dev ? *pos_offset_dev : 0);
+    const int off = pos_offset + (pos_offset_dev ? pos_offset_dev[per_seq ? b : 0] : 0);
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
         row_pos[s + t] = min(max(off + t, 0), max_pos - 1);
 }
@@ -242,11 +242,11 @@ int cast_rows_bf16(const float* x, long long ldx, int M, int d, void* out_bf16, 
 }
 
 int fill_row_pos(const int* seq_start, const int* seq_len, int batch, int pos_offset, int* row_pos, int max_len,
-                 cudaStream_t stream, const int* pos_offset_dev, int max_pos) {
+                 cudaStream_t stream, const int* pos_offset_dev, int max_pos, int per_seq_offset) {
     if (batch <= 0 || max_len <= 0) return WB_OK;
     dim3 grid(ceil_div(max_len, 256), batch);
     ProfScope _ps(PT_MISC, stream, 0.0);
-    fill_row_pos_kernel<<<grid, 256, 0, stream>>>(seq_start, seq_len, pos_offset, pos_offset_dev, max_pos, row_pos);
+    fill_row_pos_kernel<<<grid, 256, 0, stream>>>(seq_start, seq_len, pos_offset, pos_offset_dev, per_seq_offset, max_pos, row_pos);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
