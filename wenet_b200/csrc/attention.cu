@@ -44,6 +44,7 @@ struct AttnDev {
     int split3_out;
     int split_width;
     int v_mode;
+    int kbias_scaled;   // kbias already holds c * scale * log2(e): fetched by cp.async straight into shared memory
 };
 
 // KN = keys per tile.  128: 100 KB smem, 256 TMEM columns (S 128 | O 64 | L 16) -> 2 CTAs/SM.
@@ -155,16 +156,48 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     // per-key bias of a tile (log2 domain); keys past the sequence end (rows of the next utterance / TMA zero fill)
     // get -1e30 and never count.  The values of tile kt + 1 are fetched at the top of tile kt and parked in the other
     // half of sC before tile kt's only CTA barrier, so neither the load latency nor a second barrier is on the path.
-    auto fetch_c = [&](int kt) -> float {
+    // The load is issued here and its value is first USED at the store into sC at the end of the tile (the scaling happens
+    // there): with the multiply next to the load the in-order warp sat on the scoreboard at the top of every tile
+    // (profiles/r2_ncu_attn_v29.txt: 6.6 % of the samples on this line, and the other warps behind it at the CTA barrier).
+    auto fetch_c_raw = [&](int kt, bool& valid) -> float {
         const int j = kt * KN + tid;
-        if (tid >= KN || kt >= kt1 || j >= k_len) return -1.0e30f;
-        return (P.kbias != nullptr) ? P.kbias[(long long)(k_start + j) * P.ld_kbias + h] * P.scale_log2e : 0.f;
+        valid = (tid < KN) && (kt < kt1) && (j < k_len);
+        return (valid && P.kbias != nullptr) ? __ldg(P.kbias + (long long)(k_start + j) * P.ld_kbias + h) : 0.f;
     };
-    if (tid < KN && kt0 < kt1) sC[(kt0 & 1) * KN + tid] = fetch_c(kt0);
+    // Pre-scaled bias (the encoder path: relpos_kprep writes c * scale * log2 e): the next tile's 64 values go global ->
+    // shared by cp.async (LDGSTS), no register and no scoreboard wait in the in-order instruction stream at all; keys past
+    // the sequence end get -1e30 by a plain store.  cp.async.wait_all sits right before the tile's CTA barrier.
+    auto fetch_c_async = [&](int kt) {
+        if (tid < KN) {
+            const int j = kt * KN + tid;
+            float* dst = sC + (kt & 1) * KN + tid;
+            if (kt < kt1 && j < k_len) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)),
+                             "l"(P.kbias + (long long)(k_start + j) * P.ld_kbias + h)
+                             : "memory");
+            } else {
+                *dst = -1.0e30f;
+            }
+        }
+    };
+    const bool c_async = P.kbias_scaled != 0;
+    if (kt0 < kt1) {
+        if (c_async) {
+            fetch_c_async(kt0);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        } else if (tid < KN) {
+            bool v0;
+            const float c0 = fetch_c_raw(kt0, v0);
+            sC[(kt0 & 1) * KN + tid] = v0 ? c0 * P.scale_log2e : -1.0e30f;
+        }
+    }
     __syncthreads();
     for (int kt = kt0; kt < kt1; ++kt) {
         const int j0 = kt * KN;
-        const float c_next = fetch_c(kt + 1);
+        bool c_next_valid = false;
+        float c_next_raw = 0.f;
+        if (c_async) fetch_c_async(kt + 1);
+        else c_next_raw = fetch_c_raw(kt + 1, c_next_valid);
         if (tid == 0 && kt == kt0) {   // later score MMAs are issued one tile ahead, together with the P V MMA (below)
             mbar_wait(bar_q, 0);
             mbar_wait(bar_k, ph);
@@ -250,27 +283,30 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             tmem_st_wait();
         }
         const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
-        uint32_t pk[32];
+        // probabilities of one 32-key half at a time, packed and stored straight away: 16 packed words live instead of 32
+        // (the kernel runs at the 128-register cap of 4 CTAs / SM)
+        uint8_t* prow = sP + tid * 128;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const uint32_t* r = hh ? r1 : r0;
+            uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 const float p0 = fast_exp2(__uint_as_float(r[i]) - m_eff);
                 const float p1 = fast_exp2(__uint_as_float(r[i + 1]) - m_eff);
                 const float p2 = fast_exp2(__uint_as_float(r[i + 2]) - m_eff);
                 const float p3 = fast_exp2(__uint_as_float(r[i + 3]) - m_eff);
-                pk[hh * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
-                pk[hh * 16 + (i >> 1) + 1] = pack_bf16x2(p2, p3);
+                pk[i >> 1] = pack_bf16x2(p0, p1);
+                pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
                 l_acc += (p0 + p1) + (p2 + p3);
             }
-        }
-        uint8_t* prow = sP + tid * 128;
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-            *reinterpret_cast<uint4*>(prow + ((u ^ (tid & 7)) << 4)) =
-                make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        if (tid < KN) sC[((kt + 1) & 1) * KN + tid] = c_next;
+            for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(prow + (((hh * 4 + u) ^ (tid & 7)) << 4)) =
+                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+        if (c_async) asm volatile("cp.async.wait_all;" ::: "memory");
+        else if (tid < KN) sC[((kt + 1) & 1) * KN + tid] = c_next_valid ? c_next_raw * P.scale_log2e : -1.0e30f;
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -358,7 +394,7 @@ __global__ void relpos_kprep_kernel(const __nv_bfloat16* __restrict__ k, long lo
                                     const float* __restrict__ P, const int* __restrict__ row_pos,
                                     const float* __restrict__ bias_u, const float* __restrict__ bias_v, int M,
                                     int heads, __nv_bfloat16* __restrict__ kp, long long ldkp,
-                                    float* __restrict__ kbias) {
+                                    float* __restrict__ kbias, float out_scale) {
     // one warp per (row, head): 64 channels = 2 per lane
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -375,7 +411,7 @@ __global__ void relpos_kprep_kernel(const __nv_bfloat16* __restrict__ k, long lo
     *reinterpret_cast<uint32_t*>(kp + row * ldkp + col) = pack_bf16x2(k0 + p.x, k1 + p.y);
     float c = u.x * k0 + u.y * k1 + v.x * p.x + v.y * p.y;
     c = warp_sum(c);
-    if (lane == 0) kbias[row * heads + h] = c;
+    if (lane == 0) kbias[row * heads + h] = c * out_scale;
 }
 
 }  // namespace
@@ -408,6 +444,7 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     P.split3_out = a.split3_out;
     P.split_width = a.heads * DK;
     P.v_mode = a.v_mode;
+    P.kbias_scaled = (a.kbias != nullptr && a.kbias_scaled) ? 1 : 0;
     WB_REQUIRE((a.ldo % 8) == 0 && (a.out_col0 % 8) == 0, WB_ERR_BAD_ARG, "attention: output pitch/offset must be %%8");
     WB_SET_MAX_DYN_SMEM(attention_online_kernel, AttnCfg<KN>::kSmem);
     dim3 grid(ceil_div(a.max_q_len, AT_M), a.heads, a.batch);
@@ -420,7 +457,7 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
 
 int relpos_kprep(const void* k_bf16, long long ldk, const float* P, const int* row_pos, const float* bias_u,
                  const float* bias_v, int M, int heads, void* kprime_bf16, long long ldkp, float* kbias,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, float kbias_scale) {
     if (M <= 0) return WB_OK;
     const long long warps = (long long)M * heads;
     const int block = 256;
@@ -428,7 +465,7 @@ int relpos_kprep(const void* k_bf16, long long ldk, const float* P, const int* r
     ProfScope _ps(PT_KPREP, stream, (double)M * heads * 64 * 8.0);
     relpos_kprep_kernel<<<(unsigned)grid, block, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(k_bf16), ldk, P, row_pos, bias_u, bias_v, M, heads,
-        reinterpret_cast<__nv_bfloat16*>(kprime_bf16), ldkp, kbias);
+        reinterpret_cast<__nv_bfloat16*>(kprime_bf16), ldkp, kbias, kbias_scale);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

@@ -406,13 +406,13 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
             // GEMM epilogue was measured in round 1 and lost 0.8 ms of GEMM time per step to save 0.39 ms here)
             RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, Mi, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
             RC(relpos_kprep(reinterpret_cast<const uint8_t*>(qkv) + (size_t)d * 2, 3 * d, L.pos_proj, d_row_pos, L.pos_u,
-                            L.pos_v, Mi, H, kp, d, kbias, st));
+                            L.pos_v, Mi, H, kp, d, kbias, st, att_scale * 1.4426950408889634f));
             {
                 AttnArgs A;
                 A.q = qkv; A.ldq = 3 * d; A.q_rows = M; A.q_col0 = 0;
                 A.k = kp; A.ldk = d; A.k_rows = M; A.k_col0 = 0;
                 A.v = qkv; A.ldv = 3 * d; A.v_rows = M; A.v_col0 = 2 * d;
-                A.kbias = kbias; A.ld_kbias = H;
+                A.kbias = kbias; A.ld_kbias = H; A.kbias_scaled = 1;
                 A.q_start = d_ss; A.q_len = d_tp; A.k_start = d_ss; A.k_len = d_tp;
                 A.batch = batch; A.heads = H; A.max_q_len = P.max_tp;
                 A.chunk_size = chunk; A.num_left_chunks = num_decoding_left_chunks; A.scale = att_scale;
@@ -620,13 +620,13 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
                 chunk, d, H, kcat, vcat, r_att_cache_dev + li * ratt_l, nxt);
             count_launch();
             WB_CHECK_LAUNCH();
-            RC(relpos_kprep(kcat, d, L.pos_proj, d_row_pos, L.pos_u, L.pos_v, key_size, H, kp, d, kbias, st));
+            RC(relpos_kprep(kcat, d, L.pos_proj, d_row_pos, L.pos_u, L.pos_v, key_size, H, kp, d, kbias, st, att_scale * 1.4426950408889634f));
             {
                 AttnArgs A;
                 A.q = qkv; A.ldq = 3 * d; A.q_rows = chunk; A.q_col0 = 0;
                 A.k = kp; A.ldk = d; A.k_rows = key_size; A.k_col0 = 0;
                 A.v = vcat; A.ldv = d; A.v_rows = key_size; A.v_col0 = 0;
-                A.kbias = kbias; A.ld_kbias = H;
+                A.kbias = kbias; A.ld_kbias = H; A.kbias_scaled = 1;
                 A.q_start = d_zero; A.q_len = d_chunk; A.k_start = d_zero; A.k_len = d_key;
                 A.batch = 1; A.heads = H; A.max_q_len = chunk;
                 A.chunk_size = 0; A.num_left_chunks = -1; A.scale = att_scale;   // att_mask is all-ones (encoder.py:243-247)

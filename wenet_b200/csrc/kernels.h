@@ -124,6 +124,7 @@ struct AttnArgs {
     const void* k;  long long ldk;  long long k_rows;   int k_col0;
     const void* v;  long long ldv;  long long v_rows;   int v_col0;
     const float* kbias;  int ld_kbias;                  // [k_rows, heads] fp32 or null
+    int kbias_scaled = 0;                               // 1: kbias already multiplied by scale * log2(e) (relpos_kprep kbias_scale)
     const int* q_start; const int* q_len;               // [batch] device
     const int* k_start; const int* k_len;               // [batch] device
     int batch, heads, max_q_len;
@@ -139,7 +140,7 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream);
 // (rel-pos attention with rel_shift removed, wenet attention.py:395-417, folded into one score GEMM)
 int relpos_kprep(const void* k_bf16, long long ldk, const float* P /*[maxlen, d]*/, const int* row_pos,
                  const float* bias_u, const float* bias_v, int M, int heads, void* kprime_bf16,
-                 long long ldkp, float* kbias /*[M, heads]*/, cudaStream_t stream);
+                 long long ldkp, float* kbias /*[M, heads]*/, cudaStream_t stream, float kbias_scale = 1.0f);
 
 // ---- convolution module tail (convmod.cu) ------------------------------------------------------
 struct DwConvArgs {

@@ -255,13 +255,13 @@ int encoder_forward_chunk_batch(const Model* m, const float* xs, int T, int S, c
             count_launch();
             WB_CHECK_LAUNCH();
         }
-        RC(relpos_kprep(kcat, d, Ly.pos_proj, d_row_pos, Ly.pos_u, Ly.pos_v, keys, H, kp, d, kbias, st));
+        RC(relpos_kprep(kcat, d, Ly.pos_proj, d_row_pos, Ly.pos_u, Ly.pos_v, keys, H, kp, d, kbias, st, att_scale * 1.4426950408889634f));
         {
             AttnArgs A;
             A.q = qkv; A.ldq = 3 * d; A.q_rows = rows; A.q_col0 = 0;
             A.k = kp; A.ldk = d; A.k_rows = keys; A.k_col0 = 0;
             A.v = vcat; A.ldv = d; A.v_rows = keys; A.v_col0 = 0;
-            A.kbias = kbias; A.ld_kbias = H;
+            A.kbias = kbias; A.ld_kbias = H; A.kbias_scaled = 1;
             A.q_start = d_qstart; A.q_len = d_qlen; A.k_start = d_kstart; A.k_len = d_klen;
             A.batch = S; A.heads = H; A.max_q_len = chunk;
             A.chunk_size = 0; A.num_left_chunks = -1; A.scale = att_scale;   // att_mask is all-ones (encoder.py:243-247)
