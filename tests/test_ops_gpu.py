@@ -57,6 +57,32 @@ def test_gemm(M, N, K, epi):
         _close(out, ref, 2 ** -8, 2e-4)
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(47872, 2048, 256, 1), (5003, 2048, 256, 1), (2048, 512, 128, 1), (6000, 256, 192, 9),
+                                       (2100, 768, 64, 1)])
+def test_gemm_sixteen_epilogue_warps(M, N, K, epi):
+    """gemm_act16.cu (weight-stationary K <= 256, SiLU / GELU, sixteen epilogue warps alternating tiles, SWIZZLE_64B output
+    staging): the shapes gemm_bf16 routes to it (M >= 2048, N % 256 == 0), incl. ragged last row tiles, one tile per CTA
+    and several weight panels per CTA - against torch, and bit for bit against the eight-warp kernel (WB_GEMM_ACT16=0 is
+    read once per process, so the reference here is the same epilogue arithmetic through a narrower call: M < 2048 rows
+    at a time)."""
+    import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = _rb(torch.randn(M, K, generator=g)).to(_dev())
+    b = _rb(torch.randn(N, K, generator=g) / math.sqrt(K)).to(_dev())
+    bias = torch.randn(N, generator=g).to(_dev())
+    ref = a.float() @ b.float().T + bias
+    ref = torch.nn.functional.silu(ref) if epi == 1 else torch.nn.functional.gelu(ref)
+    out = ops.gemm(a, b, bias, epi, 1.0)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.bfloat16 and out.shape == (M, N)
+    _close(out, ref, 2 ** -8, 2e-4)
+    # the same rows through the eight-warp kernel (slices below the routing threshold)
+    for r0 in range(0, M, 1920):
+        r1 = min(M, r0 + 1920)
+        part = ops.gemm(a[r0:r1].contiguous(), b, bias, epi, 1.0)
+        assert torch.equal(part, out[r0:r1]), (r0, float((part.float() - out[r0:r1].float()).abs().max()))
+
+
 @pytest.mark.parametrize("M,K", [(300, 256), (47872, 256), (257, 2048), (5000, 2048), (67, 256), (128, 2048)])
 def test_gemm_resid_layernorm(M, K):
     """Residual-update GEMM with the next module's LayerNorm fused into its epilogue (N = d = 256): x in place and

@@ -517,6 +517,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_mn_ma
 // box_cols (box_cols*2 bytes must be 128 for SWIZZLE_128B).
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
+int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                           uint32_t box_rows);
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[3], const uint64_t strides_bytes[2],
                       const uint32_t box[3], const uint32_t estr[3]);
 // same for fp32 (elem_bytes = 4, box_cols = 32) or bf16 (elem_bytes = 2, box_cols = 64): 128-byte inner box

@@ -1034,6 +1034,11 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
     const int num_kb = ceil_div(K, BK);
     p.res_ring = (bn == 256) ? (pair ? GemmCfg<256, 2>::res_ring(num_kb) : GemmCfg<256>::res_ring(num_kb))
                              : GemmCfg<128>::res_ring(num_kb);
+    // activation-heavy weight-stationary shapes (FFN w_1 + SiLU): the sixteen-epilogue-warp kernel of gemm_act16.cu
+    if (bn == 256 && !pair && num_kb <= 4 && !split3 && alpha == 1.0f && (epi == EPI_BF16_SILU || epi == EPI_BF16_GELU)) {
+        const int r16 = gemm_act16_try(A, lda, tb, M, N, K, bias, epi, out, ldc, g_sm_reserve, stream);
+        if (r16 != 1) return r16;
+    }
     if (bn == 256) {
         const bool res = num_kb <= 4;   // K <= 256: weight-stationary
         switch (epi) {

@@ -53,6 +53,11 @@ int gemm_resid_ln(const void* A, long long lda, const WeightMaps* tmap_b_opt, co
                   const float* gamma, const float* beta, float eps, void* ln_out_bf16, long long ld_ln,
                   cudaStream_t stream);
 
+// gemm_act16.cu: weight-stationary K <= 256 GEMM + activation with sixteen epilogue warps; returns 1 when the shape is not
+// handled (the caller then uses gemm_tcgen05_kernel)
+int gemm_act16_try(const void* A, long long lda, const CUtensorMap* tmap_b_one, int M, int N, int K, const float* bias, int epi,
+                   void* out, long long ldc, int sm_reserve, cudaStream_t stream);
+
 int gemm_lse_partials(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream);
 

@@ -156,6 +156,24 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[3]
     return WB_OK;
 }
 
+// bf16 [rows][cols] with 64-byte boxes (32 columns) and SWIZZLE_64B: the 2 KB per-warp output staging of gemm_act16.cu
+int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                           uint32_t box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    WB_REQUIRE(fn != nullptr, WB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+    WB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_elems * 2) % 16 == 0 && box_rows <= 256, WB_ERR_BAD_ARG,
+               "tmap sw64: alignment");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WB_REQUIRE(r == CUDA_SUCCESS, WB_ERR_CUDA, "cuTensorMapEncodeTiled(sw64) failed (%d)", (int)r);
+    return WB_OK;
+}
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols) {
     return make_tmap_2d(out, base, 2, rows, cols, ld_elems, box_rows, box_cols);
