@@ -209,26 +209,17 @@ dec_cross_attn_part_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
 #pragma unroll
     for (int n = 0; n < CA_NP; ++n) o[n] = make_float2(0.f, 0.f);
     const __nv_bfloat16* vbase = kbase + d + 2 * lane;
-    // eight V rows in flight per warp (a dependent one-row-at-a-time loop is a chain of DRAM latencies)
-    constexpr int VB = 8;
-    for (int j0 = warp * VB; j0 < nk; j0 += (CA_THREADS / 32) * VB) {
-        uint32_t vv[VB];
+    for (int j = warp; j < nk; j += CA_THREADS / 32) {
+        const uint32_t vv = __ldg(reinterpret_cast<const uint32_t*>(vbase + (long long)j * 2 * d));
+        const float v0 = bf16_lo(vv), v1 = bf16_hi(vv);
+        const float4* pr = reinterpret_cast<const float4*>(sc + (size_t)j * CA_NP);
 #pragma unroll
-        for (int u = 0; u < VB; ++u)
-            vv[u] = (j0 + u < nk) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + (long long)(j0 + u) * 2 * d)) : 0u;
-#pragma unroll
-        for (int u = 0; u < VB; ++u) {
-            if (j0 + u >= nk) break;   // warp-uniform
-            const float v0 = bf16_lo(vv[u]), v1 = bf16_hi(vv[u]);
-            const float4* pr = reinterpret_cast<const float4*>(sc + (size_t)(j0 + u) * CA_NP);
-#pragma unroll
-            for (int g4 = 0; g4 < CA_NP / 4; ++g4) {
-                const float4 pv = pr[g4];
-                o[4 * g4].x = fmaf(pv.x, v0, o[4 * g4].x); o[4 * g4].y = fmaf(pv.x, v1, o[4 * g4].y);
-                o[4 * g4 + 1].x = fmaf(pv.y, v0, o[4 * g4 + 1].x); o[4 * g4 + 1].y = fmaf(pv.y, v1, o[4 * g4 + 1].y);
-                o[4 * g4 + 2].x = fmaf(pv.z, v0, o[4 * g4 + 2].x); o[4 * g4 + 2].y = fmaf(pv.z, v1, o[4 * g4 + 2].y);
-                o[4 * g4 + 3].x = fmaf(pv.w, v0, o[4 * g4 + 3].x); o[4 * g4 + 3].y = fmaf(pv.w, v1, o[4 * g4 + 3].y);
-            }
+        for (int g4 = 0; g4 < CA_NP / 4; ++g4) {
+            const float4 pv = pr[g4];
+            o[4 * g4].x = fmaf(pv.x, v0, o[4 * g4].x); o[4 * g4].y = fmaf(pv.x, v1, o[4 * g4].y);
+            o[4 * g4 + 1].x = fmaf(pv.y, v0, o[4 * g4 + 1].x); o[4 * g4 + 1].y = fmaf(pv.y, v1, o[4 * g4 + 1].y);
+            o[4 * g4 + 2].x = fmaf(pv.z, v0, o[4 * g4 + 2].x); o[4 * g4 + 2].y = fmaf(pv.z, v1, o[4 * g4 + 2].y);
+            o[4 * g4 + 3].x = fmaf(pv.w, v0, o[4 * g4 + 3].x); o[4 * g4 + 3].y = fmaf(pv.w, v1, o[4 * g4 + 3].y);
         }
     }
 #pragma unroll
