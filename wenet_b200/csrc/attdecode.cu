@@ -119,145 +119,6 @@ dec_self_attn_step_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
     reinterpret_cast<uint32_t*>(ctx + (long long)r * d + h * 64)[lane] = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
-
-// ---- cross attention of the `beam` new positions of an utterance against its encoder memory, split over the keys ------
-// The varlen tcgen05 kernel serves this shape badly: a 128-query tile holds 10 rows, one CTA per (utterance, head) walks
-// 24 key tiles serially, and 32 x 20 = 640 such CTAs are two waves of its 4-CTA/SM occupancy (147 us per layer and step
-// at the Whisper-large geometry for 245 MB of K/V = 1.7 TB/s).  Here the key range of every (utterance, head) is cut into
-// `splits` pieces (flash-decoding): a CTA streams its keys once (lane = key for the scores against the N queries held in
-// shared memory, lane = channel pair for P V with coalesced 128-byte V rows), keeps an exact fp32 softmax of its piece
-// and leaves (max, sum, unnormalised output); a second kernel merges the pieces.  CUDA cores: 3.8 MFLOP per (utterance,
-// head) is nothing, the kernel is a K/V streaming pass.
-constexpr int CA_THREADS = 128;
-constexpr int CA_NP = 12;   // queries padded to a multiple of 4 (float4 rows of the probability tile); beam <= 12 here
-
-__global__ void __launch_bounds__(CA_THREADS)
-dec_cross_attn_part_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ memkv,
-                           const int* __restrict__ enc_start, const int* __restrict__ enc_len, int N, int H, int d, int per,
-                           float scale, float* __restrict__ part_o, float2* __restrict__ part_ml) {
-    extern __shared__ __align__(16) float ca_smem[];
-    const int s = blockIdx.x, h = blockIdx.y, b = blockIdx.z, S = gridDim.x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float* qs = ca_smem;                       // [CA_NP][64], pre-scaled, rows >= N zero
-    float* sc = ca_smem + CA_NP * 64;          // [per][CA_NP] scores, then probabilities
-    float* red = sc + (size_t)per * CA_NP;     // [4 warps][CA_NP][64] partial outputs
-    const int T = enc_len[b];
-    const int k0 = min(T, s * per), k1 = min(T, k0 + per);
-    const int nk = k1 - k0;
-    const long long pbase = (((long long)b * H + h) * S + s) * N;
-    if (nk <= 0) {   // empty piece: neutral element of the merge
-        for (int i = tid; i < N * 64; i += CA_THREADS) part_o[pbase * 64 + i] = 0.f;
-        if (tid < N) part_ml[pbase + tid] = make_float2(-INFINITY, 0.f);
-        return;
-    }
-    for (int i = tid; i < CA_NP * 64; i += CA_THREADS) {
-        const int n = i >> 6, c = i & 63;
-        qs[i] = (n < N) ? __bfloat162float(q[(long long)(b * N + n) * d + h * 64 + c]) * scale : 0.f;
-    }
-    __syncthreads();
-    const __nv_bfloat16* kbase = memkv + (long long)(enc_start[b] + k0) * 2 * d + h * 64;
-    // scores: lane = key
-    for (int j = tid; j < nk; j += CA_THREADS) {
-        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)j * 2 * d);
-        float kf[64];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint4 u = __ldg(kp + i);
-            kf[8 * i] = bf16_lo(u.x); kf[8 * i + 1] = bf16_hi(u.x);
-            kf[8 * i + 2] = bf16_lo(u.y); kf[8 * i + 3] = bf16_hi(u.y);
-            kf[8 * i + 4] = bf16_lo(u.z); kf[8 * i + 5] = bf16_hi(u.z);
-            kf[8 * i + 6] = bf16_lo(u.w); kf[8 * i + 7] = bf16_hi(u.w);
-        }
-#pragma unroll 1
-        for (int n = 0; n < N; ++n) {
-            const float4* qr = reinterpret_cast<const float4*>(qs + n * 64);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float4 qv = qr[i];
-                a0 = fmaf(kf[4 * i], qv.x, a0);
-                a1 = fmaf(kf[4 * i + 1], qv.y, a1);
-                a2 = fmaf(kf[4 * i + 2], qv.z, a2);
-                a3 = fmaf(kf[4 * i + 3], qv.w, a3);
-            }
-            sc[(size_t)j * CA_NP + n] = (a0 + a1) + (a2 + a3);
-        }
-    }
-    __syncthreads();
-    // exact softmax of the piece: warp w owns queries w, w + 4, ...
-    for (int n = warp; n < N; n += CA_THREADS / 32) {
-        float mx = -INFINITY;
-        for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[(size_t)j * CA_NP + n]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < nk; j += 32) {
-            const float e = __expf(sc[(size_t)j * CA_NP + n] - mx);
-            sc[(size_t)j * CA_NP + n] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) part_ml[pbase + n] = make_float2(mx, sum);
-    }
-    // rows N .. CA_NP - 1 of the probability tile are read as part of the float4 rows below: zero them
-    for (int i = tid; i < nk * (CA_NP - N); i += CA_THREADS) {
-        const int j = i / (CA_NP - N), n = N + i - j * (CA_NP - N);
-        sc[(size_t)j * CA_NP + n] = 0.f;
-    }
-    __syncthreads();
-    // P V: lane = channel pair, the four warps take every fourth key
-    float2 o[CA_NP];
-#pragma unroll
-    for (int n = 0; n < CA_NP; ++n) o[n] = make_float2(0.f, 0.f);
-    const __nv_bfloat16* vbase = kbase + d + 2 * lane;
-    for (int j = warp; j < nk; j += CA_THREADS / 32) {
-        const uint32_t vv = __ldg(reinterpret_cast<const uint32_t*>(vbase + (long long)j * 2 * d));
-        const float v0 = bf16_lo(vv), v1 = bf16_hi(vv);
-        const float4* pr = reinterpret_cast<const float4*>(sc + (size_t)j * CA_NP);
-#pragma unroll
-        for (int g4 = 0; g4 < CA_NP / 4; ++g4) {
-            const float4 pv = pr[g4];
-            o[4 * g4].x = fmaf(pv.x, v0, o[4 * g4].x); o[4 * g4].y = fmaf(pv.x, v1, o[4 * g4].y);
-            o[4 * g4 + 1].x = fmaf(pv.y, v0, o[4 * g4 + 1].x); o[4 * g4 + 1].y = fmaf(pv.y, v1, o[4 * g4 + 1].y);
-            o[4 * g4 + 2].x = fmaf(pv.z, v0, o[4 * g4 + 2].x); o[4 * g4 + 2].y = fmaf(pv.z, v1, o[4 * g4 + 2].y);
-            o[4 * g4 + 3].x = fmaf(pv.w, v0, o[4 * g4 + 3].x); o[4 * g4 + 3].y = fmaf(pv.w, v1, o[4 * g4 + 3].y);
-        }
-    }
-#pragma unroll
-    for (int n = 0; n < CA_NP; ++n) reinterpret_cast<float2*>(red + ((size_t)warp * CA_NP + n) * 64)[lane] = o[n];
-    __syncthreads();
-    for (int i = tid; i < N * 64; i += CA_THREADS) {
-        const int n = i >> 6, c = i & 63;
-        float acc = 0.f;
-#pragma unroll
-        for (int w = 0; w < CA_THREADS / 32; ++w) acc += red[((size_t)w * CA_NP + n) * 64 + c];
-        part_o[pbase * 64 + i] = acc;
-    }
-}
-
-// merge the pieces of every (utterance, head, query): one warp each, lane = channel pair
-__global__ void dec_cross_attn_merge_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, int N, int H,
-                                            int S, int d, int total, __nv_bfloat16* __restrict__ ctx) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= total) return;   // total = B * H * N, ordered (b, h, n)
-    const int n = w % N, bh = w / N, h = bh % H, b = bh / H;
-    float M = -INFINITY;
-    for (int s = 0; s < S; ++s) M = fmaxf(M, part_ml[((long long)bh * S + s) * N + n].x);
-    float L = 0.f;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int s = 0; s < S; ++s) {
-        const long long pi = ((long long)bh * S + s) * N + n;
-        const float2 ml = part_ml[pi];
-        if (ml.y <= 0.f) continue;
-        const float wgt = __expf(ml.x - M);
-        L += ml.y * wgt;
-        const float2 ov = reinterpret_cast<const float2*>(part_o + pi * 64)[lane];
-        acc.x = fmaf(ov.x, wgt, acc.x);
-        acc.y = fmaf(ov.y, wgt, acc.y);
-    }
-    const float inv = (L > 0.f) ? 1.0f / L : 0.f;
-    reinterpret_cast<uint32_t*>(ctx + (long long)(b * N + n) * d + h * 64)[lane] = pack_bf16x2(acc.x * inv, acc.y * inv);
-}
-
 // ---- one beam-search step (search.py:309-355), one CTA per utterance -----------------------------------------------
 // topv / topi: [R][N] log-softmax top-N of every row (value desc).  Rows that have ended keep exactly one continuation
 // (<eos>, + 0); the N*N candidates of the utterance are ranked by (score desc, candidate index asc) and the best N
@@ -370,7 +231,7 @@ __global__ void final_select_kernel(const float* __restrict__ score, const int* 
 struct AbPlan {
     int R = 0, L = 0;
     size_t o_memkv = 0, o_kv = 0, o_x = 0, o_a = 0, o_qkv = 0, o_ctx = 0, o_q = 0, o_h = 0, o_logits = 0, o_topv = 0, o_topi = 0,
-           o_int = 0, o_part_o = 0, o_part_ml = 0, total = 0;
+           o_int = 0, total = 0;
     long long ldl = 0;
     size_t n_int = 0;
 };
@@ -397,9 +258,6 @@ void ab_layout(const Model* m, long long enc_rows, int batch, int beam, int max_
     // utt_ended [batch]; prefix [batch][L]
     P->n_int = 4 * R * max_len + 6 * R + 5 * (size_t)batch + (size_t)batch * max_len + 64;
     P->o_int = o; o += align_up(P->n_int * 4);
-    // split-key cross attention: per (utterance, head, piece, query) 64 fp32 outputs + (max, sum); at most 8 pieces
-    P->o_part_o = o; o += align_up(R * m->cfg.dec_heads * 8 * 64 * 4);
-    P->o_part_ml = o; o += align_up(R * m->cfg.dec_heads * 8 * 8);
     P->total = o + 256;
 }
 
@@ -524,14 +382,6 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
     WB_CHECK_LAUNCH();
 
     const float scale = 1.0f / sqrtf(64.0f);
-    // split-key cross attention geometry: pieces of <= 384 keys (a multiple of 32), at most 8 pieces
-    int max_enc_len = 0;
-    for (int b = 0; b < batch; ++b) max_enc_len = seq_len_host[b] > max_enc_len ? seq_len_host[b] : max_enc_len;
-    int ca_splits = ceil_div(max_enc_len > 0 ? max_enc_len : 1, 384);
-    ca_splits = ca_splits < 1 ? 1 : (ca_splits > 8 ? 8 : ca_splits);
-    const int ca_per = ceil_div(ceil_div(max_enc_len > 0 ? max_enc_len : 1, ca_splits), 32) * 32;
-    const size_t ca_smem = ((size_t)CA_NP * 64 + (size_t)ca_per * CA_NP + 4 * CA_NP * 64) * sizeof(float);
-    if (N <= CA_NP) WB_SET_MAX_DYN_SMEM(dec_cross_attn_part_kernel, ca_smem);
     int cur = 0;   // buffer holding the current hyps / ancestry / scores / flags
     int pos = 0;
     std::vector<int> ended_host(batch, 0);
@@ -557,24 +407,7 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
             }
             RC(resid_then_norm(ctx, d, Ly.sa_out, R, d, x, Ly.n2, c.dec_ln_eps, a, st));
             RC(gemm_bf16(a, d, &Ly.ca_q.tmap, Ly.ca_q.w, R, d, d, Ly.ca_q.b, EPI_BF16, 1.0f, q, d, 0, st));
-            if (N <= CA_NP) {
-                // split-key streaming kernel + merge (see dec_cross_attn_part_kernel)
-                const __nv_bfloat16* memkv = reinterpret_cast<const __nv_bfloat16*>(ws + P.o_memkv + (size_t)li * enc_rows * 2 * d * 2);
-                float* part_o = reinterpret_cast<float*>(ws + P.o_part_o);
-                float2* part_ml = reinterpret_cast<float2*>(ws + P.o_part_ml);
-                ProfScope _ps(PT_ATTENTION, st, (double)enc_rows * 2 * d * 2);
-                dim3 grid(ca_splits, H, batch);
-                dec_cross_attn_part_kernel<<<grid, CA_THREADS, ca_smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(q), memkv,
-                                                                              enc_start, enc_len, N, H, d, ca_per, scale, part_o,
-                                                                              part_ml);
-                count_launch();
-                WB_CHECK_LAUNCH();
-                const int total = batch * H * N;
-                dec_cross_attn_merge_kernel<<<ceil_div(total * 32, 256), 256, 0, st>>>(part_o, part_ml, N, H, ca_splits, d, total,
-                                                                                      ctx);
-                count_launch();
-                WB_CHECK_LAUNCH();
-            } else {
+            {
                 const void* memkv = ws + P.o_memkv + (size_t)li * enc_rows * 2 * d * 2;
                 AttnArgs A;
                 A.q = q; A.ldq = d; A.q_rows = R; A.q_col0 = 0;
