@@ -86,6 +86,7 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.stop_flag = False
         self.sm, self.reasons, self.sm_max = [], set(), None
+        self.power_w, self.power_limit_w = [], None
 
     def run(self):
         try:
@@ -97,6 +98,12 @@ class ClockSampler(threading.Thread):
                      0x80: "hw_power_brake_slowdown"}
             while not self.stop_flag:
                 self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    self.power_w.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    if self.power_limit_w is None:
+                        self.power_limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+                except Exception:
+                    pass
                 try:
                     r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
@@ -119,8 +126,12 @@ class ClockSampler(threading.Thread):
                 time.sleep(0.2)
 
     def summary(self):
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.power_w:    # board power next to the clocks: with several batches in flight the step runs AT the power limit
+            out["power_w"] = float(np.median(self.power_w))
+            out["power_limit_w"] = self.power_limit_w
+        return out
 
 
 def workload(name):
@@ -562,6 +573,13 @@ def main():
                             "launches": g["launches"], "avg_launch_us": 1e3 * g["ms"] / max(g["launches"], 1),
                             "share_of_step": g["ms"] / prof_ms,
                             "fused_layernorm_launches": prof.get("gemm_tcgen05+layernorm", {}).get("launches", 0),
+                            # the same fraction per profile tag: launches with a plain epilogue / launches whose epilogue also
+                            # normalises the rows (same FLOPs counted, extra HBM-bound epilogue work)
+                            "frac_plain_epilogue": (prof["gemm_tcgen05"]["work"] / (prof["gemm_tcgen05"]["ms"] * 1e-3) / 1e12
+                                                    / peaks["tf_sust"]) if prof["gemm_tcgen05"]["ms"] > 0 else None,
+                            "frac_layernorm_epilogue": (prof["gemm_tcgen05+layernorm"]["work"]
+                                                        / (prof["gemm_tcgen05+layernorm"]["ms"] * 1e-3) / 1e12 / peaks["tf_sust"])
+                            if prof.get("gemm_tcgen05+layernorm", {}).get("ms", 0) > 0 else None,
                             "measured": "CUDA events around every launch of the family, %d extra steps with one batch in "
                                         "flight right after the timed region (%.2f ms/step in that pass)"
                                         % (prof_steps, prof_ms / prof_steps)}
