@@ -77,6 +77,32 @@ def test_whisper_encoder_golden(parity):
         assert float(out[b, n:].abs().max()) == 0.0 if n < out.shape[1] else True
 
 
+def test_whisper_encoder_precise_mode():
+    """precise mode (bf16x3 GEMMs, fp32 attention): Whisper encoder_out within 1e-3 of the fp32 reference goldens, both length
+    parities; attention decoding on top of it returns the reference's token ids."""
+    from wenet_b200.whisper import B200Whisper
+    g = load_golden("whisper_tiny")
+    cfg = synth.recipe("whisper_tiny")
+    sd = synth.synth_state_dict(cfg, seed=SEED)
+    model = B200Whisper(cfg, sd, precise=True)
+    for key_o, key_l, cut in (("enc_out", "enc_lens", 0), ("enc_out_odd", "enc_lens_odd", 1)):
+        xs = torch.from_numpy(g["feats"])
+        xs = xs[:, :xs.shape[1] - cut]
+        lens = torch.minimum(torch.from_numpy(g["feat_lens"]).long(), torch.tensor(xs.shape[1]))
+        out, _ = model.encoder(xs.cuda(), lens.cuda())
+        ref = torch.from_numpy(g[key_o])
+        for b in range(xs.shape[0]):
+            n = int(g[key_l][b])
+            mx, mean = err(out[b, :n].cpu(), ref[b, :n])
+            print("whisper enc precise (%s) utt %d: max %.2e mean %.2e" % (key_o, b, mx, mean))
+            assert mx <= 1e-3
+    xs = torch.from_numpy(g["feats"]).cuda()
+    lens = torch.from_numpy(g["feat_lens"]).cuda()
+    infos = {"tasks": [str(t) for t in g["tasks"]], "langs": [str(t) for t in g["langs"]]}
+    res = model.decode(["attention"], xs, lens, beam_size=int(g["beam"]), infos=infos)["attention"]
+    assert [list(r.tokens) for r in res] == [g["att%d" % b].tolist() for b in range(len(res))]
+
+
 def test_whisper_attention_decode_golden():
     g = load_golden("whisper_tiny")
     cfg, sd, model = _whisper_model()

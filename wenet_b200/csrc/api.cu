@@ -100,11 +100,12 @@ static int finalize_whisper_encoder(Model* m) {
     const wb_model_config& c = m->cfg;
     const int d = c.d_model, ff = c.ffn_dim;
     WB_REQUIRE(c.input_dim % 8 == 0 && c.input_dim > 0, WB_ERR_UNSUPPORTED, "whisper: input_dim %d must be a multiple of 8", c.input_dim);
-    WB_REQUIRE(!c.precise && !c.has_cmvn, WB_ERR_UNSUPPORTED, "whisper: precise mode / global CMVN are not part of this path");
+    WB_REQUIRE(!c.has_cmvn, WB_ERR_UNSUPPORTED, "whisper: global CMVN is not part of this path");
+    const int p3 = c.precise ? 3 : 1;   // precise: encoder / CTC weights arrive packed [hi | hi | lo] along K
     WhisperEnc& E = m->wenc;
     const void* p;
-    RC(get_linear(m, "wenc.conv1", d, 3 * c.input_dim, true, &E.conv1));
-    RC(get_linear(m, "wenc.conv2", d, 3 * d, true, &E.conv2));
+    RC(get_linear(m, "wenc.conv1", d, 3 * c.input_dim * p3, true, &E.conv1));
+    RC(get_linear(m, "wenc.conv2", d, 3 * d * p3, true, &E.conv2));
     RC(model_get(m, "wenc.pe", WB_F32, (int64_t)c.max_pos * d, &p));
     E.pe = (const float*)p;
     m->pe = E.pe;
@@ -114,10 +115,10 @@ static int finalize_whisper_encoder(Model* m) {
         TrLayer& L = E.layers[i];
         RC(get_norm(m, b + ".norm1", d, &L.n1));
         RC(get_norm(m, b + ".norm2", d, &L.n2));
-        RC(get_linear(m, b + ".att.qkv", 3 * d, d, true, &L.qkv));
-        RC(get_linear(m, b + ".att.out", d, d, true, &L.out));
-        RC(get_linear(m, b + ".ff.w1", ff, d, true, &L.ff1));
-        RC(get_linear(m, b + ".ff.w2", d, ff, true, &L.ff2));
+        RC(get_linear(m, b + ".att.qkv", 3 * d, d * p3, true, &L.qkv));
+        RC(get_linear(m, b + ".att.out", d, d * p3, true, &L.out));
+        RC(get_linear(m, b + ".ff.w1", ff, d * p3, true, &L.ff1));
+        RC(get_linear(m, b + ".ff.w2", d, ff * p3, true, &L.ff2));
     }
     RC(get_norm(m, "after_norm", d, &E.after));
     m->after = E.after;
@@ -136,7 +137,8 @@ static int model_finalize(Model* m, cudaStream_t stream) {
             WB_REQUIRE(c.dec_heads * 64 == c.d_model && c.dec_ffn_dim % 64 == 0, WB_ERR_UNSUPPORTED,
                        "unsupported decoder geometry (heads=%d)", c.dec_heads);
         RC(finalize_whisper_encoder(m));
-        if (c.vocab > 0 && m->tensors.count("ctc.w")) RC(get_linear(m, "ctc", c.vocab, c.d_model, true, &m->ctc));
+        if (c.vocab > 0 && m->tensors.count("ctc.w"))
+            RC(get_linear(m, "ctc", c.vocab, c.d_model * (c.precise ? 3 : 1), true, &m->ctc));
         if (m->cfg.dec_ln_eps <= 0.f) m->cfg.dec_ln_eps = m->cfg.ln_eps;
         if (c.dec_layers > 0) RC(finalize_decoder(m, "dec.left", c.dec_layers, &m->left));
         WB_CHECK_CUDA(cudaStreamSynchronize(stream));

@@ -116,19 +116,28 @@ __global__ void logmel_finish_kernel(float* __restrict__ out, long long out_stri
 // Conv1dSubsampling2 as im2col + GEMM
 // ------------------------------------------------------------------------------------------------------------------
 // conv1 rows of utterance b: t in [0, rows1_b); row = [x[t-1] | x[t] | x[t+1]] (idim each), x = 0 outside [0, len_b)
+// split3 (precise mode): every tap block of idim values is written as [hi | lo | hi] (row = 9 idim wide), matching weights
+// packed [hi | hi | lo] per tap block (bf16x3, see gemm.cu)
 __global__ void w_im2col1_kernel(const float* __restrict__ feats, long long stride_b, int idim, const int* __restrict__ len,
-                                 const int* __restrict__ rows1, const long long* __restrict__ off1, int batch,
+                                 const int* __restrict__ rows1, const long long* __restrict__ off1, int batch, int split3,
                                  __nv_bfloat16* __restrict__ a1) {
     const int b = blockIdx.y;
     const int n = len[b], nr = rows1[b];
     const int per_row = 3 * idim;
+    const int p3 = split3 ? 3 : 1;
     const long long total = (long long)nr * per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i / per_row), j = (int)(i - (long long)t * per_row);
         const int tap = j / idim, cch = j - tap * idim;
         const int ts = t + tap - 1;
         const float v = (ts >= 0 && ts < n) ? feats[(long long)b * stride_b + (long long)ts * idim + cch] : 0.f;
-        a1[(off1[b] + t) * per_row + j] = __float2bfloat16_rn(v);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        __nv_bfloat16* row = a1 + (off1[b] + t) * (long long)per_row * p3 + (long long)tap * idim * p3;
+        row[cch] = hi;
+        if (split3) {
+            row[idim + cch] = __float2bfloat16_rn(v - __bfloat162float(hi));
+            row[2 * idim + cch] = hi;
+        }
     }
 }
 // conv2 rows: t' in [0, T'_b); row = [c1[2t'-1] | c1[2t'] | c1[2t'+1]] (d each), c1 = 0 outside [0, rows1_b).  16-byte copies.
@@ -149,12 +158,19 @@ __global__ void w_im2col2_kernel(const uint4* __restrict__ c1, const int* __rest
 }
 // x[m] = float(g[m]) + pe[t'] (xscale 1)
 __global__ void w_add_pe_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ pe, const int* __restrict__ seq_start,
-                                const int* __restrict__ seq_len, int d, float* __restrict__ x) {
+                                const int* __restrict__ seq_len, int d, int split3, float* __restrict__ x) {
     const int b = blockIdx.y;
     const long long total = (long long)seq_len[b] * d;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long m = (long long)seq_start[b] * d + i;
-        x[m] = __bfloat162float(g[m]) + pe[i];
+        float v;
+        if (split3) {   // rows are [hi | lo | hi]
+            const long long r = m / d, c = m - r * d;
+            v = __bfloat162float(g[r * 3 * d + c]) + __bfloat162float(g[r * 3 * d + d + c]);
+        } else {
+            v = __bfloat162float(g[m]);
+        }
+        x[m] = v + pe[i];
     }
 }
 
@@ -176,7 +192,9 @@ void we_rows(const int32_t* lens, int batch, int time_pad, std::vector<int>* row
 }
 
 void we_layout(const Model* m, const std::vector<int>& rows1, const std::vector<int>& tp, WePlan* P) {
-    const int d = m->cfg.d_model, ff = m->cfg.ffn_dim, idim = m->cfg.input_dim;
+    const size_t p3 = m->cfg.precise ? 3 : 1;   // precise: bf16 activations are [hi | lo | hi], q / k / v fp32
+    const size_t d = (size_t)m->cfg.d_model * p3, ff = (size_t)m->cfg.ffn_dim * p3, idim = (size_t)m->cfg.input_dim * p3;
+    const size_t d1 = m->cfg.d_model;
     const int batch = (int)rows1.size();
     P->rows1 = 0;
     P->M = 0;
@@ -192,9 +210,9 @@ void we_layout(const Model* m, const std::vector<int>& rows1, const std::vector<
     P->o_c1 = o; o += align_up((size_t)P->rows1 * d * 2);
     P->o_a2 = o; o += align_up((size_t)P->M * 3 * d * 2);
     P->o_g = o; o += align_up((size_t)P->M * d * 2);
-    P->o_x = o; o += align_up((size_t)P->M * d * 4);
+    P->o_x = o; o += align_up((size_t)P->M * d1 * 4);
     P->o_a = o; o += align_up((size_t)P->M * d * 2);
-    P->o_qkv = o; o += align_up((size_t)P->M * 3 * d * 2);
+    P->o_qkv = o; o += align_up((size_t)P->M * 3 * d1 * (m->cfg.precise ? 4 : 2));
     P->o_ctx = o; o += align_up((size_t)P->M * d * 2);
     P->o_h = o; o += align_up((size_t)P->M * ff * 2);
     P->total = o + 256;
@@ -298,6 +316,10 @@ int whisper_encoder_forward(const Model* m, const float* feats, long long feats_
     WB_REQUIRE(c.arch == 1, WB_ERR_BAD_ARG, "whisper_encoder_forward: not a Whisper model handle");
     const WhisperEnc& E = m->wenc;
     const int d = c.d_model, ff = c.ffn_dim, idim = c.input_dim, H = c.heads;
+    // precise (parity) mode: bf16x3 GEMMs over [hi | lo | hi] activations, fp32 q / k / v and attention (precise.cu) - the
+    // same scheme as the Conformer path (include/wenet_b200.h, wb_model_config.precise)
+    const int sp = c.precise ? 1 : 0, p3 = sp ? 3 : 1;
+    const long long lda = (long long)d * p3, ldh = (long long)ff * p3;
     std::vector<int> r1, tp;
     we_rows(lens_host, batch, time_pad, &r1, &tp);
     for (int b = 0; b < batch; ++b)
@@ -347,24 +369,27 @@ int whisper_encoder_forward(const Model* m, const float* feats, long long feats_
     {
         ProfScope _ps(PT_IM2COL, st, (double)P.rows1 * 3 * idim * 6.0);
         dim3 grid(ceil_div(max_r1 * 3 * idim, 256 * 4), batch);
-        w_im2col1_kernel<<<grid, 256, 0, st>>>(feats, feats_stride_b, idim, d_len, d_rows1, d_off1, batch, a1);
+        w_im2col1_kernel<<<grid, 256, 0, st>>>(feats, feats_stride_b, idim, d_len, d_rows1, d_off1, batch, sp, a1);
         count_launch();
         WB_CHECK_LAUNCH();
     }
-    RC(gemm_bf16(a1, 3 * idim, &E.conv1.tmap, E.conv1.w, (int)P.rows1, d, 3 * idim, E.conv1.b, EPI_BF16_GELU, 1.0f, c1, d, 0, st));
+    RC(gemm_bf16(a1, 3 * idim * p3, &E.conv1.tmap, E.conv1.w, (int)P.rows1, d, 3 * idim * p3, E.conv1.b, EPI_BF16_GELU, 1.0f, c1,
+                 lda, sp, st));
     {
         ProfScope _ps(PT_IM2COL, st, (double)P.M * 3 * d * 4.0);
-        dim3 grid(ceil_div(P.max_tp * 3 * (d / 8), 256 * 2), batch);
+        // (precise: a conv1 row is [hi | lo | hi] = 3 d wide, so a tap block of the im2col row is too)
+        const int d8 = d * p3 / 8;
+        dim3 grid(ceil_div(P.max_tp * 3 * d8, 256 * 2), batch);
         w_im2col2_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(c1), d_rows1, d_off1, seq_start_dev, seq_len_dev,
-                                               d / 8, reinterpret_cast<uint4*>(a2));
+                                               d8, reinterpret_cast<uint4*>(a2));
         count_launch();
         WB_CHECK_LAUNCH();
     }
-    RC(gemm_bf16(a2, 3 * d, &E.conv2.tmap, E.conv2.w, (int)P.M, d, 3 * d, E.conv2.b, EPI_BF16_GELU, 1.0f, g, d, 0, st));
+    RC(gemm_bf16(a2, 3 * lda, &E.conv2.tmap, E.conv2.w, (int)P.M, d, 3 * d * p3, E.conv2.b, EPI_BF16_GELU, 1.0f, g, lda, sp, st));
     {
         ProfScope _ps(PT_MISC, st, (double)P.M * d * 10.0);
         dim3 grid(ceil_div(P.max_tp * d, 256 * 4), batch);
-        w_add_pe_kernel<<<grid, 256, 0, st>>>(g, E.pe, seq_start_dev, seq_len_dev, d, x);
+        w_add_pe_kernel<<<grid, 256, 0, st>>>(g, E.pe, seq_start_dev, seq_len_dev, d, sp, x);
         count_launch();
         WB_CHECK_LAUNCH();
     }
@@ -372,7 +397,19 @@ int whisper_encoder_forward(const Model* m, const float* feats, long long feats_
     const int M = (int)P.M;
     for (size_t li = 0; li < E.layers.size(); ++li) {
         const TrLayer& L = E.layers[li];
-        RC(layernorm_rows(x, d, M, d, L.n1.g, L.n1.b, c.ln_eps, a, d, 0, nullptr, 0, st));
+        RC(layernorm_rows(x, d, M, d, L.n1.g, L.n1.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        if (sp) {
+            float* qf = reinterpret_cast<float*>(qkv);
+            RC(gemm_bf16(a, lda, &L.qkv.tmap, L.qkv.w, M, 3 * d, 3 * d, L.qkv.b, EPI_F32, 1.0f, qf, 3 * d, 0, st));
+            AttnF32Args A;
+            A.q = qf; A.ldq = 3 * d; A.k = qf + d; A.ldk = 3 * d; A.v = qf + 2 * d; A.ldv = 3 * d;
+            A.pos_proj = nullptr; A.row_pos = nullptr; A.pos_u = nullptr; A.pos_v = nullptr;
+            A.q_start = seq_start_dev; A.q_len = seq_len_dev; A.k_start = seq_start_dev; A.k_len = seq_len_dev;
+            A.batch = batch; A.heads = H; A.max_q_len = P.max_tp;
+            A.chunk_size = 0; A.num_left_chunks = -1; A.scale = scale;
+            A.out = ctx; A.ldo = lda; A.split3_out = 1;
+            RC(attention_f32(A, st));
+        } else {
         RC(gemm_bf16(a, d, &L.qkv.tmap, L.qkv.w, M, 3 * d, d, L.qkv.b, EPI_BF16, 1.0f, qkv, 3 * d, 0, st));
         {
             AttnArgs A;
@@ -386,12 +423,13 @@ int whisper_encoder_forward(const Model* m, const float* feats, long long feats_
             A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
             RC(attention_forward(A, st));
         }
-        RC(gemm_bf16(ctx, d, &L.out.tmap, L.out.w, M, d, d, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
-        RC(layernorm_rows(x, d, M, d, L.n2.g, L.n2.b, c.ln_eps, a, d, 0, nullptr, 0, st));
-        RC(gemm_bf16(a, d, &L.ff1.tmap, L.ff1.w, M, ff, d, L.ff1.b, EPI_BF16_GELU, 1.0f, h, ff, 0, st));
-        RC(gemm_bf16(h, ff, &L.ff2.tmap, L.ff2.w, M, d, ff, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        }
+        RC(gemm_bf16(ctx, lda, &L.out.tmap, L.out.w, M, d, d * p3, L.out.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
+        RC(layernorm_rows(x, d, M, d, L.n2.g, L.n2.b, c.ln_eps, a, lda, sp, nullptr, 0, st));
+        RC(gemm_bf16(a, lda, &L.ff1.tmap, L.ff1.w, M, ff, d * p3, L.ff1.b, EPI_BF16_GELU, 1.0f, h, ldh, sp, st));
+        RC(gemm_bf16(h, ldh, &L.ff2.tmap, L.ff2.w, M, d, ff * p3, L.ff2.b, EPI_RESID_F32, 1.0f, x, d, 0, st));
     }
-    RC(layernorm_rows(x, d, M, d, E.after.g, E.after.b, c.ln_eps, enc_out_bf16, d, 0, enc_out, d, st));
+    RC(layernorm_rows(x, d, M, d, E.after.g, E.after.b, c.ln_eps, enc_out_bf16, lda, sp, enc_out, d, st));
     return WB_OK;
 }
 

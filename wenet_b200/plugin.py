@@ -336,7 +336,9 @@ def _make_classes():
             ver = _version(self)
             if core is None or self.__dict__.get("_b200_ver") != ver or core.device != dev:
                 sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
-                core = B200Whisper(configs_from_reference_whisper(self), sd, device=dev, lang_table=REF_WHISPER_LANGS)
+                precise = self.__dict__.get("b200_precise", os.environ.get("WENET_B200_PRECISE", "0") == "1")
+                core = B200Whisper(configs_from_reference_whisper(self), sd, device=dev, lang_table=REF_WHISPER_LANGS,
+                                   precise=bool(precise))
                 self.__dict__["_b200_core"], self.__dict__["_b200_ver"] = core, ver
             return core
 

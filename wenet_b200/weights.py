@@ -197,7 +197,7 @@ def whisper_sinusoids(max_len: int, d: int) -> torch.Tensor:
     return torch.cat([torch.sin(st), torch.cos(st)], dim=1)
 
 
-def _pack_whisper(spec: "ModelSpec", sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+def _pack_whisper(spec: "ModelSpec", sd: Dict[str, torch.Tensor], precise: bool = False) -> Dict[str, torch.Tensor]:
     """Whisper (wenet/models/whisper/whisper.py; key names of TransformerEncoder / TransformerDecoder):
       * Conv1d(k=3) weights (out, in, 3) -> [out][(tap, in)] for the im2col GEMMs of whisper.cu
       * q/k/v fused; key_bias=False (attention.py:74-77) -> a zero bias slice
@@ -212,31 +212,40 @@ def _pack_whisper(spec: "ModelSpec", sd: Dict[str, torch.Tensor]) -> Dict[str, t
     def bf(t):
         return t.detach().float().to(torch.bfloat16).contiguous().cpu()
 
-    def lin(dst, src, n_out=None):
+    def ebf(t, block=None):
+        """encoder-side GEMM weight [N, K]: bf16, or (precise) [hi | hi | lo] per `block` columns of K (bf16x3)"""
+        t = t.detach().float()
+        if not precise:
+            return bf(t)
+        N, K = t.shape
+        block = K if block is None else block
+        return split3_weight(t.reshape(N * (K // block), block)).reshape(N, 3 * K).contiguous().cpu()
+
+    def lin(dst, src, enc=False):
         w = sd[src + ".weight"]
-        out[dst + ".w"] = bf(w)
+        out[dst + ".w"] = ebf(w) if enc else bf(w)
         b = sd.get(src + ".bias")
-        out[dst + ".b"] = f32(b) if b is not None else torch.zeros(w.shape[0] if n_out is None else n_out)
+        out[dst + ".b"] = f32(b) if b is not None else torch.zeros(w.shape[0])
 
     def norm(dst, src):
         out[dst + ".g"] = f32(sd[src + ".weight"])
         out[dst + ".b"] = f32(sd[src + ".bias"])
 
-    def qkv(dst, a):
+    def qkv(dst, a, enc=False):
         ws, bs = [], []
         for n in ("linear_q", "linear_k", "linear_v"):
             w = sd[a + "." + n + ".weight"]
             b = sd.get(a + "." + n + ".bias")
             ws.append(w)
             bs.append(b.float() if b is not None else torch.zeros(w.shape[0]))
-        out[dst + ".w"] = bf(torch.cat(ws, 0))
+        out[dst + ".w"] = ebf(torch.cat(ws, 0)) if enc else bf(torch.cat(ws, 0))
         out[dst + ".b"] = f32(torch.cat(bs, 0))
 
     w1 = sd["encoder.embed.conv.0.weight"]            # (d, idim, 3)
-    out["wenc.conv1.w"] = bf(w1.permute(0, 2, 1).reshape(d, 3 * spec.input_dim))
+    out["wenc.conv1.w"] = ebf(w1.permute(0, 2, 1).reshape(d, 3 * spec.input_dim), block=spec.input_dim)
     out["wenc.conv1.b"] = f32(sd["encoder.embed.conv.0.bias"])
     w2 = sd["encoder.embed.conv.2.weight"]            # (d, d, 3)
-    out["wenc.conv2.w"] = bf(w2.permute(0, 2, 1).reshape(d, 3 * d))
+    out["wenc.conv2.w"] = ebf(w2.permute(0, 2, 1).reshape(d, 3 * d), block=d)
     out["wenc.conv2.b"] = f32(sd["encoder.embed.conv.2.bias"])
     pe = sd.get("encoder.embed.pos_enc.pe")
     pe = whisper_sinusoids(spec.max_pos, d) if pe is None else pe.reshape(-1, d)
@@ -246,13 +255,13 @@ def _pack_whisper(spec: "ModelSpec", sd: Dict[str, torch.Tensor]) -> Dict[str, t
         s_, t = "encoder.encoders.%d" % i, "wenc.%d" % i
         norm(t + ".norm1", s_ + ".norm1")
         norm(t + ".norm2", s_ + ".norm2")
-        qkv(t + ".att.qkv", s_ + ".self_attn")
-        lin(t + ".att.out", s_ + ".self_attn.linear_out")
-        lin(t + ".ff.w1", s_ + ".feed_forward.w_1")
-        lin(t + ".ff.w2", s_ + ".feed_forward.w_2")
+        qkv(t + ".att.qkv", s_ + ".self_attn", enc=True)
+        lin(t + ".att.out", s_ + ".self_attn.linear_out", enc=True)
+        lin(t + ".ff.w1", s_ + ".feed_forward.w_1", enc=True)
+        lin(t + ".ff.w2", s_ + ".feed_forward.w_2", enc=True)
     norm("after_norm", "encoder.after_norm")
     if spec.vocab > 0 and "ctc.ctc_lo.weight" in sd:
-        lin("ctc", "ctc.ctc_lo")
+        lin("ctc", "ctc.ctc_lo", enc=True)
     if any(k.startswith("decoder.") for k in sd):
         dst, src = "dec.left", "decoder"
         out[dst + ".emb"] = f32(sd[src + ".embed.0.weight"])
@@ -287,9 +296,7 @@ def pack_state_dict(spec: ModelSpec, sd: Dict[str, torch.Tensor], precise: bool 
     the d-wide channel groups the activations are split by (one block for a Linear, one per (kh, kw) tap for conv2,
     one per frequency bin for the embed Linear)."""
     if spec.arch == 1:
-        if precise:
-            raise NotImplementedError("the precise parity mode is not built for the Whisper path")
-        return _pack_whisper(spec, sd)
+        return _pack_whisper(spec, sd, precise=precise)
     d, F1 = spec.d_model, (spec.input_dim - 3) // 2 + 1
     F2 = (F1 - 3) // 2 + 1
     out: Dict[str, torch.Tensor] = {}
