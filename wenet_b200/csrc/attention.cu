@@ -390,336 +390,6 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
 
 // ----------------------------------------------------------------------------------------------
-// Double-buffered variant: the same single-pass online softmax, but the score accumulator S lives in TWO TMEM buffers, K in
-// two and V in three shared-memory stages, P in two.  S(i+2) is issued right behind P(i) V(i), i.e. a whole softmax ahead of
-// its use, and nobody waits for the P V MMAs at the end of a tile any more: the MMA round trip (9.5 % of the samples of the
-// single-buffered kernel, plus its share of the CTA barrier, profiles/r2_ncu_attn_v29.txt) leaves the per-tile critical
-// path.  Price: 256 TMEM columns and 92 KB of shared memory per CTA -> 2 CTAs / SM instead of 4 (but up to 255 registers).
-// Buffer use by tile ordinal i: S[i & 1], K stage i & 1, V stage i % 3, P[i & 1], bias slice i % 3; barrier parities follow
-// the use count of each buffer.
-struct AttnDbCfg {
-    static constexpr int kKV = 64 * 128;    // 8 KB
-    static constexpr int kP = 64 * 256;     // 16 KB
-    static constexpr int kSmem = 1024 + TILE_BYTES + 2 * kKV + 3 * kKV + 2 * kP + 3 * 64 * 4 + 256;
-};
-
-__global__ void __launch_bounds__(128, 2)
-attention_db_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, AttnDev P) {
-    constexpr int KN = 64;
-    using Cfg = AttnDbCfg;
-    const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
-    const int q_len = P.q_len[b];
-    if (qt * AT_M >= q_len) return;
-    const int q_start = P.q_start[b];
-    const int k_start = P.k_start[b];
-    const int k_len = P.k_len[b];
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + TILE_BYTES;               // [2]
-    uint8_t* sV = sK + 2 * Cfg::kKV;               // [3]
-    uint8_t* sP = sV + 3 * Cfg::kKV;               // [2]
-    float* sC = reinterpret_cast<float*>(sP + 2 * Cfg::kP);   // [3][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kP + 3 * 64 * 4);
-    uint64_t* bar_q = bars + 0;
-    uint64_t* bar_k = bars + 1;    // [2]
-    uint64_t* bar_v = bars + 3;    // [3]
-    uint64_t* bar_s = bars + 6;    // [2]
-    uint64_t* bar_pv = bars + 8;   // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int qi = qt * AT_M + tid;
-
-    if (tid == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_k);
-        tma_prefetch_desc(&tmap_v);
-        for (int i = 0; i < 10; ++i) mbar_init(bars + i, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) {
-        tmem_alloc(tmem_holder, 256);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_o = tmem_base + 2 * KN;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-
-    int row_lo = 0, row_hi = k_len;
-    int cta_lo = 0, cta_hi = k_len;
-    int full_lo = 0, full_hi = (k_len + KN - 1) / KN * KN;
-    if (P.chunk_size > 0) {
-        const int c = P.chunk_size;
-        row_hi = min((qi / c + 1) * c, k_len);
-        row_lo = (P.num_left_chunks < 0) ? 0 : max((qi / c - P.num_left_chunks) * c, 0);
-        const int q_first = qt * AT_M, q_last = min(qt * AT_M + AT_M - 1, q_len - 1), q_last_all = qt * AT_M + AT_M - 1;
-        cta_hi = min((q_last / c + 1) * c, k_len);
-        cta_lo = (P.num_left_chunks < 0) ? 0 : max((q_first / c - P.num_left_chunks) * c, 0);
-        full_hi = min((q_first / c + 1) * c, k_len);
-        if (full_hi == k_len) full_hi = (k_len + KN - 1) / KN * KN;
-        full_lo = (P.num_left_chunks < 0) ? 0 : max((q_last_all / c - P.num_left_chunks) * c, 0);
-    }
-    const int kt0 = cta_lo / KN;
-    const int kt1 = (cta_hi + KN - 1) / KN;
-    const int n_t = kt1 - kt0;
-
-    constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, KN, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, DK, 1);
-    auto issue_s = [&](int i) {   // S(i) = Q K'(i)^T into S[i & 1]; thread 0 only, K(i) landed
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + (i & 1) * Cfg::kKV);
-        const uint32_t ts = tmem_base + (uint32_t)((i & 1) * KN);
-#pragma unroll
-        for (int k = 0; k < DK / 16; ++k)
-            umma_f16(ts, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k != 0);
-        umma_commit(&bar_s[i & 1]);
-    };
-    auto load_k = [&](int i) {
-        mbar_expect_tx(&bar_k[i & 1], Cfg::kKV);
-        tma_load_2d(sK + (i & 1) * Cfg::kKV, &tmap_k, &bar_k[i & 1], P.k_col0 + h * DK, k_start + (kt0 + i) * KN);
-    };
-    auto load_v = [&](int i) {
-        mbar_expect_tx(&bar_v[i % 3], Cfg::kKV);
-        tma_load_2d(sV + (i % 3) * Cfg::kKV, &tmap_v, &bar_v[i % 3], P.v_col0 + h * DK, k_start + (kt0 + i) * KN);
-    };
-    // per-key bias slice of tile i -> sC[i % 3] (log2 domain, -1e30 past the sequence end)
-    const bool c_async = P.kbias_scaled != 0;
-    auto fetch_c_async = [&](int i) {
-        if (tid < KN) {
-            const int j = (kt0 + i) * KN + tid;
-            float* dst = sC + (i % 3) * KN + tid;
-            if (i < n_t && j < k_len) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)),
-                             "l"(P.kbias + (long long)(k_start + j) * P.ld_kbias + h)
-                             : "memory");
-            } else {
-                *dst = -1.0e30f;
-            }
-        }
-    };
-    auto fetch_c_raw = [&](int i, bool& valid) -> float {
-        const int j = (kt0 + i) * KN + tid;
-        valid = (tid < KN) && (i < n_t) && (j < k_len);
-        return (valid && P.kbias != nullptr) ? __ldg(P.kbias + (long long)(k_start + j) * P.ld_kbias + h) : 0.f;
-    };
-
-    if (n_t > 0) {
-        if (tid == 0) {
-            mbar_expect_tx(bar_q, TILE_BYTES);
-            tma_load_2d(sQ, &tmap_q, bar_q, P.q_col0 + h * DK, q_start + qt * AT_M);
-            load_k(0);
-            load_v(0);
-            if (n_t > 1) {
-                load_k(1);
-                load_v(1);
-            }
-        }
-        for (int i = 0; i < 2; ++i) {
-            if (c_async) {
-                fetch_c_async(i);
-            } else if (tid < KN) {
-                bool v0;
-                const float c0 = fetch_c_raw(i, v0);
-                sC[(i % 3) * KN + tid] = v0 ? c0 * P.scale_log2e : -1.0e30f;
-            }
-        }
-        if (c_async) asm volatile("cp.async.wait_all;" ::: "memory");
-        if (tid == 0) {
-            mbar_wait(bar_q, 0);
-            mbar_wait(&bar_k[0], 0);
-            tc_fence_after();
-            issue_s(0);
-            if (n_t > 1) {
-                mbar_wait(&bar_k[1], 0);
-                tc_fence_after();
-                issue_s(1);
-            }
-        }
-    }
-    __syncthreads();
-
-    float m_used = -INFINITY;
-    float l_acc = 0.f;
-    for (int i = 0; i < n_t; ++i) {
-        const int j0 = (kt0 + i) * KN;
-        const int b2 = i & 1;
-        const uint32_t par2 = (uint32_t)((i >> 1) & 1);
-        bool c_next_valid = false;
-        float c_next_raw = 0.f;
-        if (c_async) fetch_c_async(i + 2);
-        else c_next_raw = fetch_c_raw(i + 2, c_next_valid);
-        mbar_wait(&bar_s[b2], par2);
-        tc_fence_after();
-        if (tid == 0 && i + 2 < n_t) load_k(i + 2);   // K stage b2 is free: S(i) has consumed it
-        const float* cc = sC + (i % 3) * KN;
-        const bool tile_full = (j0 >= full_lo) && (j0 + KN <= full_hi);
-        const uint32_t tmem_s = tmem_base + (uint32_t)(b2 * KN);
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_sel, r0);
-        tmem_ld_32x32b_x32(tmem_s + lane_sel + 32u, r1);
-        tmem_ld_wait();
-        float mt0 = -INFINITY, mt1 = -INFINITY, mt2 = -INFINITY, mt3 = -INFINITY;
-        if (tile_full) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t* r = hh ? r1 : r0;
-#pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(cc + hh * 32 + e);
-                    const float s0 = fmaf(__uint_as_float(r[e]), P.scale_log2e, c4.x);
-                    const float s1 = fmaf(__uint_as_float(r[e + 1]), P.scale_log2e, c4.y);
-                    const float s2 = fmaf(__uint_as_float(r[e + 2]), P.scale_log2e, c4.z);
-                    const float s3 = fmaf(__uint_as_float(r[e + 3]), P.scale_log2e, c4.w);
-                    mt0 = fmaxf(mt0, s0);
-                    mt1 = fmaxf(mt1, s1);
-                    mt2 = fmaxf(mt2, s2);
-                    mt3 = fmaxf(mt3, s3);
-                    r[e] = __float_as_uint(s0);
-                    r[e + 1] = __float_as_uint(s1);
-                    r[e + 2] = __float_as_uint(s2);
-                    r[e + 3] = __float_as_uint(s3);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t* r = hh ? r1 : r0;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int key = j0 + hh * 32 + e;
-                    float sv = fmaf(__uint_as_float(r[e]), P.scale_log2e, cc[hh * 32 + e]);
-                    if (key < row_lo || key >= row_hi) sv = -INFINITY;
-                    mt0 = fmaxf(mt0, sv);
-                    r[e] = __float_as_uint(sv);
-                }
-            }
-        }
-        const float mt = fmaxf(fmaxf(mt0, mt1), fmaxf(mt2, mt3));
-        const bool raise = (mt > -1.0e29f) && (m_used == -INFINITY || mt > m_used + 8.0f);
-        float alpha = 1.0f;
-        if (raise) {
-            alpha = (m_used == -INFINITY) ? 1.0f : fast_exp2(m_used - mt);
-            l_acc *= alpha;
-            m_used = mt;
-        }
-        if (i != 0 && __any_sync(0xffffffffu, raise && alpha != 1.0f)) {
-            // O is rescaled by the threads that own its rows: every P V MMA issued so far must have retired
-            mbar_wait(&bar_pv[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t o[32];
-                tmem_ld_32x32b_x32(tmem_o + lane_sel + (uint32_t)(c * 32), o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                tmem_st_32x32b_x32(tmem_o + lane_sel + (uint32_t)(c * 32), o);
-            }
-            tmem_st_wait();
-        }
-        const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
-        // P[b2] was read by P V (i - 2): long retired, the wait is a formality that keeps the proxy ordering explicit
-        if (i >= 2) mbar_wait(&bar_pv[b2], (uint32_t)(((i - 2) >> 1) & 1));
-        uint8_t* prow = sP + b2 * Cfg::kP + tid * 128;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const uint32_t* r = hh ? r1 : r0;
-            uint32_t pk[16];
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-                const float p0 = fast_exp2(__uint_as_float(r[e]) - m_eff);
-                const float p1 = fast_exp2(__uint_as_float(r[e + 1]) - m_eff);
-                const float p2 = fast_exp2(__uint_as_float(r[e + 2]) - m_eff);
-                const float p3 = fast_exp2(__uint_as_float(r[e + 3]) - m_eff);
-                pk[e >> 1] = pack_bf16x2(p0, p1);
-                pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
-                l_acc += (p0 + p1) + (p2 + p3);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                *reinterpret_cast<uint4*>(prow + (((hh * 4 + u) ^ (tid & 7)) << 4)) =
-                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
-        if (c_async) asm volatile("cp.async.wait_all;" ::: "memory");
-        else if (tid < KN) sC[((i + 2) % 3) * KN + tid] = c_next_valid ? c_next_raw * P.scale_log2e : -1.0e30f;
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(&bar_v[i % 3], (uint32_t)((i / 3) & 1));
-            tc_fence_after();
-            const uint32_t pa = smem_u32(sP + b2 * Cfg::kP), va = smem_u32(sV + (i % 3) * Cfg::kKV);
-#pragma unroll
-            for (int ks = 0; ks < KN / 16; ++ks)
-                umma_f16(tmem_o, make_smem_desc_sw128(pa + ks * 32, 16, 1024), make_smem_desc_sw128(va + ks * 2048, 1024, 1024),
-                         idesc_o, (i != 0 || ks != 0) ? 1u : 0u);
-            umma_commit(&bar_pv[b2]);
-            if (i + 2 < n_t) {
-                // S(i + 2) into the buffer every thread has just drained; its K tile was requested when S(i) completed
-                mbar_wait(&bar_k[b2], (uint32_t)(((i + 2) >> 1) & 1));
-                tc_fence_after();
-                issue_s(i + 2);
-                // V(i + 2) goes where V(i - 1) was: P V (i - 1) was issued a whole tile ago
-                if (i >= 1) mbar_wait(&bar_pv[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
-                load_v(i + 2);
-            }
-        }
-    }
-
-    // ------------------------------- epilogue -------------------------------
-    if (n_t > 0) {
-        mbar_wait(&bar_pv[(n_t - 1) & 1], (uint32_t)(((n_t - 1) >> 1) & 1));   // MMAs retire in order: the last one suffices
-        tc_fence_after();
-        const float inv = (l_acc > 0.f) ? 1.0f / l_acc : 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_sel + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            if (qi < q_len) {
-                __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK + c * 32;
-                uint32_t pk[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    pk[e] = pack_bf16x2(__uint_as_float(r[2 * e]) * inv, __uint_as_float(r[2 * e + 1]) * inv);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    reinterpret_cast<uint4*>(o)[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                if (P.split3_out) {
-                    uint32_t lo[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        lo[e] = pack_bf16x2(__uint_as_float(r[2 * e]) * inv - bf16_lo(pk[e]),
-                                            __uint_as_float(r[2 * e + 1]) * inv - bf16_hi(pk[e]));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        reinterpret_cast<uint4*>(o + P.split_width)[u] =
-                            make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
-                        reinterpret_cast<uint4*>(o + 2 * P.split_width)[u] =
-                            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                    }
-                }
-            }
-        }
-    } else if (qi < q_len) {
-        __nv_bfloat16* o = P.out + (long long)(q_start + qi) * P.ldo + P.out_col0 + h * DK;
-        for (int e = 0; e < DK; ++e) o[e] = __float2bfloat16_rn(0.f);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
-    }
-}
-
-// ----------------------------------------------------------------------------------------------
 __global__ void relpos_kprep_kernel(const __nv_bfloat16* __restrict__ k, long long ldk,
                                     const float* __restrict__ P, const int* __restrict__ row_pos,
                                     const float* __restrict__ bias_u, const float* __restrict__ bias_v, int M,
@@ -776,21 +446,10 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     P.v_mode = a.v_mode;
     P.kbias_scaled = (a.kbias != nullptr && a.kbias_scaled) ? 1 : 0;
     WB_REQUIRE((a.ldo % 8) == 0 && (a.out_col0 % 8) == 0, WB_ERR_BAD_ARG, "attention: output pitch/offset must be %%8");
+    WB_SET_MAX_DYN_SMEM(attention_online_kernel, AttnCfg<KN>::kSmem);
     dim3 grid(ceil_div(a.max_q_len, AT_M), a.heads, a.batch);
     ProfScope _ps(PT_ATTENTION, stream, 0.0);
-    // WB_ATTN_DB=1: the double-buffered schedule (2 CTAs / SM); default: the single-buffered one (4 CTAs / SM)
-    static int s_db = -1;
-    if (s_db < 0) {
-        const char* e = getenv("WB_ATTN_DB");
-        s_db = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-    }
-    if (s_db) {
-        WB_SET_MAX_DYN_SMEM(attention_db_kernel, AttnDbCfg::kSmem);
-        attention_db_kernel<<<grid, 128, AttnDbCfg::kSmem, stream>>>(tq, tk, tv, P);
-    } else {
-        WB_SET_MAX_DYN_SMEM(attention_online_kernel, AttnCfg<KN>::kSmem);
-        attention_online_kernel<<<grid, 128, AttnCfg<KN>::kSmem, stream>>>(tq, tk, tv, P);
-    }
+    attention_online_kernel<<<grid, 128, AttnCfg<KN>::kSmem, stream>>>(tq, tk, tv, P);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
