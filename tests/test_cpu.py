@@ -362,3 +362,56 @@ def test_export_model_file_layout(tmp_path):
         seen += 1
         assert name and numel > 0
     assert seen == n and off == len(raw)
+
+
+def test_whisper_spec_and_packer_shapes():
+    """Whisper configuration parsing and weight packing (host logic, no GPU): conv weights in (tap, channel) order, zero key
+    bias slices, learnable decoder positions, precise mode = [hi | hi | lo] per K block."""
+    import torch
+    from wenet_b200 import synth
+    from wenet_b200.weights import ModelSpec, pack_state_dict
+    cfg = synth.recipe("whisper_tiny")
+    spec = ModelSpec(cfg)
+    assert (spec.arch, spec.dec_flavor, spec.dec_max_len, spec.max_pos, spec.sos, spec.eos) == (1, 1, 448, 1500, 100, 99)
+    sd = synth.synth_state_dict(cfg, seed=777)
+    assert "encoder.encoders.0.self_attn.linear_k.bias" not in sd          # key_bias: false
+    pk = pack_state_dict(spec, sd)
+    d, idim = spec.d_model, spec.input_dim
+    w1 = sd["encoder.embed.conv.0.weight"]                                  # (d, idim, 3)
+    assert torch.equal(pk["wenc.conv1.w"].float().view(d, 3, idim)[:, 2, :], w1[:, :, 2].to(torch.bfloat16).float())
+    qb = pk["wenc.0.att.qkv.b"]
+    assert qb.shape == (3 * d,) and float(qb[d:2 * d].abs().max()) == 0.0 and float(qb[:d].abs().max()) > 0.0
+    assert pk["dec.left.pe"].shape == (448, d) and pk["wenc.pe"].shape == (1500, d)
+    pp = pack_state_dict(spec, sd, precise=True)
+    assert pp["wenc.conv1.w"].shape == (d, 9 * idim) and pp["wenc.0.ff.w1.w"].shape == (spec.ffn_dim, 3 * d)
+    hi, hi2, lo = pp["wenc.0.att.out.w"].float().view(d, 3, d).unbind(1)
+    w = sd["encoder.encoders.0.self_attn.linear_out.weight"]
+    assert torch.equal(hi, hi2) and float((hi + lo - w).abs().max()) < 1e-5   # bf16x3: hi + lo carries 16 mantissa bits
+    assert pp["dec.left.0.ff.w1.w"].shape == pk["dec.left.0.ff.w1.w"].shape   # the decoder stays bf16
+    with pytest.raises(NotImplementedError):
+        ModelSpec(dict(cfg, encoder_conf=dict(cfg["encoder_conf"], input_layer="conv2d")))
+
+
+def test_whisper_prefix_and_mel_filters():
+    """whisper_prefix == the forced start of add_whisper_tokens (common.py:198-226); slaney filterbank restatements of the
+    product (numpy) and the oracle (pure Python) agree."""
+    import numpy as np
+    from oracle import shim
+    from oracle import wenet_oracle as O
+    from wenet_b200 import synth
+    from wenet_b200.whisper import WHISPER_LANGS, slaney_mel_filters, whisper_prefix
+    st = synth.recipe("whisper_large_v3")["tokenizer_conf"]["special_tokens"]
+    p = whisper_prefix(st, ["transcribe", "translate", "vad"], ["en", "zh", "yue"])
+    assert p.tolist() == [[50258, 50259, 50360, 50364], [50258, 50260, 50359, 50364], [50258, 50258 + 100, 50363, 50363]]
+    assert len(WHISPER_LANGS) == 100 and len(set(WHISPER_LANGS)) == 100
+    a = slaney_mel_filters(16000, 400, 128)
+    b = O.slaney_mel_filters(16000, 400, 128).numpy()
+    assert a.shape == (128, 201) and float(np.abs(a - b).max()) < 1e-7
+    if shim.have_reference():
+        shim.install()
+        import torch
+        from wenet.utils.common import add_whisper_tokens
+        st2 = synth.recipe("whisper_tiny")["tokenizer_conf"]["special_tokens"]
+        ys_in, _ = add_whisper_tokens(st2, torch.ones(2, 0, dtype=torch.long), -1, tasks=["transcribe", "translate"],
+                                      no_timestamp=True, langs=["zh", "en"], use_prev=False)
+        assert ys_in.tolist() == whisper_prefix(st2, ["transcribe", "translate"], ["zh", "en"]).tolist()
