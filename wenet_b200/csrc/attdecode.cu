@@ -33,6 +33,7 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 constexpr int kPoll = 8;
 constexpr int kMaxBeam = 32;
+constexpr int kCaMaxSplits = 4;   // key pieces of the cross attention (flash-decoding)
 
 #define RC(x)                         \
     do {                              \
@@ -231,7 +232,7 @@ __global__ void final_select_kernel(const float* __restrict__ score, const int* 
 struct AbPlan {
     int R = 0, L = 0;
     size_t o_memkv = 0, o_kv = 0, o_x = 0, o_a = 0, o_qkv = 0, o_ctx = 0, o_q = 0, o_h = 0, o_logits = 0, o_topv = 0, o_topi = 0,
-           o_int = 0, total = 0;
+           o_int = 0, o_part_o = 0, o_part_ml = 0, total = 0;
     long long ldl = 0;
     size_t n_int = 0;
 };
@@ -256,8 +257,11 @@ void ab_layout(const Model* m, long long enc_rows, int batch, int beam, int max_
     P->o_topi = o; o += align_up(R * beam * 4);
     // ints: hyp x2, anc x2 [R][L]; score x2 (float), end x2, cur_tok, cur_pos [R]; q_start, q_len, enc_start, enc_len,
     // utt_ended [batch]; prefix [batch][L]
-    P->n_int = 4 * R * max_len + 6 * R + 5 * (size_t)batch + (size_t)batch * max_len + 64;
+    P->n_int = 4 * R * max_len + 6 * R + 5 * (size_t)batch + (size_t)batch * max_len + 64 + 4 * (size_t)batch * kCaMaxSplits;
     P->o_int = o; o += align_up(P->n_int * 4);
+    // split-key cross attention (attention.cu, AttnArgs::part_o): pieces x heads x beam rows x (64 fp32 + (m, l))
+    P->o_part_o = o; o += align_up(R * kCaMaxSplits * m->cfg.dec_heads * 64 * 4);
+    P->o_part_ml = o; o += align_up(R * kCaMaxSplits * m->cfg.dec_heads * 8);
     P->total = o + 256;
 }
 
@@ -365,6 +369,32 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
         for (int i = 0; i < batch * prefix_len; ++i) t[5 * batch + i] = prefix_host[i];
     }
     WB_CHECK_CUDA(cudaMemcpyAsync(tail, hb.data(), hb.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    // Cross attention runs as `ca_splits` key pieces per utterance (multiples of the 64-key tile): one CTA per (utterance,
+    // head) walking all key tiles is two waves of the 4-CTA/SM kernel at Whisper size (32 x 20 = 640 CTAs for 592 slots, the
+    // second wave 8 % full) - with pieces the tail wave is short.  Item b * S + s: the beam rows of b, piece s of its keys.
+    int max_enc_len = 0;
+    for (int b = 0; b < batch; ++b) max_enc_len = seq_len_host[b] > max_enc_len ? seq_len_host[b] : max_enc_len;
+    int ca_splits = ceil_div(max_enc_len > 0 ? max_enc_len : 1, 64);   // at least one 64-key tile per piece
+    ca_splits = ca_splits < 1 ? 1 : (ca_splits > kCaMaxSplits ? kCaMaxSplits : ca_splits);
+    int* ca_tab = prefix_dev + (size_t)batch * max_len;   // q_start, q_len, k_start, k_len of the batch * ca_splits items
+    {
+        const int items = batch * ca_splits;
+        std::vector<int> ct((size_t)4 * items);
+        for (int b = 0; b < batch; ++b) {
+            const int T = seq_len_host[b];
+            const int piece = ceil_div(ceil_div(T > 0 ? T : 1, ca_splits), 64) * 64;
+            for (int s2 = 0; s2 < ca_splits; ++s2) {
+                const int it = b * ca_splits + s2;
+                const int k0 = s2 * piece < T ? s2 * piece : T;
+                const int k1 = (s2 + 1) * piece < T ? (s2 + 1) * piece : T;
+                ct[it] = b * N;
+                ct[items + it] = N;
+                ct[2 * items + it] = seq_start_host[b] + k0;
+                ct[3 * items + it] = k1 - k0;
+            }
+        }
+        WB_CHECK_CUDA(cudaMemcpyAsync(ca_tab, ct.data(), ct.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
     WB_CHECK_CUDA(cudaMemsetAsync(ib, 0, (size_t)4 * R * L * sizeof(int), st));
     // the copy above reads pageable host memory: it has completed (staged) when cudaMemcpyAsync returns
 
@@ -414,8 +444,17 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
                 A.k = memkv; A.ldk = 2 * d; A.k_rows = enc_rows; A.k_col0 = 0;
                 A.v = memkv; A.ldv = 2 * d; A.v_rows = enc_rows; A.v_col0 = d;
                 A.kbias = nullptr; A.ld_kbias = 0;
-                A.q_start = q_start; A.q_len = q_len; A.k_start = enc_start; A.k_len = enc_len;
-                A.batch = batch; A.heads = H; A.max_q_len = N;
+                if (ca_splits > 1) {
+                    const int items = batch * ca_splits;
+                    A.q_start = ca_tab; A.q_len = ca_tab + items; A.k_start = ca_tab + 2 * items; A.k_len = ca_tab + 3 * items;
+                    A.batch = items; A.splits = ca_splits;
+                    A.part_o = reinterpret_cast<float*>(ws + P.o_part_o);
+                    A.part_ml = ws + P.o_part_ml;
+                } else {
+                    A.q_start = q_start; A.q_len = q_len; A.k_start = enc_start; A.k_len = enc_len;
+                    A.batch = batch;
+                }
+                A.heads = H; A.max_q_len = N;
                 A.chunk_size = 0; A.num_left_chunks = -1; A.scale = scale;
                 A.out = ctx; A.ldo = d; A.out_col0 = 0; A.split3_out = 0; A.v_mode = 0;
                 RC(attention_forward(A, st));

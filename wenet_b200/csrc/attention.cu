@@ -45,6 +45,11 @@ struct AttnDev {
     int split_width;
     int v_mode;
     int kbias_scaled;   // kbias already holds c * scale * log2(e): fetched by cp.async straight into shared memory
+    // split-key mode (part_o != null): batch item z covers ONE piece of the keys of a query block; the kernel leaves the
+    // unnormalised fp32 output and (reference point, sum) of its piece, attention_merge_parts combines the pieces
+    float* part_o;      // [items][max_q][64]
+    float2* part_ml;    // [items][max_q]  (m in the log2 domain, l)
+    int part_max_q;
 };
 
 // KN = keys per tile.  128: 100 KB smem, 256 TMEM columns (S 128 | O 64 | L 16) -> 2 CTAs/SM.
@@ -344,7 +349,29 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
 
     // ------------------------------- epilogue -------------------------------
-    if (kt0 < kt1) {
+    if (P.part_o != nullptr) {
+        // split-key mode: piece (blockIdx.z, head h) of query row qi
+        if (qi < q_len) {
+            const long long pr = ((long long)blockIdx.z * gridDim.y + h) * P.part_max_q + qi;
+            const bool any = (kt0 < kt1) && (m_used != -INFINITY);
+            P.part_ml[pr] = make_float2(any ? m_used : -INFINITY, any ? l_acc : 0.f);
+        }
+        if (kt0 < kt1) {
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_o + lane_sel + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
+                if (qi < q_len) {
+                    float4* o = reinterpret_cast<float4*>(P.part_o + (((long long)blockIdx.z * gridDim.y + h) * P.part_max_q + qi) * 64 + c * 32);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        o[u] = make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]), __uint_as_float(r[4 * u + 2]),
+                                           __uint_as_float(r[4 * u + 3]));
+                }
+            }
+        }
+    } else if (kt0 < kt1) {
         const float inv = (l_acc > 0.f) ? 1.0f / l_acc : 0.f;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -388,6 +415,35 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// merge of the split-key pieces: one warp per (query block b, head, row), lane = channel pair.  Piece s of block b is
+// batch item b * S + s of the attention launch.
+__global__ void attention_merge_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
+                                       const int* __restrict__ q_start, const int* __restrict__ q_len, int S, int H, int max_q,
+                                       int total, __nv_bfloat16* __restrict__ out, long long ldo, int out_col0) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= total) return;   // total = B * H * max_q, ordered (b, h, row)
+    const int row = w % max_q, bh = w / max_q, h = bh % H, b = bh / H;
+    if (row >= q_len[b * S]) return;
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < S; ++s2) M = fmaxf(M, part_ml[((long long)(b * S + s2) * H + h) * max_q + row].x);
+    float L = 0.f;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int s2 = 0; s2 < S; ++s2) {
+        const long long pi = ((long long)(b * S + s2) * H + h) * max_q + row;
+        const float2 ml = part_ml[pi];
+        if (!(ml.y > 0.f)) continue;
+        const float wgt = fast_exp2(ml.x - M);
+        L += ml.y * wgt;
+        const float2 ov = reinterpret_cast<const float2*>(part_o + pi * 64)[lane];
+        acc.x = fmaf(ov.x, wgt, acc.x);
+        acc.y = fmaf(ov.y, wgt, acc.y);
+    }
+    const float inv = (L > 0.f) ? 1.0f / L : 0.f;
+    reinterpret_cast<uint32_t*>(out + (long long)(q_start[b * S] + row) * ldo + out_col0 + h * DK)[lane] =
+        pack_bf16x2(acc.x * inv, acc.y * inv);
+}
 
 // ----------------------------------------------------------------------------------------------
 __global__ void relpos_kprep_kernel(const __nv_bfloat16* __restrict__ k, long long ldk,
@@ -445,6 +501,11 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     P.split_width = a.heads * DK;
     P.v_mode = a.v_mode;
     P.kbias_scaled = (a.kbias != nullptr && a.kbias_scaled) ? 1 : 0;
+    P.part_o = a.part_o;
+    P.part_ml = reinterpret_cast<float2*>(a.part_ml);
+    P.part_max_q = a.max_q_len;
+    WB_REQUIRE(a.part_o == nullptr || (a.part_ml != nullptr && a.splits >= 1 && a.batch % a.splits == 0 && !a.split3_out),
+               WB_ERR_BAD_ARG, "attention: split-key mode needs part_ml, batch = blocks x splits, no split3 output");
     WB_REQUIRE((a.ldo % 8) == 0 && (a.out_col0 % 8) == 0, WB_ERR_BAD_ARG, "attention: output pitch/offset must be %%8");
     WB_SET_MAX_DYN_SMEM(attention_online_kernel, AttnCfg<KN>::kSmem);
     dim3 grid(ceil_div(a.max_q_len, AT_M), a.heads, a.batch);
@@ -452,6 +513,15 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     attention_online_kernel<<<grid, 128, AttnCfg<KN>::kSmem, stream>>>(tq, tk, tv, P);
     count_launch();
     WB_CHECK_LAUNCH();
+    if (a.part_o != nullptr) {
+        const int blocks = a.batch / a.splits;
+        const int total = blocks * a.heads * a.max_q_len;
+        attention_merge_kernel<<<ceil_div(total * 32, 256), 256, 0, stream>>>(a.part_o, P.part_ml, a.q_start, a.q_len, a.splits,
+                                                                             a.heads, a.max_q_len, total, P.out, a.ldo,
+                                                                             a.out_col0);
+        count_launch();
+        WB_CHECK_LAUNCH();
+    }
     return WB_OK;
 }
 

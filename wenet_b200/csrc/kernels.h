@@ -139,6 +139,13 @@ struct AttnArgs {
     void* out; long long ldo;  int out_col0;            // bf16 [q_rows, ldo]
     int split3_out;                                     // write [hi|lo|hi] with block width heads*64
     int v_mode;                                         // 0: MN-major UMMA descriptor, 1: smem transpose
+    // split-key mode (flash-decoding): `batch` = blocks x splits items, item b * splits + s holding piece s of the keys of
+    // query block b (same q_start / q_len for the pieces of a block, its own k_start / k_len); the kernel leaves
+    // unnormalised fp32 partial outputs part_o [batch][heads][max_q_len][64] and (reference point, sum) part_ml
+    // [batch][heads][max_q_len] (float2), and a merge kernel writes `out`.  max_q_len <= 128.
+    float* part_o = nullptr;
+    void* part_ml = nullptr;
+    int splits = 1;
 };
 int attention_forward(const AttnArgs& a, cudaStream_t stream);
 // K' = bf16(k + P[pos]) and c[m,h] = sum_i u[h,i]*k[m,h,i] + v[h,i]*P[pos,h,i]
