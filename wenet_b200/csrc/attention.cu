@@ -36,6 +36,7 @@ struct AttnDev {
     const int* k_start;
     const int* k_len;
     int q_col0, k_col0, v_col0;
+    int kv_head_rows;   // > 0: K / V are head-major [heads][kv_head_rows][64] (row pitch 64): head h starts at row h * kv_head_rows
     int chunk_size, num_left_chunks;
     float scale_log2e;
     __nv_bfloat16* out;
@@ -143,6 +144,11 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int kt0 = cta_lo / KN;
     const int kt1 = (cta_hi + KN - 1) / KN;
 
+    // K / V tile coordinates: interleaved heads (column offset) or head-major (row offset; contiguous per head, so a
+    // (sequence, head) streams one contiguous block - the layout the decoding cross attention uses for its 8 GB of K / V)
+    const int kcol = P.kv_head_rows > 0 ? P.k_col0 : P.k_col0 + h * DK;
+    const int vcol = P.kv_head_rows > 0 ? P.v_col0 : P.v_col0 + h * DK;
+    const int kvrow0 = k_start + (P.kv_head_rows > 0 ? h * P.kv_head_rows : 0);
     uint32_t ph = 0;   // all per-tile barriers flip once per tile
     constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, KN, 0);
     constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, DK, 1);
@@ -151,9 +157,9 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_expect_tx(bar_q, TILE_BYTES);
         tma_load_2d(sQ, &tmap_q, bar_q, P.q_col0 + h * DK, q_start + qt * AT_M);
         mbar_expect_tx(bar_k, Cfg::kKVBytes);
-        tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + kt0 * KN);
+        tma_load_2d(sK, &tmap_k, bar_k, kcol, kvrow0 + kt0 * KN);
         mbar_expect_tx(bar_v, Cfg::kKVBytes);
-        tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + kt0 * KN);
+        tma_load_2d(sV, &tmap_v, bar_v, vcol, kvrow0 + kt0 * KN);
     }
 
     float m_used = -INFINITY;   // reference point of the exponentials accumulated so far
@@ -218,7 +224,7 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tc_fence_after();
         if (tid == 0 && kt + 1 < kt1) {   // K buffer is free again
             mbar_expect_tx(bar_k, Cfg::kKVBytes);
-            tma_load_2d(sK, &tmap_k, bar_k, P.k_col0 + h * DK, k_start + (kt + 1) * KN);
+            tma_load_2d(sK, &tmap_k, bar_k, kcol, kvrow0 + (kt + 1) * KN);
         }
         const float* cc = sC + (kt & 1) * KN;
         const bool tile_full = (j0 >= full_lo) && (j0 + KN <= full_hi);
@@ -343,7 +349,7 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tc_fence_after();
         if (tid == 0 && kt + 1 < kt1) {
             mbar_expect_tx(bar_v, Cfg::kKVBytes);
-            tma_load_2d(sV, &tmap_v, bar_v, P.v_col0 + h * DK, k_start + (kt + 1) * KN);
+            tma_load_2d(sV, &tmap_v, bar_v, vcol, kvrow0 + (kt + 1) * KN);
         }
         ph ^= 1;
     }
@@ -491,6 +497,7 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     P.q_col0 = a.q_col0;
     P.k_col0 = a.k_col0;
     P.v_col0 = a.v_col0;
+    P.kv_head_rows = a.kv_head_rows;
     P.chunk_size = a.chunk_size;
     P.num_left_chunks = a.num_left_chunks;
     P.scale_log2e = a.scale * 1.4426950408889634f;
