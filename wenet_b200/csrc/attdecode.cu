@@ -109,13 +109,26 @@ dec_self_attn_step_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
     sum = warp_sum(sum);
     __syncwarp();
     const float inv = 1.0f / sum;
+    // eight V rows in flight (a one-row-at-a-time loop is a chain of dependent L2 / DRAM latencies: ~100 of them per warp)
     float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < n; ++j) {
-        const float p = sc[j];
-        const __nv_bfloat16* vp = (j == pos) ? (qrow + 2 * d) : (kv + ((long long)j * R + slot[j]) * 2 * d + d + h * 64);
-        const uint32_t vv = reinterpret_cast<const uint32_t*>(vp)[lane];
-        o0 = fmaf(p, bf16_lo(vv), o0);
-        o1 = fmaf(p, bf16_hi(vv), o1);
+    constexpr int VB = 8;
+    for (int j0 = 0; j0 < n; j0 += VB) {
+        uint32_t vv[VB];
+#pragma unroll
+        for (int u = 0; u < VB; ++u) {
+            const int j = j0 + u;
+            vv[u] = 0u;
+            if (j < n) {
+                const __nv_bfloat16* vp = (j == pos) ? (qrow + 2 * d) : (kv + ((long long)j * R + slot[j]) * 2 * d + d + h * 64);
+                vv[u] = reinterpret_cast<const uint32_t*>(vp)[lane];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VB; ++u) {
+            const float p = (j0 + u < n) ? sc[j0 + u] : 0.f;
+            o0 = fmaf(p, bf16_lo(vv[u]), o0);
+            o1 = fmaf(p, bf16_hi(vv[u]), o1);
+        }
     }
     reinterpret_cast<uint32_t*>(ctx + (long long)r * d + h * 64)[lane] = pack_bf16x2(o0 * inv, o1 * inv);
 }
