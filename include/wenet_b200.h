@@ -424,6 +424,12 @@ int wb_op_logsoftmax_topk(float* logits_dev, int64_t ldl, int M, int V, int blan
 int wb_op_lse_topk(const float* logits_dev, int64_t ldl, int M, int V, int blank_id, float blank_penalty,
                    int topk, float* topk_val_dev, int32_t* topk_idx_dev, wb_stream_t stream);
 
+/* wb_op_lse_topk for few rows over a huge vocabulary (the output layer of attention decoding, logp.topk(beam_size) of
+ * search.py:309): every row is cut into `slices` pieces taken by different warps and merged; same (value desc, index asc)
+ * order.  scratch_dev: M * slices * (topk * 8 + 8) + 256 bytes. */
+int wb_op_lse_topk_sliced(const float* logits_dev, int64_t ldl, int M, int V, int topk, int slices, float* topk_val_dev,
+                          int32_t* topk_idx_dev, void* scratch_dev, size_t scratch_bytes, wb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -242,3 +242,30 @@ def test_whisper_through_install():
         assert type(res[0]).__module__.startswith("wenet.")        # the reference's DecodeResult type
     finally:
         plugin.uninstall()
+
+
+@pytest.mark.parametrize("M,V,k,slices", [(37, 51866, 10, 16), (320, 20001, 4, 16), (3, 70000, 32, 8)])
+def test_lse_topk_sliced(M, V, k, slices):
+    """Sliced top-k of the log-softmax (few rows, huge vocabulary): values within 1e-5 of torch.log_softmax(...).topk, indices
+    identical, incl. exact ties broken by index."""
+    from wenet_b200 import _lib
+    from wenet_b200._lib import check, cur_stream, ptr
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + V)
+    x = torch.randn(M, V, generator=g) * 3
+    x[0, 5] = x[0, 40000 % V] = x[0].max() + 1.0          # an exact tie across two slices: lower index first
+    ldl = (V + 7) // 8 * 8
+    buf = torch.full((M, ldl), float("nan"))
+    buf[:, :V] = x
+    xd = buf.cuda()
+    tv = torch.empty(M, k, device="cuda")
+    ti = torch.empty(M, k, dtype=torch.int32, device="cuda")
+    scr = torch.empty(M * slices * (k * 8 + 8) + 256, dtype=torch.uint8, device="cuda")
+    check(lib.wb_op_lse_topk_sliced(ptr(xd), ldl, M, V, k, slices, ptr(tv), ptr(ti), ptr(scr), scr.numel(), cur_stream()),
+          "wb_op_lse_topk_sliced")
+    rv, ri = torch.log_softmax(x.double(), -1).topk(k)
+    assert (tv.cpu().double() - rv).abs().max().item() < 1e-5
+    got = ti.cpu().long()
+    assert got[0, 0].item() == 5 and got[0, 1].item() == 40000 % V
+    same = got == ri
+    assert bool(same[1:].all()) and bool(same[0, 2:].all())

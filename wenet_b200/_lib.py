@@ -99,6 +99,7 @@ _PROTOS = {
     "wb_op_dwconv": (i32, [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, f32,
                             vp, i32, vp, i64, vp]),
     "wb_op_logsoftmax_topk": (i32, [vp, i64, i32, i32, i32, f32, i32, vp, vp, vp]),
+    "wb_op_lse_topk_sliced": (i32, [vp, i64, i32, i32, i32, i32, vp, vp, vp, sz, vp]),
     "wb_op_lse_topk": (i32, [vp, i64, i32, i32, i32, f32, i32, vp, vp, vp]),
 }
 

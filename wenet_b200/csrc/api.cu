@@ -470,6 +470,13 @@ int wb_op_lse_topk(const float* logits_dev, int64_t ldl, int M, int V, int blank
                         (cudaStream_t)stream);
 }
 
+int wb_op_lse_topk_sliced(const float* logits_dev, int64_t ldl, int M, int V, int topk, int slices, float* topk_val_dev,
+                          int32_t* topk_idx_dev, void* scratch_dev, size_t scratch_bytes, wb_stream_t stream) {
+    WB_REQUIRE(scratch_bytes >= lse_topk_sliced_scratch_bytes(M, slices, topk), WB_ERR_WORKSPACE, "lse_topk_sliced: scratch %zu < %zu",
+               scratch_bytes, lse_topk_sliced_scratch_bytes(M, slices, topk));
+    return lse_topk_sliced(logits_dev, ldl, M, V, topk, slices, topk_val_dev, topk_idx_dev, scratch_dev, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- Whisper log-mel
 struct wb_logmel {
     LogMelPlan* plan;

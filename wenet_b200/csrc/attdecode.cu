@@ -33,7 +33,8 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 constexpr int kPoll = 8;
 constexpr int kMaxBeam = 32;
-constexpr int kCaMaxSplits = 4;   // key pieces of the cross attention (flash-decoding)
+constexpr int kCaMaxSplits = 4;
+constexpr int kTopkSlices = 16;   // vocabulary slices of the output top-k when V is large   // key pieces of the cross attention (flash-decoding)
 
 #define RC(x)                         \
     do {                              \
@@ -259,7 +260,7 @@ __global__ void final_select_kernel(const float* __restrict__ score, const int* 
 
 struct AbPlan {
     int R = 0, L = 0;
-    size_t o_memtmp = 0, o_memkv = 0, o_kv = 0, o_x = 0, o_a = 0, o_qkv = 0, o_ctx = 0, o_q = 0, o_h = 0, o_logits = 0, o_topv = 0, o_topi = 0,
+    size_t o_topk_scr = 0, o_memtmp = 0, o_memkv = 0, o_kv = 0, o_x = 0, o_a = 0, o_qkv = 0, o_ctx = 0, o_q = 0, o_h = 0, o_logits = 0, o_topv = 0, o_topi = 0,
            o_int = 0, o_part_o = 0, o_part_ml = 0, total = 0;
     long long ldl = 0;
     size_t n_int = 0;
@@ -284,6 +285,7 @@ void ab_layout(const Model* m, long long enc_rows, int batch, int beam, int max_
     P->o_logits = o; o += align_up(R * P->ldl * 4);
     P->o_topv = o; o += align_up(R * beam * 4);
     P->o_topi = o; o += align_up(R * beam * 4);
+    P->o_topk_scr = o; o += align_up(lse_topk_sliced_scratch_bytes((int)R, kTopkSlices, beam));
     // ints: hyp x2, anc x2 [R][L]; score x2 (float), end x2, cur_tok, cur_pos [R]; q_start, q_len, enc_start, enc_len,
     // utt_ended [batch]; prefix [batch][L]
     P->n_int = 4 * R * max_len + 6 * R + 5 * (size_t)batch + (size_t)batch * max_len + 64 + 4 * (size_t)batch * kCaMaxSplits;
@@ -512,7 +514,10 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
             continue;
         }
         RC(gemm_bf16(a, d, &D.out.tmap, D.out.w, R, c.vocab, d, D.out.b, EPI_F32, 1.0f, logits, P.ldl, 0, st));
-        RC(ctc_lse_topk(logits, P.ldl, R, c.vocab, -1, 0.0f, N, topv, topi, st));
+        if (c.vocab >= 16384 && N + 3 <= c.vocab / kTopkSlices)   // 320 rows x 51 866 columns: one warp per row takes 260 us
+            RC(lse_topk_sliced(logits, P.ldl, R, c.vocab, N, kTopkSlices, topv, topi, ws + P.o_topk_scr, st));
+        else
+            RC(ctc_lse_topk(logits, P.ldl, R, c.vocab, -1, 0.0f, N, topv, topi, st));
         {
             BeamStepArgs B;
             B.topv = topv; B.topi = topi;

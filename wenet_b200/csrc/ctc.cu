@@ -40,14 +40,22 @@ __device__ __forceinline__ void lt_warp_best(float& v, int& i) {
 }
 
 __global__ void __launch_bounds__(LT_WARPS * 32)
-lse_topk_kernel(const float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
-                float* __restrict__ topk_val, int* __restrict__ topk_idx, float* out_logp /* may alias logits */) {
+lse_topk_kernel(const float* logits, long long ldl, int M, int V_all, int blank_id, float blank_penalty, int topk,
+                float* __restrict__ topk_val, int* __restrict__ topk_idx, float* out_logp /* may alias logits */, int slices,
+                int slice_len, float2* __restrict__ part_ml) {
     __shared__ float s_cv[LT_WARPS][LT_CAP];
     __shared__ int s_ci[LT_WARPS][LT_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * LT_WARPS + warp;
-    if (row >= M) return;
-    const float* g = logits + row * ldl;
+    // sliced mode (slices > 1; few rows over a huge vocabulary: autoregressive decoding): a warp takes ONE slice of a row and
+    // leaves the raw (un-normalised) top-k of its slice plus the slice's (max, sum of exp) - lse_topk_merge_kernel
+    // finishes the row.  Row id = row * slices + slice; indices are global.
+    const long long row_id = (long long)blockIdx.x * LT_WARPS + warp;
+    if (row_id >= (long long)M * slices) return;
+    const long long row = (slices > 1) ? row_id / slices : row_id;
+    const int col0 = (slices > 1) ? (int)(row_id - row * slices) * slice_len : 0;
+    const int V = (slices > 1) ? min(slice_len, V_all - col0) : V_all;
+    blank_id -= col0;
+    const float* g = logits + row * ldl + col0;
     const int n4 = (V + 3) >> 2;
     constexpr float kLog2e = 1.4426950408889634f;
     auto load4_from = [&](const float* src, float pen, int i4, float (&v)[4]) {
@@ -94,7 +102,8 @@ lse_topk_kernel(const float* logits, long long ldl, int M, int V, int blank_id, 
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float part = (m > -INFINITY) ? ssum * fast_exp2((m - mx) * kLog2e) : 0.f;
     part = warp_sum(part);
-    const float lse = mx + logf(part);
+    const float lse = (slices > 1) ? 0.f : mx + logf(part);   // sliced: raw values leave the kernel
+    if (slices > 1 && lane == 0) part_ml[row_id] = make_float2(mx, part);
 
     // tau: k-th largest of the 64 lane maxima
     float tau = -INFINITY;
@@ -182,8 +191,8 @@ lse_topk_kernel(const float* logits, long long ldl, int M, int V, int blank_id, 
         }
         lt_warp_best(bv, bi);
         if (lane == 0) {
-            topk_val[row * topk + r] = (count <= LT_CAP) ? bv - lse : bv - sub2;
-            topk_idx[row * topk + r] = (bi == 0x7fffffff) ? 0 : bi;
+            topk_val[row_id * topk + r] = (count <= LT_CAP) ? bv - lse : bv - sub2;
+            topk_idx[row_id * topk + r] = (bi == 0x7fffffff) ? 0 : bi + col0;
         }
         pv = bv;
         pi = bi;
@@ -191,6 +200,48 @@ lse_topk_kernel(const float* logits, long long ldl, int M, int V, int blank_id, 
 }
 
 // one warp per sequence
+// sliced mode, second half: warp per row - combine the slices' (max, sum) into the row's log-sum-exp and pick the top-k of the
+// slices' candidates in (value desc, index asc) order
+__global__ void lse_topk_merge_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, const float2* __restrict__ part_ml,
+                                      int M, int slices, int topk, float* __restrict__ topk_val, int* __restrict__ topk_idx) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float mx = -INFINITY;
+    for (int s2 = lane; s2 < slices; s2 += 32) mx = fmaxf(mx, part_ml[(long long)row * slices + s2].x);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s2 = lane; s2 < slices; s2 += 32) {
+        const float2 ml = part_ml[(long long)row * slices + s2];
+        if (ml.y > 0.f) sum += ml.y * __expf(ml.x - mx);
+    }
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    const int nc = slices * topk;
+    const float* cv = pval + (long long)row * nc;
+    const int* ci = pidx + (long long)row * nc;
+    float pv = INFINITY;
+    int pi = -1;
+    for (int r = 0; r < topk; ++r) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < nc; c += 32) {
+            const float v = cv[c];
+            const int i = ci[c];
+            if (lt_before(pv, pi, v, i) && lt_before(v, i, bv, bi)) {
+                bv = v;
+                bi = i;
+            }
+        }
+        lt_warp_best(bv, bi);
+        if (lane == 0) {
+            topk_val[(long long)row * topk + r] = bv - lse;
+            topk_idx[(long long)row * topk + r] = (bi == 0x7fffffff) ? 0 : bi;
+        }
+        pv = bv;
+        pi = bi;
+    }
+}
+
 __global__ void greedy_kernel(const int* __restrict__ topk_idx, int topk, const int* __restrict__ seq_start,
                               const int* __restrict__ seq_len, int blank_id, int* __restrict__ out_tokens,
                               int out_stride, int* __restrict__ out_len) {
@@ -224,7 +275,7 @@ static int launch_lse_topk(const float* logits, long long ldl, int M, int V, int
     WB_REQUIRE(topk == 0 || (topk_val && topk_idx), WB_ERR_BAD_ARG, "logsoftmax_topk: null top-k output");
     ProfScope _ps(PT_LOGSOFTMAX_TOPK, stream, (double)M * V * (out_logp ? 8.0 : 4.0));
     lse_topk_kernel<<<ceil_div(M, LT_WARPS), LT_WARPS * 32, 0, stream>>>(logits, ldl, M, V, blank_id, blank_penalty, topk,
-                                                                         topk_val, topk_idx, out_logp);
+                                                                         topk_val, topk_idx, out_logp, 1, 0, nullptr);
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;
@@ -238,6 +289,33 @@ int ctc_logsoftmax_topk(float* logits, long long ldl, int M, int V, int blank_id
 int ctc_lse_topk(const float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
                  float* topk_val, int* topk_idx, cudaStream_t stream) {
     return launch_lse_topk(logits, ldl, M, V, blank_id, blank_penalty, topk, topk_val, topk_idx, nullptr, stream);
+}
+
+// Few rows, huge vocabulary (the output layer of autoregressive decoding: 320 rows x 51 866 columns): every row is cut into
+// `slices` pieces handled by different warps, then merged.  scratch: M * slices * topk (float + int) + M * slices float2.
+size_t lse_topk_sliced_scratch_bytes(int M, int slices, int topk) {
+    return (size_t)M * slices * topk * 8 + (size_t)M * slices * 8 + 256;
+}
+int lse_topk_sliced(const float* logits, long long ldl, int M, int V, int topk, int slices, float* topk_val, int* topk_idx,
+                    void* scratch, cudaStream_t stream) {
+    if (M <= 0) return WB_OK;
+    WB_REQUIRE(topk >= 1 && slices >= 2 && slices <= 64 && scratch != nullptr, WB_ERR_BAD_ARG, "lse_topk_sliced: bad argument");
+    const int slice_len = ceil_div(ceil_div(V, slices), 4) * 4;
+    WB_REQUIRE((long long)(slices - 1) * slice_len < V && topk <= slice_len - 3, WB_ERR_BAD_ARG, "lse_topk_sliced: %d slices of %d",
+               slices, slice_len);
+    WB_REQUIRE(ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, WB_ERR_BAD_ARG, "lse_topk_sliced: alignment");
+    float* pval = reinterpret_cast<float*>(scratch);
+    int* pidx = reinterpret_cast<int*>(pval + (size_t)M * slices * topk);
+    float2* pml = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + (((size_t)M * slices * topk * 8 + 15) / 16) * 16);
+    ProfScope _ps(PT_LOGSOFTMAX_TOPK, stream, (double)M * V * 4.0);
+    lse_topk_kernel<<<ceil_div(M * slices, LT_WARPS), LT_WARPS * 32, 0, stream>>>(logits, ldl, M, V, -1, 0.f, topk, pval, pidx, nullptr,
+                                                                                  slices, slice_len, pml);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    lse_topk_merge_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(pval, pidx, pml, M, slices, topk, topk_val, topk_idx);
+    count_launch();
+    WB_CHECK_LAUNCH();
+    return WB_OK;
 }
 
 int ctc_greedy(const int* topk_idx, int topk, const int* seq_start, const int* seq_len, int batch, int blank_id,

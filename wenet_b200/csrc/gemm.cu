@@ -78,6 +78,8 @@ struct GemmParams {
     int split3;
     int use_tma_out;  // epilogue through shared memory + TMA store / reduce-add (all non-split3 cases)
     int res_ring;     // weight-stationary mode: A ring depth (GemmCfg::res_ring(num_kb))
+    int ksplit;       // streaming mode, EPI_RESID_F32 only: the K range is cut into ksplit pieces, each its own tile of the
+                      // schedule; the pieces meet in the TMA reduce-add of the fp32 output (bias from piece 0 only)
     int num_m_tiles, num_n_tiles;
     // conv mode (Conv2d 3x3 stride 2 as an implicit GEMM): the A tile of k-block (kh, kw, c-block) is one 3-D TMA box
     // {64 channels, 19 frequency taps (element stride 2), 6 time taps (element stride 2)} of the channels-last conv1
@@ -153,7 +155,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_mt = (NC == 2) ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;   // m-tiles of the schedule (pairs of 128-row tiles)
-    const int num_tiles = num_mt * p.num_n_tiles;
+    const int ksplit = BRES ? 1 : p.ksplit;
+    const int kb_per = (num_kb + ksplit - 1) / ksplit;
+    const int num_tiles = num_mt * p.num_n_tiles * ksplit;
     const int epi = (EPI >= 0) ? EPI : p.epi;
     WB_DIAG(long long diag[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long cta_t0 = clock64();)
 
@@ -196,9 +200,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int t_step = BRES ? 1 : num_ctas;
     // (pair mode: this CTA's 128-row tile is 2 x (schedule m-tile) + rank; an odd last tile leaves the peer with rows past
     //  M: its TMA loads are zero-filled and its stores clipped)
-#define WB_TILE_COORDS(t)                                                      \
-    const int n_tile = BRES ? (t) / num_mt : (t) % p.num_n_tiles;             \
-    const int m_tile = (BRES ? (t) % num_mt : (t) / p.num_n_tiles) * NC + rank;
+#define WB_TILE_COORDS(t)                                                                                   \
+    const int n_tile = BRES ? (t) / num_mt : (t) % p.num_n_tiles;                                          \
+    const int mt_sp = BRES ? (t) % num_mt : (t) / p.num_n_tiles;   /* streaming: m-tile fastest, then K piece */ \
+    const int k_piece = BRES ? 0 : mt_sp / num_mt;                                                         \
+    const int m_tile = (BRES ? mt_sp : mt_sp - k_piece * num_mt) * NC + rank;                              \
+    const int kb0 = k_piece * kb_per, kb1 = min(num_kb, kb0 + kb_per);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -229,7 +236,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
                 int conv_t = 0;
                 if (!BRES && p.conv) conv_t = (m_tile < p.num_m_tiles) ? __ldg(&p.tile_tab[m_tile]).x : 0;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     WB_TIMED_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
                     const uint32_t full_addr = (NC == 2) ? mapa_u32(&full_bar[stage], 0) : 0u;
                     if (!BRES && p.conv) {
@@ -281,7 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 WB_TIMED_WAIT(2, mbar_wait(&tmem_empty[acc], acc_phase ^ 1));
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     WB_TIMED_WAIT(1, mbar_wait(&full_bar[stage], phase));
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
@@ -290,8 +297,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        if (NC == 2) umma_f16_pair(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (NC == 2) umma_f16_pair(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        else umma_f16(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                     }
                     // smem slot free (in both CTAs of a pair) once these MMAs retire
                     if (NC == 2) umma_commit_pair(&empty_bar[stage]);
@@ -534,7 +541,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // values), so the chunk loop reads it with broadcast LDS instead of an L2 round trip per chunk
             float4 bpre = make_float4(0.f, 0.f, 0.f, 0.f);
             const int bcol = n_tile * BN + half * (kChunksPerWarp * 32) + 4 * lane;
-            if (p.bias != nullptr && 4 * lane < kChunksPerWarp * 32) {
+            const bool bias_on = (p.bias != nullptr) && (k_piece == 0);   // K pieces after the first add no bias
+            if (bias_on && 4 * lane < kChunksPerWarp * 32) {
                 if (bcol + 0 < p.N) bpre.x = __ldg(p.bias + bcol + 0);
                 if (bcol + 1 < p.N) bpre.y = __ldg(p.bias + bcol + 1);
                 if (bcol + 2 < p.N) bpre.z = __ldg(p.bias + bcol + 2);
@@ -566,7 +574,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     tmem_ld_32x32b_x32(taddr0 + (uint32_t)((c + 1) * 32), rbuf[(ci + 1) & 1]);
                 float v[32];
                 const bool full = (n0 + 32 <= p.N);
-                if (p.bias != nullptr) {
+                if (bias_on) {
                     const float* sb = sbias + ci * 32;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -884,7 +892,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         cfg.numAttrs = 1;
         WB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, BRES, EPI, NC>, ta, tb, tc, tc2, p));
     } else {
-        const int tiles = p.num_m_tiles * p.num_n_tiles;
+        const int tiles = p.num_m_tiles * p.num_n_tiles * (BRES ? 1 : p.ksplit);
         const int grid = tiles < usable ? tiles : usable;
         gemm_tcgen05_kernel<BN, BRES, EPI, NC><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
     }
@@ -1032,6 +1040,16 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
         if (rc != WB_OK) return rc;
     }
     const int num_kb = ceil_div(K, BK);
+    // split-K for few-row residual GEMMs with a long K (decoding: FFN w_2 with K = 5120 is 30 tiles of 80 k-blocks each -
+    // 30 CTAs streaming 2.6 MB apiece): the pieces accumulate in the TMA reduce-add of the fp32 residual stream
+    p.ksplit = 1;
+    if (epi == EPI_RESID_F32 && p.use_tma_out && bn == 128 && num_kb > GemmCfg<128>::kResMaxKB && M <= 4 * BM) {
+        const int tiles = p.num_m_tiles * p.num_n_tiles;
+        int ks = current_device_sms() / (tiles > 0 ? tiles : 1);
+        ks = ks > 8 ? 8 : ks;
+        ks = ks > num_kb / 4 ? num_kb / 4 : ks;
+        if (ks >= 2) p.ksplit = ks;
+    }
     p.res_ring = (bn == 256) ? (pair ? GemmCfg<256, 2>::res_ring(num_kb) : GemmCfg<256>::res_ring(num_kb))
                              : GemmCfg<128>::res_ring(num_kb);
     // activation-heavy weight-stationary shapes (FFN w_1 + SiLU): the sixteen-epilogue-warp kernel of gemm_act16.cu
@@ -1156,6 +1174,7 @@ int gemm_conv2_implicit(const void* out1, long long t1_total, int F1, int d, con
     p.split3 = 0;
     p.use_tma_out = 1;
     p.res_ring = 0;
+    p.ksplit = 1;
     p.num_m_tiles = num_tiles;
     p.num_n_tiles = d / 256;
     p.lse_part = nullptr;

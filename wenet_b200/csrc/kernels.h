@@ -201,6 +201,10 @@ int ctc_logsoftmax_topk(float* logits, long long ldl, int M, int V, int blank_id
 // top-k of the log-softmax (values normalised) without writing the matrix back; logits are left untouched
 int ctc_lse_topk(const float* logits, long long ldl, int M, int V, int blank_id, float blank_penalty, int topk,
                  float* topk_val, int* topk_idx, cudaStream_t stream);
+// the same top-k of the log-softmax for FEW rows over a HUGE vocabulary (attention decoding): rows cut into `slices` pieces
+size_t lse_topk_sliced_scratch_bytes(int M, int slices, int topk);
+int lse_topk_sliced(const float* logits, long long ldl, int M, int V, int topk, int slices, float* topk_val, int* topk_idx,
+                    void* scratch, cudaStream_t stream);
 // greedy collapse: per sequence, frames [start, start+len) of top-1 ids (stride topk)
 int ctc_greedy(const int* topk_idx, int topk, const int* seq_start, const int* seq_len, int batch,
                int blank_id, int* out_tokens, int out_stride, int* out_len, cudaStream_t stream);
