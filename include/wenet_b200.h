@@ -379,6 +379,11 @@ int wb_whisper_encoder_forward(const wb_model* m, const float* feats_dev, int64_
 int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K,
                const float* bias_dev, int epi, float alpha, void* c_dev, int64_t ldc, int split3,
                wb_stream_t stream);
+/* C (fp32) += alpha * (A B^T + bias) for FEW rows and a long K (the residual projections of autoregressive decoding): the K
+ * range is cut into pieces that meet in the TMA reduce-add of C, so that more than ceil(M/128) * N/128 CTAs stream the
+ * weights; the fp32 summation order is not reproducible run to run (the encoder paths never use it). */
+int wb_op_gemm_resid_splitk(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K,
+                            const float* bias_dev, float alpha, float* c_dev, int64_t ldc, wb_stream_t stream);
 /* x += alpha * (a b^T + bias) and ln_out = LayerNorm(x) * gamma + beta (bf16) in one kernel; N must be 256.  Replaces a
  * residual-update Linear followed by the next module's LayerNorm (wenet/models/transformer/encoder_layer.py:221-263).
  * gamma1_dev / beta1_dev non-null: the layer boundary (:262-263 then the next layer's :221-223) -

@@ -443,3 +443,21 @@ def test_lse_topk_without_writeback(V, k):
     tv2, ti2 = ops.logsoftmax_topk(dbuf, V, k, blank_id=0, blank_penalty=0.5)
     assert torch.equal(ti2, ti) and torch.equal(tv2, tv)
     assert (dbuf[:, :V].cpu() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(320, 1280, 5120), (40, 1280, 1280), (257, 256, 2048), (500, 640, 4096)])
+def test_gemm_resid_splitk(M, N, K):
+    """Few-row residual GEMM with the K range cut into pieces (decoding projections): C += alpha (A B^T + bias), the bias added
+    exactly once, against torch in fp32 (the reduce-add order of the pieces is free: tolerance, not bit equality)."""
+    from wenet_b200 import _lib
+    from wenet_b200._lib import check, cur_stream, ptr
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = _rb(torch.randn(M, K, generator=g)).to(_dev())
+    b = _rb(torch.randn(N, K, generator=g) / math.sqrt(K)).to(_dev())
+    bias = (torch.randn(N, generator=g) * 3).to(_dev())
+    c0 = torch.randn(M, N, generator=g).to(_dev())
+    c = c0.clone()
+    check(_lib.load().wb_op_gemm_resid_splitk(ptr(a), a.stride(0), ptr(b), M, N, K, ptr(bias), 0.5, ptr(c), c.stride(0),
+                                              cur_stream()), "wb_op_gemm_resid_splitk")
+    torch.cuda.synchronize()
+    _close(c, c0 + 0.5 * (a.float() @ b.float().T + bias), 1e-5, 3e-4)

@@ -90,6 +90,7 @@ _PROTOS = {
     "wb_whisper_encoder_forward": (i32, [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
     "wb_op_attention_beam_step": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "wb_op_gemm": (i32, [vp, i64, vp, i32, i32, i32, vp, i32, f32, vp, i64, i32, vp]),
+    "wb_op_gemm_resid_splitk": (i32, [vp, i64, vp, i32, i32, i32, vp, f32, vp, i64, vp]),
     "wb_op_gemm_resid_ln": (i32, [vp, i64, vp, i32, i32, i32, vp, f32, vp, i64, vp, vp, vp, vp, f32, vp, i64, vp]),
     "wb_op_layernorm": (i32, [vp, i64, i32, i32, vp, vp, f32, vp, i64, i32, vp, i64, vp]),
     "wb_op_cast_bf16": (i32, [vp, i64, i32, i32, vp, i64, i32, vp]),

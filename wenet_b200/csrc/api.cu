@@ -407,6 +407,10 @@ int wb_op_gemm(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, 
     return gemm_bf16(a_dev, lda, nullptr, b_dev, M, N, K, bias_dev, epi, alpha, c_dev, ldc, split3,
                      (cudaStream_t)stream);
 }
+int wb_op_gemm_resid_splitk(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K, const float* bias_dev,
+                            float alpha, float* c_dev, int64_t ldc, wb_stream_t stream) {
+    return gemm_resid_splitk(a_dev, lda, nullptr, b_dev, M, N, K, bias_dev, alpha, c_dev, ldc, (cudaStream_t)stream);
+}
 int wb_op_gemm_resid_ln(const void* a_dev, int64_t lda, const void* b_dev, int M, int N, int K, const float* bias_dev,
                         float alpha, float* x_dev, int64_t ldx, const float* gamma1_dev, const float* beta1_dev,
                         const float* gamma_dev, const float* beta_dev, float eps, void* ln_out_bf16_dev, int64_t ld_ln,

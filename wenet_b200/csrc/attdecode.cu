@@ -303,7 +303,7 @@ static int resid_then_norm(const void* A, long long lda, const Linear& W, int M,
                            void* a_out, cudaStream_t st) {
     if (W.b != nullptr && gemm_resid_ln_supported(d))
         return gemm_resid_ln(A, lda, &W.tmap, W.w, M, d, W.K, W.b, 1.0f, x, d, nullptr, nullptr, n.g, n.b, eps, a_out, d, st);
-    int rc = gemm_bf16(A, lda, &W.tmap, W.w, M, d, W.K, W.b, EPI_RESID_F32, 1.0f, x, d, 0, st);
+    int rc = gemm_resid_splitk(A, lda, &W.tmap, W.w, M, d, W.K, W.b, 1.0f, x, d, st);   // few rows, K up to 5120: split-K
     if (rc != WB_OK) return rc;
     return layernorm_rows(x, d, M, d, n.g, n.b, eps, a_out, d, 0, nullptr, 0, st);
 }

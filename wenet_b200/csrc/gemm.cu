@@ -955,7 +955,7 @@ struct LnFuse {
 
 static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N,
                      int K, const float* bias, int epi, float alpha, void* out, long long ldc, int split3,
-                     float2* lse_part, cudaStream_t stream, const LnFuse* ln = nullptr) {
+                     float2* lse_part, cudaStream_t stream, const LnFuse* ln = nullptr, bool allow_ksplit = false) {
     if (M <= 0) return WB_OK;
     WB_REQUIRE(N > 0 && K > 0, WB_ERR_BAD_ARG, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     WB_REQUIRE((K % 8) == 0 && (lda % 8) == 0, WB_ERR_BAD_ARG,
@@ -1043,7 +1043,9 @@ static int gemm_impl(const void* A, long long lda, const WeightMaps* tmap_b_opt,
     // split-K for few-row residual GEMMs with a long K (decoding: FFN w_2 with K = 5120 is 30 tiles of 80 k-blocks each -
     // 30 CTAs streaming 2.6 MB apiece): the pieces accumulate in the TMA reduce-add of the fp32 residual stream
     p.ksplit = 1;
-    if (epi == EPI_RESID_F32 && p.use_tma_out && bn == 128 && num_kb > GemmCfg<128>::kResMaxKB && M <= 4 * BM) {
+    // (opt-in, gemm_resid_splitk: the order of the fp32 reduce-adds is not fixed, and the streaming encoder promises
+    //  bit-reproducible chunks)
+    if (allow_ksplit && epi == EPI_RESID_F32 && p.use_tma_out && bn == 128 && num_kb > GemmCfg<128>::kResMaxKB && M <= 4 * BM) {
         const int tiles = p.num_m_tiles * p.num_n_tiles;
         int ks = current_device_sms() / (tiles > 0 ? tiles : 1);
         ks = ks > 8 ? 8 : ks;
@@ -1109,6 +1111,13 @@ int gemm_bf16(const void* A, long long lda, const WeightMaps* tmap_b_opt, const 
               cudaStream_t stream) {
     WB_REQUIRE(epi != EPI_LSE && epi != EPI_RESID_LN && epi != EPI_RESID_LN2, WB_ERR_BAD_ARG, "gemm: this epilogue has its own entry point");
     return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, epi, alpha, out, ldc, split3, nullptr, stream);
+}
+
+// out_f32 += alpha * (A B^T + bias) with the K range cut into pieces when only a few CTAs would otherwise stream a long K
+// (few-row decoding GEMMs); the pieces meet in the TMA reduce-add, so the fp32 summation order is not reproducible
+int gemm_resid_splitk(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
+                      const float* bias, float alpha, float* out, long long ldc, cudaStream_t stream) {
+    return gemm_impl(A, lda, tmap_b_opt, B, M, N, K, bias, EPI_RESID_F32, alpha, out, ldc, 0, nullptr, stream, nullptr, true);
 }
 
 static int g_fuse_ln = -1;

@@ -58,6 +58,8 @@ int gemm_resid_ln(const void* A, long long lda, const WeightMaps* tmap_b_opt, co
 int gemm_act16_try(const void* A, long long lda, const CUtensorMap* tmap_b_one, int M, int N, int K, const float* bias, int epi,
                    void* out, long long ldc, int sm_reserve, cudaStream_t stream);
 
+int gemm_resid_splitk(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
+                      const float* bias, float alpha, float* out, long long ldc, cudaStream_t stream);
 int gemm_lse_partials(const void* A, long long lda, const WeightMaps* tmap_b_opt, const void* B, int M, int N, int K,
                       const float* bias, float2* part, cudaStream_t stream);
 
