@@ -134,21 +134,6 @@ dec_self_attn_step_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
     reinterpret_cast<uint32_t*>(ctx + (long long)r * d + h * 64)[lane] = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
-// memkv [rows][2d] (K heads | V heads interleaved per row) -> head-major kvh [2][H][rows][64]: every (utterance, head)
-// then streams ONE contiguous block per decoding step instead of 128-byte pieces 4 d bytes apart
-__global__ void kv_head_major_kernel(const uint4* __restrict__ memkv, long long rows, int H, uint4* __restrict__ kvh) {
-    // one warp per (row, K|V): 2 H x 8 vectors of 16 bytes
-    const long long total = rows * 2 * H * 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int v8 = (int)(i & 7);
-        const long long t = i >> 3;
-        const int hh = (int)(t % (2 * H));      // 0 .. H-1: K head, H .. 2H-1: V head
-        const long long r = t / (2 * H);
-        const int kv = hh / H, h = hh - kv * H;
-        kvh[(((long long)kv * H + h) * rows + r) * 8 + v8] = memkv[r * (2 * H * 8) + (long long)hh * 8 + v8];
-    }
-}
-
 // ---- one beam-search step (search.py:309-355), one CTA per utterance -----------------------------------------------
 // topv / topi: [R][N] log-softmax top-N of every row (value desc).  Rows that have ended keep exactly one continuation
 // (<eos>, + 0); the N*N candidates of the utterance are ranked by (score desc, candidate index asc) and the best N
@@ -260,7 +245,7 @@ __global__ void final_select_kernel(const float* __restrict__ score, const int* 
 
 struct AbPlan {
     int R = 0, L = 0;
-    size_t o_topk_scr = 0, o_memtmp = 0, o_memkv = 0, o_kv = 0, o_x = 0, o_a = 0, o_qkv = 0, o_ctx = 0, o_q = 0, o_h = 0, o_logits = 0, o_topv = 0, o_topi = 0,
+    size_t o_topk_scr = 0, o_memkv = 0, o_kv = 0, o_x = 0, o_a = 0, o_qkv = 0, o_ctx = 0, o_q = 0, o_h = 0, o_logits = 0, o_topv = 0, o_topi = 0,
            o_int = 0, o_part_o = 0, o_part_ml = 0, total = 0;
     long long ldl = 0;
     size_t n_int = 0;
@@ -273,8 +258,7 @@ void ab_layout(const Model* m, long long enc_rows, int batch, int beam, int max_
     P->L = max_len;
     P->ldl = (m->cfg.vocab + 7) / 8 * 8;
     size_t o = 0;
-    P->o_memtmp = o; o += align_up((size_t)enc_rows * 2 * d * 2);      // one layer's row-major projection (GEMM output)
-    P->o_memkv = o; o += align_up((size_t)nl * enc_rows * 2 * d * 2);  // head-major [layer][K | V][head][row][64]
+    P->o_memkv = o; o += align_up((size_t)nl * enc_rows * 2 * d * 2);
     P->o_kv = o; o += align_up((size_t)nl * max_len * R * 2 * d * 2);
     P->o_x = o; o += align_up(R * d * 4);
     P->o_a = o; o += align_up(R * d * 2);
@@ -433,17 +417,9 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
     const long long lda_enc = c.precise ? 3 * d : d;   // precise encoder rows are [hi | lo | hi]; the decoder reads hi
     for (int li = 0; li < nl; ++li) {
         const DecLayer& Ly = D.layers[li];
-        void* memtmp = ws + P.o_memtmp;
         void* memkv = ws + P.o_memkv + (size_t)li * enc_rows * 2 * d * 2;
-        RC(gemm_bf16(enc_bf16, lda_enc, &Ly.ca_kv.tmap, Ly.ca_kv.w, (int)enc_rows, 2 * d, d, Ly.ca_kv.b, EPI_BF16, 1.0f, memtmp,
+        RC(gemm_bf16(enc_bf16, lda_enc, &Ly.ca_kv.tmap, Ly.ca_kv.w, (int)enc_rows, 2 * d, d, Ly.ca_kv.b, EPI_BF16, 1.0f, memkv,
                      2 * d, 0, st));
-        {
-            ProfScope _ps(PT_MISC, st, (double)enc_rows * 2 * d * 4.0);
-            kv_head_major_kernel<<<current_device_sms() * 8, 256, 0, st>>>(reinterpret_cast<const uint4*>(memtmp), enc_rows, H,
-                                                                           reinterpret_cast<uint4*>(memkv));
-            count_launch();
-            WB_CHECK_LAUNCH();
-        }
     }
     prefix_step_kernel<<<ceil_div(R, 128), 128, 0, st>>>(prefix_dev, prefix_len, N, L, -1, R, hyp[0], hyp[1], anc[0], anc[1],
                                                          cur_tok, cur_pos);
@@ -480,11 +456,8 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
                 const void* memkv = ws + P.o_memkv + (size_t)li * enc_rows * 2 * d * 2;
                 AttnArgs A;
                 A.q = q; A.ldq = d; A.q_rows = R; A.q_col0 = 0;
-                // head-major: K heads at [0, H * enc_rows), V heads behind them
-                A.k = memkv; A.ldk = 64; A.k_rows = (long long)H * enc_rows; A.k_col0 = 0;
-                A.v = reinterpret_cast<const uint8_t*>(memkv) + (size_t)H * enc_rows * 64 * 2; A.ldv = 64;
-                A.v_rows = (long long)H * enc_rows; A.v_col0 = 0;
-                A.kv_head_rows = (int)enc_rows;
+                A.k = memkv; A.ldk = 2 * d; A.k_rows = enc_rows; A.k_col0 = 0;
+                A.v = memkv; A.ldv = 2 * d; A.v_rows = enc_rows; A.v_col0 = d;
                 A.kbias = nullptr; A.ld_kbias = 0;
                 if (ca_splits > 1) {
                     const int items = batch * ca_splits;

@@ -36,7 +36,6 @@ struct AttnDev {
     const int* k_start;
     const int* k_len;
     int q_col0, k_col0, v_col0;
-    int kv_head_rows;   // > 0: K / V are head-major [heads][kv_head_rows][64] (row pitch 64): head h starts at row h * kv_head_rows
     int chunk_size, num_left_chunks;
     float scale_log2e;
     __nv_bfloat16* out;
@@ -144,11 +143,8 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int kt0 = cta_lo / KN;
     const int kt1 = (cta_hi + KN - 1) / KN;
 
-    // K / V tile coordinates: interleaved heads (column offset) or head-major (row offset; contiguous per head, so a
-    // (sequence, head) streams one contiguous block - the layout the decoding cross attention uses for its 8 GB of K / V)
-    const int kcol = P.kv_head_rows > 0 ? P.k_col0 : P.k_col0 + h * DK;
-    const int vcol = P.kv_head_rows > 0 ? P.v_col0 : P.v_col0 + h * DK;
-    const int kvrow0 = k_start + (P.kv_head_rows > 0 ? h * P.kv_head_rows : 0);
+    const int kcol = P.k_col0 + h * DK, vcol = P.v_col0 + h * DK;
+    const int kvrow0 = k_start;
     uint32_t ph = 0;   // all per-tile barriers flip once per tile
     constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, KN, 0);
     constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, DK, 1);
@@ -497,7 +493,6 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     P.q_col0 = a.q_col0;
     P.k_col0 = a.k_col0;
     P.v_col0 = a.v_col0;
-    P.kv_head_rows = a.kv_head_rows;
     P.chunk_size = a.chunk_size;
     P.num_left_chunks = a.num_left_chunks;
     P.scale_log2e = a.scale * 1.4426950408889634f;

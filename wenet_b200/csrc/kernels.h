@@ -148,9 +148,6 @@ struct AttnArgs {
     float* part_o = nullptr;
     void* part_ml = nullptr;
     int splits = 1;
-    // head-major K / V: k and v point at [heads][kv_head_rows][64] bf16 (ldk = ldv = 64, k_rows = v_rows = heads *
-    // kv_head_rows), head h of key row r lives at row h * kv_head_rows + r.  0: heads interleaved along the columns.
-    int kv_head_rows = 0;
 };
 int attention_forward(const AttnArgs& a, cudaStream_t stream);
 // K' = bf16(k + P[pos]) and c[m,h] = sum_i u[h,i]*k[m,h,i] + v[h,i]*P[pos,h,i]
