@@ -219,7 +219,6 @@ __global__ void final_select_kernel(const float* __restrict__ score, const int* 
                                     int P, int eos, float length_penalty, int* __restrict__ out_tok, int out_stride,
                                     int* __restrict__ out_len, float* __restrict__ out_score) {
     const int b = blockIdx.x;
-    __shared__ int best_s;
     if (threadIdx.x == 0) {
         float bs = 0.f;
         int bi = -1;
@@ -233,7 +232,6 @@ __global__ void final_select_kernel(const float* __restrict__ score, const int* 
                 bi = n;
             }
         }
-        best_s = bi;
         if (out_score) out_score[b] = bs;
         const int* hr = hyp + (long long)(b * N + bi) * L;
         int cnt = 0;
@@ -373,13 +371,11 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
             s0[R + r] = s0[r];
         }
         int* t = hb.data() + 6 * (size_t)R;
-        int max_enc = 0;
         for (int b = 0; b < batch; ++b) {
             t[b] = b * N;
             t[batch + b] = N;
             t[2 * batch + b] = seq_start_host[b];
             t[3 * batch + b] = seq_len_host[b];
-            if (seq_len_host[b] > max_enc) max_enc = seq_len_host[b];
         }
         for (int i = 0; i < batch * prefix_len; ++i) t[5 * batch + i] = prefix_host[i];
     }
@@ -430,7 +426,6 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
     int cur = 0;   // buffer holding the current hyps / ancestry / scores / flags
     int pos = 0;
     std::vector<int> ended_host(batch, 0);
-    bool all_ended = false;
     int steps = 0;
     // token positions 0 .. max_len - 2 are consumed; the step at position `pos` produces the token of position pos + 1
     for (pos = 0; pos + 1 < max_len; ++pos) {
@@ -512,14 +507,12 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
             WB_CHECK_CUDA(cudaStreamSynchronize(st));
             long long tot = 0;
             for (int b = 0; b < batch; ++b) tot += ended_host[b];
-            if (tot == R) {
-                all_ended = true;
+            if (tot == R) {   // every hypothesis of every utterance has ended (search.py:301-302)
                 ++pos;
                 break;
             }
         }
     }
-    (void)all_ended;
     // hyps now hold tokens at positions 0 .. pos (pos = number of consumed positions)
     const int n_tok = pos + 1 <= max_len ? pos + 1 : max_len;
     final_select_kernel<<<batch, 32, 0, st>>>(score[cur], hyp[cur], N, L, n_tok, prefix_len, eos, length_penalty, out_tokens_dev,
