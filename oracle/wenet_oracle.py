@@ -701,10 +701,12 @@ def beam_step(top_k_logp, top_k_index, scores, end_flag, hyps, beam_size: int, e
 
 
 def attention_beam_search(p, pre, n_layers, heads, encoder_out, encoder_mask, beam_size: int, prefix, eos: int,
-                          length_penalty: float = 0.0, flavor: str = "wenet", quant=None) -> List[List[int]]:
+                          length_penalty: float = 0.0, flavor: str = "wenet", quant=None, maxlen: Optional[int] = None) -> List[List[int]]:
     """search.py:252-371.  prefix: (B, P) long - [[sos]] * B for wenet models, add_whisper_tokens' forced start for
     Whisper (common.py:198-226).  Returns the best hypothesis of every utterance (prefix and eos stripped)."""
-    B, maxlen = encoder_out.shape[0], encoder_out.shape[1]
+    B = encoder_out.shape[0]
+    if maxlen is None:
+        maxlen = encoder_out.shape[1]      # the reference's bound (search.py:263); tests may shorten the loop
     running = B * beam_size
     hyps = torch.as_tensor(prefix, dtype=torch.long).repeat_interleave(beam_size, dim=0)
     P = hyps.shape[1]

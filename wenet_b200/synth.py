@@ -351,6 +351,11 @@ def recipe(name: str) -> dict:
         return dict(base, output_dim=61, encoder_conf=enc(512, 8, 1024, 2, 15, True, "layer_norm", True),
                     decoder="bitransformer", decoder_conf=dec(8, 1024, 1, 1),
                     model_conf=dict(ctc_weight=0.3, lsm_weight=0.1, length_normalized_loss=False, reverse_weight=0.3))
+    if name == "whisper_wide":      # the large-v3 WIDTHS (d 1280, 20 heads, ff 5120, V 51 866, 128 mel) with 2 + 2 layers: test size
+        c = recipe("whisper_large_v3")
+        c["encoder_conf"] = dict(c["encoder_conf"], num_blocks=2)
+        c["decoder_conf"] = dict(c["decoder_conf"], num_blocks=2, tie_word_embedding=False)
+        return c
     if name in ("whisper_tiny", "whisper_large_v3"):
         # examples/aishell/whisper/conf/finetune_whisper_largev3.yaml (32 + 32 L, d 1280, 20 heads, ff 5120, V 51866, 128 mel);
         # whisper_tiny: the same structure at test size
