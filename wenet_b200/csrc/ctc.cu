@@ -73,31 +73,20 @@ lse_topk_kernel(const float* logits, long long ldl, int M, int V_all, int blank_
     // ---- pass 1 ----
     float m = -INFINITY, ssum = 0.f;
     float v1 = -INFINITY, v2 = -INFINITY;
-    // two 16-byte loads in flight per lane and iteration (one load per trip left the row read at 2.2 TB/s: a warp's 33 trips
-    // were 33 serial memory latencies); the second group is all -inf past the end of the row
-    for (int i4 = lane; i4 < n4; i4 += 64) {
-        float v[8];
-        {
-            float va[4], vb[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            load4(i4, va);
-            if (i4 + 32 < n4) load4(i4 + 32, vb);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                v[e] = va[e];
-                v[4 + e] = vb[e];
-            }
-        }
-        const float gm = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+    for (int i4 = lane; i4 < n4; i4 += 32) {
+        float v[4];
+        load4(i4, v);
+        const float gm = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
         const float mn = fmaxf(m, gm);
         if (mn > -INFINITY) {
             float acc = ssum * fast_exp2((m - mn) * kLog2e);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc += fast_exp2((v[e] - mn) * kLog2e);
+            for (int e = 0; e < 4; ++e) acc += fast_exp2((v[e] - mn) * kLog2e);
             ssum = acc;
             m = mn;
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < 4; ++e) {
             if (v[e] > v2) {          // only the VALUES of the two largest elements are needed for tau
                 if (v[e] > v1) {
                     v2 = v1;
