@@ -33,7 +33,8 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 constexpr int kPoll = 8;
 constexpr int kMaxBeam = 32;
-constexpr int kCaMaxSplits = 4;
+constexpr int kCaMaxSplits = 8;    // workspace bound; the default cap is kCaSplits (WB_CA_SPLITS overrides it, tuning only)
+constexpr int kCaSplits = 4;
 constexpr int kTopkSlices = 16;   // vocabulary slices of the output top-k when V is large   // key pieces of the cross attention (flash-decoding)
 
 #define RC(x)                         \
@@ -386,7 +387,12 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
     int max_enc_len = 0;
     for (int b = 0; b < batch; ++b) max_enc_len = seq_len_host[b] > max_enc_len ? seq_len_host[b] : max_enc_len;
     int ca_splits = ceil_div(max_enc_len > 0 ? max_enc_len : 1, 64);   // at least one 64-key tile per piece
-    ca_splits = ca_splits < 1 ? 1 : (ca_splits > kCaMaxSplits ? kCaMaxSplits : ca_splits);
+    static const int ca_cap = [] {
+        const char* e = getenv("WB_CA_SPLITS");
+        const int v = e ? atoi(e) : kCaSplits;
+        return v < 1 ? 1 : (v > kCaMaxSplits ? kCaMaxSplits : v);
+    }();
+    ca_splits = ca_splits < 1 ? 1 : (ca_splits > ca_cap ? ca_cap : ca_splits);
     int* ca_tab = prefix_dev + (size_t)batch * max_len;   // q_start, q_len, k_start, k_len of the batch * ca_splits items
     {
         const int items = batch * ca_splits;

@@ -102,6 +102,15 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int qi = qt * AT_M + tid;
+    // A warp whose 32 query rows all lie past the sequence end only keeps the CTA barriers company: no tcgen05.ld, no
+    // exponentials, no P store (its P rows hold stale shared memory, which only reaches its own, never stored, O rows).
+    // Autoregressive decoding runs this kernel with `beam` (10) queries per (utterance, head): three of the four warps
+    // are idle there, and with 4 CTAs per SM the one live warp per CTA gets the MUFU pipe and the issue slots to itself.
+#ifdef WB_ATT_NO_WARP_SKIP
+    const bool warp_live = true;
+#else
+    const bool warp_live = (qt * AT_M + warp * 32) < q_len;
+#endif
 
     if (tid == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -222,6 +231,7 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             mbar_expect_tx(bar_k, Cfg::kKVBytes);
             tma_load_2d(sK, &tmap_k, bar_k, kcol, kvrow0 + (kt + 1) * KN);
         }
+        if (warp_live) {
         const float* cc = sC + (kt & 1) * KN;
         const bool tile_full = (j0 >= full_lo) && (j0 + KN <= full_hi);
         uint32_t r0[32], r1[32];
@@ -312,6 +322,7 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 *reinterpret_cast<uint4*>(prow + (((hh * 4 + u) ^ (tid & 7)) << 4)) =
                     make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
         }
+        }   // warp_live
         if (c_async) asm volatile("cp.async.wait_all;" ::: "memory");
         else if (tid < KN) sC[((kt + 1) & 1) * KN + tid] = c_next_valid ? c_next_raw * P.scale_log2e : -1.0e30f;
         fence_proxy_async_smem();
