@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(SA_WARPS * 32)
 dec_self_attn_step_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kv,
                           const int* __restrict__ anc, int anc_stride, int pos, int R, int H, int d, float scale,
                           __nv_bfloat16* __restrict__ ctx) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sa_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * SA_WARPS + warp;
@@ -433,6 +435,7 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
     int pos = 0;
     std::vector<int> ended_host(batch, 0);
     int steps = 0;
+    PdlScope pdl_scope;   // the step loop is a chain of short dependent launches: GEMMs start ahead of their predecessor's end
     // token positions 0 .. max_len - 2 are consumed; the step at position `pos` produces the token of position pos + 1
     for (pos = 0; pos + 1 < max_len; ++pos) {
         const bool beam_update = pos >= prefix_len - 1;
@@ -446,8 +449,8 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
             {
                 ProfScope _ps(PT_ATTENTION, st, 0.0);
                 const size_t smem = (size_t)SA_WARPS * 2 * (pos + 1) * sizeof(float);
-                dec_self_attn_step_kernel<<<ceil_div(R * H, SA_WARPS), SA_WARPS * 32, smem, st>>>(
-                    qkv, kvl, anc[cur], L, pos, R, H, d, scale, ctx);
+                WB_CHECK_CUDA(launch_maybe_pdl(dec_self_attn_step_kernel, dim3(ceil_div(R * H, SA_WARPS)), dim3(SA_WARPS * 32), smem,
+                                               st, qkv, kvl, anc[cur], L, pos, R, H, d, scale, ctx));
                 count_launch();
                 WB_CHECK_LAUNCH();
             }

@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(128, 4)
 attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, AttnDev P) {
     constexpr int KN = 64;
+    pdl_launch_dependents();
+    pdl_wait();   // (ahead of everything: q_len / k_len tables may come from an earlier kernel of the chain)
     using Cfg = AttnCfg<KN>;
     const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
     const int q_len = P.q_len[b];
@@ -435,6 +437,8 @@ attention_online_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 __global__ void attention_merge_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
                                        const int* __restrict__ q_start, const int* __restrict__ q_len, int S, int H, int max_q,
                                        int total, __nv_bfloat16* __restrict__ out, long long ldo, int out_col0) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= total) return;   // total = B * H * max_q, ordered (b, h, row)
     const int row = w % max_q, bh = w / max_q, h = bh % H, b = bh / H;
@@ -523,15 +527,15 @@ int attention_forward(const AttnArgs& a, cudaStream_t stream) {
     WB_SET_MAX_DYN_SMEM(attention_online_kernel, AttnCfg<KN>::kSmem);
     dim3 grid(ceil_div(a.max_q_len, AT_M), a.heads, a.batch);
     ProfScope _ps(PT_ATTENTION, stream, 0.0);
-    attention_online_kernel<<<grid, 128, AttnCfg<KN>::kSmem, stream>>>(tq, tk, tv, P);
+    WB_CHECK_CUDA(launch_maybe_pdl(attention_online_kernel, grid, dim3(128), AttnCfg<KN>::kSmem, stream, tq, tk, tv, P));
     count_launch();
     WB_CHECK_LAUNCH();
     if (a.part_o != nullptr) {
         const int blocks = a.batch / a.splits;
         const int total = blocks * a.heads * a.max_q_len;
-        attention_merge_kernel<<<ceil_div(total * 32, 256), 256, 0, stream>>>(a.part_o, P.part_ml, a.q_start, a.q_len, a.splits,
-                                                                             a.heads, a.max_q_len, total, P.out, a.ldo,
-                                                                             a.out_col0);
+        WB_CHECK_CUDA(launch_maybe_pdl(attention_merge_kernel, dim3(ceil_div(total * 32, 256)), dim3(256), 0, stream, a.part_o,
+                                       P.part_ml, a.q_start, a.q_len, a.splits, a.heads, a.max_q_len, total, P.out, a.ldo,
+                                       a.out_col0));
         count_launch();
         WB_CHECK_LAUNCH();
     }

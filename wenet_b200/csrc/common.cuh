@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+#include <string.h>
 #include "../../include/wenet_b200.h"  // wb_status codes
 
 namespace wb {
@@ -42,6 +43,48 @@ const char* get_last_error();
 
 // launch counter: every kernel launch made by this library bumps it (bench.py reports it)
 extern std::atomic<unsigned long long> g_launch_count;
+// ---- programmatic dependent launch (PDL) ----
+// The latency-bound chains (autoregressive decoding: ~450 dependent launches per step; streaming chunks) spend a good part of
+// every GEMM on its launch latency, prologue (barriers, TMEM allocation, descriptor prefetch) and the first weight fetch.
+// Inside a PdlScope the GEMM launches carry cudaLaunchAttributeProgrammaticStreamSerialization: the kernel may start while
+// its predecessor is still running, does everything that does not depend on it (prologue + the first weight tiles, which
+// nothing ever writes), and only then executes griddepcontrol.wait (= predecessor complete and visible).  Predecessors
+// call griddepcontrol.launch_dependents at their top.  Kernels launched without the attribute are ordinary stream
+// successors, whatever their predecessor did.  WB_PDL=0 turns the attribute off.
+extern thread_local int g_pdl_depth;
+bool pdl_allowed();
+struct PdlScope {
+    bool on;
+    explicit PdlScope(bool enable = true) : on(enable) { if (on) ++g_pdl_depth; }
+    ~PdlScope() { if (on) --g_pdl_depth; }
+};
+bool pdl_stream_allowed();   // WB_PDL_STREAM=0: the streaming chunk paths launch the ordinary way
+static inline bool pdl_active() { return g_pdl_depth > 0 && pdl_allowed(); }
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Launch of a kernel that executes pdl_wait() before it touches anything an earlier kernel of the stream wrote (or still
+// reads): inside a PdlScope with the programmatic-serialization attribute, otherwise an ordinary launch.  NOTE for such
+// kernels: ahead of pdl_wait() not even the output of the last-but-one kernel is safe (the direct predecessor may itself
+// still be waiting for it) - only data that was complete before the last ordinary launch, i.e. weights and tables.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                           Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_active() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline void count_launch(int n = 1) { g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 // Optional per-kernel-family profiler (CUDA events on the launching stream around every launch).

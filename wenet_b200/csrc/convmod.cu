@@ -48,6 +48,7 @@ constexpr int MAX_PASSES = 4;                 // d <= 512
 template <int KT, int NP>
 __global__ void __launch_bounds__(DW_THREADS)
 dwconv_kernel(DwDev P) {
+    pdl_launch_dependents();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int b = blockIdx.y;
     const int n_in = P.seq_len[b];

@@ -12,6 +12,8 @@ namespace {
 __global__ void embed_kernel(const int* __restrict__ tokens, const int* __restrict__ pos, int R, int d,
                              const float* __restrict__ emb, const float* __restrict__ pe, float xscale,
                              float* __restrict__ x) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int dv = d / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)R * dv;
          i += (long long)gridDim.x * blockDim.x) {
@@ -152,7 +154,7 @@ int embed_tokens(const int* tokens, const int* pos, int R, int d, const float* e
     const long long n = (long long)R * (d / 4);
     const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
     ProfScope _ps(PT_EMBED, stream, (double)R * d * 12.0);
-    embed_kernel<<<grid, 256, 0, stream>>>(tokens, pos, R, d, emb, pe, xscale, x);
+    WB_CHECK_CUDA(launch_maybe_pdl(embed_kernel, dim3(grid), dim3(256), 0, stream, tokens, pos, R, d, emb, pe, xscale, x));
     count_launch();
     WB_CHECK_LAUNCH();
     return WB_OK;

@@ -524,6 +524,7 @@ static int encoder_forward_chunk_impl(const wb_model* mm, const float* xs_dev, i
     WB_REQUIRE(xs_dev && y_dev && r_att_cache_dev && workspace_dev, WB_ERR_BAD_ARG, "forward_chunk: null argument");
     WB_REQUIRE(cache_t1 == 0 || att_cache_dev, WB_ERR_BAD_ARG, "forward_chunk: att_cache missing");
     cudaStream_t st = (cudaStream_t)stream;
+    PdlScope pdl_scope(pdl_stream_allowed());   // a chunk is ~100 short dependent launches (also when captured into a CUDA graph)
     const wb_model_config& c = m->cfg;
     const int d = c.d_model, ff = c.ffn_dim, H = c.heads;
     ChunkPlan P;

@@ -130,6 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                     GemmParams p) {
     using Cfg = GemmCfg<BN, NC>;
+    pdl_launch_dependents();   // a PDL successor may set itself up (and fetch its weights) while this grid works
     const int rank = (NC == 2) ? (int)cluster_ctarank() : 0;          // 0 = leader (issues the MMAs)
     const int cta_id = (NC == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-schedule id of this CTA (pair)
     const int num_ctas = (NC == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -217,6 +218,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int cur_n = -1;
             uint32_t bemp_phase = 0;
             const int b_row0 = (NC == 2) ? rank * (BN / 2) : 0;
+            // PDL: the weights are never written by a kernel, so the first tile's weight boxes are requested BEFORE waiting
+            // for the predecessor grid (the activations, `tile_tab` and everything the epilogue touches come after it).
+            // Streaming mode: the first ring pass' B boxes (with their barriers' byte counts); weight-stationary mode: the
+            // panel is loaded ahead of the first A tile anyway, the wait sits behind it (`pdl_pending`).
+            int pre_b = 0;
+            bool pdl_pending = true;
+            if (!BRES && t_begin < t_end && !p.conv) {
+                WB_TILE_COORDS(t_begin)
+                (void)m_tile;
+                pre_b = min(kRing, kb1 - kb0);
+                for (int s = 0; s < pre_b; ++s) {
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], Cfg::kStageBytes * NC);
+                    if (NC == 2)
+                        tma_load_2d_pair(smem_b + s * Cfg::kBBytes, &tmap_b, mapa_u32(&full_bar[s], 0), (kb0 + s) * BK,
+                                         n_tile * BN + b_row0);
+                    else
+                        tma_load_2d(smem_b + s * Cfg::kBBytes, &tmap_b, &full_bar[s], (kb0 + s) * BK, n_tile * BN);
+                }
+            }
+            if (!BRES) {
+                pdl_wait();
+                pdl_pending = false;
+            }
             for (int t = t_begin; t < t_end; t += t_step) {
                 WB_TILE_COORDS(t)
                 if (BRES && n_tile != cur_n) {
@@ -234,9 +258,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                     cur_n = n_tile;
                 }
+                if (pdl_pending) {
+                    pdl_wait();
+                    pdl_pending = false;
+                }
                 int conv_t = 0;
                 if (!BRES && p.conv) conv_t = (m_tile < p.num_m_tiles) ? __ldg(&p.tile_tab[m_tile]).x : 0;
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    const bool b_done = pre_b > 0;   // this slot's byte count and B box were issued ahead of the PDL wait
+                    if (b_done) --pre_b;
                     WB_TIMED_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
                     const uint32_t full_addr = (NC == 2) ? mapa_u32(&full_bar[stage], 0) : 0u;
                     if (!BRES && p.conv) {
@@ -248,13 +278,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         else
                             tma_load_3d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], cb * BK, kw, conv_t + kh);
                     } else {
-                        if (rank == 0) mbar_expect_tx(&full_bar[stage], (BRES ? Cfg::kABytes : Cfg::kStageBytes) * NC);
+                        if (rank == 0 && !b_done) mbar_expect_tx(&full_bar[stage], (BRES ? Cfg::kABytes : Cfg::kStageBytes) * NC);
                         if (NC == 2)
                             tma_load_2d_pair(smem_a + stage * Cfg::kABytes, &tmap_a, full_addr, kb * BK, m_tile * BM);
                         else
                             tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
                     }
-                    if (!BRES) {
+                    if (!BRES && !b_done) {
                         if (NC == 2)
                             tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, full_addr, kb * BK, n_tile * BN + b_row0);
                         else
@@ -333,6 +363,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t acc_phase = 0;
         bool need_wait = false;
         int tile_par = 0;
+        pdl_wait();   // residual stream / output buffers belong to the predecessor grid until it has completed
         WB_DIAG(const long long epi_t0 = clock64();)
         for (int t = t_begin; t < t_end; t += t_step) {
             WB_TILE_COORDS(t)
@@ -883,18 +914,35 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         cfg.blockDim = dim3(320);
         cfg.dynamicSmemBytes = Cfg::kSmemBytes;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl_active() ? 2 : 1;
         WB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, BRES, EPI, NC>, ta, tb, tc, tc2, p));
     } else {
         const int tiles = p.num_m_tiles * p.num_n_tiles * (BRES ? 1 : p.ksplit);
         const int grid = tiles < usable ? tiles : usable;
-        gemm_tcgen05_kernel<BN, BRES, EPI, NC><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
+        if (pdl_active()) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(320);
+            cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            WB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, BRES, EPI, NC>, ta, tb, tc, tc2, p));
+        } else {
+            gemm_tcgen05_kernel<BN, BRES, EPI, NC><<<grid, 320, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tc2, p);
+        }
     }
     count_launch();
     WB_CHECK_LAUNCH();

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const float* __restrict__ x, long long ldx, int M, int d, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16,
                  long long ld_bf16, int split3, float* out_f32, long long ld_f32) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * LN_WARPS + warp;
     if (row >= M) return;
@@ -175,8 +177,8 @@ int layernorm_rows(const float* x, long long ldx, int M, int d, const float* gam
     ProfScope _ps(PT_LAYERNORM, stream, (double)M * d * (4.0 + (out_bf16 ? 2.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
 #define WB_LN(V)                                                                                          \
-    layernorm_kernel<V><<<grid, LN_WARPS * 32, 0, stream>>>(x, ldx, M, d, gamma, beta, eps, ob, ld_bf16, \
-                                                            split3, out_f32, ld_f32)
+    WB_CHECK_CUDA(launch_maybe_pdl(layernorm_kernel<V>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, x, ldx, M, d, gamma, beta, \
+                                   eps, ob, ld_bf16, split3, out_f32, ld_f32))
     switch (d / 128) {
         case 1: WB_LN(1); break;
         case 2: WB_LN(2); break;

@@ -1,4 +1,5 @@
 // Host-side runtime glue: last-error string, launch counter, TMA descriptor encoding.
+#include <stdlib.h>
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
@@ -10,6 +11,21 @@
 namespace wb {
 
 std::atomic<unsigned long long> g_launch_count{0};
+thread_local int g_pdl_depth = 0;
+bool pdl_stream_allowed() {
+    static const bool on = [] {
+        const char* e = getenv("WB_PDL_STREAM");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
+bool pdl_allowed() {
+    static const bool on = [] {
+        const char* e = getenv("WB_PDL");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
 
 static thread_local char g_err[1024] = {0};
 

@@ -161,6 +161,7 @@ int encoder_forward_chunk_batch(const Model* m, const float* xs, int T, int S, c
                "forward_chunk_batch: sessions >= 1 and exactly one of offsets_host / offsets_dev");
     WB_REQUIRE(cache_t1 == 0 || att_cache, WB_ERR_BAD_ARG, "forward_chunk_batch: att_cache missing");
     const int d = c.d_model, ff = c.ffn_dim, H = c.heads, L = c.enc_layers;
+    PdlScope pdl_scope(pdl_stream_allowed());
     SbPlan P;
     sb_plan(m, T, cache_t1, S, &P);
     WB_REQUIRE(P.chunk > 0, WB_ERR_BAD_ARG, "forward_chunk_batch: %d input frames give no output frame", T);
