@@ -277,6 +277,10 @@ int wb_encoder_forward(const wb_model* mm, const float* feats_dev, int64_t feats
     WB_REQUIRE(decoding_chunk_size != 0, WB_ERR_UNSUPPORTED,
                "decoding_chunk_size == 0 selects the random training chunk (mask.py:167-180); not an inference mode");
     cudaStream_t st = (cudaStream_t)stream;
+    // (the offline batch path keeps several batches in flight on separate streams, which already fills launch gaps; PDL here
+    //  is an experiment switch, WB_PDL_OFFLINE=1)
+    static const bool pdl_offline = [] { const char* e = getenv("WB_PDL_OFFLINE"); return e != nullptr && atoi(e) != 0; }();
+    PdlScope pdl_scope(pdl_offline);
     const wb_model_config& c = m->cfg;
     const int d = c.d_model, ff = c.ffn_dim, H = c.heads;
     EncPlan P;
