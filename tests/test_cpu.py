@@ -30,6 +30,38 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.wb_version()
 
 
+def test_c_abi_rejects_bad_arguments_with_status_and_message():
+    """Every compute entry point validates its handle / pointers before touching CUDA: a negative wb_status and a
+    wb_last_error() message, never a crash (include/wenet_b200.h: error convention).  No GPU is needed for this."""
+    import ctypes as C
+    from wenet_b200 import _lib
+    lib = _lib.load()
+    NOT_LOADED, BAD_ARG = -4, -1
+    null = None
+    steps = C.c_int32(0)
+    calls = {
+        "wb_attention_beam_search": (NOT_LOADED, [null, null, 0, null, null, 1, 10, null, 1, 0, 8, 0.0, null, 8, null, null,
+                                                  C.byref(steps), null, 0, null]),
+        "wb_whisper_encoder_forward": (NOT_LOADED, [null, null, 0, null, 1, 3000, null, null, null, null, null, 0, null]),
+        "wb_encoder_forward_chunk_batch": (NOT_LOADED, [null, null, 67, 2, null, 64, null, 0, null, null, null, null, None, None,
+                                                        null, 0, null]),
+        "wb_encoder_forward_chunk_batch_static": (NOT_LOADED, [null, null, 67, 2, null, 64, null, 0, null, null, null, null, null,
+                                                               0, null]),
+        "wb_logmel_forward": (BAD_ARG, [null, null, 0, null, 1, null, 0, 0, null, null]),
+    }
+    for name, (want, args) in calls.items():
+        rc = getattr(lib, name)(*args)
+        assert rc == want, (name, rc)
+        msg = lib.wb_last_error().decode()
+        assert msg and name.replace("wb_", "").replace("encoder_forward_chunk", "forward_chunk").split(":")[0] in msg, (name, msg)
+    out = C.c_void_p()
+    assert lib.wb_logmel_create(C.byref(out), 400, 160, 128, null, null) == BAD_ARG
+    # the size queries answer 0 for a null handle instead of dereferencing it
+    assert lib.wb_attention_beam_workspace_bytes(null, 100, 1, 10, 8) == 0
+    assert lib.wb_encoder_chunk_batch_workspace_bytes(null, 67, 0, 2) == 0
+    assert lib.wb_whisper_encoder_workspace_bytes(null, 1, null, 3000) == 0
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly, never route to the oracle."""
     if torch.cuda.is_available():

@@ -435,6 +435,12 @@ int attention_beam_search(const Model* m, const void* enc_bf16, long long enc_ro
     int pos = 0;
     std::vector<int> ended_host(batch, 0);
     int steps = 0;
+    // the self-attention step kernel keeps one score + one slot per past position and warp in shared memory
+    constexpr size_t kSaSmemMax = 200 * 1024;
+    WB_REQUIRE((size_t)SA_WARPS * 2 * max_len * sizeof(float) <= kSaSmemMax, WB_ERR_UNSUPPORTED,
+               "attention_beam_search: max_len %d exceeds the %zu positions the self-attention step kernel holds", max_len,
+               kSaSmemMax / (SA_WARPS * 2 * sizeof(float)));
+    WB_SET_MAX_DYN_SMEM(dec_self_attn_step_kernel, kSaSmemMax);
     PdlScope pdl_scope;   // the step loop is a chain of short dependent launches: GEMMs start ahead of their predecessor's end
     // token positions 0 .. max_len - 2 are consumed; the step at position `pos` produces the token of position pos + 1
     for (pos = 0; pos + 1 < max_len; ++pos) {
