@@ -25,6 +25,35 @@ def test_prefix_beam_search_kat():
     assert O.ctc_greedy_search(probs, torch.tensor([3])) == [[1, 1]]
 
 
+@needs_ref
+def test_prefix_beam_search_random_posteriors_vs_reference():
+    """search.py:127-249 on 40 random posterior matrices (peaky and flat, blank-heavy, repeated frames, beams up to the vocabulary size):
+    n-best token lists, fp64 scores and times of the oracle equal the reference's, element for element."""
+    shim.install()
+    from wenet.models.transformer.search import ctc_greedy_search, ctc_prefix_beam_search
+    g = torch.Generator().manual_seed(2024)
+    for case in range(40):
+        B = 1 + case % 3
+        T = int(torch.randint(1, 48, (1,), generator=g))
+        V = int(torch.randint(3, 14, (1,), generator=g))
+        beam = min(int(torch.randint(1, 8, (1,), generator=g)), V)   # the reference's topk(beam) needs beam <= V
+        sharp = [0.5, 2.0, 6.0][case % 3]
+        logits = torch.randn(B, T, V, generator=g) * sharp
+        logits[..., 0] += [0.0, 1.5, 3.0][(case // 3) % 3]          # blank-heavy cases
+        if case % 4 == 0:                                            # runs of the same token
+            logits = logits.repeat_interleave(2, dim=1)[:, :T]
+        lp = logits.log_softmax(-1)
+        lens = torch.randint(1, T + 1, (B,), generator=g)
+        lens[0] = T
+        ref = ctc_prefix_beam_search(lp, lens, beam)
+        got = O.ctc_prefix_beam_search(lp, lens, beam)
+        for r, o in zip(ref, got):
+            assert [list(x) for x in r.nbest] == o["nbest"], case
+            assert r.nbest_scores == o["nbest_scores"], case
+            assert [list(x) for x in r.nbest_times] == o["nbest_times"], case
+        assert [r.tokens for r in ctc_greedy_search(lp, lens)] == O.ctc_greedy_search(lp, lens), case
+
+
 def test_fbank_vs_torchaudio():
     import torchaudio.compliance.kaldi as kaldi
     g = torch.Generator().manual_seed(3)
