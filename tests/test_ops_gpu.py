@@ -366,6 +366,49 @@ def test_logsoftmax_topk_greedy_and_prefix_beam():
             assert abs(float(pscores[b, r]) - ref_b[b]["nbest_scores"][r]) < 1e-9 * max(1.0, abs(ref_b[b]["nbest_scores"][r]))
 
 
+def test_prefix_beam_random_posteriors_gpu():
+    """The 40 random posterior matrices on which the oracle is pinned to the reference (tests/test_oracle_pin.py:
+    peaky / flat / blank-heavy / repeated frames, ragged lengths, beams up to the vocabulary size) through the CUDA
+    kernels: greedy ids, n-best ids and times exact, scores to 1e-9."""
+    import ops
+    g = torch.Generator().manual_seed(2024)
+    tI = lambda t: torch.tensor(t, dtype=torch.int32, device=_dev())
+    for case in range(40):
+        B = 1 + case % 3
+        T = int(torch.randint(1, 48, (1,), generator=g))
+        V = int(torch.randint(3, 14, (1,), generator=g))
+        beam = min(int(torch.randint(1, 8, (1,), generator=g)), V)
+        sharp = [0.5, 2.0, 6.0][case % 3]
+        logits = torch.randn(B, T, V, generator=g) * sharp
+        logits[..., 0] += [0.0, 1.5, 3.0][(case // 3) % 3]
+        if case % 4 == 0:
+            logits = logits.repeat_interleave(2, dim=1)[:, :T]
+        lp = logits.log_softmax(-1)
+        lens = torch.randint(1, T + 1, (B,), generator=g)
+        lens[0] = T
+        ref_b = O.ctc_prefix_beam_search(lp, lens, beam)
+        ref_g = O.ctc_greedy_search(lp, lens)
+        # packed rows, as the library takes them
+        starts = [0]
+        for n in lens.tolist()[:-1]:
+            starts.append(starts[-1] + n)
+        rows = torch.cat([lp[b, :int(lens[b])] for b in range(B)], 0)
+        tv, ti = rows.topk(beam, dim=-1)
+        tvd, tid = tv.to(_dev()).contiguous(), ti.to(torch.int32).to(_dev()).contiguous()
+        gt, gl = ops.ctc_greedy_search(tid, tI(starts), tI(lens.tolist()))
+        toks, times, plens, scores, nhyp = ops.ctc_prefix_beam_search(tvd, tid, tI(starts), tI(lens.tolist()), beam)
+        for b in range(B):
+            assert gt[b, :int(gl[b])].cpu().tolist() == ref_g[b], case
+            n = int(nhyp[b])
+            assert n == len(ref_b[b]["nbest"]), case
+            for r in range(n):
+                ln = int(plens[b, r])
+                assert toks[b, r, :ln].cpu().tolist() == ref_b[b]["nbest"][r], (case, b, r)
+                assert times[b, r, :ln].cpu().tolist() == ref_b[b]["nbest_times"][r], (case, b, r)
+                want = ref_b[b]["nbest_scores"][r]
+                assert abs(float(scores[b, r]) - want) < 1e-9 * max(1.0, abs(want)), (case, b, r)
+
+
 def test_prefix_beam_kat_gpu():
     """runtime/core/test/ctc_prefix_beam_search_test.cc:29-72 through the CUDA kernel."""
     import ops
