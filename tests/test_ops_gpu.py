@@ -452,6 +452,42 @@ def test_fbank():
         assert (out_i[b, m:] == 0).all()
 
 
+def test_fbank_edge_inputs():
+    """Digital silence (the log floor), a large DC offset under a small signal (remove_dc_offset), full-scale int16 and an
+    all-maximum row, in one ragged batch: against the oracle, which tests/test_oracle_pin.py pins to torchaudio on the same
+    kinds of input."""
+    from wenet_b200.fbank import FbankExtractor
+    g = torch.Generator().manual_seed(11)
+    n = 8000
+    rows = [torch.zeros(n),
+            torch.randn(n, generator=g) * 50 + 12000,
+            torch.where(torch.rand(n, generator=g) > 0.5, 32767.0, -32768.0),
+            torch.full((n,), 32767.0)]
+    ns = [n, n - 1, n - 160, 4000]
+    pcm_i = torch.zeros(len(rows), n, dtype=torch.int16)
+    for b, (r, k) in enumerate(zip(rows, ns)):
+        pcm_i[b, :k] = r[:k].round().clamp(-32768, 32767).to(torch.int16)
+    ex = FbankExtractor(80)
+    nsd = torch.tensor(ns, dtype=torch.int32, device=_dev())
+    out = ex(pcm_i.to(_dev()), nsd)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    worst = []
+    for b, k in enumerate(ns):
+        ref = O.fbank(pcm_i[b, :k].float())
+        m = ref.shape[0]
+        assert ex.num_frames(k) == m
+        worst.append((out[b, :m].cpu() - ref).abs().max().item())
+        assert (out[b, m:] == 0).all()
+    print("fbank edge inputs, max |gpu - oracle| per row (silence, dc, full scale, constant):", worst)
+    assert worst[0] == 0.0                      # silence: every bin is log(FLT_EPSILON) on both sides
+    assert worst[1] < 1e-2 and worst[2] < 1e-3
+    # row 3 is pure DC: after remove_dc_offset what is left is the rounding of the frame mean (exactly zero in the oracle),
+    # so only the floor and finiteness are pinned there
+    floor = math.log(torch.finfo(torch.float32).eps)
+    assert (out[3, :ex.num_frames(ns[3])] >= floor - 1e-3).all() and (out[3, :ex.num_frames(ns[3])] < 0).all()
+
+
 @pytest.mark.parametrize("V,k", [(4233, 10), (37, 5), (5538, 1), (300, 64)])
 def test_lse_topk_without_writeback(V, k):
     """wb_ctc_topk's kernel mode (no normalised matrix written): same top-k as the write-back mode and as torch,

@@ -65,6 +65,39 @@ def test_fbank_vs_torchaudio():
     assert (got - ref).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("kind", ["one_frame", "just_short_of_two", "silence", "dc_offset", "full_scale", "mel23"])
+def test_fbank_edge_cases_vs_torchaudio(kind):
+    """kaldi.py:514-645 on the inputs where a restatement goes wrong first: exactly one frame, one sample short of the
+    second frame (snip_edges), digital silence (the log floor), a DC offset (remove_dc_offset), full-scale int16, and a
+    different filterbank size."""
+    import torchaudio.compliance.kaldi as kaldi
+    g = torch.Generator().manual_seed(11)
+    mel = 23 if kind == "mel23" else 80
+    if kind == "one_frame":
+        wav = torch.randn(1, 400, generator=g) * 2000
+    elif kind == "just_short_of_two":
+        wav = torch.randn(1, 559, generator=g) * 2000
+    elif kind == "silence":
+        wav = torch.zeros(1, 4000)
+    elif kind == "dc_offset":
+        wav = torch.randn(1, 8000, generator=g) * 50 + 12000
+    elif kind == "full_scale":
+        wav = torch.where(torch.rand(1, 8000, generator=g) > 0.5, 32767.0, -32768.0)
+    else:
+        wav = torch.randn(1, 16000, generator=g) * 3000
+    wav = wav.round()
+    ref = kaldi.fbank(wav, num_mel_bins=mel, frame_length=25, frame_shift=10, dither=0.0, energy_floor=0.0,
+                      sample_frequency=16000)
+    got = O.fbank(wav[0], num_mel_bins=mel)
+    assert got.shape == ref.shape and ref.shape[0] == 1 + (wav.shape[1] - 400) // 160
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 2e-4, (got - ref).abs().max().item()
+    # shorter than one window: torchaudio refuses the input (kaldi.py:142 assert); the restatement yields zero frames
+    assert O.fbank(wav[0, :399], num_mel_bins=mel).shape[0] == 0
+    with pytest.raises(AssertionError):
+        kaldi.fbank(wav[:, :399], num_mel_bins=mel, dither=0.0, energy_floor=0.0)
+
+
 def _tiny_cfg(bidir=True, causal=True, norm="layer_norm", kernel=8):
     return {
         "input_dim": 80, "output_dim": 37, "cmvn": None,
