@@ -185,6 +185,73 @@ def test_oracle_matches_reference(variant):
 
 
 @needs_ref
+@pytest.mark.parametrize("chunk,left", [(1, 0), (1, -1), (3, 1), (8, -1), (16, 4), (32, 0)])
+def test_oracle_chunk_masks_and_streaming_vs_reference(chunk, left):
+    """add_optional_chunk_mask (mask.py:162-227) and forward_chunk_by_chunk (encoder.py:302-362) for chunk / left-chunk
+    settings from the degenerate (1 frame, no history) to wider than the utterance: the masked full forward and the chunk
+    loop of the oracle equal the reference's, and (with limited history only when left >= 0) each other's cache semantics."""
+    torch.manual_seed(777)
+    cfg = _tiny_cfg(bidir=True)
+    cfg["encoder_conf"]["use_dynamic_chunk"] = True
+    cfg["encoder_conf"]["use_dynamic_left_chunk"] = False
+    model = shim.init_reference_model(cfg)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ecfg = O.encoder_cfg(p, heads=2, causal=True, cnn_norm="layer_norm")
+    xs = torch.randn(2, 99, 80)
+    lens = torch.tensor([99, 58])
+    with torch.no_grad():
+        r, rm = model.encoder(xs, lens, decoding_chunk_size=chunk, num_decoding_left_chunks=left)
+        o, om = O.encoder_forward(p, ecfg, xs, lens, chunk, left)
+        assert torch.equal(rm, om)
+        for b in range(2):
+            n = int(rm[b].sum())
+            assert (r[b, :n] - o[b, :n]).abs().max().item() < 2e-5, (chunk, left, b)
+        # the streaming loop over one utterance (batch 1 by construction, encoder.py:330-333)
+        rs, _ = model.encoder.forward_chunk_by_chunk(xs[:1], chunk, left)
+        win, stride = (chunk - 1) * 4 + 7, 4 * chunk
+        att = cnn = torch.zeros(0, 0, 0, 0)
+        off, outs = 0, []
+        req = chunk * left if left >= 0 else -1
+        for cur in range(0, 99 - 7 + 1, stride):
+            y, att, cnn = O.encoder_forward_chunk(p, ecfg, xs[:1, cur:min(cur + win, 99)], off, req, att, cnn)
+            outs.append(y)
+            off += y.size(1)
+        os_ = torch.cat(outs, 1)
+        assert os_.shape == rs.shape
+        assert (os_ - rs).abs().max().item() < 2e-5, (chunk, left)
+        # and the chunk loop reproduces the chunk-masked full forward (same attention context by construction)
+        assert (rs[0] - r[0, :rs.size(1)]).abs().max().item() < 1e-4
+
+
+@needs_ref
+@pytest.mark.parametrize("ctc_weight,reverse_weight", [(0.0, 0.0), (0.5, 0.0), (0.3, 0.3), (1.0, 0.5), (0.0, 1.0)])
+def test_oracle_rescoring_weights_vs_reference(ctc_weight, reverse_weight):
+    """attention_rescoring (search.py:374-458) over the weight settings that change which terms count: decoder only,
+    CTC-weighted, bidirectional mix, right-to-left only; n-best lists with empty, single-token and equal-length hypotheses."""
+    shim.install()
+    from wenet.models.transformer.search import DecodeResult, attention_rescoring
+    torch.manual_seed(3)
+    cfg = _tiny_cfg(bidir=True)
+    model = shim.init_reference_model(cfg)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    enc = torch.randn(3, 17, 128)
+    lens = torch.tensor([17, 9, 4])
+    nbest = [[[5, 7, 7, 30], [5, 7], [], [36]], [[2, 3, 4], [4, 3, 2]], [[11]]]
+    scores = [[-1.5, -2.25, -9.0, -3.0], [-0.5, -0.5], [-0.1]]
+    ref_in = [DecodeResult(tokens=n[0], nbest=[tuple(h) for h in n], nbest_scores=sc, nbest_times=[[0] * len(h) for h in n])
+              for n, sc in zip(nbest, scores)]
+    got_in = [dict(nbest=n, nbest_scores=sc) for n, sc in zip(nbest, scores)]
+    with torch.no_grad():
+        ref = attention_rescoring(model, ref_in, enc, lens, ctc_weight, reverse_weight)
+        dcfg = dict(bidirectional=True, layers=2, r_layers=1, heads=2)
+        got = O.attention_rescoring(p, dcfg, got_in, enc, lens, model.sos_symbol(), model.eos_symbol(), ctc_weight,
+                                    reverse_weight)
+    for r, g in zip(ref, got):
+        assert list(r.tokens) == g["tokens"]
+        assert abs(r.score - g["best_score"]) < 1e-4
+
+
+@needs_ref
 def test_plugin_config_reconstruction_and_registry():
     """wenet_b200.plugin: the train.yaml subset is recovered from a constructed reference model, and
     install() rebinds the reference's registries."""
