@@ -561,7 +561,9 @@ def main():
         ach = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         traffic, traffic_of = None, None
         try:   # DRAM bytes per launch of the family's largest member, from the committed `ncu --set full` capture
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_traffic.json")) as f:
+            pdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+            tfile = os.path.join(pdir, "r2_gemm_traffic.json")
+            with open(tfile if os.path.exists(tfile) else os.path.join(pdir, "r1_gemm_traffic.json")) as f:
                 tj = json.load(f)
             traffic, traffic_of = tj["traffic_bytes_per_launch"], tj["kernel"]
         except (OSError, KeyError, ValueError):
