@@ -568,7 +568,7 @@ def main():
             traffic, traffic_of = tj["traffic_bytes_per_launch"], tj["kernel"]
         except (OSError, KeyError, ValueError):
             pass
-        line["roofline"] = {"kernel": "tcgen05 GEMM family: gemm_tcgen05_kernel (Linear / pointwise-conv / implicit-GEMM conv2)",
+        line["roofline"] = {"kernel": "tcgen05 GEMM family: gemm_tcgen05_kernel + gemm_act16_kernel (Linear / pointwise-conv / implicit-GEMM conv2)",
                             "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                             "frac": ach / peaks["tf_sust"], "traffic": traffic, "traffic_of": traffic_of,
                             "peak_source": peaks["src"] + " (sustained bf16)",
