@@ -406,9 +406,10 @@ def test_whisper_oracle_matches_reference():
     from wenet.models.transformer.search import attention_beam_search
     from wenet_b200.whisper import whisper_prefix
     infos = {"tasks": ["transcribe", "transcribe", "translate"], "langs": ["en", "zh", "en"]}
-    with torch.no_grad():
-        ref = attention_beam_search(model, r_out, r_mask, 4, 0.0, infos)
-        prefix = whisper_prefix(cfg["tokenizer_conf"]["special_tokens"], infos["tasks"], infos["langs"])
-        got = O.attention_beam_search(p, "decoder", 2, 2, r_out, r_mask, 4, prefix.tolist(), model.eos, 0.0, "whisper")
-    assert [list(r.tokens) for r in ref] == got
-    assert sum(len(g) for g in got) > 0
+    prefix = whisper_prefix(cfg["tokenizer_conf"]["special_tokens"], infos["tasks"], infos["langs"])
+    for beam, lp in ((4, 0.0), (1, 0.0), (6, 0.8)):      # beam 1 = greedy over the beam machinery; a length penalty
+        with torch.no_grad():
+            ref = attention_beam_search(model, r_out, r_mask, beam, lp, infos)
+            got = O.attention_beam_search(p, "decoder", 2, 2, r_out, r_mask, beam, prefix.tolist(), model.eos, lp, "whisper")
+        assert [list(r.tokens) for r in ref] == got, (beam, lp)
+        assert sum(len(g) for g in got) > 0
