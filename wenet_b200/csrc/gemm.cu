@@ -908,8 +908,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         // one CTA pair (cluster of two, same TPC) per two SMs; the schedule walks pairs of 128-row tiles
         const int tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
         const int pairs = tiles < usable / 2 ? tiles : (usable / 2 > 0 ? usable / 2 : 1);
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
         cfg.blockDim = dim3(320);
         cfg.dynamicSmemBytes = Cfg::kSmemBytes;
@@ -928,8 +927,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         const int tiles = p.num_m_tiles * p.num_n_tiles * (BRES ? 1 : p.ksplit);
         const int grid = tiles < usable ? tiles : usable;
         if (pdl_active()) {
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
+            cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
             cfg.blockDim = dim3(320);
             cfg.dynamicSmemBytes = Cfg::kSmemBytes;
