@@ -84,6 +84,22 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert d["metric"] == json.load(f)["metric"]
 
 
+def test_bench_reference_arm_under_torchrun_two_ranks():
+    """The driver launches the reference arm exactly like the GPU arm: under torchrun for N > 1.  Rank 0 alone runs and
+    prints the line, the other rank exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly, never route to the oracle."""
     if torch.cuda.is_available():
