@@ -5,7 +5,10 @@ product package `wenet_b200/` (which has no CPU path at all).
 
 Pinned (tests/test_oracle_pin.py, run in the build container where /root/reference exists, and
 through the committed goldens elsewhere):
-  * fbank            == torchaudio.compliance.kaldi.fbank via wenet/dataset/processor.py:226-256
+  * fbank            == torchaudio.compliance.kaldi.fbank via wenet/dataset/processor.py:226-256, AND the
+    reference's own C++ front-end (runtime/core/frontend/fbank.h + fft.cc compiled into oracle/_ref/fbank_ref by
+    oracle/Makefile) in the runtime's Kaldi configuration
+  * slaney_mel_filters == the reference's C++ slaney filterbank (fbank.h:91-150, 176-218) through the same binary
   * encoder / ctc / decoder == the reference modules loaded with the same state_dict (fp32)
   * ctc_prefix_beam_search  == the reference's Python search AND the C++ known-answer test
     runtime/core/test/ctc_prefix_beam_search_test.cc:29-72
@@ -564,9 +567,13 @@ def attention_rescoring(p, dcfg, beam_results, encoder_outs, encoder_lens, sos, 
 # =============================================================================================
 def slaney_mel_filters(sr: int = 16000, n_fft: int = 400, n_mels: int = 128) -> torch.Tensor:
     """librosa.filters.mel(sr, n_fft, n_mels) (slaney scale, slaney norm) restated from its published algorithm; the
-    reference calls it at processor.py:360-361.  PARITY UNPINNED for this one function: librosa is not installed in the
-    build container, so only its call site is pinned (tests/test_oracle_pin.py injects this restatement as
-    librosa.filters.mel and compares everything around it with the reference's own compute_log_mel_spectrogram)."""
+    reference calls it at processor.py:360-361.  librosa is not installed in the build container, so the pin is the
+    REFERENCE'S OWN C++ implementation of the same filterbank (runtime/core/frontend/fbank.h:91-150 InitMelFilters with
+    MelType::kSlaney, :176-218 MelScale / InverseMelScale), compiled from the reference sources into oracle/_ref/fbank_ref:
+    same support and weights to fp32 rounding for 128 and 80 bins on the C++ front-end's 512-point grid
+    (tests/test_oracle_pin.py::test_slaney_mel_filters_vs_reference_cxx; n_fft enters this function only through the
+    bin-frequency grid `fft`).  The Python call site is pinned with this restatement injected as librosa.filters.mel
+    (test_whisper_oracle_matches_reference compares everything around it with compute_log_mel_spectrogram)."""
     def hz_to_mel(f):
         f_sp, min_log_hz = 200.0 / 3, 1000.0
         if f >= min_log_hz:

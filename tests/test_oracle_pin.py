@@ -13,6 +13,83 @@ from oracle import wenet_oracle as O
 needs_ref = pytest.mark.skipif(not shim.have_reference(), reason="/root/reference not present (GPU box)")
 
 
+def _fbank_ref():
+    """oracle/_ref/fbank_ref: the reference's C++ front-end (runtime/core/frontend/fbank.h + fft.cc) behind the driver
+    oracle/cxx/fbank_ref_main.cc; built here when /root/reference is present, prebuilt on the GPU box."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "fbank_ref")
+    if os.path.isdir("/root/reference/runtime/core/frontend"):
+        r = subprocess.run(["make", "-C", os.path.dirname(os.path.dirname(exe))], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/fbank_ref not built (no /root/reference here)")
+
+    def run(*args):
+        r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        return r.stdout
+    return run
+
+
+def _ref_filters(run, mel, bins, low):
+    W = torch.zeros(bins, 256)
+    for line in run("filters", mel, bins, 16000, 400, low).splitlines():
+        p = line.split()
+        b, first, n = int(p[0]), int(p[1]), int(p[2])
+        W[b, first:first + n] = torch.tensor([float(x) for x in p[3:3 + n]])
+    return W
+
+
+@pytest.mark.parametrize("bins", [128, 80])
+def test_slaney_mel_filters_vs_reference_cxx(bins):
+    """The slaney filterbank (the one function the Python reference takes from librosa, which is not installed): the
+    oracle's restatement against the REFERENCE'S OWN C++ implementation, runtime/core/frontend/fbank.h:91-150 (InitMelFilters,
+    MelType::kSlaney) with :176-218 (MelScale / InverseMelScale), compiled from the reference sources.  The C++ front-end
+    works on a 512-point FFT grid (UpperPowerOfTwo(400)); the frequency grid is the only place n_fft enters the restatement,
+    so it is evaluated at n_fft = 512: same support, weights equal to fp32 rounding."""
+    run = _fbank_ref()
+    W = _ref_filters(run, "slaney", bins, 0)
+    mine = O.slaney_mel_filters(16000, 512, bins)[:, :256]
+    assert torch.equal(W > 0, mine > 0)
+    assert (W - mine).abs().max().item() < 1e-5 * mine.max().item()
+    # the scale functions themselves, below and above the 1 kHz knee
+    fs = [0.0, 20.0, 333.3, 999.9, 1000.0, 1000.1, 2500.0, 7999.0, 8000.0]
+    f_sp, knee, step = 200.0 / 3, 1000.0, math.log(6.4) / 27.0
+    for line, f in zip(run("melscale", "slaney", *fs).splitlines(), fs):
+        _, mel, inv = (float(x) for x in line.split())
+        want = knee / f_sp + math.log(f / knee) / step if f >= knee else f / f_sp
+        assert abs(mel - want) < 1e-5 * max(1.0, want) and abs(inv - f) < 1e-5 * max(1.0, f)
+
+
+def test_fbank_vs_reference_cxx(tmp_path):
+    """Kaldi fbank: the oracle (pinned to torchaudio above) against the reference's own C++ front-end in the runtime's
+    configuration (feature_pipeline.h:55-63 -> fbank.h:247-326: povey window, HTK mel from 20 Hz, pre-emphasis, DC removal,
+    natural log with an FLT_EPSILON floor) on 2 s of noise; and the C++ Whisper configuration (feature_pipeline.h:64-73:
+    hanning, slaney, log10, max - 8 clamp, (x + 4) / 4) against a per-frame restatement that uses the oracle's slaney
+    filterbank.  (The Python Whisper front-end frames differently - centred STFT of size 400 - and is pinned separately.)"""
+    import numpy as np
+    run = _fbank_ref()
+    g = torch.Generator().manual_seed(3)
+    wav = (torch.randn(16000 * 2 + 123, generator=g) * 3000).clamp(-32767, 32767).round()
+    path = tmp_path / "pcm.f32"
+    path.write_bytes(wav.numpy().astype("<f4").tobytes())
+    ref = torch.tensor([[float(x) for x in l.split()] for l in run("fbank", "kaldi", 80, path).splitlines()])
+    got = O.fbank(wav)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 1e-3 and (got - ref).abs().mean().item() < 5e-5
+    refw = torch.tensor([[float(x) for x in l.split()] for l in run("fbank", "whisper", 128, path).splitlines()])
+    m = 1 + (wav.numel() - 400) // 160
+    frames = (wav / 32768.0).as_strided((m, 400), (160, 1)).clone()
+    frames = frames - frames.mean(1, keepdim=True)                     # fbank.h:281-286 (remove_dc_offset stays on)
+    x = torch.zeros(m, 512, dtype=torch.float64)
+    x[:, :400] = (frames * torch.hann_window(400, periodic=True)).double()
+    power = torch.fft.rfft(x, dim=1).abs() ** 2
+    mel = power[:, :256].float() @ O.slaney_mel_filters(16000, 512, 128)[:, :256].T
+    lg = torch.clamp(mel, min=1e-10).log10()
+    lg = (torch.maximum(lg, lg.max() - 8.0) + 4.0) / 4.0
+    assert refw.shape == lg.shape and (refw - lg).abs().max().item() < 1e-4
+
+
 def test_prefix_beam_search_kat():
     """runtime/core/test/ctc_prefix_beam_search_test.cc:29-72 (the reference's only golden vector on this path)."""
     probs = torch.tensor([[0.25, 0.40, 0.35], [0.40, 0.35, 0.25], [0.10, 0.50, 0.40]]).log().unsqueeze(0)
