@@ -10,8 +10,10 @@ through the committed goldens elsewhere):
     oracle/Makefile) in the runtime's Kaldi configuration
   * slaney_mel_filters == the reference's C++ slaney filterbank (fbank.h:91-150, 176-218) through the same binary
   * encoder / ctc / decoder == the reference modules loaded with the same state_dict (fp32)
-  * ctc_prefix_beam_search  == the reference's Python search AND the C++ known-answer test
-    runtime/core/test/ctc_prefix_beam_search_test.cc:29-72
+  * ctc_prefix_beam_search  == the reference's Python search (incl. 40 random posterior matrices) AND the C++ known-answer
+    test runtime/core/test/ctc_prefix_beam_search_test.cc:29-72; the reference's C++ search itself, compiled into
+    oracle/_ref/ctc_search_ref, reproduces that KAT and agrees on the best hypothesis everywhere (its deeper n-best differs
+    from the reference's Python search, which is the parity target)
   * attention_rescoring     == reference search.py:374-458
 
 Every function cites the reference lines it restates.  Parameters are a flat dict keyed by the
