@@ -452,6 +452,38 @@ def test_fbank():
         assert (out_i[b, m:] == 0).all()
 
 
+def test_fbank_kernel_vs_reference_cxx(tmp_path):
+    """The CUDA fbank against the REFERENCE'S OWN compiled C++ front-end (oracle/_ref/fbank_ref = runtime/core/frontend/fbank.h
+    + fft.cc built by oracle/Makefile; Kaldi configuration of feature_pipeline.h:55-63) on 2 s of noise - the product against
+    the real reference, not only against the restatement.  Gate as for torchaudio (two fp32 FFT front-ends): 2e-3."""
+    import os
+    import subprocess
+    from wenet_b200.fbank import FbankExtractor
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "fbank_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/fbank_ref not built")
+    g = torch.Generator().manual_seed(3)
+    n = 16000 * 2 + 123
+    wav = (torch.randn(n, generator=g) * 3000).clamp(-32767, 32767).round()
+    path = tmp_path / "pcm.f32"
+    path.write_bytes(wav.numpy().astype("<f4").tobytes())
+    r = subprocess.run([exe, "fbank", "kaldi", "80", str(path)], capture_output=True, text=True, timeout=120)
+    if r.returncode != 0:
+        pytest.skip("oracle/_ref/fbank_ref does not run here: %s" % r.stderr[:200])
+    ref = torch.tensor([[float(x) for x in l.split()] for l in r.stdout.splitlines()])
+    ex = FbankExtractor(80)
+    N = (n + 3) // 4 * 4
+    pcm = torch.zeros(1, N, dtype=torch.int16)
+    pcm[0, :n] = wav.to(torch.int16)
+    out = ex(pcm.to(_dev()), torch.tensor([n], dtype=torch.int32, device=_dev()))
+    torch.cuda.synchronize()
+    m = ref.shape[0]
+    assert ex.num_frames(n) == m
+    d = (out[0, :m].cpu() - ref).abs()
+    print("fbank kernel vs reference C++ front-end: max %.3g mean %.3g" % (d.max().item(), d.mean().item()))
+    assert d.max().item() < 2e-3 and d.mean().item() < 1e-4
+
+
 def test_fbank_edge_inputs():
     """Digital silence (the log floor), a large DC offset under a small signal (remove_dc_offset), full-scale int16 and an
     all-maximum row, in one ragged batch: against the oracle, which tests/test_oracle_pin.py pins to torchaudio on the same
